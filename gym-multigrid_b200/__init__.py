@@ -1,0 +1,43 @@
+"""gym-multigrid_b200: B200-native batched gridworld simulator for the hot path of
+Tran-Research-Group/gym-multigrid (MultiGridEnv.step + Grid.encode), behind the reference's
+gymnasium surface.
+
+    import gym_multigrid_b200 as mg
+    envs = mg.make_vec("multigrid-collect-respawn-clustered-v0", num_envs=65536, device="cuda:0")
+    obs, info = envs.reset()
+    obs, rewards, terminated, truncated, info = envs.step(actions)      # CUDA tensors, no host sync
+
+    env = mg.make("multigrid-collect-respawn-clustered-v0")              # reference-style single env
+
+The compute path is hand-written CUDA for sm_100a behind the C ABI in include/multigrid_b200.h;
+there is no CPU fallback (construction raises when the library or a B200 is missing).
+"""
+from .registration import registry, register, spec  # noqa: F401
+from .registration import COLLECT_CLASSES as _COLLECT_CLASSES
+
+__version__ = "0.1.0"
+
+
+def _collect_kwargs(s, overrides):
+    cls = s.entry_point.split(":")[-1]
+    if cls not in _COLLECT_CLASSES:
+        raise NotImplementedError(f"entry point {s.entry_point!r} has no CUDA implementation")
+    layout, fixed = _COLLECT_CLASSES[cls]
+    kw = dict(s.kwargs)
+    kw.update(layout=layout, fixed_horizon=fixed, max_episode_steps=s.max_episode_steps)
+    kw.update(overrides)
+    return kw
+
+
+def make_vec(env_id: str, num_envs: int, device="cuda:0", seed: int = 0, autoreset: bool = True, **overrides):
+    """gymnasium.vector-style constructor keyed by the reference's env ids (gym_multigrid/__init__.py:6-147)."""
+    from .vector_env import CollectVecEnv
+    kw = _collect_kwargs(spec(env_id), overrides)
+    return CollectVecEnv(num_envs, device=device, seed=seed, autoreset=autoreset, **kw)
+
+
+def make(env_id: str, device="cuda:0", seed: int = 0, **overrides):
+    """gymnasium.make-style constructor: one env with the reference's reset/step signatures."""
+    from .vector_env import CollectEnv
+    kw = _collect_kwargs(spec(env_id), overrides)
+    return CollectEnv(device=device, seed=seed, **kw)

@@ -1,0 +1,93 @@
+"""ctypes binding of include/multigrid_b200.h (the C ABI of libmultigrid_b200.so).
+
+There is no CPU fallback: loading fails loudly when the library has not been built, and
+`mg_create` fails when no sm_100 CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from ._build import LIB_PATH
+
+MAX_AGENTS = 8
+MAX_BALL_TYPES = 8
+FAMILY_COLLECT = 0
+LAYOUTS = {"even_dist": 0, "quadrants": 1, "rooms": 2, "quadrants_respawn": 3}
+PLANE_GRID, PLANE_AGENT_POS, PLANE_HDR, PLANE_INFO = 0, 1, 2, 3
+ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
+
+EXPORTS = [
+    "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
+    "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
+    "mg_launch_count",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("family", C.c_int32), ("num_envs", C.c_int64), ("env_id_base", C.c_int64),
+        ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32), ("num_ball_types", C.c_int32),
+        ("agent_colour", C.c_int32 * MAX_AGENTS), ("ball_colour", C.c_int32 * MAX_BALL_TYPES),
+        ("ball_reward", C.c_double * MAX_BALL_TYPES), ("num_balls", C.c_int32), ("respawn", C.c_int32),
+        ("layout", C.c_int32), ("fixed_horizon", C.c_int32), ("max_steps", C.c_int32), ("time_limit", C.c_int32),
+        ("autoreset", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
+class StepIO(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("obs", C.c_void_p), ("rewards", C.c_void_p), ("terminated", C.c_void_p),
+                ("truncated", C.c_void_p), ("final_obs", C.c_void_p)]
+
+
+class Trace(C.Structure):
+    _fields_ = [("order", C.c_void_p), ("draws", C.c_void_p), ("n_draws", C.c_void_p), ("K", C.c_int32),
+                ("reset_draws", C.c_void_p), ("n_reset_draws", C.c_void_p), ("R", C.c_int32),
+                ("draws_used", C.c_void_p), ("reset_draws_used", C.c_void_p)]
+
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load libmultigrid_b200.so (built in-tree by __graft_entry__.build / _build.build_library)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  gym-multigrid_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mg_abi_version.restype = C.c_int
+    lib.mg_create.restype = C.c_int
+    lib.mg_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
+    lib.mg_destroy.argtypes = [C.c_void_p]
+    lib.mg_last_error.restype = C.c_char_p
+    lib.mg_last_error.argtypes = [C.c_void_p]
+    lib.mg_state_bytes.restype = C.c_size_t
+    lib.mg_state_bytes.argtypes = [C.c_void_p]
+    lib.mg_obs_bytes.restype = C.c_size_t
+    lib.mg_obs_bytes.argtypes = [C.c_void_p]
+    lib.mg_state_plane.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.mg_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mg_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_void_p]
+    lib.mg_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(StepIO), C.c_void_p]
+    lib.mg_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mg_set_trace.argtypes = [C.c_void_p, C.POINTER(Trace)]
+    lib.mg_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    lib.mg_launch_count.restype = C.c_int64
+    lib.mg_launch_count.argtypes = [C.c_void_p]
+    if lib.mg_abi_version() != 1:
+        raise RuntimeError("libmultigrid_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error(handle=None) -> str:
+    msg = load().mg_last_error(handle)
+    return msg.decode() if msg else ""

@@ -1,0 +1,179 @@
+// mg_device.cuh -- device-side building blocks shared by the sm_100a kernels:
+// packed cell codes, Philox4x32-10, the per-env random source (trace replay or Philox),
+// and the TMA (cp.async.bulk) / mbarrier PTX wrappers used to move env tiles.
+//
+// Reference citations are file:line under the gym-multigrid checkout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/multigrid_b200.h"
+
+namespace mg {
+
+// ---------------------------------------------------------------------------- cell codes
+// CollectWorld (core/world.py:54-64): empty 0, wall 1, ball 2, agent 3; colours
+// core/constants.py:8-19 (< 10); agent state = dir (< 4, core/agent.py:119-126).
+// One byte per cell: type | colour << 2 | state << 6; the empty cell is 0 = (0, 0, 0).
+constexpr int T_EMPTY = 0, T_WALL = 1, T_BALL = 2, T_AGENT = 3;
+__host__ __device__ constexpr uint8_t cell(int type, int colour, int state) {
+  return (uint8_t)(type | (colour << 2) | (state << 6));
+}
+constexpr uint8_t WALL_GREY = cell(T_WALL, 7, 0);  // Wall(world) colour "grey" (object.py:174-176)
+
+// ------------------------------------------------------------------------------- params
+struct CollectParams {
+  // geometry / rules
+  int W, H, cells, A, nb;
+  int num_balls, respawn, layout, fixed_horizon, max_steps, time_limit, autoreset;
+  uint8_t agent_code[MG_MAX_AGENTS];   // cell(T_AGENT, agents_index[i], dir = 3)
+  uint8_t ball_colour[MG_MAX_BALL_TYPES];
+  int8_t type_of_colour[16];
+  double reward_of_colour[16];
+  long long N;            // envs on this device
+  unsigned long long env_id_base, seed;
+  // state planes (caller-owned buffer)
+  uint8_t* grid;          // [N_pad][cells]
+  uint8_t* agent_pos;     // [N_pad][A][2]
+  int4* hdr;              // [N_pad] {step_count, collected, rng_ctr, episodes}
+  int32_t* info;          // [N_pad][A*nb]
+  // io
+  const int8_t* actions;
+  uint8_t* obs;
+  double* rewards;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  uint8_t* final_obs;
+  const uint8_t* reset_mask;
+  // trace replay (rng_mode 0) -- pointers may be null in Philox mode (rng_mode 1)
+  int rng_mode;
+  const uint8_t* order;
+  const uint8_t* draws;
+  const int32_t* n_draws;
+  int K;
+  const uint8_t* reset_draws;
+  const int32_t* n_reset_draws;
+  int R;
+  int32_t* draws_used;
+  int32_t* reset_draws_used;
+  int32_t* status;
+  int obs_bulk_ok;        // obs / final_obs base pointers are 16-byte aligned
+};
+
+// ------------------------------------------------------------------------ Philox4x32-10
+// Salmon et al. SC'11.  Production-mode generator (the reference's python `random` and legacy
+// numpy MT19937 streams cannot be reproduced on a device; they are replayed in trace mode).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Per-env cursor over the random source.  MODE 0 = trace replay, MODE 1 = Philox.
+template <int MODE>
+struct Rng {
+  const uint8_t* draws; int n, k;                       // trace
+  uint32_t k0, k1, id0, id1, ctr, b0, b1, b2, b3; int have;  // philox
+  int err;
+
+  __device__ __forceinline__ void open_trace(const uint8_t* d, int n_) { draws = d; n = n_; k = 0; err = 0; have = 0; }
+  __device__ __forceinline__ void open_philox(unsigned long long seed, unsigned long long env_id, uint32_t ctr_) {
+    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); id0 = (uint32_t)env_id; id1 = (uint32_t)(env_id >> 32);
+    ctr = ctr_; have = 0; err = 0; k = 0; n = 0; draws = nullptr;
+  }
+  __device__ __forceinline__ uint32_t u32() {
+    if (have == 0) {
+      uint32_t o[4];
+      philox4x32_10(id0, id1, ctr, 0u, k0, k1, o);
+      b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+      ++ctr; have = 4;
+    }
+    const uint32_t v = b0;
+    b0 = b1; b1 = b2; b2 = b3; --have;
+    return v;
+  }
+  // MultiGridEnv._rand_int = random.randint(low, high): INCLUSIVE bounds (multigrid.py:225-230)
+  __device__ __forceinline__ int rand_int(int lo, int hi) {
+    if (MODE == 0) {
+      if (k >= n) { err |= MG_ERR_TRACE_OVERFLOW; return lo; }
+      const int v = draws[k++];
+      if (v < lo || v > hi) err |= MG_ERR_TRACE_RANGE;
+      return v;
+    } else {
+      return lo + (int)__umulhi(u32(), (uint32_t)(hi - lo + 1));
+    }
+  }
+};
+
+// ------------------------------------------------------------------- TMA / mbarrier PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D).  16-byte aligned addresses, size % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (TMA, 1-D).
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------- encode
+// Grid.encode, encode_dim 3 (grid.py:223-252 + object.py:58-74 + agent.py:119-126):
+// 16 packed cells (one uint4) -> 48 obs bytes (three uint4), byte order (type, colour, state).
+__device__ __forceinline__ void expand4(uint32_t w, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+  const uint32_t t = w & 0x03030303u, c = (w >> 2) & 0x0F0F0F0Fu, s = (w >> 6) & 0x03030303u;
+  // out bytes: t0 c0 s0 t1 | c1 s1 t2 c2 | s2 t3 c3 s3
+  const uint32_t tc = __byte_perm(t, c, 0x5140);   // t0 c0 t1 c1  (bytes: [t0, c0, t1, c1])
+  o0 = __byte_perm(tc, s, 0x2410);                 // t0 c0 s0 t1
+  const uint32_t cs = __byte_perm(c, s, 0x6251);   // c1 s1 c2 s2
+  o1 = __byte_perm(cs, t, 0x2610);                 // c1 s1 t2 c2
+  const uint32_t st = __byte_perm(s, t, 0x3072);   // s2 t3 .  s3
+  o2 = __byte_perm(st, c, 0x3710);                 // s2 t3 c3 s3
+}
+
+__device__ __forceinline__ void expand16(const uint4 in, uint4& a, uint4& b, uint4& c) {
+  uint32_t o[12];
+  expand4(in.x, o[0], o[1], o[2]);
+  expand4(in.y, o[3], o[4], o[5]);
+  expand4(in.z, o[6], o[7], o[8]);
+  expand4(in.w, o[9], o[10], o[11]);
+  a = make_uint4(o[0], o[1], o[2], o[3]);
+  b = make_uint4(o[4], o[5], o[6], o[7]);
+  c = make_uint4(o[8], o[9], o[10], o[11]);
+}
+
+}  // namespace mg

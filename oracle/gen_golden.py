@@ -1,0 +1,106 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz (deterministic)
+
+The committed .npz files are what the CPU and GPU parity tests replay; this script is the
+provenance record the task statement asks for ("commit the vectors ... together with the
+script that made them").  Every array is produced by reference code executing under
+oracle/ref_harness.py's shim with RNG taps; nothing is synthesised here except the
+action streams (seeded numpy Generator, including a few out-of-range actions, and a
+greedy ball-seeking policy on some episodes so that `terminated` is exercised).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# id -> (file stem, episodes, greedy fraction)
+COLLECT_PLAN = {
+    "multigrid-collect-respawn-clustered-v0": ("collect_respawn_clustered", 256, 0.25),
+    "multigrid-collect-v0": ("collect_even", 12, 0.5),
+    "multigrid-collect-single-v0": ("collect_single", 8, 0.5),
+    "multigrid-collect-quadrants-v0": ("collect_quadrants", 12, 0.5),
+    "multigrid-collect-rooms-v0": ("collect_rooms", 12, 0.5),
+    "multigrid-collect-rooms-fixed-horizon-v0": ("collect_rooms_fixed", 8, 0.5),
+    "multigrid-collect-rooms-respawn-v0": ("collect_rooms_respawn", 12, 0.25),
+    "multigrid-collect-respawn-v0": ("collect_respawn", 12, 0.25),
+    "multigrid-collect-quadrants15-v0": ("collect_quadrants15", 6, 0.5),
+}
+
+
+class GreedyActions:
+    """Action source handed to record_collect_episode: mostly walks towards the nearest ball."""
+
+    def __init__(self, env, seed, eps=0.2):
+        self.env, self.rng, self.eps = env, np.random.default_rng(seed), eps
+
+    def random(self, n):
+        return self.rng.random(n)
+
+    def choice(self, a, size):
+        return self.rng.choice(a, size=size)
+
+    def integers(self, lo, hi, size):
+        env = self.env
+        acts = self.rng.integers(lo, hi, size=size)
+        balls = [(i, j) for i in range(env.width) for j in range(env.height)
+                 if (o := env.grid.get(i, j)) is not None and o.type == "ball"]
+        if not balls:
+            return acts
+        for k, a in enumerate(env.agents):
+            if self.rng.random() < self.eps:
+                continue
+            x, y = int(a.pos[0]), int(a.pos[1])
+            bx, by = min(balls, key=lambda b: abs(b[0] - x) + abs(b[1] - y))
+            if abs(bx - x) >= abs(by - y) and bx != x:
+                acts[k] = 1 if bx > x else 3
+            elif by != y:
+                acts[k] = 2 if by > y else 0
+        return acts
+
+
+def gen_collect():
+    rh.import_reference()
+    for env_id, (stem, episodes, greedy_frac) in COLLECT_PLAN.items():
+        env, time_limit = rh.make_collect(env_id)
+        eps = []
+        for seed in range(episodes):
+            greedy = seed < int(round(greedy_frac * episodes))
+            src = GreedyActions(env, 1000 + seed) if greedy else np.random.default_rng(1000 + seed)
+            eps.append(rh.record_collect_episode(env, time_limit, seed, src, oob_action_prob=0.03))
+        T = max(e["length"] for e in eps)
+        K = max(2, max(int(e["n_draws"].max()) for e in eps))
+        packed = rh.pack_collect_episodes(eps, T, K)
+        from gymnasium.envs.registration import registry
+        kw = registry[env_id]["kwargs"]
+        packed["meta_env_id"] = np.array(env_id)
+        packed["meta_time_limit"] = np.array(time_limit or 0)
+        packed["meta_size"] = np.array(kw["size"])
+        packed["meta_num_balls"] = np.array(kw["num_balls"])
+        packed["meta_agents_index"] = np.array(kw["agents_index"])
+        packed["meta_balls_index"] = np.array(kw["balls_index"])
+        packed["meta_balls_reward"] = np.array(kw["balls_reward"], dtype=np.float64)
+        packed["meta_respawn"] = np.array(kw["respawn"])
+        path = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path, **packed)
+        term = int(packed["terminated"].any(axis=1).sum())
+        lost = 0
+        print(f"{stem}: {episodes} episodes, T={T}, K={K}, terminated episodes={term}, "
+              f"steps={int(packed['length'].sum())}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["collect"]
+    if "collect" in which:
+        gen_collect()

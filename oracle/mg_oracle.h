@@ -1,0 +1,107 @@
+/* mg_oracle.h -- CPU restatement ("oracle") of the gym-multigrid hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product
+ * (gym-multigrid_b200/ + include/multigrid_b200.h) never links, imports or calls it.
+ *
+ * Parity pin: every function here is checked bit-for-bit against traces recorded from
+ * the unmodified reference (oracle/gen_golden.py -> tests/golden/*.npz, replayed by
+ * tests/test_oracle_golden.py).  The reference ships no golden vectors of its own
+ * (SURVEY.md section 4), so those recorded traces are the pin.
+ *
+ * Citations are file:line under the reference checkout (/root/reference).
+ */
+#ifndef MG_ORACLE_H
+#define MG_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_MAX_AGENTS 8
+#define OC_MAX_BALL_TYPES 8
+
+/* Packed Collect cell: type | colour << 2 | state << 6 (CollectWorld, core/world.py:54-64;
+ * colours core/constants.py:8-19; agent state = dir, core/agent.py:119-126). */
+#define OC_T_EMPTY 0
+#define OC_T_WALL 1
+#define OC_T_BALL 2
+#define OC_T_AGENT 3
+#define OC_CELL(type, colour, state) ((uint8_t)((type) | ((colour) << 2) | ((state) << 6)))
+#define OC_WALL_GREY OC_CELL(OC_T_WALL, 7, 0)
+
+enum { OC_LAYOUT_EVEN_DIST = 0,        /* CollectGameEvenDist._gen_grid        collect_game.py:236-259 */
+       OC_LAYOUT_QUADRANTS = 1,        /* CollectGameQuadrants._gen_grid       collect_game.py:266-300 */
+       OC_LAYOUT_ROOMS = 2,            /* CollectGameRooms._gen_grid           collect_game.py:306-362 */
+       OC_LAYOUT_QUADRANTS_RESPAWN = 3 /* CollectGameQuadrantsRespawn          collect_game.py:376-409 */ };
+
+typedef struct {
+  int32_t width, height;
+  int32_t num_agents;                       /* len(agents_index) */
+  int32_t num_ball_types;                   /* len(balls_index) */
+  int32_t agent_colour[OC_MAX_AGENTS];      /* agents_index */
+  int32_t ball_colour[OC_MAX_BALL_TYPES];   /* balls_index */
+  double ball_reward[OC_MAX_BALL_TYPES];    /* balls_reward */
+  int32_t num_balls;                        /* np.sum(num_balls), collect_game.py:37 */
+  int32_t respawn;
+  int32_t layout;
+  int32_t fixed_horizon;                    /* CollectGameRoomsFixedHorizon.step :368-370 */
+  int32_t max_steps;                        /* env-internal, 100 (collect_game.py:65) */
+  int32_t time_limit;                       /* gymnasium TimeLimit from registration; 0 = none */
+} oc_collect_cfg;
+
+/* Batched struct-of-arrays env state (same planes the CUDA library keeps in HBM). */
+typedef struct {
+  uint8_t* grid;       /* [N][W*H] packed cells, index x*H + y (the obs order, grid.py:234-250) */
+  uint8_t* agent_pos;  /* [N][A][2] (x, y) */
+  int32_t* step_count; /* [N] */
+  int32_t* collected;  /* [N] */
+  int32_t* info;       /* [N][A*num_ball_types]  info[keys[nb*i + colour]] collect_game.py:147 */
+  uint32_t* rng_ctr;   /* [N] Philox block counter (production RNG mode only) */
+} oc_collect_state;
+
+/* Where random numbers come from.
+ * mode 0 (trace): outputs recorded from the reference's own generators are replayed:
+ *    order = np.random.permutation(A) (collect_game.py:186), draws = random.randint
+ *    outputs in call order (multigrid.py:225-230 via place_obj :316-321).
+ * mode 1 (philox): counter-based Philox4x32-10 keyed by (seed), counter (env id, ctr). */
+typedef struct {
+  int32_t mode;
+  const uint8_t* order;   /* [N][A]      trace */
+  const uint8_t* draws;   /* [N][K]      trace */
+  const int32_t* n_draws; /* [N]         trace: valid entries per env */
+  int32_t K;
+  int32_t* draws_used;    /* [N] out, may be NULL */
+  uint64_t seed;          /* philox */
+  uint64_t env_id_base;   /* philox: global id of env 0 of this shard */
+} oc_rng_src;
+
+/* status bits accumulated into *status (may be NULL) */
+#define OC_ERR_TRACE_OVERFLOW 1 /* trace ran out of recorded draws */
+#define OC_ERR_TRACE_RANGE 2    /* a recorded draw is outside the requested [lo, hi] */
+#define OC_ERR_OOB 4            /* an agent tried to leave the grid (reference would assert, grid.py:62-63) */
+
+void oc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Grid.encode for encode_dim 3 (grid.py:223-252): n_cells packed cells -> 3*n_cells bytes. */
+void oc_encode3(const uint8_t* cells, int64_t n_cells, uint8_t* obs);
+
+/* reset: CollectGameEnv.reset + _gen_grid (collect_game.py:107-119 + layout).  mask may be NULL
+ * (= all).  obs may be NULL. */
+int oc_collect_reset(const oc_collect_cfg* cfg, int64_t N, oc_collect_state* st, const uint8_t* mask,
+                     const oc_rng_src* rng, uint8_t* obs, int32_t* status, int nthreads);
+
+/* step: CollectGameEnv.step (collect_game.py:183-214).  autoreset: 0 = none; 1 = gymnasium 0.29.1
+ * same-step autoreset (obs returned for finished envs is the reset obs; the terminal obs goes to
+ * final_obs when non-NULL).  reset_rng is used for the autoreset in trace mode (philox mode keeps
+ * drawing from the env's own stream). */
+int oc_collect_step(const oc_collect_cfg* cfg, int64_t N, oc_collect_state* st, const int8_t* actions,
+                    const oc_rng_src* rng, uint8_t* obs, double* rewards, uint8_t* terminated,
+                    uint8_t* truncated, int autoreset, const oc_rng_src* reset_rng, uint8_t* final_obs,
+                    int32_t* status, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

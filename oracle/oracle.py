@@ -1,0 +1,200 @@
+"""ctypes binding of the CPU oracle (oracle/mg_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libmg_oracle.so")
+
+MAX_AGENTS = 8
+MAX_BALL_TYPES = 8
+LAYOUTS = {"even_dist": 0, "quadrants": 1, "rooms": 2, "quadrants_respawn": 3}
+
+ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, seconds)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in os.listdir(_HERE) if f.endswith((".c", ".h"))
+    ):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class CollectCfg(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32),
+        ("num_ball_types", C.c_int32), ("agent_colour", C.c_int32 * MAX_AGENTS),
+        ("ball_colour", C.c_int32 * MAX_BALL_TYPES), ("ball_reward", C.c_double * MAX_BALL_TYPES),
+        ("num_balls", C.c_int32), ("respawn", C.c_int32), ("layout", C.c_int32),
+        ("fixed_horizon", C.c_int32), ("max_steps", C.c_int32), ("time_limit", C.c_int32),
+    ]
+
+
+class CollectState(C.Structure):
+    _fields_ = [("grid", C.c_void_p), ("agent_pos", C.c_void_p), ("step_count", C.c_void_p),
+                ("collected", C.c_void_p), ("info", C.c_void_p), ("rng_ctr", C.c_void_p)]
+
+
+class RngSrc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("order", C.c_void_p), ("draws", C.c_void_p), ("n_draws", C.c_void_p),
+                ("K", C.c_int32), ("draws_used", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oc_collect_reset.restype = C.c_int
+        _lib.oc_collect_step.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_collect_cfg(size, agents_index, balls_index, balls_reward, num_balls, respawn, layout,
+                     fixed_horizon=False, max_steps=100, time_limit=0, width=None, height=None) -> CollectCfg:
+    c = CollectCfg()
+    c.width = width or size
+    c.height = height or size
+    c.num_agents = len(agents_index)
+    c.num_ball_types = len(balls_index)
+    for i, v in enumerate(agents_index):
+        c.agent_colour[i] = v
+    for i, v in enumerate(balls_index):
+        c.ball_colour[i] = v
+    for i, v in enumerate(balls_reward):
+        c.ball_reward[i] = float(v)
+    c.num_balls = int(np.sum(np.array(num_balls)))
+    c.respawn = int(bool(respawn))
+    c.layout = LAYOUTS[layout] if isinstance(layout, str) else int(layout)
+    c.fixed_horizon = int(bool(fixed_horizon))
+    c.max_steps = max_steps
+    c.time_limit = int(time_limit or 0)
+    return c
+
+
+class TraceRng:
+    """Replay source: recorded np.random.permutation outputs + random.randint outputs."""
+
+    def __init__(self, order=None, draws=None, n_draws=None):
+        self.order = None if order is None else np.ascontiguousarray(order, np.uint8)
+        self.draws = None if draws is None else np.ascontiguousarray(draws, np.uint8)
+        self.n_draws = None if n_draws is None else np.ascontiguousarray(n_draws, np.int32)
+        N = (self.draws if self.draws is not None else self.order).shape[0]
+        self.draws_used = np.zeros(N, np.int32)
+
+    def struct(self):
+        s = RngSrc()
+        s.mode = 0
+        s.order, s.draws, s.n_draws = _p(self.order), _p(self.draws), _p(self.n_draws)
+        s.K = 0 if self.draws is None else self.draws.shape[1]
+        s.draws_used = _p(self.draws_used)
+        return s
+
+
+class PhiloxRng:
+    def __init__(self, seed, env_id_base=0):
+        self.seed, self.env_id_base = int(seed), int(env_id_base)
+
+    def struct(self):
+        s = RngSrc()
+        s.mode = 1
+        s.seed, s.env_id_base = self.seed, self.env_id_base
+        return s
+
+
+class CollectOracle:
+    """Batched CPU Collect envs with the same state planes as the CUDA library."""
+
+    def __init__(self, cfg: CollectCfg, num_envs: int, nthreads: int = 1):
+        self.cfg, self.N, self.nthreads = cfg, int(num_envs), nthreads
+        W, H, A, nb = cfg.width, cfg.height, cfg.num_agents, cfg.num_ball_types
+        self.W, self.H, self.A, self.nb = W, H, A, nb
+        N = self.N
+        self.grid = np.zeros((N, W * H), np.uint8)
+        self.agent_pos = np.zeros((N, A, 2), np.uint8)
+        self.step_count = np.zeros(N, np.int32)
+        self.collected = np.zeros(N, np.int32)
+        self.info = np.zeros((N, A * nb), np.int32)
+        self.rng_ctr = np.zeros(N, np.uint32)
+        self.status = C.c_int32(0)
+
+    def _state(self):
+        s = CollectState()
+        s.grid, s.agent_pos, s.step_count = _p(self.grid), _p(self.agent_pos), _p(self.step_count)
+        s.collected, s.info, s.rng_ctr = _p(self.collected), _p(self.info), _p(self.rng_ctr)
+        return s
+
+    def reset(self, rng, mask=None, want_obs=True):
+        obs = np.empty((self.N, self.W, self.H, 3), np.uint8) if want_obs else None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            if obs is not None:
+                obs[:] = self.encode()
+        st, rs = self._state(), rng.struct()
+        rc = lib().oc_collect_reset(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(mask), C.byref(rs),
+                                    _p(obs), C.byref(self.status), C.c_int(self.nthreads))
+        if rc:
+            raise RuntimeError("oc_collect_reset failed (invalid layout/config)")
+        return obs
+
+    def step(self, actions, rng, autoreset=False, reset_rng=None, want_final_obs=False, want_obs=True):
+        actions = np.ascontiguousarray(actions, np.int8).reshape(self.N, self.A)
+        obs = np.empty((self.N, self.W, self.H, 3), np.uint8) if want_obs else None
+        rew = np.empty((self.N, self.A), np.float64)
+        term = np.empty(self.N, np.uint8)
+        trunc = np.empty(self.N, np.uint8)
+        fin = np.zeros((self.N, self.W, self.H, 3), np.uint8) if want_final_obs else None
+        st, rs = self._state(), rng.struct()
+        rrs = reset_rng.struct() if reset_rng is not None else RngSrc()
+        rc = lib().oc_collect_step(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(actions), C.byref(rs),
+                                   _p(obs), _p(rew), _p(term), _p(trunc), C.c_int(int(autoreset)), C.byref(rrs),
+                                   _p(fin), C.byref(self.status), C.c_int(self.nthreads))
+        if rc:
+            raise RuntimeError("oc_collect_step failed")
+        out = (obs, rew, term.astype(bool), trunc.astype(bool))
+        return out + (fin,) if want_final_obs else out
+
+    def encode(self):
+        return encode3(self.grid).reshape(self.N, self.W, self.H, 3)
+
+    def set_state_from_obs(self, obs, agent_pos, step_count=0):
+        """Inject a state given Grid.encode() arrays [N,W,H,3] (e.g. a reference reset)."""
+        obs = np.asarray(obs, np.uint8).reshape(self.N, self.W * self.H, 3)
+        self.grid[:] = obs[..., 0] | (obs[..., 1] << 2) | (obs[..., 2] << 6)
+        self.agent_pos[:] = np.asarray(agent_pos).reshape(self.N, self.A, 2)
+        self.step_count[:] = step_count
+        self.collected[:] = 0
+        self.info[:] = 0
+
+
+def encode3(cells: np.ndarray) -> np.ndarray:
+    cells = np.ascontiguousarray(cells, np.uint8)
+    out = np.empty(cells.shape + (3,), np.uint8)
+    lib().oc_encode3(_p(cells), C.c_int64(cells.size), _p(out))
+    return out
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().oc_philox4x32_10(c, k, o)
+    return [int(v) for v in o]

@@ -1,0 +1,244 @@
+"""Run the UNMODIFIED reference under a shim and record RNG-tapped traces.
+
+TEST INFRASTRUCTURE ONLY.  Usable only where /root/reference exists (the build
+container); nothing in the product path, `-m gpu` tests, smoke() or bench.py imports
+this module.  It is what `oracle/gen_golden.py` uses to produce `tests/golden/*.npz`.
+
+How the reference is made to run here; no reference source is edited:
+  * `oracle/refshim/` supplies stub `gymnasium` + `matplotlib` packages;
+  * `np.float_` (removed in numpy 2) is aliased to `np.float64` before import
+    (annotations at multigrid.py:399, collect_game.py:122,135,151, ctf.py:1365-1368);
+  * `CollectGameQuadrantsRespawn.__init__(self)` (collect_game.py:372-374) accepts no
+    kwargs although registration passes six (__init__.py:122-134): the instance is
+    created with `object.__new__` and `CollectGameQuadrants.__init__` is called;
+  * `env.num_balls = int(env.num_balls)` for the variants whose `_gen_grid` does
+    `isinstance(self.num_balls, int)` on an `np.int64` (collect_game.py:37 vs 245,343).
+
+RNG taps (the reference's hot path uses three generators, none seeded by reset()):
+  * `random.randint`          <- MultiGridEnv._rand_int (multigrid.py:225-230)
+  * `np.random.permutation`   <- CollectGameEnv.step agent order (collect_game.py:186)
+  * `np.random.randint`       <- Maze start cell (maze.py:204)
+  * proxy around `env.np_random` for CtF (`integers`, `shuffle`, `choice`).
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+from contextlib import contextmanager
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("MG_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_multigrid"))
+
+
+def import_reference():
+    """Import `gym_multigrid` from /root/reference under the shim; returns the package."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
+    if not hasattr(np, "float_"):
+        np.float_ = np.float64  # numpy>=2 removed the alias the reference annotates with
+    for p in (_SHIM, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gym_multigrid  # noqa: F401  (registers the ids with the shim registry)
+    import gym_multigrid.envs  # noqa: F401
+    return gym_multigrid
+
+
+# ----------------------------------------------------------------------------- taps
+class Taps:
+    """Records the outputs of the global-RNG call sites while installed."""
+
+    def __init__(self):
+        self.randint = []       # python random.randint outputs, in call order
+        self.perm = []          # np.random.permutation outputs
+        self.np_randint = []    # np.random.randint outputs
+
+    def clear(self):
+        self.randint.clear()
+        self.perm.clear()
+        self.np_randint.clear()
+
+
+@contextmanager
+def installed_taps():
+    taps = Taps()
+    o_randint, o_perm, o_nprandint = random.randint, np.random.permutation, np.random.randint
+
+    def t_randint(a, b):
+        v = o_randint(a, b)
+        taps.randint.append(int(v))
+        return v
+
+    def t_perm(n):
+        v = o_perm(n)
+        taps.perm.append(np.asarray(v).copy())
+        return v
+
+    def t_nprandint(*a, **k):
+        v = o_nprandint(*a, **k)
+        taps.np_randint.append(int(v))
+        return v
+
+    random.randint, np.random.permutation, np.random.randint = t_randint, t_perm, t_nprandint
+    try:
+        yield taps
+    finally:
+        random.randint, np.random.permutation, np.random.randint = o_randint, o_perm, o_nprandint
+
+
+class GeneratorProxy:
+    """Wraps a numpy Generator and records integers/shuffle/choice outputs (CtF)."""
+
+    def __init__(self, gen):
+        self._gen = gen
+        self.events = []  # (kind, payload)
+
+    def integers(self, *a, **k):
+        v = self._gen.integers(*a, **k)
+        self.events.append(("integers", int(v)))
+        return v
+
+    def shuffle(self, x):
+        self._gen.shuffle(x)
+        self.events.append(("shuffle", list(int(i) for i in x)))
+
+    def choice(self, a, size=None, replace=True, p=None):
+        v = self._gen.choice(a, size=size, replace=replace, p=p)
+        self.events.append(("choice", np.asarray(v).copy()))
+        return v
+
+    def __getattr__(self, name):
+        return getattr(self._gen, name)
+
+
+# ------------------------------------------------------------------- env construction
+COLLECT_IDS = [
+    "multigrid-collect-v0",
+    "multigrid-collect-single-v0",
+    "multigrid-collect-quadrants-v0",
+    "multigrid-collect-rooms-v0",
+    "multigrid-collect-rooms-fixed-horizon-v0",
+    "multigrid-collect-rooms-respawn-v0",
+    "multigrid-collect-respawn-v0",
+    "multigrid-collect-respawn-clustered-v0",
+    "multigrid-collect-quadrants15-v0",
+]
+
+
+def make_collect(env_id: str):
+    """Construct a reference Collect env for a registered id; returns (env, time_limit)."""
+    import_reference()
+    import importlib
+    from gymnasium.envs.registration import registry
+
+    spec = registry[env_id]
+    mod, cls_name = spec["entry_point"].split(":")
+    cls = getattr(importlib.import_module(mod), cls_name)
+    kw = dict(spec["kwargs"])
+    if cls_name == "CollectGameQuadrantsRespawn":
+        from gym_multigrid.envs.collect_game import CollectGameQuadrants
+        env = object.__new__(cls)
+        CollectGameQuadrants.__init__(env, **kw)
+    else:
+        env = cls(**kw)
+    env.num_balls = int(env.num_balls)
+    return env, spec["max_episode_steps"]
+
+
+# ---------------------------------------------------------------- Collect trace record
+def record_collect_episode(env, time_limit, seed, action_rng, oob_action_prob=0.0, max_len=None):
+    """One episode of a reference Collect env -> dict of arrays.
+
+    Seeds the generators the reference really uses (`random`, legacy `np.random`), the
+    way the reference's own `set_seed` does (utils/misc.py:9-19).  The TimeLimit wrapper
+    gymnasium.make would add (truncated |= elapsed >= max_episode_steps) is emulated here.
+    """
+    random.seed(seed)
+    np.random.seed(seed)
+    A = len(env.agents)
+    with installed_taps() as taps:
+        obs0, info0 = env.reset(seed=seed)
+        reset_draws = list(taps.randint)
+        taps.clear()
+        W, H = env.width, env.height
+        init_pos = np.array([np.asarray(a.pos) for a in env.agents], dtype=np.int16)
+        init_dir = np.array([a.dir for a in env.agents], dtype=np.int8)
+        T = max_len or (time_limit if time_limit is not None else env.max_steps)
+        rec = dict(actions=[], order=[], draws=[], n_draws=[], obs=[], rewards=[], terminated=[],
+                   truncated=[], info=[], pos=[], collected=[])
+        t = 0
+        while True:
+            acts = action_rng.integers(0, 4, size=A)
+            if oob_action_prob > 0:
+                oob = action_rng.random(A) < oob_action_prob
+                acts = np.where(oob, action_rng.choice([-1, 4, 7], size=A), acts)
+            obs, rew, term, trunc, info = env.step([int(a) for a in acts])
+            t += 1
+            if time_limit is not None and t >= time_limit:
+                trunc = True
+            assert len(taps.perm) == 1
+            rec["actions"].append(acts.astype(np.int8))
+            rec["order"].append(taps.perm[0].astype(np.uint8))
+            rec["draws"].append(np.array(taps.randint, dtype=np.uint8))
+            rec["n_draws"].append(len(taps.randint))
+            rec["obs"].append(obs.copy())
+            rec["rewards"].append(np.asarray(rew, dtype=np.float64).copy())
+            rec["terminated"].append(bool(term))
+            rec["truncated"].append(bool(trunc))
+            rec["info"].append(np.array([info[k] for k in env.keys], dtype=np.int32))
+            rec["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], dtype=np.int16))
+            rec["collected"].append(int(env.collected_balls))
+            taps.clear()
+            if term or trunc or t >= T:
+                break
+    out = dict(
+        init_obs=np.asarray(obs0, dtype=np.uint8).copy(), init_pos=init_pos, init_dir=init_dir,
+        reset_draws=np.array(reset_draws, dtype=np.uint8), length=t,
+        actions=np.stack(rec["actions"]), order=np.stack(rec["order"]),
+        draws=rec["draws"], n_draws=np.array(rec["n_draws"], dtype=np.int32),
+        obs=np.stack(rec["obs"]), rewards=np.stack(rec["rewards"]),
+        terminated=np.array(rec["terminated"]), truncated=np.array(rec["truncated"]),
+        info=np.stack(rec["info"]), pos=np.stack(rec["pos"]),
+        collected=np.array(rec["collected"], dtype=np.int32),
+    )
+    return out
+
+
+def pack_collect_episodes(eps, T, K):
+    """Stack episodes into fixed-shape arrays: steps padded to T, draws padded to K ints."""
+    E = len(eps)
+    A = eps[0]["actions"].shape[1]
+    W, H, D = eps[0]["init_obs"].shape
+    R = max(len(e["reset_draws"]) for e in eps)
+    out = dict(
+        init_obs=np.stack([e["init_obs"] for e in eps]),
+        init_pos=np.stack([e["init_pos"] for e in eps]),
+        init_dir=np.stack([e["init_dir"] for e in eps]),
+        length=np.array([e["length"] for e in eps], dtype=np.int32),
+        n_reset_draws=np.array([len(e["reset_draws"]) for e in eps], dtype=np.int32),
+        reset_draws=np.zeros((E, R), np.uint8),
+        actions=np.zeros((E, T, A), np.int8), order=np.zeros((E, T, A), np.uint8),
+        n_draws=np.zeros((E, T), np.int32), draws=np.zeros((E, T, K), np.uint8),
+        obs=np.zeros((E, T, W, H, D), np.uint8), rewards=np.zeros((E, T, A), np.float64),
+        terminated=np.zeros((E, T), bool), truncated=np.zeros((E, T), bool),
+        info=np.zeros((E, T, eps[0]["info"].shape[1]), np.int32),
+        pos=np.zeros((E, T, A, 2), np.int16), collected=np.zeros((E, T), np.int32),
+    )
+    for i, e in enumerate(eps):
+        L = e["length"]
+        out["reset_draws"][i, :len(e["reset_draws"])] = e["reset_draws"]
+        for k in ("actions", "order", "n_draws", "obs", "rewards", "terminated", "truncated",
+                  "info", "pos", "collected"):
+            out[k][i, :L] = e[k]
+        for t, d in enumerate(e["draws"]):
+            if len(d) > K:
+                raise ValueError(f"episode {i} step {t}: {len(d)} draws > K={K}")
+            out["draws"][i, t, :len(d)] = d
+    return out
