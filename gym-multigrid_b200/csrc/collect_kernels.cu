@@ -396,45 +396,37 @@ static cudaError_t set_smem(const void* fn, size_t bytes) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// once per handle (mg_create): opt every kernel in to the tile's dynamic shared memory size
+cudaError_t configure_kernels(int cells, int A) {
+  const size_t smem = tile_smem_bytes(kE, cells, A);
+  cudaError_t e;
+  if ((e = set_smem((const void*)collect_step_kernel<0, kE, kThreads>, smem)) != cudaSuccess) return e;
+  if ((e = set_smem((const void*)collect_step_kernel<1, kE, kThreads>, smem)) != cudaSuccess) return e;
+  if ((e = set_smem((const void*)collect_reset_kernel<0, kE, kThreads>, smem)) != cudaSuccess) return e;
+  if ((e = set_smem((const void*)collect_reset_kernel<1, kE, kThreads>, smem)) != cudaSuccess) return e;
+  return set_smem((const void*)encode3_kernel<kE, kThreads>, (size_t)kE * cells * 4);
+}
+
 cudaError_t launch_collect_step(const CollectParams& p, cudaStream_t st) {
   const size_t smem = tile_smem_bytes(kE, p.cells, p.A);
   const unsigned blocks = (unsigned)((p.N + kE - 1) / kE);
-  cudaError_t e;
-  if (p.rng_mode == 0) {
-    auto fn = collect_step_kernel<0, kE, kThreads>;
-    if ((e = set_smem((const void*)fn, smem)) != cudaSuccess) return e;
-    fn<<<blocks, kThreads, smem, st>>>(p);
-  } else {
-    auto fn = collect_step_kernel<1, kE, kThreads>;
-    if ((e = set_smem((const void*)fn, smem)) != cudaSuccess) return e;
-    fn<<<blocks, kThreads, smem, st>>>(p);
-  }
+  if (p.rng_mode == 0) collect_step_kernel<0, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
+  else collect_step_kernel<1, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_collect_reset(const CollectParams& p, cudaStream_t st) {
   const size_t smem = tile_smem_bytes(kE, p.cells, p.A);
   const unsigned blocks = (unsigned)((p.N + kE - 1) / kE);
-  cudaError_t e;
-  if (p.rng_mode == 0) {
-    auto fn = collect_reset_kernel<0, kE, kThreads>;
-    if ((e = set_smem((const void*)fn, smem)) != cudaSuccess) return e;
-    fn<<<blocks, kThreads, smem, st>>>(p);
-  } else {
-    auto fn = collect_reset_kernel<1, kE, kThreads>;
-    if ((e = set_smem((const void*)fn, smem)) != cudaSuccess) return e;
-    fn<<<blocks, kThreads, smem, st>>>(p);
-  }
+  if (p.rng_mode == 0) collect_reset_kernel<0, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
+  else collect_reset_kernel<1, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_encode3(const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st) {
   const size_t smem = (size_t)kE * cells * 4;
   const unsigned blocks = (unsigned)((N + kE - 1) / kE);
-  auto fn = encode3_kernel<kE, kThreads>;
-  cudaError_t e;
-  if ((e = set_smem((const void*)fn, smem)) != cudaSuccess) return e;
-  fn<<<blocks, kThreads, smem, st>>>(grid, obs, N, cells, obs_bulk_ok);
+  encode3_kernel<kE, kThreads><<<blocks, kThreads, smem, st>>>(grid, obs, N, cells, obs_bulk_ok);
   return cudaGetLastError();
 }
 

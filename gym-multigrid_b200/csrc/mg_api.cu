@@ -17,6 +17,7 @@ cudaError_t launch_collect_step(const CollectParams& p, cudaStream_t st);
 cudaError_t launch_collect_reset(const CollectParams& p, cudaStream_t st);
 cudaError_t launch_encode3(const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st);
 int tile_envs();
+cudaError_t configure_kernels(int cells, int A);
 size_t tile_smem(int cells, int A);
 }  // namespace mg
 
@@ -100,6 +101,8 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   if (prop.major != 10) return fail(nullptr, "mg_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
   if (mg::tile_smem(W * H, A) > (size_t)prop.sharedMemPerBlockOptin)
     return fail(nullptr, "mg_create: grid too large for the shared-memory tile (W*H*4*64 bytes must fit 227 KB)");
+
+  if ((ce = mg::configure_kernels(W * H, A)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute(max dynamic shared memory)", ce);
 
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");

@@ -281,7 +281,7 @@ int oc_collect_reset(const oc_collect_cfg* c, int64_t N, oc_collect_state* st, c
   int32_t err = 0;
   int rc = 0;
   if (nthreads < 1) nthreads = 1;
-#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : err) reduction(| : rc)
+#pragma omp parallel for schedule(dynamic, 512) num_threads(nthreads) reduction(| : err) reduction(| : rc)
   for (int64_t e = 0; e < N; ++e) {
     if (mask && !mask[e]) continue;
     rng_t r;
@@ -306,7 +306,7 @@ int oc_collect_step(const oc_collect_cfg* c, int64_t N, oc_collect_state* st, co
   int32_t err = 0;
   int rc = 0;
   if (nthreads < 1) nthreads = 1;
-#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : err) reduction(| : rc)
+#pragma omp parallel for schedule(dynamic, 512) num_threads(nthreads) reduction(| : err) reduction(| : rc)
   for (int64_t e = 0; e < N; ++e) {
     rng_t r;
     rng_open(&r, rng, e, st->rng_ctr ? st->rng_ctr[e] : 0);

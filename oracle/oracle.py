@@ -155,12 +155,19 @@ class CollectOracle:
             raise RuntimeError("oc_collect_reset failed (invalid layout/config)")
         return obs
 
-    def step(self, actions, rng, autoreset=False, reset_rng=None, want_final_obs=False, want_obs=True):
+    def step(self, actions, rng, autoreset=False, reset_rng=None, want_final_obs=False, want_obs=True, reuse_buffers=False):
         actions = np.ascontiguousarray(actions, np.int8).reshape(self.N, self.A)
-        obs = np.empty((self.N, self.W, self.H, 3), np.uint8) if want_obs else None
-        rew = np.empty((self.N, self.A), np.float64)
-        term = np.empty(self.N, np.uint8)
-        trunc = np.empty(self.N, np.uint8)
+        if reuse_buffers:  # benchmark mode: no per-step allocation / page faults
+            if not hasattr(self, "_out"):
+                self._out = (np.zeros((self.N, self.W, self.H, 3), np.uint8), np.zeros((self.N, self.A), np.float64),
+                             np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8))
+            obs, rew, term, trunc = self._out
+            obs = obs if want_obs else None
+        else:
+            obs = np.empty((self.N, self.W, self.H, 3), np.uint8) if want_obs else None
+            rew = np.empty((self.N, self.A), np.float64)
+            term = np.empty(self.N, np.uint8)
+            trunc = np.empty(self.N, np.uint8)
         fin = np.zeros((self.N, self.W, self.H, 3), np.uint8) if want_final_obs else None
         st, rs = self._state(), rng.struct()
         rrs = reset_rng.struct() if reset_rng is not None else RngSrc()

@@ -1,0 +1,98 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/multigrid_b200.h
+declares (no compute calls without a GPU), and the host-side mirror of the reference's
+registration / spaces is faithful."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "multigrid_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gym_multigrid_b200 import _lib
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/multigrid_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.mg_abi_version() == 1
+
+
+def test_config_struct_matches_header_layout():
+    from gym_multigrid_b200 import _lib
+    # uint32 + int32 + 2*int64 + 4*int32 + 8*int32 + 8*int32 + 8*double + 7*int32 (+pad) + uint64
+    assert C.sizeof(_lib.Config) == 4 + 4 + 16 + 16 + 32 + 32 + 64 + 28 + 4 + 8
+    assert C.sizeof(_lib.StepIO) == 6 * 8
+    assert C.sizeof(_lib.Trace) == 9 * 8
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_abi():
+    import torch
+    from gym_multigrid_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.Config()
+    h = C.c_void_p()
+    cfg.struct_size = 3
+    assert lib.mg_create(C.byref(cfg), 0, C.byref(h)) != 0 and "size mismatch" in _lib.last_error(None)
+    if not torch.cuda.is_available():
+        import gym_multigrid_b200 as mg
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mg.make_vec("multigrid-collect-respawn-clustered-v0", 8)
+
+
+def test_registry_mirrors_reference_ids_and_kwargs():
+    import gym_multigrid_b200 as mg
+    ids = {
+        "multigrid-collect-v0": ("CollectGameEvenDist", 100, [3, 5], False, 10, 15),
+        "multigrid-collect-single-v0": ("CollectGameEvenDist", 100, [3], False, 10, 15),
+        "multigrid-collect-quadrants-v0": ("CollectGameQuadrants", 100, [3, 5], False, 10, 15),
+        "multigrid-collect-rooms-v0": ("CollectGameRooms", 100, [3, 5], False, 10, 15),
+        "multigrid-collect-rooms-fixed-horizon-v0": ("CollectGameRoomsFixedHorizon", 100, [3, 5], False, 10, 15),
+        "multigrid-collect-rooms-respawn-v0": ("CollectGameRoomsFixedHorizon", 50, [3, 5], True, 10, 15),
+        "multigrid-collect-respawn-v0": ("CollectGameEvenDist", 50, [3, 5], True, 10, 15),
+        "multigrid-collect-respawn-clustered-v0": ("CollectGameQuadrantsRespawn", 50, [3, 5], True, 10, 15),
+        "multigrid-collect-quadrants15-v0": ("CollectGameQuadrants", None, [3, 5], False, 15, 30),
+    }
+    assert set(mg.registry) == set(ids)
+    for k, (cls, steps, agents, respawn, size, balls) in ids.items():
+        s = mg.spec(k)
+        assert s.entry_point == f"gym_multigrid.envs:{cls}" and s.max_episode_steps == steps
+        assert s.kwargs == dict(size=size, num_balls=balls, agents_index=agents, balls_index=[0, 1, 2],
+                                balls_reward=[1, 1, 1], respawn=respawn)
+    assert mg.spec("gym_multigrid:multigrid-collect-v0").id == "multigrid-collect-v0"
+    with pytest.raises(KeyError):
+        mg.spec("multigrid-nope-v0")
+
+
+def test_golden_registry_agrees_with_fixture_metadata():
+    """The ids/kwargs in our registry are the ones the reference registered when the fixtures were recorded."""
+    import gym_multigrid_b200 as mg
+    from replay import COLLECT_FIXTURES, load_golden
+    for stem in COLLECT_FIXTURES:
+        g = load_golden(stem)
+        s = mg.spec(str(g["meta_env_id"]))
+        assert s.kwargs["size"] == int(g["meta_size"]) and s.kwargs["num_balls"] == int(g["meta_num_balls"])
+        assert s.kwargs["agents_index"] == g["meta_agents_index"].tolist()
+        assert (s.max_episode_steps or 0) == int(g["meta_time_limit"])
+        assert s.kwargs["respawn"] == bool(g["meta_respawn"])
+
+
+def test_spaces():
+    from gym_multigrid_b200.spaces import Box, Discrete, MultiDiscrete
+    d = Discrete(4)
+    assert d.n == 4
+    b = Box(0, 255, (10, 10, 3), np.uint8)
+    assert b.shape == (10, 10, 3) and b.dtype == np.uint8
+    m = MultiDiscrete([5, 5])
+    assert m.nvec.tolist() == [5, 5]

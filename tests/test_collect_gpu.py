@@ -1,0 +1,221 @@
+"""GPU parity suite (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+(include/multigrid_b200.h) via gym_multigrid_b200; the oracle is only the checker.
+
+ * bit-exact replay of the golden traces recorded from the reference (tests/golden/*.npz),
+   tiled across thousands of envs so that every tile shape (full, ragged last tile) is hit;
+ * CUDA vs the C oracle in Philox mode on seeded inputs (same counter-based RNG on both sides);
+ * size-independent properties at BASELINE.json's full sizes (65 536 envs).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle as oc
+from replay import COLLECT_FIXTURES, collect_kwargs, expected, load_golden, step_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(g, stem, n, **extra):
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    kw = collect_kwargs(g, stem)
+    tl = kw.pop("time_limit")
+    kw.update(extra)
+    return CollectVecEnv(n, max_episode_steps=tl or None, **kw)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("stem", sorted(COLLECT_FIXTURES))
+def test_reset_replay_bit_exact(stem, cuda_device):
+    g = load_golden(stem)
+    E = len(g["length"])
+    tile = 3
+    env = _make(g, stem, E * tile, autoreset=False)
+    t = env.set_trace(reset_draws=np.concatenate([g["reset_draws"]] * tile), n_reset_draws=np.concatenate([g["n_reset_draws"]] * tile))
+    obs, _ = env.reset()
+    assert env.status() == 0
+    assert np.array_equal(_np(obs), np.concatenate([g["init_obs"]] * tile))
+    assert np.array_equal(_np(env.agent_pos), np.concatenate([g["init_pos"]] * tile))
+    assert np.array_equal(_np(t["reset_draws_used"]), np.concatenate([g["n_reset_draws"]] * tile))
+    assert int(env.step_count.abs().sum()) == 0 and int(env.collected_balls.abs().sum()) == 0
+    env.close()
+
+
+@pytest.mark.parametrize("stem", sorted(COLLECT_FIXTURES))
+def test_step_replay_bit_exact(stem, cuda_device):
+    """The reference's own trajectories, replayed through the CUDA step kernel."""
+    g = load_golden(stem)
+    E, T, A = g["actions"].shape
+    tile = 5 if stem == "collect_respawn_clustered" else 11   # 1280 / 66..132 envs: full + ragged tiles
+    env = _make(g, stem, E * tile, autoreset=False)
+    env.set_state_from_obs(np.concatenate([g["init_obs"]] * tile), np.concatenate([g["init_pos"]] * tile))
+    for t in range(T):
+        act, order, draws, n_draws, live = step_inputs(g, t, tile)
+        tr = env.set_trace(order=order, draws=draws, n_draws=n_draws)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        x = expected(g, t, tile)
+        assert np.array_equal(_np(tr["draws_used"])[live], n_draws[live]), f"step {t}: draws consumed"
+        assert np.array_equal(_np(obs)[live], x["obs"][live]), f"step {t}: obs"
+        assert np.array_equal(_np(rew)[live], x["rewards"][live]), f"step {t}: rewards"
+        assert np.array_equal(_np(term)[live], x["terminated"][live]), f"step {t}: terminated"
+        assert np.array_equal(_np(trunc)[live], x["truncated"][live]), f"step {t}: truncated"
+        assert np.array_equal(_np(env.agent_pos)[live], x["pos"][live]), f"step {t}: agent positions"
+        assert np.array_equal(_np(env.collected_balls)[live], x["collected"][live]), f"step {t}: collected"
+        ni = env.num_agents * env.num_ball_types
+        assert np.array_equal(_np(env.pickups).reshape(len(live), -1)[live], x["info"][live][:, :ni]), f"step {t}: info"
+    assert env.status() == 0
+    env.close()
+
+
+def test_replay_at_65536_envs(cuda_device):
+    """BASELINE config 2 at full size: 256 reference traces x 50 steps tiled over 65 536 envs."""
+    stem = "collect_respawn_clustered"
+    g = load_golden(stem)
+    E, T, A = g["actions"].shape
+    tile = 65536 // E
+    env = _make(g, stem, E * tile, autoreset=False)
+    env.set_state_from_obs(np.concatenate([g["init_obs"]] * tile), np.concatenate([g["init_pos"]] * tile))
+    for t in range(T):
+        act, order, draws, n_draws, live = step_inputs(g, t, tile)
+        env.set_trace(order=order, draws=draws, n_draws=n_draws)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        if t % 7 == 0 or t == T - 1:
+            x = expected(g, t, tile)
+            assert np.array_equal(_np(obs), x["obs"]) and np.array_equal(_np(rew), x["rewards"])
+            assert np.array_equal(_np(trunc), x["truncated"]) and np.array_equal(_np(term), x["terminated"])
+    assert env.status() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("stem,n", [("collect_respawn_clustered", 4099), ("collect_respawn", 1000), ("collect_rooms_respawn", 777),
+                                    ("collect_quadrants15", 300), ("collect_single", 129), ("collect_even", 64)])
+def test_philox_mode_matches_oracle(stem, n, cuda_device):
+    """Production RNG mode: same Philox streams on both sides -> CUDA == oracle, incl. autoreset."""
+    g = load_golden(stem)
+    kw = collect_kwargs(g, stem)
+    env = _make(g, stem, n, autoreset=True, seed=2024, env_id_base=17)
+    env.enable_final_observation()
+    o = oc.CollectOracle(oc.make_collect_cfg(**kw), n)
+    r = oc.PhiloxRng(seed=2024, env_id_base=17)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(5)
+    steps = 120 if kw["time_limit"] else 210
+    for t in range(steps):
+        act = rng.integers(-1, 5, size=(n, env.num_agents)).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        oobs, orew, oterm, otrunc, ofin = o.step(act, r, autoreset=True, want_final_obs=True)
+        assert np.array_equal(_np(obs), oobs), f"step {t}: obs"
+        assert np.array_equal(_np(rew), orew), f"step {t}: rewards"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc), f"step {t}: flags"
+        done = oterm | otrunc
+        assert np.array_equal(_np(info["_final_observation"]), done)
+        assert np.array_equal(_np(info["final_observation"])[done], ofin[done]), f"step {t}: final obs"
+        assert np.array_equal(_np(env.grid), o.grid), f"step {t}: grids"
+        assert np.array_equal(_np(env.agent_pos), o.agent_pos)
+        assert np.array_equal(_np(env.step_count), o.step_count) and np.array_equal(_np(env.collected_balls), o.collected)
+        assert np.array_equal(_np(env.pickups).reshape(n, -1), o.info)
+    assert env.status() == 0
+    assert int(env.episode_count.min()) >= 2   # every env went through the on-device autoreset
+    env.close()
+
+
+def test_encode_matches_oracle_all_codes(cuda_device):
+    """Grid.encode kernel on every possible packed cell value, ragged size."""
+    g = load_golden("collect_respawn_clustered")
+    n = 1031
+    env = _make(g, "collect_respawn_clustered", n, autoreset=False)
+    cells = torch.randint(0, 256, (n, 100), dtype=torch.uint8, device=cuda_device)
+    cells[0, :] = torch.arange(100, dtype=torch.uint8)
+    cells[1, :] = torch.arange(156, 256, dtype=torch.uint8)
+    env.grid.copy_(cells)
+    out = torch.zeros((n, 10, 10, 3), dtype=torch.uint8, device=cuda_device)
+    env.encode(out)
+    assert np.array_equal(_np(out).reshape(n, 100, 3), oc.encode3(_np(cells)))
+    # unaligned output pointer -> plain-store path must give the same bytes
+    buf = torch.zeros(n * 300 + 1, dtype=torch.uint8, device=cuda_device)
+    env.encode(buf[1:].view(n, 10, 10, 3))
+    assert np.array_equal(_np(buf[1:]).reshape(n, 100, 3), oc.encode3(_np(cells)))
+    env.close()
+
+
+def test_step_host_matches_device_path(cuda_device):
+    g = load_golden("collect_respawn_clustered")
+    envs = [_make(g, "collect_respawn_clustered", 2051, autoreset=True, seed=9) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(3)
+    for t in range(60):
+        act = rng.integers(0, 4, size=(2051, 2)).astype(np.int8)
+        a = envs[0].step(torch.as_tensor(act, device=cuda_device))
+        b = envs[1].step(act)   # numpy in -> numpy out through mg_step_host
+        assert isinstance(b[0], np.ndarray)
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(_np(x), y)
+    for e in envs:
+        e.close()
+
+
+def test_properties_at_full_size(cuda_device):
+    """Size-independent invariants at 65 536 envs (BASELINE config 2), Philox mode, autoreset."""
+    import gym_multigrid_b200 as mg
+    n = 65536
+    env = mg.make_vec("multigrid-collect-respawn-clustered-v0", n, seed=1)
+    obs, _ = env.reset()
+    walls = torch.zeros((10, 10), dtype=torch.bool, device=cuda_device)
+    walls[0, :] = walls[-1, :] = walls[:, 0] = walls[:, -1] = True
+    gen = torch.Generator(device=cuda_device).manual_seed(0)
+    total_reward = torch.zeros((n, 2), dtype=torch.float64, device=cuda_device)
+    for t in range(1, 101):
+        act = torch.randint(0, 4, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8)
+        prev_pick = env.pickups.sum(dim=(1, 2)).clone()
+        obs, rew, term, trunc, info = env.step(act)
+        typ = obs[..., 0]
+        assert bool(((typ == 1) == walls).all()), "border walls intact, no wall elsewhere"
+        assert bool(((typ == 3).sum(dim=(1, 2)) == 2).all()), "exactly two agents visible"   # quadrant layouts: agents never co-located
+        assert bool(((typ == 2).sum(dim=(1, 2)) <= 15).all()), "balls never exceed 15 (respawn can only lose balls)"
+        assert bool((obs[..., 2][typ == 3] == 3).all()) and bool((obs[..., 2][typ != 3] == 0).all()), "state plane = dir 3 on agents only"
+        assert not bool(term.any()), "respawn variant never terminates"
+        assert bool((trunc == (t % 50 == 0)).all()), "TimeLimit 50 truncation, in lockstep"
+        if t % 50 != 0:
+            assert bool((rew.sum(1) == (env.pickups.sum(dim=(1, 2)) - prev_pick)).all()), "reward == pickups this step"
+            total_reward += rew
+        else:
+            assert int(env.step_count.max()) == 0 and int(env.pickups.abs().sum()) == 0, "autoreset cleared counters"
+            total_reward.zero_()
+    assert env.status() == 0
+    env.close()
+
+
+def test_single_env_adapter_matches_reference_trace(cuda_device):
+    """config 1: the gymnasium.make-style single env with the reference's signatures."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("collect_respawn_clustered")
+    env = mg.make("multigrid-collect-respawn-clustered-v0")
+    assert env.action_space.n == 4 and env.observation_space.shape == (10, 10, 3)
+    e = 3
+    env.vec.set_state_from_obs(g["init_obs"][e:e + 1], g["init_pos"][e:e + 1])
+    for t in range(int(g["length"][e])):
+        env.vec.set_trace(order=g["order"][e:e + 1, t], draws=g["draws"][e:e + 1, t], n_draws=g["n_draws"][e:e + 1, t])
+        obs, rew, term, trunc, info = env.step([int(a) for a in g["actions"][e, t]])
+        assert obs.dtype == np.uint8 and rew.dtype == np.float64 and isinstance(term, bool) and isinstance(trunc, bool)
+        assert np.array_equal(obs, g["obs"][e, t]) and np.array_equal(rew, g["rewards"][e, t])
+        assert term == bool(g["terminated"][e, t]) and trunc == bool(g["truncated"][e, t])
+        assert [info[k] for k in env.keys] == g["info"][e, t].tolist()
+    env.close()
+
+
+def test_create_rejects_bad_configs(cuda_device):
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    with pytest.raises(ValueError):
+        CollectVecEnv(4, size=2)
+    with pytest.raises(ValueError):
+        CollectVecEnv(4, size=10, num_balls=200)
+    with pytest.raises(ValueError):
+        CollectVecEnv(4, size=10, num_balls=16, layout="quadrants_respawn")
+    with pytest.raises(ValueError):
+        CollectVecEnv(4, device="cpu")
