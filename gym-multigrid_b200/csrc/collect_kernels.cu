@@ -10,6 +10,9 @@
 // blocking, respawn between pickup and move); finally all threads expand the packed cells to
 // the 3-byte (OBJECT_IDX, COLOR_IDX, STATE) encoding in shared memory and one thread issues
 // two TMA bulk stores: the obs slab (E * 3*W*H contiguous bytes) and the updated grid slab.
+#include <cstdlib>
+#include <type_traits>
+
 #include "mg_device.cuh"
 
 namespace mg {
@@ -35,7 +38,7 @@ __device__ __forceinline__ void place_obj(const CollectParams& p, uint8_t* g, Rn
 
 // CollectGameEnv._respawn (collect_game.py:129-130) / CollectGameQuadrantsRespawn._respawn (:401-409)
 template <int MODE>
-__device__ __noinline__ void respawn(const CollectParams& p, uint8_t* g, Rng<MODE>& r, int colour) {
+__device__ __forceinline__ int respawn(const CollectParams& p, uint8_t* g, Rng<MODE>& r, int colour) {
   int x, y;
   if (p.layout == MG_LAYOUT_QUADRANTS_RESPAWN) {
     const int q = colour < 3 ? colour : 0;
@@ -44,6 +47,7 @@ __device__ __noinline__ void respawn(const CollectParams& p, uint8_t* g, Rng<MOD
   } else {
     place_obj<MODE>(p, g, r, cell(T_BALL, colour, 0), 0, 0, p.W, p.H, x, y);
   }
+  return x * p.H + y;  // the cell that received the ball
 }
 
 // CollectGameEnv.reset (collect_game.py:107-119) + the layout's _gen_grid.  `g`, `pos` live in smem.
@@ -118,28 +122,37 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
   }
 }
 
-// shared-memory carve-up of one tile (all offsets 16-byte aligned because E % 16 == 0)
+// shared-memory carve-up of one tile.  Every array starts 16-byte aligned (E % 16 == 0) so that each
+// one can be the source / destination of a TMA bulk copy.
 struct TileSmem {
-  uint8_t* grid;   // [E][cells]
-  uint8_t* obs;    // [E][cells][3]
-  double* rew;     // [E][A]
-  uint8_t* pos;    // [E][A][2]
-  int8_t* act;     // [E][A]
-  uint8_t* ord;    // [E][A]
+  uint8_t* grid;   // [E][cells]          in+out
+  uint8_t* obs;    // [E][cells][3]       out
+  int4* hdr;       // [E]                 in+out
+  double* rew;     // [E][A]              out
+  uint8_t* pos;    // [E][A][2]           in+out
+  int8_t* act;     // [E][A]              in
+  uint8_t* ord;    // [E][A]              in (trace) / scratch (Philox)
+  uint8_t* term;   // [E]                 out
+  uint8_t* trunc;  // [E]                 out
   uint8_t* done;   // [E]
+  uint16_t* chg;   // [E][3A] cells written by the step (index x*H+y), for patching the pre-expanded obs
 };
 __host__ __device__ inline size_t tile_smem_bytes(int E, int cells, int A) {
-  return (size_t)E * cells * 4 + (size_t)E * A * 8 + (size_t)E * A * 4 + E + 16;
+  return (size_t)E * cells * 4 + (size_t)E * 16 + (size_t)E * A * 8 + (size_t)E * A * 4 + (size_t)E * 3 + (size_t)E * A * 6 + 16;
 }
 __device__ __forceinline__ TileSmem carve(uint8_t* base, int E, int cells, int A) {
   TileSmem s;
   s.grid = base;
   s.obs = base + (size_t)E * cells;
-  s.rew = reinterpret_cast<double*>(base + (size_t)E * cells * 4);
+  s.hdr = reinterpret_cast<int4*>(base + (size_t)E * cells * 4);
+  s.rew = reinterpret_cast<double*>(s.hdr + E);
   s.pos = reinterpret_cast<uint8_t*>(s.rew + (size_t)E * A);
   s.act = reinterpret_cast<int8_t*>(s.pos + (size_t)E * A * 2);
   s.ord = reinterpret_cast<uint8_t*>(s.act + (size_t)E * A);
-  s.done = s.ord + (size_t)E * A;
+  s.term = s.ord + (size_t)E * A;
+  s.trunc = s.term + E;
+  s.done = s.trunc + E;
+  s.chg = reinterpret_cast<uint16_t*>(s.done + E + (E & 1));
   return s;
 }
 
@@ -148,6 +161,7 @@ template <int THREADS>
 __device__ __forceinline__ void expand_tile(const uint8_t* s_grid, uint8_t* s_obs, int n16, int tid) {
   const uint4* in = reinterpret_cast<const uint4*>(s_grid);
   uint4* out = reinterpret_cast<uint4*>(s_obs);
+#pragma unroll 1
   for (int g = tid; g < n16; g += THREADS) {
     uint4 a, b, c;
     expand16(in[g], a, b, c);
@@ -155,15 +169,79 @@ __device__ __forceinline__ void expand_tile(const uint8_t* s_grid, uint8_t* s_ob
   }
 }
 
-// store `bytes` of the tile's obs from smem to global: TMA bulk for the 16-byte multiple, plain
-// byte stores for a ragged tail (last tile only) or when the caller's pointer is unaligned.
+// plain (non-TMA) copy of `bytes` starting at offset `from`: ragged last tile / unaligned caller pointers
 template <int THREADS>
-__device__ __forceinline__ void store_obs_tail(uint8_t* gdst, const uint8_t* s_obs, uint32_t bulk, uint32_t bytes, int tid) {
-  for (uint32_t i = bulk + tid; i < bytes; i += THREADS) gdst[i] = s_obs[i];
+__device__ __forceinline__ void copy_out_tail(uint8_t* gdst, const uint8_t* src, uint32_t from, uint32_t bytes, int tid) {
+  for (uint32_t i = from + tid; i < bytes; i += THREADS) gdst[i] = src[i];
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// CollectGameEnv.step for ONE env on its shared-memory grid (collect_game.py:183-211).
+// Returns the device error bits; h = {step_count, collected, rng_ctr, episodes}.
+template <int MODE>
+__device__ __forceinline__ int step_one_env(const CollectParams& p, long long e, uint8_t* g, uint8_t* pos, uint8_t* ord,
+                                            const int8_t* act, double* rew, int4& h, Rng<MODE>& r, bool& term, bool& trunc,
+                                            uint16_t* chg, int& nchg) {
+  const int A = p.A;
+  int err = 0;
+  if (MODE == 1) {  // production order: Fisher-Yates over Philox draws (trace mode replays np.random.permutation)
+    for (int i = 0; i < A; ++i) ord[i] = (uint8_t)i;
+    for (int i = A - 1; i > 0; --i) {
+      const int j = (int)__umulhi(r.u32(), (uint32_t)(i + 1));
+      const uint8_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
+    }
+  }
+  for (int i = 0; i < A; ++i) rew[i] = 0.0;  // :187
+  h.x += 1;                                  // step_count += 1 :190
+  for (int k = 0; k < A; ++k) {              // for i in order :191
+    const int i = ord[k];
+    const int a = act[i];
+    if (a < 0 || a > 3) continue;  // no branch of :192-207 matches: silently ignored
+    const int ox = pos[2 * i], oy = pos[2 * i + 1];
+    // north (0,-1) east (+1,0) south (0,+1) west (-1,0)  agent.py:230-264
+    const int nx = ox + (a == 1) - (a == 3), ny = oy + (a == 2) - (a == 0);
+    if (nx < 0 || ny < 0 || nx >= p.W || ny >= p.H) { err |= MG_ERR_OOB; continue; }
+    const uint8_t c = GCELL(g, p.H, nx, ny);
+    bool enter = (c == 0);                       // :178-181
+    if ((c & 3) == T_BALL) {                     // move_agent :169-177 -> _handle_pickup :132-147
+      const int colour = (c >> 2) & 15;
+      GCELL(g, p.H, nx, ny) = 0;                 // grid.set(*fwd_pos, None) :141
+      if (p.respawn) chg[nchg++] = (uint16_t)respawn<MODE>(p, g, r, colour);  // :142-143 -- may land on (nx, ny)
+      h.y += 1;                                  // collected_balls += 1 :144
+      rew[i] += p.reward_of_colour[colour];      // _reward(i, rewards, fwd_cell.reward) :145
+      const int t = p.type_of_colour[colour];
+      if (t >= 0) atomicAdd(&p.info[e * (A * p.nb) + p.nb * i + t], 1);  // info[keys[nb*i + ball_idx]] += 1 :147 (fire-and-forget RED)
+      enter = true;
+    }
+    if (enter) {  // wall / other agent: neither ball nor None -> blocked (:169-171)
+      GCELL(g, p.H, nx, ny) = p.agent_code[i];  // overwrites a respawn that landed here (ball lost)
+      GCELL(g, p.H, ox, oy) = 0;                // also erases a co-located partner from the grid
+      pos[2 * i] = (uint8_t)nx; pos[2 * i + 1] = (uint8_t)ny;
+      chg[nchg++] = (uint16_t)(nx * p.H + ny); chg[nchg++] = (uint16_t)(ox * p.H + oy);
+    }
+  }
+  term = !p.respawn && h.y == p.num_balls;  // :208-209
+  if (p.fixed_horizon) term = false;        // CollectGameRoomsFixedHorizon.step :368-370
+  trunc = h.x >= p.max_steps;               // :210-211
+  if (p.time_limit > 0 && h.x >= p.time_limit) trunc = true;  // gymnasium TimeLimit of the registration
+  return err | r.err;
+}
+
+// CTAs per SM the register allocation must allow: what the ~455 B/env shared-memory tile permits
+// (10x10 grid, A = 2), so that 65 536 envs are resident in a single wave.
+__host__ __device__ constexpr int min_blocks(int E, int threads) {
+  const int by_smem = (227 * 1024) / (E * 456 + 1024), by_threads = 2048 / threads;
+  return by_smem < by_threads ? (by_smem < 1 ? 1 : by_smem) : by_threads;
 }
 
 template <int MODE, int E, int THREADS>
-__global__ void __launch_bounds__(THREADS) collect_step_kernel(const __grid_constant__ CollectParams p) {
+__global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_kernel(const __grid_constant__ CollectParams p) {
+  static_assert(E % 16 == 0 && E <= THREADS, "tile must be a multiple of 16 envs and fit one thread per env");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, A = p.A, cells = p.cells;
@@ -171,136 +249,137 @@ __global__ void __launch_bounds__(THREADS) collect_step_kernel(const __grid_cons
   const long long e0 = (long long)blockIdx.x * E;
   const int n_here = (int)min((long long)E, p.N - e0);
   const uint32_t grid_bytes = (uint32_t)E * cells;
+  // the caller's per-env arrays are not padded: bulk copies only for full tiles with aligned pointers
+  const bool io_bulk = p.io_bulk_ok && n_here == E;
+  unsigned long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 8 : nullptr;
+  if (tl && tid == 0) tl[0] = globaltimer_ns();
 
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  pdl_launch_dependents();  // let the next launch in the stream get scheduled behind this one
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, grid_bytes);
-    tma_load_1d(s.grid, p.grid + e0 * cells, grid_bytes, &bar);  // grid plane is padded to whole tiles
+  pdl_wait();               // ... and do not touch global memory before the previous launch has fully completed
+  if (tid == 0) {  // every input of the tile arrives by TMA on one mbarrier (state planes are padded to whole tiles)
+    const uint32_t act_bytes = io_bulk ? (uint32_t)E * A : 0u;
+    mbar_expect_tx(&bar, grid_bytes + (uint32_t)E * 16 + (uint32_t)E * A * 2 + act_bytes);
+    tma_load_1d(s.grid, p.grid + e0 * cells, grid_bytes, &bar);
+    tma_load_1d(s.hdr, p.hdr + e0, (uint32_t)E * 16, &bar);
+    tma_load_1d(s.pos, p.agent_pos + e0 * A * 2, (uint32_t)E * A * 2, &bar);
+    if (io_bulk) tma_load_1d(s.act, p.actions + e0 * A, act_bytes, &bar);
   }
-  // small per-env arrays: coalesced cooperative loads while the TMA copy is in flight
-  for (int i = tid; i < n_here * A * 2; i += THREADS) s.pos[i] = p.agent_pos[e0 * A * 2 + i];
-  for (int i = tid; i < n_here * A; i += THREADS) {
-    s.act[i] = p.actions[e0 * A + i];
-    if (MODE == 0) s.ord[i] = p.order[e0 * A + i];
-  }
-  int4 h = make_int4(0, 0, 0, 0);
-  if (tid < n_here) h = p.hdr[e0 + tid];
+  if (!io_bulk)
+    for (int i = tid; i < n_here * A; i += THREADS) s.act[i] = p.actions[e0 * A + i];
+  if (MODE == 0)
+    for (int i = tid; i < n_here * A; i += THREADS) s.ord[i] = p.order[e0 * A + i];
   __syncthreads();
   mbar_wait(&bar, 0);
+  if (tl && tid == 0) tl[1] = globaltimer_ns();
 
-  // ---- one thread per env: the ordered agent loop (collect_game.py:183-211)
+  // ---- warps [0, E/32): one thread per env walks the ordered agent loop.
+  //      warps [E/32, ..): meanwhile expand the PRE-step grid (only the <= 3A cells a step writes can change;
+  //      they are patched below), which takes Grid.encode off the critical path of the tile.
+  constexpr bool OVERLAP = (THREADS - E) >= 64;
+  const int n16 = (int)(grid_bytes / 16);
   bool done = false;
-  int err = 0;
+  int err = 0, nchg = 0;
+  int4 h = make_int4(0, 0, 0, 0);
   Rng<MODE> r;
+  uint16_t* chg = s.chg + (size_t)(tid < E ? tid : 0) * 3 * A;
   if (tid < n_here) {
     const long long e = e0 + tid;
-    uint8_t* g = s.grid + (size_t)tid * cells;
-    uint8_t* pos = s.pos + tid * A * 2;
-    uint8_t* ord = s.ord + tid * A;
-    double* rew = s.rew + tid * A;
-    if (MODE == 0) {
-      r.open_trace(p.draws ? p.draws + e * p.K : nullptr, p.draws ? (p.n_draws ? p.n_draws[e] : p.K) : 0);
-    } else {
-      r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
-      for (int i = 0; i < A; ++i) ord[i] = (uint8_t)i;  // Fisher-Yates over Philox draws
-      for (int i = A - 1; i > 0; --i) {
-        const int j = (int)__umulhi(r.u32(), (uint32_t)(i + 1));
-        const uint8_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
-      }
-    }
-    for (int i = 0; i < A; ++i) rew[i] = 0.0;  // :187
-    h.x += 1;                                  // step_count += 1 :190
-    for (int k = 0; k < A; ++k) {              // for i in order :191
-      const int i = ord[k];
-      const int a = s.act[tid * A + i];
-      if (a < 0 || a > 3) continue;  // no branch of :192-207 matches: silently ignored
-      const int ox = pos[2 * i], oy = pos[2 * i + 1];
-      // north (0,-1) east (+1,0) south (0,+1) west (-1,0)  agent.py:230-264
-      const int nx = ox + (a == 1) - (a == 3), ny = oy + (a == 2) - (a == 0);
-      if (nx < 0 || ny < 0 || nx >= p.W || ny >= p.H) { err |= MG_ERR_OOB; continue; }
-      const uint8_t c = GCELL(g, p.H, nx, ny);
-      bool enter = (c == 0);                       // :178-181
-      if ((c & 3) == T_BALL) {                     // move_agent :169-177 -> _handle_pickup :132-147
-        const int colour = (c >> 2) & 15;
-        GCELL(g, p.H, nx, ny) = 0;                 // grid.set(*fwd_pos, None) :141
-        if (p.respawn) respawn<MODE>(p, g, r, colour);  // :142-143 -- may land on (nx, ny)
-        h.y += 1;                                  // collected_balls += 1 :144
-        rew[i] += p.reward_of_colour[colour];      // _reward(i, rewards, fwd_cell.reward) :145
-        const int t = p.type_of_colour[colour];
-        if (t >= 0) p.info[e * (A * p.nb) + p.nb * i + t] += 1;  // info[keys[nb*i + ball_idx]] :147 (rare RMW)
-        enter = true;
-      }
-      if (enter) {  // wall / other agent: neither ball nor None -> blocked (:169-171)
-        GCELL(g, p.H, nx, ny) = p.agent_code[i];  // overwrites a respawn that landed here (ball lost)
-        GCELL(g, p.H, ox, oy) = 0;                // also erases a co-located partner from the grid
-        pos[2 * i] = (uint8_t)nx; pos[2 * i + 1] = (uint8_t)ny;
-      }
-    }
-    bool term = !p.respawn && h.y == p.num_balls;  // :208-209
-    if (p.fixed_horizon) term = false;             // CollectGameRoomsFixedHorizon.step :368-370
-    bool trunc = h.x >= p.max_steps;               // :210-211
-    if (p.time_limit > 0 && h.x >= p.time_limit) trunc = true;  // gymnasium TimeLimit of the registration
-    p.terminated[e] = term; p.truncated[e] = trunc;
+    h = s.hdr[tid];
+    if (MODE == 0) r.open_trace(p.draws ? p.draws + e * p.K : nullptr, p.draws ? (p.n_draws ? p.n_draws[e] : p.K) : 0);
+    else r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
+    bool term, trunc;
+    err = step_one_env<MODE>(p, e, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, s.ord + tid * A, s.act + tid * A,
+                             s.rew + tid * A, h, r, term, trunc, chg, nchg);
+    s.term[tid] = term; s.trunc[tid] = trunc;
     if (MODE == 0 && p.draws_used) p.draws_used[e] = r.k;
-    err |= r.err;
     done = p.autoreset && (term || trunc);
+  } else if (OVERLAP && tid >= E && p.obs) {
+    expand_tile<THREADS - E>(s.grid, s.obs, n16, tid - E);
+  }
+  if (tl && tid == 0) tl[2] = globaltimer_ns();
+  if (tid < E) s.done[tid] = done;
+  const int any_done = __syncthreads_or(done);
+
+  if (p.obs) {
+    if (!OVERLAP) {
+      expand_tile<THREADS>(s.grid, s.obs, n16, tid);
+    } else if (tid < n_here) {  // patch the cells this env's step wrote
+      const uint8_t* g = s.grid + (size_t)tid * cells;
+      uint8_t* o = s.obs + (size_t)tid * cells * 3;
+      for (int k = 0; k < nchg; ++k) {
+        const int idx = chg[k];
+        const uint8_t c = g[idx];
+        o[3 * idx] = c & 3; o[3 * idx + 1] = (c >> 2) & 15; o[3 * idx + 2] = c >> 6;
+      }
+    }
   }
 
   // ---- rare path: same-step autoreset (gymnasium 0.29.1 VectorEnv semantics)
-  if (p.autoreset) {
-    if (tid < E) s.done[tid] = done;
-    if (__syncthreads_or(done)) {
-      if (p.final_obs) {  // terminal observation of the finished envs
-        expand_tile<THREADS>(s.grid, s.obs, (int)(grid_bytes / 16), tid);
-        __syncthreads();
-        for (int j = 0; j < n_here; ++j) {
-          if (!s.done[j]) continue;
-          uint8_t* dst = p.final_obs + (e0 + j) * 3 * cells;
-          const uint8_t* src = s.obs + (size_t)j * 3 * cells;
-          for (int i = tid; i < 3 * cells; i += THREADS) dst[i] = src[i];
-        }
-        __syncthreads();
+  if (any_done) {
+    __syncthreads();
+    if (p.final_obs && p.obs) {  // terminal observation of the finished envs (s.obs holds the post-step encoding)
+      for (int j = 0; j < n_here; ++j) {
+        if (!s.done[j]) continue;
+        uint8_t* dst = p.final_obs + (e0 + j) * 3 * cells;
+        const uint8_t* src = s.obs + (size_t)j * 3 * cells;
+        for (int i = tid; i < 3 * cells; i += THREADS) dst[i] = src[i];
       }
-      if (done) {
-        const long long e = e0 + tid;
-        if (MODE == 0) {
-          Rng<MODE> rr;
-          rr.open_trace(p.reset_draws ? p.reset_draws + e * p.R : nullptr,
-                        p.reset_draws ? (p.n_reset_draws ? p.n_reset_draws[e] : p.R) : 0);
-          reset_env<MODE>(p, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, rr);
-          if (p.reset_draws_used) p.reset_draws_used[e] = rr.k;
-          err |= rr.err;
-        } else {
-          reset_env<MODE>(p, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, r);
-        }
-        h.x = 0; h.y = 0; h.w += 1;  // step_count, collected_balls (:108, multigrid.py:141); episode counter
-        for (int k = 0; k < A * p.nb; ++k) p.info[e * (A * p.nb) + k] = 0;  // :109-116
-      }
+      __syncthreads();
     }
+    if (done) {
+      const long long e = e0 + tid;
+      Rng<MODE> rr;  // a copy: only this rarely-taken path hands the generator to a non-inlined function
+      if (MODE == 0)
+        rr.open_trace(p.reset_draws ? p.reset_draws + e * p.R : nullptr,
+                      p.reset_draws ? (p.n_reset_draws ? p.n_reset_draws[e] : p.R) : 0);
+      else
+        rr = r;
+      reset_env<MODE>(p, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, rr);
+      if (MODE == 0) { if (p.reset_draws_used) p.reset_draws_used[e] = rr.k; }
+      else r.ctr = rr.ctr;
+      err |= rr.err;
+      h.x = 0; h.y = 0; h.w += 1;  // step_count, collected_balls (:108, multigrid.py:141); episode counter
+      for (int k = 0; k < A * p.nb; ++k) p.info[e * (A * p.nb) + k] = 0;  // :109-116
+    }
+    __syncthreads();
+    if (p.obs) expand_tile<THREADS>(s.grid, s.obs, n16, tid);  // re-encode (the reset envs changed everywhere)
   }
   if (tid < n_here) {
     if (MODE == 1) h.z = (int)r.ctr;
-    p.hdr[e0 + tid] = h;
+    s.hdr[tid] = h;
     if (err) atomicOr(p.status, err);
   }
-  __syncthreads();
+  if (tl && tid == 0) tl[3] = globaltimer_ns();
 
-  // ---- all threads: Grid.encode of the tile, then TMA bulk stores
-  expand_tile<THREADS>(s.grid, s.obs, (int)(grid_bytes / 16), tid);
+  // ---- TMA bulk stores of every output of the tile
   fence_proxy_async_smem();
   __syncthreads();
+  if (tl && tid == 0) tl[4] = globaltimer_ns();
   const uint32_t obs_bytes = (uint32_t)n_here * 3 * cells;
-  const uint32_t bulk = (p.obs && p.obs_bulk_ok) ? (obs_bytes & ~15u) : 0u;
+  const uint32_t obs_bulk = (p.obs && p.obs_bulk_ok) ? (obs_bytes & ~15u) : 0u;
   if (tid == 0) {
+    if (obs_bulk) tma_store_1d(p.obs + e0 * 3 * cells, s.obs, obs_bulk);
     tma_store_1d(p.grid + e0 * cells, s.grid, grid_bytes);
-    if (bulk) tma_store_1d(p.obs + e0 * 3 * cells, s.obs, bulk);
+    tma_store_1d(p.hdr + e0, s.hdr, (uint32_t)E * 16);
+    tma_store_1d(p.agent_pos + e0 * A * 2, s.pos, (uint32_t)E * A * 2);
+    if (io_bulk) {
+      tma_store_1d(p.rewards + e0 * A, s.rew, (uint32_t)E * A * 8);
+      tma_store_1d(p.terminated + e0, s.term, (uint32_t)E);
+      tma_store_1d(p.truncated + e0, s.trunc, (uint32_t)E);
+    }
     tma_commit();
   }
-  if (p.obs) store_obs_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, bulk, obs_bytes, tid);
-  for (int i = tid; i < n_here * A; i += THREADS) p.rewards[e0 * A + i] = s.rew[i];
-  for (int i = tid; i < n_here * A * 2; i += THREADS) p.agent_pos[e0 * A * 2 + i] = s.pos[i];
-  if (tid == 0) tma_wait_read_all();  // shared memory must outlive the bulk reads
+  if (p.obs) copy_out_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, obs_bulk, obs_bytes, tid);
+  if (!io_bulk) {
+    for (int i = tid; i < n_here * A; i += THREADS) p.rewards[e0 * A + i] = s.rew[i];
+    for (int i = tid; i < n_here; i += THREADS) { p.terminated[e0 + i] = s.term[i]; p.truncated[e0 + i] = s.trunc[i]; }
+  }
+  if (tid == 0) {
+    tma_wait_read_all();  // shared memory must outlive the bulk reads
+    if (tl) tl[5] = globaltimer_ns();
+  }
 }
 
 // reset(mask): envs with mask[e] != 0 (or all when mask == NULL) are re-generated; obs (if given)
@@ -318,17 +397,17 @@ __global__ void __launch_bounds__(THREADS) collect_reset_kernel(const __grid_con
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bar, grid_bytes);
+    mbar_expect_tx(&bar, grid_bytes + (uint32_t)E * 16 + (uint32_t)E * A * 2);
     tma_load_1d(s.grid, p.grid + e0 * cells, grid_bytes, &bar);
+    tma_load_1d(s.hdr, p.hdr + e0, (uint32_t)E * 16, &bar);
+    tma_load_1d(s.pos, p.agent_pos + e0 * A * 2, (uint32_t)E * A * 2, &bar);
   }
-  for (int i = tid; i < n_here * A * 2; i += THREADS) s.pos[i] = p.agent_pos[e0 * A * 2 + i];
-  __syncthreads();
   mbar_wait(&bar, 0);
 
   if (tid < n_here) {
     const long long e = e0 + tid;
     if (!p.reset_mask || p.reset_mask[e]) {
-      int4 h = p.hdr[e];
+      int4 h = s.hdr[tid];
       Rng<MODE> r;
       if (MODE == 0)
         r.open_trace(p.reset_draws ? p.reset_draws + e * p.R : nullptr,
@@ -338,7 +417,7 @@ __global__ void __launch_bounds__(THREADS) collect_reset_kernel(const __grid_con
       reset_env<MODE>(p, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, r);
       h.x = 0; h.y = 0; h.w += 1;
       if (MODE == 1) h.z = (int)r.ctr;
-      p.hdr[e] = h;
+      s.hdr[tid] = h;
       for (int k = 0; k < A * p.nb; ++k) p.info[e * (A * p.nb) + k] = 0;
       if (MODE == 0 && p.reset_draws_used) p.reset_draws_used[e] = r.k;
       if (r.err) atomicOr(p.status, r.err);
@@ -349,14 +428,15 @@ __global__ void __launch_bounds__(THREADS) collect_reset_kernel(const __grid_con
   fence_proxy_async_smem();
   __syncthreads();
   const uint32_t obs_bytes = (uint32_t)n_here * 3 * cells;
-  const uint32_t bulk = (p.obs && p.obs_bulk_ok) ? (obs_bytes & ~15u) : 0u;
+  const uint32_t obs_bulk = (p.obs && p.obs_bulk_ok) ? (obs_bytes & ~15u) : 0u;
   if (tid == 0) {
+    if (obs_bulk) tma_store_1d(p.obs + e0 * 3 * cells, s.obs, obs_bulk);
     tma_store_1d(p.grid + e0 * cells, s.grid, grid_bytes);
-    if (bulk) tma_store_1d(p.obs + e0 * 3 * cells, s.obs, bulk);
+    tma_store_1d(p.hdr + e0, s.hdr, (uint32_t)E * 16);
+    tma_store_1d(p.agent_pos + e0 * A * 2, s.pos, (uint32_t)E * A * 2);
     tma_commit();
   }
-  if (p.obs) store_obs_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, bulk, obs_bytes, tid);
-  for (int i = tid; i < n_here * A * 2; i += THREADS) p.agent_pos[e0 * A * 2 + i] = s.pos[i];
+  if (p.obs) copy_out_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, obs_bulk, obs_bytes, tid);
   if (tid == 0) tma_wait_read_all();
 }
 
@@ -385,52 +465,95 @@ __global__ void __launch_bounds__(THREADS) encode3_kernel(const uint8_t* __restr
   const uint32_t obs_bytes = (uint32_t)n_here * 3 * cells;
   const uint32_t bulk = obs_bulk_ok ? (obs_bytes & ~15u) : 0u;
   if (tid == 0 && bulk) { tma_store_1d(obs + e0 * 3 * cells, s_obs, bulk); tma_commit(); }
-  store_obs_tail<THREADS>(obs + e0 * 3 * cells, s_obs, bulk, obs_bytes, tid);
+  copy_out_tail<THREADS>(obs + e0 * 3 * cells, s_obs, bulk, obs_bytes, tid);
   if (tid == 0) tma_wait_read_all();
 }
 
 // ------------------------------------------------------------------------------ launchers
-constexpr int kE = 64, kThreads = 128;
+// Tile variants (envs per CTA x threads per CTA); MG_TILE=<index> selects one at mg_create time.
+struct TileCfg { int E, threads; };
+static const TileCfg kTiles[] = {{64, 128}, {32, 64}, {64, 64}, {128, 128}, {128, 256}, {32, 128}, {16, 64}, {64, 192}, {64, 256}, {32, 96}};
+constexpr int kNumTiles = sizeof(kTiles) / sizeof(kTiles[0]);
+
+template <typename F>
+static cudaError_t for_tile(int v, F&& f) {
+  switch (v) {
+    case 0: return f(std::integral_constant<int, 64>{}, std::integral_constant<int, 128>{});
+    case 1: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 64>{});
+    case 2: return f(std::integral_constant<int, 64>{}, std::integral_constant<int, 64>{});
+    case 3: return f(std::integral_constant<int, 128>{}, std::integral_constant<int, 128>{});
+    case 4: return f(std::integral_constant<int, 128>{}, std::integral_constant<int, 256>{});
+    case 5: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 128>{});
+    case 6: return f(std::integral_constant<int, 16>{}, std::integral_constant<int, 64>{});
+    case 7: return f(std::integral_constant<int, 64>{}, std::integral_constant<int, 192>{});
+    case 8: return f(std::integral_constant<int, 64>{}, std::integral_constant<int, 256>{});
+    case 9: return f(std::integral_constant<int, 32>{}, std::integral_constant<int, 96>{});
+  }
+  return cudaErrorInvalidValue;
+}
+
+static bool pdl_enabled() {
+  static const bool on = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
 
 static cudaError_t set_smem(const void* fn, size_t bytes) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+int num_tile_variants() { return kNumTiles; }
+int tile_envs(int v) { return kTiles[v].E; }
+size_t tile_smem(int v, int cells, int A) { return tile_smem_bytes(kTiles[v].E, cells, A); }
+
 // once per handle (mg_create): opt every kernel in to the tile's dynamic shared memory size
-cudaError_t configure_kernels(int cells, int A) {
-  const size_t smem = tile_smem_bytes(kE, cells, A);
-  cudaError_t e;
-  if ((e = set_smem((const void*)collect_step_kernel<0, kE, kThreads>, smem)) != cudaSuccess) return e;
-  if ((e = set_smem((const void*)collect_step_kernel<1, kE, kThreads>, smem)) != cudaSuccess) return e;
-  if ((e = set_smem((const void*)collect_reset_kernel<0, kE, kThreads>, smem)) != cudaSuccess) return e;
-  if ((e = set_smem((const void*)collect_reset_kernel<1, kE, kThreads>, smem)) != cudaSuccess) return e;
-  return set_smem((const void*)encode3_kernel<kE, kThreads>, (size_t)kE * cells * 4);
+cudaError_t configure_kernels(int v, int cells, int A) {
+  return for_tile(v, [&](auto e, auto t) {
+    constexpr int E = decltype(e)::value, T = decltype(t)::value;
+    const size_t smem = tile_smem_bytes(E, cells, A);
+    cudaError_t r;
+    if ((r = set_smem((const void*)collect_step_kernel<0, E, T>, smem)) != cudaSuccess) return r;
+    if ((r = set_smem((const void*)collect_step_kernel<1, E, T>, smem)) != cudaSuccess) return r;
+    if ((r = set_smem((const void*)collect_reset_kernel<0, E, T>, smem)) != cudaSuccess) return r;
+    if ((r = set_smem((const void*)collect_reset_kernel<1, E, T>, smem)) != cudaSuccess) return r;
+    return set_smem((const void*)encode3_kernel<E, T>, (size_t)E * cells * 4);
+  });
 }
 
-cudaError_t launch_collect_step(const CollectParams& p, cudaStream_t st) {
-  const size_t smem = tile_smem_bytes(kE, p.cells, p.A);
-  const unsigned blocks = (unsigned)((p.N + kE - 1) / kE);
-  if (p.rng_mode == 0) collect_step_kernel<0, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
-  else collect_step_kernel<1, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+cudaError_t launch_collect_step(int v, const CollectParams& p, cudaStream_t st) {
+  return for_tile(v, [&](auto e, auto t) {
+    constexpr int E = decltype(e)::value, T = decltype(t)::value;
+    const size_t smem = tile_smem_bytes(E, p.cells, p.A);
+    const unsigned blocks = (unsigned)((p.N + E - 1) / E);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (p.rng_mode == 0) return cudaLaunchKernelEx(&cfg, collect_step_kernel<0, E, T>, p);
+    return cudaLaunchKernelEx(&cfg, collect_step_kernel<1, E, T>, p);
+  });
 }
 
-cudaError_t launch_collect_reset(const CollectParams& p, cudaStream_t st) {
-  const size_t smem = tile_smem_bytes(kE, p.cells, p.A);
-  const unsigned blocks = (unsigned)((p.N + kE - 1) / kE);
-  if (p.rng_mode == 0) collect_reset_kernel<0, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
-  else collect_reset_kernel<1, kE, kThreads><<<blocks, kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+cudaError_t launch_collect_reset(int v, const CollectParams& p, cudaStream_t st) {
+  return for_tile(v, [&](auto e, auto t) {
+    constexpr int E = decltype(e)::value, T = decltype(t)::value;
+    const size_t smem = tile_smem_bytes(E, p.cells, p.A);
+    const unsigned blocks = (unsigned)((p.N + E - 1) / E);
+    if (p.rng_mode == 0) collect_reset_kernel<0, E, T><<<blocks, T, smem, st>>>(p);
+    else collect_reset_kernel<1, E, T><<<blocks, T, smem, st>>>(p);
+    return cudaGetLastError();
+  });
 }
 
-cudaError_t launch_encode3(const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st) {
-  const size_t smem = (size_t)kE * cells * 4;
-  const unsigned blocks = (unsigned)((N + kE - 1) / kE);
-  encode3_kernel<kE, kThreads><<<blocks, kThreads, smem, st>>>(grid, obs, N, cells, obs_bulk_ok);
-  return cudaGetLastError();
+cudaError_t launch_encode3(int v, const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st) {
+  return for_tile(v, [&](auto e, auto t) {
+    constexpr int E = decltype(e)::value, T = decltype(t)::value;
+    const size_t smem = (size_t)E * cells * 4;
+    const unsigned blocks = (unsigned)((N + E - 1) / E);
+    encode3_kernel<E, T><<<blocks, T, smem, st>>>(grid, obs, N, cells, obs_bulk_ok);
+    return cudaGetLastError();
+  });
 }
-
-int tile_envs() { return kE; }
-size_t tile_smem(int cells, int A) { return tile_smem_bytes(kE, cells, A); }
 
 }  // namespace mg

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -13,17 +14,19 @@
 #include "mg_device.cuh"
 
 namespace mg {
-cudaError_t launch_collect_step(const CollectParams& p, cudaStream_t st);
-cudaError_t launch_collect_reset(const CollectParams& p, cudaStream_t st);
-cudaError_t launch_encode3(const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st);
-int tile_envs();
-cudaError_t configure_kernels(int cells, int A);
-size_t tile_smem(int cells, int A);
+cudaError_t launch_collect_step(int v, const CollectParams& p, cudaStream_t st);
+cudaError_t launch_collect_reset(int v, const CollectParams& p, cudaStream_t st);
+cudaError_t launch_encode3(int v, const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st);
+int num_tile_variants();
+int tile_envs(int v);
+cudaError_t configure_kernels(int v, int cells, int A);
+size_t tile_smem(int v, int cells, int A);
 }  // namespace mg
 
 struct mg_env {
   mg_config cfg;
   int device;
+  int tile;  // kernel tile variant (envs per CTA x threads), MG_TILE env var, default 0
   long long n_pad;
   size_t plane_off[MG_PLANE_COUNT], plane_bytes[MG_PLANE_COUNT], plane_row[MG_PLANE_COUNT], state_bytes;
   mg::CollectParams base;  // rules + constants; pointers filled per call
@@ -33,6 +36,7 @@ struct mg_env {
   // staging for the *_host entry points (allocated on first use)
   int8_t* d_actions; uint8_t* d_obs; double* d_rewards; uint8_t* d_term; uint8_t* d_trunc; uint8_t* d_final;
   long long launches;
+  unsigned long long* timeline;
   std::string err;
 };
 
@@ -99,21 +103,28 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
-  if (mg::tile_smem(W * H, A) > (size_t)prop.sharedMemPerBlockOptin)
-    return fail(nullptr, "mg_create: grid too large for the shared-memory tile (W*H*4*64 bytes must fit 227 KB)");
+  int tile = 0;
+  if (const char* tv = std::getenv("MG_TILE")) tile = std::atoi(tv);
+  if (tile < 0 || tile >= mg::num_tile_variants()) return fail(nullptr, "mg_create: MG_TILE out of range");
+  // large grids: fall back to the smallest tile that fits the 227 KB of shared memory
+  while (mg::tile_smem(tile, W * H, A) > (size_t)prop.sharedMemPerBlockOptin && tile != 6) tile = (tile == 0 ? 5 : 6);
+  if (mg::tile_smem(tile, W * H, A) > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(nullptr, "mg_create: grid too large for the shared-memory tile (16 envs x 4*W*H bytes must fit 227 KB)");
 
-  if ((ce = mg::configure_kernels(W * H, A)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute(max dynamic shared memory)", ce);
+  if ((ce = mg::configure_kernels(tile, W * H, A)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute(max dynamic shared memory)", ce);
 
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");
   env->cfg = *cfg;
   env->device = device;
+  env->tile = tile;
   env->has_trace = false;
   env->launches = 0;
+  env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr;
   env->d_term = nullptr; env->d_trunc = nullptr; env->d_final = nullptr;
   std::memset(&env->trace, 0, sizeof env->trace);
-  const int E = mg::tile_envs();
+  const int E = mg::tile_envs(tile);
   env->n_pad = (cfg->num_envs + E - 1) / E * E;
   const size_t rows[MG_PLANE_COUNT] = {(size_t)W * H, (size_t)A * 2, 16, (size_t)A * nb * 4};
   size_t off = 0;
@@ -204,13 +215,14 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   bind_state(env, p, state);
   bind_trace(env, p);
   p.reset_mask = mask; p.obs = obs; p.obs_bulk_ok = aligned16(obs);
-  if ((ce = mg::launch_collect_reset(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "collect_reset_kernel", ce);
+  if ((ce = mg::launch_collect_reset(env->tile, p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "collect_reset_kernel", ce);
   env->launches += 1;
   return 0;
 }
 
 static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
+  if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
   bind_trace(env, p);
@@ -218,8 +230,10 @@ static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStrea
   p.actions = io->actions; p.obs = io->obs; p.rewards = io->rewards;
   p.terminated = io->terminated; p.truncated = io->truncated; p.final_obs = io->final_obs;
   p.obs_bulk_ok = aligned16(io->obs);
+  p.io_bulk_ok = aligned16(io->actions) && aligned16(io->rewards) && aligned16(io->terminated) && aligned16(io->truncated);
+  p.timeline = env->timeline;
   cudaError_t ce;
-  if ((ce = mg::launch_collect_step(p, st)) != cudaSuccess) return cuda_fail(env, "collect_step_kernel", ce);
+  if ((ce = mg::launch_collect_step(env->tile, p, st)) != cudaSuccess) return cuda_fail(env, "collect_step_kernel", ce);
   env->launches += 1;
   return 0;
 }
@@ -237,7 +251,7 @@ extern "C" int mg_encode(mg_env* env, const void* state, uint8_t* obs, void* str
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   const uint8_t* grid = static_cast<const uint8_t*>(state) + env->plane_off[MG_PLANE_GRID];
-  if ((ce = mg::launch_encode3(grid, obs, env->cfg.num_envs, env->cfg.width * env->cfg.height, aligned16(obs),
+  if ((ce = mg::launch_encode3(env->tile, grid, obs, env->cfg.num_envs, env->cfg.width * env->cfg.height, aligned16(obs),
                                static_cast<cudaStream_t>(stream))) != cudaSuccess)
     return cuda_fail(env, "encode3_kernel", ce);
   env->launches += 1;
@@ -286,5 +300,13 @@ extern "C" int mg_status(mg_env* env, void* stream, int32_t* status_out) {
   if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
   return 0;
 }
+
+extern "C" int mg_debug_set_timeline(mg_env* env, uint64_t* timeline_dev) {
+  if (!env) return -1;
+  env->timeline = reinterpret_cast<unsigned long long*>(timeline_dev);
+  return 0;
+}
+
+extern "C" int mg_tile_envs(const mg_env* env) { return env ? mg::tile_envs(env->tile) : -1; }
 
 extern "C" int64_t mg_launch_count(const mg_env* env) { return env ? env->launches : 0; }

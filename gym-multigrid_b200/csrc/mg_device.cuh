@@ -57,7 +57,9 @@ struct CollectParams {
   int32_t* draws_used;
   int32_t* reset_draws_used;
   int32_t* status;
-  int obs_bulk_ok;        // obs / final_obs base pointers are 16-byte aligned
+  int obs_bulk_ok;        // obs base pointer is 16-byte aligned
+  int io_bulk_ok;         // actions / rewards / terminated / truncated pointers are 16-byte aligned
+  unsigned long long* timeline;  // optional [tiles][8] per-CTA phase timestamps (globaltimer ns), profiling only
 };
 
 // ------------------------------------------------------------------------ Philox4x32-10
@@ -150,6 +152,11 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Programmatic dependent launch (PDL): the next kernel in the stream may be scheduled while this one
+// drains; it blocks in pdl_wait() until every prerequisite grid has completed and flushed its writes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- encode
 // Grid.encode, encode_dim 3 (grid.py:223-252 + object.py:58-74 + agent.py:119-126):

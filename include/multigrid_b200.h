@@ -133,6 +133,12 @@ int mg_set_trace(mg_env* env, const mg_trace* trace_dev);
 /* device status word: read (synchronises the stream) and clear */
 int mg_status(mg_env* env, void* stream, int32_t* status_out);
 
+/* Profiling hooks (no reference counterpart).  mg_debug_set_timeline: device buffer u64[tiles][8]; each
+ * CTA of the step kernel records globaltimer ns at {start, inputs landed, stepped, autoreset done,
+ * encoded, stores drained}; NULL switches it off.  mg_tile_envs: envs per CTA tile (N_pad granule). */
+int mg_debug_set_timeline(mg_env* env, uint64_t* timeline_dev);
+int mg_tile_envs(const mg_env* env);
+
 /* number of kernel launches issued through this handle since creation */
 int64_t mg_launch_count(const mg_env* env);
 
