@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--timeline", action="store_true")
     ap.add_argument("--autoreset", type=int, default=1)
+    ap.add_argument("--time-limit", type=int, default=None, help="override max_episode_steps (1 = every step autoresets)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n, B = args.num_envs, args.batches
@@ -67,7 +68,8 @@ def main():
 
     for tile in [int(t) for t in args.tiles.split(",")]:
         os.environ["MG_TILE"] = str(tile)
-        envs = [mg.make_vec(ENV_ID, n, device=dev, seed=0, autoreset=bool(args.autoreset), env_id_base=b * n) for b in range(B)]
+        extra = {} if args.time_limit is None else {"max_episode_steps": args.time_limit}
+        envs = [mg.make_vec(ENV_ID, n, device=dev, seed=0, autoreset=bool(args.autoreset), env_id_base=b * n, **extra) for b in range(B)]
         gen = torch.Generator(device=dev).manual_seed(1)
         acts = [torch.randint(0, 4, (n, 2), generator=gen, device=dev, dtype=torch.int8) for _ in range(B)]
         for e in envs:
