@@ -26,8 +26,8 @@ __device__ __forceinline__ void place_obj(const CollectParams& p, uint8_t* g, Rn
                                           int sx, int sy, int& ox, int& oy) {
   const int hx = min(tx + sx, p.W - 1), hy = min(ty + sy, p.H - 1);
   for (;;) {
-    const int x = r.rand_int(tx, hx);
-    const int y = r.rand_int(ty, hy);
+    int x, y;
+    r.rand_pair(tx, hx, ty, hy, x, y);
     ox = x; oy = y;
     if (MODE == 0 && (r.err & MG_ERR_TRACE_OVERFLOW)) return;  // trace exhausted: leave the grid untouched
     if (GCELL(g, p.H, x, y) != 0) continue;
@@ -54,9 +54,15 @@ __device__ __forceinline__ int respawn(const CollectParams& p, uint8_t* g, Rng<M
 template <int MODE>
 __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8_t* pos, Rng<MODE>& r) {
   const int W = p.W, H = p.H, A = p.A, nb = p.nb;
-  for (int i = 0; i < p.cells; ++i) g[i] = 0;
-  for (int i = 0; i < W; ++i) { GCELL(g, H, i, 0) = WALL_GREY; GCELL(g, H, i, H - 1) = WALL_GREY; }  // horz_wall grid.py:66-78
-  for (int j = 0; j < H; ++j) { GCELL(g, H, 0, j) = WALL_GREY; GCELL(g, H, W - 1, j) = WALL_GREY; }  // vert_wall grid.py:80-89
+  // Grid(width, height) + border walls (+ the Rooms inner walls): copied from the handle's template
+  // (grid.py:66-89; collect_game.py:239-243, 269-273, 309-320, 379-382)
+  if ((p.cells & 3) == 0) {
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(p.wall_template);
+    uint32_t* g32 = reinterpret_cast<uint32_t*>(g);
+    for (int i = 0; i < p.cells / 4; ++i) g32[i] = __ldg(t32 + i);
+  } else {
+    for (int i = 0; i < p.cells; ++i) g[i] = __ldg(p.wall_template + i);
+  }
   int x, y;
   if (p.layout == MG_LAYOUT_EVEN_DIST) {  // collect_game.py:236-259
     const int per = p.num_balls / nb;
@@ -78,11 +84,7 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
       pos[2 * i] = (uint8_t)(1 + i); pos[2 * i + 1] = (uint8_t)(H - 2);
     }
   } else if (p.layout == MG_LAYOUT_ROOMS) {  // collect_game.py:306-362 (`width` on both axes)
-    const int ws = W / 2 - 1, m = W / 2;
-    for (int i = 0; i < ws; ++i) {
-      GCELL(g, H, i, m) = WALL_GREY; GCELL(g, H, W - ws + i, m) = WALL_GREY;
-      GCELL(g, H, m, i) = WALL_GREY; GCELL(g, H, m, W - ws + i) = WALL_GREY;
-    }
+    const int m = W / 2;
     for (int i = 0; i < A; ++i) {  // _rand_elem(possible_coords) -> _rand_int(0, 4)
       const int k = r.rand_int(0, 4);
       const int cx = k == 0 ? m : (k <= 2 ? m - 1 : m + 1);
@@ -92,10 +94,10 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
     }
     const int ps = W / 2 - 1;
     const int num_ball = (int)nearbyint((double)p.num_balls / nb);  // python round(): half-to-even
-    int index = 0, tx = 0, ty = 0;
-    for (int ball = 0; ball < p.num_balls; ++ball) {
-      if (ball % num_ball == 0) {
-        index = ball / num_ball;
+    int index = -1, tx = 0, ty = 0, left = 0;
+    for (int ball = 0; ball < p.num_balls; ++ball, --left) {
+      if (left == 0) {  // ball % num_ball == 0
+        ++index; left = num_ball;
         tx = (index == 1 || index == 2) ? m + 1 : 0;
         ty = (index == 1 || index == 3) ? m + 1 : 0;
         // the extra ball of this colour in partition 3 (:349-355)
@@ -105,13 +107,14 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
     }
   } else {  // MG_LAYOUT_QUADRANTS_RESPAWN, collect_game.py:376-399
     const int per = p.num_balls / 3;
-    int index = 0, tx = 0, ty = 0;
+    int index = -1, tx = 0, ty = 0, left = 0;
     for (int ball = 0; ball < p.num_balls; ++ball) {
-      if (ball % per == 0) {
-        index = ball / per;
+      if (left == 0) {  // ball % per == 0
+        ++index; left = per;
         tx = index == 0 ? 0 : W / 2 - 1;
         ty = index == 1 ? H / 2 - 1 : 0;
       }
+      --left;
       // Ball(self.world, index, 1): the colour IS the partition index (:391)
       place_obj<MODE>(p, g, r, cell(T_BALL, index, 0), tx, ty, W / 2 + 1, H / 2 + 1, x, y);
     }

@@ -33,6 +33,7 @@ struct mg_env {
   mg_trace trace;
   bool has_trace;
   int32_t* d_status;
+  uint8_t* d_wall_template;
   // staging for the *_host entry points (allocated on first use)
   int8_t* d_actions; uint8_t* d_obs; double* d_rewards; uint8_t* d_term; uint8_t* d_trunc; uint8_t* d_final;
   long long launches;
@@ -155,6 +156,21 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   if ((ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess) { delete env; return cuda_fail(nullptr, "cudaMalloc(status)", ce); }
   if ((ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) { cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "cudaMemset(status)", ce); }
   p.status = env->d_status;
+  {  // the layout's walls on an empty grid, index x*H + y (grid.py:66-89; collect_game.py:309-320 for Rooms)
+    std::string t((size_t)W * H, '\0');
+    auto set = [&](int x, int y) { t[(size_t)x * H + y] = (char)mg::WALL_GREY; };
+    for (int i = 0; i < W; ++i) { set(i, 0); set(i, H - 1); }
+    for (int j = 0; j < H; ++j) { set(0, j); set(W - 1, j); }
+    if (cfg->layout == MG_LAYOUT_ROOMS) {
+      const int ws = W / 2 - 1, m = W / 2;
+      for (int i = 0; i < ws; ++i) { set(i, m); set(W - ws + i, m); set(m, i); set(m, W - ws + i); }
+    }
+    if ((ce = cudaMalloc(&env->d_wall_template, t.size())) != cudaSuccess ||
+        (ce = cudaMemcpy(env->d_wall_template, t.data(), t.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "wall template upload", ce);
+    }
+    p.wall_template = env->d_wall_template;
+  }
   *out = env;
   return 0;
 }
@@ -163,6 +179,7 @@ extern "C" int mg_destroy(mg_env* env) {
   if (!env) return 0;
   cudaSetDevice(env->device);
   cudaFree(env->d_status);
+  cudaFree(env->d_wall_template);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_rewards);
   cudaFree(env->d_term); cudaFree(env->d_trunc); cudaFree(env->d_final);
   delete env;

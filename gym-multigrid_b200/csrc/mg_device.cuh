@@ -37,6 +37,7 @@ struct CollectParams {
   uint8_t* agent_pos;     // [N_pad][A][2]
   int4* hdr;              // [N_pad] {step_count, collected, rng_ctr, episodes}
   int32_t* info;          // [N_pad][A*nb]
+  const uint8_t* wall_template;  // [cells] handle-owned: the layout's walls on an empty grid (reset starts from it)
   // io
   const int8_t* actions;
   uint8_t* obs;
@@ -110,6 +111,19 @@ struct Rng {
       return v;
     } else {
       return lo + (int)__umulhi(u32(), (uint32_t)(hi - lo + 1));
+    }
+  }
+  // One placement candidate (x, y) of place_obj (multigrid.py:316-321: x is drawn before y).
+  // Trace mode replays the two recorded randint outputs; Philox mode spends ONE 32-bit word per
+  // candidate (x from the low half, y from the high half), i.e. four candidates per Philox block.
+  __device__ __forceinline__ void rand_pair(int lox, int hix, int loy, int hiy, int& x, int& y) {
+    if (MODE == 0) {
+      x = rand_int(lox, hix);
+      y = rand_int(loy, hiy);
+    } else {
+      const uint32_t w = u32();
+      x = lox + (int)(((w & 0xFFFFu) * (uint32_t)(hix - lox + 1)) >> 16);
+      y = loy + (int)(((w >> 16) * (uint32_t)(hiy - loy + 1)) >> 16);
     }
   }
 };

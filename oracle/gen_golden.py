@@ -99,8 +99,73 @@ def gen_collect():
               f"steps={int(packed['length'].sum())}, {os.path.getsize(path)/1024:.0f} KiB")
 
 
+MAZE_MAP = os.path.join(rh.REFERENCE_ROOT, "tests", "assets", "board_maze.txt")
+CTF_MAP = os.path.join(rh.REFERENCE_ROOT, "tests", "assets", "board.txt")
+
+
+def make_maze64(seed=0, size=64, density=0.2):
+    """SURVEY 8(d) config 4 map: obstacle border, random obstacles (density 0.2), one flag; MazeWorld codes."""
+    rng = np.random.default_rng(seed)
+    m = (rng.random((size, size)) < density).astype(np.int64) * 3
+    m[0, :] = m[-1, :] = m[:, 0] = m[:, -1] = 3
+    free = np.argwhere(m == 0)
+    fx, fy = free[rng.integers(len(free))]
+    m[fx, fy] = 2
+    return m
+
+
+def gen_maze():
+    import tempfile
+    plans = [("maze_board13", MAZE_MAP, 0.0, 24), ("maze_board13_penalty", MAZE_MAP, 0.5, 24)]
+    tmp = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
+    np.savetxt(tmp.name, make_maze64().T, fmt="%d")   # load_text_map transposes (utils/map.py:37)
+    plans += [("maze_gen64", tmp.name, 0.0, 6), ("maze_gen64_penalty", tmp.name, 0.5, 6)]
+    for stem, path, pen, episodes in plans:
+        eps = [rh.record_maze_episode(path, seed, np.random.default_rng(2000 + seed), pen) for seed in range(episodes)]
+        for e in eps:
+            assert e["obs"].dtype == np.float64   # the reference's dtype (maze.py:246); values are small integers
+            e["obs"] = e["obs"].astype(np.uint8)
+            e["init_obs"] = e["init_obs"].astype(np.uint8)
+            e["start_index"] = np.array(e["start_index"], np.int32)
+        out = rh.pack_episodes(eps, ["actions", "obs", "reward", "terminated", "truncated", "pos", "dir", "info"],
+                               ["field_map", "init_obs", "start_index", "init_info"])
+        out["field_map"] = out["field_map"][0].astype(np.uint8)
+        out["meta_obstacle_penalty_ratio"] = np.array(pen)
+        out["meta_ref_obs_dtype"] = np.array("float64")
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, terminated={int(out['terminated'].any(1).sum())}, "
+              f"{os.path.getsize(path_out)/1024:.0f} KiB")
+    os.unlink(tmp.name)
+
+
+def gen_ctf():
+    plans = [("ctf_2v2", 2, 2, 0.0, 32), ("ctf_3v4", 3, 4, 0.0, 12), ("ctf_2v2_penalty", 2, 2, 0.5, 12), ("ctf_1v1", 1, 1, 0.0, 8)]
+    for stem, nb, nr, pen, episodes in plans:
+        eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, np.random.default_rng(3000 + seed), nb, nr, pen) for seed in range(episodes)]
+        for e in eps:
+            assert e["obs"].dtype == np.int64     # the reference's dtype (ctf.py:1138)
+            e["obs"] = e["obs"].astype(np.uint8)
+            e["init_obs"] = e["init_obs"].astype(np.uint8)
+        out = rh.pack_episodes(eps, ["actions", "red_actions", "order", "n_battles", "blue_win", "obs", "reward", "terminated",
+                                     "truncated", "pos", "dir", "dead"],
+                               ["field_map", "init_obs", "init_pos", "init_dir", "blue_place", "red_place"])
+        out["field_map"] = out["field_map"][0].astype(np.uint8)
+        out["meta_num_blue"], out["meta_num_red"] = np.array(nb), np.array(nr)
+        out["meta_obstacle_penalty_ratio"] = np.array(pen)
+        out["meta_ref_obs_dtype"] = np.array("int64")
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, battles={int(out['n_battles'].sum())}, "
+              f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf"]
     if "collect" in which:
         gen_collect()
+    if "maze" in which:
+        gen_maze()
+    if "ctf" in which:
+        gen_ctf()

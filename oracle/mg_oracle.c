@@ -67,6 +67,19 @@ static int rng_int(rng_t* r, int lo, int hi) {
   return lo + (int)(((uint64_t)rng_u32(r) * (uint32_t)(hi - lo + 1)) >> 32);
 }
 
+/* One placement candidate of place_obj (multigrid.py:316-321, x before y).  Trace mode replays the two
+ * recorded randint outputs; Philox mode spends one 32-bit word per candidate (x low half, y high half). */
+static void rng_pair(rng_t* r, int lox, int hix, int loy, int hiy, int* x, int* y) {
+  if (r->mode == 0) {
+    *x = rng_int(r, lox, hix);
+    *y = rng_int(r, loy, hiy);
+  } else {
+    uint32_t w = rng_u32(r);
+    *x = lox + (int)(((w & 0xFFFFu) * (uint32_t)(hix - lox + 1)) >> 16);
+    *y = loy + (int)(((w >> 16) * (uint32_t)(hiy - loy + 1)) >> 16);
+  }
+}
+
 /* -------------------------------------------------------------------------------- encode */
 void oc_encode3(const uint8_t* cells, int64_t n, uint8_t* obs) {
   /* Grid.encode (grid.py:223-252): None -> (empty=0,0,0); WorldObj.encode (object.py:58-74) ->
@@ -91,8 +104,8 @@ static void place_obj(const oc_collect_cfg* c, uint8_t* g, rng_t* r, uint8_t cod
   if (ty < 0) ty = 0;
   int hx = tx + sx < W - 1 ? tx + sx : W - 1, hy = ty + sy < H - 1 ? ty + sy : H - 1;
   for (;;) {
-    int x = rng_int(r, tx, hx);
-    int y = rng_int(r, ty, hy);
+    int x, y;
+    rng_pair(r, tx, hx, ty, hy, &x, &y);
     if (r->err & OC_ERR_TRACE_OVERFLOW) { *ox = x; *oy = y; return; } /* leave the grid untouched */
     if (CELL(g, H, x, y) != 0) continue;
     CELL(g, H, x, y) = code;

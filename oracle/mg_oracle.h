@@ -5,7 +5,7 @@
  * (gym-multigrid_b200/ + include/multigrid_b200.h) never links, imports or calls it.
  *
  * Parity pin: every function here is checked bit-for-bit against traces recorded from
- * the unmodified reference (oracle/gen_golden.py -> tests/golden/*.npz, replayed by
+ * the unmodified reference (oracle/gen_golden.py -> tests/golden/ (npz files), replayed by
  * tests/test_oracle_golden.py).  The reference ships no golden vectors of its own
  * (SURVEY.md section 4), so those recorded traces are the pin.
  *
@@ -100,6 +100,75 @@ int oc_collect_step(const oc_collect_cfg* cfg, int64_t N, oc_collect_state* st, 
                     const oc_rng_src* rng, uint8_t* obs, double* rewards, uint8_t* terminated,
                     uint8_t* truncated, int autoreset, const oc_rng_src* reset_rng, uint8_t* final_obs,
                     int32_t* status, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
+
+/* ===================================================================== Maze and Capture-the-Flag
+ * Both run on a static text map (utils/map.py:22-39: field_map = np.loadtxt(path).T, indexed
+ * [x][y]); per-env state is only the agents.  Square maps only (the reference mixes width/height,
+ * maze.py:68-70 vs :184-186). */
+#ifndef MG_ORACLE_MAP_H
+#define MG_ORACLE_MAP_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_MAX_CTF_AGENTS 16
+#define OC_MAX_BATTLES 64
+
+typedef struct {
+  int32_t size;                /* W == H */
+  const uint8_t* field_map;    /* [W*H] index x*H + y */
+  /* maze (maze.py:31-40): products formed by the caller in double exactly as the reference does */
+  double flag_reward, obstacle_penalty, step_penalty;
+  int32_t max_steps;
+  /* ctf (ctf.py:662-679) */
+  int32_t num_blue, num_red;
+  double battle_range, randomness, battle_reward;
+} oc_map_cfg;
+
+typedef struct {
+  uint8_t* pos;        /* [N][n][2] (x, y) */
+  uint8_t* dir;        /* [N][n] */
+  uint8_t* flags;      /* [N][n] bit0 = terminated (defeated), bit1 = collided  (ctf only) */
+  int32_t* step_count; /* [N] */
+  uint32_t* rng_ctr;   /* [N] */
+} oc_map_state;
+
+typedef struct {
+  int32_t mode;               /* 0 trace, 1 philox */
+  /* maze reset: np.random.randint(0, len(background)) output (maze.py:204) */
+  const int32_t* start_index; /* [N] */
+  /* ctf reset: np_random.choice(len(territory), k, replace=False) outputs (ctf.py:1034, 1041) */
+  const int32_t* blue_place;  /* [N][num_blue] */
+  const int32_t* red_place;   /* [N][num_red] */
+  /* ctf step: RwPolicy integers(0,5) (heuristic.py:72), np_random.shuffle (ctf.py:1245), battle choice (:1393-1403) */
+  const int8_t* red_actions;  /* [N][num_red] */
+  const uint8_t* order;       /* [N][n] */
+  const uint8_t* blue_win;    /* [N][KB] */
+  int32_t KB;
+  int32_t* battles_used;      /* [N] out, may be NULL */
+  uint64_t seed, env_id_base;
+} oc_map_rng;
+
+/* MazeSingleAgentEnv (maze.py).  obs: u8 [N][W][H] "map" codes (the reference returns the same values as float64). */
+int oc_maze_reset(const oc_map_cfg* c, int64_t N, oc_map_state* st, const uint8_t* mask, const oc_map_rng* rng,
+                  uint8_t* obs, int32_t* status);
+int oc_maze_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* actions, const oc_map_rng* rng,
+                 uint8_t* obs, double* reward, uint8_t* terminated, uint8_t* truncated, int autoreset,
+                 uint8_t* final_obs, int32_t* status);
+
+/* CtFMvNEnv (ctf.py:657-1433).  obs: u8 [N][H][W] "map" codes = _encode_map().T (the reference returns int64). */
+int oc_ctf_reset(const oc_map_cfg* c, int64_t N, oc_map_state* st, const uint8_t* mask, const oc_map_rng* rng,
+                 uint8_t* obs, int32_t* status);
+int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* blue_actions, const oc_map_rng* rng,
+                uint8_t* obs, double* reward, uint8_t* terminated, uint8_t* truncated, int autoreset,
+                uint8_t* final_obs, int32_t* status);
+
+#define OC_ERR_BAD_ACTION 8 /* action outside the env's action set (reference: ValueError, maze.py:286, ctf.py:1200) */
 
 #ifdef __cplusplus
 }

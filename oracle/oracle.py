@@ -205,3 +205,118 @@ def philox4x32_10(ctr, key):
     o = (C.c_uint32 * 4)()
     lib().oc_philox4x32_10(c, k, o)
     return [int(v) for v in o]
+
+
+# =========================================================================== Maze / CtF
+class MapCfg(C.Structure):
+    _fields_ = [("size", C.c_int32), ("field_map", C.c_void_p), ("flag_reward", C.c_double),
+                ("obstacle_penalty", C.c_double), ("step_penalty", C.c_double), ("max_steps", C.c_int32),
+                ("num_blue", C.c_int32), ("num_red", C.c_int32), ("battle_range", C.c_double),
+                ("randomness", C.c_double), ("battle_reward", C.c_double)]
+
+
+class MapState(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("dir", C.c_void_p), ("flags", C.c_void_p), ("step_count", C.c_void_p),
+                ("rng_ctr", C.c_void_p)]
+
+
+class MapRng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("start_index", C.c_void_p), ("blue_place", C.c_void_p), ("red_place", C.c_void_p),
+                ("red_actions", C.c_void_p), ("order", C.c_void_p), ("blue_win", C.c_void_p), ("KB", C.c_int32),
+                ("battles_used", C.c_void_p), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+def map_rng(mode=1, seed=0, env_id_base=0, **arrays):
+    """Build a MapRng; keeps the numpy arrays alive on the returned struct."""
+    r = MapRng()
+    r.mode, r.seed, r.env_id_base = mode, int(seed), int(env_id_base)
+    keep = {}
+    dt = dict(start_index=np.int32, blue_place=np.int32, red_place=np.int32, red_actions=np.int8, order=np.uint8,
+              blue_win=np.uint8, battles_used=np.int32)
+    for k, v in arrays.items():
+        if v is None:
+            continue
+        a = np.ascontiguousarray(v, dt[k])
+        keep[k] = a
+        setattr(r, k, a.ctypes.data)
+        if k == "blue_win":
+            r.KB = a.shape[1]
+    r._keep = keep
+    return r
+
+
+class _MapOracle:
+    def __init__(self, field_map, num_envs, n_agents, **cfg):
+        self.fm = np.ascontiguousarray(np.asarray(field_map).astype(np.uint8))
+        assert self.fm.ndim == 2 and self.fm.shape[0] == self.fm.shape[1], "square maps only"
+        self.S, self.N, self.n = self.fm.shape[0], int(num_envs), n_agents
+        c = MapCfg()
+        c.size, c.field_map = self.S, self.fm.ctypes.data
+        for k, v in cfg.items():
+            setattr(c, k, v)
+        self.cfg = c
+        self.pos = np.zeros((self.N, n_agents, 2), np.uint8)
+        self.dir = np.zeros((self.N, n_agents), np.uint8)
+        self.flags = np.zeros((self.N, n_agents), np.uint8)
+        self.step_count = np.zeros(self.N, np.int32)
+        self.rng_ctr = np.zeros(self.N, np.uint32)
+        self.status = C.c_int32(0)
+
+    def _state(self):
+        s = MapState()
+        s.pos, s.dir, s.flags = _p(self.pos), _p(self.dir), _p(self.flags)
+        s.step_count, s.rng_ctr = _p(self.step_count), _p(self.rng_ctr)
+        return s
+
+    def _call_reset(self, fn, rng, mask):
+        obs = np.zeros((self.N, self.S, self.S), np.uint8)
+        st = self._state()
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        fn(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(m), C.byref(rng), _p(obs), C.byref(self.status))
+        return obs
+
+    def _call_step(self, fn, actions, rng, autoreset, want_final_obs):
+        actions = np.ascontiguousarray(actions, np.int8)
+        obs = np.zeros((self.N, self.S, self.S), np.uint8)
+        rew = np.zeros(self.N, np.float64)
+        term, trunc = np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8)
+        fin = np.zeros_like(obs) if want_final_obs else None
+        st = self._state()
+        fn(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(actions), C.byref(rng), _p(obs), _p(rew), _p(term),
+           _p(trunc), C.c_int(int(autoreset)), _p(fin), C.byref(self.status))
+        out = (obs, rew, term.astype(bool), trunc.astype(bool))
+        return out + (fin,) if want_final_obs else out
+
+
+class MazeOracle(_MapOracle):
+    """MazeSingleAgentEnv (maze.py) batched on the CPU; obs = `_encode_map()` values as uint8 [N, W, H]."""
+
+    def __init__(self, field_map, num_envs, flag_reward=1.0, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100):
+        super().__init__(field_map, num_envs, 1, flag_reward=float(flag_reward),
+                         obstacle_penalty=float(flag_reward) * float(obstacle_penalty_ratio),   # maze.py:349
+                         step_penalty=float(flag_reward) * float(step_penalty_ratio), max_steps=max_steps)  # :350
+
+    def reset(self, rng, mask=None):
+        return self._call_reset(lib().oc_maze_reset, rng, mask)
+
+    def step(self, actions, rng, autoreset=False, want_final_obs=False):
+        return self._call_step(lib().oc_maze_step, np.asarray(actions).reshape(self.N), rng, autoreset, want_final_obs)
+
+
+class CtfOracle(_MapOracle):
+    """CtFMvNEnv (ctf.py:657-1433) batched on the CPU; obs = `_encode_map()` (transposed) as uint8 [N, H, W]."""
+
+    def __init__(self, field_map, num_envs, num_blue=2, num_red=2, battle_range=1.0, randomness=0.75, flag_reward=1.0,
+                 battle_reward_ratio=0.25, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100):
+        fr = float(flag_reward)
+        super().__init__(field_map, num_envs, num_blue + num_red, flag_reward=fr, battle_reward=float(battle_reward_ratio) * fr,
+                         obstacle_penalty=float(obstacle_penalty_ratio) * fr, step_penalty=float(step_penalty_ratio) * fr,
+                         max_steps=max_steps, num_blue=num_blue, num_red=num_red, battle_range=float(battle_range),
+                         randomness=float(randomness))   # ctf.py:724-727
+        self.nb, self.nr = num_blue, num_red
+
+    def reset(self, rng, mask=None):
+        return self._call_reset(lib().oc_ctf_reset, rng, mask)
+
+    def step(self, blue_actions, rng, autoreset=False, want_final_obs=False):
+        return self._call_step(lib().oc_ctf_step, np.asarray(blue_actions).reshape(self.N, self.nb), rng, autoreset, want_final_obs)

@@ -242,3 +242,125 @@ def pack_collect_episodes(eps, T, K):
                 raise ValueError(f"episode {i} step {t}: {len(d)} draws > K={K}")
             out["draws"][i, t, :len(d)] = d
     return out
+
+
+# ------------------------------------------------------------------ generator proxy hook
+@contextmanager
+def tapped_generators():
+    """Every gymnasium np_random generator created while installed records into ONE ordered log."""
+    import gymnasium
+    log = []
+
+    def wrap(g):
+        p = GeneratorProxy(g)
+        p.events = log
+        return p
+
+    old = gymnasium.Env.wrap_generator
+    gymnasium.Env.wrap_generator = staticmethod(wrap)
+    try:
+        yield log
+    finally:
+        gymnasium.Env.wrap_generator = old
+
+
+# ----------------------------------------------------------------------- Maze recording
+def record_maze_episode(map_path, seed, action_rng, obstacle_penalty_ratio=0.0, max_steps=100, invalid_prob=0.0):
+    """One episode of the reference MazeSingleAgentEnv (maze.py:26-377), "map" observations."""
+    import_reference()
+    from gym_multigrid.envs.maze import MazeSingleAgentEnv
+    env = MazeSingleAgentEnv(map_path, max_steps=max_steps, obstacle_penalty_ratio=obstacle_penalty_ratio,
+                             observation_option="map")
+    np.random.seed(seed)
+    with installed_taps() as taps:
+        obs0, info0 = env.reset(seed=seed)
+        start_index = taps.np_randint[0]          # maze.py:204 np.random.randint(0, len(background))
+    rec = dict(actions=[], obs=[], reward=[], terminated=[], truncated=[], pos=[], dir=[], info=[])
+    while True:
+        a = int(action_rng.integers(0, 5))
+        obs, rew, term, trunc, info = env.step(a)
+        rec["actions"].append(a)
+        rec["obs"].append(np.asarray(obs).copy())
+        rec["reward"].append(float(rew))
+        rec["terminated"].append(bool(term))
+        rec["truncated"].append(bool(trunc))
+        rec["pos"].append(np.asarray(env.agents[0].pos, dtype=np.int16).copy())
+        rec["dir"].append(int(env.agents[0].dir))
+        rec["info"].append([info["d_a_f"], info["d_a_ob"]])
+        if term or trunc:
+            break
+    L = len(rec["actions"])
+    return dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(), start_index=start_index,
+                init_info=np.array([info0["d_a_f"], info0["d_a_ob"]]), length=L,
+                actions=np.array(rec["actions"], np.int8), obs=np.stack(rec["obs"]),
+                reward=np.array(rec["reward"], np.float64), terminated=np.array(rec["terminated"]),
+                truncated=np.array(rec["truncated"]), pos=np.stack(rec["pos"]), dir=np.array(rec["dir"], np.int8),
+                info=np.array(rec["info"], np.float64))
+
+
+def pack_episodes(eps, keys_per_step, keys_static, T=None):
+    """Generic packer: per-step arrays padded to T along axis 1, static arrays stacked."""
+    T = T or max(e["length"] for e in eps)
+    out = {k: np.stack([e[k] for e in eps]) for k in keys_static}
+    out["length"] = np.array([e["length"] for e in eps], np.int32)
+    for k in keys_per_step:
+        first = np.asarray(eps[0][k])
+        arr = np.zeros((len(eps), T) + first.shape[1:], first.dtype)
+        for i, e in enumerate(eps):
+            arr[i, :e["length"]] = e[k]
+        out[k] = arr
+    return out
+
+
+# ------------------------------------------------------------------------ CtF recording
+def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, obstacle_penalty_ratio=0.0,
+                           max_steps=100, observation_option="map", max_battles=16):
+    """One episode of the reference CtFMvNEnv (ctf.py:657-1433) on a FRESH instance (agent.terminated is
+    never cleared by reset in the reference), with the ordered RNG event log split per step."""
+    import_reference()
+    with tapped_generators() as log:
+        from gym_multigrid.envs.ctf import CtFMvNEnv
+        from gym_multigrid.policy.ctf.heuristic import RwPolicy
+        env = CtFMvNEnv(map_path, num_blue_agents=num_blue, num_red_agents=num_red, enemy_policies=RwPolicy(),
+                        obstacle_penalty_ratio=obstacle_penalty_ratio, max_steps=max_steps,
+                        observation_option=observation_option)
+        obs0, info0 = env.reset(seed=seed)
+        # the red policies keep the generator they were given at construction (ctf.py:820-826); after reset(seed)
+        # the env owns a new one.  Both record into `log`, in call order.
+        place = [np.asarray(ev[1]).copy() for ev in log if ev[0] == "choice"]
+        del log[:]
+        n = num_blue + num_red
+        rec = dict(actions=[], red_actions=[], order=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[],
+                   truncated=[], pos=[], dir=[], dead=[])
+        init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
+        init_dir = np.array([a.dir for a in env.agents], np.int8)
+        while True:
+            acts = action_rng.integers(0, 5, size=num_blue)
+            obs, rew, term, trunc, info = env.step([int(a) for a in acts])
+            ints = [ev[1] for ev in log if ev[0] == "integers"]
+            shuf = [ev[1] for ev in log if ev[0] == "shuffle"]
+            wins = [bool(ev[1]) for ev in log if ev[0] == "choice"]
+            assert len(ints) == num_red and len(shuf) == 1 and len(wins) <= max_battles
+            del log[:]
+            rec["actions"].append(acts.astype(np.int8))
+            rec["red_actions"].append(np.array(ints, np.int8))
+            rec["order"].append(np.array(shuf[0], np.uint8))
+            rec["n_battles"].append(len(wins))
+            rec["blue_win"].append(np.array(wins + [False] * (max_battles - len(wins)), np.uint8))
+            rec["obs"].append(np.asarray(obs).copy())
+            rec["reward"].append(float(rew))
+            rec["terminated"].append(bool(term))
+            rec["truncated"].append(bool(trunc))
+            rec["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+            rec["dir"].append(np.array([a.dir for a in env.agents], np.int8))
+            rec["dead"].append(np.array([a.terminated for a in env.agents], np.uint8))
+            if term or trunc:
+                break
+    L = len(rec["actions"])
+    out = dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(), init_pos=init_pos,
+               init_dir=init_dir, blue_place=place[0].astype(np.int32), red_place=place[1].astype(np.int32), length=L)
+    for k, v in rec.items():
+        out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
+    out["n_battles"] = out["n_battles"].astype(np.int32)
+    out["reward"] = out["reward"].astype(np.float64)
+    return out

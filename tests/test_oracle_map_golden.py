@@ -1,0 +1,71 @@
+"""CPU suite: the C oracle for Maze and CtF (oracle/mg_oracle_map.c) against golden traces recorded
+from the unmodified reference MazeSingleAgentEnv / CtFMvNEnv (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+
+import oracle as oc
+from replay import load_golden
+
+MAZE = ["maze_board13", "maze_board13_penalty", "maze_gen64", "maze_gen64_penalty"]
+CTF = ["ctf_2v2", "ctf_3v4", "ctf_2v2_penalty", "ctf_1v1"]
+
+
+@pytest.mark.parametrize("stem", MAZE)
+def test_maze_matches_reference(stem):
+    g = load_golden(stem)
+    E, T = g["actions"].shape
+    o = oc.MazeOracle(g["field_map"], E, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]))
+    obs = o.reset(oc.map_rng(mode=0, start_index=g["start_index"]))
+    assert np.array_equal(obs, g["init_obs"])
+    checked = 0
+    for t in range(T):
+        live = g["length"] > t
+        obs, rew, term, trunc = o.step(np.where(live, g["actions"][:, t], 0), oc.map_rng(mode=0))
+        assert np.array_equal(obs[live], g["obs"][live, t]), f"step {t}: obs"
+        assert np.array_equal(rew[live], g["reward"][live, t]), f"step {t}: reward (float64, bit-exact)"
+        assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
+        assert np.array_equal(o.pos[live, 0], g["pos"][live, t]) and np.array_equal(o.dir[live, 0], g["dir"][live, t])
+        checked += int(live.sum())
+    assert checked == int(g["length"].sum()) and o.status.value == 0
+
+
+@pytest.mark.parametrize("stem", CTF)
+def test_ctf_matches_reference(stem):
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    o = oc.CtfOracle(g["field_map"], E, nb, nr, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]))
+    obs = o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
+    assert np.array_equal(obs, g["init_obs"]) and np.array_equal(o.pos, g["init_pos"]) and np.array_equal(o.dir, g["init_dir"])
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    for t in range(T):
+        live = g["length"] > t
+        used = np.zeros(E, np.int32)
+        r = oc.map_rng(mode=0, red_actions=g["red_actions"][:, t], order=np.where(live[:, None], g["order"][:, t], ident),
+                       blue_win=g["blue_win"][:, t], battles_used=used)
+        obs, rew, term, trunc = o.step(np.where(live[:, None], g["actions"][:, t], 0), r)
+        assert np.array_equal(obs[live], g["obs"][live, t]), f"step {t}: obs"
+        assert np.array_equal(rew[live], g["reward"][live, t]), f"step {t}: reward (float64, bit-exact)"
+        assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
+        assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal(o.dir[live], g["dir"][live, t])
+        assert np.array_equal((o.flags & 1)[live], g["dead"][live, t]) and np.array_equal(used[live], g["n_battles"][live, t])
+    assert o.status.value == 0
+
+
+def test_map_philox_mode_shard_invariant():
+    g = load_golden("ctf_3v4")
+    acts = np.random.default_rng(0).integers(0, 5, size=(40, 48, 3)).astype(np.int8)
+
+    def run(base, n):
+        o = oc.CtfOracle(g["field_map"], n, 3, 4)
+        r = oc.map_rng(mode=1, seed=5, env_id_base=base)
+        o.reset(r)
+        out = []
+        for t in range(40):
+            out.append(o.step(acts[t, base:base + n], r, autoreset=True)[:2])
+        return out
+
+    full, lo, hi = run(0, 48), run(0, 20), run(20, 28)
+    for t in range(40):
+        assert np.array_equal(full[t][0], np.concatenate([lo[t][0], hi[t][0]]))
+        assert np.array_equal(full[t][1], np.concatenate([lo[t][1], hi[t][1]]))
