@@ -41,3 +41,15 @@ def make(env_id: str, device="cuda:0", seed: int = 0, **overrides):
     from .vector_env import CollectEnv
     kw = _collect_kwargs(spec(env_id), overrides)
     return CollectEnv(device=device, seed=seed, **kw)
+
+
+def make_maze_vec(num_envs: int, map_path, **kwargs):
+    """Batched `MazeSingleAgentEnv` (envs/maze.py); kwargs as the reference constructor (maze.py:31-40)."""
+    from .map_env import MazeVecEnv
+    return MazeVecEnv(num_envs, map_path, **kwargs)
+
+
+def make_ctf_vec(num_envs: int, map_path, **kwargs):
+    """Batched `CtFMvNEnv` (envs/ctf.py:657-1433); kwargs as the reference constructor (ctf.py:662-679)."""
+    from .map_env import CtfVecEnv
+    return CtfVecEnv(num_envs, map_path, **kwargs)

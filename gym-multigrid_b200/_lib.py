@@ -12,7 +12,11 @@ from ._build import LIB_PATH
 
 MAX_AGENTS = 8
 MAX_BALL_TYPES = 8
-FAMILY_COLLECT = 0
+FAMILY_COLLECT, FAMILY_MAZE, FAMILY_CTF = 0, 1, 2
+OBS_U8, OBS_REFERENCE = 0, 1
+MAP_PLANE_POS, MAP_PLANE_DIR, MAP_PLANE_FLAGS, MAP_PLANE_HDR = 0, 1, 2, 3
+ERR_BAD_ACTION = 8
+MAX_MAP_AGENTS = 16
 LAYOUTS = {"even_dist": 0, "quadrants": 1, "rooms": 2, "quadrants_respawn": 3}
 PLANE_GRID, PLANE_AGENT_POS, PLANE_HDR, PLANE_INFO = 0, 1, 2, 3
 ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
@@ -20,7 +24,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace",
 ]
 
 
@@ -44,6 +48,22 @@ class Trace(C.Structure):
     _fields_ = [("order", C.c_void_p), ("draws", C.c_void_p), ("n_draws", C.c_void_p), ("K", C.c_int32),
                 ("reset_draws", C.c_void_p), ("n_reset_draws", C.c_void_p), ("R", C.c_int32),
                 ("draws_used", C.c_void_p), ("reset_draws_used", C.c_void_p)]
+
+
+class MapConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("family", C.c_int32), ("num_envs", C.c_int64), ("env_id_base", C.c_int64),
+        ("size", C.c_int32), ("field_map", C.c_void_p), ("num_blue", C.c_int32), ("num_red", C.c_int32),
+        ("flag_reward", C.c_double), ("battle_reward", C.c_double), ("obstacle_penalty", C.c_double),
+        ("step_penalty", C.c_double), ("battle_range", C.c_double), ("randomness", C.c_double),
+        ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("obs_dtype", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
+class MapTrace(C.Structure):
+    _fields_ = [("start_index", C.c_void_p), ("blue_place", C.c_void_p), ("red_place", C.c_void_p),
+                ("red_actions", C.c_void_p), ("order", C.c_void_p), ("blue_win", C.c_void_p), ("KB", C.c_int32),
+                ("battles_used", C.c_void_p)]
 
 
 _lib = None
@@ -82,6 +102,9 @@ def load():
     lib.mg_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     lib.mg_debug_set_timeline.argtypes = [C.c_void_p, C.c_void_p]
     lib.mg_tile_envs.argtypes = [C.c_void_p]
+    lib.mg_create_map.restype = C.c_int
+    lib.mg_create_map.argtypes = [C.POINTER(MapConfig), C.c_int, C.POINTER(C.c_void_p)]
+    lib.mg_set_map_trace.argtypes = [C.c_void_p, C.POINTER(MapTrace)]
     lib.mg_launch_count.restype = C.c_int64
     lib.mg_launch_count.argtypes = [C.c_void_p]
     if lib.mg_abi_version() != 1:

@@ -21,10 +21,23 @@ int num_tile_variants();
 int tile_envs(int v);
 cudaError_t configure_kernels(int v, int cells, int A);
 size_t tile_smem(int v, int cells, int A);
+struct MapParams;
+cudaError_t launch_map(const MapParams& p, cudaStream_t st);
+cudaError_t configure_map_kernels(int L, int n);
+size_t map_smem_bytes(int L, int n);
+int map_tile_envs();
 }  // namespace mg
+#include "map_params.cuh"
 
 struct mg_env {
+  int family;
   mg_config cfg;
+  mg_map_config mcfg;
+  mg::MapParams mbase;
+  mg_map_trace mtrace;
+  uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
+  size_t obs_elem;        // bytes per obs element
+  int act_cols, rew_cols;
   int device;
   int tile;  // kernel tile variant (envs per CTA x threads), MG_TILE env var, default 0
   long long n_pad;
@@ -116,6 +129,9 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
 
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");
+  env->family = MG_FAMILY_COLLECT;
+  env->d_map_tables = nullptr;
+  env->obs_elem = 1; env->act_cols = cfg->num_agents; env->rew_cols = cfg->num_agents;
   env->cfg = *cfg;
   env->device = device;
   env->tile = tile;
@@ -180,6 +196,7 @@ extern "C" int mg_destroy(mg_env* env) {
   cudaSetDevice(env->device);
   cudaFree(env->d_status);
   cudaFree(env->d_wall_template);
+  cudaFree(env->d_map_tables);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_rewards);
   cudaFree(env->d_term); cudaFree(env->d_trunc); cudaFree(env->d_final);
   delete env;
@@ -188,10 +205,12 @@ extern "C" int mg_destroy(mg_env* env) {
 
 extern "C" size_t mg_state_bytes(const mg_env* env) { return env ? env->state_bytes : 0; }
 extern "C" size_t mg_obs_bytes(const mg_env* env) {
-  return env ? (size_t)env->cfg.num_envs * env->cfg.width * env->cfg.height * 3 : 0;
+  if (!env) return 0;
+  if (env->family != MG_FAMILY_COLLECT) return (size_t)env->mcfg.num_envs * env->mcfg.size * env->mcfg.size * env->obs_elem;
+  return (size_t)env->cfg.num_envs * env->cfg.width * env->cfg.height * 3;
 }
 extern "C" int mg_state_plane(const mg_env* env, int plane, size_t* offset, size_t* bytes, size_t* row_bytes) {
-  if (!env || plane < 0 || plane >= MG_PLANE_COUNT) return -1;
+  if (!env || plane < 0 || plane >= MG_PLANE_COUNT) return -1;  // (MG_MAP_PLANE_COUNT == MG_PLANE_COUNT)
   if (offset) *offset = env->plane_off[plane];
   if (bytes) *bytes = env->plane_bytes[plane];
   if (row_bytes) *row_bytes = env->plane_row[plane];
@@ -215,6 +234,157 @@ static void bind_trace(mg_env* env, mg::CollectParams& p) {
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ------------------------------------------------------------------------------ Maze / CtF
+static size_t gcd_sz(size_t a, size_t b) { while (b) { size_t t = a % b; a = b; b = t; } return a; }
+
+extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out) {
+  if (!cfg || !out) return fail(nullptr, "mg_create_map: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(mg_map_config)) return fail(nullptr, "mg_create_map: mg_map_config size mismatch (ABI)");
+  const bool maze = cfg->family == MG_FAMILY_MAZE;
+  if (!maze && cfg->family != MG_FAMILY_CTF) return fail(nullptr, "mg_create_map: family must be MG_FAMILY_MAZE or MG_FAMILY_CTF");
+  const int S = cfg->size, cells = S * S;
+  if (cfg->num_envs < 1) return fail(nullptr, "mg_create_map: num_envs must be >= 1");
+  if (S < 3 || S > 255 || !cfg->field_map) return fail(nullptr, "mg_create_map: need a square field_map with 3 <= size <= 255");
+  const int nb = maze ? 1 : cfg->num_blue, nr = maze ? 0 : cfg->num_red, n = nb + nr;
+  if (nb < 1 || nr < 0 || n > MG_MAX_MAP_AGENTS || (!maze && nr < 1)) return fail(nullptr, "mg_create_map: agent counts out of range (1..16 agents in total)");
+  if (cfg->max_steps < 1) return fail(nullptr, "mg_create_map: max_steps must be >= 1");
+  // cell lists in np.where order (row-major over field_map[x][y])
+  std::string bg, bt, rt;  // uint16 lists packed in strings
+  auto push = [](std::string& v, int c) { uint16_t u = (uint16_t)c; v.append(reinterpret_cast<const char*>(&u), 2); };
+  int blue_flag = -1, red_flag = -1;
+  for (int i = 0; i < cells; ++i) {
+    const int c = cfg->field_map[i];
+    if (maze) {
+      if (c > 3) return fail(nullptr, "mg_create_map: Maze map codes must be 0 background, 2 flag, 3 obstacle (world.py:81-91)");
+      if (c == 0) push(bg, i);
+    } else {
+      if (c > 6 || c == 2 || c == 3) return fail(nullptr, "mg_create_map: CtF map codes must be 0/1 territory, 4/5 flags, 6 obstacle (world.py:66-79)");
+      if (c == 0) push(bt, i);
+      if (c == 1) push(rt, i);
+      if (c == 4 && blue_flag < 0) blue_flag = i;   // list(zip(*np.where(...)))[0]  ctf.py:757-763
+      if (c == 5 && red_flag < 0) red_flag = i;
+    }
+  }
+  if (maze && bg.empty()) return fail(nullptr, "mg_create_map: Maze map has no background cell to start on");
+  if (!maze) {
+    if (blue_flag < 0 || red_flag < 0) return fail(nullptr, "mg_create_map: CtF map needs a blue flag (4) and a red flag (5)");
+    push(bt, blue_flag); push(rt, red_flag);  // territory lists end with the flag cell (ctf.py:765-773)
+    if ((int)bt.size() / 2 < nb || (int)rt.size() / 2 < nr) return fail(nullptr, "mg_create_map: more agents than territory cells");
+  }
+  const size_t L = (size_t)cells / gcd_sz((size_t)cells, 16) * 16;  // lcm(cells, 16)
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, std::string("mg_create_map: no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, "mg_create_map: device index out of range");
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, "cudaSetDevice", ce);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
+  if (prop.major != 10) return fail(nullptr, "mg_create_map: kernels are built for sm_100a only");
+  if (mg::map_smem_bytes((int)L, n) > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(nullptr, "mg_create_map: map too large: lcm(size*size, 16) bytes must fit in shared memory");
+  if ((ce = mg::configure_map_kernels((int)L, n)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
+
+  mg_env* env = new (std::nothrow) mg_env();
+  if (!env) return fail(nullptr, "mg_create_map: out of host memory");
+  env->family = cfg->family;
+  env->mcfg = *cfg; env->mcfg.field_map = nullptr;
+  env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
+  env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
+  env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
+  std::memset(&env->mtrace, 0, sizeof env->mtrace);
+  env->obs_elem = cfg->obs_dtype == MG_OBS_U8 ? 1 : 8;
+  env->act_cols = nb; env->rew_cols = 1;
+  const int E = mg::map_tile_envs();
+  env->n_pad = (cfg->num_envs + E - 1) / E * E;
+  const size_t rows[MG_MAP_PLANE_COUNT] = {(size_t)n * 2, (size_t)n, (size_t)n, 16};
+  size_t off = 0;
+  for (int i = 0; i < MG_MAP_PLANE_COUNT; ++i) {
+    env->plane_off[i] = off; env->plane_row[i] = rows[i]; env->plane_bytes[i] = rows[i] * (size_t)env->n_pad;
+    off = align_up(off + env->plane_bytes[i], 256);
+  }
+  env->state_bytes = off;
+
+  // device tables: field_map | obs_period | cell lists
+  std::string period(L, '\0');
+  for (size_t k = 0; k < L; ++k) {
+    const int i = (int)(k % cells);
+    // Maze obs is field_map as is (maze.py:245-260); CtF returns the transpose (ctf.py:1163): obs[y][x] = map[x][y]
+    period[k] = (char)(maze ? cfg->field_map[i] : cfg->field_map[(i % S) * S + (i / S)]);
+  }
+  const size_t o_map = 0, o_per = align_up((size_t)cells, 256), o_bg = align_up(o_per + L, 256),
+               o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), total = align_up(o_rt + rt.size(), 256) + 256;
+  std::string blob(total, '\0');
+  std::memcpy(&blob[o_map], cfg->field_map, cells);
+  std::memcpy(&blob[o_per], period.data(), L);
+  if (!bg.empty()) std::memcpy(&blob[o_bg], bg.data(), bg.size());
+  if (!bt.empty()) std::memcpy(&blob[o_bt], bt.data(), bt.size());
+  if (!rt.empty()) std::memcpy(&blob[o_rt], rt.data(), rt.size());
+  if ((ce = cudaMalloc(&env->d_map_tables, total)) != cudaSuccess ||
+      (ce = cudaMemcpy(env->d_map_tables, blob.data(), total, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess ||
+      (ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) {
+    cudaFree(env->d_map_tables); cudaFree(env->d_status); delete env;
+    return cuda_fail(nullptr, "mg_create_map: device tables", ce);
+  }
+  mg::MapParams& p = env->mbase;
+  std::memset(&p, 0, sizeof p);
+  p.S = S; p.cells = cells; p.nb = nb; p.nr = nr; p.n = n; p.family = cfg->family; p.max_steps = cfg->max_steps;
+  p.autoreset = cfg->autoreset != 0; p.obs_dtype = cfg->obs_dtype;
+  p.flag_reward = cfg->flag_reward; p.obstacle_penalty = cfg->obstacle_penalty; p.step_penalty = cfg->step_penalty;
+  p.battle_reward = cfg->battle_reward; p.battle_range = cfg->battle_range; p.randomness = cfg->randomness;
+  p.n_background = (int)bg.size() / 2; p.len_blue = (int)bt.size() / 2; p.len_red = (int)rt.size() / 2;
+  p.blue_flag = blue_flag; p.red_flag = red_flag;
+  p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
+  p.field_map = env->d_map_tables + o_map; p.obs_period = env->d_map_tables + o_per; p.L = (int)L;
+  p.background = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bg);
+  p.blue_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bt);
+  p.red_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_rt);
+  p.status = env->d_status; p.rng_mode = 1;
+  *out = env;
+  return 0;
+}
+
+extern "C" int mg_set_map_trace(mg_env* env, const mg_map_trace* t) {
+  if (!env || env->family == MG_FAMILY_COLLECT) return -1;
+  if (!t) { env->has_trace = false; return 0; }
+  env->mtrace = *t;
+  env->has_trace = true;
+  return 0;
+}
+
+static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, const uint8_t* mask, void* obs, cudaStream_t st) {
+  mg::MapParams p = env->mbase;
+  uint8_t* s = static_cast<uint8_t*>(state);
+  p.pos = s + env->plane_off[MG_MAP_PLANE_POS]; p.dir = s + env->plane_off[MG_MAP_PLANE_DIR];
+  p.flags = s + env->plane_off[MG_MAP_PLANE_FLAGS]; p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_MAP_PLANE_HDR]);
+  p.op = op; p.reset_mask = mask;
+  if (env->has_trace) {
+    const mg_map_trace& t = env->mtrace;
+    p.rng_mode = 0;
+    p.start_index = t.start_index; p.blue_place = t.blue_place; p.red_place = t.red_place; p.red_actions = t.red_actions;
+    p.order = t.order; p.blue_win = t.blue_win; p.KB = t.KB; p.battles_used = t.battles_used;
+    const bool maze = env->family == MG_FAMILY_MAZE;
+    const bool need_reset = op == 0 || p.autoreset;
+    if (need_reset && maze && !p.start_index) return fail(env, "trace mode: Maze reset needs start_index");
+    if (need_reset && !maze && (!p.blue_place || !p.red_place)) return fail(env, "trace mode: CtF reset needs blue_place / red_place");
+    if (op == 1 && !maze && (!p.red_actions || !p.order)) return fail(env, "trace mode: CtF step needs red_actions and order");
+  }
+  if (op == 1) {
+    p.actions = io->actions; p.obs = io->obs; p.rewards = io->rewards; p.terminated = io->terminated;
+    p.truncated = io->truncated; p.final_obs = io->final_obs;
+  } else {
+    p.obs = obs;
+  }
+  if (p.obs && !aligned16(p.obs)) return fail(env, "obs buffer must be 16-byte aligned");
+  cudaError_t ce;
+  if ((ce = mg::launch_map(p, st)) != cudaSuccess) return cuda_fail(env, "map_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
 extern "C" int mg_set_trace(mg_env* env, const mg_trace* t) {
   if (!env) return -1;
   if (!t) { env->has_trace = false; return 0; }
@@ -228,6 +398,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   if (!aligned16(state)) return fail(env, "mg_reset: state buffer must be 16-byte aligned");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
   bind_trace(env, p);
@@ -240,6 +411,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
 static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
   if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
+  if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 1, io, nullptr, nullptr, st);
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
   bind_trace(env, p);
@@ -265,6 +437,7 @@ extern "C" int mg_step(mg_env* env, void* state, const mg_step_io* io, void* str
 
 extern "C" int mg_encode(mg_env* env, const void* state, uint8_t* obs, void* stream) {
   if (!env || !state || !obs) return fail(env, "mg_encode: null argument");
+  if (env->family != MG_FAMILY_COLLECT) return fail(env, "mg_encode: Collect family only (Grid.encode); Maze/CtF observations come from mg_reset/mg_step");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   const uint8_t* grid = static_cast<const uint8_t*>(state) + env->plane_off[MG_PLANE_GRID];
@@ -281,11 +454,12 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t N = (size_t)env->cfg.num_envs, A = (size_t)env->cfg.num_agents, ob = mg_obs_bytes(env);
+  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->mcfg.num_envs);
+  const size_t A = (size_t)env->act_cols, R = (size_t)env->rew_cols, ob = mg_obs_bytes(env);
   if (!env->d_actions) {
     if ((ce = cudaMalloc(&env->d_actions, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
     if ((ce = cudaMalloc(&env->d_obs, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_rewards, N * A * sizeof(double))) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMalloc(&env->d_rewards, N * R * sizeof(double))) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
     if ((ce = cudaMalloc(&env->d_term, N)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
     if ((ce = cudaMalloc(&env->d_trunc, N)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
   }
@@ -295,11 +469,11 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   }
   if ((ce = cudaMemcpyAsync(env->d_actions, io->actions, N * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(env, "H2D actions", ce);
   mg_step_io dio;
-  dio.actions = env->d_actions; dio.obs = io->obs ? env->d_obs : nullptr; dio.rewards = env->d_rewards;
+  dio.actions = env->d_actions; dio.obs = io->obs ? static_cast<uint8_t*>(static_cast<void*>(env->d_obs)) : nullptr; dio.rewards = env->d_rewards;
   dio.terminated = env->d_term; dio.truncated = env->d_trunc; dio.final_obs = io->final_obs ? env->d_final : nullptr;
   if (step_device(env, state, &dio, st)) return -1;
   if (io->obs && (ce = cudaMemcpyAsync(io->obs, env->d_obs, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H obs", ce);
-  if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, N * A * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards", ce);
+  if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, N * R * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards", ce);
   if ((ce = cudaMemcpyAsync(io->terminated, env->d_term, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H terminated", ce);
   if ((ce = cudaMemcpyAsync(io->truncated, env->d_trunc, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H truncated", ce);
   if (io->final_obs && (ce = cudaMemcpyAsync(io->final_obs, env->d_final, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H final_obs", ce);
@@ -324,6 +498,9 @@ extern "C" int mg_debug_set_timeline(mg_env* env, uint64_t* timeline_dev) {
   return 0;
 }
 
-extern "C" int mg_tile_envs(const mg_env* env) { return env ? mg::tile_envs(env->tile) : -1; }
+extern "C" int mg_tile_envs(const mg_env* env) {
+  if (!env) return -1;
+  return env->family == MG_FAMILY_COLLECT ? mg::tile_envs(env->tile) : mg::map_tile_envs();
+}
 
 extern "C" int64_t mg_launch_count(const mg_env* env) { return env ? env->launches : 0; }

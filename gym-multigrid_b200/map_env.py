@@ -1,0 +1,279 @@
+"""Batched Maze and Capture-the-Flag environments on one B200: host-side mirrors of the reference's
+`MazeSingleAgentEnv` (envs/maze.py) and `CtFMvNEnv` (envs/ctf.py:657-1433).  The text map is shared by
+all envs (device tables owned by the C handle); per-env state (agent positions, dirs, flags, step
+counter) is one caller-owned torch uint8 CUDA tensor; `step` / `reset` are one kernel launch each."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spaces import Box, Discrete, MultiDiscrete
+
+
+def load_text_map(map_path) -> np.ndarray:
+    """utils/map.py:22-39: `np.loadtxt(map_path).T`, i.e. field_map[x, y]; arrays are passed through."""
+    if isinstance(map_path, (str, bytes)) or hasattr(map_path, "__fspath__"):
+        return np.loadtxt(map_path).T
+    return np.asarray(map_path)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _MapVecEnv:
+    family = None
+    ref_dtype = None
+
+    def _create(self, num_envs, field_map, num_blue, num_red, flag_reward, battle_reward, obstacle_penalty, step_penalty,
+                battle_range, randomness, max_steps, device, seed, autoreset, env_id_base, reference_dtypes):
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("gym-multigrid_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device available: gym-multigrid_b200 has no CPU fallback")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        fm = np.ascontiguousarray(np.asarray(field_map))
+        if fm.ndim != 2 or fm.shape[0] != fm.shape[1]:
+            raise ValueError("square maps only (the reference mixes width and height: maze.py:68-70, ctf.py:745-747)")
+        if not np.array_equal(fm, fm.astype(np.uint8)):
+            raise ValueError("map codes must be small non-negative integers")
+        self.field_map = fm.astype(np.uint8)
+        self.size = self.width = self.height = int(fm.shape[0])
+        self.num_envs, self.num_blue, self.num_red = int(num_envs), int(num_blue), int(num_red)
+        self.n_agents = self.num_blue + self.num_red
+        self.max_steps, self.autoreset = int(max_steps), bool(autoreset)
+        self.reference_dtypes = bool(reference_dtypes)
+        cfg = _lib.MapConfig()
+        cfg.struct_size = C.sizeof(_lib.MapConfig)
+        cfg.family, cfg.num_envs, cfg.env_id_base = self.family, self.num_envs, int(env_id_base)
+        cfg.size, cfg.field_map = self.size, self.field_map.ctypes.data
+        cfg.num_blue, cfg.num_red = self.num_blue, self.num_red
+        cfg.flag_reward, cfg.battle_reward = float(flag_reward), float(battle_reward)
+        cfg.obstacle_penalty, cfg.step_penalty = float(obstacle_penalty), float(step_penalty)
+        cfg.battle_range, cfg.randomness = float(battle_range), float(randomness)
+        cfg.max_steps, cfg.autoreset = self.max_steps, int(self.autoreset)
+        cfg.obs_dtype = _lib.OBS_REFERENCE if self.reference_dtypes else _lib.OBS_U8
+        cfg.seed = int(seed) & (2**64 - 1)
+        h = C.c_void_p()
+        if self._lib.mg_create_map(C.byref(cfg), idx, C.byref(h)) != 0:
+            raise ValueError(_lib.last_error(None))
+        self._h = h
+        N, S, n = self.num_envs, self.size, self.n_agents
+        odt = self.ref_dtype if self.reference_dtypes else torch.uint8
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(self._lib.mg_state_bytes(self._h), dtype=torch.uint8, device=self.device)
+            self._obs = torch.zeros((N, S, S), dtype=odt, device=self.device)
+            self._rewards = torch.zeros(N, dtype=torch.float64, device=self.device)
+            self._term = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self._trunc = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self._final_obs = None
+        self._planes = {}
+        for name, pid, dt, cols in (("pos", _lib.MAP_PLANE_POS, torch.uint8, n * 2), ("dir", _lib.MAP_PLANE_DIR, torch.uint8, n),
+                                    ("flags", _lib.MAP_PLANE_FLAGS, torch.uint8, n), ("hdr", _lib.MAP_PLANE_HDR, torch.int32, 4)):
+            off, nbytes, row = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            self._lib.mg_state_plane(self._h, pid, C.byref(off), C.byref(nbytes), C.byref(row))
+            self._planes[name] = self.state[off.value: off.value + nbytes.value].view(dt).view(-1, cols)[:N]
+        self._io = _lib.StepIO()
+        self._host = None
+        self._trace_keepalive = None
+        self.closed = False
+
+    # --- zero-copy state views
+    @property
+    def agent_pos(self):
+        return self._planes["pos"].view(self.num_envs, self.n_agents, 2)
+
+    @property
+    def agent_dir(self):
+        return self._planes["dir"]
+
+    @property
+    def agent_terminated(self):
+        return (self._planes["flags"] & 1).bool()
+
+    @property
+    def step_count(self):
+        return self._planes["hdr"][:, 0]
+
+    @property
+    def episode_count(self):
+        return self._planes["hdr"][:, 3]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(_lib.last_error(self._h))
+
+    def reset(self, *, seed=None, options=None, mask=None):
+        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        self._check(self._lib.mg_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self._obs), self._stream()))
+        return self._obs, {}
+
+    def _prep_actions(self, actions):
+        a = actions
+        if a.device != self.device:
+            a = a.to(self.device, non_blocking=True)
+        if a.dtype.is_floating_point:
+            a = torch.round(a)  # "Just in case NN outputs are, for some reason, not discrete." (ctf.py:1303-1304)
+        if a.dtype != torch.int8:
+            a = a.to(torch.int8)
+        return a.reshape(self.num_envs, self.num_blue).contiguous()
+
+    def step(self, actions):
+        if not isinstance(actions, torch.Tensor):
+            return self.step_host(actions)
+        a = self._prep_actions(actions)
+        io = self._io
+        io.actions, io.obs, io.rewards = a.data_ptr(), self._obs.data_ptr(), self._rewards.data_ptr()
+        io.terminated, io.truncated = self._term.data_ptr(), self._trunc.data_ptr()
+        io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
+        self._check(self._lib.mg_step(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        return self._obs, self._rewards, self._term.view(torch.bool), self._trunc.view(torch.bool), self._info()
+
+    def step_host(self, actions):
+        if self._host is None:
+            N, S = self.num_envs, self.size
+            pin = dict(pin_memory=True)
+            self._host = dict(act=torch.zeros((N, self.num_blue), dtype=torch.int8, **pin),
+                              obs=torch.zeros((N, S, S), dtype=self._obs.dtype, **pin), rew=torch.zeros(N, dtype=torch.float64, **pin),
+                              term=torch.zeros(N, dtype=torch.uint8, **pin), trunc=torch.zeros(N, dtype=torch.uint8, **pin))
+            self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        h = self._host
+        self._host_np["act"][...] = np.round(np.asarray(actions)).astype(np.int64).reshape(self.num_envs, self.num_blue)
+        io = _lib.StepIO()
+        io.actions, io.obs, io.rewards = h["act"].data_ptr(), h["obs"].data_ptr(), h["rew"].data_ptr()
+        io.terminated, io.truncated, io.final_obs = h["term"].data_ptr(), h["trunc"].data_ptr(), None
+        self._check(self._lib.mg_step_host(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        n = self._host_np
+        return n["obs"], n["rew"], n["term"].view(np.bool_), n["trunc"].view(np.bool_), {}
+
+    def _info(self):
+        if self._final_obs is None:
+            return {}
+        return {"final_observation": self._final_obs, "_final_observation": (self._term | self._trunc).view(torch.bool)}
+
+    def enable_final_observation(self, enable=True):
+        self._final_obs = torch.zeros_like(self._obs) if enable else None
+
+    def set_trace(self, **arrays):
+        """Validation mode: recorded reference RNG outputs (see include/multigrid_b200.h: mg_map_trace).
+        No arguments = back to Philox mode."""
+        arrays = {k: v for k, v in arrays.items() if v is not None}
+        if not arrays:
+            self._lib.mg_set_map_trace(self._h, None)
+            self._trace_keepalive = None
+            return None
+        dt = dict(start_index=torch.int32, blue_place=torch.int32, red_place=torch.int32, red_actions=torch.int8,
+                  order=torch.uint8, blue_win=torch.uint8)
+        t = {k: torch.as_tensor(np.ascontiguousarray(v), device=self.device).to(dt[k]).contiguous() for k, v in arrays.items()}
+        t["battles_used"] = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        tr = _lib.MapTrace()
+        for k, v in t.items():
+            setattr(tr, k, v.data_ptr())
+        tr.KB = t["blue_win"].reshape(self.num_envs, -1).shape[1] if "blue_win" in t else 0
+        self._lib.mg_set_map_trace(self._h, C.byref(tr))
+        self._trace_keepalive = t
+        return t
+
+    def status(self) -> int:
+        s = C.c_int32(0)
+        self._check(self._lib.mg_status(self._h, self._stream(), C.byref(s)))
+        return s.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mg_launch_count(self._h))
+
+    def close(self):
+        if not self.closed and getattr(self, "_h", None):
+            torch.cuda.synchronize(self.device)
+            self._lib.mg_destroy(self._h)
+            self._h, self.closed = None, True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class MazeVecEnv(_MapVecEnv):
+    """`num_envs` x MazeSingleAgentEnv (maze.py:26-377), constructor kwargs as in maze.py:31-40.
+    Observations: the "map" option - `_encode_map()` values [N, W, H] indexed [x][y] (uint8, or float64 with
+    `reference_dtypes=True` as the reference returns, maze.py:246); actions MazeActions Discrete(5)."""
+    family = _lib.FAMILY_MAZE
+    ref_dtype = torch.float64
+
+    def __init__(self, num_envs, map_path, max_steps=100, flag_reward=1.0, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01,
+                 observation_option="map", device="cuda:0", seed=0, autoreset=True, env_id_base=0, reference_dtypes=False):
+        if observation_option != "map":
+            raise NotImplementedError('only observation_option="map" runs on the device; "positional" is agent_pos + the static lists')
+        fm = load_text_map(map_path)
+        fr = float(flag_reward)
+        self._create(num_envs, fm, 1, 0, fr, 0.0, fr * float(obstacle_penalty_ratio), fr * float(step_penalty_ratio), 0.0, 0.0,
+                     max_steps, device, seed, autoreset, env_id_base, reference_dtypes)
+        self.single_action_space = Discrete(5)
+        self.action_space = MultiDiscrete(np.full((self.num_envs,), 5))
+        hi = 3  # len(MazeWorld.OBJECT_TO_IDX) - 1 (maze.py:150-155)
+        odt = np.float64 if reference_dtypes else np.uint8
+        self.single_observation_space = Box(0, hi, (self.size, self.size), odt)
+        self.observation_space = Box(0, hi, (self.num_envs, self.size, self.size), odt)
+        self.background = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 0))]
+        self.obstacle = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 3))]
+        self.flag = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 2))]
+
+
+class CtfVecEnv(_MapVecEnv):
+    """`num_envs` x CtFMvNEnv (ctf.py:657-1433) with RwPolicy red agents (policy/ctf/heuristic.py:69-72) drawn on
+    the device.  Observations: the "map" option - `_encode_map()` (transposed, [N, H, W]; uint8, or int64 with
+    `reference_dtypes=True`); `positional_obs()` / `flattened_obs()` assemble the other two options from the
+    state planes.  Actions MultiDiscrete([5] * num_blue_agents); reward = scalar team reward (float64)."""
+    family = _lib.FAMILY_CTF
+    ref_dtype = torch.int64
+
+    def __init__(self, num_envs, map_path, num_blue_agents=2, num_red_agents=2, battle_range=1, randomness=0.75, flag_reward=1,
+                 battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
+                 observation_option="map", observation_scaling=1, device="cuda:0", seed=0, autoreset=True, env_id_base=0,
+                 reference_dtypes=False):
+        if observation_option != "map":
+            raise NotImplementedError('the device writes observation_option="map"; use positional_obs()/flattened_obs() for the others')
+        fm = load_text_map(map_path)
+        fr = flag_reward
+        self._create(num_envs, fm, num_blue_agents, num_red_agents, float(fr), float(battle_reward_ratio * fr),
+                     float(obstacle_penalty_ratio * fr), float(step_penalty_ratio * fr), float(battle_range), float(randomness),
+                     max_steps, device, seed, autoreset, env_id_base, reference_dtypes)
+        self.num_blue_agents, self.num_red_agents = self.num_blue, self.num_red
+        self.single_action_space = MultiDiscrete([5] * self.num_blue)
+        self.action_space = MultiDiscrete(np.full((self.num_envs, self.num_blue), 5))
+        odt = np.int64 if reference_dtypes else np.uint8
+        self.single_observation_space = Box(0, 6, (self.size, self.size), odt)
+        self.observation_space = Box(0, 6, (self.num_envs, self.size, self.size), odt)
+        f = self.field_map
+        cells = lambda code: [tuple(int(v) for v in c) for c in zip(*np.where(f == code))]  # noqa: E731
+        self.obstacle, self.blue_flag, self.red_flag = cells(6), cells(4)[0], cells(5)[0]
+        self.blue_territory = cells(0) + [self.blue_flag]
+        self.red_territory = cells(1) + [self.red_flag]
+
+    def positional_obs(self):
+        """observation_option="positional" (ctf.py:1112-1135) as batched int64 CUDA tensors."""
+        N, nb = self.num_envs, self.num_blue
+        pos = self.agent_pos.to(torch.int64)
+        st = lambda x: torch.as_tensor(np.array(x).flatten(), device=self.device).expand(N, -1)  # noqa: E731
+        return {"blue_agent": pos[:, :nb].reshape(N, -1), "red_agent": pos[:, nb:].reshape(N, -1),
+                "blue_flag": st(self.blue_flag), "red_flag": st(self.red_flag), "blue_territory": st(self.blue_territory),
+                "red_territory": st(self.red_territory), "obstacle": st(self.obstacle),
+                "terminated_agents": self.agent_terminated.to(torch.int64)}
+
+    def flattened_obs(self):
+        """observation_option="flattened" (ctf.py:1084-1104)."""
+        d = self.positional_obs()
+        return torch.cat([d["blue_agent"], d["red_agent"], d["blue_flag"], d["red_flag"], d["blue_territory"], d["red_territory"],
+                          d["obstacle"], d["terminated_agents"]], dim=1)

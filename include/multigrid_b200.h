@@ -29,7 +29,7 @@ extern "C" {
 #define MG_MAX_BALL_TYPES 8
 
 /* env families (reference: gym_multigrid/envs/{collect_game,maze,ctf}.py) */
-enum { MG_FAMILY_COLLECT = 0 };
+enum { MG_FAMILY_COLLECT = 0, MG_FAMILY_MAZE = 1, MG_FAMILY_CTF = 2 };
 
 /* Collect layouts = the reference's _gen_grid variants */
 enum { MG_LAYOUT_EVEN_DIST = 0,         /* CollectGameEvenDist          collect_game.py:227-259 */
@@ -141,6 +141,65 @@ int mg_tile_envs(const mg_env* env);
 
 /* number of kernel launches issued through this handle since creation */
 int64_t mg_launch_count(const mg_env* env);
+
+/* ===================================================================================== Maze and CtF
+ * Static text-map families: MazeSingleAgentEnv (envs/maze.py:26-377) and CtFMvNEnv (envs/ctf.py:657-1433).
+ * The map (utils/map.py:22-39, field_map = np.loadtxt(path).T, indexed [x][y]) is shared by all envs and
+ * lives in handle-owned device tables; per-env state is only the agents.  Square maps only (the
+ * reference mixes width and height: maze.py:68-70 vs :184-186, ctf.py:745-747). */
+#define MG_MAX_MAP_AGENTS 16
+
+enum { MG_OBS_U8 = 0,        /* "map" codes as uint8 (compact default) */
+       MG_OBS_REFERENCE = 1  /* the reference's dtype: float64 for Maze (maze.py:246), int64 for CtF (ctf.py:1138) */ };
+
+typedef struct mg_map_config {
+  uint32_t struct_size;       /* = sizeof(mg_map_config) */
+  int32_t family;             /* MG_FAMILY_MAZE | MG_FAMILY_CTF */
+  int64_t num_envs;
+  int64_t env_id_base;
+  int32_t size;               /* W == H */
+  const uint8_t* field_map;   /* HOST pointer, [size*size], index x*size + y; MazeWorld / CtfWorld codes (world.py:66-91) */
+  int32_t num_blue, num_red;  /* CtF: num_blue_agents / num_red_agents; Maze: 1 / 0 */
+  double flag_reward;         /* flag_reward */
+  double battle_reward;       /* battle_reward_ratio * flag_reward      (ctf.py:725), formed by the caller in double */
+  double obstacle_penalty;    /* obstacle_penalty_ratio * flag_reward   (ctf.py:726, maze.py:349) */
+  double step_penalty;        /* step_penalty_ratio * flag_reward       (ctf.py:727, maze.py:350) */
+  double battle_range;        /* ctf.py:667 */
+  double randomness;          /* ctf.py:668 */
+  int32_t max_steps;
+  int32_t autoreset;
+  int32_t obs_dtype;          /* MG_OBS_* */
+  uint64_t seed;
+} mg_map_config;
+
+/* planes of the map families' state buffer */
+enum { MG_MAP_PLANE_POS = 0,    /* u8  [N_pad][n][2] (x, y), n = num_blue + num_red   Agent.pos */
+       MG_MAP_PLANE_DIR = 1,    /* u8  [N_pad][n]                                     Agent.dir */
+       MG_MAP_PLANE_FLAGS = 2,  /* u8  [N_pad][n]  bit0 terminated (defeated), bit1 collided (agent.py:97-100) */
+       MG_MAP_PLANE_HDR = 3,    /* i32 [N_pad][4]  step_count, 0, Philox block counter, episodes */
+       MG_MAP_PLANE_COUNT = 4 };
+
+/* Validation mode for the map families: recorded outputs of the reference's RNG call sites. */
+typedef struct mg_map_trace {
+  const int32_t* start_index;  /* [N]           Maze reset: np.random.randint(0, len(background))  maze.py:204 */
+  const int32_t* blue_place;   /* [N][num_blue] CtF reset: np_random.choice(len(blue_territory), k, replace=False) ctf.py:1034 */
+  const int32_t* red_place;    /* [N][num_red]  ctf.py:1041 */
+  const int8_t* red_actions;   /* [N][num_red]  RwPolicy: np_random.integers(0, 5)  policy/ctf/heuristic.py:72 */
+  const uint8_t* order;        /* [N][n]        np_random.shuffle(agent_indices)    ctf.py:1245 */
+  const uint8_t* blue_win;     /* [N][KB]       battle outcomes np_random.choice    ctf.py:1393-1403 */
+  int32_t KB;
+  int32_t* battles_used;       /* [N] out (NULL = skip) */
+} mg_map_trace;
+
+#define MG_ERR_BAD_ACTION 8     /* action outside the action set (reference: ValueError, maze.py:286, ctf.py:1200) */
+
+/* MazeSingleAgentEnv.__init__ / CtFMvNEnv.__init__.  mg_reset / mg_step / mg_step_host / mg_status /
+ * mg_destroy work on the returned handle; mg_step_io then means: actions int8 [N][1] (Maze, MazeActions) or
+ * [N][num_blue] (CtF, CtfActions: 0 stay 1 left 2 down 3 right 4 up); rewards float64 [N] (scalar reward);
+ * obs [N][size][size] of obs_dtype (Maze: [x][y] as _encode_map maze.py:245-260; CtF: [y][x] as
+ * _encode_map().T ctf.py:1137-1163). */
+int mg_create_map(const mg_map_config* cfg, int device, mg_env** out);
+int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
 
 #ifdef __cplusplus
 }

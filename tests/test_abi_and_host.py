@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     from gym_multigrid_b200 import _lib
     lib = _lib.load()
     names = _declared_functions()
-    assert len(names) >= 14
+    assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/multigrid_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
@@ -34,6 +34,7 @@ def test_config_struct_matches_header_layout():
     # uint32 + int32 + 2*int64 + 4*int32 + 8*int32 + 8*int32 + 8*double + 7*int32 (+pad) + uint64
     assert C.sizeof(_lib.Config) == 4 + 4 + 16 + 16 + 32 + 32 + 64 + 28 + 4 + 8
     assert C.sizeof(_lib.StepIO) == 6 * 8
+    assert C.sizeof(_lib.MapConfig) == 120 and C.sizeof(_lib.MapTrace) == 8 * 8
     assert C.sizeof(_lib.Trace) == 9 * 8
 
 

@@ -1,0 +1,194 @@
+"""GPU parity suite for the static-map families (Maze, CtF MvN) through the C ABI.
+ * bit-exact replay of golden traces recorded from the reference MazeSingleAgentEnv / CtFMvNEnv;
+ * CUDA vs the C oracle in Philox mode (same counter-based RNG), incl. autoreset + final_observation;
+ * reference dtypes (float64 / int64 observations), host-buffer path, invariants at scale."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as oc
+from replay import load_golden
+
+pytestmark = pytest.mark.gpu
+MAZE = ["maze_board13", "maze_board13_penalty", "maze_gen64", "maze_gen64_penalty"]
+CTF = ["ctf_2v2", "ctf_3v4", "ctf_2v2_penalty", "ctf_1v1"]
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _tile(x, k):
+    return np.concatenate([x] * k)
+
+
+@pytest.mark.parametrize("stem", MAZE)
+@pytest.mark.parametrize("ref_dtypes", [False, True])
+def test_maze_replay_bit_exact(stem, ref_dtypes, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    E, T = g["actions"].shape
+    k = 7
+    env = mg.make_maze_vec(E * k, g["field_map"], obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]),
+                           autoreset=False, reference_dtypes=ref_dtypes)
+    env.set_trace(start_index=_tile(g["start_index"], k))
+    obs, _ = env.reset()
+    assert obs.dtype == (torch.float64 if ref_dtypes else torch.uint8)
+    assert np.array_equal(_np(obs), _tile(g["init_obs"], k))
+    for t in range(T):
+        live = _tile(g["length"] > t, k)
+        act = _tile(np.where(g["length"] > t, g["actions"][:, t], 0), k).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        assert np.array_equal(_np(obs)[live], _tile(g["obs"][:, t], k)[live]), f"step {t}: obs"
+        assert np.array_equal(_np(rew)[live], _tile(g["reward"][:, t], k)[live]), f"step {t}: reward (float64 bit-exact)"
+        assert np.array_equal(_np(term)[live], _tile(g["terminated"][:, t], k)[live])
+        assert np.array_equal(_np(trunc)[live], _tile(g["truncated"][:, t], k)[live])
+        assert np.array_equal(_np(env.agent_pos)[live, 0], _tile(g["pos"][:, t], k)[live])
+        assert np.array_equal(_np(env.agent_dir)[live, 0], _tile(g["dir"][:, t], k)[live])
+    assert env.status() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("stem", CTF)
+def test_ctf_replay_bit_exact(stem, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    k = 9
+    env = mg.make_ctf_vec(E * k, g["field_map"], num_blue_agents=nb, num_red_agents=nr,
+                          obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]), autoreset=False,
+                          reference_dtypes=(stem == "ctf_3v4"))
+    env.set_trace(blue_place=_tile(g["blue_place"], k), red_place=_tile(g["red_place"], k))
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), _tile(g["init_obs"], k)) and np.array_equal(_np(env.agent_pos), _tile(g["init_pos"], k))
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    for t in range(T):
+        lv = g["length"] > t
+        live = _tile(lv, k)
+        tr = env.set_trace(red_actions=_tile(g["red_actions"][:, t], k), order=_tile(np.where(lv[:, None], g["order"][:, t], ident), k),
+                           blue_win=_tile(g["blue_win"][:, t], k))
+        act = _tile(np.where(lv[:, None], g["actions"][:, t], 0), k).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        assert np.array_equal(_np(obs)[live], _tile(g["obs"][:, t], k)[live]), f"step {t}: obs"
+        assert np.array_equal(_np(rew)[live], _tile(g["reward"][:, t], k)[live]), f"step {t}: reward (float64 bit-exact)"
+        assert np.array_equal(_np(term)[live], _tile(g["terminated"][:, t], k)[live])
+        assert np.array_equal(_np(trunc)[live], _tile(g["truncated"][:, t], k)[live])
+        assert np.array_equal(_np(env.agent_pos)[live], _tile(g["pos"][:, t], k)[live])
+        assert np.array_equal(_np(env.agent_dir)[live], _tile(g["dir"][:, t], k)[live])
+        assert np.array_equal(_np(env.agent_terminated)[live], _tile(g["dead"][:, t], k)[live].astype(bool))
+        assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
+    assert env.status() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("stem,n,pen", [("maze_board13", 1000, 0.0), ("maze_board13", 333, 0.5), ("maze_gen64", 300, 0.5)])
+def test_maze_philox_matches_oracle(stem, n, pen, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    env = mg.make_maze_vec(n, g["field_map"], obstacle_penalty_ratio=pen, max_steps=30, seed=99, env_id_base=5)
+    env.enable_final_observation()
+    o = oc.MazeOracle(g["field_map"], n, obstacle_penalty_ratio=pen, max_steps=30)
+    r = oc.map_rng(mode=1, seed=99, env_id_base=5)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(1)
+    for t in range(100):
+        act = rng.integers(0, 5, size=n).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        oo, orew, oterm, otrunc, ofin = o.step(act, r, autoreset=True, want_final_obs=True)
+        assert np.array_equal(_np(obs), oo), f"step {t}: obs"
+        assert np.array_equal(_np(rew), orew) and np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+        d = oterm | otrunc
+        assert np.array_equal(_np(info["final_observation"])[d], ofin[d])
+        assert np.array_equal(_np(env.agent_pos), o.pos) and np.array_equal(_np(env.step_count), o.step_count)
+    assert env.status() == 0 and int(env.episode_count.min()) >= 3
+    env.close()
+
+
+@pytest.mark.parametrize("nb,nr,n,pen", [(2, 2, 2000, 0.0), (3, 4, 515, 0.0), (2, 2, 300, 0.5), (8, 8, 200, 0.0)])
+def test_ctf_philox_matches_oracle(nb, nr, n, pen, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, obstacle_penalty_ratio=pen, max_steps=40,
+                          seed=7, env_id_base=3)
+    env.enable_final_observation()
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, obstacle_penalty_ratio=pen, max_steps=40)
+    r = oc.map_rng(mode=1, seed=7, env_id_base=3)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(2)
+    battles = 0
+    for t in range(130):
+        act = rng.integers(0, 5, size=(n, nb)).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        oo, orew, oterm, otrunc, ofin = o.step(act, r, autoreset=True, want_final_obs=True)
+        assert np.array_equal(_np(obs), oo), f"step {t}: obs"
+        assert np.array_equal(_np(rew), orew), f"step {t}: reward"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+        d = oterm | otrunc
+        assert np.array_equal(_np(info["final_observation"])[d], ofin[d])
+        assert np.array_equal(_np(env.agent_pos), o.pos) and np.array_equal(_np(env._planes["flags"]), o.flags)
+        assert np.array_equal(_np(env.agent_dir), o.dir)
+        battles += int((np.abs(orew + 0.01 * nb) > 0.2).sum())
+    assert env.status() == 0 and battles > 0
+    env.close()
+
+
+def test_ctf_other_observation_options_and_host_path(cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    n = 700
+    a, b = (mg.make_ctf_vec(n, g["field_map"], seed=4) for _ in range(2))
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        act = rng.integers(0, 5, size=(n, 2)).astype(np.int8)
+        x = a.step(torch.as_tensor(act, device=cuda_device))
+        y = b.step(act.astype(np.float32) + 0.2)   # numpy in/out through mg_step_host; rounded like ctf.py:1303-1304
+        for u, v in zip(x[:4], y[:4]):
+            assert np.array_equal(_np(u), v)
+    d = a.positional_obs()
+    assert d["blue_agent"].shape == (n, 4) and d["blue_territory"].shape == (n, 2 * 48) and d["terminated_agents"].shape == (n, 4)
+    f = a.flattened_obs()
+    assert f.shape == (n, 216) and f.dtype == torch.int64   # ctf.py:940-948
+    # the map observation is consistent with the positions
+    obs = _np(a._obs); pos = _np(a.agent_pos); dead = _np(a.agent_terminated)
+    for e in range(0, n, 97):
+        for i in range(4):
+            want = 6 if dead[e, i] else (2 if i < 2 else 3)
+            assert obs[e, pos[e, i, 1], pos[e, i, 0]] == want
+    a.close(); b.close()
+
+
+def test_maze_invariants_at_scale(cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden("maze_gen64")
+    n = 16384
+    env = mg.make_maze_vec(n, g["field_map"], seed=1)
+    fm = torch.as_tensor(g["field_map"], device=cuda_device)
+    obs, _ = env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(0)
+    for t in range(1, 121):
+        act = torch.randint(0, 5, (n,), generator=gen, device=cuda_device, dtype=torch.int8)
+        obs, rew, term, trunc, _ = env.step(act)
+        assert bool(((obs == 1).sum(dim=(1, 2)) == 1).all()), "exactly one agent cell"
+        assert bool(((obs != 1) <= (obs == fm[None])).all()), "everything else is the static map"
+        p = env.agent_pos[:, 0].long()
+        assert bool((fm[p[:, 0], p[:, 1]] != 3).all()), "penalty 0: never on an obstacle"
+        if t % 100:
+            assert not bool(trunc.any())
+    assert env.status() == 0
+    env.close()
+
+
+def test_map_create_rejects_bad_configs(cuda_device):
+    import gym_multigrid_b200 as mg
+    with pytest.raises(ValueError):
+        mg.make_maze_vec(4, np.zeros((5, 6)))
+    with pytest.raises(ValueError):
+        mg.make_maze_vec(4, np.full((5, 5), 3))
+    with pytest.raises(ValueError):
+        mg.make_ctf_vec(4, np.zeros((6, 6)))            # no flags
+    with pytest.raises(ValueError):
+        mg.make_ctf_vec(4, load_golden("ctf_2v2")["field_map"], num_blue_agents=12, num_red_agents=12)
