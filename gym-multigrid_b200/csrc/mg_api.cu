@@ -28,6 +28,14 @@ size_t map_smem_bytes(int L, int n);
 int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
+#include "view_params.cuh"
+namespace mg {
+cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
+cudaError_t configure_view_kernels(size_t bytes);
+size_t view_smem_bytes(int family, int cells, int A, int V);
+int view_max();
+int view_tile_envs();
+}  // namespace mg
 
 struct mg_env {
   int family;
@@ -38,6 +46,8 @@ struct mg_env {
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
   int act_cols, rew_cols;
+  size_t view_smem_configured;
+  size_t map_codes_off;   // Maze: offset of the packed static map (partial views) inside d_map_tables
   int device;
   int tile;  // kernel tile variant (envs per CTA x threads), MG_TILE env var, default 0
   long long n_pad;
@@ -130,6 +140,7 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");
   env->family = MG_FAMILY_COLLECT;
+  env->view_smem_configured = 0; env->map_codes_off = 0;
   env->d_map_tables = nullptr;
   env->obs_elem = 1; env->act_cols = cfg->num_agents; env->rew_cols = cfg->num_agents;
   env->cfg = *cfg;
@@ -141,7 +152,7 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr;
   env->d_term = nullptr; env->d_trunc = nullptr; env->d_final = nullptr;
   std::memset(&env->trace, 0, sizeof env->trace);
-  const int E = mg::tile_envs(tile);
+  const int E = mg::tile_envs(tile) > mg::view_tile_envs() ? mg::tile_envs(tile) : mg::view_tile_envs();  // both tile sizes are powers of two
   env->n_pad = (cfg->num_envs + E - 1) / E * E;
   const size_t rows[MG_PLANE_COUNT] = {(size_t)W * H, (size_t)A * 2, 16, (size_t)A * nb * 4};
   size_t off = 0;
@@ -290,6 +301,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_map: out of host memory");
   env->family = cfg->family;
+  env->view_smem_configured = 0; env->map_codes_off = 0;
   env->mcfg = *cfg; env->mcfg.field_map = nullptr;
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
@@ -315,13 +327,18 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
     period[k] = (char)(maze ? cfg->field_map[i] : cfg->field_map[(i % S) * S + (i / S)]);
   }
   const size_t o_map = 0, o_per = align_up((size_t)cells, 256), o_bg = align_up(o_per + L, 256),
-               o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), total = align_up(o_rt + rt.size(), 256) + 256;
+               o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), o_pk = align_up(o_rt + rt.size(), 256), total = align_up(o_pk + cells, 256) + 256;
   std::string blob(total, '\0');
   std::memcpy(&blob[o_map], cfg->field_map, cells);
   std::memcpy(&blob[o_per], period.data(), L);
   if (!bg.empty()) std::memcpy(&blob[o_bg], bg.data(), bg.size());
   if (!bt.empty()) std::memcpy(&blob[o_bt], bt.data(), bt.size());
   if (!rt.empty()) std::memcpy(&blob[o_rt], rt.data(), rt.size());
+  if (maze)  // packed (type | colour << 2) static map for partial views: Floor "background" white, Flag red, Obstacle grey (maze.py:183-198)
+    for (int i = 0; i < cells; ++i) {
+      const int c = cfg->field_map[i];
+      blob[o_pk + i] = (char)(c == 0 ? mg::cell(0, 10, 0) : (c == 2 ? mg::cell(2, 0, 0) : mg::cell(3, 7, 0)));
+    }
   if ((ce = cudaMalloc(&env->d_map_tables, total)) != cudaSuccess ||
       (ce = cudaMemcpy(env->d_map_tables, blob.data(), total, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess ||
@@ -343,6 +360,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   p.blue_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bt);
   p.red_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_rt);
   p.status = env->d_status; p.rng_mode = 1;
+  env->map_codes_off = o_pk;
   *out = env;
   return 0;
 }
@@ -444,6 +462,43 @@ extern "C" int mg_encode(mg_env* env, const void* state, uint8_t* obs, void* str
   if ((ce = mg::launch_encode3(env->tile, grid, obs, env->cfg.num_envs, env->cfg.width * env->cfg.height, aligned16(obs),
                                static_cast<cudaStream_t>(stream))) != cudaSuccess)
     return cuda_fail(env, "encode3_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_gen_obs(mg_env* env, const void* state, const uint8_t* dirs, int view_size, int see_through_walls,
+                          uint8_t* out, void* stream) {
+  if (!env || !state || !out) return fail(env, "mg_gen_obs: null argument");
+  if (env->family == MG_FAMILY_CTF) return fail(env, "mg_gen_obs: Collect and Maze families only");
+  if (view_size < 1 || view_size > mg::view_max()) return fail(env, "mg_gen_obs: view_size must be in [1, 15]");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  mg::ViewParams p;
+  std::memset(&p, 0, sizeof p);
+  const uint8_t* s = static_cast<const uint8_t*>(state);
+  p.V = view_size; p.see_through = see_through_walls != 0; p.family = env->family;
+  if (env->family == MG_FAMILY_COLLECT) {
+    p.W = env->cfg.width; p.H = env->cfg.height; p.A = env->cfg.num_agents; p.N = env->cfg.num_envs;
+    p.grid = s + env->plane_off[MG_PLANE_GRID]; p.pos = s + env->plane_off[MG_PLANE_AGENT_POS];
+    p.dirs = dirs;                                  // NULL = 3 for every agent
+    p.oob_code = mg::WALL_GREY;                     // Grid.slice: Wall(self.world) outside the grid (grid.py:124-127)
+  } else {
+    p.W = p.H = env->mcfg.size; p.A = 1; p.N = env->mcfg.num_envs;
+    p.pos = s + env->plane_off[MG_MAP_PLANE_POS];
+    p.dirs = dirs ? dirs : s + env->plane_off[MG_MAP_PLANE_DIR];
+    p.map_codes = env->d_map_tables + env->map_codes_off;
+    p.oob_code = mg::cell(3, 7, 1);                 // extension: MazeWorld has no wall (world.py:81-91); an opaque obstacle-coloured filler, state 1 marks it
+    p.agent_code = mg::cell(1, 4, 0);               // Agent(color="blue", type="agent") maze.py:93-101
+  }
+  p.cells = p.W * p.H;
+  p.out = out; p.out_bulk_ok = aligned16(out);
+  const size_t smem = mg::view_smem_bytes(p.family, p.cells, p.A, p.V);
+  if (smem > 227 * 1024) return fail(env, "mg_gen_obs: view tile does not fit in shared memory (reduce view_size)");
+  if (smem > env->view_smem_configured) {
+    if ((ce = mg::configure_view_kernels(smem)) != cudaSuccess) return cuda_fail(env, "cudaFuncSetAttribute", ce);
+    env->view_smem_configured = smem;
+  }
+  if ((ce = mg::launch_view(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "view_kernel", ce);
   env->launches += 1;
   return 0;
 }

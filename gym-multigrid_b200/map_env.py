@@ -231,6 +231,17 @@ class MazeVecEnv(_MapVecEnv):
         self.flag = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 2))]
 
 
+    def gen_obs(self, view_size=7, see_through_walls=False, out=None):
+        """Partial view of the maze (BASELINE config 4): reference dynamics x the reference's gen_obs algorithm
+        (multigrid.py:485-532) with MazeWorld encodings; u8 [N, 1, V, V, 3].  Cells outside the map show the filler
+        (3, 7, 1) - MazeWorld has no wall type, so this one code is an extension (see include/multigrid_b200.h)."""
+        V = int(view_size)
+        if out is None:
+            out = torch.empty((self.num_envs, 1, V, V, 3), dtype=torch.uint8, device=self.device)
+        self._check(self._lib.mg_gen_obs(self._h, _ptr(self.state), None, V, int(bool(see_through_walls)), _ptr(out), self._stream()))
+        return out
+
+
 class CtfVecEnv(_MapVecEnv):
     """`num_envs` x CtFMvNEnv (ctf.py:657-1433) with RwPolicy red agents (policy/ctf/heuristic.py:69-72) drawn on
     the device.  Observations: the "map" option - `_encode_map()` (transposed, [N, H, W]; uint8, or int64 with

@@ -215,6 +215,17 @@ class CollectVecEnv:
         self._check(self._lib.mg_encode(self._h, _ptr(self.state), _ptr(out), self._stream()))
         return out
 
+    def gen_obs(self, view_size=7, see_through_walls=False, dirs=None, out=None):
+        """Partial observations (MultiGridEnv.gen_obs, multigrid.py:485-532): u8 [N, A, V, V, 3], the egocentric
+        V x V window in front of each agent with MiniGrid-style occlusion.  `dirs` [N, A] overrides the agents'
+        directions (Collect agents always face 3 = up)."""
+        V = int(view_size)
+        if out is None:
+            out = torch.empty((self.num_envs, self.num_agents, V, V, 3), dtype=torch.uint8, device=self.device)
+        d = None if dirs is None else torch.as_tensor(dirs, device=self.device).to(torch.uint8).contiguous()
+        self._check(self._lib.mg_gen_obs(self._h, _ptr(self.state), _ptr(d), V, int(bool(see_through_walls)), _ptr(out), self._stream()))
+        return out
+
     def _info(self):
         info = {"pickups": self.pickups}
         if self._final_obs is not None:

@@ -123,6 +123,15 @@ int mg_step(mg_env* env, void* state_dev, const mg_step_io* io_dev, void* stream
 /* Grid.encode alone: state grid plane -> obs (grid.py:223-252). */
 int mg_encode(mg_env* env, const void* state_dev, uint8_t* obs_dev, void* stream);
 
+/* MultiGridEnv.gen_obs (multigrid.py:485-532): per agent the egocentric view_size x view_size window in front of
+ * the agent (slice + rotate_left x (dir+1) + process_vis + encode_for_agents), out u8 [N][A][V][V][3].
+ * dirs_dev: u8 [N][A] agent directions or NULL (Collect: 3, the only direction its agents ever have; Maze: the
+ * state's dir plane).  Collect: cells outside the grid are grey walls (grid.py:124-127).  Maze (a composition the
+ * reference does not ship: MazeWorld has no wall, world.py:81-91): outside cells are an opaque obstacle-coloured
+ * filler (3, 7, 1) -- an extension, parity unpinned for that one code. */
+int mg_gen_obs(mg_env* env, const void* state_dev, const uint8_t* dirs_dev, int view_size, int see_through_walls,
+               uint8_t* out_dev, void* stream);
+
 /* Same as mg_step with HOST buffers: copies actions host->device, steps, copies obs / rewards /
  * flags device->host and waits.  This is the call a gymnasium-style user makes with numpy
  * arrays; buffers should be page-locked for full PCIe bandwidth. */

@@ -160,12 +160,26 @@ def gen_ctf():
               f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_partial():
+    rh.import_reference()
+    parts = [rh.record_partial_views("multigrid-collect-rooms-respawn-v0", 11, 120),
+             rh.record_partial_views("multigrid-collect-respawn-clustered-v0", 12, 120),
+             rh.record_partial_views("multigrid-collect-quadrants15-v0", 13, 60)]
+    for stem, r in zip(("partial_rooms", "partial_clustered", "partial_quadrants15"), parts):
+        path = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path, **r)
+        print(f"{stem}: {len(r['V'])} states x {r['pos'].shape[1]} agents, V in {sorted(set(r['V'].tolist()))}, "
+              f"see_through in {sorted(set(r['see_through'].tolist()))}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "partial"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
         gen_maze()
     if "ctf" in which:
         gen_ctf()
+    if "partial" in which:
+        gen_partial()

@@ -348,3 +348,60 @@ int oc_collect_step(const oc_collect_cfg* c, int64_t N, oc_collect_state* st, co
   if (status) *status |= err;
   return rc ? -1 : 0;
 }
+
+/* ----------------------------------------------------------------------------- partial views */
+static uint8_t view_cell(const uint8_t* g, int W, int H, int x, int y, int oob) {
+  if (x < 0 || y < 0 || x >= W || y >= H) return (uint8_t)oob; /* Grid.slice: v = Wall(self.world) grid.py:124-127 */
+  return g[x * H + y];
+}
+
+void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* dirs, int64_t N, int W, int H, int A,
+                      int V, int see_through_walls, int oob_code, int opaque_rule, uint8_t* out) {
+  enum { VMAX = 32 };
+  if (V > VMAX || V < 1) return;
+  for (int64_t e = 0; e < N; ++e)
+    for (int k = 0; k < A; ++k) {
+      const uint8_t* g = grid + e * W * H;
+      const int x = pos[(e * A + k) * 2], y = pos[(e * A + k) * 2 + 1];
+      const int dir = dirs ? dirs[e * A + k] : 3;
+      uint8_t cell[VMAX][VMAX];
+      /* get_view_exts (agent.py:294-324) + slice + (dir+1) x rotate_left, folded into direct indices */
+      const int hs = V / 2;
+      for (int a = 0; a < V; ++a)
+        for (int b = 0; b < V; ++b) {
+          int wx, wy;
+          switch (dir) {
+          case 0: wx = x + V - 1 - b;      wy = y - hs + a;          break; /* facing right: one rotation   */
+          case 1: wx = x - hs + V - 1 - a; wy = y + V - 1 - b;       break; /* facing down:  two rotations  */
+          case 2: wx = x - V + 1 + b;      wy = y - hs + V - 1 - a;  break; /* facing left:  three rotations */
+          default: wx = x - hs + a;        wy = y - V + 1 + b;       break; /* facing up:    four = identity */
+          }
+          cell[a][b] = view_cell(g, W, H, wx, wy, oob_code);
+        }
+      uint8_t mask[VMAX][VMAX];
+      memset(mask, see_through_walls ? 1 : 0, sizeof mask);
+      if (!see_through_walls) { /* process_vis grid.py:286-323; only Wall blocks sight in CollectWorld (object.py:174-179) */
+        mask[hs][V - 1] = 1;
+        for (int j = V - 1; j >= 0; --j) {
+          for (int i = 0; i < V - 1; ++i) {
+            if (!mask[i][j]) continue;
+            if (opaque_rule == 0 ? (cell[i][j] & 3) == OC_T_WALL : cell[i][j] == oob_code) continue;
+            mask[i + 1][j] = 1;
+            if (j > 0) { mask[i + 1][j - 1] = 1; mask[i][j - 1] = 1; }
+          }
+          for (int i = V - 1; i >= 1; --i) {
+            if (!mask[i][j]) continue;
+            if (opaque_rule == 0 ? (cell[i][j] & 3) == OC_T_WALL : cell[i][j] == oob_code) continue;
+            mask[i - 1][j] = 1;
+            if (j > 0) { mask[i - 1][j - 1] = 1; mask[i][j - 1] = 1; }
+          }
+        }
+      }
+      uint8_t* o = out + ((e * A + k) * V * V) * 3;
+      for (int a = 0; a < V; ++a)
+        for (int b = 0; b < V; ++b) { /* encode_for_agents grid.py:254-284: unseen cells stay (0,0,0) */
+          const uint8_t c = mask[a][b] ? cell[a][b] : 0;
+          o[(a * V + b) * 3 + 0] = c & 3; o[(a * V + b) * 3 + 1] = (c >> 2) & 15; o[(a * V + b) * 3 + 2] = c >> 6;
+        }
+    }
+}

@@ -174,3 +174,17 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
 }
 #endif
 #endif
+
+/* ============================================================================ partial views
+ * MultiGridEnv.gen_obs (multigrid.py:485-532): per agent an egocentric V x V window in front of the
+ * agent = Grid.slice (grid.py:111-130, out-of-bounds -> Wall) + rotate_left x (dir+1) (grid.py:97-109) +
+ * process_vis (grid.py:286-323) + encode_for_agents (grid.py:254-284), encode_dim 3.
+ * grid: packed Collect cells [N][W*H]; pos [N][A][2]; dirs [N][A] (NULL = 3, the only direction a Collect
+ * agent ever has, multigrid.py:371-374).  out: u8 [N][A][V][V][3].
+ * oob_code: packed cell shown outside the grid (reference: grey Wall = OC_WALL_GREY); opaque_rule 0: walls block
+ * sight (reference); 1: only oob_code does (the Maze composition, an extension). */
+#ifdef __cplusplus
+extern "C"
+#endif
+void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* dirs, int64_t N, int W, int H, int A,
+                      int V, int see_through_walls, int oob_code, int opaque_rule, uint8_t* out);

@@ -320,3 +320,21 @@ class CtfOracle(_MapOracle):
 
     def step(self, blue_actions, rng, autoreset=False, want_final_obs=False):
         return self._call_step(lib().oc_ctf_step, np.asarray(blue_actions).reshape(self.N, self.nb), rng, autoreset, want_final_obs)
+
+
+def partial_view3(grid, pos, W, H, V, see_through_walls=False, dirs=None, oob_code=1 | 7 << 2, opaque_rule=0):
+    """MultiGridEnv.gen_obs for packed Collect grids [N, W*H] and agent positions [N, A, 2] -> [N, A, V, V, 3]."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    pos = np.ascontiguousarray(pos, np.uint8)
+    N, A = pos.shape[0], pos.shape[1]
+    out = np.zeros((N, A, V, V, 3), np.uint8)
+    dirs = None if dirs is None else np.ascontiguousarray(dirs, np.uint8)
+    lib().oc_partial_view3(_p(grid), _p(pos), _p(dirs), C.c_int64(N), C.c_int(W), C.c_int(H), C.c_int(A), C.c_int(V),
+                           C.c_int(int(see_through_walls)), C.c_int(int(oob_code)), C.c_int(int(opaque_rule)), _p(out))
+    return out
+
+
+def pack_obs(obs):
+    """Grid.encode() arrays [..., 3] -> packed cells type | colour << 2 | state << 6."""
+    o = np.asarray(obs, np.uint8)
+    return (o[..., 0] | (o[..., 1] << 2) | (o[..., 2] << 6)).astype(np.uint8)

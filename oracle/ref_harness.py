@@ -364,3 +364,40 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
     out["n_battles"] = out["n_battles"].astype(np.int32)
     out["reward"] = out["reward"].astype(np.float64)
     return out
+
+
+# ------------------------------------------------------------------- partial-view recording
+def record_partial_views(env_id, seed, n_samples, view_sizes=(3, 5, 7)):
+    """Reference partial observations (MultiGridEnv.gen_obs_grid multigrid.py:485-515 + Grid.encode_for_agents
+    grid.py:254-284) on states of a Collect env.  `gen_obs` itself passes one positional argument too many
+    (multigrid.py:526-528 vs grid.py:254) and raises TypeError, so its two steps are called directly - the
+    algorithm, not the crash.  Agent directions are set by hand (Collect never turns its agents)."""
+    env, tl = make_collect(env_id)
+    random.seed(seed); np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env.reset(seed=seed)
+    A = len(env.agents)
+    out = dict(grid_obs=[], pos=[], dirs=[], V=[], see_through=[], views=[])
+    for s in range(n_samples):
+        for _ in range(int(rng.integers(1, 6))):
+            _, _, term, trunc, _ = env.step([int(a) for a in rng.integers(0, 4, size=A)])
+            if term or trunc or env.step_count >= 45:
+                env.reset(seed=seed + s)
+        V = int(rng.choice(view_sizes))
+        st = bool(rng.integers(0, 2))
+        for a in env.agents:
+            a.dir = int(rng.integers(0, 4))
+            a.view_size = V
+        env.see_through_walls = st
+        grids, masks = env.gen_obs_grid()
+        views = [g.encode_for_agents(agent_pos=(V // 2, V - 1), vis_mask=m) for g, m in zip(grids, masks)]
+        pad = np.zeros((A, max(view_sizes), max(view_sizes), 3), np.uint8)
+        for k, v in enumerate(views):
+            pad[k, :V, :V] = v
+        out["grid_obs"].append(env.grid.encode().copy())
+        out["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+        out["dirs"].append(np.array([a.dir for a in env.agents], np.int8))
+        out["V"].append(V); out["see_through"].append(st); out["views"].append(pad)
+        for a in env.agents:   # Collect expects dir 3 forever
+            a.dir = 3
+    return {k: np.array(v) for k, v in out.items()}

@@ -176,8 +176,8 @@ def test_maze_invariants_at_scale(cuda_device):
         assert bool(((obs != 1) <= (obs == fm[None])).all()), "everything else is the static map"
         p = env.agent_pos[:, 0].long()
         assert bool((fm[p[:, 0], p[:, 1]] != 3).all()), "penalty 0: never on an obstacle"
-        if t % 100:
-            assert not bool(trunc.any())
+        assert bool((env.step_count[term | trunc] == 0).all()), "finished envs were reset in the same step"
+        assert bool((env.step_count[~(term | trunc)] > 0).all())
     assert env.status() == 0
     env.close()
 

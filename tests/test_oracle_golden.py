@@ -120,3 +120,18 @@ def test_oracle_openmp_threads_agree():
         res.append((obs, rew, o.grid.copy(), o.rng_ctr.copy()))
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("stem", ["partial_rooms", "partial_clustered", "partial_quadrants15"])
+def test_partial_view_matches_reference(stem):
+    """MultiGridEnv.gen_obs_grid + encode_for_agents of the reference vs the oracle's direct-index form,
+    all four directions, V in {3,5,7}, with and without see_through_walls (incl. two agents on one cell)."""
+    g = load_golden(stem)
+    W = g["grid_obs"].shape[1]
+    seen = set()
+    for i in range(len(g["V"])):
+        V, st = int(g["V"][i]), bool(g["see_through"][i])
+        out = oc.partial_view3(oc.pack_obs(g["grid_obs"][i]).reshape(1, -1), g["pos"][i][None], W, W, V, st, dirs=g["dirs"][i][None])
+        assert np.array_equal(out[0], g["views"][i][:, :V, :V]), f"state {i}"
+        seen |= {(V, st, int(d)) for d in g["dirs"][i]}
+    assert len(seen) >= 20

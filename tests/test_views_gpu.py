@@ -1,0 +1,77 @@
+"""GPU parity for partial observations (MultiGridEnv.gen_obs) through mg_gen_obs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as oc
+from replay import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("stem,env_id", [("partial_rooms", "multigrid-collect-rooms-respawn-v0"),
+                                         ("partial_clustered", "multigrid-collect-respawn-clustered-v0"),
+                                         ("partial_quadrants15", "multigrid-collect-quadrants15-v0")])
+def test_collect_views_match_reference(stem, env_id, cuda_device):
+    """The reference's gen_obs_grid + encode_for_agents outputs, every recorded state, grouped by (V, see_through)."""
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    for V in (3, 5, 7):
+        for st in (False, True):
+            sel = np.where((g["V"] == V) & (g["see_through"] == st))[0]
+            if len(sel) == 0:
+                continue
+            env = mg.make_vec(env_id, len(sel), autoreset=False)
+            env.set_state_from_obs(g["grid_obs"][sel], g["pos"][sel])
+            out = env.gen_obs(view_size=V, see_through_walls=st, dirs=g["dirs"][sel])
+            assert np.array_equal(_np(out), g["views"][sel][:, :, :V, :V]), f"V={V} see_through={st}"
+            env.close()
+
+
+@pytest.mark.parametrize("V", [1, 3, 7, 9, 15])
+def test_collect_views_match_oracle_at_scale(V, cuda_device):
+    import gym_multigrid_b200 as mg
+    n = 5000
+    env = mg.make_vec("multigrid-collect-rooms-respawn-v0", n, seed=3)
+    env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(1)
+    for _ in range(7):
+        env.step(torch.randint(0, 4, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8))
+    dirs = torch.randint(0, 4, (n, 2), generator=gen, device=cuda_device, dtype=torch.uint8)
+    for st in (False, True):
+        out = env.gen_obs(view_size=V, see_through_walls=st, dirs=dirs)
+        want = oc.partial_view3(_np(env.grid), _np(env.agent_pos), 10, 10, V, st, dirs=_np(dirs))
+        assert np.array_equal(_np(out), want)
+    out = env.gen_obs(view_size=V)   # default: every Collect agent faces up (dir 3)
+    assert np.array_equal(_np(out), oc.partial_view3(_np(env.grid), _np(env.agent_pos), 10, 10, V, False))
+    env.close()
+
+
+@pytest.mark.parametrize("stem", ["maze_board13", "maze_gen64"])
+def test_maze_views_match_composed_oracle(stem, cuda_device):
+    """BASELINE config 4 (Maze + partial view): reference dynamics x the reference's gen_obs algorithm.  The oracle side
+    draws each env's MazeWorld grid (Floor white / Flag red / Obstacle grey / Agent blue) and runs the pinned
+    partial-view restatement on it; cells outside the map use the documented filler (3, 7, 1)."""
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    fm = g["field_map"]
+    S = fm.shape[0]
+    n = 777
+    env = mg.make_maze_vec(n, fm, seed=5)
+    env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(2)
+    packed_map = np.where(fm == 0, 0 | 10 << 2, np.where(fm == 2, 2 | 0 << 2, 3 | 7 << 2)).astype(np.uint8)
+    for t in range(12):
+        env.step(torch.randint(0, 5, (n,), generator=gen, device=cuda_device, dtype=torch.int8))
+        pos, d = _np(env.agent_pos), _np(env.agent_dir)
+        grids = np.repeat(packed_map.reshape(1, -1), n, axis=0)
+        grids[np.arange(n), pos[:, 0, 0].astype(int) * S + pos[:, 0, 1]] = (1 | 4 << 2) | (d[:, 0] << 6)
+        for V, st in ((7, False), (5, True)):
+            out = env.gen_obs(view_size=V, see_through_walls=st)
+            want = oc.partial_view3(grids, pos, S, S, V, st, dirs=d, oob_code=3 | 7 << 2 | 1 << 6, opaque_rule=1)
+            assert np.array_equal(_np(out), want), f"step {t} V={V}"
+    env.close()
