@@ -24,7 +24,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     lib.mg_create_map.argtypes = [C.POINTER(MapConfig), C.c_int, C.POINTER(C.c_void_p)]
     lib.mg_set_map_trace.argtypes = [C.c_void_p, C.POINTER(MapTrace)]
     lib.mg_gen_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.mg_toroid_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mg_launch_count.restype = C.c_int64
     lib.mg_launch_count.argtypes = [C.c_void_p]
     if lib.mg_abi_version() != 1:

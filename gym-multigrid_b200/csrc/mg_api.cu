@@ -31,6 +31,7 @@ int map_tile_envs();
 #include "view_params.cuh"
 namespace mg {
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
+cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
 cudaError_t configure_view_kernels(size_t bytes);
 size_t view_smem_bytes(int family, int cells, int A, int V);
 int view_max();
@@ -499,6 +500,20 @@ extern "C" int mg_gen_obs(mg_env* env, const void* state, const uint8_t* dirs, i
     env->view_smem_configured = smem;
   }
   if ((ce = mg::launch_view(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "view_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_toroid_obs(mg_env* env, const void* state, float* out, void* stream) {
+  if (!env || !state || !out) return fail(env, "mg_toroid_obs: null argument");
+  if (env->family != MG_FAMILY_COLLECT) return fail(env, "mg_toroid_obs: Collect family only (wrappers/toroid.py wraps CollectGameEnv)");
+  if (env->cfg.width != env->cfg.height) return fail(env, "mg_toroid_obs: square grids only (the reference indexes [y][x] into a (W, H) array)");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  const uint8_t* s = static_cast<const uint8_t*>(state);
+  if ((ce = mg::launch_toroid(s + env->plane_off[MG_PLANE_GRID], s + env->plane_off[MG_PLANE_AGENT_POS], out, env->cfg.num_envs,
+                              env->cfg.width, env->cfg.num_agents, env->cfg.num_ball_types, static_cast<cudaStream_t>(stream))) != cudaSuccess)
+    return cuda_fail(env, "toroid_kernel", ce);
   env->launches += 1;
   return 0;
 }

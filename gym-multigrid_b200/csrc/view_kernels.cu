@@ -114,6 +114,42 @@ __global__ void __launch_bounds__(kViewThreads) view_kernel(const __grid_constan
   if (tid == 0) tma_wait_read_all();
 }
 
+// ToroidObservation.observation (wrappers/toroid.py:28-68): agent-centred, wrap-around one-hot planes,
+// float32 [N][A][W][W][depth], depth = num_ball_types + num_agents; written at [y'][x'] like the reference.
+// One thread per output cell (gathers its source cell), so every warp writes one contiguous run of floats.
+__global__ void __launch_bounds__(256) toroid_kernel(const uint8_t* __restrict__ grid, const uint8_t* __restrict__ pos,
+                                                     float* __restrict__ out, long long N, int W, int A, int nb) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cells = W * W, depth = nb + A;
+  const long long total = N * A * cells;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long v = idx / cells;             // view index e*A + k
+    const int c = (int)(idx - v * cells);
+    const int ny = c / W, nx = c - ny * W;       // tor[new_coords[1], new_coords[0], ...]  toroid.py:58-66
+    const long long e = v / A;
+    const int px = pos[v * 2], py = pos[v * 2 + 1];
+    int i = nx + px, j = ny + py;                // inverse of new = (i - px, j - py) wrapped into [0, W)
+    if (i >= W) i -= W;
+    if (j >= W) j -= W;
+    const uint8_t code = grid[e * cells + i * W + j];
+    const int type = code & 3;
+    int ch = -1;
+    if (type == T_WALL) ch = depth - 1;
+    else if (type == T_BALL) ch = (code >> 2) & 15;
+    else if (type == T_AGENT && !(i == px && j == py)) ch = depth - 2;  // another agent, not on this agent's cell
+    float* o = out + idx * depth;
+    for (int d = 0; d < depth; ++d) o[d] = (d == ch) ? 1.0f : 0.0f;
+  }
+}
+
+cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st) {
+  const long long total = N * A * W * W;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  toroid_kernel<<<blocks, 256, 0, st>>>(grid, pos, out, N, W, A, nb);
+  return cudaGetLastError();
+}
+
 size_t view_smem_bytes(int family, int cells, int A, int V) {
   return (size_t)kViewE * A * V * V * 3 + (size_t)kViewThreads * V * V + 16 +
          (family == MG_FAMILY_COLLECT ? (size_t)kViewE * cells : 0);

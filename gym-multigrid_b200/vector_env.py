@@ -226,6 +226,14 @@ class CollectVecEnv:
         self._check(self._lib.mg_gen_obs(self._h, _ptr(self.state), _ptr(d), V, int(bool(see_through_walls)), _ptr(out), self._stream()))
         return out
 
+    def toroid_obs(self, out=None):
+        """ToroidObservation (wrappers/toroid.py:28-68) of the current state: float32 [N, A, W, H, nb + A]."""
+        if out is None:
+            out = torch.empty((self.num_envs, self.num_agents, self.width, self.height, self.num_ball_types + self.num_agents),
+                              dtype=torch.float32, device=self.device)
+        self._check(self._lib.mg_toroid_obs(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
+
     def _info(self):
         info = {"pickups": self.pickups}
         if self._final_obs is not None:

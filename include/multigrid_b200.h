@@ -132,6 +132,10 @@ int mg_encode(mg_env* env, const void* state_dev, uint8_t* obs_dev, void* stream
 int mg_gen_obs(mg_env* env, const void* state_dev, const uint8_t* dirs_dev, int view_size, int see_through_walls,
                uint8_t* out_dev, void* stream);
 
+/* ToroidObservation.observation (wrappers/toroid.py:28-68) for every env and agent: agent-centred wrap-around
+ * one-hot planes, out f32 [N][A][W][H][num_ball_types + num_agents].  Collect family, square grids. */
+int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stream);
+
 /* Same as mg_step with HOST buffers: copies actions host->device, steps, copies obs / rewards /
  * flags device->host and waits.  This is the call a gymnasium-style user makes with numpy
  * arrays; buffers should be page-locked for full PCIe bandwidth. */

@@ -172,9 +172,19 @@ def gen_partial():
               f"see_through in {sorted(set(r['see_through'].tolist()))}, {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def gen_toroid():
+    for stem, env_id, n in (("toroid_clustered", "multigrid-collect-respawn-clustered-v0", 40),
+                            ("toroid_rooms", "multigrid-collect-rooms-respawn-v0", 40),
+                            ("toroid_single", "multigrid-collect-single-v0", 20)):
+        r = rh.record_toroid(env_id, 21, n)
+        path = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path, **r)
+        print(f"{stem}: {n} states, toroid {r['toroid'].shape} {r['toroid'].dtype}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "partial"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "partial", "toroid"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -183,3 +193,5 @@ if __name__ == "__main__":
         gen_ctf()
     if "partial" in which:
         gen_partial()
+    if "toroid" in which:
+        gen_toroid()

@@ -405,3 +405,28 @@ void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* di
         }
     }
 }
+
+/* ------------------------------------------------------------------------------ Toroid wrapper */
+void oc_toroid(const uint8_t* grid, const uint8_t* pos, int64_t N, int W, int A, int nb, float* out) {
+  const int depth = nb + A; /* toroid.py:24 */
+  memset(out, 0, (size_t)N * A * W * W * depth * sizeof(float));
+  for (int64_t e = 0; e < N; ++e)
+    for (int k = 0; k < A; ++k) {
+      const int px = pos[(e * A + k) * 2], py = pos[(e * A + k) * 2 + 1];
+      float* tor = out + ((e * A + k) * W * W) * depth;
+      for (int i = 0; i < W; ++i)
+        for (int j = 0; j < W; ++j) { /* toroid.py:46-66 */
+          int nx = i - px, ny = j - py;
+          if (nx < 0) nx += W;
+          if (ny < 0) ny += W;
+          const uint8_t c = grid[e * W * W + i * W + j];
+          const int type = c & 3, colour = (c >> 2) & 15;
+          if (c == 0) continue;
+          int ch = -1;
+          if (type == OC_T_WALL) ch = depth - 1;
+          else if (type == OC_T_BALL) ch = colour;
+          else if (type == OC_T_AGENT && !(i == px && j == py)) ch = depth - 2; /* obj.pos != this agent's pos */
+          if (ch >= 0 && ch < depth) tor[(ny * W + nx) * depth + ch] = 1.0f;
+        }
+    }
+}

@@ -188,3 +188,12 @@ extern "C"
 #endif
 void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* dirs, int64_t N, int W, int H, int A,
                       int V, int see_through_walls, int oob_code, int opaque_rule, uint8_t* out);
+
+/* ToroidObservation.observation (wrappers/toroid.py:28-68): per agent an agent-centred, wrap-around one-hot
+ * float32 tensor [W][H][depth], depth = num_ball_types + num_agents, written at [y'][x'] (the reference's axis
+ * swap), channels: ball colour index | depth-2 = another agent (at a different cell) | depth-1 = wall.
+ * grid: packed Collect cells [N][W*H] (square); out: f32 [N][A][W][H][depth]. */
+#ifdef __cplusplus
+extern "C"
+#endif
+void oc_toroid(const uint8_t* grid, const uint8_t* pos, int64_t N, int W, int A, int num_ball_types, float* out);

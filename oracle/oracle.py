@@ -338,3 +338,13 @@ def pack_obs(obs):
     """Grid.encode() arrays [..., 3] -> packed cells type | colour << 2 | state << 6."""
     o = np.asarray(obs, np.uint8)
     return (o[..., 0] | (o[..., 1] << 2) | (o[..., 2] << 6)).astype(np.uint8)
+
+
+def toroid(grid, pos, W, num_ball_types):
+    """ToroidObservation (wrappers/toroid.py) for packed Collect grids [N, W*W] -> float32 [N, A, W, W, nb + A]."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    pos = np.ascontiguousarray(pos, np.uint8)
+    N, A = pos.shape[0], pos.shape[1]
+    out = np.zeros((N, A, W, W, num_ball_types + A), np.float32)
+    lib().oc_toroid(_p(grid), _p(pos), C.c_int64(N), C.c_int(W), C.c_int(A), C.c_int(num_ball_types), _p(out))
+    return out

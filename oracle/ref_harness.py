@@ -401,3 +401,28 @@ def record_partial_views(env_id, seed, n_samples, view_sizes=(3, 5, 7)):
         for a in env.agents:   # Collect expects dir 3 forever
             a.dir = 3
     return {k: np.array(v) for k, v in out.items()}
+
+
+# --------------------------------------------------------------------- Toroid wrapper recording
+def record_toroid(env_id, seed, n_samples):
+    """Reference ToroidObservation (wrappers/toroid.py:6-68) outputs on states of a Collect env."""
+    import_reference()
+    from gym_multigrid.wrappers.toroid import ToroidObservation
+    env, tl = make_collect(env_id)
+    random.seed(seed); np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    wrapped = ToroidObservation(env)
+    env.reset(seed=seed)
+    A = len(env.agents)
+    out = dict(grid_obs=[], pos=[], toroid=[])
+    for s in range(n_samples):
+        for _ in range(int(rng.integers(1, 5))):
+            _, _, term, trunc, _ = env.step([int(a) for a in rng.integers(0, 4, size=A)])
+            if term or trunc or env.step_count >= 45:
+                env.reset(seed=seed + s)
+        tor = wrapped.observation(env.grid.encode())
+        assert all(t.dtype == np.float32 for t in tor)
+        out["grid_obs"].append(env.grid.encode().copy())
+        out["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+        out["toroid"].append(np.stack(tor))
+    return {k: np.array(v) for k, v in out.items()}

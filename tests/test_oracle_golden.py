@@ -135,3 +135,11 @@ def test_partial_view_matches_reference(stem):
         assert np.array_equal(out[0], g["views"][i][:, :V, :V]), f"state {i}"
         seen |= {(V, st, int(d)) for d in g["dirs"][i]}
     assert len(seen) >= 20
+
+
+@pytest.mark.parametrize("stem", ["toroid_clustered", "toroid_rooms", "toroid_single"])
+def test_toroid_matches_reference(stem):
+    g = load_golden(stem)
+    W = g["grid_obs"].shape[1]
+    out = oc.toroid(oc.pack_obs(g["grid_obs"]).reshape(len(g["pos"]), -1), g["pos"], W, 3)
+    assert out.dtype == np.float32 and np.array_equal(out, g["toroid"])

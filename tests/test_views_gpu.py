@@ -75,3 +75,34 @@ def test_maze_views_match_composed_oracle(stem, cuda_device):
             want = oc.partial_view3(grids, pos, S, S, V, st, dirs=d, oob_code=3 | 7 << 2 | 1 << 6, opaque_rule=1)
             assert np.array_equal(_np(out), want), f"step {t} V={V}"
     env.close()
+
+
+@pytest.mark.parametrize("stem,env_id", [("toroid_clustered", "multigrid-collect-respawn-clustered-v0"),
+                                         ("toroid_rooms", "multigrid-collect-rooms-respawn-v0"),
+                                         ("toroid_single", "multigrid-collect-single-v0")])
+def test_toroid_matches_reference(stem, env_id, cuda_device):
+    """The reference's ToroidObservation.observation outputs on recorded states (incl. single-agent depth 4)."""
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.wrappers import ToroidObservation
+    g = load_golden(stem)
+    n = len(g["pos"])
+    env = ToroidObservation(mg.make_vec(env_id, n, autoreset=False))
+    env.env.set_state_from_obs(g["grid_obs"], g["pos"])
+    out = env.observation()
+    assert out.dtype == torch.float32 and tuple(out.shape) == g["toroid"].shape
+    assert np.array_equal(_np(out), g["toroid"])
+    env.close()
+
+
+def test_toroid_wrapper_matches_oracle_while_stepping(cuda_device):
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.wrappers import ToroidObservation
+    n = 3000
+    env = ToroidObservation(mg.make_vec("multigrid-collect-rooms-respawn-v0", n, seed=8))
+    obs, _ = env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(4)
+    for t in range(60):
+        obs, rew, term, trunc, _ = env.step(torch.randint(0, 4, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8))
+        if t % 10 == 9:
+            assert np.array_equal(_np(obs), oc.toroid(_np(env.grid), _np(env.agent_pos), 10, 3))
+    env.close()
