@@ -53,3 +53,9 @@ def make_ctf_vec(num_envs: int, map_path, **kwargs):
     """Batched `CtFMvNEnv` (envs/ctf.py:657-1433); kwargs as the reference constructor (ctf.py:662-679)."""
     from .map_env import CtfVecEnv
     return CtfVecEnv(num_envs, map_path, **kwargs)
+
+
+def make_wildfire_vec(num_envs: int, **kwargs):
+    """Batched Wildfire (extension; the reference has no Wildfire code - see include/multigrid_b200.h for the rules)."""
+    from .wildfire_env import WildfireVecEnv
+    return WildfireVecEnv(num_envs, **kwargs)

@@ -12,7 +12,9 @@ from ._build import LIB_PATH
 
 MAX_AGENTS = 8
 MAX_BALL_TYPES = 8
-FAMILY_COLLECT, FAMILY_MAZE, FAMILY_CTF = 0, 1, 2
+FAMILY_COLLECT, FAMILY_MAZE, FAMILY_CTF, FAMILY_WILDFIRE = 0, 1, 2, 3
+WF_PLANE_TERRAIN, WF_PLANE_AGENTS, WF_PLANE_HDR = 0, 1, 2
+MAX_WILDFIRE_AGENTS = 32
 OBS_U8, OBS_REFERENCE = 0, 1
 MAP_PLANE_POS, MAP_PLANE_DIR, MAP_PLANE_FLAGS, MAP_PLANE_HDR = 0, 1, 2, 3
 ERR_BAD_ACTION = 8
@@ -24,7 +26,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire",
 ]
 
 
@@ -57,6 +59,15 @@ class MapConfig(C.Structure):
         ("flag_reward", C.c_double), ("battle_reward", C.c_double), ("obstacle_penalty", C.c_double),
         ("step_penalty", C.c_double), ("battle_range", C.c_double), ("randomness", C.c_double),
         ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("obs_dtype", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
+class WildfireConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("family", C.c_int32), ("num_envs", C.c_int64), ("env_id_base", C.c_int64),
+        ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32), ("agent_colour", C.c_int32 * 32),
+        ("num_fires", C.c_int32), ("ignite_threshold", C.c_uint32 * 5), ("burnout_threshold", C.c_uint32),
+        ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("seed", C.c_uint64),
     ]
 
 
@@ -107,6 +118,8 @@ def load():
     lib.mg_set_map_trace.argtypes = [C.c_void_p, C.POINTER(MapTrace)]
     lib.mg_gen_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.mg_toroid_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mg_create_wildfire.restype = C.c_int
+    lib.mg_create_wildfire.argtypes = [C.POINTER(WildfireConfig), C.c_int, C.POINTER(C.c_void_p)]
     lib.mg_launch_count.restype = C.c_int64
     lib.mg_launch_count.argtypes = [C.c_void_p]
     if lib.mg_abi_version() != 1:

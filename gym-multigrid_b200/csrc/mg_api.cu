@@ -29,6 +29,7 @@ int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
 #include "view_params.cuh"
+#include "wildfire_params.cuh"
 namespace mg {
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
@@ -36,6 +37,9 @@ cudaError_t configure_view_kernels(size_t bytes);
 size_t view_smem_bytes(int family, int cells, int A, int V);
 int view_max();
 int view_tile_envs();
+cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st);
+cudaError_t configure_wildfire_kernel(int cells);
+size_t wildfire_smem_bytes(int cells);
 }  // namespace mg
 
 struct mg_env {
@@ -43,6 +47,8 @@ struct mg_env {
   mg_config cfg;
   mg_map_config mcfg;
   mg::MapParams mbase;
+  mg_wildfire_config wcfg;
+  mg::WildfireParams wbase;
   mg_map_trace mtrace;
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
@@ -218,11 +224,12 @@ extern "C" int mg_destroy(mg_env* env) {
 extern "C" size_t mg_state_bytes(const mg_env* env) { return env ? env->state_bytes : 0; }
 extern "C" size_t mg_obs_bytes(const mg_env* env) {
   if (!env) return 0;
+  if (env->family == MG_FAMILY_WILDFIRE) return (size_t)env->wcfg.num_envs * env->wcfg.width * env->wcfg.height * 3;
   if (env->family != MG_FAMILY_COLLECT) return (size_t)env->mcfg.num_envs * env->mcfg.size * env->mcfg.size * env->obs_elem;
   return (size_t)env->cfg.num_envs * env->cfg.width * env->cfg.height * 3;
 }
 extern "C" int mg_state_plane(const mg_env* env, int plane, size_t* offset, size_t* bytes, size_t* row_bytes) {
-  if (!env || plane < 0 || plane >= MG_PLANE_COUNT) return -1;  // (MG_MAP_PLANE_COUNT == MG_PLANE_COUNT)
+  if (!env || plane < 0 || plane >= (env->family == MG_FAMILY_WILDFIRE ? (int)MG_WF_PLANE_COUNT : (int)MG_PLANE_COUNT)) return -1;
   if (offset) *offset = env->plane_off[plane];
   if (bytes) *bytes = env->plane_bytes[plane];
   if (row_bytes) *row_bytes = env->plane_row[plane];
@@ -404,6 +411,83 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
   return 0;
 }
 
+// -------------------------------------------------------------------------------- Wildfire
+extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_env** out) {
+  if (!cfg || !out) return fail(nullptr, "mg_create_wildfire: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(mg_wildfire_config)) return fail(nullptr, "mg_create_wildfire: mg_wildfire_config size mismatch (ABI)");
+  if (cfg->family != MG_FAMILY_WILDFIRE) return fail(nullptr, "mg_create_wildfire: family must be MG_FAMILY_WILDFIRE");
+  const int W = cfg->width, H = cfg->height, cells = W * H, A = cfg->num_agents;
+  if (cfg->num_envs < 1) return fail(nullptr, "mg_create_wildfire: num_envs must be >= 1");
+  if (W < 2 || H < 2 || W > 255 || H > 255 || cells % 16) return fail(nullptr, "mg_create_wildfire: need 2 <= W, H <= 255 and W*H a multiple of 16 (TMA tiles)");
+  if (A < 1 || A > MG_MAX_WILDFIRE_AGENTS) return fail(nullptr, "mg_create_wildfire: num_agents must be in [1, 32] (one warp resolves the moves)");
+  if (cfg->num_fires < 0 || cfg->num_fires + A > cells) return fail(nullptr, "mg_create_wildfire: num_fires + num_agents exceed the grid");
+  if (cfg->max_steps < 1) return fail(nullptr, "mg_create_wildfire: max_steps must be >= 1");
+  for (int i = 0; i < A; ++i)
+    if (cfg->agent_colour[i] < 0 || cfg->agent_colour[i] > 9) return fail(nullptr, "mg_create_wildfire: agent colour index outside COLORS");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, std::string("mg_create_wildfire: no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, "mg_create_wildfire: device index out of range");
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, "cudaSetDevice", ce);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
+  if (prop.major != 10) return fail(nullptr, "mg_create_wildfire: kernels are built for sm_100a only");
+  if (mg::wildfire_smem_bytes(cells) > (size_t)prop.sharedMemPerBlockOptin) return fail(nullptr, "mg_create_wildfire: grid too large for one CTA's shared memory");
+  if ((ce = mg::configure_wildfire_kernel(cells)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
+  mg_env* env = new (std::nothrow) mg_env();
+  if (!env) return fail(nullptr, "mg_create_wildfire: out of host memory");
+  env->family = MG_FAMILY_WILDFIRE;
+  env->wcfg = *cfg;
+  env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
+  env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
+  env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
+  env->view_smem_configured = 0; env->map_codes_off = 0;
+  std::memset(&env->trace, 0, sizeof env->trace);
+  env->obs_elem = 1; env->act_cols = A; env->rew_cols = A;
+  env->n_pad = cfg->num_envs;
+  const size_t rows[MG_WF_PLANE_COUNT] = {(size_t)cells, (size_t)A * 4, 16};
+  size_t off = 0;
+  for (int i = 0; i < MG_WF_PLANE_COUNT; ++i) {
+    env->plane_off[i] = off; env->plane_row[i] = rows[i]; env->plane_bytes[i] = rows[i] * (size_t)env->n_pad;
+    off = align_up(off + env->plane_bytes[i], 256);
+  }
+  env->state_bytes = off;
+  if ((ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess || (ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) {
+    cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "cudaMalloc(status)", ce);
+  }
+  mg::WildfireParams& p = env->wbase;
+  std::memset(&p, 0, sizeof p);
+  p.W = W; p.H = H; p.cells = cells; p.A = A; p.num_fires = cfg->num_fires; p.max_steps = cfg->max_steps; p.autoreset = cfg->autoreset != 0;
+  for (int k = 0; k < 5; ++k) p.ignite_threshold[k] = cfg->ignite_threshold[k];
+  p.burnout_threshold = cfg->burnout_threshold;
+  for (int i = 0; i < A; ++i) p.agent_colour[i] = (uint8_t)cfg->agent_colour[i];
+  p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
+  *out = env;
+  return 0;
+}
+
+static int wildfire_launch(mg_env* env, void* state, int op, const mg_step_io* io, const uint8_t* mask, uint8_t* obs, cudaStream_t st) {
+  mg::WildfireParams p = env->wbase;
+  uint8_t* s = static_cast<uint8_t*>(state);
+  p.terrain = s + env->plane_off[MG_WF_PLANE_TERRAIN]; p.agents = s + env->plane_off[MG_WF_PLANE_AGENTS];
+  p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_WF_PLANE_HDR]);
+  p.op = op; p.reset_mask = mask;
+  p.order = env->has_trace ? env->trace.order : nullptr;
+  if (op == 1) {
+    p.actions = io->actions; p.obs = io->obs; p.rewards = io->rewards; p.terminated = io->terminated;
+    p.truncated = io->truncated; p.final_obs = io->final_obs;
+  } else {
+    p.obs = obs;
+  }
+  if ((p.obs && !aligned16(p.obs)) || (p.final_obs && !aligned16(p.final_obs))) return fail(env, "obs buffers must be 16-byte aligned");
+  cudaError_t ce;
+  if ((ce = mg::launch_wildfire(p, st)) != cudaSuccess) return cuda_fail(env, "wildfire_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
 extern "C" int mg_set_trace(mg_env* env, const mg_trace* t) {
   if (!env) return -1;
   if (!t) { env->has_trace = false; return 0; }
@@ -417,6 +501,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   if (!aligned16(state)) return fail(env, "mg_reset: state buffer must be 16-byte aligned");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
   if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
@@ -430,6 +515,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
 static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
   if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
+  if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 1, io, nullptr, nullptr, st);
   if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 1, io, nullptr, nullptr, st);
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
@@ -524,7 +610,7 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->mcfg.num_envs);
+  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs : env->mcfg.num_envs);
   const size_t A = (size_t)env->act_cols, R = (size_t)env->rew_cols, ob = mg_obs_bytes(env);
   if (!env->d_actions) {
     if ((ce = cudaMalloc(&env->d_actions, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
@@ -570,6 +656,7 @@ extern "C" int mg_debug_set_timeline(mg_env* env, uint64_t* timeline_dev) {
 
 extern "C" int mg_tile_envs(const mg_env* env) {
   if (!env) return -1;
+  if (env->family == MG_FAMILY_WILDFIRE) return 1;
   return env->family == MG_FAMILY_COLLECT ? mg::tile_envs(env->tile) : mg::map_tile_envs();
 }
 

@@ -29,7 +29,7 @@ extern "C" {
 #define MG_MAX_BALL_TYPES 8
 
 /* env families (reference: gym_multigrid/envs/{collect_game,maze,ctf}.py) */
-enum { MG_FAMILY_COLLECT = 0, MG_FAMILY_MAZE = 1, MG_FAMILY_CTF = 2 };
+enum { MG_FAMILY_COLLECT = 0, MG_FAMILY_MAZE = 1, MG_FAMILY_CTF = 2, MG_FAMILY_WILDFIRE = 3 };
 
 /* Collect layouts = the reference's _gen_grid variants */
 enum { MG_LAYOUT_EVEN_DIST = 0,         /* CollectGameEvenDist          collect_game.py:227-259 */
@@ -213,6 +213,50 @@ typedef struct mg_map_trace {
  * _encode_map().T ctf.py:1137-1163). */
 int mg_create_map(const mg_map_config* cfg, int device, mg_env** out);
 int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
+
+/* ========================================================================================= Wildfire
+ * EXTENSION: the reference has no Wildfire code (only a README heading, README.md:43); BASELINE.json config 5
+ * asks for it, so the rules below are OUR specification (docs in DESIGN.md section 10), checked against an
+ * in-repo CPU oracle (oracle/mg_oracle_wildfire.c) - parity vs the reference is unpinned by construction.
+ *
+ * World: every cell of a W x H grid is a tree: healthy (0), burning (1) or burnt (2); up to 32 agents walk on
+ * top (5-way CtfActions: 0 stay, 1 left (0,-1), 2 down (-1,0), 3 right (0,+1), 4 up (+1,0)).  One step:
+ *   1. step_count += 1, tick += 1
+ *   2. agents act in a per-step random order (Philox Fisher-Yates, or replayed): the target cell is entered
+ *      unless it is off the grid or holds another agent (order-dependent blocking, as in CtF); dir follows
+ *      DIR_TO_VEC; then, moved or not, a burning cell under the agent is extinguished (-> burnt), reward[i] += 1
+ *   3. fire dynamics from the post-agent terrain (double-buffered stencil): a burning cell burns out (-> burnt)
+ *      iff u < burnout_threshold; a healthy cell with k >= 1 burning 4-neighbours ignites iff u < ignite_threshold[k];
+ *      u = word (cell & 3) of Philox4x32-10(key = seed, counter = (env id lo, env id hi, tick, 1 + cell / 4))
+ *   4. terminated = no burning cell left; truncated = step_count >= max_steps
+ *   5. obs = (OBJECT_IDX, COLOR_IDX, STATE) per cell, u8 [W][H][3]: healthy (0, 3 green, 0), burning (1, 0 red, 0),
+ *      burnt (2, 7 grey, 0), agent (3, agent_colour[i], dir)
+ * reset: all healthy, num_fires distinct burning cells, then agents on distinct cells (Philox rejection sampling). */
+#define MG_MAX_WILDFIRE_AGENTS 32
+
+typedef struct mg_wildfire_config {
+  uint32_t struct_size;
+  int32_t family;                 /* MG_FAMILY_WILDFIRE */
+  int64_t num_envs, env_id_base;
+  int32_t width, height;
+  int32_t num_agents;
+  int32_t agent_colour[MG_MAX_WILDFIRE_AGENTS];
+  int32_t num_fires;              /* burning cells after reset */
+  uint32_t ignite_threshold[5];   /* floor(2^32 * (1 - (1 - alpha)^k)), k = 0..4 (entry 0 unused) */
+  uint32_t burnout_threshold;     /* floor(2^32 * beta) */
+  int32_t max_steps;
+  int32_t autoreset;
+  uint64_t seed;
+} mg_wildfire_config;
+
+enum { MG_WF_PLANE_TERRAIN = 0, /* u8  [N_pad][W*H] 0 healthy 1 burning 2 burnt, index x*H + y */
+       MG_WF_PLANE_AGENTS = 1,  /* u8  [N_pad][A][4] x, y, dir, 0 */
+       MG_WF_PLANE_HDR = 2,     /* i32 [N_pad][4] step_count, tick, Philox block counter, episodes */
+       MG_WF_PLANE_COUNT = 3 };
+
+/* mg_reset / mg_step / mg_step_host / mg_status / mg_destroy work on the handle; mg_step_io: actions int8 [N][A],
+ * rewards f64 [N][A], obs u8 [N][W][H][3].  mg_set_trace (order only) replays agent orders. */
+int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_env** out);
 
 #ifdef __cplusplus
 }

@@ -197,3 +197,35 @@ void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* di
 extern "C"
 #endif
 void oc_toroid(const uint8_t* grid, const uint8_t* pos, int64_t N, int W, int A, int num_ball_types, float* out);
+
+/* ==================================================================================== Wildfire (extension)
+ * No reference code exists (README.md:43 is a heading only): this restates OUR specification
+ * (include/multigrid_b200.h "Wildfire"), so the CUDA kernels have an independent
+ * checker.  Parity versus the reference is unpinned by construction. */
+#define OC_MAX_WF_AGENTS 32
+typedef struct {
+  int32_t width, height, num_agents;
+  int32_t agent_colour[OC_MAX_WF_AGENTS];
+  int32_t num_fires;
+  uint32_t ignite_threshold[5];
+  uint32_t burnout_threshold;
+  int32_t max_steps;
+} oc_wf_cfg;
+
+typedef struct {
+  uint8_t* terrain;  /* [N][W*H] */
+  uint8_t* agents;   /* [N][A][4] x, y, dir, 0 */
+  int32_t* hdr;      /* [N][4] step_count, tick, rng ctr, episodes */
+} oc_wf_state;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int oc_wf_reset(const oc_wf_cfg* c, int64_t N, oc_wf_state* st, const uint8_t* mask, uint64_t seed, uint64_t env_id_base,
+                uint8_t* obs);
+int oc_wf_step(const oc_wf_cfg* c, int64_t N, oc_wf_state* st, const int8_t* actions, const uint8_t* order /* NULL = Philox */,
+               uint64_t seed, uint64_t env_id_base, uint8_t* obs, double* rewards, uint8_t* terminated, uint8_t* truncated,
+               int autoreset, uint8_t* final_obs);
+#ifdef __cplusplus
+}
+#endif

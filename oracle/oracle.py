@@ -348,3 +348,65 @@ def toroid(grid, pos, W, num_ball_types):
     out = np.zeros((N, A, W, W, num_ball_types + A), np.float32)
     lib().oc_toroid(_p(grid), _p(pos), C.c_int64(N), C.c_int(W), C.c_int(A), C.c_int(num_ball_types), _p(out))
     return out
+
+
+# ============================================================================ Wildfire (extension)
+class WfCfg(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32), ("agent_colour", C.c_int32 * 32),
+                ("num_fires", C.c_int32), ("ignite_threshold", C.c_uint32 * 5), ("burnout_threshold", C.c_uint32),
+                ("max_steps", C.c_int32)]
+
+
+class WfState(C.Structure):
+    _fields_ = [("terrain", C.c_void_p), ("agents", C.c_void_p), ("hdr", C.c_void_p)]
+
+
+def wildfire_thresholds(alpha, beta):
+    """The integer thresholds both the oracle and the kernels compare Philox words with."""
+    ign = [min(2**32 - 1, int(np.floor((1.0 - (1.0 - alpha) ** k) * 2.0**32))) for k in range(5)]
+    return ign, min(2**32 - 1, int(np.floor(beta * 2.0**32)))
+
+
+class WildfireOracle:
+    """CPU restatement of the Wildfire extension (spec: include/multigrid_b200.h).  No reference exists."""
+
+    def __init__(self, num_envs, size=64, num_agents=16, agents_index=None, num_fires=4, alpha=0.15, beta=0.05, max_steps=200,
+                 seed=0, env_id_base=0, width=None, height=None):
+        self.N, self.W, self.H, self.A = int(num_envs), int(width or size), int(height or size), int(num_agents)
+        c = WfCfg()
+        c.width, c.height, c.num_agents, c.num_fires, c.max_steps = self.W, self.H, self.A, num_fires, max_steps
+        for i, v in enumerate(agents_index or [4] * self.A):
+            c.agent_colour[i] = v
+        ign, bo = wildfire_thresholds(alpha, beta)
+        for k in range(5):
+            c.ignite_threshold[k] = ign[k]
+        c.burnout_threshold = bo
+        self.cfg, self.seed, self.base = c, int(seed), int(env_id_base)
+        self.terrain = np.zeros((self.N, self.W * self.H), np.uint8)
+        self.agents = np.zeros((self.N, self.A, 4), np.uint8)
+        self.hdr = np.zeros((self.N, 4), np.int32)
+
+    def _st(self):
+        s = WfState()
+        s.terrain, s.agents, s.hdr = _p(self.terrain), _p(self.agents), _p(self.hdr)
+        return s
+
+    def reset(self, mask=None):
+        obs = np.zeros((self.N, self.W, self.H, 3), np.uint8)
+        st = self._st()
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().oc_wf_reset(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(m), C.c_uint64(self.seed), C.c_uint64(self.base), _p(obs))
+        return obs
+
+    def step(self, actions, order=None, autoreset=False, want_final_obs=False):
+        actions = np.ascontiguousarray(actions, np.int8).reshape(self.N, self.A)
+        order = None if order is None else np.ascontiguousarray(order, np.uint8)
+        obs = np.zeros((self.N, self.W, self.H, 3), np.uint8)
+        rew = np.zeros((self.N, self.A), np.float64)
+        term, trunc = np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8)
+        fin = np.zeros_like(obs) if want_final_obs else None
+        st = self._st()
+        lib().oc_wf_step(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(actions), _p(order), C.c_uint64(self.seed),
+                         C.c_uint64(self.base), _p(obs), _p(rew), _p(term), _p(trunc), C.c_int(int(autoreset)), _p(fin))
+        out = (obs, rew, term.astype(bool), trunc.astype(bool))
+        return out + (fin,) if want_final_obs else out

@@ -35,6 +35,7 @@ def test_config_struct_matches_header_layout():
     assert C.sizeof(_lib.Config) == 4 + 4 + 16 + 16 + 32 + 32 + 64 + 28 + 4 + 8
     assert C.sizeof(_lib.StepIO) == 6 * 8
     assert C.sizeof(_lib.MapConfig) == 120 and C.sizeof(_lib.MapTrace) == 8 * 8
+    assert C.sizeof(_lib.WildfireConfig) == 4 + 4 + 16 + 12 + 128 + 4 + 20 + 4 + 8 + 8
     assert C.sizeof(_lib.Trace) == 9 * 8
 
 
