@@ -59,3 +59,9 @@ def make_wildfire_vec(num_envs: int, **kwargs):
     """Batched Wildfire (extension; the reference has no Wildfire code - see include/multigrid_b200.h for the rules)."""
     from .wildfire_env import WildfireVecEnv
     return WildfireVecEnv(num_envs, **kwargs)
+
+
+def make_ctf1v1_vec(num_envs: int, map_path, **kwargs):
+    """Batched `Ctf1v1Env` (envs/ctf.py:50-654); kwargs as the reference constructor (ctf.py:55-70)."""
+    from .map_env import Ctf1v1VecEnv
+    return Ctf1v1VecEnv(num_envs, map_path, **kwargs)

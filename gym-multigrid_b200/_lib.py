@@ -58,7 +58,8 @@ class MapConfig(C.Structure):
         ("size", C.c_int32), ("field_map", C.c_void_p), ("num_blue", C.c_int32), ("num_red", C.c_int32),
         ("flag_reward", C.c_double), ("battle_reward", C.c_double), ("obstacle_penalty", C.c_double),
         ("step_penalty", C.c_double), ("battle_range", C.c_double), ("randomness", C.c_double),
-        ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("obs_dtype", C.c_int32), ("seed", C.c_uint64),
+        ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("obs_dtype", C.c_int32), ("variant_1v1", C.c_int32),
+        ("seed", C.c_uint64),
     ]
 
 

@@ -121,7 +121,9 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
   for (int i = 0; i < nb; ++i) act[i] = blue_act[i];
   for (int k = 0; k < nr; ++k)  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301)
     act[nb + k] = MODE == 0 ? p.red_actions[e * nr + k] : below(r, 5);
-  if (MODE == 0) {
+  if (p.variant_1v1) {  // Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510)
+    order[0] = 0; order[1] = 1;
+  } else if (MODE == 0) {
     for (int i = 0; i < n; ++i) order[i] = p.order[e * n + i];
   } else {  // np_random.shuffle stand-in: Fisher-Yates
     for (int i = 0; i < n; ++i) order[i] = i;
@@ -138,7 +140,7 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
     if (nx < 0 || ny < 0 || nx >= S || ny >= S) continue;
     bool occupied = false;  // an agent object (alive, defeated, or itself when staying) sits on the cell
     for (int j = 0; j < n; ++j) occupied |= (ag.x[j] == nx && ag.y[j] == ny);
-    if (occupied) { if (p.obstacle_penalty != 0) ag.fl[i] |= 2; continue; }  // :1231-1236
+    if (occupied) { if (p.obstacle_penalty != 0 && !p.variant_1v1) ag.fl[i] |= 2; continue; }  // :1231-1236 (1v1 has no collided logic, :498-501)
     if (p.field_map[nx * S + ny] == CT_OBSTACLE && p.obstacle_penalty == 0) continue;  // Obstacle.can_overlap()
     ag.dir[i] = (uint8_t)dir_of(dx, dy, ag.dir[i]);  // Agent.move agent.py:167-200
     ag.x[i] = (uint8_t)nx; ag.y[i] = (uint8_t)ny;
@@ -168,7 +170,9 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
         blue_win = (double)r.u32() * (1.0 / 4294967296.0) < pb;
       }
       ++nbattle;
-      if (blue_win) { rew += p.battle_reward; ag.fl[nb + q] |= 1; } else { rew -= p.battle_reward; ag.fl[b] |= 1; }  // :1409-1418
+      if (blue_win) { rew += p.battle_reward; ag.fl[nb + q] |= 1; }                 // :1409-1418
+      else if (p.variant_1v1) { rew -= p.battle_reward; term = true; }              // 1v1: losing ends the episode (ctf.py:629-632)
+      else { rew -= p.battle_reward; ag.fl[b] |= 1; }
     }
   if (MODE == 0 && p.battles_used) p.battles_used[e] = nbattle;
   bool all_dead = true;

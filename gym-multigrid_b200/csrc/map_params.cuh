@@ -7,7 +7,7 @@
 namespace mg {
 
 struct MapParams {
-  int S, cells, nb, nr, n, family, max_steps, autoreset, obs_dtype;
+  int S, cells, nb, nr, n, family, max_steps, autoreset, obs_dtype, variant_1v1;
   double flag_reward, obstacle_penalty, step_penalty, battle_reward, battle_range, randomness;
   int n_background, len_blue, len_red, blue_flag, red_flag;
   long long N;

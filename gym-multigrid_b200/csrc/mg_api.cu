@@ -268,6 +268,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   const int nb = maze ? 1 : cfg->num_blue, nr = maze ? 0 : cfg->num_red, n = nb + nr;
   if (nb < 1 || nr < 0 || n > MG_MAX_MAP_AGENTS || (!maze && nr < 1)) return fail(nullptr, "mg_create_map: agent counts out of range (1..16 agents in total)");
   if (cfg->max_steps < 1) return fail(nullptr, "mg_create_map: max_steps must be >= 1");
+  if (cfg->variant_1v1 && (maze || nb != 1 || nr != 1)) return fail(nullptr, "mg_create_map: variant_1v1 needs the CtF family with one blue and one red agent");
   // cell lists in np.where order (row-major over field_map[x][y])
   std::string bg, bt, rt;  // uint16 lists packed in strings
   auto push = [](std::string& v, int c) { uint16_t u = (uint16_t)c; v.append(reinterpret_cast<const char*>(&u), 2); };
@@ -357,7 +358,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   mg::MapParams& p = env->mbase;
   std::memset(&p, 0, sizeof p);
   p.S = S; p.cells = cells; p.nb = nb; p.nr = nr; p.n = n; p.family = cfg->family; p.max_steps = cfg->max_steps;
-  p.autoreset = cfg->autoreset != 0; p.obs_dtype = cfg->obs_dtype;
+  p.autoreset = cfg->autoreset != 0; p.obs_dtype = cfg->obs_dtype; p.variant_1v1 = cfg->variant_1v1 != 0;
   p.flag_reward = cfg->flag_reward; p.obstacle_penalty = cfg->obstacle_penalty; p.step_penalty = cfg->step_penalty;
   p.battle_reward = cfg->battle_reward; p.battle_range = cfg->battle_range; p.randomness = cfg->randomness;
   p.n_background = (int)bg.size() / 2; p.len_blue = (int)bt.size() / 2; p.len_red = (int)rt.size() / 2;
@@ -396,7 +397,7 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
     const bool need_reset = op == 0 || p.autoreset;
     if (need_reset && maze && !p.start_index) return fail(env, "trace mode: Maze reset needs start_index");
     if (need_reset && !maze && (!p.blue_place || !p.red_place)) return fail(env, "trace mode: CtF reset needs blue_place / red_place");
-    if (op == 1 && !maze && (!p.red_actions || !p.order)) return fail(env, "trace mode: CtF step needs red_actions and order");
+    if (op == 1 && !maze && (!p.red_actions || (!p.order && !p.variant_1v1))) return fail(env, "trace mode: CtF step needs red_actions and order");
   }
   if (op == 1) {
     p.actions = io->actions; p.obs = io->obs; p.rewards = io->rewards; p.terminated = io->terminated;

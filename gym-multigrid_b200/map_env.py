@@ -29,7 +29,7 @@ class _MapVecEnv:
     ref_dtype = None
 
     def _create(self, num_envs, field_map, num_blue, num_red, flag_reward, battle_reward, obstacle_penalty, step_penalty,
-                battle_range, randomness, max_steps, device, seed, autoreset, env_id_base, reference_dtypes):
+                battle_range, randomness, max_steps, device, seed, autoreset, env_id_base, reference_dtypes, variant_1v1=False):
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -59,6 +59,7 @@ class _MapVecEnv:
         cfg.battle_range, cfg.randomness = float(battle_range), float(randomness)
         cfg.max_steps, cfg.autoreset = self.max_steps, int(self.autoreset)
         cfg.obs_dtype = _lib.OBS_REFERENCE if self.reference_dtypes else _lib.OBS_U8
+        cfg.variant_1v1 = int(bool(variant_1v1))
         cfg.seed = int(seed) & (2**64 - 1)
         h = C.c_void_p()
         if self._lib.mg_create_map(C.byref(cfg), idx, C.byref(h)) != 0:
@@ -253,14 +254,14 @@ class CtfVecEnv(_MapVecEnv):
     def __init__(self, num_envs, map_path, num_blue_agents=2, num_red_agents=2, battle_range=1, randomness=0.75, flag_reward=1,
                  battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
                  observation_option="map", observation_scaling=1, device="cuda:0", seed=0, autoreset=True, env_id_base=0,
-                 reference_dtypes=False):
+                 reference_dtypes=False, variant_1v1=False):
         if observation_option != "map":
             raise NotImplementedError('the device writes observation_option="map"; use positional_obs()/flattened_obs() for the others')
         fm = load_text_map(map_path)
         fr = flag_reward
         self._create(num_envs, fm, num_blue_agents, num_red_agents, float(fr), float(battle_reward_ratio * fr),
                      float(obstacle_penalty_ratio * fr), float(step_penalty_ratio * fr), float(battle_range), float(randomness),
-                     max_steps, device, seed, autoreset, env_id_base, reference_dtypes)
+                     max_steps, device, seed, autoreset, env_id_base, reference_dtypes, variant_1v1)
         self.num_blue_agents, self.num_red_agents = self.num_blue, self.num_red
         self.single_action_space = MultiDiscrete([5] * self.num_blue)
         self.action_space = MultiDiscrete(np.full((self.num_envs, self.num_blue), 5))
@@ -288,3 +289,20 @@ class CtfVecEnv(_MapVecEnv):
         d = self.positional_obs()
         return torch.cat([d["blue_agent"], d["red_agent"], d["blue_flag"], d["red_flag"], d["blue_territory"], d["red_territory"],
                           d["obstacle"], d["terminated_agents"]], dim=1)
+
+
+class Ctf1v1VecEnv(CtfVecEnv):
+    """`num_envs` x Ctf1v1Env (ctf.py:50-654): one blue agent vs one RwPolicy red agent, fixed move order blue then
+    red, a lost battle ends the episode.  `obstacle_penalty_ratio` must be 0: with a non-zero ratio the reference's
+    own step raises (`blue_agent_loc in self.obstacle`, ctf.py:639, is an ambiguous ndarray test), so no behaviour
+    is defined there.  Action space Discrete(5); constructor kwargs as ctf.py:55-70."""
+
+    def __init__(self, num_envs, map_path, battle_range=1.0, randomness=0.75, flag_reward=1.0, battle_reward_ratio=0.25,
+                 obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100, observation_option="map", **kwargs):
+        if obstacle_penalty_ratio != 0:
+            raise ValueError("Ctf1v1Env is only defined for obstacle_penalty_ratio == 0 (the reference raises otherwise, ctf.py:639)")
+        super().__init__(num_envs, map_path, num_blue_agents=1, num_red_agents=1, battle_range=battle_range, randomness=randomness,
+                         flag_reward=flag_reward, battle_reward_ratio=battle_reward_ratio, obstacle_penalty_ratio=0,
+                         step_penalty_ratio=step_penalty_ratio, max_steps=max_steps, observation_option=observation_option,
+                         variant_1v1=True, **kwargs)
+        self.single_action_space = Discrete(5)

@@ -182,6 +182,8 @@ typedef struct mg_map_config {
   int32_t max_steps;
   int32_t autoreset;
   int32_t obs_dtype;          /* MG_OBS_* */
+  int32_t variant_1v1;        /* CtF only: 1 = Ctf1v1Env rules (ctf.py:50-654): fixed order blue then red, no shuffle draw, losing a
+                                 battle ends the episode instead of defeating blue, no collision penalty; needs num_blue = num_red = 1 */
   uint64_t seed;
 } mg_map_config;
 

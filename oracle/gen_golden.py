@@ -160,6 +160,21 @@ def gen_ctf():
               f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_ctf1v1():
+    eps = [rh.record_ctf_1v1_episode(CTF_MAP, seed, np.random.default_rng(4000 + seed)) for seed in range(40)]
+    for e in eps:
+        assert e["obs"].dtype == np.int64
+        e["obs"] = e["obs"].astype(np.uint8)
+        e["init_obs"] = e["init_obs"].astype(np.uint8)
+    out = rh.pack_episodes(eps, ["actions", "red_actions", "n_battles", "blue_win", "obs", "reward", "terminated", "truncated",
+                                 "pos", "dir", "dead"], ["field_map", "init_obs", "init_pos", "blue_place", "red_place"])
+    out["field_map"] = out["field_map"][0].astype(np.uint8)
+    path_out = os.path.join(OUT, "ctf1v1.npz")
+    np.savez_compressed(path_out, **out)
+    print(f"ctf1v1: {len(eps)} episodes, steps={int(out['length'].sum())}, battles={int(out['n_battles'].sum())}, "
+          f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 def gen_partial():
     rh.import_reference()
     parts = [rh.record_partial_views("multigrid-collect-rooms-respawn-v0", 11, 120),
@@ -184,13 +199,15 @@ def gen_toroid():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "partial", "toroid"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
         gen_maze()
     if "ctf" in which:
         gen_ctf()
+    if "ctf1v1" in which:
+        gen_ctf1v1()
     if "partial" in which:
         gen_partial()
     if "toroid" in which:

@@ -128,6 +128,7 @@ typedef struct {
   /* ctf (ctf.py:662-679) */
   int32_t num_blue, num_red;
   double battle_range, randomness, battle_reward;
+  int32_t variant_1v1;         /* 1 = Ctf1v1Env (ctf.py:50-654): fixed order blue->red, losing a battle ends the episode */
 } oc_map_cfg;
 
 typedef struct {

@@ -175,7 +175,7 @@ int oc_ctf_reset(const oc_map_cfg* c, int64_t N, oc_map_state* st, const uint8_t
         for (int i = 0; i < nr; ++i) rp[i] = rng->red_place[e * nr + i];
       } else {
         prng_t r = {rng->seed, rng->env_id_base + (uint64_t)e, st->rng_ctr[e], {0}, 0};
-        sample_distinct(&r, lb, nb, bp);
+        sample_distinct(&r, lb, nb, bp); /* 1v1: one np_random.integers(0, len) each (ctf.py:317,322) = one draw */
         sample_distinct(&r, lr, nr, rp);
         st->rng_ctr[e] = r.ctr;
       }
@@ -200,7 +200,8 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
     for (int i = 0; i < nb; ++i) act[i] = blue_actions[e * nb + i];
     for (int k = 0; k < nr; ++k) /* RwPolicy.act for EVERY red agent, defeated or not (:1297-1301) */
       act[nb + k] = rng->mode == 0 ? rng->red_actions[e * nr + k] : p_below(&r, 5);
-    if (rng->mode == 0) for (int i = 0; i < n; ++i) order[i] = rng->order[e * n + i];
+    if (c->variant_1v1) { order[0] = 0; order[1] = 1; } /* Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510) */
+    else if (rng->mode == 0) for (int i = 0; i < n; ++i) order[i] = rng->order[e * n + i];
     else { /* np_random.shuffle stand-in: Fisher-Yates */
       for (int i = 0; i < n; ++i) order[i] = i;
       for (int i = n - 1; i > 0; --i) { int j = p_below(&r, i + 1), t = order[i]; order[i] = order[j]; order[j] = t; }
@@ -214,7 +215,7 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
       if (nx < 0 || ny < 0 || nx >= S || ny >= S) continue;
       int occupied = 0; /* an agent object (alive or defeated, or itself when staying) sits on the cell */
       for (int j = 0; j < n; ++j) occupied |= (pos[2 * j] == nx && pos[2 * j + 1] == ny);
-      if (occupied) { if (c->obstacle_penalty != 0) fl[i] |= 2; continue; } /* :1231-1236 */
+      if (occupied) { if (c->obstacle_penalty != 0 && !c->variant_1v1) fl[i] |= 2; continue; } /* :1231-1236; the 1v1 env has no collided logic (:498-501) */
       const int code = c->field_map[nx * S + ny];
       if (code == CT_OBSTACLE && c->obstacle_penalty == 0) continue; /* Obstacle.can_overlap() <=> penalty != 0 */
       dir[i] = (uint8_t)dir_of(nx - pos[2 * i], ny - pos[2 * i + 1], dir[i]); /* Agent.move agent.py:167-200 */
@@ -245,13 +246,15 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
           blue_win = (double)p_u32(&r) * (1.0 / 4294967296.0) < pb;
         }
         ++nbattle;
-        if (blue_win) { rew += c->battle_reward; fl[nb + q] |= 1; } else { rew -= c->battle_reward; fl[b] |= 1; } /* :1409-1418 */
+        if (blue_win) { rew += c->battle_reward; fl[nb + q] |= 1; } /* :1409-1418 */
+        else if (c->variant_1v1) { rew -= c->battle_reward; term = 1; } /* 1v1: blue losing ends the episode (ctf.py:629-632) */
+        else { rew -= c->battle_reward; fl[b] |= 1; }
       }
     if (rng->mode == 0 && rng->battles_used) rng->battles_used[e] = nbattle;
     int all_dead = 1;
     for (int i = 0; i < nb; ++i) all_dead &= (fl[i] & 1);
     if (all_dead) term = 1;                  /* :1423 */
-    rew -= c->step_penalty * nb;             /* :1428 */
+    rew -= c->step_penalty * nb;             /* :1428; 1v1: reward -= step_penalty (:646), nb == 1 */
     reward[e] = rew; terminated[e] = term; truncated[e] = trunc;
     if (autoreset && (term || trunc)) {
       if (final_obs) ctf_encode(c, pos, fl, final_obs + e * S * S);

@@ -426,3 +426,47 @@ def record_toroid(env_id, seed, n_samples):
         out["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
         out["toroid"].append(np.stack(tor))
     return {k: np.array(v) for k, v in out.items()}
+
+
+def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battles=4):
+    """One episode of the reference Ctf1v1Env (ctf.py:50-654), "map" observations, fresh instance."""
+    import_reference()
+    with tapped_generators() as log:
+        from gym_multigrid.envs.ctf import Ctf1v1Env
+        from gym_multigrid.policy.ctf.heuristic import RwPolicy
+        env = Ctf1v1Env(map_path, enemy_policy=RwPolicy(), max_steps=max_steps, observation_option="map")
+        obs0, info0 = env.reset(seed=seed)
+        place = [ev[1] for ev in log if ev[0] == "integers"]      # ctf.py:317, :322
+        assert len(place) == 2
+        del log[:]
+        rec = dict(actions=[], red_actions=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[], truncated=[],
+                   pos=[], dir=[], dead=[])
+        init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
+        while True:
+            a = int(action_rng.integers(0, 5))
+            obs, rew, term, trunc, info = env.step(a)
+            ints = [ev[1] for ev in log if ev[0] == "integers"]
+            wins = [bool(ev[1]) for ev in log if ev[0] == "choice"]
+            assert len(ints) == 1 and len(wins) <= 1 and not [ev for ev in log if ev[0] == "shuffle"]
+            del log[:]
+            rec["actions"].append(np.array([a], np.int8))
+            rec["red_actions"].append(np.array(ints, np.int8))
+            rec["n_battles"].append(len(wins))
+            rec["blue_win"].append(np.array(wins + [False] * (max_battles - len(wins)), np.uint8))
+            rec["obs"].append(np.asarray(obs).copy())
+            rec["reward"].append(float(rew))
+            rec["terminated"].append(bool(term))
+            rec["truncated"].append(bool(trunc))
+            rec["pos"].append(np.array([np.asarray(a_.pos) for a_ in env.agents], np.int16))
+            rec["dir"].append(np.array([a_.dir for a_ in env.agents], np.int8))
+            rec["dead"].append(np.array([0, int(env._is_red_agent_defeated)], np.uint8))
+            if term or trunc:
+                break
+    L = len(rec["actions"])
+    out = dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(), init_pos=init_pos,
+               blue_place=np.array([place[0]], np.int32), red_place=np.array([place[1]], np.int32), length=L)
+    for k, v in rec.items():
+        out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
+    out["n_battles"] = out["n_battles"].astype(np.int32)
+    out["reward"] = out["reward"].astype(np.float64)
+    return out

@@ -192,3 +192,44 @@ def test_map_create_rejects_bad_configs(cuda_device):
         mg.make_ctf_vec(4, np.zeros((6, 6)))            # no flags
     with pytest.raises(ValueError):
         mg.make_ctf_vec(4, load_golden("ctf_2v2")["field_map"], num_blue_agents=12, num_red_agents=12)
+
+
+def test_ctf1v1_replay_and_philox(cuda_device):
+    """Ctf1v1Env (ctf.py:50-654): golden replay, then Philox mode against the oracle."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf1v1")
+    E, T, _ = g["actions"].shape
+    k = 5
+    env = mg.make_ctf1v1_vec(E * k, g["field_map"], autoreset=False)
+    env.set_trace(blue_place=_tile(g["blue_place"], k), red_place=_tile(g["red_place"], k))
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), _tile(g["init_obs"], k))
+    for t in range(T):
+        lv = g["length"] > t
+        live = _tile(lv, k)
+        tr = env.set_trace(red_actions=_tile(g["red_actions"][:, t], k), blue_win=_tile(g["blue_win"][:, t], k))
+        act = _tile(np.where(lv[:, None], g["actions"][:, t], 0), k).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        assert np.array_equal(_np(obs)[live], _tile(g["obs"][:, t], k)[live]), f"step {t}: obs"
+        assert np.array_equal(_np(rew)[live], _tile(g["reward"][:, t], k)[live]), f"step {t}: reward"
+        assert np.array_equal(_np(term)[live], _tile(g["terminated"][:, t], k)[live])
+        assert np.array_equal(_np(trunc)[live], _tile(g["truncated"][:, t], k)[live])
+        assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
+    assert env.status() == 0
+    env.close()
+    n = 3000
+    env = mg.make_ctf1v1_vec(n, g["field_map"], max_steps=30, seed=21)
+    o = oc.CtfOracle(g["field_map"], n, 1, 1, max_steps=30, variant_1v1=True)
+    r = oc.map_rng(mode=1, seed=21)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(0)
+    for t in range(80):
+        act = rng.integers(0, 5, size=(n, 1)).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        oo, orew, oterm, otrunc = o.step(act, r, autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew)
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+    with pytest.raises(ValueError):
+        mg.make_ctf1v1_vec(4, g["field_map"], obstacle_penalty_ratio=0.5)
+    env.close()

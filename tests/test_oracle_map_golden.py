@@ -69,3 +69,20 @@ def test_map_philox_mode_shard_invariant():
     for t in range(40):
         assert np.array_equal(full[t][0], np.concatenate([lo[t][0], hi[t][0]]))
         assert np.array_equal(full[t][1], np.concatenate([lo[t][1], hi[t][1]]))
+
+
+def test_ctf1v1_matches_reference():
+    g = load_golden("ctf1v1")
+    E, T, _ = g["actions"].shape
+    o = oc.CtfOracle(g["field_map"], E, 1, 1, variant_1v1=True)
+    obs = o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
+    assert np.array_equal(obs, g["init_obs"]) and np.array_equal(o.pos, g["init_pos"])
+    for t in range(T):
+        live = g["length"] > t
+        used = np.zeros(E, np.int32)
+        r = oc.map_rng(mode=0, red_actions=g["red_actions"][:, t], blue_win=g["blue_win"][:, t], battles_used=used)
+        obs, rew, term, trunc = o.step(np.where(live[:, None], g["actions"][:, t], 0), r)
+        assert np.array_equal(obs[live], g["obs"][live, t]) and np.array_equal(rew[live], g["reward"][live, t])
+        assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
+        assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal((o.flags & 1)[live], g["dead"][live, t])
+        assert np.array_equal(used[live], g["n_battles"][live, t])
