@@ -65,3 +65,9 @@ def make_ctf1v1_vec(num_envs: int, map_path, **kwargs):
     """Batched `Ctf1v1Env` (envs/ctf.py:50-654); kwargs as the reference constructor (ctf.py:55-70)."""
     from .map_env import Ctf1v1VecEnv
     return Ctf1v1VecEnv(num_envs, map_path, **kwargs)
+
+
+def make_generic_vec(num_envs: int, width: int, **kwargs):
+    """Batched base-class `MultiGridEnv.step` with DefaultWorld (multigrid.py:397-483; layout injected, see generic_env.py)."""
+    from .generic_env import GenericVecEnv
+    return GenericVecEnv(num_envs, width, **kwargs)

@@ -12,7 +12,8 @@ from ._build import LIB_PATH
 
 MAX_AGENTS = 8
 MAX_BALL_TYPES = 8
-FAMILY_COLLECT, FAMILY_MAZE, FAMILY_CTF, FAMILY_WILDFIRE = 0, 1, 2, 3
+FAMILY_COLLECT, FAMILY_MAZE, FAMILY_CTF, FAMILY_WILDFIRE, FAMILY_GENERIC = 0, 1, 2, 3, 4
+GEN_PLANES = dict(cell=0, state=1, pos=2, hdr=3, init_cell=4, init_state=5, init_pos=6)
 WF_PLANE_TERRAIN, WF_PLANE_AGENTS, WF_PLANE_HDR = 0, 1, 2
 MAX_WILDFIRE_AGENTS = 32
 OBS_U8, OBS_REFERENCE = 0, 1
@@ -26,7 +27,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic",
 ]
 
 
@@ -70,6 +71,12 @@ class WildfireConfig(C.Structure):
         ("num_fires", C.c_int32), ("ignite_threshold", C.c_uint32 * 5), ("burnout_threshold", C.c_uint32),
         ("max_steps", C.c_int32), ("autoreset", C.c_int32), ("seed", C.c_uint64),
     ]
+
+
+class GenericConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("family", C.c_int32), ("num_envs", C.c_int64), ("env_id_base", C.c_int64),
+                ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32), ("max_steps", C.c_int32),
+                ("autoreset", C.c_int32), ("seed", C.c_uint64)]
 
 
 class MapTrace(C.Structure):
@@ -121,6 +128,8 @@ def load():
     lib.mg_toroid_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mg_create_wildfire.restype = C.c_int
     lib.mg_create_wildfire.argtypes = [C.POINTER(WildfireConfig), C.c_int, C.POINTER(C.c_void_p)]
+    lib.mg_create_generic.restype = C.c_int
+    lib.mg_create_generic.argtypes = [C.POINTER(GenericConfig), C.c_int, C.POINTER(C.c_void_p)]
     lib.mg_launch_count.restype = C.c_int64
     lib.mg_launch_count.argtypes = [C.c_void_p]
     if lib.mg_abi_version() != 1:

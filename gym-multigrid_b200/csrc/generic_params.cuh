@@ -1,0 +1,20 @@
+// generic_params.cuh -- kernel parameter block of the generic MultiGridEnv.step family (DefaultWorld).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mg {
+
+struct GenericParams {
+  int W, H, cells, A, max_steps, autoreset, op;   // op: 0 = reset(mask) from the snapshot planes, 1 = step
+  long long N;
+  unsigned long long env_id_base, seed;
+  uint8_t* gcell; uint8_t* gstate; uint8_t* pos; int4* hdr;               // live state
+  const uint8_t* icell; const uint8_t* istate; const uint8_t* ipos;       // episode-start snapshot (reset source)
+  const int8_t* actions; uint8_t* obs; double* rewards; uint8_t* terminated; uint8_t* truncated; uint8_t* final_obs;
+  const uint8_t* reset_mask;
+  const uint8_t* order;   // replayed np.random.permutation outputs, or null (Philox Fisher-Yates)
+  int32_t* status;
+};
+
+}  // namespace mg

@@ -30,6 +30,7 @@ int map_tile_envs();
 #include "map_params.cuh"
 #include "view_params.cuh"
 #include "wildfire_params.cuh"
+#include "generic_params.cuh"
 namespace mg {
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
@@ -40,6 +41,8 @@ int view_tile_envs();
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st);
 cudaError_t configure_wildfire_kernel(int cells);
 size_t wildfire_smem_bytes(int cells);
+cudaError_t launch_generic(const GenericParams& p, cudaStream_t st);
+int generic_tile_envs();
 }  // namespace mg
 
 struct mg_env {
@@ -49,6 +52,8 @@ struct mg_env {
   mg::MapParams mbase;
   mg_wildfire_config wcfg;
   mg::WildfireParams wbase;
+  mg_generic_config gcfg;
+  mg::GenericParams gbase;
   mg_map_trace mtrace;
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
@@ -58,7 +63,7 @@ struct mg_env {
   int device;
   int tile;  // kernel tile variant (envs per CTA x threads), MG_TILE env var, default 0
   long long n_pad;
-  size_t plane_off[MG_PLANE_COUNT], plane_bytes[MG_PLANE_COUNT], plane_row[MG_PLANE_COUNT], state_bytes;
+  size_t plane_off[8], plane_bytes[8], plane_row[8], state_bytes;
   mg::CollectParams base;  // rules + constants; pointers filled per call
   mg_trace trace;
   bool has_trace;
@@ -225,11 +230,12 @@ extern "C" size_t mg_state_bytes(const mg_env* env) { return env ? env->state_by
 extern "C" size_t mg_obs_bytes(const mg_env* env) {
   if (!env) return 0;
   if (env->family == MG_FAMILY_WILDFIRE) return (size_t)env->wcfg.num_envs * env->wcfg.width * env->wcfg.height * 3;
+  if (env->family == MG_FAMILY_GENERIC) return (size_t)env->gcfg.num_envs * env->gcfg.num_agents * env->gcfg.width * env->gcfg.height * 6;
   if (env->family != MG_FAMILY_COLLECT) return (size_t)env->mcfg.num_envs * env->mcfg.size * env->mcfg.size * env->obs_elem;
   return (size_t)env->cfg.num_envs * env->cfg.width * env->cfg.height * 3;
 }
 extern "C" int mg_state_plane(const mg_env* env, int plane, size_t* offset, size_t* bytes, size_t* row_bytes) {
-  if (!env || plane < 0 || plane >= (env->family == MG_FAMILY_WILDFIRE ? (int)MG_WF_PLANE_COUNT : (int)MG_PLANE_COUNT)) return -1;
+  if (!env || plane < 0 || plane >= (env->family == MG_FAMILY_WILDFIRE ? (int)MG_WF_PLANE_COUNT : env->family == MG_FAMILY_GENERIC ? (int)MG_GEN_PLANE_COUNT : (int)MG_PLANE_COUNT)) return -1;
   if (offset) *offset = env->plane_off[plane];
   if (bytes) *bytes = env->plane_bytes[plane];
   if (row_bytes) *row_bytes = env->plane_row[plane];
@@ -489,6 +495,76 @@ static int wildfire_launch(mg_env* env, void* state, int op, const mg_step_io* i
   return 0;
 }
 
+// --------------------------------------------------------------------------------- generic
+extern "C" int mg_create_generic(const mg_generic_config* cfg, int device, mg_env** out) {
+  if (!cfg || !out) return fail(nullptr, "mg_create_generic: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(mg_generic_config)) return fail(nullptr, "mg_create_generic: mg_generic_config size mismatch (ABI)");
+  if (cfg->family != MG_FAMILY_GENERIC) return fail(nullptr, "mg_create_generic: family must be MG_FAMILY_GENERIC");
+  const int W = cfg->width, H = cfg->height, A = cfg->num_agents, cells = W * H;
+  if (cfg->num_envs < 1 || W < 3 || H < 3 || W > 255 || H > 255 || A < 1 || A > 8 || cfg->max_steps < 1)
+    return fail(nullptr, "mg_create_generic: need num_envs >= 1, 3 <= W, H <= 255 (grid.py:19-20), 1 <= num_agents <= 8, max_steps >= 1");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, std::string("mg_create_generic: no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, "mg_create_generic: device index out of range");
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, "cudaSetDevice", ce);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
+  if (prop.major != 10) return fail(nullptr, "mg_create_generic: kernels are built for sm_100a only");
+  mg_env* env = new (std::nothrow) mg_env();
+  if (!env) return fail(nullptr, "mg_create_generic: out of host memory");
+  env->family = MG_FAMILY_GENERIC;
+  env->gcfg = *cfg;
+  env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
+  env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
+  env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
+  env->view_smem_configured = 0; env->map_codes_off = 0;
+  std::memset(&env->trace, 0, sizeof env->trace);
+  env->obs_elem = 1; env->act_cols = A; env->rew_cols = A;
+  const int E = mg::generic_tile_envs();
+  env->n_pad = (cfg->num_envs + E - 1) / E * E;
+  const size_t rows[MG_GEN_PLANE_COUNT] = {(size_t)cells, (size_t)cells, (size_t)A * 2, 16, (size_t)cells, (size_t)cells, (size_t)A * 2};
+  size_t off = 0;
+  for (int i = 0; i < MG_GEN_PLANE_COUNT; ++i) {
+    env->plane_off[i] = off; env->plane_row[i] = rows[i]; env->plane_bytes[i] = rows[i] * (size_t)env->n_pad;
+    off = align_up(off + env->plane_bytes[i], 256);
+  }
+  env->state_bytes = off;
+  if ((ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess || (ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) {
+    cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "cudaMalloc(status)", ce);
+  }
+  mg::GenericParams& p = env->gbase;
+  std::memset(&p, 0, sizeof p);
+  p.W = W; p.H = H; p.cells = cells; p.A = A; p.max_steps = cfg->max_steps; p.autoreset = cfg->autoreset != 0;
+  p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed; p.status = env->d_status;
+  *out = env;
+  return 0;
+}
+
+static int generic_launch(mg_env* env, void* state, int op, const mg_step_io* io, const uint8_t* mask, uint8_t* obs, cudaStream_t st) {
+  mg::GenericParams p = env->gbase;
+  uint8_t* s = static_cast<uint8_t*>(state);
+  p.gcell = s + env->plane_off[MG_GEN_PLANE_CELL]; p.gstate = s + env->plane_off[MG_GEN_PLANE_STATE];
+  p.pos = s + env->plane_off[MG_GEN_PLANE_POS]; p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_GEN_PLANE_HDR]);
+  p.icell = s + env->plane_off[MG_GEN_PLANE_INIT_CELL]; p.istate = s + env->plane_off[MG_GEN_PLANE_INIT_STATE];
+  p.ipos = s + env->plane_off[MG_GEN_PLANE_INIT_POS];
+  p.op = op; p.reset_mask = mask;
+  p.order = env->has_trace ? env->trace.order : nullptr;
+  if (op == 1) {
+    p.actions = io->actions; p.obs = io->obs; p.rewards = io->rewards; p.terminated = io->terminated;
+    p.truncated = io->truncated; p.final_obs = io->final_obs;
+  } else {
+    p.obs = obs;
+  }
+  if ((reinterpret_cast<uintptr_t>(p.obs) & 1) || (reinterpret_cast<uintptr_t>(p.final_obs) & 1)) return fail(env, "obs buffers must be 2-byte aligned");
+  cudaError_t ce;
+  if ((ce = mg::launch_generic(p, st)) != cudaSuccess) return cuda_fail(env, "generic_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
 extern "C" int mg_set_trace(mg_env* env, const mg_trace* t) {
   if (!env) return -1;
   if (!t) { env->has_trace = false; return 0; }
@@ -503,6 +579,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
+  if (env->family == MG_FAMILY_GENERIC) return generic_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
   if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 0, nullptr, mask, obs, static_cast<cudaStream_t>(stream));
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
@@ -517,6 +594,7 @@ static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStrea
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
   if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
   if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 1, io, nullptr, nullptr, st);
+  if (env->family == MG_FAMILY_GENERIC) return generic_launch(env, state, 1, io, nullptr, nullptr, st);
   if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 1, io, nullptr, nullptr, st);
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
@@ -611,7 +689,7 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs : env->mcfg.num_envs);
+  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs : env->family == MG_FAMILY_GENERIC ? env->gcfg.num_envs : env->mcfg.num_envs);
   const size_t A = (size_t)env->act_cols, R = (size_t)env->rew_cols, ob = mg_obs_bytes(env);
   if (!env->d_actions) {
     if ((ce = cudaMalloc(&env->d_actions, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
@@ -658,6 +736,7 @@ extern "C" int mg_debug_set_timeline(mg_env* env, uint64_t* timeline_dev) {
 extern "C" int mg_tile_envs(const mg_env* env) {
   if (!env) return -1;
   if (env->family == MG_FAMILY_WILDFIRE) return 1;
+  if (env->family == MG_FAMILY_GENERIC) return mg::generic_tile_envs();
   return env->family == MG_FAMILY_COLLECT ? mg::tile_envs(env->tile) : mg::map_tile_envs();
 }
 

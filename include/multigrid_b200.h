@@ -29,7 +29,7 @@ extern "C" {
 #define MG_MAX_BALL_TYPES 8
 
 /* env families (reference: gym_multigrid/envs/{collect_game,maze,ctf}.py) */
-enum { MG_FAMILY_COLLECT = 0, MG_FAMILY_MAZE = 1, MG_FAMILY_CTF = 2, MG_FAMILY_WILDFIRE = 3 };
+enum { MG_FAMILY_COLLECT = 0, MG_FAMILY_MAZE = 1, MG_FAMILY_CTF = 2, MG_FAMILY_WILDFIRE = 3, MG_FAMILY_GENERIC = 4 };
 
 /* Collect layouts = the reference's _gen_grid variants */
 enum { MG_LAYOUT_EVEN_DIST = 0,         /* CollectGameEvenDist          collect_game.py:227-259 */
@@ -259,6 +259,33 @@ enum { MG_WF_PLANE_TERRAIN = 0, /* u8  [N_pad][W*H] 0 healthy 1 burning 2 burnt,
 /* mg_reset / mg_step / mg_step_host / mg_status / mg_destroy work on the handle; mg_step_io: actions int8 [N][A],
  * rewards f64 [N][A], obs u8 [N][W][H][3].  mg_set_trace (order only) replays agent orders. */
 int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_env** out);
+
+/* ================================================================ generic MultiGridEnv.step (DefaultWorld)
+ * The base-class step (multigrid.py:397-483) with DefaultWorld (world.py:33-52, encode_dim 6): still / left /
+ * right / forward, goal termination with `_reward` = 1 - 0.9 * step_count / max_steps (float64, multigrid.py:218-223),
+ * per-agent full-grid observations `encode_for_agents` (grid.py:254-284).  Other actions raise in the reference
+ * (`self.actions.available`, multigrid.py:447) and set MG_ERR_BAD_ACTION here.  `_gen_grid` is env-specific in the
+ * reference, so the layout is injected: the caller fills the INIT_* planes (episode-start snapshot) and mg_reset /
+ * autoreset restore them. */
+typedef struct mg_generic_config {
+  uint32_t struct_size;
+  int32_t family;          /* MG_FAMILY_GENERIC */
+  int64_t num_envs, env_id_base;
+  int32_t width, height, num_agents;   /* num_agents <= 8 */
+  int32_t max_steps, autoreset;
+  uint64_t seed;
+} mg_generic_config;
+
+enum { MG_GEN_PLANE_CELL = 0,       /* u8 [N_pad][W*H] type | colour << 4 (type 1 = empty), index x*H + y */
+       MG_GEN_PLANE_STATE = 1,      /* u8 [N_pad][W*H] door state 0 open 1 closed 2 locked / agent dir */
+       MG_GEN_PLANE_POS = 2,        /* u8 [N_pad][A][2] */
+       MG_GEN_PLANE_HDR = 3,        /* i32 [N_pad][4] step_count, 0, Philox block counter, episodes */
+       MG_GEN_PLANE_INIT_CELL = 4, MG_GEN_PLANE_INIT_STATE = 5, MG_GEN_PLANE_INIT_POS = 6,
+       MG_GEN_PLANE_COUNT = 7 };
+
+/* mg_step_io: actions int8 [N][A] (DefaultActions 0 still 1 left 2 right 3 forward), rewards f64 [N][A],
+ * obs u8 [N][A][W][H][6].  mg_set_trace (order only) replays np.random.permutation outputs (multigrid.py:402). */
+int mg_create_generic(const mg_generic_config* cfg, int device, mg_env** out);
 
 #ifdef __cplusplus
 }

@@ -197,9 +197,23 @@ def gen_toroid():
         print(f"{stem}: {n} states, toroid {r['toroid'].shape} {r['toroid'].dtype}, {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def gen_generic():
+    """Base-class MultiGridEnv.step + encode_dim-6 encode_for_agents on a DefaultWorld env assembled from reference classes."""
+    for stem, size, A, max_steps, episodes in (("generic_9x9_a3", 9, 3, 40, 24), ("generic_12x12_a5", 12, 5, 60, 12),
+                                                ("generic_7x7_a1", 7, 1, 30, 8)):
+        eps = [rh.record_generic_episode(size, A, max_steps, seed, np.random.default_rng(5000 + seed)) for seed in range(episodes)]
+        out = rh.pack_episodes(eps, ["actions", "order", "obs", "rewards", "terminated", "truncated", "pos", "dir"],
+                               ["init_obs", "init_pos", "init_dir"])
+        out["meta_size"], out["meta_num_agents"], out["meta_max_steps"] = np.array(size), np.array(A), np.array(max_steps)
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, terminated={int(out['terminated'].any(1).sum())}, "
+              f"{os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -212,3 +226,5 @@ if __name__ == "__main__":
         gen_partial()
     if "toroid" in which:
         gen_toroid()
+    if "generic" in which:
+        gen_generic()

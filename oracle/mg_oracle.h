@@ -230,3 +230,19 @@ int oc_wf_step(const oc_wf_cfg* c, int64_t N, oc_wf_state* st, const int8_t* act
 #ifdef __cplusplus
 }
 #endif
+
+/* ============================================================ generic MultiGridEnv.step (DefaultWorld)
+ * The base-class step (multigrid.py:397-483) with DefaultWorld (world.py:33-52, encode_dim 6) and per-agent
+ * full-grid observations `encode_for_agents` (grid.py:254-284).  Only still/left/right/forward are defined:
+ * for any other action the reference evaluates `self.actions.available` (multigrid.py:447), which no action
+ * enum has, and raises.  Cells: gcell = type | colour << 4 (type 1 = empty), gstate = door state / agent dir. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+int oc_generic_step(int64_t N, int W, int H, int A, int max_steps, uint8_t* gcell, uint8_t* gstate, uint8_t* pos /*[N][A][2]*/,
+                    int32_t* step_count, const int8_t* actions, const uint8_t* order, uint8_t* obs /*[N][A][W][H][6]*/,
+                    double* rewards, uint8_t* terminated, uint8_t* truncated, int32_t* status);
+void oc_generic_encode(int64_t N, int W, int H, int A, const uint8_t* gcell, const uint8_t* gstate, const uint8_t* pos, uint8_t* obs);
+#ifdef __cplusplus
+}
+#endif

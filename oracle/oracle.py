@@ -410,3 +410,39 @@ class WildfireOracle:
                          C.c_uint64(self.base), _p(obs), _p(rew), _p(term), _p(trunc), C.c_int(int(autoreset)), _p(fin))
         out = (obs, rew, term.astype(bool), trunc.astype(bool))
         return out + (fin,) if want_final_obs else out
+
+
+# ========================================================================== generic MultiGridEnv.step
+class GenericOracle:
+    """Base-class MultiGridEnv.step with DefaultWorld on the CPU (see mg_oracle.h)."""
+
+    def __init__(self, num_envs, width, height, num_agents, max_steps):
+        self.N, self.W, self.H, self.A, self.max_steps = int(num_envs), width, height, num_agents, max_steps
+        self.gcell = np.ones((self.N, width * height), np.uint8)
+        self.gstate = np.zeros((self.N, width * height), np.uint8)
+        self.pos = np.zeros((self.N, num_agents, 2), np.uint8)
+        self.step_count = np.zeros(self.N, np.int32)
+        self.status = C.c_int32(0)
+
+    def set_state_from_obs(self, obs6, pos):
+        """obs6: encode_for_agents arrays [N, W, H, 6] (any agent's view), pos [N, A, 2]."""
+        o = np.asarray(obs6, np.uint8).reshape(self.N, -1, 6)
+        self.gcell[:] = o[..., 0] | (o[..., 1] << 4)
+        self.gstate[:] = np.where(o[..., 0] == 4, o[..., 2], np.where(o[..., 0] == 10, o[..., 4], 0))
+        self.pos[:] = np.asarray(pos).reshape(self.N, self.A, 2)
+        self.step_count[:] = 0
+
+    def encode(self):
+        obs = np.zeros((self.N, self.A, self.W, self.H, 6), np.uint8)
+        lib().oc_generic_encode(C.c_int64(self.N), self.W, self.H, self.A, _p(self.gcell), _p(self.gstate), _p(self.pos), _p(obs))
+        return obs
+
+    def step(self, actions, order):
+        actions = np.ascontiguousarray(actions, np.int8).reshape(self.N, self.A)
+        order = np.ascontiguousarray(order, np.uint8).reshape(self.N, self.A)
+        obs = np.zeros((self.N, self.A, self.W, self.H, 6), np.uint8)
+        rew = np.zeros((self.N, self.A), np.float64)
+        term, trunc = np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8)
+        lib().oc_generic_step(C.c_int64(self.N), self.W, self.H, self.A, self.max_steps, _p(self.gcell), _p(self.gstate), _p(self.pos),
+                              _p(self.step_count), _p(actions), _p(order), _p(obs), _p(rew), _p(term), _p(trunc), C.byref(self.status))
+        return obs, rew, term.astype(bool), trunc.astype(bool)

@@ -470,3 +470,74 @@ def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battle
     out["n_battles"] = out["n_battles"].astype(np.int32)
     out["reward"] = out["reward"].astype(np.float64)
     return out
+
+
+# ------------------------------------------------------------------ generic MultiGridEnv.step
+def make_generic_env(size, n_agents, max_steps, layout_seed):
+    """A DefaultWorld env built ONLY from reference classes, to exercise the base-class step
+    (multigrid.py:397-483) and encode_dim-6 `encode_for_agents` (grid.py:254-284) that no shipped env reaches:
+    border walls plus a random sprinkle of every DefaultWorld object type, SmallActions-compatible actions."""
+    import_reference()
+    from gym_multigrid.multigrid import MultiGridEnv
+    from gym_multigrid.core.agent import Agent, DefaultActions
+    from gym_multigrid.core.grid import Grid
+    from gym_multigrid.core.object import Ball, Box, Door, Floor, Goal, Key, Lava, ObjectGoal, Switch, Wall
+    from gym_multigrid.core.world import DefaultWorld
+
+    class GenericEnv(MultiGridEnv):
+        def __init__(self):
+            agents = [Agent(DefaultWorld, i, actions=DefaultActions) for i in range(n_agents)]
+            super().__init__(agents=agents, grid_size=size, max_steps=max_steps, world=DefaultWorld,
+                             actions_set=DefaultActions, partial_obs=False)
+
+        def _gen_grid(self, width, height):
+            self.grid = Grid(width, height, self.world)
+            self.grid.wall_rect(0, 0, width, height)
+            w = self.world
+            rs = random.Random(layout_seed)
+            objs = [Goal(w, 1), Goal(w, 3), Switch(w), Floor(w, "blue"), Lava(w), Door(w, "yellow"), Door(w, "green", is_open=True),
+                    Door(w, "purple", is_locked=True), Key(w, "yellow"), Ball(w, 2, 1), Box(w, "orange"), ObjectGoal(w, 4), Wall(w),
+                    Goal(w, 0), Floor(w, "red"), Lava(w)]
+            for o in objs:
+                while True:
+                    x, y = rs.randint(1, width - 2), rs.randint(1, height - 2)
+                    if self.grid.get(x, y) is None:
+                        self.put_obj(o, x, y)
+                        break
+            for a in self.agents:
+                while True:
+                    x, y = rs.randint(1, width - 2), rs.randint(1, height - 2)
+                    if self.grid.get(x, y) is None:
+                        self.place_agent(a, pos=(x, y))
+                        a.dir = rs.randint(0, 3)
+                        break
+
+    return GenericEnv()
+
+
+def record_generic_episode(size, n_agents, max_steps, seed, action_rng):
+    env = make_generic_env(size, n_agents, max_steps, seed)
+    np.random.seed(seed)
+    with installed_taps() as taps:
+        obs0, _ = env.reset(seed=seed)
+        rec = dict(actions=[], order=[], obs=[], rewards=[], terminated=[], truncated=[], pos=[], dir=[])
+        init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
+        init_dir = np.array([a.dir for a in env.agents], np.int8)
+        taps.clear()
+        while True:
+            acts = action_rng.choice(4, size=n_agents, p=[0.1, 0.2, 0.2, 0.5])      # still / left / right / forward
+            obs, rew, term, trunc, _ = env.step([int(a) for a in acts])
+            rec["actions"].append(acts.astype(np.int8))
+            rec["order"].append(np.asarray(taps.perm[0], np.uint8))
+            taps.clear()
+            rec["obs"].append(np.stack(obs).astype(np.uint8))
+            rec["rewards"].append(np.asarray(rew, np.float64).copy())
+            rec["terminated"].append(bool(term)); rec["truncated"].append(bool(trunc))
+            rec["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+            rec["dir"].append(np.array([a.dir for a in env.agents], np.int8))
+            if term or trunc:
+                break
+    out = dict(init_obs=np.stack(obs0).astype(np.uint8), init_pos=init_pos, init_dir=init_dir, length=len(rec["actions"]))
+    for k, v in rec.items():
+        out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
+    return out
