@@ -17,7 +17,7 @@ GEN_PLANES = dict(cell=0, state=1, pos=2, hdr=3, init_cell=4, init_state=5, init
 WF_PLANE_TERRAIN, WF_PLANE_AGENTS, WF_PLANE_HDR = 0, 1, 2
 MAX_WILDFIRE_AGENTS = 32
 OBS_U8, OBS_REFERENCE = 0, 1
-MAP_PLANE_POS, MAP_PLANE_DIR, MAP_PLANE_FLAGS, MAP_PLANE_HDR = 0, 1, 2, 3
+MAP_PLANE_AGENTS, MAP_PLANE_HDR = 0, 1
 ERR_BAD_ACTION = 8
 MAX_MAP_AGENTS = 16
 LAYOUTS = {"even_dist": 0, "quadrants": 1, "rooms": 2, "quadrants_respawn": 3}

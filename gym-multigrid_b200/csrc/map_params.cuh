@@ -19,8 +19,14 @@ struct MapParams {
   const uint16_t* background;  // Maze: cells with code background, np.where order
   const uint16_t* blue_terr;   // CtF: blue territory cells + blue flag (ctf.py:765-769)
   const uint16_t* red_terr;
+  // battle tests restated in integers (bit-exact, computed on the host with the same double arithmetic):
+  int d2_max;                              // largest squared distance d2 with sqrt((double)d2) <= battle_range (-1: none)
+  unsigned long long thr_blue_home, thr_red_home, thr_even;  // blue wins iff u32 < ceil(p * 2^32), p = randomness / 1 - randomness / 0.5
+  int obs_staged;                          // 1 = the tile's u8 obs slab is assembled in shared memory (small maps)
   // state planes
-  uint8_t* pos; uint8_t* dir; uint8_t* flags; int4* hdr;
+  uint8_t* agents;   // [N_pad][row_bytes]: agent i at bytes 4i..4i+3 = x, y, dir, flags (bit0 terminated, bit1 collided)
+  int row_bytes;     // 4 * (n rounded up to a power of two)
+  int4* hdr;
   // io
   const int8_t* actions; void* obs; double* rewards; uint8_t* terminated; uint8_t* truncated; void* final_obs;
   const uint8_t* reset_mask;

@@ -4,6 +4,7 @@
 // entry point that produces results does so by launching a kernel on the handle's device.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,8 +24,9 @@ cudaError_t configure_kernels(int v, int cells, int A);
 size_t tile_smem(int v, int cells, int A);
 struct MapParams;
 cudaError_t launch_map(const MapParams& p, cudaStream_t st);
-cudaError_t configure_map_kernels(int L, int n);
-size_t map_smem_bytes(int L, int n);
+cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype);
+size_t map_smem_bytes(int L, int n, int cells, int obs_dtype);
+bool map_obs_staged(int cells, int obs_dtype);
 int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
@@ -34,8 +36,7 @@ int map_tile_envs();
 namespace mg {
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
-cudaError_t configure_view_kernels(size_t bytes);
-size_t view_smem_bytes(int family, int cells, int A, int V);
+size_t view_smem_bytes(const ViewParams& p);
 int view_max();
 int view_tile_envs();
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st);
@@ -60,6 +61,8 @@ struct mg_env {
   int act_cols, rew_cols;
   size_t view_smem_configured;
   size_t map_codes_off;   // Maze: offset of the packed static map (partial views) inside d_map_tables
+  size_t map_padded_off, map_padded_bytes;  // ... and of the copy padded with the out-of-map filler (fast view kernel)
+  int map_pad;
   int device;
   int tile;  // kernel tile variant (envs per CTA x threads), MG_TILE env var, default 0
   long long n_pad;
@@ -309,9 +312,9 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create_map: kernels are built for sm_100a only");
-  if (mg::map_smem_bytes((int)L, n) > (size_t)prop.sharedMemPerBlockOptin)
+  if (mg::map_smem_bytes((int)L, n, cells, cfg->obs_dtype) > (size_t)prop.sharedMemPerBlockOptin)
     return fail(nullptr, "mg_create_map: map too large: lcm(size*size, 16) bytes must fit in shared memory");
-  if ((ce = mg::configure_map_kernels((int)L, n)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
+  if ((ce = mg::configure_map_kernels((int)L, n, cells, cfg->obs_dtype)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
 
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_map: out of host memory");
@@ -326,7 +329,9 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   env->act_cols = nb; env->rew_cols = 1;
   const int E = mg::map_tile_envs();
   env->n_pad = (cfg->num_envs + E - 1) / E * E;
-  const size_t rows[MG_MAP_PLANE_COUNT] = {(size_t)n * 2, (size_t)n, (size_t)n, 16};
+  int slots = 1;
+  while (slots < n) slots *= 2;
+  const size_t rows[MG_MAP_PLANE_COUNT] = {(size_t)slots * 4, 16};
   size_t off = 0;
   for (int i = 0; i < MG_MAP_PLANE_COUNT; ++i) {
     env->plane_off[i] = off; env->plane_row[i] = rows[i]; env->plane_bytes[i] = rows[i] * (size_t)env->n_pad;
@@ -342,7 +347,10 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
     period[k] = (char)(maze ? cfg->field_map[i] : cfg->field_map[(i % S) * S + (i / S)]);
   }
   const size_t o_map = 0, o_per = align_up((size_t)cells, 256), o_bg = align_up(o_per + L, 256),
-               o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), o_pk = align_up(o_rt + rt.size(), 256), total = align_up(o_pk + cells, 256) + 256;
+               o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), o_pk = align_up(o_rt + rt.size(), 256),
+               o_pad = align_up(o_pk + cells, 256);
+  const int pad = 14, pitch = S + 2 * pad;   // view_size <= 15: a view reaches at most 14 cells beyond the map
+  const size_t padded_bytes = align_up((size_t)pitch * pitch, 16), total = align_up(o_pad + padded_bytes, 256) + 256;
   std::string blob(total, '\0');
   std::memcpy(&blob[o_map], cfg->field_map, cells);
   std::memcpy(&blob[o_per], period.data(), L);
@@ -354,6 +362,11 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
       const int c = cfg->field_map[i];
       blob[o_pk + i] = (char)(c == 0 ? mg::cell(0, 10, 0) : (c == 2 ? mg::cell(2, 0, 0) : mg::cell(3, 7, 0)));
     }
+  if (maze) {
+    std::memset(&blob[o_pad], (int)mg::cell(3, 7, 1), padded_bytes);   // the out-of-map filler (see mg_gen_obs)
+    for (int x = 0; x < S; ++x) std::memcpy(&blob[o_pad + (size_t)(x + pad) * pitch + pad], &blob[o_pk + (size_t)x * S], S);
+  }
+  env->map_padded_off = o_pad; env->map_padded_bytes = padded_bytes; env->map_pad = pad;
   if ((ce = cudaMalloc(&env->d_map_tables, total)) != cudaSuccess ||
       (ce = cudaMemcpy(env->d_map_tables, blob.data(), total, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess ||
@@ -369,6 +382,15 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   p.battle_reward = cfg->battle_reward; p.battle_range = cfg->battle_range; p.randomness = cfg->randomness;
   p.n_background = (int)bg.size() / 2; p.len_blue = (int)bt.size() / 2; p.len_red = (int)rt.size() / 2;
   p.blue_flag = blue_flag; p.red_flag = red_flag;
+  // integer restatements of the battle tests (ctf.py:1368, 1392-1407), formed with the reference's double arithmetic
+  p.d2_max = -1;
+  for (int d2 = 0; d2 <= 2 * 255 * 255 && std::sqrt((double)d2) <= cfg->battle_range; ++d2) p.d2_max = d2;
+  auto win_threshold = [](double pb) -> unsigned long long {
+    const double t = std::ceil(pb * 4294967296.0);   // (double)u / 2^32 < pb  <=>  u < ceil(pb * 2^32): scaling by 2^32 is exact
+    return t <= 0.0 ? 0ull : (t >= 4294967296.0 ? 4294967296ull : (unsigned long long)t);
+  };
+  p.thr_blue_home = win_threshold(cfg->randomness); p.thr_red_home = win_threshold(1.0 - cfg->randomness); p.thr_even = win_threshold(0.5);
+  p.obs_staged = mg::map_obs_staged(cells, cfg->obs_dtype) ? 1 : 0;
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.field_map = env->d_map_tables + o_map; p.obs_period = env->d_map_tables + o_per; p.L = (int)L;
   p.background = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bg);
@@ -391,8 +413,8 @@ extern "C" int mg_set_map_trace(mg_env* env, const mg_map_trace* t) {
 static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, const uint8_t* mask, void* obs, cudaStream_t st) {
   mg::MapParams p = env->mbase;
   uint8_t* s = static_cast<uint8_t*>(state);
-  p.pos = s + env->plane_off[MG_MAP_PLANE_POS]; p.dir = s + env->plane_off[MG_MAP_PLANE_DIR];
-  p.flags = s + env->plane_off[MG_MAP_PLANE_FLAGS]; p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_MAP_PLANE_HDR]);
+  p.agents = s + env->plane_off[MG_MAP_PLANE_AGENTS]; p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
+  p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_MAP_PLANE_HDR]);
   p.op = op; p.reset_mask = mask;
   if (env->has_trace) {
     const mg_map_trace& t = env->mtrace;
@@ -645,25 +667,23 @@ extern "C" int mg_gen_obs(mg_env* env, const void* state, const uint8_t* dirs, i
   p.V = view_size; p.see_through = see_through_walls != 0; p.family = env->family;
   if (env->family == MG_FAMILY_COLLECT) {
     p.W = env->cfg.width; p.H = env->cfg.height; p.A = env->cfg.num_agents; p.N = env->cfg.num_envs;
-    p.grid = s + env->plane_off[MG_PLANE_GRID]; p.pos = s + env->plane_off[MG_PLANE_AGENT_POS];
-    p.dirs = dirs;                                  // NULL = 3 for every agent
+    p.grid = s + env->plane_off[MG_PLANE_GRID]; p.pos = s + env->plane_off[MG_PLANE_AGENT_POS]; p.pos_stride = 2;
+    p.dirs = dirs; p.dir_stride = 1;                // NULL = 3 for every agent
     p.oob_code = mg::WALL_GREY;                     // Grid.slice: Wall(self.world) outside the grid (grid.py:124-127)
   } else {
     p.W = p.H = env->mcfg.size; p.A = 1; p.N = env->mcfg.num_envs;
-    p.pos = s + env->plane_off[MG_MAP_PLANE_POS];
-    p.dirs = dirs ? dirs : s + env->plane_off[MG_MAP_PLANE_DIR];
+    p.pos = s + env->plane_off[MG_MAP_PLANE_AGENTS]; p.pos_stride = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
+    p.dirs = dirs ? dirs : p.pos + 2; p.dir_stride = dirs ? 1 : p.pos_stride;
     p.map_codes = env->d_map_tables + env->map_codes_off;
+    p.map_padded = env->d_map_tables + env->map_padded_off; p.pad = env->map_pad; p.pitch = p.W + 2 * env->map_pad;
+    p.map_padded_bytes = (int)env->map_padded_bytes;
     p.oob_code = mg::cell(3, 7, 1);                 // extension: MazeWorld has no wall (world.py:81-91); an opaque obstacle-coloured filler, state 1 marks it
     p.agent_code = mg::cell(1, 4, 0);               // Agent(color="blue", type="agent") maze.py:93-101
   }
   p.cells = p.W * p.H;
   p.out = out; p.out_bulk_ok = aligned16(out);
-  const size_t smem = mg::view_smem_bytes(p.family, p.cells, p.A, p.V);
-  if (smem > 227 * 1024) return fail(env, "mg_gen_obs: view tile does not fit in shared memory (reduce view_size)");
-  if (smem > env->view_smem_configured) {
-    if ((ce = mg::configure_view_kernels(smem)) != cudaSuccess) return cuda_fail(env, "cudaFuncSetAttribute", ce);
-    env->view_smem_configured = smem;
-  }
+  if (mg::view_smem_bytes(p) > 227 * 1024) { p.map_padded = nullptr; }  // large padded maps: the generic kernel reads the map through L1
+  if (mg::view_smem_bytes(p) > 227 * 1024) return fail(env, "mg_gen_obs: view tile does not fit in shared memory (reduce view_size)");
   if ((ce = mg::launch_view(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "view_kernel", ce);
   env->launches += 1;
   return 0;

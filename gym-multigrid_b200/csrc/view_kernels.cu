@@ -5,18 +5,178 @@
 // The reference's gen_obs passes one positional argument too many to encode_for_agents
 // (multigrid.py:526-528 vs grid.py:254) and raises; this follows the algorithm its pieces define.
 //
-// One thread per (env, agent) view.  slice + rotations are folded into direct world indices; the
-// visibility flood is a row sweep over V-bit masks; views are assembled in shared memory and the tile's
-// contiguous slab of views leaves with one TMA bulk store.
+// This path is instruction-issue bound, not HBM bound (147 output bytes per view need several hundred
+// instructions), so the fast kernel (odd V <= 7) is written for instruction count: one thread per view with
+// everything in registers (V is a template parameter, all loops unroll) -
+//   * slice + rotations folded into one base index and two strides; cells are byte gathers from shared memory
+//     (Collect: the tile's grid slab, staged by one TMA bulk load, with guard bands so that out-of-grid reads need
+//     no predication; Maze: the static map pre-padded with the out-of-bounds filler, staged the same way);
+//   * out-of-grid cells are selected by two V-bit range masks instead of per-cell bounds tests;
+//   * process_vis as a bit-parallel (Kogge-Stone) flood over V-bit row masks: ~30 ALU ops per row;
+//   * the masked codes are packed four per register in output order, expanded to (type, colour, state) bytes with
+//     PRMT, re-aligned with one funnel shift per word and written to shared memory as 32-bit stores (the 147-byte
+//     view pitch spreads a warp over all 32 banks); the tile's contiguous slab of views leaves as one TMA bulk store.
+// Other view sizes (even V, V > 7) take the generic kernel below (runtime V, per-cell loops).
+#include <cstdlib>
+
 #include "mg_device.cuh"
 #include "view_params.cuh"
 
 namespace mg {
 
-constexpr int kViewE = 64;        // envs per CTA
+constexpr int kViewE = 64;        // envs per CTA (generic kernel; fast kernel, Collect)
 constexpr int kViewThreads = 128;
 constexpr int kViewMax = 15;      // largest view size
+constexpr int kViewMazeE = 128;   // envs per CTA (fast kernel, Maze: one view per env)
 
+// V-bit mask of the t in [0, V) with 0 <= u0 + s*t < L  (s = +1 / -1)
+__device__ __forceinline__ uint32_t range_mask(int u0, int s, int L, int V) {
+  int lo = s > 0 ? -u0 : u0 - (L - 1), hi = s > 0 ? L - 1 - u0 : u0;
+  lo = max(lo, 0); hi = min(hi, V - 1);
+  return hi < lo ? 0u : (((2u << hi) - 1u) & ~((1u << lo) - 1u));
+}
+
+__host__ __device__ constexpr int view_guard_bytes(int V, int H) { return ((V - 1) * (H + 1) + 15) / 16 * 16; }
+
+template <int FAMILY, int V>
+__global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_constant__ ViewParams p) {
+  static_assert(V % 2 == 1 && V <= 7, "fast path: odd view sizes up to 7");
+  constexpr int VV = V * V, HS = V / 2, NPK = (VV + 3) / 4, NW = (3 * VV + 1) / 4, NFULL = (3 * VV - 3) / 4;
+  constexpr uint32_t FULL = (1u << V) - 1u;
+  constexpr int E = FAMILY == MG_FAMILY_COLLECT ? kViewE : kViewMazeE;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, A = p.A;
+  const long long e0 = (long long)blockIdx.x * E;
+  const int n_here = (int)min((long long)E, p.N - e0);
+  const int views = n_here * A;
+  const uint32_t out_bytes_tile = (uint32_t)E * A * VV * 3;
+  uint8_t* s_out = smem_raw;                                              // [E*A][VV*3]
+  uint8_t* s_src = smem_raw + ((out_bytes_tile + 15u) & ~15u);            // Collect: guard | [E][cells] | guard; Maze: padded map
+  const int guard = FAMILY == MG_FAMILY_COLLECT ? view_guard_bytes(V, p.H) : 0;
+
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  pdl_launch_dependents();
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0) {
+    if (FAMILY == MG_FAMILY_COLLECT) {  // the grid plane is padded to whole tiles of >= 64 envs
+      mbar_expect_tx(&bar, (uint32_t)E * p.cells);
+      tma_load_1d(s_src + guard, p.grid + e0 * p.cells, (uint32_t)E * p.cells, &bar);
+    } else {
+      mbar_expect_tx(&bar, (uint32_t)p.map_padded_bytes);
+      tma_load_1d(s_src, p.map_padded, (uint32_t)p.map_padded_bytes, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+
+  const int pitch = FAMILY == MG_FAMILY_COLLECT ? p.H : p.pitch;
+  for (int v = tid; v < views; v += kViewThreads) {
+    const long long gv = e0 * A + v;
+    const int x = p.pos[gv * p.pos_stride], y = p.pos[gv * p.pos_stride + 1];
+    const int dir = p.dirs ? (p.dirs[gv * p.dir_stride] & 3) : 3;
+    // world cell of view cell (a, b): (x0 + a*ax + b*bx, y0 + a*ay + b*by); linear index i0 + a*sa + b*sb
+    int x0, y0, sa, sb;
+    if (dir == 3)      { x0 = x - HS;      y0 = y - (V - 1); sa = pitch;  sb = 1; }       // facing up
+    else if (dir == 1) { x0 = x + HS;      y0 = y + (V - 1); sa = -pitch; sb = -1; }      // facing down
+    else if (dir == 0) { x0 = x + (V - 1); y0 = y - HS;      sa = 1;      sb = -pitch; }  // facing right
+    else               { x0 = x - (V - 1); y0 = y + HS;      sa = -1;     sb = pitch; }   // facing left
+    const uint8_t* src;
+    uint32_t mA = FULL, mB = FULL;
+    if (FAMILY == MG_FAMILY_COLLECT) {
+      src = s_src + guard + (v / A) * p.cells + x0 * pitch + y0;
+      const bool a_is_x = dir & 1;  // dirs 1, 3: a walks along x, b along y
+      mA = a_is_x ? range_mask(x0, dir == 3 ? 1 : -1, p.W, V) : range_mask(y0, dir == 0 ? 1 : -1, p.H, V);
+      mB = a_is_x ? range_mask(y0, dir == 3 ? 1 : -1, p.H, V) : range_mask(x0, dir == 2 ? 1 : -1, p.W, V);
+    } else {
+      src = s_src + (x0 + p.pad) * pitch + (y0 + p.pad);
+    }
+    uint32_t pk[NPK], opq[V], msk[V];
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) pk[k] = 0;
+#pragma unroll
+    for (int b = 0; b < V; ++b) {
+      const uint32_t rowv = ((mB >> b) & 1u) ? mA : 0u;
+      uint32_t o = 0;
+#pragma unroll
+      for (int a = 0; a < V; ++a) {
+        uint32_t c = src[a * sa + b * sb];
+        if (FAMILY == MG_FAMILY_COLLECT) {
+          c = ((rowv >> a) & 1u) ? c : (uint32_t)p.oob_code;
+          o |= (uint32_t)((c & 3u) == (uint32_t)T_WALL) << a;     // see_behind() is False only for Wall (object.py:174-179)
+        } else {
+          if (a == HS && b == V - 1) c = (uint32_t)p.agent_code | ((uint32_t)dir << 6);  // the agent stands at view cell (V/2, V-1)
+          o |= (uint32_t)(c == (uint32_t)p.oob_code) << a;         // Maze: only the out-of-map filler blocks sight
+        }
+        pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
+      }
+      opq[b] = o; msk[b] = 0;
+    }
+    if (p.see_through) {
+#pragma unroll
+      for (int b = 0; b < V; ++b) msk[b] = FULL;
+    } else {  // process_vis (grid.py:286-323): rows bottom-up; inside a row left->right, then right->left
+      msk[V - 1] = 1u << HS;
+#pragma unroll
+      for (int j = V - 1; j >= 0; --j) {
+        const uint32_t clear = ~opq[j] & FULL;
+        uint32_t m = msk[j];
+        // left -> right: F = cells that are visible AND transparent once the sweep has passed them
+        uint32_t F = m & clear, P = clear;
+        F |= P & (F << 1); P &= P << 1;
+        F |= P & (F << 2);
+        if (V > 4) { P &= P << 2; F |= P & (F << 4); }
+        F &= FULL >> 1;                       // the loop runs i = 0 .. V-2
+        m |= F << 1;
+        uint32_t up = F | (F << 1);
+        // right -> left
+        uint32_t G = m & clear; P = clear;
+        G |= P & (G >> 1); P &= P >> 1;
+        G |= P & (G >> 2);
+        if (V > 4) { P &= P >> 2; G |= P & (G >> 4); }
+        G &= ~1u;                             // the loop runs i = V-1 .. 1
+        m |= G >> 1;
+        up |= G | (G >> 1);
+        msk[j] = m;
+        if (j > 0) msk[j - 1] |= up;
+      }
+    }
+    // encode_for_agents: cells outside the mask stay (0, 0, 0)
+#pragma unroll
+    for (int a = 0; a < V; ++a)
+#pragma unroll
+      for (int b = 0; b < V; ++b)
+        if (!((msk[b] >> a) & 1u)) pk[(a * V + b) / 4] &= ~(0xFFu << (8 * ((a * V + b) % 4)));
+    uint32_t w[NW + 2];
+#pragma unroll
+    for (int k = 0; k < NPK; ++k) {
+      uint32_t o0, o1, o2;
+      expand4(pk[k], o0, o1, o2);
+      w[3 * k] = o0;
+      if (3 * k + 1 < NW + 2) w[3 * k + 1] = o1;
+      if (3 * k + 2 < NW + 2) w[3 * k + 2] = o2;
+    }
+    // 3*VV bytes at byte offset v*3*VV: h head bytes up to the next word boundary, NFULL aligned words, 3-h tail bytes
+    uint8_t* dst = s_out + (size_t)v * (3 * VV);
+    const int h = (int)((4u - ((uint32_t)v * (3u * VV) & 3u)) & 3u);
+    uint32_t* q = reinterpret_cast<uint32_t*>(dst + h);
+#pragma unroll
+    for (int j = 0; j < NFULL; ++j) q[j] = __funnelshift_r(w[j], w[j + 1], 8 * h);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const bool head = i < h;
+      dst[head ? i : 4 * NFULL + i] = (uint8_t)((head ? w[0] : w[NFULL]) >> (8 * i));
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  const uint32_t bytes = (uint32_t)views * VV * 3;
+  const uint32_t bulk = p.out_bulk_ok ? (bytes & ~15u) : 0u;
+  uint8_t* dst = p.out + e0 * A * VV * 3;
+  if (tid == 0 && bulk) { tma_store_1d(dst, s_out, bulk); tma_commit(); }
+  for (uint32_t i = bulk + tid; i < bytes; i += kViewThreads) dst[i] = s_out[i];
+  if (tid == 0) tma_wait_read_all();
+}
 
 template <int FAMILY>
 __device__ __forceinline__ uint8_t fetch_cell(const ViewParams& p, const uint8_t* g, int ax, int ay, int adir, int x, int y) {
@@ -64,8 +224,8 @@ __global__ void __launch_bounds__(kViewThreads) view_kernel(const __grid_constan
     const int el = v / A, k = v - el * A;
     const long long e = e0 + el;
     const uint8_t* g = s_grid + (size_t)el * cells;
-    const int x = p.pos[(e * A + k) * 2], y = p.pos[(e * A + k) * 2 + 1];
-    const int dir = p.dirs ? p.dirs[e * A + k] : 3;
+    const int x = p.pos[(e * A + k) * p.pos_stride], y = p.pos[(e * A + k) * p.pos_stride + 1];
+    const int dir = p.dirs ? (p.dirs[(e * A + k) * p.dir_stride] & 3) : 3;
     const int hs = V / 2;
     uint32_t opq[kViewMax + 1], msk[kViewMax + 1];
     for (int b = 0; b < V; ++b) {
@@ -150,22 +310,67 @@ cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, l
   return cudaGetLastError();
 }
 
-size_t view_smem_bytes(int family, int cells, int A, int V) {
-  return (size_t)kViewE * A * V * V * 3 + (size_t)kViewThreads * V * V + 16 +
-         (family == MG_FAMILY_COLLECT ? (size_t)kViewE * cells : 0);
+static bool view_is_fast(const ViewParams& p) {
+  static const bool off = [] { const char* v = std::getenv("MG_VIEW_GENERIC"); return v && v[0] == '1'; }();
+  if (off || !(p.V == 3 || p.V == 5 || p.V == 7)) return false;
+  return p.family == MG_FAMILY_COLLECT || p.map_padded != nullptr;
+}
+
+static size_t view_fast_smem(const ViewParams& p) {
+  const size_t E = p.family == MG_FAMILY_COLLECT ? kViewE : kViewMazeE;
+  const size_t out = (E * p.A * p.V * p.V * 3 + 15) / 16 * 16;
+  return out + (p.family == MG_FAMILY_COLLECT ? E * p.cells + 2 * (size_t)view_guard_bytes(p.V, p.H) : (size_t)p.map_padded_bytes);
+}
+
+size_t view_smem_bytes(const ViewParams& p) {
+  if (view_is_fast(p)) return view_fast_smem(p);
+  return (size_t)kViewE * p.A * p.V * p.V * 3 + (size_t)kViewThreads * p.V * p.V + 16 +
+         (p.family == MG_FAMILY_COLLECT ? (size_t)kViewE * p.cells : 0);
 }
 int view_max() { return kViewMax; }
 int view_tile_envs() { return kViewE; }
 
-// opt the kernels in to `bytes` of dynamic shared memory (call outside stream capture, before the first launch)
-cudaError_t configure_view_kernels(size_t bytes) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_MAZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+template <int FAMILY, int V>
+static cudaError_t launch_fast(const ViewParams& p, size_t smem, cudaStream_t st) {
+  static size_t configured[64] = {};   // per kernel instantiation and device; raised by the first (eager) call
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)view_fast_kernel<FAMILY, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = smem;
+  }
+  constexpr int E = FAMILY == MG_FAMILY_COLLECT ? kViewE : kViewMazeE;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((p.N + E - 1) / E)); cfg.blockDim = dim3(kViewThreads);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, view_fast_kernel<FAMILY, V>, p);
 }
 
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st) {
-  const size_t smem = view_smem_bytes(p.family, p.cells, p.A, p.V);
+  const size_t smem = view_smem_bytes(p);
+  if (view_is_fast(p)) {
+    const bool c = p.family == MG_FAMILY_COLLECT;
+    switch (p.V) {
+      case 3: return c ? launch_fast<MG_FAMILY_COLLECT, 3>(p, smem, st) : launch_fast<MG_FAMILY_MAZE, 3>(p, smem, st);
+      case 5: return c ? launch_fast<MG_FAMILY_COLLECT, 5>(p, smem, st) : launch_fast<MG_FAMILY_MAZE, 5>(p, smem, st);
+      default: return c ? launch_fast<MG_FAMILY_COLLECT, 7>(p, smem, st) : launch_fast<MG_FAMILY_MAZE, 7>(p, smem, st);
+    }
+  }
+  static size_t configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_MAZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev & 63] = smem;
+  }
   const unsigned blocks = (unsigned)((p.N + kViewE - 1) / kViewE);
   if (p.family == MG_FAMILY_COLLECT) view_kernel<MG_FAMILY_COLLECT><<<blocks, kViewThreads, smem, st>>>(p);
   else view_kernel<MG_FAMILY_MAZE><<<blocks, kViewThreads, smem, st>>>(p);

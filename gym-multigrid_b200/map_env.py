@@ -75,11 +75,15 @@ class _MapVecEnv:
             self._trunc = torch.zeros(N, dtype=torch.uint8, device=self.device)
         self._final_obs = None
         self._planes = {}
-        for name, pid, dt, cols in (("pos", _lib.MAP_PLANE_POS, torch.uint8, n * 2), ("dir", _lib.MAP_PLANE_DIR, torch.uint8, n),
-                                    ("flags", _lib.MAP_PLANE_FLAGS, torch.uint8, n), ("hdr", _lib.MAP_PLANE_HDR, torch.int32, 4)):
+        slots = 1
+        while slots < n:
+            slots *= 2
+        for name, pid, dt, cols in (("agents", _lib.MAP_PLANE_AGENTS, torch.uint8, slots * 4), ("hdr", _lib.MAP_PLANE_HDR, torch.int32, 4)):
             off, nbytes, row = C.c_size_t(), C.c_size_t(), C.c_size_t()
             self._lib.mg_state_plane(self._h, pid, C.byref(off), C.byref(nbytes), C.byref(row))
+            assert row.value == cols * dt.itemsize, "state plane layout mismatch between the library and the host mirror"
             self._planes[name] = self.state[off.value: off.value + nbytes.value].view(dt).view(-1, cols)[:N]
+        self._agents = self._planes["agents"].view(N, slots, 4)[:, :n]     # (x, y, dir, flags) per agent
         self._io = _lib.StepIO()
         self._host = None
         self._trace_keepalive = None
@@ -88,15 +92,20 @@ class _MapVecEnv:
     # --- zero-copy state views
     @property
     def agent_pos(self):
-        return self._planes["pos"].view(self.num_envs, self.n_agents, 2)
+        return self._agents[..., 0:2]
 
     @property
     def agent_dir(self):
-        return self._planes["dir"]
+        return self._agents[..., 2]
+
+    @property
+    def agent_flags(self):
+        """u8 [N, n]: bit0 terminated (defeated), bit1 collided (agent.py:97-100)."""
+        return self._agents[..., 3]
 
     @property
     def agent_terminated(self):
-        return (self._planes["flags"] & 1).bool()
+        return (self._agents[..., 3] & 1).bool()
 
     @property
     def step_count(self):

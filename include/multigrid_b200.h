@@ -188,11 +188,11 @@ typedef struct mg_map_config {
 } mg_map_config;
 
 /* planes of the map families' state buffer */
-enum { MG_MAP_PLANE_POS = 0,    /* u8  [N_pad][n][2] (x, y), n = num_blue + num_red   Agent.pos */
-       MG_MAP_PLANE_DIR = 1,    /* u8  [N_pad][n]                                     Agent.dir */
-       MG_MAP_PLANE_FLAGS = 2,  /* u8  [N_pad][n]  bit0 terminated (defeated), bit1 collided (agent.py:97-100) */
-       MG_MAP_PLANE_HDR = 3,    /* i32 [N_pad][4]  step_count, 0, Philox block counter, episodes */
-       MG_MAP_PLANE_COUNT = 4 };
+enum { MG_MAP_PLANE_AGENTS = 0, /* u8  [N_pad][row]: agent i (blue first, n = num_blue + num_red) at bytes 4i .. 4i+3 =
+                                   x, y (Agent.pos), dir (Agent.dir), flags (bit0 terminated / defeated, bit1 collided,
+                                   agent.py:97-100); row = 4 * (n rounded up to a power of two) bytes */
+       MG_MAP_PLANE_HDR = 1,    /* i32 [N_pad][4]  step_count, 0, Philox block counter, episodes */
+       MG_MAP_PLANE_COUNT = 2 };
 
 /* Validation mode for the map families: recorded outputs of the reference's RNG call sites. */
 typedef struct mg_map_trace {

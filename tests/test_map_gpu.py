@@ -128,7 +128,7 @@ def test_ctf_philox_matches_oracle(nb, nr, n, pen, cuda_device):
         assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
         d = oterm | otrunc
         assert np.array_equal(_np(info["final_observation"])[d], ofin[d])
-        assert np.array_equal(_np(env.agent_pos), o.pos) and np.array_equal(_np(env._planes["flags"]), o.flags)
+        assert np.array_equal(_np(env.agent_pos), o.pos) and np.array_equal(_np(env.agent_flags), o.flags)
         assert np.array_equal(_np(env.agent_dir), o.dir)
         battles += int((np.abs(orew + 0.01 * nb) > 0.2).sum())
     assert env.status() == 0 and battles > 0

@@ -1,0 +1,208 @@
+#!/usr/bin/env python
+"""Micro-benchmark of every kernel family besides the Collect step (development aid; tools/kbench.py covers Collect).
+
+    python tools/kbench_families.py [--which ctf,maze,view,toroid,wildfire,generic,collect_streams] [--reps 40]
+
+Same protocol as bench.py: CUDA graph over B independent env batches whose working set exceeds the 126 MB L2,
+CUDA events on the launching stream, warm-up first.  Each line reports the algorithmic bytes per env-step of that
+configuration and the achieved GB/s against MEASURED_PEAKS.json.  Runs on the GPU box only:
+maps come from the committed golden fixtures, nothing under /root/reference is read.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gym_multigrid_b200 as mg  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        return 6650.0
+
+
+def golden(stem, key):
+    with np.load(os.path.join(GOLDEN, stem + ".npz")) as z:
+        return z[key]
+
+
+def graph_time(fns, reps, streams=1):
+    """us per call of the callables in `fns`, captured once into a CUDA graph (forked over `streams` streams)."""
+    dev = torch.device("cuda:0")
+    main = torch.cuda.Stream(device=dev)
+    side = [torch.cuda.Stream(device=dev) for _ in range(streams - 1)]
+    with torch.cuda.stream(main):
+        for f in fns:
+            f()
+        main.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            for s in side:
+                s.wait_stream(main)
+            for i, f in enumerate(fns):
+                st = main if i % streams == 0 else side[i % streams - 1]
+                with torch.cuda.stream(st):
+                    f()
+            for s in side:
+                main.wait_stream(s)
+        for _ in range(3):
+            g.replay()
+        main.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for _ in range(reps):
+            g.replay()
+        e1.record(main)
+        main.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * len(fns))
+
+
+def report(name, n, us, bytes_per_env, **extra):
+    gbs = n * bytes_per_env / us / 1e3
+    print(json.dumps({"kernel": name, "num_envs": n, "us_per_launch": round(us, 3), "algorithmic_bytes_per_env": bytes_per_env,
+                      "GBps": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak(), 4), "env_steps_per_s": n / us * 1e6, **extra}),
+          flush=True)
+
+
+def batches_for(bytes_per_env, n, want=400e6, lo=2, hi=32):
+    return int(max(lo, min(hi, np.ceil(want / (bytes_per_env * n)))))
+
+
+def bench_ctf(args):
+    fm = golden("ctf_2v2", "field_map")
+    for nb, nr, n in ((2, 2, 65536), (2, 2, 1 << 20), (8, 8, 1 << 18)):
+        if nb + nr > 8 and fm.shape[0] < 10:
+            continue
+        bpe = 100 + 2 * (4 * (nb + nr) + 16) + nb + 10          # obs u8 + state r/w + actions + reward/flags
+        B = batches_for(bpe, n)
+        envs = [mg.make_ctf_vec(n, fm, num_blue_agents=nb, num_red_agents=nr, seed=b, env_id_base=b * n) for b in range(B)]
+        acts = [torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+        for e in envs:
+            e.reset()
+        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        report(f"map_kernel<ctf> {nb}v{nr} 10x10 map obs u8", n, us, bpe, batches=B)
+        for e in envs:
+            e.close()
+    n = 65536
+    envs = [mg.make_ctf_vec(n, fm, reference_dtypes=True, seed=b, env_id_base=b * n) for b in range(8)]
+    acts = [torch.randint(0, 5, (n, 2), device="cuda:0", dtype=torch.int8) for _ in range(8)]
+    for e in envs:
+        e.reset()
+    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    report("map_kernel<ctf> 2v2 10x10 map obs int64 (reference dtype)", n, us, 800 + 2 * 32 + 12, batches=8)
+    for e in envs:
+        e.close()
+
+
+def bench_maze(args):
+    fm = golden("maze_gen64", "field_map")
+    for n, ref in ((16384, False), (131072, False), (16384, True)):
+        elem = 8 if ref else 1
+        bpe = 4096 * elem + 2 * (4 + 16) + 1 + 10
+        B = batches_for(bpe, n)
+        envs = [mg.make_maze_vec(n, fm, seed=b, env_id_base=b * n, reference_dtypes=ref) for b in range(B)]
+        acts = [torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+        for e in envs:
+            e.reset()
+        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        report(f"map_kernel<maze> 64x64 full-map obs {'float64 (reference dtype)' if ref else 'u8'}", n, us, bpe, batches=B)
+        if not ref:
+            outs = [torch.empty((n, 1, 7, 7, 3), dtype=torch.uint8, device="cuda:0") for _ in range(B)]
+            us = graph_time([lambda e=e, o=o: e.gen_obs(7, False, out=o) for e, o in zip(envs, outs)], args.reps)
+            report("view_kernel maze 64x64 V=7 partial obs", n, us, 147 + 4, batches=B)
+        for e in envs:
+            e.close()
+
+
+def bench_view(args):
+    n = 65536
+    for env_id, V in (("multigrid-collect-respawn-clustered-v0", 7), ("multigrid-collect-rooms-respawn-v0", 5)):
+        B = 8
+        envs = [mg.make_vec(env_id, n, seed=b, env_id_base=b * n) for b in range(B)]
+        for e in envs:
+            e.reset()
+        A, cells = envs[0].num_agents, envs[0].width * envs[0].height
+        outs = [torch.empty((n, A, V, V, 3), dtype=torch.uint8, device="cuda:0") for _ in range(B)]
+        us = graph_time([lambda e=e, o=o: e.gen_obs(V, False, out=o) for e, o in zip(envs, outs)], args.reps)
+        report(f"view_kernel collect {env_id} V={V}", n, us, cells + 2 * A + A * V * V * 3, batches=B)
+        touts = [torch.empty((n, A, envs[0].width, envs[0].height, envs[0].num_ball_types + A), dtype=torch.float32, device="cuda:0")
+                 for _ in range(B)]
+        us = graph_time([lambda e=e, o=o: e.toroid_obs(out=o) for e, o in zip(envs, touts)], args.reps)
+        report(f"toroid_kernel {env_id}", n, us, cells + 2 * A + touts[0][0].numel() * 4, batches=B)
+        for e in envs:
+            e.close()
+
+
+def bench_wildfire(args):
+    for size, A, n in ((64, 16, 16384), (64, 16, 131072), (32, 32, 65536)):
+        cells = size * size
+        bpe = A + 2 * (cells + 4 * A + 16) + 3 * cells + 8 * A + 2
+        B = batches_for(bpe, n, lo=2, hi=8)
+        envs = [mg.make_wildfire_vec(n, size=size, num_agents=A, seed=b, env_id_base=b * n) for b in range(B)]
+        acts = [torch.randint(0, 5, (n, A), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+        for e in envs:
+            e.reset()
+        for _ in range(10):          # let the fires develop: the stencil skips quiet groups
+            for e, a in zip(envs, acts):
+                e.step(a)
+        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], max(4, args.reps // 4))
+        report(f"wildfire_kernel {size}x{size} A={A}", n, us, bpe, batches=B)
+        for e in envs:
+            e.close()
+
+
+def bench_generic(args):
+    g = {k: golden("generic_12x12_a5", k) for k in ("init_obs", "init_pos")}
+    n, A, S = 65536, 5, 12
+    cells = S * S
+    bpe = A + 2 * (2 * cells + 2 * A + 16) + A * cells * 6 + 8 * A + 2
+    B = 4
+    envs = []
+    for b in range(B):
+        e = mg.make_generic_vec(n, S, num_agents=A, max_steps=60, seed=b, env_id_base=b * n)
+        idx = np.arange(n) % g["init_obs"].shape[0]
+        e.set_layout(g["init_obs"][idx, 0], g["init_pos"][idx])
+        e.reset()
+        envs.append(e)
+    acts = [torch.randint(0, 4, (n, A), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    report("generic_kernel 12x12 A=5 encode_dim 6 obs per agent", n, us, bpe, batches=B)
+    for e in envs:
+        e.close()
+
+
+def bench_collect_streams(args):
+    """Collect step: the 16 independent env batches forked over 1/2/4 streams inside the graph."""
+    n, B = 65536, 16
+    envs = [mg.make_vec("multigrid-collect-respawn-clustered-v0", n, seed=0, env_id_base=b * n) for b in range(B)]
+    acts = [torch.randint(0, 4, (n, 2), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+    for e in envs:
+        e.reset()
+    for S in (1, 2, 4, 8):
+        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps * 4, streams=S)
+        report(f"collect_step_kernel streams={S}", n, us, 592, batches=B)
+    for e in envs:
+        e.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="ctf,maze,view,wildfire,generic,collect_streams")
+    ap.add_argument("--reps", type=int, default=40)
+    args = ap.parse_args()
+    for w in args.which.split(","):
+        globals()["bench_" + w](args)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
