@@ -38,55 +38,52 @@ __device__ __forceinline__ int ag_x(uint32_t w) { return (int)(w & 255u); }
 __device__ __forceinline__ int ag_y(uint32_t w) { return (int)((w >> 8) & 255u); }
 
 // CtfActions / MazeActions: 0 stay, 1 left (0,-1), 2 down (-1,0), 3 right (0,+1), 4 up (+1,0)  (agent.py:54-67)
-__device__ __forceinline__ void action_delta(int a, int& dx, int& dy) {
-  dx = (a == 4) - (a == 2);
-  dy = (a == 3) - (a == 1);
+__device__ __forceinline__ void action_delta(int a, int& dx, int& dy) {  // two-bit lookup tables holding delta + 1, a in [0, 4]
+  dx = (int)((0x245u >> (2 * a)) & 3u) - 1;
+  dy = (int)((0x191u >> (2 * a)) & 3u) - 1;
 }
 // DIR_TO_VEC (constants.py:65-74) for the four unit moves; Agent.move leaves dir alone when no vector matches (agent.py:176-183)
-__device__ __forceinline__ int dir_of_action(int a, int old) {
-  return a == 4 ? 0 : (a == 3 ? 1 : (a == 2 ? 2 : (a == 1 ? 3 : old)));
-}
+__device__ __forceinline__ int dir_of_action(int a, int old) { return a == 0 ? old : ((4 - a) & 3); }
 
 template <int MODE>
 __device__ __forceinline__ int below(Rng<MODE>& r, int n) { return (int)__umulhi(r.u32(), (uint32_t)n); }
 
-// our Philox-mode stand-in for np_random.choice(len, k, replace=False)
-template <int MODE>
-__device__ __forceinline__ void sample_distinct(Rng<MODE>& r, int len, int k, int* out) {
-  for (int i = 0; i < k; ++i) {
-    for (;;) {
-      const int v = below(r, len);
-      bool dup = false;
-      for (int j = 0; j < i; ++j) dup |= out[j] == v;
-      if (!dup) { out[i] = v; break; }
-    }
-  }
-}
-
-// `ag` = this env's column of the transposed agent words: agent i at ag[i * kMapE]
+// `ag` = this env's column of the transposed agent words: agent i at ag[i * kMapE].  Cell lists hold packed x | y << 8.
 template <int FAMILY, int MODE>
-__device__ __noinline__ void reset_one(const MapParams& p, long long e, uint32_t* ag, int4& h, Rng<MODE>& r) {
-  const int S = p.S;
+__device__ __forceinline__ void reset_one(const MapParams& p, long long e, uint32_t* ag, Rng<MODE>& r) {
   if (FAMILY == MG_FAMILY_MAZE) {  // maze.py:202-205: agent on a random background cell, dir 3
     const int idx = MODE == 0 ? p.start_index[e] : below(r, p.n_background);
-    const int cell = p.background[idx];
-    ag[0] = ag_pack(cell / S, cell % S, 3, 0);
-  } else {  // ctf.py:1033-1048
-    int bp[MG_MAX_MAP_AGENTS], rp[MG_MAX_MAP_AGENTS];
-    if (MODE == 0) {
-      for (int i = 0; i < p.nb; ++i) bp[i] = p.blue_place[e * p.nb + i];
-      for (int i = 0; i < p.nr; ++i) rp[i] = p.red_place[e * p.nr + i];
-    } else {
-      sample_distinct(r, p.len_blue, p.nb, bp);
-      sample_distinct(r, p.len_red, p.nr, rp);
-    }
-    for (int i = 0; i < p.n; ++i) {
-      const int cell = i < p.nb ? p.blue_terr[bp[i]] : p.red_terr[rp[i - p.nb]];
-      // flags 0: a fresh env instance (the reference never clears terminated/collided on reset)
-      ag[i * kMapE] = ag_pack(cell / S, cell % S, 3, 0);
+    ag[0] = (uint32_t)p.background[idx] | (3u << 16);
+  } else {  // ctf.py:1033-1048; flags 0: a fresh env instance (the reference never clears terminated/collided on reset)
+    for (int team = 0; team < 2; ++team) {
+      const int k = team ? p.nr : p.nb, len = team ? p.len_red : p.len_blue, base = team ? p.nb : 0;
+      const uint16_t* terr = team ? p.red_terr : p.blue_terr;
+      const int32_t* place = team ? p.red_place : p.blue_place;
+      unsigned long long lo = 0, hi = 0;   // np_random.choice(len, k, replace=False) stand-in: rejection over a bitmap of <= 128 entries
+      for (int i = 0; i < k; ++i) {
+        int v;
+        if (MODE == 0) v = place[e * k + i];
+        else if (len <= 128) {
+          for (;;) {
+            v = below(r, len);
+            const unsigned long long bit = 1ull << (v & 63);
+            if (v < 64) { if (lo & bit) continue; lo |= bit; }
+            else { if (hi & bit) continue; hi |= bit; }
+            break;
+          }
+        } else {  // large territories: compare with the agents already placed
+          for (;;) {
+            v = below(r, len);
+            const uint32_t cand = terr[v];
+            bool dup = false;
+            for (int j = 0; j < i; ++j) dup |= (ag[(base + j) * kMapE] & 0xFFFFu) == cand;
+            if (!dup) break;
+          }
+        }
+        ag[(base + i) * kMapE] = (uint32_t)terr[v] | (3u << 16);
+      }
     }
   }
-  h.x = 0; h.w += 1;  // step_count = 0 (multigrid.py:141); episode counter
 }
 
 // MazeSingleAgentEnv.step on the env's single agent word
@@ -114,41 +111,41 @@ __device__ __forceinline__ void maze_step_one(const MapParams& p, int a, uint32_
 }
 
 // CtFMvNEnv.step / Ctf1v1Env.step for ONE env.  `terr` = the map in observation order (s_period), `ag` as in reset_one.
-template <int MODE>
+template <int MODE, typename NIB>
 __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, const int8_t* blue_act, const uint8_t* terr,
                                              uint32_t* ag, int4& h, Rng<MODE>& r, double& rew, bool& term, bool& trunc,
                                              int& err) {
   const int S = p.S, nb = p.nb, nr = p.nr, n = p.n;
   h.x += 1;  // ctf.py:1295
   // actions and order, one nibble per agent (n <= 16); action nibble 15 = outside the action set
-  unsigned long long acts = 0, order = 0;
+  NIB acts = 0, order = 0;   // NIB = uint32_t when n <= 8, else 64 bits
   for (int i = 0; i < nb; ++i) {
     const int a = blue_act[i];
     if (a < 0 || a > 4) err |= MG_ERR_BAD_ACTION;  // reference: ValueError (ctf.py:1200-1201)
-    acts |= (unsigned long long)((a < 0 || a > 4) ? 15 : a) << (4 * i);
+    acts |= (NIB)((a < 0 || a > 4) ? 15 : a) << (4 * i);
   }
   for (int k = 0; k < nr; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301)
     const int a = MODE == 0 ? p.red_actions[e * nr + k] : below(r, 5);
     if (a < 0 || a > 4) err |= MG_ERR_BAD_ACTION;
-    acts |= (unsigned long long)((a < 0 || a > 4) ? 15 : a) << (4 * (nb + k));
+    acts |= (NIB)((a < 0 || a > 4) ? 15 : a) << (4 * (nb + k));
   }
   if (p.variant_1v1) {  // Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510)
-    order = 0x10ull;
+    order = (NIB)0x10;
   } else if (MODE == 0) {
-    for (int i = 0; i < n; ++i) order |= (unsigned long long)(p.order[e * n + i] & 15) << (4 * i);
+    for (int i = 0; i < n; ++i) order |= (NIB)(p.order[e * n + i] & 15) << (4 * i);
   } else {  // np_random.shuffle stand-in: Fisher-Yates
-    order = 0xFEDCBA9876543210ull;
+    order = (NIB)0xFEDCBA9876543210ull;
     for (int i = n - 1; i > 0; --i) {
       const int j = below(r, i + 1);
-      const unsigned long long x = ((order >> (4 * i)) ^ (order >> (4 * j))) & 15ull;
+      const NIB x = ((order >> (4 * i)) ^ (order >> (4 * j))) & (NIB)15;
       order ^= (x << (4 * i)) | (x << (4 * j));
     }
   }
   for (int k = 0; k < n; ++k) {  // _move_agents :1240-1251
-    const int i = (int)((order >> (4 * k)) & 15ull);
+    const int i = (int)((order >> (4 * k)) & (NIB)15);
     const uint32_t w = ag[i * kMapE];
     if (w & FL_DEAD) continue;  // "Defeated agent doesn't move, sadly."
-    const int a = (int)((acts >> (4 * i)) & 15ull);
+    const int a = (int)((acts >> (4 * i)) & (NIB)15);
     if (a == 15) continue;
     int dx, dy;
     action_delta(a, dx, dy);
@@ -169,8 +166,7 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
       if (w & FL_COLLIDED) { if (i < nb) rew -= p.obstacle_penalty; ag[i * kMapE] = w | FL_DEAD; }
     }
   }
-  const uint32_t red_flag = (uint32_t)(p.red_flag / S) | ((uint32_t)(p.red_flag % S) << 8);
-  const uint32_t blue_flag = (uint32_t)(p.blue_flag / S) | ((uint32_t)(p.blue_flag % S) << 8);
+  const uint32_t red_flag = (uint32_t)p.red_flag, blue_flag = (uint32_t)p.blue_flag;
   for (int i = 0; i < nb; ++i) if (((ag[i * kMapE] ^ red_flag) & 0xFFFFu) == 0) { rew += p.flag_reward; term = true; }   // :1335-1344
   for (int i = nb; i < n; ++i) if (((ag[i * kMapE] ^ blue_flag) & 0xFFFFu) == 0) { rew -= p.flag_reward; term = true; }  // :1347-1356
   int nbattle = 0;
@@ -260,7 +256,7 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     ag[0] = *reinterpret_cast<const uint32_t*>(row);
   }
   int4 h = p.hdr[e];
-  bool done = false;
+  bool done = false, want_reset = false;
   int err = 0;
   Rng<MODE> r;
   r.open_trace(nullptr, 0);
@@ -268,38 +264,38 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
   if (tid < n_here) {
     if (MODE == 1) r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
     if (p.op == 0) {
-      if (!p.reset_mask || p.reset_mask[e]) { Rng<MODE> rr = r; reset_one<FAMILY, MODE>(p, e, ag, h, rr); r.ctr = rr.ctr; }
+      want_reset = !p.reset_mask || p.reset_mask[e];
     } else {
       double rew; bool term, trunc;
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
-      else ctf_step_one<MODE>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
+      else if (n <= 8) ctf_step_one<MODE, uint32_t>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
+      else ctf_step_one<MODE, unsigned long long>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       p.rewards[e] = rew; p.terminated[e] = term; p.truncated[e] = trunc;
-      done = p.autoreset && (term || trunc);
+      want_reset = done = p.autoreset && (term || trunc);  // same-step autoreset
     }
-    // same-step autoreset; when the caller wants final_observation the reset waits until it has been drawn
-    // (the generator is handed to the non-inlined reset as a COPY so that the step's own draws stay in registers)
-    if (done && !p.final_obs) { Rng<MODE> rr = r; reset_one<FAMILY, MODE>(p, e, ag, h, rr); r.ctr = rr.ctr; }
   }
-  s_done[tid] = done;
-  const int any_final = p.final_obs ? __syncthreads_or(done) : 0;
   mbar_wait(&bar, 0);
 
-  // ---- rare path: terminal observations of finished envs, then their reset
-  if (any_final) {
-    for (int j = 0; j < n_here; ++j) {
-      if (!s_done[j]) continue;
-      for (int i = tid; i < cells; i += kMapE) put_obs(p, p.final_obs, (e0 + j) * cells + i, s_period[i]);
-    }
-    __syncthreads();
-    if (done) {
-      for (int i = 0; i < n; ++i) {
-        const uint32_t w = ag[i * kMapE];
-        put_obs(p, p.final_obs, e * cells + obs_index<FAMILY>(p, w), agent_code<FAMILY>(p, i, w));
+  // ---- terminal observations of the finished envs are drawn before their reset (only when the caller asked for them)
+  if (p.final_obs) {
+    s_done[tid] = done;
+    if (__syncthreads_or(done)) {
+      for (int j = 0; j < n_here; ++j) {
+        if (!s_done[j]) continue;
+        for (int i = tid; i < cells; i += kMapE) put_obs(p, p.final_obs, (e0 + j) * cells + i, s_period[i]);
       }
-      Rng<MODE> rr = r;
-      reset_one<FAMILY, MODE>(p, e, ag, h, rr);
-      r.ctr = rr.ctr;
+      __syncthreads();
+      if (done)
+        for (int i = 0; i < n; ++i) {
+          const uint32_t w = ag[i * kMapE];
+          put_obs(p, p.final_obs, e * cells + obs_index<FAMILY>(p, w), agent_code<FAMILY>(p, i, w));
+        }
     }
+  }
+  // ---- reset(mask) / autoreset: ONE call site (a random CtF episode lasts ~20 steps, so most warps take it every step)
+  if (want_reset) {
+    reset_one<FAMILY, MODE>(p, e, ag, r);
+    h.x = 0; h.w += 1;  // step_count = 0 (multigrid.py:141); episode counter
   }
 
   // ---- state write-back (rows of padded envs of the last tile are written too: the planes are padded)
@@ -328,11 +324,11 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
   if (!p.obs) return;
   const long long slab = (long long)n_here * cells;  // elements in this tile's obs slab
   if (p.obs_staged) {  // u8, small map: assemble the tile in shared memory, one TMA bulk store
-    const int L16 = p.L / 16, chunks = kMapE * cells / 16;
+    const int L16 = p.L16, chunks = kMapE * cells / 16;
     uint4* dst = reinterpret_cast<uint4*>(s_obs);
     const uint4* src = reinterpret_cast<const uint4*>(s_period);
-    int m = tid % L16;
-    const int step = kMapE % L16;
+    int m = tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
+    const int step = p.tile_mod_L16;
     for (int c = tid; c < chunks; c += kMapE) {
       dst[c] = src[m];
       m += step; if (m >= L16) m -= L16;
@@ -353,12 +349,12 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     return;
   }
   if (p.obs_dtype == MG_OBS_U8) {
-    const int L16 = p.L / 16;
+    const int L16 = p.L16;
     const long long chunks = slab / 16;
     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.obs) + e0 * cells);  // e0*cells is a multiple of L
     const uint4* src = reinterpret_cast<const uint4*>(s_period);
-    int m = tid % L16;
-    const int step = kMapE % L16;
+    int m = tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
+    const int step = p.tile_mod_L16;
     for (long long c = tid; c < chunks; c += kMapE) {
       dst[c] = src[m];
       m += step; if (m >= L16) m -= L16;

@@ -9,14 +9,17 @@ namespace mg {
 struct MapParams {
   int S, cells, nb, nr, n, family, max_steps, autoreset, obs_dtype, variant_1v1;
   double flag_reward, obstacle_penalty, step_penalty, battle_reward, battle_range, randomness;
-  int n_background, len_blue, len_red, blue_flag, red_flag;
+  int n_background, len_blue, len_red;
+  int blue_flag, red_flag;     // packed x | y << 8
+  int L16, tile_mod_L16;       // L / 16, (envs per tile) mod L16
+  unsigned L16_magic;          // floor(2^32 / L16) + 1: t mod L16 = t - umulhi(t, magic) * L16 for t < 2^16
   long long N;
   unsigned long long env_id_base, seed;
   // handle-owned tables
   const uint8_t* field_map;    // [cells] x*S+y
   const uint8_t* obs_period;   // [L] obs base repeated to a multiple of 16 bytes (CtF: transposed map)
   int L;                       // lcm(cells, 16)
-  const uint16_t* background;  // Maze: cells with code background, np.where order
+  const uint16_t* background;  // Maze: cells with code background, np.where order; every list entry is packed x | y << 8
   const uint16_t* blue_terr;   // CtF: blue territory cells + blue flag (ctf.py:765-769)
   const uint16_t* red_terr;
   // battle tests restated in integers (bit-exact, computed on the host with the same double arithmetic):

@@ -280,7 +280,8 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   if (cfg->variant_1v1 && (maze || nb != 1 || nr != 1)) return fail(nullptr, "mg_create_map: variant_1v1 needs the CtF family with one blue and one red agent");
   // cell lists in np.where order (row-major over field_map[x][y])
   std::string bg, bt, rt;  // uint16 lists packed in strings
-  auto push = [](std::string& v, int c) { uint16_t u = (uint16_t)c; v.append(reinterpret_cast<const char*>(&u), 2); };
+  // entries are packed cells x | y << 8 (cell index i = x * S + y), so the kernels never divide by S
+  auto push = [S](std::string& v, int c) { uint16_t u = (uint16_t)((c / S) | ((c % S) << 8)); v.append(reinterpret_cast<const char*>(&u), 2); };
   int blue_flag = -1, red_flag = -1;
   for (int i = 0; i < cells; ++i) {
     const int c = cfg->field_map[i];
@@ -381,7 +382,8 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   p.flag_reward = cfg->flag_reward; p.obstacle_penalty = cfg->obstacle_penalty; p.step_penalty = cfg->step_penalty;
   p.battle_reward = cfg->battle_reward; p.battle_range = cfg->battle_range; p.randomness = cfg->randomness;
   p.n_background = (int)bg.size() / 2; p.len_blue = (int)bt.size() / 2; p.len_red = (int)rt.size() / 2;
-  p.blue_flag = blue_flag; p.red_flag = red_flag;
+  p.blue_flag = maze ? 0 : (blue_flag / S) | ((blue_flag % S) << 8); p.red_flag = maze ? 0 : (red_flag / S) | ((red_flag % S) << 8);
+  p.L16 = (int)(L / 16); p.L16_magic = (unsigned)(4294967296ull / (L / 16)) + 1u; p.tile_mod_L16 = mg::map_tile_envs() % (int)(L / 16);
   // integer restatements of the battle tests (ctf.py:1368, 1392-1407), formed with the reference's double arithmetic
   p.d2_max = -1;
   for (int d2 = 0; d2 <= 2 * 255 * 255 && std::sqrt((double)d2) <= cfg->battle_range; ++d2) p.d2_max = d2;
