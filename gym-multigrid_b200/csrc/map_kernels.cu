@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     const int L16 = p.L16, chunks = kMapE * cells / 16;
     uint4* dst = reinterpret_cast<uint4*>(s_obs);
     const uint4* src = reinterpret_cast<const uint4*>(s_period);
-    int m = tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
+    int m = L16 == 1 ? 0 : tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
     const int step = p.tile_mod_L16;
     for (int c = tid; c < chunks; c += kMapE) {
       dst[c] = src[m];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     const long long chunks = slab / 16;
     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.obs) + e0 * cells);  // e0*cells is a multiple of L
     const uint4* src = reinterpret_cast<const uint4*>(s_period);
-    int m = tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
+    int m = L16 == 1 ? 0 : tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
     const int step = p.tile_mod_L16;
     for (long long c = tid; c < chunks; c += kMapE) {
       dst[c] = src[m];

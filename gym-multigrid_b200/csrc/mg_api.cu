@@ -40,8 +40,8 @@ size_t view_smem_bytes(const ViewParams& p);
 int view_max();
 int view_tile_envs();
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st);
-cudaError_t configure_wildfire_kernel(int cells);
-size_t wildfire_smem_bytes(int cells);
+cudaError_t configure_wildfire_kernel(int cells, int H);
+size_t wildfire_smem_bytes(int cells, int H);
 cudaError_t launch_generic(const GenericParams& p, cudaStream_t st);
 int generic_tile_envs();
 }  // namespace mg
@@ -465,8 +465,8 @@ extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create_wildfire: kernels are built for sm_100a only");
-  if (mg::wildfire_smem_bytes(cells) > (size_t)prop.sharedMemPerBlockOptin) return fail(nullptr, "mg_create_wildfire: grid too large for one CTA's shared memory");
-  if ((ce = mg::configure_wildfire_kernel(cells)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
+  if (mg::wildfire_smem_bytes(cells, H) > (size_t)prop.sharedMemPerBlockOptin) return fail(nullptr, "mg_create_wildfire: grid too large for one CTA's shared memory");
+  if ((ce = mg::configure_wildfire_kernel(cells, H)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_wildfire: out of host memory");
   env->family = MG_FAMILY_WILDFIRE;
@@ -493,6 +493,7 @@ extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_
   p.W = W; p.H = H; p.cells = cells; p.A = A; p.num_fires = cfg->num_fires; p.max_steps = cfg->max_steps; p.autoreset = cfg->autoreset != 0;
   for (int k = 0; k < 5; ++k) p.ignite_threshold[k] = cfg->ignite_threshold[k];
   p.burnout_threshold = cfg->burnout_threshold;
+  p.rw_magic = (H >= 4) ? (uint32_t)(4294967296ull / (unsigned)(H / 4)) + 1u : 0u;
   for (int i = 0; i < A; ++i) p.agent_colour[i] = (uint8_t)cfg->agent_colour[i];
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   *out = env;

@@ -175,8 +175,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // ------------------------------------------------------------------------------- encode
 // Grid.encode, encode_dim 3 (grid.py:223-252 + object.py:58-74 + agent.py:119-126):
 // 16 packed cells (one uint4) -> 48 obs bytes (three uint4), byte order (type, colour, state).
+// four cells given as separate type / colour / state byte planes -> 12 interleaved obs bytes
+__device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2);
 __device__ __forceinline__ void expand4(uint32_t w, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
-  const uint32_t t = w & 0x03030303u, c = (w >> 2) & 0x0F0F0F0Fu, s = (w >> 6) & 0x03030303u;
+  interleave3(w & 0x03030303u, (w >> 2) & 0x0F0F0F0Fu, (w >> 6) & 0x03030303u, o0, o1, o2);
+}
+__device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
   // out bytes: t0 c0 s0 t1 | c1 s1 t2 c2 | s2 t3 c3 s3
   const uint32_t tc = __byte_perm(t, c, 0x5140);   // t0 c0 t1 c1  (bytes: [t0, c0, t1, c1])
   o0 = __byte_perm(tc, s, 0x2410);                 // t0 c0 s0 t1

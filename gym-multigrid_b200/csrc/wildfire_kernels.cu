@@ -30,14 +30,14 @@ struct WfSmem {
 
 // all threads: terrain + agents -> packed cells (in `packed`) -> 3-byte encoding in s.obs
 __device__ __forceinline__ void wf_encode(const WildfireParams& p, const uint8_t* terrain, uint8_t* packed, uint8_t* obs,
-                                          const int* s_ax, const int* s_ay, const int* s_adir, int tid) {
-  for (int i = tid; i < p.cells; i += kWfThreads) packed[i] = wf_packed(terrain[i]);
+                                          const int* s_ax, const int* s_ay, const int* s_adir, int tid, int nthreads = kWfThreads) {
+  for (int i = tid; i < p.cells; i += nthreads) packed[i] = wf_packed(terrain[i]);
   __syncthreads();
   if (tid < p.A) packed[s_ax[tid] * p.H + s_ay[tid]] = (uint8_t)(cell(3, p.agent_colour[tid], 0) | (s_adir[tid] << 6));
   __syncthreads();
   const uint4* in = reinterpret_cast<const uint4*>(packed);
   uint4* out = reinterpret_cast<uint4*>(obs);
-  for (int g = tid; g < p.cells / 16; g += kWfThreads) {
+  for (int g = tid; g < p.cells / 16; g += nthreads) {
     uint4 a, b, c;
     expand16(in[g], a, b, c);
     out[3 * g] = a; out[3 * g + 1] = b; out[3 * g + 2] = c;
@@ -206,22 +206,214 @@ __global__ void __launch_bounds__(kWfThreads) wildfire_kernel(const __grid_const
   if (tid == 0) tma_wait_read_all();
 }
 
-size_t wildfire_smem_bytes(int cells) { return (size_t)cells * 5 + 64; }
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path (H % 4 == 0): the same step with the fire dynamics and the encoding done four cells per 32-bit word (SWAR).
+// States are 0 / 1 / 2, so "burning" is bit 0 of each byte: the four neighbour flags of a word are the words one row
+// up / down and the word itself shifted by one byte with the carry byte of the adjacent word (zero at the row ends; zero
+// guard rows above and below the staged terrain stand in for the x bounds tests).  A Philox block is computed only for
+// words that hold a burning cell or a healthy cell with a burning neighbour - the fire front - which is what makes the
+// step memory-bound instead of RNG-bound.  The agent order is drawn by warp 0 in parallel (lane d computes the Philox
+// block of draw d; the Fisher-Yates swaps are register shuffles), so the serial section per env is the ordered move loop
+// only.  Same Philox counters and word assignment as the generic kernel and the oracle: results are bit-identical.
+template <int T>
+__global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant__ WildfireParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_ax[MG_MAX_WILDFIRE_AGENTS], s_ay[MG_MAX_WILDFIRE_AGENTS], s_adir[MG_MAX_WILDFIRE_AGENTS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, A = p.A, W = p.W, H = p.H, cells = p.cells;
+  const int rw = H >> 2, nwords = cells >> 2, guard = (H + 15) & ~15;
+  const long long e = blockIdx.x;
+  uint8_t* s_told = smem_raw + guard;                                      // guard | [cells] | guard
+  uint8_t* s_tnew = smem_raw + 2 * (size_t)guard + cells;                  // [cells]
+  uint8_t* s_obs = s_tnew + cells;                                         // [3 * cells]
+  uint32_t* t32 = reinterpret_cast<uint32_t*>(s_told);
+  uint32_t* n32 = reinterpret_cast<uint32_t*>(s_tnew);
+  uint8_t* g_terrain = p.terrain + e * cells;
 
-cudaError_t configure_wildfire_kernel(int cells) {
-  return cudaFuncSetAttribute((const void*)wildfire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wildfire_smem_bytes(cells));
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  pdl_launch_dependents();
+  for (int i = tid; i < guard / 4; i += T) { reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u; t32[nwords + i] = 0u; }
+  __syncthreads();
+  pdl_wait();
+  if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)cells); tma_load_1d(s_told, g_terrain, (uint32_t)cells, &bar); }
+  int4 h = p.hdr[e];                        // every thread: one broadcast load
+  const uint32_t ctr0 = (uint32_t)h.z;
+  const unsigned long long env_id = p.env_id_base + (unsigned long long)e;
+  const uint32_t id0 = (uint32_t)env_id, id1 = (uint32_t)(env_id >> 32), k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  if (tid < A) {
+    const uchar4 a = reinterpret_cast<const uchar4*>(p.agents)[e * A + tid];
+    s_ax[tid] = a.x; s_ay[tid] = a.y; s_adir[tid] = a.z;
+  }
+  const bool do_reset = p.op == 0 && (!p.reset_mask || p.reset_mask[e]);
+  bool need_reset = do_reset;
+  uint32_t order_blocks = 0;                // Philox blocks the agent order consumed
+  mbar_wait(&bar, 0);
+  __syncthreads();
+
+  if (p.op == 1) {
+    h.x += 1; h.y += 1;  // step_count, tick
+    // ---- 1/2. ordered agent moves: warp 0, lane = agent
+    order_blocks = (!p.order && A > 1) ? (uint32_t)(A - 1 + 3) / 4u : 0u;
+    if (warp == 0) {
+      int ord = lane;  // value at position `lane` of the order
+      if (p.order) {
+        if (lane < A) ord = p.order[e * A + lane];
+      } else if (A > 1) {  // Fisher-Yates: draw d (for i = A-1-d) is word d % 4 of block ctr0 + d / 4
+        uint32_t u[4];
+        philox4x32_10(id0, id1, ctr0 + (uint32_t)(lane >> 2), 0u, k0, k1, u);
+        const uint32_t word = (lane & 2) ? ((lane & 1) ? u[3] : u[2]) : ((lane & 1) ? u[1] : u[0]);
+        const int jl = (int)__umulhi(word, (uint32_t)(A - lane));   // below(i + 1), i = A - 1 - lane
+        for (int d = 0; d < A - 1; ++d) {
+          const int i = A - 1 - d, j = __shfl_sync(0xffffffffu, jl, d);
+          const int vi = __shfl_sync(0xffffffffu, ord, i), vj = __shfl_sync(0xffffffffu, ord, j);
+          if (lane == i) ord = vj; else if (lane == j) ord = vi;
+        }
+      }
+      int x = lane < A ? s_ax[lane] : -1, y = lane < A ? s_ay[lane] : -1, dir = lane < A ? s_adir[lane] : 0;
+      const int a = lane < A ? p.actions[e * A + lane] : 0;
+      double rew = 0.0;
+      for (int k = 0; k < A; ++k) {
+        const int i = __shfl_sync(0xffffffffu, ord, k);  // the acting agent; warp-uniform
+        int dx = 0, dy = 0;
+        if (lane == i && a >= 1 && a <= 4) { dx = (a == 4) - (a == 2); dy = (a == 3) - (a == 1); }
+        const int nx = __shfl_sync(0xffffffffu, x + dx, i), ny = __shfl_sync(0xffffffffu, y + dy, i);
+        const unsigned occupied = __ballot_sync(0xffffffffu, lane != i && lane < A && x == nx && y == ny);
+        if (lane == i) {
+          if ((dx | dy) && nx >= 0 && ny >= 0 && nx < W && ny < H && !occupied) {
+            dir = dx == 1 ? 0 : (dy == 1 ? 1 : (dx == -1 ? 2 : 3));  // DIR_TO_VEC (constants.py:65-74)
+            x = nx; y = ny;
+          }
+          if (s_told[x * H + y] == WF_BURNING) { s_told[x * H + y] = WF_BURNT; rew += 1.0; }  // extinguish
+        }
+        __syncwarp();
+      }
+      if (lane < A) { s_ax[lane] = x; s_ay[lane] = y; s_adir[lane] = dir; p.rewards[e * A + lane] = rew; }
+    }
+    __syncthreads();
+
+    // ---- 3. fire dynamics, four cells per word
+    const uint32_t tick = (uint32_t)h.y;
+    bool any_burning = false;
+    for (int j = tid; j < nwords; j += T) {
+      const int wy = rw == 1 ? 0 : j - (int)__umulhi((uint32_t)j, p.rw_magic) * rw;   // word index inside its row
+      const uint32_t w = t32[j];
+      const uint32_t b = w & 0x01010101u;
+      const uint32_t up = t32[j - rw] & 0x01010101u, dn = t32[j + rw] & 0x01010101u;
+      const uint32_t pv = wy > 0 ? (t32[j - 1] & 0x01010101u) : 0u, nx = wy < rw - 1 ? (t32[j + 1] & 0x01010101u) : 0u;
+      const uint32_t k4 = up + dn + ((b << 8) | (pv >> 24)) + ((b >> 8) | (nx << 24));   // burning neighbours per byte (<= 4)
+      const uint32_t healthy = ~(w | (w >> 1)) & 0x01010101u;
+      const uint32_t kh = k4 & (healthy * 7u);
+      uint32_t nw = w;
+      if (kh | b) {
+        uint32_t u[4];
+        philox4x32_10(id0, id1, tick, 1u + (uint32_t)j, k0, k1, u);
+        nw = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t s = (w >> (8 * i)) & 3u, k = (kh >> (8 * i)) & 7u;
+          uint32_t ns = s;
+          if (s == WF_BURNING) ns = u[i] < p.burnout_threshold ? WF_BURNT : WF_BURNING;
+          else if (k) ns = u[i] < p.ignite_threshold[k] ? WF_BURNING : WF_HEALTHY;
+          nw |= ns << (8 * i);
+        }
+      }
+      n32[j] = nw;
+      any_burning |= (nw & 0x01010101u) != 0;
+    }
+    // ---- 4. termination, same-step autoreset
+    const bool term = !__syncthreads_or(any_burning), trunc = h.x >= p.max_steps;
+    if (tid == 0) { p.terminated[e] = term; p.truncated[e] = trunc; }
+    need_reset = p.autoreset && (term || trunc);
+    if (need_reset && p.final_obs) {
+      wf_encode(p, s_tnew, s_told, s_obs, s_ax, s_ay, s_adir, tid, T);
+      __syncthreads();
+      uint4* dst = reinterpret_cast<uint4*>(p.final_obs + e * 3 * cells);
+      for (int i = tid; i < 3 * cells / 16; i += T) dst[i] = reinterpret_cast<const uint4*>(s_obs)[i];
+      __syncthreads();
+    }
+  } else if (!do_reset) {
+    for (int j = tid; j < nwords; j += T) n32[j] = t32[j];
+  }
+  // ---- reset(mask) / autoreset (rare): all healthy, then thread 0 places fires and agents from the env's Philox stream
+  uint32_t ctr_end = ctr0 + order_blocks;
+  if (need_reset) {
+    for (int j = tid; j < nwords; j += T) n32[j] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+      Rng<1> r;
+      r.open_philox(p.seed, env_id, ctr_end);
+      const int used = (A - 1) & 3;   // words of the last order block already consumed (0 = block boundary)
+      if (order_blocks && used) {     // the sequential stream continues inside that block
+        uint32_t u[4];
+        philox4x32_10(id0, id1, ctr_end - 1u, 0u, k0, k1, u);
+        r.have = 4 - used;
+        r.b0 = u[used]; r.b1 = used + 1 < 4 ? u[used + 1] : 0u; r.b2 = used + 2 < 4 ? u[used + 2] : 0u; r.b3 = 0u;
+      }
+      wf_reset_agents_fires(p, s_tnew, s_ax, s_ay, s_adir, r);
+      ctr_end = r.ctr;
+    }
+    h.x = 0; h.w += 1;
+  }
+  __syncthreads();
+
+  // ---- 5. observation (type byte = state; colour green / red / grey) + write-back
+  if (p.obs) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(s_obs);
+    for (int j = tid; j < nwords; j += T) {
+      const uint32_t w = n32[j];
+      const uint32_t burnt = (w >> 1) & 0x01010101u, healthy = ~(w | (w >> 1)) & 0x01010101u;
+      uint32_t o0, o1, o2;
+      interleave3(w, healthy * 3u + burnt * 7u, 0u, o0, o1, o2);
+      o32[3 * j] = o0; o32[3 * j + 1] = o1; o32[3 * j + 2] = o2;
+    }
+    __syncthreads();
+    if (tid < A) {
+      uint8_t* o = s_obs + 3 * (s_ax[tid] * H + s_ay[tid]);
+      o[0] = 3; o[1] = p.agent_colour[tid]; o[2] = (uint8_t)s_adir[tid];
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_1d(g_terrain, s_tnew, (uint32_t)cells);
+    if (p.obs) tma_store_1d(p.obs + e * 3 * cells, s_obs, (uint32_t)(3 * cells));
+    tma_commit();
+    h.z = (int)ctr_end;
+    p.hdr[e] = h;
+  }
+  if (tid < A) reinterpret_cast<uchar4*>(p.agents)[e * A + tid] = make_uchar4((uint8_t)s_ax[tid], (uint8_t)s_ay[tid], (uint8_t)s_adir[tid], 0);
+  if (tid == 0) tma_wait_read_all();
+}
+
+static bool wf_fast(int H) {
+  static const bool off = [] { const char* v = std::getenv("MG_WF_GENERIC"); return v && v[0] == '1'; }();
+  return !off && (H & 3) == 0;
+}
+static size_t wf_fast_smem(int cells, int H) { return (size_t)cells * 5 + 2 * (size_t)((H + 15) & ~15) + 16; }
+
+size_t wildfire_smem_bytes(int cells, int H) { return wf_fast(H) ? wf_fast_smem(cells, H) : (size_t)cells * 5 + 64; }
+
+cudaError_t configure_wildfire_kernel(int cells, int H) {
+  const int bytes = (int)wildfire_smem_bytes(cells, H);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute((const void*)wildfire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
+  const bool fast = wf_fast(p.H);
+  const int threads = fast ? (p.cells / 4 >= 512 ? 128 : 64) : kWfThreads;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)p.N); cfg.blockDim = dim3(kWfThreads);
-  cfg.dynamicSmemBytes = wildfire_smem_bytes(p.cells); cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)p.N); cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = wildfire_smem_bytes(p.cells, p.H); cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool pdl = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, wildfire_kernel, p);
+  if (!fast) return cudaLaunchKernelEx(&cfg, wildfire_kernel, p);
+  return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64>, p);
 }
 
 }  // namespace mg

@@ -13,10 +13,13 @@ def _np(t):
     return t.cpu().numpy()
 
 
-@pytest.mark.parametrize("size,A,fires,n", [(16, 5, 3, 300), (64, 16, 4, 96), (32, 32, 6, 128), (8, 1, 1, 257)])
+@pytest.mark.parametrize("size,A,fires,n", [(16, 5, 3, 300), (64, 16, 4, 96), (32, 32, 6, 128), (8, 1, 1, 257), (4, 2, 2, 65),
+                                            ((8, 10), 6, 3, 130), ((12, 20), 7, 5, 90), ((24, 6), 4, 2, 70)])
 def test_wildfire_matches_oracle(size, A, fires, n, cuda_device):
+    """Square grids and W x H grids; H % 4 == 0 takes the word-parallel kernel, other heights the generic one."""
     import gym_multigrid_b200 as mg
-    kw = dict(size=size, num_agents=A, num_fires=fires, alpha=0.2, beta=0.08, max_steps=40, seed=13, env_id_base=9)
+    kw = dict(num_agents=A, num_fires=fires, alpha=0.2, beta=0.08, max_steps=40, seed=13, env_id_base=9)
+    kw.update(dict(width=size[0], height=size[1]) if isinstance(size, tuple) else dict(size=size))
     env = mg.make_wildfire_vec(n, **kw)
     env.enable_final_observation()
     o = oc.WildfireOracle(n, **kw)
