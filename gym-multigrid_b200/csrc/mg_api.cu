@@ -494,6 +494,7 @@ extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_
   for (int k = 0; k < 5; ++k) p.ignite_threshold[k] = cfg->ignite_threshold[k];
   p.burnout_threshold = cfg->burnout_threshold;
   p.rw_magic = (H >= 4) ? (uint32_t)(4294967296ull / (unsigned)(H / 4)) + 1u : 0u;
+  p.rv_magic = (H % 16 == 0) ? (uint32_t)(4294967296ull / (unsigned)(H / 16)) + 1u : p.rw_magic;
   for (int i = 0; i < A; ++i) p.agent_colour[i] = (uint8_t)cfg->agent_colour[i];
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   *out = env;

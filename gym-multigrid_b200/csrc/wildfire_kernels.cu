@@ -215,11 +215,12 @@ __global__ void __launch_bounds__(kWfThreads) wildfire_kernel(const __grid_const
 // step memory-bound instead of RNG-bound.  The agent order is drawn by warp 0 in parallel (lane d computes the Philox
 // block of draw d; the Fisher-Yates swaps are register shuffles), so the serial section per env is the ordered move loop
 // only.  Same Philox counters and word assignment as the generic kernel and the oracle: results are bit-identical.
-template <int T>
+template <int T, int VEC>
 __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant__ WildfireParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_ax[MG_MAX_WILDFIRE_AGENTS], s_ay[MG_MAX_WILDFIRE_AGENTS], s_adir[MG_MAX_WILDFIRE_AGENTS];
+  __shared__ int s_count;   // length of the fire-front queue
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, A = p.A, W = p.W, H = p.H, cells = p.cells;
   const int rw = H >> 2, nwords = cells >> 2, guard = (H + 15) & ~15;
   const long long e = blockIdx.x;
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
   uint32_t* n32 = reinterpret_cast<uint32_t*>(s_tnew);
   uint8_t* g_terrain = p.terrain + e * cells;
 
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); s_count = 0; }
   pdl_launch_dependents();
   for (int i = tid; i < guard / 4; i += T) { reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u; t32[nwords + i] = 0u; }
   __syncthreads();
@@ -291,33 +292,66 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    // ---- 3. fire dynamics, four cells per word
+    // ---- 3. fire dynamics, four cells per word, VEC words per thread and iteration
+    //      pass 1: neighbour counts for every word; quiet words are copied, words on the fire front are queued
+    //      (word index + packed state / neighbour-count bytes) in the not-yet-used obs area
     const uint32_t tick = (uint32_t)h.y;
-    bool any_burning = false;
-    for (int j = tid; j < nwords; j += T) {
-      const int wy = rw == 1 ? 0 : j - (int)__umulhi((uint32_t)j, p.rw_magic) * rw;   // word index inside its row
-      const uint32_t w = t32[j];
-      const uint32_t b = w & 0x01010101u;
-      const uint32_t up = t32[j - rw] & 0x01010101u, dn = t32[j + rw] & 0x01010101u;
-      const uint32_t pv = wy > 0 ? (t32[j - 1] & 0x01010101u) : 0u, nx = wy < rw - 1 ? (t32[j + 1] & 0x01010101u) : 0u;
-      const uint32_t k4 = up + dn + ((b << 8) | (pv >> 24)) + ((b >> 8) | (nx << 24));   // burning neighbours per byte (<= 4)
-      const uint32_t healthy = ~(w | (w >> 1)) & 0x01010101u;
-      const uint32_t kh = k4 & (healthy * 7u);
-      uint32_t nw = w;
-      if (kh | b) {
-        uint32_t u[4];
-        philox4x32_10(id0, id1, tick, 1u + (uint32_t)j, k0, k1, u);
-        nw = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t s = (w >> (8 * i)) & 3u, k = (kh >> (8 * i)) & 7u;
-          uint32_t ns = s;
-          if (s == WF_BURNING) ns = u[i] < p.burnout_threshold ? WF_BURNT : WF_BURNING;
-          else if (k) ns = u[i] < p.ignite_threshold[k] ? WF_BURNING : WF_HEALTHY;
-          nw |= ns << (8 * i);
-        }
+    uint2* s_list = reinterpret_cast<uint2*>(s_obs);
+    const int rv = rw / VEC;   // vectors per row (VEC == 4 only when H % 16 == 0)
+    for (int q = tid; q < nwords / VEC; q += T) {
+      const int j0 = q * VEC;
+      const int vy = rv == 1 ? 0 : q - (int)__umulhi((uint32_t)q, p.rv_magic) * rv;   // vector index inside its row
+      uint32_t w[VEC], up[VEC], dn[VEC];
+      if (VEC == 4) {
+        const uint4 a = reinterpret_cast<const uint4*>(t32)[q], u4 = *reinterpret_cast<const uint4*>(t32 + j0 - rw),
+                    d4 = *reinterpret_cast<const uint4*>(t32 + j0 + rw);
+        w[0] = a.x; w[VEC > 1 ? 1 : 0] = a.y; w[VEC > 2 ? 2 : 0] = a.z; w[VEC > 3 ? 3 : 0] = a.w;
+        up[0] = u4.x; up[VEC > 1 ? 1 : 0] = u4.y; up[VEC > 2 ? 2 : 0] = u4.z; up[VEC > 3 ? 3 : 0] = u4.w;
+        dn[0] = d4.x; dn[VEC > 1 ? 1 : 0] = d4.y; dn[VEC > 2 ? 2 : 0] = d4.z; dn[VEC > 3 ? 3 : 0] = d4.w;
+      } else {
+        w[0] = t32[j0]; up[0] = t32[j0 - rw]; dn[0] = t32[j0 + rw];
       }
-      n32[j] = nw;
+      const uint32_t pv = vy > 0 ? (t32[j0 - 1] & 0x01010101u) : 0u, nx = vy < rv - 1 ? (t32[j0 + VEC] & 0x01010101u) : 0u;
+      uint32_t b[VEC], code[VEC];
+      int n_act = 0;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) b[i] = w[i] & 0x01010101u;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const uint32_t left = i > 0 ? b[i > 0 ? i - 1 : 0] : pv, right = i < VEC - 1 ? b[i + 1 < VEC ? i + 1 : 0] : nx;
+        const uint32_t k4 = (up[i] & 0x01010101u) + (dn[i] & 0x01010101u) + ((b[i] << 8) | (left >> 24)) + ((b[i] >> 8) | (right << 24));
+        const uint32_t healthy = ~(w[i] | (w[i] >> 1)) & 0x01010101u;
+        const uint32_t kh = k4 & (healthy * 7u);           // burning 4-neighbours of the healthy cells (<= 4 per byte)
+        code[i] = (kh | b[i]) ? (w[i] | (kh << 2)) : 0u;   // != 0 <=> some cell of the word can change
+        n_act += code[i] != 0;
+      }
+      if (VEC == 4) reinterpret_cast<uint4*>(n32)[q] = make_uint4(w[0], w[VEC > 1 ? 1 : 0], w[VEC > 2 ? 2 : 0], w[VEC > 3 ? 3 : 0]);
+      else n32[j0] = w[0];
+      if (n_act) {
+        int pos = atomicAdd(&s_count, n_act);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (code[i]) s_list[pos++] = make_uint2((uint32_t)(j0 + i), code[i]);
+      }
+    }
+    __syncthreads();
+    //      pass 2: one Philox block per queued word, all lanes busy
+    bool any_burning = false;
+    const int n_list = s_count;
+    for (int idx = tid; idx < n_list; idx += T) {
+      const uint2 ent = s_list[idx];
+      uint32_t u[4];
+      philox4x32_10(id0, id1, tick, 1u + ent.x, k0, k1, u);
+      uint32_t nw = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t s = (ent.y >> (8 * i)) & 3u, k = (ent.y >> (8 * i + 2)) & 7u;
+        uint32_t ns = s;
+        if (s == WF_BURNING) ns = u[i] < p.burnout_threshold ? WF_BURNT : WF_BURNING;
+        else if (k) ns = u[i] < p.ignite_threshold[k] ? WF_BURNING : WF_HEALTHY;
+        nw |= ns << (8 * i);
+      }
+      n32[ent.x] = nw;
       any_burning |= (nw & 0x01010101u) != 0;
     }
     // ---- 4. termination, same-step autoreset
@@ -359,12 +393,27 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
   // ---- 5. observation (type byte = state; colour green / red / grey) + write-back
   if (p.obs) {
     uint32_t* o32 = reinterpret_cast<uint32_t*>(s_obs);
-    for (int j = tid; j < nwords; j += T) {
-      const uint32_t w = n32[j];
-      const uint32_t burnt = (w >> 1) & 0x01010101u, healthy = ~(w | (w >> 1)) & 0x01010101u;
-      uint32_t o0, o1, o2;
-      interleave3(w, healthy * 3u + burnt * 7u, 0u, o0, o1, o2);
-      o32[3 * j] = o0; o32[3 * j + 1] = o1; o32[3 * j + 2] = o2;
+    for (int q = tid; q < nwords / VEC; q += T) {
+      uint32_t w[VEC], o[3 * VEC];
+      if (VEC == 4) {
+        const uint4 a = reinterpret_cast<const uint4*>(n32)[q];
+        w[0] = a.x; w[VEC > 1 ? 1 : 0] = a.y; w[VEC > 2 ? 2 : 0] = a.z; w[VEC > 3 ? 3 : 0] = a.w;
+      } else {
+        w[0] = n32[q];
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const uint32_t burnt = (w[i] >> 1) & 0x01010101u, healthy = ~(w[i] | (w[i] >> 1)) & 0x01010101u;
+        interleave3(w[i], healthy * 3u + burnt * 7u, 0u, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      }
+      if (VEC == 4) {
+        uint4* d = reinterpret_cast<uint4*>(o32) + 3 * q;
+        d[0] = make_uint4(o[0], o[1], o[2], o[3 % (3 * VEC)]);
+        d[1] = make_uint4(o[4 % (3 * VEC)], o[5 % (3 * VEC)], o[6 % (3 * VEC)], o[7 % (3 * VEC)]);
+        d[2] = make_uint4(o[8 % (3 * VEC)], o[9 % (3 * VEC)], o[10 % (3 * VEC)], o[11 % (3 * VEC)]);
+      } else {
+        o32[3 * q] = o[0]; o32[3 * q + 1] = o[1]; o32[3 * q + 2] = o[2];
+      }
     }
     __syncthreads();
     if (tid < A) {
@@ -397,13 +446,16 @@ cudaError_t configure_wildfire_kernel(int cells, int H) {
   const int bytes = (int)wildfire_smem_bytes(cells, H);
   cudaError_t e;
   if ((e = cudaFuncSetAttribute((const void*)wildfire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
   const bool fast = wf_fast(p.H);
-  const int threads = fast ? (p.cells / 4 >= 512 ? 128 : 64) : kWfThreads;
+  const bool vec = (p.H & 15) == 0;   // rows are whole 16-byte vectors
+  const int threads = fast ? (p.cells / (vec ? 16 : 4) >= 256 ? 128 : 64) : kWfThreads;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.N); cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = wildfire_smem_bytes(p.cells, p.H); cfg.stream = st;
@@ -413,7 +465,8 @@ cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
   static const bool pdl = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   if (!fast) return cudaLaunchKernelEx(&cfg, wildfire_kernel, p);
-  return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64>, p);
+  if (vec) return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128, 4>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64, 4>, p);
+  return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128, 1>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64, 1>, p);
 }
 
 }  // namespace mg

@@ -10,6 +10,7 @@ namespace mg {
 struct WildfireParams {
   int W, H, cells, A, num_fires, max_steps, autoreset, op;   // op: 0 = reset(mask), 1 = step
   uint32_t ignite_threshold[5], burnout_threshold;
+  uint32_t rv_magic;       // same for 16-byte vectors per row (H / 16), used when H % 16 == 0; else = rw_magic
   uint32_t rw_magic;       // floor(2^32 / (H / 4)) + 1: word-in-row index without a division (fast kernel)
   uint8_t agent_colour[MG_MAX_WILDFIRE_AGENTS];
   long long N;
