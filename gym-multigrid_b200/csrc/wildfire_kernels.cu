@@ -264,31 +264,36 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
         philox4x32_10(id0, id1, ctr0 + (uint32_t)(lane >> 2), 0u, k0, k1, u);
         const uint32_t word = (lane & 2) ? ((lane & 1) ? u[3] : u[2]) : ((lane & 1) ? u[1] : u[0]);
         const int jl = (int)__umulhi(word, (uint32_t)(A - lane));   // below(i + 1), i = A - 1 - lane
-        for (int d = 0; d < A - 1; ++d) {
+        for (int d = 0; d < A - 1; ++d) {  // swap positions i and j: one broadcast + one permuting shuffle
           const int i = A - 1 - d, j = __shfl_sync(0xffffffffu, jl, d);
-          const int vi = __shfl_sync(0xffffffffu, ord, i), vj = __shfl_sync(0xffffffffu, ord, j);
-          if (lane == i) ord = vj; else if (lane == j) ord = vi;
+          ord = __shfl_sync(0xffffffffu, ord, lane == i ? j : (lane == j ? i : lane));
         }
       }
-      int x = lane < A ? s_ax[lane] : -1, y = lane < A ? s_ay[lane] : -1, dir = lane < A ? s_adir[lane] : 0;
+      // an agent acts once per step, so its target cell is known up front; positions travel packed as x | y << 8
       const int a = lane < A ? p.actions[e * A + lane] : 0;
-      double rew = 0.0;
+      int x = lane < A ? s_ax[lane] : 0, y = lane < A ? s_ay[lane] : 0, dir = lane < A ? s_adir[lane] : 0;
+      const int dx = (a == 4) - (a == 2), dy = (a == 3) - (a == 1);
+      const int nx = x + dx, ny = y + dy;
+      const bool wants = lane < A && a >= 1 && a <= 4 && nx >= 0 && ny >= 0 && nx < W && ny < H;
+      const uint32_t target = (uint32_t)nx | ((uint32_t)ny << 8);
+      uint32_t cur = lane < A ? ((uint32_t)x | ((uint32_t)y << 8)) : 0xFFFFFFFFu;   // idle lanes never match a target
       for (int k = 0; k < A; ++k) {
-        const int i = __shfl_sync(0xffffffffu, ord, k);  // the acting agent; warp-uniform
-        int dx = 0, dy = 0;
-        if (lane == i && a >= 1 && a <= 4) { dx = (a == 4) - (a == 2); dy = (a == 3) - (a == 1); }
-        const int nx = __shfl_sync(0xffffffffu, x + dx, i), ny = __shfl_sync(0xffffffffu, y + dy, i);
-        const unsigned occupied = __ballot_sync(0xffffffffu, lane != i && lane < A && x == nx && y == ny);
-        if (lane == i) {
-          if ((dx | dy) && nx >= 0 && ny >= 0 && nx < W && ny < H && !occupied) {
-            dir = dx == 1 ? 0 : (dy == 1 ? 1 : (dx == -1 ? 2 : 3));  // DIR_TO_VEC (constants.py:65-74)
-            x = nx; y = ny;
-          }
-          if (s_told[x * H + y] == WF_BURNING) { s_told[x * H + y] = WF_BURNT; rew += 1.0; }  // extinguish
+        const int i = __shfl_sync(0xffffffffu, ord, k);          // the acting agent; warp-uniform
+        const uint32_t t = __shfl_sync(0xffffffffu, target, i);
+        const unsigned occupied = __ballot_sync(0xffffffffu, cur == t && lane != i);
+        if (lane == i && wants && !occupied) {
+          cur = t;
+          dir = dx == 1 ? 0 : (dy == 1 ? 1 : (dx == -1 ? 2 : 3));  // DIR_TO_VEC (constants.py:65-74)
         }
-        __syncwarp();
       }
-      if (lane < A) { s_ax[lane] = x; s_ay[lane] = y; s_adir[lane] = dir; p.rewards[e * A + lane] = rew; }
+      // extinguish the burning cell under each agent: agents stand on distinct cells and never act twice, so this
+      // does not depend on the order
+      if (lane < A) {
+        x = (int)(cur & 255u); y = (int)(cur >> 8);
+        double rew = 0.0;
+        if (s_told[x * H + y] == WF_BURNING) { s_told[x * H + y] = WF_BURNT; rew = 1.0; }
+        s_ax[lane] = x; s_ay[lane] = y; s_adir[lane] = dir; p.rewards[e * A + lane] = rew;
+      }
     }
     __syncthreads();
 
