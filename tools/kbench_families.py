@@ -160,6 +160,22 @@ def bench_wildfire(args):
             e.close()
 
 
+def bench_memset(args):
+    """Write-only and copy ceilings measured with the same protocol (graph over rotating buffers > L2)."""
+    nbytes = 256 << 20
+    bufs = [torch.empty(nbytes, dtype=torch.uint8, device="cuda:0") for _ in range(4)]
+    us = graph_time([lambda b=b: b.zero_() for b in bufs], args.reps)
+    print(json.dumps({"kernel": "torch zero_ (write only)", "bytes": nbytes, "us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                      "frac_of_measured_peak": round(nbytes / us / 1e3 / peak(), 4)}), flush=True)
+    us = graph_time([lambda a=bufs[i], b=bufs[(i + 1) % 4]: b.copy_(a) for i in range(4)], args.reps)
+    print(json.dumps({"kernel": "torch copy_ (read + write)", "bytes": 2 * nbytes, "us": round(us, 2), "GBps": round(2 * nbytes / us / 1e3, 1),
+                      "frac_of_measured_peak": round(2 * nbytes / us / 1e3 / peak(), 4)}), flush=True)
+    x = [torch.empty(nbytes // 4, dtype=torch.float32, device="cuda:0") for _ in range(4)]
+    us = graph_time([lambda b=b: b.sum() for b in x], args.reps)
+    print(json.dumps({"kernel": "torch sum (read only)", "bytes": nbytes, "us": round(us, 2), "GBps": round(nbytes / us / 1e3, 1),
+                      "frac_of_measured_peak": round(nbytes / us / 1e3 / peak(), 4)}), flush=True)
+
+
 def bench_generic(args):
     g = {k: golden("generic_12x12_a5", k) for k in ("init_obs", "init_pos")}
     n, A, S = 65536, 5, 12
