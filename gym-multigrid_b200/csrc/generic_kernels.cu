@@ -1,8 +1,6 @@
 // generic_kernels.cu -- the base-class MultiGridEnv.step (multigrid.py:397-483) with DefaultWorld
 // (world.py:33-52, encode_dim 6) and per-agent full-grid observations Grid.encode_for_agents (grid.py:254-284).
-// No shipped env reaches this path; it is here for API completeness, built for correctness first:
-// one thread per env walks the agents in the given order on the env's two cell planes (type|colour, state), then
-// the whole tile encodes [env][agent][cell] -> 6 bytes with consecutive threads on consecutive cells.
+// No shipped env reaches this path; it is here for API completeness.
 // Only still / left / right / forward are defined: any other action makes the reference evaluate
 // `self.actions.available` (multigrid.py:447), which no action enum defines, and raise.
 #include <cstdlib>
@@ -12,67 +10,125 @@
 
 namespace mg {
 
-constexpr int kGenE = 32, kGenThreads = 128;
+// One CTA = a tile of 8 envs.  The tile's two cell planes and agent positions are staged in shared memory (coalesced
+// loads); warp 0 steps the envs, one lane per env, in the given agent order; then all threads encode
+// [env][agent][cell] -> 6 bytes into shared memory and the tile's contiguous observation slab leaves as ONE TMA bulk
+// store (full-line writes); the cell planes are written back coalesced.
+constexpr int kGenE = 8, kGenThreads = 128;
 constexpr int G_EMPTY = 1, G_DOOR = 4, G_GOAL = 8, G_AGENT = 10;  // DefaultWorld.OBJECT_TO_IDX (world.py:37-51)
 
-__device__ __forceinline__ void generic_encode_tile(const GenericParams& p, long long e0, int n_here, uint8_t* out, const uint8_t* done_only,
-                                                    int tid) {
+struct GenSmem {
+  uint8_t* obs;     // [kGenE][A][cells][6]
+  uint8_t* cell;    // [kGenE][cells]
+  uint8_t* state;   // [kGenE][cells]
+  uint8_t* pos;     // [kGenE][A][2]
+};
+__host__ __device__ inline size_t gen_obs_bytes(int A, int cells) { return ((size_t)kGenE * A * cells * 6 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t gen_smem_bytes(int A, int cells) {
+  return gen_obs_bytes(A, cells) + 2 * (((size_t)kGenE * cells + 15) & ~(size_t)15) + (size_t)kGenE * A * 2 + 16;
+}
+
+// all threads: encode_for_agents (grid.py:254-284) of the tile's envs (those with sel[el] != 0 when sel is given) into s.obs
+__device__ __forceinline__ void generic_encode_tile(const GenericParams& p, const GenSmem& s, int n_here, const uint8_t* sel, int tid) {
   const int cells = p.cells, A = p.A;
-  const long long total = (long long)n_here * A * cells;
-  for (long long idx = tid; idx < total; idx += kGenThreads) {
-    const int el = (int)(idx / ((long long)A * cells));
-    if (done_only && !done_only[el]) continue;
-    const int rem = (int)(idx - (long long)el * A * cells), k = rem / cells, i = rem - k * cells;
-    const long long e = e0 + el;
-    const uint8_t c = p.gcell[e * cells + i], s = p.gstate[e * cells + i];
-    const int type = c & 15;
-    uint8_t o2 = 0, o4 = 0, o5 = 0;
-    if (type == G_DOOR) o2 = s;                                   // Door.encode object.py:238-259
-    else if (type == G_AGENT) {                                   // Agent.encode agent.py:127-165 (carrying is always None here)
-      o4 = s & 3;
-      o5 = (i == p.pos[(e * A + k) * 2] * p.H + p.pos[(e * A + k) * 2 + 1]);
+  const int total = n_here * cells;
+  for (int idx = tid; idx < total; idx += kGenThreads) {   // one thread per (env, cell): decoded once, written for every agent
+    const int el = (int)__umulhi((uint32_t)idx, p.cells_magic);
+    if (sel && !sel[el]) continue;
+    const int i = idx - el * cells;
+    const uint32_t c = s.cell[idx], st = s.state[idx];
+    const uint32_t type = c & 15u;
+    const uint16_t w0 = (uint16_t)(type | ((c >> 4) << 8));
+    const uint16_t w1 = (uint16_t)(type == G_DOOR ? st : 0u);                 // Door.encode object.py:238-259
+    const bool agent = type == G_AGENT;
+    const uint16_t w2 = (uint16_t)(agent ? (st & 3u) : 0u);                   // Agent.encode agent.py:127-165 (carrying is always None here)
+    uint16_t* o = reinterpret_cast<uint16_t*>(s.obs + ((size_t)el * A * cells + i) * 6);
+    for (int k = 0; k < A; ++k) {
+      const bool self = agent && i == s.pos[(el * A + k) * 2] * p.H + s.pos[(el * A + k) * 2 + 1];   // the is_self plane
+      o[0] = w0; o[1] = w1; o[2] = (uint16_t)(w2 | (self ? 0x100u : 0u));
+      o += cells * 3;
     }
-    uint16_t* o = reinterpret_cast<uint16_t*>(out + ((e * A + k) * cells + i) * 6);
-    o[0] = (uint16_t)(type | ((c >> 4) << 8)); o[1] = o2; o[2] = (uint16_t)(o4 | (o5 << 8));
   }
 }
 
-__device__ __forceinline__ void generic_reset_env(const GenericParams& p, long long e, int4& h) {
-  for (int i = 0; i < p.cells; ++i) { p.gcell[e * p.cells + i] = p.icell[e * p.cells + i]; p.gstate[e * p.cells + i] = p.istate[e * p.cells + i]; }
-  for (int i = 0; i < p.A * 2; ++i) p.pos[e * p.A * 2 + i] = p.ipos[e * p.A * 2 + i];
-  h.x = 0; h.w += 1;
+// all threads: the tile's slab (or the selected envs of it) -> global; full tiles with an aligned destination use one TMA bulk store
+__device__ __forceinline__ void generic_store_tile(const GenericParams& p, const GenSmem& s, uint8_t* dst_base, long long e0, int n_here,
+                                                   const uint8_t* sel, int tid) {
+  const size_t per_env = (size_t)p.A * p.cells * 6;
+  uint8_t* dst = dst_base + (size_t)e0 * per_env;
+  if (!sel && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const uint32_t bytes = (uint32_t)(n_here * per_env), bulk = bytes & ~15u;
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0 && bulk) { tma_store_1d(dst, s.obs, bulk); tma_commit(); }
+    for (uint32_t i = bulk + tid; i < bytes; i += kGenThreads) dst[i] = s.obs[i];
+    if (tid == 0) tma_wait_read_all();
+    __syncthreads();
+    return;
+  }
+  __syncthreads();
+  for (int el = 0; el < n_here; ++el) {
+    if (sel && !sel[el]) continue;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(s.obs + el * per_env);
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst + el * per_env);
+    for (int i = tid; i < (int)(per_env / 2); i += kGenThreads) d[i] = src[i];
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kGenThreads) generic_kernel(const __grid_constant__ GenericParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint8_t s_done[kGenE];
   const int tid = threadIdx.x, A = p.A, cells = p.cells, H = p.H;
   const long long e0 = (long long)blockIdx.x * kGenE;
   const int n_here = (int)min((long long)kGenE, p.N - e0);
+  GenSmem s;
+  s.obs = smem_raw;
+  s.cell = smem_raw + gen_obs_bytes(A, cells);
+  s.state = s.cell + (((size_t)kGenE * cells + 15) & ~(size_t)15);
+  s.pos = s.state + (((size_t)kGenE * cells + 15) & ~(size_t)15);
   pdl_launch_dependents();
   pdl_wait();
+  // ---- stage the tile (reset: from the episode-start snapshot planes of the selected envs)
+  for (int i = tid; i < n_here * cells; i += kGenThreads) {
+    const int el = (int)__umulhi((uint32_t)i, p.cells_magic);
+    const bool from_init = p.op == 0 && (!p.reset_mask || p.reset_mask[e0 + el]);
+    s.cell[i] = from_init ? p.icell[e0 * cells + i] : p.gcell[e0 * cells + i];
+    s.state[i] = from_init ? p.istate[e0 * cells + i] : p.gstate[e0 * cells + i];
+  }
+  for (int i = tid; i < n_here * A * 2; i += kGenThreads) {
+    const int el = i / (A * 2);
+    const bool from_init = p.op == 0 && (!p.reset_mask || p.reset_mask[e0 + el]);
+    s.pos[i] = from_init ? p.ipos[e0 * A * 2 + i] : p.pos[e0 * A * 2 + i];
+  }
+  if (tid < kGenE) s_done[tid] = 0;
+  __syncthreads();
+
   bool done = false;
   int4 h = make_int4(0, 0, 0, 0);
   if (tid < n_here) {
     const long long e = e0 + tid;
     h = p.hdr[e];
     if (p.op == 0) {
-      if (!p.reset_mask || p.reset_mask[e]) generic_reset_env(p, e, h);
+      if (!p.reset_mask || p.reset_mask[e]) { h.x = 0; h.w += 1; }
     } else {
-      uint8_t* gc = p.gcell + e * cells; uint8_t* gs = p.gstate + e * cells; uint8_t* pos = p.pos + e * A * 2;
+      uint8_t* gc = s.cell + tid * cells; uint8_t* gs = s.state + tid * cells; uint8_t* pos = s.pos + tid * A * 2;
       Rng<1> r;
       r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
-      uint8_t order[8];
-      if (p.order) { for (int i = 0; i < A; ++i) order[i] = p.order[e * A + i]; }
-      else {
-        for (int i = 0; i < A; ++i) order[i] = (uint8_t)i;
-        for (int i = A - 1; i > 0; --i) { const int j = (int)__umulhi(r.u32(), (uint32_t)(i + 1)); const uint8_t t = order[i]; order[i] = order[j]; order[j] = t; }
-      }
+      uint32_t order = 0x76543210u;   // one nibble per agent (A <= 8)
+      if (p.order) { order = 0; for (int i = 0; i < A; ++i) order |= (uint32_t)(p.order[e * A + i] & 7) << (4 * i); }
+      else
+        for (int i = A - 1; i > 0; --i) {
+          const int j = (int)__umulhi(r.u32(), (uint32_t)(i + 1));
+          const uint32_t x = ((order >> (4 * i)) ^ (order >> (4 * j))) & 15u;
+          order ^= (x << (4 * i)) | (x << (4 * j));
+        }
       h.x += 1;  // multigrid.py:400
       bool term = false;
       int err = 0;
       for (int i = 0; i < A; ++i) p.rewards[e * A + i] = 0.0;
       for (int k = 0; k < A; ++k) {  // for i in order :408
-        const int i = order[k], a = p.actions[e * A + i];
+        const int i = (int)((order >> (4 * k)) & 15u), a = p.actions[e * A + i];
         if (a == 0) continue;  // still :413
         const int x = pos[2 * i], y = pos[2 * i + 1], here = x * H + y, dir = gs[here] & 3;
         const int fx = x + (dir == 0) - (dir == 2), fy = y + (dir == 1) - (dir == 3);  // DIR_TO_VEC constants.py:65-74
@@ -99,25 +155,44 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const __grid_const
       done = p.autoreset && (term || trunc);
       h.z = (int)r.ctr;
       if (err) atomicOr(p.status, err);
+      s_done[tid] = done;
     }
   }
-  if (tid < kGenE) s_done[tid] = done;
   const int any_done = __syncthreads_or(done);
   if (any_done) {  // same-step autoreset: terminal observation first, then restore the episode-start snapshot
-    if (p.final_obs) generic_encode_tile(p, e0, n_here, p.final_obs, s_done, tid);
+    if (p.final_obs) {
+      generic_encode_tile(p, s, n_here, s_done, tid);
+      generic_store_tile(p, s, p.final_obs, e0, n_here, s_done, tid);
+    }
+    for (int el = 0; el < n_here; ++el) {
+      if (!s_done[el]) continue;
+      for (int i = tid; i < cells; i += kGenThreads) { s.cell[el * cells + i] = p.icell[(e0 + el) * cells + i]; s.state[el * cells + i] = p.istate[(e0 + el) * cells + i]; }
+      for (int i = tid; i < A * 2; i += kGenThreads) s.pos[el * A * 2 + i] = p.ipos[(e0 + el) * A * 2 + i];
+    }
+    if (done) { h.x = 0; h.w += 1; }
     __syncthreads();
-    if (done) generic_reset_env(p, e0 + tid, h);
   }
   if (tid < n_here) p.hdr[e0 + tid] = h;
-  __syncthreads();
-  if (p.obs) generic_encode_tile(p, e0, n_here, p.obs, nullptr, tid);
+  // ---- state write-back (coalesced) and the observation
+  for (int i = tid; i < n_here * cells; i += kGenThreads) { p.gcell[e0 * cells + i] = s.cell[i]; p.gstate[e0 * cells + i] = s.state[i]; }
+  for (int i = tid; i < n_here * A * 2; i += kGenThreads) p.pos[e0 * A * 2 + i] = s.pos[i];
+  if (p.obs) {
+    generic_encode_tile(p, s, n_here, nullptr, tid);
+    generic_store_tile(p, s, p.obs, e0, n_here, nullptr, tid);
+  }
 }
 
 int generic_tile_envs() { return kGenE; }
+size_t generic_smem_bytes(int A, int cells) { return gen_smem_bytes(A, cells); }
+
+cudaError_t configure_generic_kernel(int A, int cells) {
+  return cudaFuncSetAttribute((const void*)generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes(A, cells));
+}
 
 cudaError_t launch_generic(const GenericParams& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((p.N + kGenE - 1) / kGenE)); cfg.blockDim = dim3(kGenThreads); cfg.stream = st;
+  cfg.dynamicSmemBytes = gen_smem_bytes(p.A, p.cells);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -6,6 +6,7 @@
 namespace mg {
 
 struct GenericParams {
+  uint32_t cells_magic, per_env_magic;   // floor(2^32 / cells) + 1, floor(2^32 / (A * cells)) + 1 (tile-local indices < 2^16)
   int W, H, cells, A, max_steps, autoreset, op;   // op: 0 = reset(mask) from the snapshot planes, 1 = step
   long long N;
   unsigned long long env_id_base, seed;

@@ -43,6 +43,8 @@ cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st);
 cudaError_t configure_wildfire_kernel(int cells, int H);
 size_t wildfire_smem_bytes(int cells, int H);
 cudaError_t launch_generic(const GenericParams& p, cudaStream_t st);
+cudaError_t configure_generic_kernel(int A, int cells);
+size_t generic_smem_bytes(int A, int cells);
 int generic_tile_envs();
 }  // namespace mg
 
@@ -539,6 +541,9 @@ extern "C" int mg_create_generic(const mg_generic_config* cfg, int device, mg_en
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create_generic: kernels are built for sm_100a only");
+  if ((size_t)mg::generic_tile_envs() * A * cells >= 65536 || mg::generic_smem_bytes(A, cells) > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(nullptr, "mg_create_generic: num_agents * width * height too large for one tile (8 envs' observations must fit in shared memory)");
+  if ((ce = mg::configure_generic_kernel(A, cells)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_generic: out of host memory");
   env->family = MG_FAMILY_GENERIC;
@@ -564,6 +569,7 @@ extern "C" int mg_create_generic(const mg_generic_config* cfg, int device, mg_en
   mg::GenericParams& p = env->gbase;
   std::memset(&p, 0, sizeof p);
   p.W = W; p.H = H; p.cells = cells; p.A = A; p.max_steps = cfg->max_steps; p.autoreset = cfg->autoreset != 0;
+  p.cells_magic = (uint32_t)(4294967296ull / (unsigned)cells) + 1u; p.per_env_magic = (uint32_t)(4294967296ull / (unsigned)(A * cells)) + 1u;
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed; p.status = env->d_status;
   *out = env;
   return 0;
