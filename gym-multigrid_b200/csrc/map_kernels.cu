@@ -383,6 +383,43 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     }
 }
 
+// _get_info of the map families (maze.py:262-269; ctf.py:1165-1182, 434-452): distances from agents[0] / agents[1] to the
+// flags and to the nearest cell of the territory / obstacle lists.  distance_points is np.linalg.norm of an integer
+// vector = sqrt((double)d2) (correctly rounded on both sides); distance_area_point is the minimum of such norms =
+// sqrt(min d2), looked up in host-built per-cell tables.  out: float64 [N][2] (Maze) or [N][11] (CtF, dict key order).
+template <int FAMILY>
+__global__ void __launch_bounds__(256) map_info_kernel(const __grid_constant__ MapParams p, double* __restrict__ out) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  const int S = p.S, cells = p.cells;
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(p.agents + e * p.row_bytes);
+  auto area = [&](int table, uint32_t w) {
+    const int d2 = __ldg(p.d2_tables + table * cells + ag_x(w) * S + ag_y(w));
+    return d2 < 0 ? __longlong_as_double(0x7FF0000000000000ll) : sqrt((double)d2);   // empty list: inf (the reference raises)
+  };
+  auto points = [](uint32_t a, uint32_t b) {
+    const int dx = ag_x(a) - ag_x(b), dy = ag_y(a) - ag_y(b);
+    return sqrt((double)(dx * dx + dy * dy));
+  };
+  const uint32_t a0 = row[0];
+  if (FAMILY == MG_FAMILY_MAZE) {
+    out[e * 2] = area(0, a0); out[e * 2 + 1] = area(1, a0);
+    return;
+  }
+  const uint32_t a1 = row[1], bf = (uint32_t)p.blue_flag, rf = (uint32_t)p.red_flag;   // agents[1]: the second agent of the list
+  double* o = out + e * 11;
+  o[0] = points(a0, a1); o[1] = points(a0, bf); o[2] = points(a0, rf); o[3] = points(a1, bf); o[4] = points(a1, rf);
+  o[5] = points(bf, rf);
+  o[6] = area(0, a0); o[7] = area(1, a0); o[8] = area(0, a1); o[9] = area(1, a1); o[10] = area(2, a0);
+}
+
+cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((p.N + 255) / 256);
+  if (p.family == MG_FAMILY_MAZE) map_info_kernel<MG_FAMILY_MAZE><<<blocks, 256, 0, st>>>(p, out);
+  else map_info_kernel<MG_FAMILY_CTF><<<blocks, 256, 0, st>>>(p, out);
+  return cudaGetLastError();
+}
+
 static bool map_pdl_enabled() {
   static const bool on = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
   return on;

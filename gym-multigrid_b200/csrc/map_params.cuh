@@ -22,6 +22,7 @@ struct MapParams {
   const uint16_t* background;  // Maze: cells with code background, np.where order; every list entry is packed x | y << 8
   const uint16_t* blue_terr;   // CtF: blue territory cells + blue flag (ctf.py:765-769)
   const uint16_t* red_terr;
+  const int32_t* d2_tables;    // [3][cells] min squared distance from each cell to: Maze flag / obstacle / -, CtF blue territory / red territory / obstacle (-1 = empty list)
   // battle tests restated in integers (bit-exact, computed on the host with the same double arithmetic):
   int d2_max;                              // largest squared distance d2 with sqrt((double)d2) <= battle_range (-1: none)
   unsigned long long thr_blue_home, thr_red_home, thr_even;  // blue wins iff u32 < ceil(p * 2^32), p = randomness / 1 - randomness / 0.5

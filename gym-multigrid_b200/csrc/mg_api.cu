@@ -27,6 +27,7 @@ cudaError_t launch_map(const MapParams& p, cudaStream_t st);
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype);
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype);
 bool map_obs_staged(int cells, int obs_dtype);
+cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st);
 int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
@@ -351,9 +352,11 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   }
   const size_t o_map = 0, o_per = align_up((size_t)cells, 256), o_bg = align_up(o_per + L, 256),
                o_bt = align_up(o_bg + bg.size(), 256), o_rt = align_up(o_bt + bt.size(), 256), o_pk = align_up(o_rt + rt.size(), 256),
-               o_pad = align_up(o_pk + cells, 256);
+               o_pad = align_up(o_pk + cells, 256), o_d2 = 0;  /* o_d2 set below */
   const int pad = 14, pitch = S + 2 * pad;   // view_size <= 15: a view reaches at most 14 cells beyond the map
-  const size_t padded_bytes = align_up((size_t)pitch * pitch, 16), total = align_up(o_pad + padded_bytes, 256) + 256;
+  const size_t padded_bytes = align_up((size_t)pitch * pitch, 16);
+  const size_t o_d2b = align_up(o_pad + padded_bytes, 256), total = align_up(o_d2b + (size_t)3 * cells * sizeof(int32_t), 256) + 256;
+  (void)o_d2;
   std::string blob(total, '\0');
   std::memcpy(&blob[o_map], cfg->field_map, cells);
   std::memcpy(&blob[o_per], period.data(), L);
@@ -370,6 +373,24 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
     for (int x = 0; x < S; ++x) std::memcpy(&blob[o_pad + (size_t)(x + pad) * pitch + pad], &blob[o_pk + (size_t)x * S], S);
   }
   env->map_padded_off = o_pad; env->map_padded_bytes = padded_bytes; env->map_pad = pad;
+  {  // _get_info tables: min squared distance from every cell to the cell lists of maze.py:262-269 / ctf.py:1165-1182
+    int32_t* d2 = reinterpret_cast<int32_t*>(&blob[o_d2b]);
+    for (int t = 0; t < 3; ++t) {
+      // Maze: flag list, obstacle list; CtF: blue territory + blue flag, red territory + red flag (ctf.py:765-773), obstacle list
+      const int ca = maze ? (t == 0 ? 2 : (t == 1 ? 3 : -1)) : (t == 0 ? 0 : (t == 1 ? 1 : 6));
+      const int cb = maze ? ca : (t == 0 ? 4 : (t == 1 ? 5 : 6));
+      for (int i = 0; i < cells; ++i) {
+        int best = -1;
+        for (int j = 0; j < cells; ++j) {
+          const int c = cfg->field_map[j];
+          if (c != ca && c != cb) continue;
+          const int dx = i / S - j / S, dy = i % S - j % S, v = dx * dx + dy * dy;
+          if (best < 0 || v < best) best = v;
+        }
+        d2[t * cells + i] = best;
+      }
+    }
+  }
   if ((ce = cudaMalloc(&env->d_map_tables, total)) != cudaSuccess ||
       (ce = cudaMemcpy(env->d_map_tables, blob.data(), total, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess ||
@@ -401,6 +422,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   p.blue_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bt);
   p.red_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_rt);
   p.status = env->d_status; p.rng_mode = 1;
+  p.d2_tables = reinterpret_cast<const int32_t*>(env->d_map_tables + o_d2b);
   env->map_codes_off = o_pk;
   *out = env;
   return 0;
@@ -440,6 +462,19 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
   if (p.obs && !aligned16(p.obs)) return fail(env, "obs buffer must be 16-byte aligned");
   cudaError_t ce;
   if ((ce = mg::launch_map(p, st)) != cudaSuccess) return cuda_fail(env, "map_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_map_info(mg_env* env, const void* state, double* out, void* stream) {
+  if (!env || !state || !out) return fail(env, "mg_map_info: null argument");
+  if (env->family != MG_FAMILY_MAZE && env->family != MG_FAMILY_CTF) return fail(env, "mg_map_info: Maze and CtF families only");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  mg::MapParams p = env->mbase;
+  p.agents = const_cast<uint8_t*>(static_cast<const uint8_t*>(state)) + env->plane_off[MG_MAP_PLANE_AGENTS];
+  p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
+  if ((ce = mg::launch_map_info(p, out, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "map_info_kernel", ce);
   env->launches += 1;
   return 0;
 }

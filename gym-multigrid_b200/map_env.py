@@ -86,6 +86,7 @@ class _MapVecEnv:
         self._agents = self._planes["agents"].view(N, slots, 4)[:, :n]     # (x, y, dir, flags) per agent
         self._io = _lib.StepIO()
         self._host = None
+        self.with_info = False      # True: step() / reset() also return the reference's info dict (one more launch)
         self._trace_keepalive = None
         self.closed = False
 
@@ -125,7 +126,7 @@ class _MapVecEnv:
     def reset(self, *, seed=None, options=None, mask=None):
         m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         self._check(self._lib.mg_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self._obs), self._stream()))
-        return self._obs, {}
+        return self._obs, (self.get_info() if self.with_info else {})
 
     def _prep_actions(self, actions):
         a = actions
@@ -165,10 +166,21 @@ class _MapVecEnv:
         n = self._host_np
         return n["obs"], n["rew"], n["term"].view(np.bool_), n["trunc"].view(np.bool_), {}
 
+    def get_info(self, out=None):
+        """`_get_info()` of every env as a dict of float64 CUDA tensors [N], keys and values as the reference's dict
+        (maze.py:262-269; ctf.py:1165-1182): one extra kernel launch over the state planes."""
+        K = len(self.info_keys)
+        if out is None:
+            out = torch.empty((self.num_envs, K), dtype=torch.float64, device=self.device)
+        self._check(self._lib.mg_map_info(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return {k: out[:, i] for i, k in enumerate(self.info_keys)}
+
     def _info(self):
-        if self._final_obs is None:
-            return {}
-        return {"final_observation": self._final_obs, "_final_observation": (self._term | self._trunc).view(torch.bool)}
+        info = self.get_info() if self.with_info else {}
+        if self._final_obs is not None:
+            info["final_observation"] = self._final_obs
+            info["_final_observation"] = (self._term | self._trunc).view(torch.bool)
+        return info
 
     def enable_final_observation(self, enable=True):
         self._final_obs = torch.zeros_like(self._obs) if enable else None
@@ -221,6 +233,7 @@ class MazeVecEnv(_MapVecEnv):
     `reference_dtypes=True` as the reference returns, maze.py:246); actions MazeActions Discrete(5)."""
     family = _lib.FAMILY_MAZE
     ref_dtype = torch.float64
+    info_keys = ("d_a_f", "d_a_ob")
 
     def __init__(self, num_envs, map_path, max_steps=100, flag_reward=1.0, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01,
                  observation_option="map", device="cuda:0", seed=0, autoreset=True, env_id_base=0, reference_dtypes=False):
@@ -259,6 +272,7 @@ class CtfVecEnv(_MapVecEnv):
     state planes.  Actions MultiDiscrete([5] * num_blue_agents); reward = scalar team reward (float64)."""
     family = _lib.FAMILY_CTF
     ref_dtype = torch.int64
+    info_keys = ("d_ba_ra", "d_ba_bf", "d_ba_rf", "d_ra_bf", "d_ra_rf", "d_bf_rf", "d_ba_bb", "d_ba_rb", "d_ra_bb", "d_ra_rb", "d_ba_ob")
 
     def __init__(self, num_envs, map_path, num_blue_agents=2, num_red_agents=2, battle_range=1, randomness=0.75, flag_reward=1,
                  battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,

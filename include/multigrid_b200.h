@@ -216,6 +216,13 @@ typedef struct mg_map_trace {
 int mg_create_map(const mg_map_config* cfg, int device, mg_env** out);
 int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
 
+/* `_get_info()` of every env (maze.py:262-269; ctf.py:1165-1182, 434-452) -> out float64, device:
+ *   Maze [N][2]  = d_a_f, d_a_ob
+ *   CtF  [N][11] = d_ba_ra, d_ba_bf, d_ba_rf, d_ra_bf, d_ra_rf, d_bf_rf, d_ba_bb, d_ba_rb, d_ra_bb, d_ra_rb, d_ba_ob
+ * ("ba" = agents[0], "ra" = agents[1] - the second agent of the list, a red one only with a single blue agent, as in the
+ * reference).  A distance to an empty cell list is +inf (the reference raises there). */
+int mg_map_info(mg_env* env, const void* state_dev, double* out_dev, void* stream);
+
 /* ========================================================================================= Wildfire
  * EXTENSION: the reference has no Wildfire code (only a README heading, README.md:43); BASELINE.json config 5
  * asks for it, so the rules below are OUR specification (docs in DESIGN.md section 10), checked against an

@@ -169,6 +169,9 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
                 uint8_t* obs, double* reward, uint8_t* terminated, uint8_t* truncated, int autoreset,
                 uint8_t* final_obs, int32_t* status);
 
+/* _get_info of the map families: Maze [N][2] (d_a_f, d_a_ob), CtF [N][11] (ctf.py:1165-1182 key order) */
+int oc_map_info(const oc_map_cfg* c, int is_maze, int64_t N, const oc_map_state* st, double* out);
+
 #define OC_ERR_BAD_ACTION 8 /* action outside the env's action set (reference: ValueError, maze.py:286, ctf.py:1200) */
 
 #ifdef __cplusplus

@@ -270,3 +270,40 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------ infos
+ * MazeSingleAgentEnv._get_info (maze.py:262-269) -> [N][2] = d_a_f, d_a_ob
+ * CtFMvNEnv._get_info / Ctf1v1Env._get_info (ctf.py:1165-1182, 434-452) -> [N][11] in the dict's key order.
+ * distance_points = np.linalg.norm of an int vector; distance_area_point = min over the listed cells (utils/map.py:7-19).
+ * Note agents[1] is the SECOND agent of the env's list: a red agent only when there is a single blue one. */
+#include <math.h>
+static double d_points(int x0, int y0, int x1, int y1) { const int dx = x0 - x1, dy = y0 - y1; return sqrt((double)(dx * dx + dy * dy)); }
+static double d_area(const oc_map_cfg* c, int x, int y, int code_a, int code_b) { /* min over cells whose code is code_a or code_b */
+  const int S = c->size;
+  double best = INFINITY; /* the reference raises on an empty list (np.min of []); inf marks that case */
+  for (int i = 0; i < S * S; ++i)
+    if (c->field_map[i] == code_a || c->field_map[i] == code_b) { const double d = d_points(x, y, i / S, i % S); if (d < best) best = d; }
+  return best;
+}
+int oc_map_info(const oc_map_cfg* c, int is_maze, int64_t N, const oc_map_state* st, double* out) {
+  const int S = c->size, n = is_maze ? 1 : c->num_blue + c->num_red;
+  for (int64_t e = 0; e < N; ++e) {
+    const uint8_t* pos = st->pos + e * n * 2;
+    if (is_maze) {
+      out[e * 2 + 0] = d_area(c, pos[0], pos[1], MZ_FLAG, MZ_FLAG);
+      out[e * 2 + 1] = d_area(c, pos[0], pos[1], MZ_OBSTACLE, MZ_OBSTACLE);
+      continue;
+    }
+    const int bf = nth_cell(c, CT_BLUE_FLAG, 0), rf = nth_cell(c, CT_RED_FLAG, 0);
+    const int ax = pos[0], ay = pos[1], bx = pos[2], by = pos[3]; /* agents[0], agents[1] */
+    double* o = out + e * 11;
+    o[0] = d_points(ax, ay, bx, by);
+    o[1] = d_points(ax, ay, bf / S, bf % S); o[2] = d_points(ax, ay, rf / S, rf % S);
+    o[3] = d_points(bx, by, bf / S, bf % S); o[4] = d_points(bx, by, rf / S, rf % S);
+    o[5] = d_points(bf / S, bf % S, rf / S, rf % S);
+    o[6] = d_area(c, ax, ay, CT_BLUE_TERR, CT_BLUE_FLAG); o[7] = d_area(c, ax, ay, CT_RED_TERR, CT_RED_FLAG); /* territory lists include the flag cell (ctf.py:765-773) */
+    o[8] = d_area(c, bx, by, CT_BLUE_TERR, CT_BLUE_FLAG); o[9] = d_area(c, bx, by, CT_RED_TERR, CT_RED_FLAG);
+    o[10] = d_area(c, ax, ay, CT_OBSTACLE, CT_OBSTACLE);
+  }
+  return 0;
+}

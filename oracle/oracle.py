@@ -268,6 +268,14 @@ class _MapOracle:
         s.step_count, s.rng_ctr = _p(self.step_count), _p(self.rng_ctr)
         return s
 
+    def info(self):
+        """`_get_info()` of every env: float64 [N, 2] (Maze) or [N, 11] (CtF), columns in the reference dict's key order."""
+        maze = isinstance(self, MazeOracle)
+        out = np.zeros((self.N, 2 if maze else 11), np.float64)
+        st = self._state()
+        lib().oc_map_info(C.byref(self.cfg), C.c_int(int(maze)), C.c_int64(self.N), C.byref(st), _p(out))
+        return out
+
     def _call_reset(self, fn, rng, mask):
         obs = np.zeros((self.N, self.S, self.S), np.uint8)
         st = self._state()
@@ -286,6 +294,11 @@ class _MapOracle:
            _p(trunc), C.c_int(int(autoreset)), _p(fin), C.byref(self.status))
         out = (obs, rew, term.astype(bool), trunc.astype(bool))
         return out + (fin,) if want_final_obs else out
+
+
+MAZE_INFO_KEYS = ("d_a_f", "d_a_ob")                                                       # maze.py:262-269
+CTF_INFO_KEYS = ("d_ba_ra", "d_ba_bf", "d_ba_rf", "d_ra_bf", "d_ra_rf", "d_bf_rf", "d_ba_bb", "d_ba_rb", "d_ra_bb", "d_ra_rb",
+                 "d_ba_ob")                                                                 # ctf.py:1165-1182
 
 
 class MazeOracle(_MapOracle):

@@ -246,10 +246,12 @@ def pack_collect_episodes(eps, T, K):
 
 # ------------------------------------------------------------------ generator proxy hook
 @contextmanager
-def tapped_generators():
-    """Every gymnasium np_random generator created while installed records into ONE ordered log."""
+def tapped_generators(unseeded_entropy=None):
+    """Every gymnasium np_random generator created while installed records into ONE ordered log.  `unseeded_entropy`
+    makes the generators the reference never seeds (the scripted policies') reproducible."""
     import gymnasium
     log = []
+    gymnasium.Env.unseeded_entropy = unseeded_entropy
 
     def wrap(g):
         p = GeneratorProxy(g)
@@ -262,6 +264,7 @@ def tapped_generators():
         yield log
     finally:
         gymnasium.Env.wrap_generator = old
+        gymnasium.Env.unseeded_entropy = None
 
 
 # ----------------------------------------------------------------------- Maze recording
@@ -313,12 +316,15 @@ def pack_episodes(eps, keys_per_step, keys_static, T=None):
 
 
 # ------------------------------------------------------------------------ CtF recording
+# key order of CtFMvNEnv._get_info / Ctf1v1Env._get_info (ctf.py:1165-1182, 434-452)
+CTF_INFO_KEYS = ("d_ba_ra", "d_ba_bf", "d_ba_rf", "d_ra_bf", "d_ra_rf", "d_bf_rf", "d_ba_bb", "d_ba_rb", "d_ra_bb", "d_ra_rb", "d_ba_ob")
+
 def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, obstacle_penalty_ratio=0.0,
                            max_steps=100, observation_option="map", max_battles=16):
     """One episode of the reference CtFMvNEnv (ctf.py:657-1433) on a FRESH instance (agent.terminated is
     never cleared by reset in the reference), with the ordered RNG event log split per step."""
     import_reference()
-    with tapped_generators() as log:
+    with tapped_generators(unseeded_entropy=770000 + seed) as log:
         from gym_multigrid.envs.ctf import CtFMvNEnv
         from gym_multigrid.policy.ctf.heuristic import RwPolicy
         env = CtFMvNEnv(map_path, num_blue_agents=num_blue, num_red_agents=num_red, enemy_policies=RwPolicy(),
@@ -331,7 +337,7 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
         del log[:]
         n = num_blue + num_red
         rec = dict(actions=[], red_actions=[], order=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[],
-                   truncated=[], pos=[], dir=[], dead=[])
+                   truncated=[], pos=[], dir=[], dead=[], info=[])
         init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
         init_dir = np.array([a.dir for a in env.agents], np.int8)
         while True:
@@ -354,11 +360,13 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
             rec["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
             rec["dir"].append(np.array([a.dir for a in env.agents], np.int8))
             rec["dead"].append(np.array([a.terminated for a in env.agents], np.uint8))
+            rec["info"].append(np.array([info[k] for k in CTF_INFO_KEYS], np.float64))
             if term or trunc:
                 break
     L = len(rec["actions"])
     out = dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(), init_pos=init_pos,
-               init_dir=init_dir, blue_place=place[0].astype(np.int32), red_place=place[1].astype(np.int32), length=L)
+               init_dir=init_dir, blue_place=place[0].astype(np.int32), red_place=place[1].astype(np.int32), length=L,
+               init_info=np.array([info0[k] for k in CTF_INFO_KEYS], np.float64))
     for k, v in rec.items():
         out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
     out["n_battles"] = out["n_battles"].astype(np.int32)
@@ -431,7 +439,7 @@ def record_toroid(env_id, seed, n_samples):
 def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battles=4):
     """One episode of the reference Ctf1v1Env (ctf.py:50-654), "map" observations, fresh instance."""
     import_reference()
-    with tapped_generators() as log:
+    with tapped_generators(unseeded_entropy=880000 + seed) as log:
         from gym_multigrid.envs.ctf import Ctf1v1Env
         from gym_multigrid.policy.ctf.heuristic import RwPolicy
         env = Ctf1v1Env(map_path, enemy_policy=RwPolicy(), max_steps=max_steps, observation_option="map")
@@ -440,7 +448,7 @@ def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battle
         assert len(place) == 2
         del log[:]
         rec = dict(actions=[], red_actions=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[], truncated=[],
-                   pos=[], dir=[], dead=[])
+                   pos=[], dir=[], dead=[], info=[])
         init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
         while True:
             a = int(action_rng.integers(0, 5))
@@ -460,11 +468,13 @@ def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battle
             rec["pos"].append(np.array([np.asarray(a_.pos) for a_ in env.agents], np.int16))
             rec["dir"].append(np.array([a_.dir for a_ in env.agents], np.int8))
             rec["dead"].append(np.array([0, int(env._is_red_agent_defeated)], np.uint8))
+            rec["info"].append(np.array([info[k] for k in CTF_INFO_KEYS], np.float64))
             if term or trunc:
                 break
     L = len(rec["actions"])
     out = dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(), init_pos=init_pos,
-               blue_place=np.array([place[0]], np.int32), red_place=np.array([place[1]], np.int32), length=L)
+               blue_place=np.array([place[0]], np.int32), red_place=np.array([place[1]], np.int32), length=L,
+               init_info=np.array([info0[k] for k in CTF_INFO_KEYS], np.float64))
     for k, v in rec.items():
         out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
     out["n_battles"] = out["n_battles"].astype(np.int32)

@@ -20,11 +20,15 @@ class Env:
     _np_random = None
     # test hook: oracle/ref_harness.py sets this to wrap every generator in a recording proxy
     wrap_generator = staticmethod(lambda g: g)
+    # test hook: entropy of lazily created (unseeded) generators; None = OS entropy as in gymnasium.  The recorders set it
+    # so that the committed fixtures are reproducible (the reference's scripted-policy generators are never seeded).
+    unseeded_entropy = None
 
     @property
     def np_random(self):
         if self._np_random is None:
-            self._np_random = Env.wrap_generator(np.random.Generator(np.random.PCG64(np.random.SeedSequence())))
+            ss = np.random.SeedSequence() if Env.unseeded_entropy is None else np.random.SeedSequence(Env.unseeded_entropy)
+            self._np_random = Env.wrap_generator(np.random.Generator(np.random.PCG64(ss)))
         return self._np_random
 
     @np_random.setter

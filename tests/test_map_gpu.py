@@ -35,10 +35,15 @@ def test_maze_replay_bit_exact(stem, ref_dtypes, cuda_device):
     obs, _ = env.reset()
     assert obs.dtype == (torch.float64 if ref_dtypes else torch.uint8)
     assert np.array_equal(_np(obs), _tile(g["init_obs"], k))
+    info = env.get_info()
+    assert list(info) == ["d_a_f", "d_a_ob"]
+    assert np.array_equal(np.stack([_np(v) for v in info.values()], 1), _tile(g["init_info"], k))
+    env.with_info = True
     for t in range(T):
         live = _tile(g["length"] > t, k)
         act = _tile(np.where(g["length"] > t, g["actions"][:, t], 0), k).astype(np.int8)
-        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        assert np.array_equal(np.stack([_np(info[q]) for q in ("d_a_f", "d_a_ob")], 1)[live], _tile(g["info"][:, t], k)[live]), f"step {t}: info"
         assert np.array_equal(_np(obs)[live], _tile(g["obs"][:, t], k)[live]), f"step {t}: obs"
         assert np.array_equal(_np(rew)[live], _tile(g["reward"][:, t], k)[live]), f"step {t}: reward (float64 bit-exact)"
         assert np.array_equal(_np(term)[live], _tile(g["terminated"][:, t], k)[live])
@@ -62,6 +67,7 @@ def test_ctf_replay_bit_exact(stem, cuda_device):
     env.set_trace(blue_place=_tile(g["blue_place"], k), red_place=_tile(g["red_place"], k))
     obs, _ = env.reset()
     assert np.array_equal(_np(obs), _tile(g["init_obs"], k)) and np.array_equal(_np(env.agent_pos), _tile(g["init_pos"], k))
+    assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1), _tile(g["init_info"], k)), "reset info (ctf.py:1165-1182)"
     ident = np.arange(nb + nr, dtype=np.uint8)[None]
     for t in range(T):
         lv = g["length"] > t
@@ -78,6 +84,7 @@ def test_ctf_replay_bit_exact(stem, cuda_device):
         assert np.array_equal(_np(env.agent_dir)[live], _tile(g["dir"][:, t], k)[live])
         assert np.array_equal(_np(env.agent_terminated)[live], _tile(g["dead"][:, t], k)[live].astype(bool))
         assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
+        assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1)[live], _tile(g["info"][:, t], k)[live]), f"step {t}: info"
     assert env.status() == 0
     env.close()
 
@@ -129,6 +136,8 @@ def test_ctf_philox_matches_oracle(nb, nr, n, pen, cuda_device):
         d = oterm | otrunc
         assert np.array_equal(_np(info["final_observation"])[d], ofin[d])
         assert np.array_equal(_np(env.agent_pos), o.pos) and np.array_equal(_np(env.agent_flags), o.flags)
+        if t % 8 == 0:
+            assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1), o.info()), f"step {t}: info"
         assert np.array_equal(_np(env.agent_dir), o.dir)
         battles += int((np.abs(orew + 0.01 * nb) > 0.2).sum())
     assert env.status() == 0 and battles > 0
@@ -215,6 +224,7 @@ def test_ctf1v1_replay_and_philox(cuda_device):
         assert np.array_equal(_np(term)[live], _tile(g["terminated"][:, t], k)[live])
         assert np.array_equal(_np(trunc)[live], _tile(g["truncated"][:, t], k)[live])
         assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
+        assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1)[live], _tile(g["info"][:, t], k)[live]), f"step {t}: info"
     assert env.status() == 0
     env.close()
     n = 3000

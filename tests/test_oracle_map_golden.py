@@ -16,11 +16,12 @@ def test_maze_matches_reference(stem):
     E, T = g["actions"].shape
     o = oc.MazeOracle(g["field_map"], E, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]))
     obs = o.reset(oc.map_rng(mode=0, start_index=g["start_index"]))
-    assert np.array_equal(obs, g["init_obs"])
+    assert np.array_equal(obs, g["init_obs"]) and np.array_equal(o.info(), g["init_info"])
     checked = 0
     for t in range(T):
         live = g["length"] > t
         obs, rew, term, trunc = o.step(np.where(live, g["actions"][:, t], 0), oc.map_rng(mode=0))
+        assert np.array_equal(o.info()[live], g["info"][live, t]), f"step {t}: _get_info (float64, bit-exact)"
         assert np.array_equal(obs[live], g["obs"][live, t]), f"step {t}: obs"
         assert np.array_equal(rew[live], g["reward"][live, t]), f"step {t}: reward (float64, bit-exact)"
         assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
@@ -37,6 +38,7 @@ def test_ctf_matches_reference(stem):
     o = oc.CtfOracle(g["field_map"], E, nb, nr, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]))
     obs = o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
     assert np.array_equal(obs, g["init_obs"]) and np.array_equal(o.pos, g["init_pos"]) and np.array_equal(o.dir, g["init_dir"])
+    assert np.array_equal(o.info(), g["init_info"])
     ident = np.arange(nb + nr, dtype=np.uint8)[None]
     for t in range(T):
         live = g["length"] > t
@@ -49,6 +51,7 @@ def test_ctf_matches_reference(stem):
         assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
         assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal(o.dir[live], g["dir"][live, t])
         assert np.array_equal((o.flags & 1)[live], g["dead"][live, t]) and np.array_equal(used[live], g["n_battles"][live, t])
+        assert np.array_equal(o.info()[live], g["info"][live, t]), f"step {t}: _get_info (float64, bit-exact)"
     assert o.status.value == 0
 
 
@@ -86,3 +89,4 @@ def test_ctf1v1_matches_reference():
         assert np.array_equal(term[live], g["terminated"][live, t]) and np.array_equal(trunc[live], g["truncated"][live, t])
         assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal((o.flags & 1)[live], g["dead"][live, t])
         assert np.array_equal(used[live], g["n_battles"][live, t])
+        assert np.array_equal(o.info()[live], g["info"][live, t])
