@@ -348,7 +348,47 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     if (tid == 0) tma_wait_read_all();
     return;
   }
-  if (p.obs_dtype == MG_OBS_U8) {
+  if (p.obs_tma) {
+    // large tiles: the static map leaves straight from the staged period, one TMA bulk store per period (full-line
+    // writes, no per-thread store instructions); the stores are spread over the CTA's threads, each waits for its own
+    // to be performed, and after the barrier every env's thread patches its agents' cells on top
+    const uint32_t elem = p.obs_dtype == MG_OBS_U8 ? 1u : 8u, reps = (uint32_t)p.tma_reps, Lb = (uint32_t)p.L * elem * reps;
+    uint8_t* src = s_period;
+    if (elem == 8 || reps > 1) {  // `reps` copies of the period in the observation dtype (float64 Maze / int64 CtF for the reference's dtypes):
+      src = s_obs;                // bulk stores of ~32 KB run closer to the write bandwidth than 4 KB ones
+      if (elem == 1) {
+        const int total16 = p.L16 * (int)reps;
+        int m = p.L16 == 1 ? 0 : tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * p.L16;   // tid mod L16
+        for (int i = tid; i < total16; i += kMapE) {
+          reinterpret_cast<uint4*>(src)[i] = reinterpret_cast<const uint4*>(s_period)[m];
+          m += p.tile_mod_L16; if (m >= p.L16) m -= p.L16;
+        }
+      } else {
+        const int total = p.L * (int)reps;
+        int m = tid;                // tid < L is not guaranteed for tiny maps
+        while (m >= p.L) m -= p.L;
+        const int step = kMapE % p.L;
+        for (int i = tid; i < total; i += kMapE) {
+          const uint8_t v = s_period[m];
+          if (FAMILY == MG_FAMILY_MAZE) reinterpret_cast<double*>(src)[i] = (double)v;
+          else reinterpret_cast<long long*>(src)[i] = (long long)v;
+          m += step; if (m >= p.L) m -= p.L;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+    }
+    uint8_t* g = static_cast<uint8_t*>(p.obs) + (size_t)e0 * cells * elem;
+    const size_t slab_bytes = (size_t)slab * elem;
+    const int nch = (int)(slab_bytes / Lb);
+    for (int c = tid; c < nch; c += kMapE) tma_store_1d(g + (size_t)c * Lb, src, Lb);
+    if (tid == 0 && (slab_bytes - (size_t)nch * Lb) >= (size_t)p.L * elem)   // whole periods left over by the big chunks
+      tma_store_1d(g + (size_t)nch * Lb, src, (uint32_t)((slab_bytes - (size_t)nch * Lb) / ((size_t)p.L * elem) * ((size_t)p.L * elem)));
+    tma_commit();
+    for (size_t k = (size_t)slab / p.L * p.L + tid; k < (size_t)slab; k += kMapE) put_obs(p, p.obs, e0 * cells + (long long)k, s_period[k % p.L]);  // ragged last tile
+    tma_wait_all();
+    __syncthreads();
+  } else if (p.obs_dtype == MG_OBS_U8) {
     const int L16 = p.L16;
     const long long chunks = slab / 16;
     uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.obs) + e0 * cells);  // e0*cells is a multiple of L
@@ -375,7 +415,7 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
       m += step; if (m >= p.L) m -= p.L;
     }
   }
-  __syncthreads();  // the tile's static fill is ordered before the per-env patches
+  if (!p.obs_tma) __syncthreads();  // the tile's static fill is ordered before the per-env patches
   if (tid < n_here)
     for (int i = 0; i < n; ++i) {
       const uint32_t w = ag[i * kMapE];
@@ -431,8 +471,27 @@ bool map_obs_staged(int cells, int obs_dtype) {
   static const bool off = [] { const char* v = std::getenv("MG_MAP_DIRECT"); return v && v[0] == '1'; }();
   return !off && obs_dtype == MG_OBS_U8 && (size_t)kMapE * cells <= 48 * 1024 && (kMapE * cells) % 16 == 0;
 }
+// tiles that are not staged stream the period with TMA bulk stores; the 8-byte dtypes need an 8-byte copy of it
+bool map_obs_tma(int L, int cells, int obs_dtype) {
+  static const bool off = [] { const char* v = std::getenv("MG_MAP_NO_TMA"); return v && v[0] == '1'; }();
+  if (off || map_obs_staged(cells, obs_dtype)) return false;
+  return obs_dtype == MG_OBS_U8 || (size_t)L * 8 <= 64 * 1024;
+}
+// copies of the period per bulk store: ~32 KB chunks, but never more than 1/16 of a tile (the copies must amortise)
+int map_tma_reps(int L, int cells, int obs_dtype) {
+  const size_t Lb = (size_t)L * (obs_dtype == MG_OBS_U8 ? 1 : 8), tile = (size_t)kMapE * cells * (obs_dtype == MG_OBS_U8 ? 1 : 8);
+  size_t r = 32768 / Lb;
+  if (r > tile / (16 * Lb)) r = tile / (16 * Lb);
+  return r < 1 ? 1 : (int)r;
+}
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
-  return (size_t)L + (size_t)4 * kMapE * n + (map_obs_staged(cells, obs_dtype) ? (size_t)kMapE * cells : 0) + 16;
+  size_t extra = 0;
+  if (map_obs_staged(cells, obs_dtype)) extra = (size_t)kMapE * cells;
+  else if (map_obs_tma(L, cells, obs_dtype)) {
+    const int reps = map_tma_reps(L, cells, obs_dtype);
+    if (obs_dtype != MG_OBS_U8 || reps > 1) extra = (size_t)L * (obs_dtype == MG_OBS_U8 ? 1 : 8) * reps;
+  }
+  return (size_t)L + (size_t)4 * kMapE * n + extra + 16;
 }
 int map_tile_envs() { return kMapE; }
 

@@ -26,6 +26,8 @@ struct MapParams {
   // battle tests restated in integers (bit-exact, computed on the host with the same double arithmetic):
   int d2_max;                              // largest squared distance d2 with sqrt((double)d2) <= battle_range (-1: none)
   unsigned long long thr_blue_home, thr_red_home, thr_even;  // blue wins iff u32 < ceil(p * 2^32), p = randomness / 1 - randomness / 0.5
+  int tma_reps;                            // copies of the period per bulk store (~32 KB chunks)
+  int obs_tma;                             // 1 = (not staged) the period streams out through TMA bulk stores
   int obs_staged;                          // 1 = the tile's u8 obs slab is assembled in shared memory (small maps)
   // state planes
   uint8_t* agents;   // [N_pad][row_bytes]: agent i at bytes 4i..4i+3 = x, y, dir, flags (bit0 terminated, bit1 collided)

@@ -27,6 +27,8 @@ cudaError_t launch_map(const MapParams& p, cudaStream_t st);
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype);
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype);
 bool map_obs_staged(int cells, int obs_dtype);
+bool map_obs_tma(int L, int cells, int obs_dtype);
+int map_tma_reps(int L, int cells, int obs_dtype);
 cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st);
 int map_tile_envs();
 }  // namespace mg
@@ -416,6 +418,8 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   };
   p.thr_blue_home = win_threshold(cfg->randomness); p.thr_red_home = win_threshold(1.0 - cfg->randomness); p.thr_even = win_threshold(0.5);
   p.obs_staged = mg::map_obs_staged(cells, cfg->obs_dtype) ? 1 : 0;
+  p.obs_tma = mg::map_obs_tma((int)L, cells, cfg->obs_dtype) ? 1 : 0;
+  p.tma_reps = mg::map_tma_reps((int)L, cells, cfg->obs_dtype);
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.field_map = env->d_map_tables + o_map; p.obs_period = env->d_map_tables + o_per; p.L = (int)L;
   p.background = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bg);

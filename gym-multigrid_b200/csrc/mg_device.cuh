@@ -166,6 +166,8 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... until the bulk stores of this thread have been PERFORMED (their global writes are complete), not just read
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Programmatic dependent launch (PDL): the next kernel in the stream may be scheduled while this one
 // drains; it blocks in pdl_wait() until every prerequisite grid has completed and flushed its writes.
