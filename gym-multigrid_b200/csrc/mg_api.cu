@@ -38,6 +38,7 @@ int map_tile_envs();
 #include "generic_params.cuh"
 namespace mg {
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
+cudaError_t launch_view6(const View6Params& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
 size_t view_smem_bytes(const ViewParams& p);
 int view_max();
@@ -706,10 +707,23 @@ extern "C" int mg_encode(mg_env* env, const void* state, uint8_t* obs, void* str
 extern "C" int mg_gen_obs(mg_env* env, const void* state, const uint8_t* dirs, int view_size, int see_through_walls,
                           uint8_t* out, void* stream) {
   if (!env || !state || !out) return fail(env, "mg_gen_obs: null argument");
-  if (env->family == MG_FAMILY_CTF) return fail(env, "mg_gen_obs: Collect and Maze families only");
+  if (env->family == MG_FAMILY_CTF || env->family == MG_FAMILY_WILDFIRE) return fail(env, "mg_gen_obs: Collect, Maze and generic families only");
   if (view_size < 1 || view_size > mg::view_max()) return fail(env, "mg_gen_obs: view_size must be in [1, 15]");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if (env->family == MG_FAMILY_GENERIC) {   // DefaultWorld, encode_dim 6: out u8 [N][A][V][V][6]
+    if (reinterpret_cast<uintptr_t>(out) & 1) return fail(env, "mg_gen_obs: out must be 2-byte aligned");
+    mg::View6Params q;
+    std::memset(&q, 0, sizeof q);
+    const uint8_t* gsb = static_cast<const uint8_t*>(state);
+    q.W = env->gcfg.width; q.H = env->gcfg.height; q.cells = q.W * q.H; q.A = env->gcfg.num_agents; q.N = env->gcfg.num_envs;
+    q.V = view_size; q.see_through = see_through_walls != 0;
+    q.gcell = gsb + env->plane_off[MG_GEN_PLANE_CELL]; q.gstate = gsb + env->plane_off[MG_GEN_PLANE_STATE];
+    q.pos = gsb + env->plane_off[MG_GEN_PLANE_POS]; q.dirs = dirs; q.out = out;
+    if ((ce = mg::launch_view6(q, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "view6_kernel", ce);
+    env->launches += 1;
+    return 0;
+  }
   mg::ViewParams p;
   std::memset(&p, 0, sizeof p);
   const uint8_t* s = static_cast<const uint8_t*>(state);

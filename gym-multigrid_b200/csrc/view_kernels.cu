@@ -416,6 +416,93 @@ cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, l
   return cudaGetLastError();
 }
 
+// MultiGridEnv.gen_obs with DefaultWorld (encode_dim 6; generic family): one thread per view, runtime V.  Wall and a
+// closed / locked Door block sight (object.py:178-179, 223-224), out-of-grid cells are grey walls (grid.py:124-127), the
+// agent's own cell (view cell (V/2, V-1)) carries the is_self byte (grid.py:279-281).  No shipped env reaches this path.
+__global__ void __launch_bounds__(128) view6_kernel(const __grid_constant__ View6Params p) {
+  constexpr int G_WALL = 2, G_DOOR = 4, G_AGENT = 10;   // DefaultWorld.OBJECT_TO_IDX (world.py:37-51)
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= p.N * p.A) return;
+  const int V = p.V, hs = V / 2, W = p.W, H = p.H;
+  const long long e = v / p.A;
+  const uint8_t* gc = p.gcell + e * p.cells;
+  const uint8_t* gs = p.gstate + e * p.cells;
+  const int x = p.pos[v * 2], y = p.pos[v * 2 + 1];
+  const int dir = p.dirs ? (p.dirs[v] & 3) : (gs[x * H + y] & 3);
+  // world cell of view cell (a, b): slice + (dir + 1) x rotate_left folded into direct indices (same table as view_kernel)
+  auto world = [&](int a, int b, int& wx, int& wy) {
+    if (dir == 0)      { wx = x + V - 1 - b;      wy = y - hs + a; }
+    else if (dir == 1) { wx = x - hs + V - 1 - a; wy = y + V - 1 - b; }
+    else if (dir == 2) { wx = x - V + 1 + b;      wy = y - hs + V - 1 - a; }
+    else               { wx = x - hs + a;         wy = y - V + 1 + b; }
+  };
+  uint32_t msk[kViewMax + 1];
+  const uint32_t FULL = (1u << V) - 1u;
+  if (p.see_through) {
+    for (int b = 0; b < V; ++b) msk[b] = FULL;
+  } else {  // process_vis (grid.py:286-323) with the bit-parallel row flood of view_fast_kernel
+    for (int b = 0; b < V; ++b) msk[b] = 0;
+    msk[V - 1] = 1u << hs;
+    for (int j = V - 1; j >= 0; --j) {
+      uint32_t opq = 0;
+      for (int a = 0; a < V; ++a) {
+        int wx, wy;
+        world(a, j, wx, wy);
+        bool o = true;   // outside the grid: Wall
+        if (wx >= 0 && wy >= 0 && wx < W && wy < H) {
+          const int type = gc[wx * H + wy] & 15;
+          o = type == G_WALL || (type == G_DOOR && gs[wx * H + wy] != 0);
+        }
+        opq |= (uint32_t)o << a;
+      }
+      const uint32_t clear = ~opq & FULL;
+      uint32_t m = msk[j];
+      uint32_t F = m & clear, P = clear;
+      F |= P & (F << 1); P &= P << 1;
+      F |= P & (F << 2); P &= P << 2;
+      F |= P & (F << 4); P &= P << 4;
+      F |= P & (F << 8);
+      F &= FULL >> 1;
+      m |= F << 1;
+      uint32_t up = F | (F << 1);
+      uint32_t G = m & clear; P = clear;
+      G |= P & (G >> 1); P &= P >> 1;
+      G |= P & (G >> 2); P &= P >> 2;
+      G |= P & (G >> 4); P &= P >> 4;
+      G |= P & (G >> 8);
+      G &= ~1u;
+      m |= G >> 1;
+      up |= G | (G >> 1);
+      msk[j] = m;
+      if (j > 0) msk[j - 1] |= up;
+    }
+  }
+  uint16_t* o = reinterpret_cast<uint16_t*>(p.out + v * (long long)V * V * 6);
+  for (int a = 0; a < V; ++a)
+    for (int b = 0; b < V; ++b) {
+      uint16_t w0 = 0, w1 = 0, w2 = 0;   // unseen
+      if ((msk[b] >> a) & 1u) {
+        int wx, wy;
+        world(a, b, wx, wy);
+        uint32_t c = G_WALL | (7u << 4), st = 0;
+        if (wx >= 0 && wy >= 0 && wx < W && wy < H) { c = gc[wx * H + wy]; st = gs[wx * H + wy]; }
+        const uint32_t type = c & 15u;
+        w0 = (uint16_t)(type | ((c >> 4) << 8));
+        if (type == G_DOOR) w1 = (uint16_t)st;
+        else if (type == G_AGENT) w2 = (uint16_t)((st & 3u) | ((a == hs && b == V - 1) ? 0x100u : 0u));
+      }
+      o[(a * V + b) * 3] = w0; o[(a * V + b) * 3 + 1] = w1; o[(a * V + b) * 3 + 2] = w2;
+    }
+}
+
+cudaError_t launch_view6(const View6Params& p, cudaStream_t st) {
+  const long long views = p.N * p.A;
+  view6_kernel<<<(unsigned)((views + 127) / 128), 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 static bool view_is_fast(const ViewParams& p) {
   static const bool off = [] { const char* v = std::getenv("MG_VIEW_GENERIC"); return v && v[0] == '1'; }();
   if (off || !(p.V == 3 || p.V == 5 || p.V == 7)) return false;

@@ -22,4 +22,15 @@ struct ViewParams {
   int out_bulk_ok;
 };
 
+// MultiGridEnv.gen_obs for the generic (DefaultWorld, encode_dim 6) family
+struct View6Params {
+  int W, H, cells, A, V, see_through;
+  long long N;
+  const uint8_t* gcell;   // [N_pad][cells] type | colour << 4
+  const uint8_t* gstate;  // [N_pad][cells] door state / agent dir
+  const uint8_t* pos;     // [N_pad][A][2]
+  const uint8_t* dirs;    // [N][A] override, or null = the dir stored with the agent cell
+  uint8_t* out;           // [N][A][V][V][6]
+};
+
 }  // namespace mg

@@ -135,6 +135,24 @@ class GenericVecEnv:
                                                    "_final_observation": (self._term | self._trunc).view(torch.bool)}
         return self._obs, self._rewards, self._term.view(torch.bool), self._trunc.view(torch.bool), info
 
+    def gen_obs(self, view_size=7, see_through_walls=False, dirs=None, out=None):
+        """Partial observations (MultiGridEnv.gen_obs, multigrid.py:485-532) with encode_dim 6: u8 [N, A, V, V, 6], the
+        egocentric V x V window in front of each agent (walls and closed / locked doors occlude)."""
+        V = int(view_size)
+        if out is None:
+            out = torch.empty((self.num_envs, self.num_agents, V, V, 6), dtype=torch.uint8, device=self.device)
+        d = None if dirs is None else torch.as_tensor(dirs, device=self.device).to(torch.uint8).contiguous()
+        self._check(self._lib.mg_gen_obs(self._h, _ptr(self.state), _ptr(d), V, int(bool(see_through_walls)), _ptr(out), self._stream()))
+        return out
+
+    def set_state_from_obs(self, obs6, agent_pos):
+        """Load a live state (not the reset snapshot) from `encode_for_agents` arrays [N, W, H, 6] + positions (validation)."""
+        keep = {k: self._planes[k].clone() for k in ("init_cell", "init_state", "init_pos")}
+        self.set_layout(obs6, agent_pos)
+        for live, init in (("cell", "init_cell"), ("state", "init_state"), ("pos", "init_pos")):
+            self._planes[live].copy_(self._planes[init])
+            self._planes[init].copy_(keep[init])
+
     def enable_final_observation(self, enable=True):
         self._final_obs = torch.zeros_like(self._obs) if enable else None
 

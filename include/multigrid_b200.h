@@ -128,7 +128,9 @@ int mg_encode(mg_env* env, const void* state_dev, uint8_t* obs_dev, void* stream
  * dirs_dev: u8 [N][A] agent directions or NULL (Collect: 3, the only direction its agents ever have; Maze: the
  * state's dir plane).  Collect: cells outside the grid are grey walls (grid.py:124-127).  Maze (a composition the
  * reference does not ship: MazeWorld has no wall, world.py:81-91): outside cells are an opaque obstacle-coloured
- * filler (3, 7, 1) -- an extension, parity unpinned for that one code. */
+ * filler (3, 7, 1) -- an extension, parity unpinned for that one code.  Generic family (DefaultWorld, encode_dim 6):
+ * out u8 [N][A][V][V][6]; walls and closed / locked doors block sight (object.py:178-179, 223-224); dirs NULL = the
+ * dir stored with each agent's cell. */
 int mg_gen_obs(mg_env* env, const void* state_dev, const uint8_t* dirs_dev, int view_size, int see_through_walls,
                uint8_t* out_dev, void* stream);
 

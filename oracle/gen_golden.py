@@ -197,6 +197,16 @@ def gen_toroid():
         print(f"{stem}: {n} states, toroid {r['toroid'].shape} {r['toroid'].dtype}, {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def gen_generic_partial():
+    for stem, size, A, n in (("partial6_9x9_a3", 9, 3, 120), ("partial6_12x12_a5", 12, 5, 60)):
+        r = rh.record_generic_partial(size, A, 31, n)
+        r["meta_size"], r["meta_num_agents"] = np.array(size), np.array(A)
+        path = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path, **r)
+        print(f"{stem}: {len(r['V'])} states x {A} agents, V in {sorted(set(r['V'].tolist()))}, "
+              f"see_through in {sorted(set(r['see_through'].tolist()))}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def gen_generic():
     """Base-class MultiGridEnv.step + encode_dim-6 encode_for_agents on a DefaultWorld env assembled from reference classes."""
     for stem, size, A, max_steps, episodes in (("generic_9x9_a3", 9, 3, 40, 24), ("generic_12x12_a5", 12, 5, 60, 12),
@@ -213,7 +223,7 @@ def gen_generic():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -228,3 +238,5 @@ if __name__ == "__main__":
         gen_toroid()
     if "generic" in which:
         gen_generic()
+    if "generic_partial" in which:
+        gen_generic_partial()

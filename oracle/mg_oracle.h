@@ -246,6 +246,9 @@ int oc_generic_step(int64_t N, int W, int H, int A, int max_steps, uint8_t* gcel
                     int32_t* step_count, const int8_t* actions, const uint8_t* order, uint8_t* obs /*[N][A][W][H][6]*/,
                     double* rewards, uint8_t* terminated, uint8_t* truncated, int32_t* status);
 void oc_generic_encode(int64_t N, int W, int H, int A, const uint8_t* gcell, const uint8_t* gstate, const uint8_t* pos, uint8_t* obs);
+/* MultiGridEnv.gen_obs with DefaultWorld (encode_dim 6): u8 [N][A][V][V][6]; dirs NULL = the dir stored with the agent cell */
+void oc_partial_view6(int64_t N, int W, int H, int A, int V, int see_through_walls, const uint8_t* gcell, const uint8_t* gstate,
+                      const uint8_t* pos, const uint8_t* dirs, uint8_t* out);
 #ifdef __cplusplus
 }
 #endif

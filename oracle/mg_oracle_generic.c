@@ -1,5 +1,7 @@
 /* mg_oracle_generic.c -- CPU restatement of the base-class MultiGridEnv.step with DefaultWorld.
  * TEST INFRASTRUCTURE ONLY (see mg_oracle.h). */
+#include <string.h>
+
 #include "mg_oracle.h"
 
 enum { G_EMPTY = 1, G_DOOR = 4, G_GOAL = 8, G_AGENT = 10 }; /* DefaultWorld.OBJECT_TO_IDX world.py:37-51 */
@@ -57,4 +59,71 @@ int oc_generic_step(int64_t N, int W, int H, int A, int max_steps, uint8_t* gcel
   }
   if (obs) oc_generic_encode(N, W, H, A, gcell, gstate, pos, obs);
   return 0;
+}
+
+/* MultiGridEnv.gen_obs for DefaultWorld (encode_dim 6), restated step by step as the reference performs it:
+ * Agent.get_view_exts (agent.py:294-324) -> Grid.slice (grid.py:111-130, out of bounds = Wall) -> (dir + 1) x Grid.rotate_left
+ * (grid.py:97-109) -> Grid.process_vis (grid.py:286-323; Wall and a closed / locked Door block sight, object.py:178-179, 223-224)
+ * -> Grid.encode_for_agents with agent_pos = (V // 2, V - 1) (grid.py:254-284).  out: u8 [N][A][V][V][6].
+ * `dirs` overrides the agents' directions (NULL = the dir stored with the agent cell). */
+void oc_partial_view6(int64_t N, int W, int H, int A, int V, int see_through_walls, const uint8_t* gcell, const uint8_t* gstate,
+                      const uint8_t* pos, const uint8_t* dirs, uint8_t* out) {
+  enum { VMAX = 32, G_WALL = 2 };
+  if (V < 1 || V > VMAX) return;
+  const uint8_t WALL_GREY = (uint8_t)(G_WALL | (7 << 4)); /* Wall(world): colour "grey" = index 7 (constants.py:8-19) */
+  for (int64_t e = 0; e < N; ++e)
+    for (int k = 0; k < A; ++k) {
+      const uint8_t* gc = gcell + e * W * H; const uint8_t* gs = gstate + e * W * H;
+      const int px = pos[(e * A + k) * 2], py = pos[(e * A + k) * 2 + 1];
+      const int dir = dirs ? dirs[e * A + k] : (gs[px * H + py] & 3);
+      int topX, topY;
+      if (dir == 0) { topX = px; topY = py - V / 2; }
+      else if (dir == 1) { topX = px - V / 2; topY = py; }
+      else if (dir == 2) { topX = px - V + 1; topY = py - V / 2; }
+      else { topX = px - V / 2; topY = py - V + 1; }
+      uint8_t c0[VMAX][VMAX], s0[VMAX][VMAX], c1[VMAX][VMAX], s1[VMAX][VMAX];
+      for (int j = 0; j < V; ++j) /* slice */
+        for (int i = 0; i < V; ++i) {
+          const int x = topX + i, y = topY + j;
+          if (x >= 0 && x < W && y >= 0 && y < H) { c0[i][j] = gc[x * H + y]; s0[i][j] = gs[x * H + y]; }
+          else { c0[i][j] = WALL_GREY; s0[i][j] = 0; }
+        }
+      for (int r = 0; r < dir + 1; ++r) { /* rotate_left: new(j, V-1-i) = old(i, j) */
+        for (int i = 0; i < V; ++i)
+          for (int j = 0; j < V; ++j) { c1[j][V - 1 - i] = c0[i][j]; s1[j][V - 1 - i] = s0[i][j]; }
+        memcpy(c0, c1, sizeof c0); memcpy(s0, s1, sizeof s0);
+      }
+      uint8_t mask[VMAX][VMAX];
+      memset(mask, see_through_walls ? 1 : 0, sizeof mask);
+      if (!see_through_walls) {
+        mask[V / 2][V - 1] = 1;
+        for (int j = V - 1; j >= 0; --j) {
+          for (int i = 0; i < V - 1; ++i) {
+            if (!mask[i][j]) continue;
+            const int type = c0[i][j] & 15;
+            if (type == G_WALL || (type == G_DOOR && s0[i][j] != 0)) continue; /* not see_behind() */
+            mask[i + 1][j] = 1;
+            if (j > 0) { mask[i + 1][j - 1] = 1; mask[i][j - 1] = 1; }
+          }
+          for (int i = V - 1; i >= 1; --i) {
+            if (!mask[i][j]) continue;
+            const int type = c0[i][j] & 15;
+            if (type == G_WALL || (type == G_DOOR && s0[i][j] != 0)) continue;
+            mask[i - 1][j] = 1;
+            if (j > 0) { mask[i - 1][j - 1] = 1; mask[i][j - 1] = 1; }
+          }
+        }
+      }
+      uint8_t* o = out + ((e * A + k) * V * V) * 6;
+      for (int i = 0; i < V; ++i)
+        for (int j = 0; j < V; ++j) {
+          uint8_t* q = o + (i * V + j) * 6;
+          q[0] = q[1] = q[2] = q[3] = q[4] = q[5] = 0; /* unseen */
+          if (!mask[i][j]) continue;
+          const int type = c0[i][j] & 15;
+          q[0] = (uint8_t)type; q[1] = c0[i][j] >> 4;
+          if (type == G_DOOR) q[2] = s0[i][j];
+          else if (type == G_AGENT) { q[4] = s0[i][j] & 3; q[5] = (i == V / 2 && j == V - 1); }
+        }
+    }
 }

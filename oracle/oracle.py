@@ -450,6 +450,14 @@ class GenericOracle:
         lib().oc_generic_encode(C.c_int64(self.N), self.W, self.H, self.A, _p(self.gcell), _p(self.gstate), _p(self.pos), _p(obs))
         return obs
 
+    def partial_views(self, V, see_through_walls=False, dirs=None):
+        """MultiGridEnv.gen_obs (encode_dim 6): u8 [N, A, V, V, 6]."""
+        out = np.zeros((self.N, self.A, V, V, 6), np.uint8)
+        d = None if dirs is None else np.ascontiguousarray(dirs, np.uint8)
+        lib().oc_partial_view6(C.c_int64(self.N), self.W, self.H, self.A, int(V), int(bool(see_through_walls)), _p(self.gcell),
+                               _p(self.gstate), _p(self.pos), _p(d), _p(out))
+        return out
+
     def step(self, actions, order):
         actions = np.ascontiguousarray(actions, np.int8).reshape(self.N, self.A)
         order = np.ascontiguousarray(order, np.uint8).reshape(self.N, self.A)

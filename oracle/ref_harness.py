@@ -551,3 +551,35 @@ def record_generic_episode(size, n_agents, max_steps, seed, action_rng):
     for k, v in rec.items():
         out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
     return out
+
+
+def record_generic_partial(size, n_agents, seed, n_samples, view_sizes=(3, 5, 7)):
+    """Reference partial observations with encode_dim 6 (DefaultWorld): gen_obs_grid (multigrid.py:485-515) +
+    encode_for_agents (grid.py:254-284) on states of the DefaultWorld env of `make_generic_env` (doors open / closed /
+    locked, walls, every other object type).  As in record_partial_views the two steps of `gen_obs` are called directly
+    (its own call passes one argument too many, multigrid.py:526-528)."""
+    env = make_generic_env(size, n_agents, 10 ** 6, seed)
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env.reset(seed=seed)
+    A = n_agents
+    out = dict(obs6=[], pos=[], V=[], see_through=[], views=[])
+    for s in range(n_samples):
+        for _ in range(int(rng.integers(1, 6))):
+            _, _, term, _, _ = env.step([int(a) for a in rng.choice(4, size=A, p=[0.1, 0.25, 0.25, 0.4])])
+            if term:
+                env.reset(seed=seed + s)
+        V = int(rng.choice(view_sizes))
+        st = bool(rng.integers(0, 2))
+        for a in env.agents:
+            a.view_size = V
+        env.see_through_walls = st
+        grids, masks = env.gen_obs_grid()
+        views = [g.encode_for_agents(agent_pos=(V // 2, V - 1), vis_mask=m) for g, m in zip(grids, masks)]
+        pad = np.zeros((A, max(view_sizes), max(view_sizes), 6), np.uint8)
+        for k, v in enumerate(views):
+            pad[k, :V, :V] = v
+        out["obs6"].append(env.grid.encode_for_agents(agent_pos=env.agents[0].pos).copy())
+        out["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+        out["V"].append(V); out["see_through"].append(st); out["views"].append(pad)
+    return {k: np.array(v) for k, v in out.items()}

@@ -109,3 +109,37 @@ def test_generic_philox_orders_are_shard_invariant_and_bad_actions_flagged(cuda_
     env.step(torch.full((4, A), 6, dtype=torch.int8, device=cuda_device))      # toggle: the reference raises (multigrid.py:447)
     assert env.status() & 8
     env.close()
+
+
+@pytest.mark.parametrize("stem", ["partial6_9x9_a3", "partial6_12x12_a5"])
+def test_generic_partial_views_match_reference(stem, cuda_device):
+    """encode_dim-6 gen_obs: the reference's gen_obs_grid + encode_for_agents outputs on recorded DefaultWorld states."""
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    S, A = int(g["meta_size"]), int(g["meta_num_agents"])
+    for V in (3, 5, 7):
+        for st in (False, True):
+            sel = np.where((g["V"] == V) & (g["see_through"] == st))[0]
+            if len(sel) == 0:
+                continue
+            env = mg.make_generic_vec(len(sel), S, num_agents=A, autoreset=False)
+            env.set_state_from_obs(g["obs6"][sel], g["pos"][sel])
+            assert np.array_equal(_np(env.gen_obs(V, st)), g["views"][sel][:, :, :V, :V]), f"V={V} see_through={st}"
+            env.close()
+
+
+@pytest.mark.parametrize("V", [1, 2, 4, 9, 15])
+def test_generic_partial_views_match_oracle_any_size(V, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden("partial6_12x12_a5")
+    n, A, S = 700, 5, 12
+    idx = np.arange(n) % len(g["V"])
+    env = mg.make_generic_vec(n, S, num_agents=A, autoreset=False)
+    env.set_state_from_obs(g["obs6"][idx], g["pos"][idx])
+    o = oc.GenericOracle(n, S, S, A, 100)
+    o.set_state_from_obs(g["obs6"][idx], g["pos"][idx])
+    dirs = np.random.default_rng(V).integers(0, 4, size=(n, A)).astype(np.uint8)
+    for st in (False, True):
+        assert np.array_equal(_np(env.gen_obs(V, st)), o.partial_views(V, st))
+        assert np.array_equal(_np(env.gen_obs(V, st, dirs=dirs)), o.partial_views(V, st, dirs=dirs))
+    env.close()

@@ -38,3 +38,21 @@ def test_generic_bad_action_sets_status():
     o.pos[0, 0] = (2, 2)
     o.step(np.array([[5]], np.int8), np.array([[0]], np.uint8))      # toggle: the reference raises (multigrid.py:447)
     assert o.status.value & 8      # OC_ERR_BAD_ACTION
+
+
+@pytest.mark.parametrize("stem", ["partial6_9x9_a3", "partial6_12x12_a5"])
+def test_generic_partial_views_match_reference(stem):
+    """encode_dim-6 partial observations (gen_obs_grid + encode_for_agents) on recorded DefaultWorld states."""
+    g = load_golden(stem)
+    S, A = int(g["meta_size"]), int(g["meta_num_agents"])
+    checked = 0
+    for V in (3, 5, 7):
+        for st in (False, True):
+            sel = np.where((g["V"] == V) & (g["see_through"] == st))[0]
+            if len(sel) == 0:
+                continue
+            o = oc.GenericOracle(len(sel), S, S, A, 100)
+            o.set_state_from_obs(g["obs6"][sel], g["pos"][sel])
+            assert np.array_equal(o.partial_views(V, st), g["views"][sel][:, :, :V, :V]), f"V={V} see_through={st}"
+            checked += len(sel)
+    assert checked == len(g["V"])
