@@ -111,11 +111,12 @@ __device__ __forceinline__ void maze_step_one(const MapParams& p, int a, uint32_
 }
 
 // CtFMvNEnv.step / Ctf1v1Env.step for ONE env.  `terr` = the map in observation order (s_period), `ag` as in reset_one.
-template <int MODE, typename NIB>
+// NB / NR: compile-time team sizes of the common configurations (all loops unroll), 0 = read them from the parameters.
+template <int MODE, typename NIB, int NB, int NR>
 __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, const int8_t* blue_act, const uint8_t* terr,
                                              uint32_t* ag, int4& h, Rng<MODE>& r, double& rew, bool& term, bool& trunc,
                                              int& err) {
-  const int S = p.S, nb = p.nb, nr = p.nr, n = p.n;
+  const int S = p.S, nb = NB ? NB : p.nb, nr = NB ? NR : p.nr, n = nb + nr;
   h.x += 1;  // ctf.py:1295
   // actions and order, one nibble per agent (n <= 16); action nibble 15 = outside the action set
   NIB acts = 0, order = 0;   // NIB = uint32_t when n <= 8, else 64 bits
@@ -268,8 +269,10 @@ __global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapP
     } else {
       double rew; bool term, trunc;
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
-      else if (n <= 8) ctf_step_one<MODE, uint32_t>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
-      else ctf_step_one<MODE, unsigned long long>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
+      else if (p.nb == 2 && p.nr == 2) ctf_step_one<MODE, uint32_t, 2, 2>(p, e, p.actions + e * 2, s_period, ag, h, r, rew, term, trunc, err);
+      else if (p.nb == 1 && p.nr == 1) ctf_step_one<MODE, uint32_t, 1, 1>(p, e, p.actions + e, s_period, ag, h, r, rew, term, trunc, err);
+      else if (n <= 8) ctf_step_one<MODE, uint32_t, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
+      else ctf_step_one<MODE, unsigned long long, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       p.rewards[e] = rew; p.terminated[e] = term; p.truncated[e] = trunc;
       want_reset = done = p.autoreset && (term || trunc);  // same-step autoreset
     }
