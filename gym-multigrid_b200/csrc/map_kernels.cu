@@ -220,8 +220,11 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
   else put<long long>(base, idx, v);
 }
 
-template <int FAMILY, int MODE>
-__global__ void __launch_bounds__(kMapE) map_kernel(const __grid_constant__ MapParams p) {
+// MINB: minimum resident CTAs per SM the register allocation must allow.  8 (64 registers, a few spills) wins when many
+// waves of tiles keep every SM full (>= 256 K envs); 1 (no cap, no spills) has the shorter dependent chain and wins for
+// launches of a wave or two, which are latency-bound.
+template <int FAMILY, int MODE, int MINB>
+__global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint8_t s_done[kMapE];
@@ -498,7 +501,7 @@ size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
 }
 int map_tile_envs() { return kMapE; }
 
-template <int FAMILY, int MODE>
+template <int FAMILY, int MODE, int MINB>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   const size_t smem = map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
   cudaLaunchConfig_t cfg = {};
@@ -508,21 +511,33 @@ static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = map_pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE>, p);
+  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB>, p);
+}
+
+template <int FAMILY, int MODE>
+static cudaError_t configure_pair(int smem) {
+  cudaError_t e = cudaFuncSetAttribute((const void*)map_kernel<FAMILY, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)map_kernel<FAMILY, MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
   const int smem = (int)map_smem_bytes(L, n, cells, obs_dtype);
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute((const void*)map_kernel<MG_FAMILY_MAZE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)map_kernel<MG_FAMILY_MAZE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)map_kernel<MG_FAMILY_CTF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)map_kernel<MG_FAMILY_CTF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if ((e = configure_pair<MG_FAMILY_MAZE, 0>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_MAZE, 1>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 0>(smem)) != cudaSuccess) return e;
+  return configure_pair<MG_FAMILY_CTF, 1>(smem);
+}
+
+template <int FAMILY, int MODE>
+static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
+  return p.N >= 262144 ? launch_one<FAMILY, MODE, 8>(p, st) : launch_one<FAMILY, MODE, 1>(p, st);
 }
 
 cudaError_t launch_map(const MapParams& p, cudaStream_t st) {
-  if (p.family == MG_FAMILY_MAZE) return p.rng_mode == 0 ? launch_one<MG_FAMILY_MAZE, 0>(p, st) : launch_one<MG_FAMILY_MAZE, 1>(p, st);
-  return p.rng_mode == 0 ? launch_one<MG_FAMILY_CTF, 0>(p, st) : launch_one<MG_FAMILY_CTF, 1>(p, st);
+  if (p.family == MG_FAMILY_MAZE) return p.rng_mode == 0 ? launch_by_size<MG_FAMILY_MAZE, 0>(p, st) : launch_by_size<MG_FAMILY_MAZE, 1>(p, st);
+  return p.rng_mode == 0 ? launch_by_size<MG_FAMILY_CTF, 0>(p, st) : launch_by_size<MG_FAMILY_CTF, 1>(p, st);
 }
 
 }  // namespace mg

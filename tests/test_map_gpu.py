@@ -144,6 +144,33 @@ def test_ctf_philox_matches_oracle(nb, nr, n, pen, cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("family", ["ctf", "maze"])
+def test_large_batch_kernel_variant_matches_oracle(family, cuda_device):
+    """Launches of >= 262 144 envs take the 8-CTAs-per-SM register allocation of map_kernel: same results, ragged last tile."""
+    import gym_multigrid_b200 as mg
+    n = 262144 + 77
+    if family == "ctf":
+        fm = load_golden("ctf_2v2")["field_map"]
+        env = mg.make_ctf_vec(n, fm, max_steps=12, seed=4, env_id_base=1)
+        o = oc.CtfOracle(fm, n, 2, 2, max_steps=12)
+    else:
+        fm = load_golden("maze_board13")["field_map"]
+        env = mg.make_maze_vec(n, fm, max_steps=12, seed=4, env_id_base=1)
+        o = oc.MazeOracle(fm, n, max_steps=12)
+    r = oc.map_rng(mode=1, seed=4, env_id_base=1)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    for t in range(16):
+        act = torch.randint(0, 5, (n, 2) if family == "ctf" else (n,), generator=gen, device=cuda_device, dtype=torch.int8)
+        obs, rew, term, trunc, _ = env.step(act)
+        oo, orew, oterm, otrunc = o.step(_np(act), r, autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+    assert np.array_equal(_np(env.agent_pos), o.pos) and env.status() == 0 and int(env.episode_count.min()) >= 2
+    env.close()
+
+
 def test_ctf_other_observation_options_and_host_path(cuda_device):
     import gym_multigrid_b200 as mg
     g = load_golden("ctf_2v2")
