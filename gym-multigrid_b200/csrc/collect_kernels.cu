@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "mg_device.cuh"
+#include "smem_config.h"
 
 namespace mg {
 
@@ -501,7 +502,7 @@ static bool pdl_enabled() {
 }
 
 static cudaError_t set_smem(const void* fn, size_t bytes) {
-  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return raise_smem_limit(fn, bytes);
 }
 
 int num_tile_variants() { return kNumTiles; }

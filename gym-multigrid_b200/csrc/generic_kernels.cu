@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "mg_device.cuh"
+#include "smem_config.h"
 #include "generic_params.cuh"
 
 namespace mg {
@@ -186,7 +187,7 @@ int generic_tile_envs() { return kGenE; }
 size_t generic_smem_bytes(int A, int cells) { return gen_smem_bytes(A, cells); }
 
 cudaError_t configure_generic_kernel(int A, int cells) {
-  return cudaFuncSetAttribute((const void*)generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem_bytes(A, cells));
+  return raise_smem_limit((const void*)generic_kernel, (size_t)gen_smem_bytes(A, cells));
 }
 
 cudaError_t launch_generic(const GenericParams& p, cudaStream_t st) {

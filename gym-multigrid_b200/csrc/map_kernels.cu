@@ -19,7 +19,9 @@
 #include <cstdlib>
 
 #include "mg_device.cuh"
+#include "smem_config.h"
 #include "map_params.cuh"
+#include "view_device.cuh"
 
 namespace mg {
 
@@ -229,9 +231,11 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint8_t s_done[kMapE];
   const int tid = threadIdx.x, n = p.n, cells = p.cells;
-  uint8_t* s_period = smem_raw;                                                     // [L]
-  uint32_t* s_ag = reinterpret_cast<uint32_t*>(smem_raw + p.L);                     // [n][kMapE] agent words, transposed
-  uint8_t* s_obs = smem_raw + p.L + (size_t)n * kMapE * 4;                          // [kMapE][cells] (staged tiles only)
+  const bool view_mode = FAMILY == MG_FAMILY_MAZE && p.view_V != 0;                 // obs = partial views (gen_obs) instead of the map
+  const int head = view_mode ? p.map_padded_bytes : p.L;
+  uint8_t* s_period = smem_raw;                                                     // [L], or the padded packed map in view mode
+  uint32_t* s_ag = reinterpret_cast<uint32_t*>(smem_raw + head);                    // [n][kMapE] agent words, transposed
+  uint8_t* s_obs = smem_raw + head + (size_t)n * kMapE * 4;                         // [kMapE][cells] (staged tiles) / the tile's views
   const long long e0 = (long long)blockIdx.x * kMapE;
   const int n_here = (int)min((long long)kMapE, p.N - e0);
   const long long e = e0 + tid;
@@ -240,7 +244,10 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   pdl_launch_dependents();
   __syncthreads();
   pdl_wait();
-  if (tid == 0) { mbar_expect_tx(&bar, (uint32_t)p.L); tma_load_1d(s_period, p.obs_period, (uint32_t)p.L, &bar); }
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)head);
+    tma_load_1d(s_period, view_mode ? p.map_padded : p.obs_period, (uint32_t)head, &bar);
+  }
 
   // ---- the env's agent row (padded to row_bytes = 4 * 2^k) and header; state planes are padded to whole tiles
   uint32_t* ag = s_ag + tid;
@@ -326,8 +333,36 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     }
   }
 
-  // ---- observation: static map for the whole tile, then the agents on top
   if (!p.obs) return;
+  // ---- Maze partial-observation mode: this env's egocentric view (fused MazeSingleAgentEnv.step + MultiGridEnv.gen_obs)
+  if (view_mode) {
+    const int V = p.view_V, VV3 = V * V * 3;
+    if (tid < n_here) {
+      const uint32_t w = ag[0];
+      const int x = ag_x(w), y = ag_y(w), dir = (int)((w >> 16) & 3u);
+      const uint32_t agent_cell = (uint32_t)p.view_agent | ((uint32_t)dir << 6);
+      int x0, y0, sa, sb;
+      if (V == 7) {
+        view_geometry<7>(x, y, dir, p.pitch, x0, y0, sa, sb);
+        view_compute_store<false, 7>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+      } else if (V == 5) {
+        view_geometry<5>(x, y, dir, p.pitch, x0, y0, sa, sb);
+        view_compute_store<false, 5>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+      } else {
+        view_geometry<3>(x, y, dir, p.pitch, x0, y0, sa, sb);
+        view_compute_store<false, 3>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    const uint32_t bytes = (uint32_t)n_here * VV3, bulk = bytes & ~15u;
+    uint8_t* g = static_cast<uint8_t*>(p.obs) + (size_t)e0 * VV3;   // 128 * 3 * V * V is a multiple of 16
+    if (tid == 0 && bulk) { tma_store_1d(g, s_obs, bulk); tma_commit(); }
+    for (uint32_t k = bulk + tid; k < bytes; k += kMapE) g[k] = s_obs[k];
+    if (tid == 0) tma_wait_read_all();
+    return;
+  }
+  // ---- observation: static map for the whole tile, then the agents on top
   const long long slab = (long long)n_here * cells;  // elements in this tile's obs slab
   if (p.obs_staged) {  // u8, small map: assemble the tile in shared memory, one TMA bulk store
     const int L16 = p.L16, chunks = kMapE * cells / 16;
@@ -490,6 +525,14 @@ int map_tma_reps(int L, int cells, int obs_dtype) {
   if (r > tile / (16 * Lb)) r = tile / (16 * Lb);
   return r < 1 ? 1 : (int)r;
 }
+size_t map_view_smem_bytes(int padded_bytes, int V) { return (size_t)padded_bytes + (size_t)4 * kMapE + (size_t)kMapE * V * V * 3 + 16; }
+cudaError_t configure_map_view_mode(size_t smem) {
+  cudaError_t e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 0, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 0, 8>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  return raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 8>, (size_t)smem);
+}
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
   size_t extra = 0;
   if (map_obs_staged(cells, obs_dtype)) extra = (size_t)kMapE * cells;
@@ -503,7 +546,8 @@ int map_tile_envs() { return kMapE; }
 
 template <int FAMILY, int MODE, int MINB>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
-  const size_t smem = map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
+  const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.map_padded_bytes, p.view_V)
+                                                               : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((p.N + kMapE - 1) / kMapE)); cfg.blockDim = dim3(kMapE);
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -516,9 +560,9 @@ static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
 
 template <int FAMILY, int MODE>
 static cudaError_t configure_pair(int smem) {
-  cudaError_t e = cudaFuncSetAttribute((const void*)map_kernel<FAMILY, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 1>, (size_t)smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)map_kernel<FAMILY, MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 8>, (size_t)smem);
 }
 
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {

@@ -28,6 +28,10 @@ struct MapParams {
   unsigned long long thr_blue_home, thr_red_home, thr_even;  // blue wins iff u32 < ceil(p * 2^32), p = randomness / 1 - randomness / 0.5
   int tma_reps;                            // copies of the period per bulk store (~32 KB chunks)
   int obs_tma;                             // 1 = (not staged) the period streams out through TMA bulk stores
+  // Maze partial-observation mode (mg_set_partial_obs): the step / reset write gen_obs views [N][1][V][V][3] instead of the map
+  int view_V, view_see_through;            // 0 = off; 3 / 5 / 7
+  const uint8_t* map_padded; int pad, pitch, map_padded_bytes;   // packed static map surrounded by the out-of-map filler
+  uint8_t view_oob, view_agent;
   int obs_staged;                          // 1 = the tile's u8 obs slab is assembled in shared memory (small maps)
   // state planes
   uint8_t* agents;   // [N_pad][row_bytes]: agent i at bytes 4i..4i+3 = x, y, dir, flags (bit0 terminated, bit1 collided)

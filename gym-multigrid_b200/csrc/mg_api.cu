@@ -13,6 +13,7 @@
 
 #include "../../include/multigrid_b200.h"
 #include "mg_device.cuh"
+#include "smem_config.h"
 
 namespace mg {
 cudaError_t launch_collect_step(int v, const CollectParams& p, cudaStream_t st);
@@ -29,6 +30,8 @@ size_t map_smem_bytes(int L, int n, int cells, int obs_dtype);
 bool map_obs_staged(int cells, int obs_dtype);
 bool map_obs_tma(int L, int cells, int obs_dtype);
 int map_tma_reps(int L, int cells, int obs_dtype);
+size_t map_view_smem_bytes(int padded_bytes, int V);
+cudaError_t configure_map_view_mode(size_t smem);
 cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st);
 int map_tile_envs();
 }  // namespace mg
@@ -240,6 +243,7 @@ extern "C" size_t mg_obs_bytes(const mg_env* env) {
   if (!env) return 0;
   if (env->family == MG_FAMILY_WILDFIRE) return (size_t)env->wcfg.num_envs * env->wcfg.width * env->wcfg.height * 3;
   if (env->family == MG_FAMILY_GENERIC) return (size_t)env->gcfg.num_envs * env->gcfg.num_agents * env->gcfg.width * env->gcfg.height * 6;
+  if (env->family == MG_FAMILY_MAZE && env->mbase.view_V) return (size_t)env->mcfg.num_envs * env->mbase.view_V * env->mbase.view_V * 3;
   if (env->family != MG_FAMILY_COLLECT) return (size_t)env->mcfg.num_envs * env->mcfg.size * env->mcfg.size * env->obs_elem;
   return (size_t)env->cfg.num_envs * env->cfg.width * env->cfg.height * 3;
 }
@@ -465,9 +469,29 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
     p.obs = obs;
   }
   if (p.obs && !aligned16(p.obs)) return fail(env, "obs buffer must be 16-byte aligned");
+  if (p.view_V && p.final_obs) return fail(env, "final_obs is not available in partial-observation mode");
   cudaError_t ce;
   if ((ce = mg::launch_map(p, st)) != cudaSuccess) return cuda_fail(env, "map_kernel", ce);
   env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_set_partial_obs(mg_env* env, int view_size, int see_through_walls) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_MAZE) return fail(env, "mg_set_partial_obs: Maze family only (Collect / generic handles use mg_gen_obs)");
+  if (view_size != 0 && view_size != 3 && view_size != 5 && view_size != 7) return fail(env, "mg_set_partial_obs: view_size must be 0 (off), 3, 5 or 7");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  mg::MapParams& p = env->mbase;
+  if (view_size) {
+    const size_t smem = mg::map_view_smem_bytes((int)env->map_padded_bytes, view_size);
+    if (smem > 227 * 1024) return fail(env, "mg_set_partial_obs: padded map does not fit in shared memory");
+    if ((ce = mg::configure_map_view_mode(smem)) != cudaSuccess) return cuda_fail(env, "cudaFuncSetAttribute", ce);
+    p.map_padded = env->d_map_tables + env->map_padded_off; p.pad = env->map_pad; p.pitch = p.S + 2 * env->map_pad;
+    p.map_padded_bytes = (int)env->map_padded_bytes;
+    p.view_oob = mg::cell(3, 7, 1); p.view_agent = mg::cell(1, 4, 0);   // as mg_gen_obs: out-of-map filler, Agent(color="blue")
+  }
+  p.view_V = view_size; p.view_see_through = see_through_walls != 0;
   return 0;
 }
 

@@ -20,6 +20,8 @@
 #include <cstdlib>
 
 #include "mg_device.cuh"
+#include "smem_config.h"
+#include "view_device.cuh"
 #include "view_params.cuh"
 
 namespace mg {
@@ -29,20 +31,10 @@ constexpr int kViewThreads = 128;
 constexpr int kViewMax = 15;      // largest view size
 constexpr int kViewMazeE = 128;   // envs per CTA (fast kernel, Maze: one view per env)
 
-// V-bit mask of the t in [0, V) with 0 <= u0 + s*t < L  (s = +1 / -1)
-__device__ __forceinline__ uint32_t range_mask(int u0, int s, int L, int V) {
-  int lo = s > 0 ? -u0 : u0 - (L - 1), hi = s > 0 ? L - 1 - u0 : u0;
-  lo = max(lo, 0); hi = min(hi, V - 1);
-  return hi < lo ? 0u : (((2u << hi) - 1u) & ~((1u << lo) - 1u));
-}
-
-__host__ __device__ constexpr int view_guard_bytes(int V, int H) { return ((V - 1) * (H + 1) + 15) / 16 * 16; }
-
 template <int FAMILY, int V>
 __global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_constant__ ViewParams p) {
   static_assert(V % 2 == 1 && V <= 7, "fast path: odd view sizes up to 7");
-  constexpr int VV = V * V, HS = V / 2, NPK = (VV + 3) / 4, NW = (3 * VV + 1) / 4, NFULL = (3 * VV - 3) / 4;
-  constexpr uint32_t FULL = (1u << V) - 1u;
+  constexpr int VV = V * V;
   constexpr int E = FAMILY == MG_FAMILY_COLLECT ? kViewE : kViewMazeE;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
@@ -75,14 +67,10 @@ __global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_co
     const long long gv = e0 * A + v;
     const int x = p.pos[gv * p.pos_stride], y = p.pos[gv * p.pos_stride + 1];
     const int dir = p.dirs ? (p.dirs[gv * p.dir_stride] & 3) : 3;
-    // world cell of view cell (a, b): (x0 + a*ax + b*bx, y0 + a*ay + b*by); linear index i0 + a*sa + b*sb
     int x0, y0, sa, sb;
-    if (dir == 3)      { x0 = x - HS;      y0 = y - (V - 1); sa = pitch;  sb = 1; }       // facing up
-    else if (dir == 1) { x0 = x + HS;      y0 = y + (V - 1); sa = -pitch; sb = -1; }      // facing down
-    else if (dir == 0) { x0 = x + (V - 1); y0 = y - HS;      sa = 1;      sb = -pitch; }  // facing right
-    else               { x0 = x - (V - 1); y0 = y + HS;      sa = -1;     sb = pitch; }   // facing left
+    view_geometry<V>(x, y, dir, pitch, x0, y0, sa, sb);
+    uint32_t mA = (1u << V) - 1u, mB = mA;
     const uint8_t* src;
-    uint32_t mA = FULL, mB = FULL;
     if (FAMILY == MG_FAMILY_COLLECT) {
       src = s_src + guard + (v / A) * p.cells + x0 * pitch + y0;
       const bool a_is_x = dir & 1;  // dirs 1, 3: a walks along x, b along y
@@ -91,82 +79,8 @@ __global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_co
     } else {
       src = s_src + (x0 + p.pad) * pitch + (y0 + p.pad);
     }
-    uint32_t pk[NPK], opq[V], msk[V];
-#pragma unroll
-    for (int k = 0; k < NPK; ++k) pk[k] = 0;
-#pragma unroll
-    for (int b = 0; b < V; ++b) {
-      const uint32_t rowv = ((mB >> b) & 1u) ? mA : 0u;
-      uint32_t o = 0;
-#pragma unroll
-      for (int a = 0; a < V; ++a) {
-        uint32_t c = src[a * sa + b * sb];
-        if (FAMILY == MG_FAMILY_COLLECT) {
-          c = ((rowv >> a) & 1u) ? c : (uint32_t)p.oob_code;
-          o |= (uint32_t)((c & 3u) == (uint32_t)T_WALL) << a;     // see_behind() is False only for Wall (object.py:174-179)
-        } else {
-          if (a == HS && b == V - 1) c = (uint32_t)p.agent_code | ((uint32_t)dir << 6);  // the agent stands at view cell (V/2, V-1)
-          o |= (uint32_t)(c == (uint32_t)p.oob_code) << a;         // Maze: only the out-of-map filler blocks sight
-        }
-        pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
-      }
-      opq[b] = o; msk[b] = 0;
-    }
-    if (p.see_through) {
-#pragma unroll
-      for (int b = 0; b < V; ++b) msk[b] = FULL;
-    } else {  // process_vis (grid.py:286-323): rows bottom-up; inside a row left->right, then right->left
-      msk[V - 1] = 1u << HS;
-#pragma unroll
-      for (int j = V - 1; j >= 0; --j) {
-        const uint32_t clear = ~opq[j] & FULL;
-        uint32_t m = msk[j];
-        // left -> right: F = cells that are visible AND transparent once the sweep has passed them
-        uint32_t F = m & clear, P = clear;
-        F |= P & (F << 1); P &= P << 1;
-        F |= P & (F << 2);
-        if (V > 4) { P &= P << 2; F |= P & (F << 4); }
-        F &= FULL >> 1;                       // the loop runs i = 0 .. V-2
-        m |= F << 1;
-        uint32_t up = F | (F << 1);
-        // right -> left
-        uint32_t G = m & clear; P = clear;
-        G |= P & (G >> 1); P &= P >> 1;
-        G |= P & (G >> 2);
-        if (V > 4) { P &= P >> 2; G |= P & (G >> 4); }
-        G &= ~1u;                             // the loop runs i = V-1 .. 1
-        m |= G >> 1;
-        up |= G | (G >> 1);
-        msk[j] = m;
-        if (j > 0) msk[j - 1] |= up;
-      }
-    }
-    // encode_for_agents: cells outside the mask stay (0, 0, 0)
-#pragma unroll
-    for (int a = 0; a < V; ++a)
-#pragma unroll
-      for (int b = 0; b < V; ++b)
-        if (!((msk[b] >> a) & 1u)) pk[(a * V + b) / 4] &= ~(0xFFu << (8 * ((a * V + b) % 4)));
-    uint32_t w[NW + 2];
-#pragma unroll
-    for (int k = 0; k < NPK; ++k) {
-      uint32_t o0, o1, o2;
-      expand4(pk[k], o0, o1, o2);
-      w[3 * k] = o0;
-      if (3 * k + 1 < NW + 2) w[3 * k + 1] = o1;
-      if (3 * k + 2 < NW + 2) w[3 * k + 2] = o2;
-    }
-    // 3*VV bytes at byte offset v*3*VV: h head bytes up to the next word boundary, NFULL aligned words, 3-h tail bytes
-    uint8_t* dst = s_out + (size_t)v * (3 * VV);
-    const int h = (int)((4u - ((uint32_t)v * (3u * VV) & 3u)) & 3u);
-    uint32_t* q = reinterpret_cast<uint32_t*>(dst + h);
-#pragma unroll
-    for (int j = 0; j < NFULL; ++j) q[j] = __funnelshift_r(w[j], w[j + 1], 8 * h);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const bool head = i < h;
-      dst[head ? i : 4 * NFULL + i] = (uint8_t)((head ? w[0] : w[NFULL]) >> (8 * i));
-    }
+    view_compute_store<FAMILY == MG_FAMILY_COLLECT, V>(src, sa, sb, mA, mB, p.oob_code, (uint32_t)p.agent_code | ((uint32_t)dir << 6),
+                                                       p.see_through != 0, s_out, v);
   }
   fence_proxy_async_smem();
   __syncthreads();
@@ -315,7 +229,7 @@ template <int DEPTH>
 __global__ void __launch_bounds__(kTorThreads) toroid_fast_kernel(const uint8_t* __restrict__ grid, const uint8_t* __restrict__ pos,
                                                                   float* __restrict__ out, long long N, int W, int A,
                                                                   uint32_t cells_magic, uint32_t w_magic, uint32_t a_magic) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, cells = W * W;
   const long long e0 = (long long)blockIdx.x * kTorE;
   const int n_here = (int)min((long long)kTorE, N - e0);
@@ -377,7 +291,7 @@ static cudaError_t launch_toroid_fast(const uint8_t* grid, const uint8_t* pos, f
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > 48 * 1024 && smem > configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)toroid_fast_kernel<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_smem_limit((const void*)toroid_fast_kernel<DEPTH>, (size_t)smem);
     if (e != cudaSuccess) return e;
     configured[dev & 63] = smem;
   }
@@ -529,7 +443,7 @@ static cudaError_t launch_fast(const ViewParams& p, size_t smem, cudaStream_t st
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)view_fast_kernel<FAMILY, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_smem_limit((const void*)view_fast_kernel<FAMILY, V>, (size_t)smem);
     if (e != cudaSuccess) return e;
     configured[dev & 63] = smem;
   }
@@ -559,8 +473,8 @@ cudaError_t launch_view(const ViewParams& p, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (smem > configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)view_kernel<MG_FAMILY_MAZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_COLLECT>, (size_t)smem);
+    if (e == cudaSuccess) e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_MAZE>, (size_t)smem);
     if (e != cudaSuccess) return e;
     configured[dev & 63] = smem;
   }

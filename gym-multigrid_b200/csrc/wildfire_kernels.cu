@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "mg_device.cuh"
+#include "smem_config.h"
 #include "wildfire_params.cuh"
 
 namespace mg {
@@ -450,11 +451,11 @@ size_t wildfire_smem_bytes(int cells, int H) { return wf_fast(H) ? wf_fast_smem(
 cudaError_t configure_wildfire_kernel(int cells, int H) {
   const int bytes = (int)wildfire_smem_bytes(cells, H);
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute((const void*)wildfire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute((const void*)wildfire_fast_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute((const void*)wildfire_fast_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if ((e = raise_smem_limit((const void*)wildfire_kernel, (size_t)bytes)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<64, 1>, (size_t)bytes)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<128, 1>, (size_t)bytes)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<64, 4>, (size_t)bytes)) != cudaSuccess) return e;
+  return raise_smem_limit((const void*)wildfire_fast_kernel<128, 4>, (size_t)bytes);
 }
 
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {

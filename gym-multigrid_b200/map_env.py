@@ -154,7 +154,7 @@ class _MapVecEnv:
             N, S = self.num_envs, self.size
             pin = dict(pin_memory=True)
             self._host = dict(act=torch.zeros((N, self.num_blue), dtype=torch.int8, **pin),
-                              obs=torch.zeros((N, S, S), dtype=self._obs.dtype, **pin), rew=torch.zeros(N, dtype=torch.float64, **pin),
+                              obs=torch.zeros(tuple(self._obs.shape), dtype=self._obs.dtype, **pin), rew=torch.zeros(N, dtype=torch.float64, **pin),
                               term=torch.zeros(N, dtype=torch.uint8, **pin), trunc=torch.zeros(N, dtype=torch.uint8, **pin))
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
         h = self._host
@@ -236,9 +236,11 @@ class MazeVecEnv(_MapVecEnv):
     info_keys = ("d_a_f", "d_a_ob")
 
     def __init__(self, num_envs, map_path, max_steps=100, flag_reward=1.0, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01,
-                 observation_option="map", device="cuda:0", seed=0, autoreset=True, env_id_base=0, reference_dtypes=False):
-        if observation_option != "map":
-            raise NotImplementedError('only observation_option="map" runs on the device; "positional" is agent_pos + the static lists')
+                 observation_option="map", device="cuda:0", seed=0, autoreset=True, env_id_base=0, reference_dtypes=False,
+                 view_size=7, see_through_walls=False):
+        if observation_option not in ("map", "partial"):
+            raise NotImplementedError('observation_option "map" (the reference\'s) or "partial" (gen_obs views, BASELINE config 4); '
+                                      '"positional" is agent_pos + the static lists')
         fm = load_text_map(map_path)
         fr = float(flag_reward)
         self._create(num_envs, fm, 1, 0, fr, 0.0, fr * float(obstacle_penalty_ratio), fr * float(step_penalty_ratio), 0.0, 0.0,
@@ -252,6 +254,23 @@ class MazeVecEnv(_MapVecEnv):
         self.background = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 0))]
         self.obstacle = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 3))]
         self.flag = [tuple(int(v) for v in c) for c in zip(*np.where(self.field_map == 2))]
+        if observation_option == "partial":
+            self.set_partial_obs(view_size, see_through_walls)
+
+    def set_partial_obs(self, view_size=7, see_through_walls=False):
+        """Switch `reset` / `step` observations to MultiGridEnv.gen_obs partial views u8 [N, 1, V, V, 3] (V in 3, 5, 7), computed
+        by the same kernel launch that steps the envs; view_size 0 switches back to the "map" observation."""
+        V = int(view_size)
+        self._check(self._lib.mg_set_partial_obs(self._h, V, int(bool(see_through_walls))))
+        self._final_obs = None
+        if V:
+            self._obs = torch.zeros((self.num_envs, 1, V, V, 3), dtype=torch.uint8, device=self.device)
+            self.single_observation_space = Box(0, 255, (V, V, 3), np.uint8)
+            self.observation_space = Box(0, 255, (self.num_envs, 1, V, V, 3), np.uint8)
+        else:
+            odt = self.ref_dtype if self.reference_dtypes else torch.uint8
+            self._obs = torch.zeros((self.num_envs, self.size, self.size), dtype=odt, device=self.device)
+        self._host = None
 
 
     def gen_obs(self, view_size=7, see_through_walls=False, out=None):

@@ -218,6 +218,11 @@ typedef struct mg_map_trace {
 int mg_create_map(const mg_map_config* cfg, int device, mg_env** out);
 int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
 
+/* Maze handles: observation mode of mg_reset / mg_step / mg_step_host.  view_size 0 (default) = the "map" observation;
+ * 3 / 5 / 7 = MultiGridEnv.gen_obs partial views u8 [N][1][V][V][3] computed by the SAME launch that steps the envs
+ * (BASELINE config 4; same cells as mg_gen_obs would return after the step).  final_obs is not available in this mode. */
+int mg_set_partial_obs(mg_env* env, int view_size, int see_through_walls);
+
 /* `_get_info()` of every env (maze.py:262-269; ctf.py:1165-1182, 434-452) -> out float64, device:
  *   Maze [N][2]  = d_a_f, d_a_ob
  *   CtF  [N][11] = d_ba_ra, d_ba_bf, d_ba_rf, d_ra_bf, d_ra_rf, d_bf_rf, d_ba_bb, d_ba_rb, d_ra_bb, d_ra_rb, d_ba_ob

@@ -77,6 +77,39 @@ def test_maze_views_match_composed_oracle(stem, cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("V,st", [(7, False), (5, True), (3, False)])
+def test_maze_fused_step_and_partial_view(V, st, cuda_device):
+    """observation_option="partial": the step kernel itself writes the gen_obs views (mg_set_partial_obs); they must equal
+    mg_gen_obs on the post-step state and the composed oracle, including across same-step autoresets and a ragged tile."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("maze_gen64")
+    fm = g["field_map"]
+    S, n = fm.shape[0], 1000
+    env = mg.make_maze_vec(n, fm, seed=6, max_steps=9, observation_option="partial", view_size=V, see_through_walls=st)
+    packed_map = np.where(fm == 0, 0 | 10 << 2, np.where(fm == 2, 2 | 0 << 2, 3 | 7 << 2)).astype(np.uint8)
+
+    def want():
+        pos, d = _np(env.agent_pos), _np(env.agent_dir)
+        grids = np.repeat(packed_map.reshape(1, -1), n, axis=0)
+        grids[np.arange(n), pos[:, 0, 0].astype(int) * S + pos[:, 0, 1]] = (1 | 4 << 2) | (d[:, 0] << 6)
+        return oc.partial_view3(grids, pos, S, S, V, st, dirs=d, oob_code=3 | 7 << 2 | 1 << 6, opaque_rule=1)
+
+    obs, _ = env.reset()
+    assert tuple(obs.shape) == (n, 1, V, V, 3) and np.array_equal(_np(obs), want())
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    for t in range(25):
+        obs, rew, term, trunc, _ = env.step(torch.randint(0, 5, (n,), generator=gen, device=cuda_device, dtype=torch.int8))
+        assert np.array_equal(_np(obs), _np(env.gen_obs(V, st))), f"step {t}: fused views != mg_gen_obs"
+        assert np.array_equal(_np(obs), want()), f"step {t}: fused views != oracle"
+    assert int(env.episode_count.min()) >= 3
+    host_obs = env.step(np.zeros(n, np.int8))[0]
+    assert host_obs.shape == (n, 1, V, V, 3) and np.array_equal(host_obs, want())
+    env.set_partial_obs(0)
+    obs, *_ = env.step(torch.zeros(n, dtype=torch.int8, device=cuda_device))
+    assert tuple(obs.shape) == (n, S, S)
+    env.close()
+
+
 @pytest.mark.parametrize("stem,env_id", [("toroid_clustered", "multigrid-collect-respawn-clustered-v0"),
                                          ("toroid_rooms", "multigrid-collect-rooms-respawn-v0"),
                                          ("toroid_single", "multigrid-collect-single-v0")])

@@ -119,6 +119,10 @@ def bench_maze(args):
             outs = [torch.empty((n, 1, 7, 7, 3), dtype=torch.uint8, device="cuda:0") for _ in range(B)]
             us = graph_time([lambda e=e, o=o: e.gen_obs(7, False, out=o) for e, o in zip(envs, outs)], args.reps)
             report("view_kernel maze 64x64 V=7 partial obs", n, us, 147 + 4, batches=B)
+            for e in envs:
+                e.set_partial_obs(7)
+            us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+            report("map_kernel<maze> 64x64 fused step + V=7 partial obs (config 4)", n, us, 147 + 2 * (4 + 16) + 1 + 10, batches=B)
         for e in envs:
             e.close()
 
