@@ -270,3 +270,44 @@ def test_ctf1v1_replay_and_philox(cuda_device):
     with pytest.raises(ValueError):
         mg.make_ctf1v1_vec(4, g["field_map"], obstacle_penalty_ratio=0.5)
     env.close()
+
+
+def test_full_size_invariants_ctf_and_maze(cuda_device):
+    """BASELINE configs 3 / 4 at full size (1 M CtF envs, 131 072 Maze envs on a 64x64 map): size-independent properties."""
+    import gym_multigrid_b200 as mg
+    fm = load_golden("ctf_2v2")["field_map"]
+    n = 1 << 20
+    env = mg.make_ctf_vec(n, fm, seed=12)
+    obs, _ = env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(9)
+    static = torch.as_tensor(fm.T.copy(), device=cuda_device)      # obs[y][x] = map[x][y]
+    steps_before = env.step_count.clone()
+    for t in range(12):
+        obs, rew, term, trunc, _ = env.step(torch.randint(0, 5, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8))
+        agents = (obs == 2) | (obs == 3)
+        dead = env.agent_terminated
+        # every living agent is drawn exactly once unless a later agent hides it (positions are distinct for living agents)
+        assert int(agents.sum(dim=(1, 2)).max()) <= 4 and bool((agents.sum(dim=(1, 2)) == (~dead).sum(dim=1)).all())
+        assert bool(((obs == static) | agents | (obs == 6)).all()), "cells are the static map, an agent, or a defeated agent"
+        assert bool((rew >= -(1.0 + 2 * 0.25 + 0.02) - 1e-12).all()) and bool((rew <= 2 * 1.0 + 4 * 0.25).all())
+        done = term | trunc
+        assert bool((env.step_count[done] == 0).all()) and bool((env.step_count[~done] == steps_before[~done] + 1).all())
+        steps_before = env.step_count.clone()
+    assert env.status() == 0 and int(env.episode_count.max()) >= 2
+    env.close()
+
+    g = load_golden("maze_gen64")
+    fm = torch.as_tensor(g["field_map"], device=cuda_device)
+    n = 131072
+    env = mg.make_maze_vec(n, g["field_map"], seed=3)
+    obs, _ = env.reset()
+    for t in range(6):
+        obs, rew, term, trunc, _ = env.step(torch.randint(0, 5, (n,), generator=gen, device=cuda_device, dtype=torch.int8))
+        diff = obs != fm
+        assert bool((diff.sum(dim=(1, 2)) == 1).all()), "the observation is the map plus exactly one agent cell"
+        pos = env.agent_pos[:, 0].long()
+        assert bool((obs[torch.arange(n, device=cuda_device), pos[:, 0], pos[:, 1]] == 1).all())
+        assert bool((fm[pos[:, 0], pos[:, 1]] != 3).all()), "obstacles are never entered with penalty 0"
+        assert bool(((rew == -0.01) | (rew == 1.0 - 0.01) | term).all())
+    assert env.status() == 0
+    env.close()

@@ -75,3 +75,26 @@ def test_wildfire_rejects_bad_configs(cuda_device):
         mg.make_wildfire_vec(4, size=10)            # 100 cells: not a multiple of 16
     with pytest.raises(ValueError):
         mg.make_wildfire_vec(4, size=16, num_agents=33)
+
+
+def test_wildfire_full_size_invariants(cuda_device):
+    """BASELINE config 5 per-GPU share: 131 072 envs, 64x64 cells, 16 agents - size-independent properties."""
+    import gym_multigrid_b200 as mg
+    n, A, S = 131072, 16, 64
+    env = mg.make_wildfire_vec(n, size=S, num_agents=A, num_fires=4, alpha=0.15, beta=0.05, max_steps=200, seed=5)
+    obs, _ = env.reset()
+    assert bool(((obs[..., 0] == 1).sum(dim=(1, 2)) + (obs[..., 0] == 3).sum(dim=(1, 2)) >= 4).all())
+    gen = torch.Generator(device=cuda_device).manual_seed(1)
+    prev_burnt = (env.terrain == 2).sum(dim=1)
+    for t in range(8):
+        obs, rew, term, trunc, _ = env.step(torch.randint(0, 5, (n, A), generator=gen, device=cuda_device, dtype=torch.int8))
+        typ = obs[..., 0]
+        assert bool(((typ == 3).sum(dim=(1, 2)) == A).all()), "agents never share a cell"
+        assert bool((typ <= 3).all()) and bool(((obs[..., 2] == 0) | (typ == 3)).all())
+        burnt = (env.terrain == 2).sum(dim=1)
+        done = term | trunc
+        assert bool((burnt[~done] >= prev_burnt[~done]).all()), "burnt cells never recover inside an episode"
+        assert bool((rew.sum(dim=1) <= A).all()) and bool((rew >= 0).all())
+        assert bool((term == ((env.terrain == 1).sum(dim=1) == 0))[~done].all())
+        prev_burnt = burnt
+    env.close()
