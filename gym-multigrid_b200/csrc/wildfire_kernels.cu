@@ -257,40 +257,65 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
     // ---- 1/2. ordered agent moves: warp 0, lane = agent
     order_blocks = (!p.order && A > 1) ? (uint32_t)(A - 1 + 3) / 4u : 0u;
     if (warp == 0) {
-      int ord = lane;  // value at position `lane` of the order
+      // rank = this agent's position in the step's order.  Fisher-Yates: draw d (for i = A-1-d) is word d % 4 of Philox
+      // block ctr0 + d / 4; instead of permuting an array serially every lane tracks ITS OWN element through the swaps
+      // (p == i -> j, p == j -> i): the draws are broadcast by independent shuffles, no lane waits for another.
+      int rank = lane;
       if (p.order) {
-        if (lane < A) ord = p.order[e * A + lane];
-      } else if (A > 1) {  // Fisher-Yates: draw d (for i = A-1-d) is word d % 4 of block ctr0 + d / 4
+        int* s_rank = s_adir;                // scratch: s_adir is read into `dir` first
+        const int d0 = lane < A ? s_adir[lane] : 0;
+        __syncwarp();
+        if (lane < A) s_rank[p.order[e * A + lane]] = lane;
+        __syncwarp();
+        if (lane < A) rank = s_rank[lane];
+        __syncwarp();
+        if (lane < A) s_adir[lane] = d0;
+        __syncwarp();
+      } else if (A > 1) {
         uint32_t u[4];
         philox4x32_10(id0, id1, ctr0 + (uint32_t)(lane >> 2), 0u, k0, k1, u);
         const uint32_t word = (lane & 2) ? ((lane & 1) ? u[3] : u[2]) : ((lane & 1) ? u[1] : u[0]);
         const int jl = (int)__umulhi(word, (uint32_t)(A - lane));   // below(i + 1), i = A - 1 - lane
-        for (int d = 0; d < A - 1; ++d) {  // swap positions i and j: one broadcast + one permuting shuffle
+        for (int d = 0; d < A - 1; ++d) {
           const int i = A - 1 - d, j = __shfl_sync(0xffffffffu, jl, d);
-          ord = __shfl_sync(0xffffffffu, ord, lane == i ? j : (lane == j ? i : lane));
+          rank = rank == i ? j : (rank == j ? i : rank);
         }
       }
-      // an agent acts once per step, so its target cell is known up front; positions travel packed as x | y << 8
+      // an agent acts once per step, so its target cell is known up front; positions travel packed as x | y << 8.
+      // `tgt` = the cell the agent will stand on if nothing blocks it (its own cell when it stays).
       const int a = lane < A ? p.actions[e * A + lane] : 0;
       int x = lane < A ? s_ax[lane] : 0, y = lane < A ? s_ay[lane] : 0, dir = lane < A ? s_adir[lane] : 0;
       const int dx = (a == 4) - (a == 2), dy = (a == 3) - (a == 1);
       const int nx = x + dx, ny = y + dy;
       const bool wants = lane < A && a >= 1 && a <= 4 && nx >= 0 && ny >= 0 && nx < W && ny < H;
-      const uint32_t target = (uint32_t)nx | ((uint32_t)ny << 8);
-      uint32_t cur = lane < A ? ((uint32_t)x | ((uint32_t)y << 8)) : 0xFFFFFFFFu;   // idle lanes never match a target
-      for (int k = 0; k < A; ++k) {
-        const int i = __shfl_sync(0xffffffffu, ord, k);          // the acting agent; warp-uniform
-        const uint32_t t = __shfl_sync(0xffffffffu, target, i);
-        const unsigned occupied = __ballot_sync(0xffffffffu, cur == t && lane != i);
-        if (lane == i && wants && !occupied) {
-          cur = t;
-          dir = dx == 1 ? 0 : (dy == 1 ? 1 : (dx == -1 ? 2 : 3));  // DIR_TO_VEC (constants.py:65-74)
-        }
+      const uint32_t cur = lane < A ? ((uint32_t)x | ((uint32_t)y << 8)) : (0xFFFF0000u | (uint32_t)lane);   // idle lanes: unique, never a cell
+      const uint32_t tgt = wants ? ((uint32_t)nx | ((uint32_t)ny << 8)) : cur;
+      // A move can only be blocked (or depend on the order at all) if another agent stands on the target now, stays on it,
+      // or wants the same target: those few lanes are resolved in rank order below, everybody else just moves.
+      // (every lane executes every warp collective: no short-circuit in front of a *_sync call)
+      const unsigned same_tgt = __match_any_sync(0xffffffffu, tgt);             // same target, or the target of a stayer
+      bool conflict = __popc(same_tgt) > 1;
+      for (int d = 0; d < A; ++d) {
+        const uint32_t cd = __shfl_sync(0xffffffffu, cur, d);                   // someone stands there now
+        conflict |= (cd == tgt) & (d != lane);
       }
+      conflict &= wants;
+      uint32_t fin = (wants && !conflict) ? tgt : cur;   // position after this agent's own turn
+      unsigned rem = __ballot_sync(0xffffffffu, conflict);
+      while (rem) {  // sequential semantics for the conflicting lanes: at k's turn agent j is at (rank_j < rank_k ? fin_j : cur_j)
+        const int rk = (int)__reduce_min_sync(0xffffffffu, (unsigned)(((rem >> lane) & 1u) ? rank : 255));
+        const int k = __ffs(__ballot_sync(0xffffffffu, ((rem >> lane) & 1u) && rank == rk)) - 1;
+        const uint32_t t = __shfl_sync(0xffffffffu, tgt, k);
+        const unsigned occupied = __ballot_sync(0xffffffffu, lane != k && (rank < rk ? fin : cur) == t);
+        if (lane == k && !occupied) fin = tgt;
+        rem &= ~(1u << k);
+      }
+      if (fin != cur) dir = dx == 1 ? 0 : (dy == 1 ? 1 : (dx == -1 ? 2 : 3));  // DIR_TO_VEC (constants.py:65-74): dir follows an actual move
+      const uint32_t cur_after = fin;
       // extinguish the burning cell under each agent: agents stand on distinct cells and never act twice, so this
       // does not depend on the order
       if (lane < A) {
-        x = (int)(cur & 255u); y = (int)(cur >> 8);
+        x = (int)(cur_after & 255u); y = (int)(cur_after >> 8);
         double rew = 0.0;
         if (s_told[x * H + y] == WF_BURNING) { s_told[x * H + y] = WF_BURNT; rew = 1.0; }
         s_ax[lane] = x; s_ay[lane] = y; s_adir[lane] = dir; p.rewards[e * A + lane] = rew;
