@@ -277,7 +277,9 @@ def run_ours(args):
                               "achieved": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3, "frac": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3 / peak,
                               "note": "same graph on ONE stream (launches serialised by programmatic dependent launch)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": n * (300 + 16 + 2),
-                    "steps": e2e_steps, "api": "CollectVecEnv.step(numpy) -> mg_step_host (pinned host buffers)"},
+                    "steps": e2e_steps, "api": "CollectVecEnv.step(numpy) -> mg_step_host (pinned host buffers)",
+                    "d2h_GBps_per_gpu": n * (300 + 16 + 2) / (e2e_ms_max * 1e-3 / e2e_steps) / 1e9,
+                    "note": "bound by the device-to-host copy of the observations (300 B/env over PCIe), not by the kernel"},
             "gpu_launches": K_eff,
             "clocks": sampler.summary(),
         }

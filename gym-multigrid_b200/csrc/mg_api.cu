@@ -68,7 +68,6 @@ struct mg_env {
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
   int act_cols, rew_cols;
-  size_t view_smem_configured;
   size_t map_codes_off;   // Maze: offset of the packed static map (partial views) inside d_map_tables
   size_t map_padded_off, map_padded_bytes;  // ... and of the copy padded with the out-of-map filler (fast view kernel)
   int map_pad;
@@ -164,7 +163,7 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");
   env->family = MG_FAMILY_COLLECT;
-  env->view_smem_configured = 0; env->map_codes_off = 0;
+  env->map_codes_off = 0;
   env->d_map_tables = nullptr;
   env->obs_elem = 1; env->act_cols = cfg->num_agents; env->rew_cols = cfg->num_agents;
   env->cfg = *cfg;
@@ -330,7 +329,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_map: out of host memory");
   env->family = cfg->family;
-  env->view_smem_configured = 0; env->map_codes_off = 0;
+  env->map_codes_off = 0;
   env->mcfg = *cfg; env->mcfg.field_map = nullptr;
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
@@ -540,7 +539,7 @@ extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
   env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
-  env->view_smem_configured = 0; env->map_codes_off = 0;
+  env->map_codes_off = 0;
   std::memset(&env->trace, 0, sizeof env->trace);
   env->obs_elem = 1; env->act_cols = A; env->rew_cols = A;
   env->n_pad = cfg->num_envs;
@@ -615,7 +614,7 @@ extern "C" int mg_create_generic(const mg_generic_config* cfg, int device, mg_en
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
   env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
-  env->view_smem_configured = 0; env->map_codes_off = 0;
+  env->map_codes_off = 0;
   std::memset(&env->trace, 0, sizeof env->trace);
   env->obs_elem = 1; env->act_cols = A; env->rew_cols = A;
   const int E = mg::generic_tile_envs();

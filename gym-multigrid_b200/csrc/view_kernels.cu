@@ -287,14 +287,8 @@ template <int DEPTH>
 static cudaError_t launch_toroid_fast(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, cudaStream_t st) {
   const int cells = W * W;
   const size_t smem = (size_t)kTorE * cells * (1 + A) + (size_t)kTorE * A * 2 + 16;
-  static size_t configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (smem > 48 * 1024 && smem > configured[dev & 63]) {
-    cudaError_t e = raise_smem_limit((const void*)toroid_fast_kernel<DEPTH>, (size_t)smem);
-    if (e != cudaSuccess) return e;
-    configured[dev & 63] = smem;
-  }
+  cudaError_t e = raise_smem_limit((const void*)toroid_fast_kernel<DEPTH>, smem);
+  if (e != cudaSuccess) return e;
   auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)(4294967296ull / (unsigned)d) + 1u; };  // exact quotients for operands < 2^16
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((N + kTorE - 1) / kTorE)); cfg.blockDim = dim3(kTorThreads);
@@ -439,14 +433,8 @@ int view_tile_envs() { return kViewE; }
 
 template <int FAMILY, int V>
 static cudaError_t launch_fast(const ViewParams& p, size_t smem, cudaStream_t st) {
-  static size_t configured[64] = {};   // per kernel instantiation and device; raised by the first (eager) call
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (smem > configured[dev & 63]) {
-    cudaError_t e = raise_smem_limit((const void*)view_fast_kernel<FAMILY, V>, (size_t)smem);
-    if (e != cudaSuccess) return e;
-    configured[dev & 63] = smem;
-  }
+  cudaError_t e = raise_smem_limit((const void*)view_fast_kernel<FAMILY, V>, smem);   // raised by the first (eager) call
+  if (e != cudaSuccess) return e;
   constexpr int E = FAMILY == MG_FAMILY_COLLECT ? kViewE : kViewMazeE;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((p.N + E - 1) / E)); cfg.blockDim = dim3(kViewThreads);
@@ -469,15 +457,9 @@ cudaError_t launch_view(const ViewParams& p, cudaStream_t st) {
       default: return c ? launch_fast<MG_FAMILY_COLLECT, 7>(p, smem, st) : launch_fast<MG_FAMILY_MAZE, 7>(p, smem, st);
     }
   }
-  static size_t configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (smem > configured[dev & 63]) {
-    cudaError_t e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_COLLECT>, (size_t)smem);
-    if (e == cudaSuccess) e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_MAZE>, (size_t)smem);
-    if (e != cudaSuccess) return e;
-    configured[dev & 63] = smem;
-  }
+  cudaError_t e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_COLLECT>, smem);
+  if (e == cudaSuccess) e = raise_smem_limit((const void*)view_kernel<MG_FAMILY_MAZE>, smem);
+  if (e != cudaSuccess) return e;
   const unsigned blocks = (unsigned)((p.N + kViewE - 1) / kViewE);
   if (p.family == MG_FAMILY_COLLECT) view_kernel<MG_FAMILY_COLLECT><<<blocks, kViewThreads, smem, st>>>(p);
   else view_kernel<MG_FAMILY_MAZE><<<blocks, kViewThreads, smem, st>>>(p);
