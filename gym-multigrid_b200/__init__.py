@@ -12,7 +12,7 @@ gymnasium surface.
 The compute path is hand-written CUDA for sm_100a behind the C ABI in include/multigrid_b200.h;
 there is no CPU fallback (construction raises when the library or a B200 is missing).
 """
-from .registration import registry, register, spec  # noqa: F401
+from .registration import registry, register, register_with_gymnasium, spec  # noqa: F401
 from .registration import COLLECT_CLASSES as _COLLECT_CLASSES
 
 __version__ = "0.1.0"

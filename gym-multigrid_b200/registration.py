@@ -55,3 +55,31 @@ def spec(env_id: str) -> EnvSpec:
 def register(id: str, entry_point: str, max_episode_steps: int | None = None, kwargs: dict | None = None):
     """Same signature as gymnasium.register for the subset the reference uses."""
     registry[id] = EnvSpec(id, entry_point, max_episode_steps, dict(kwargs or {}))
+
+
+def register_with_gymnasium(prefix: str = "", device: str = "cuda:0") -> list[str]:
+    """When `gymnasium` is installed: make `gymnasium.make(id)` / `gymnasium.make_vec(id, num_envs=N)` resolve the reference's
+    ids (optionally prefixed, e.g. "b200/") to the CUDA-backed envs of this package, with the registered kwargs and
+    `max_episode_steps` of gym_multigrid/__init__.py:6-147.  The single-env entry point applies the TimeLimit itself
+    (the library counts steps on the device), so no TimeLimit wrapper is requested from gymnasium.  Returns the ids registered."""
+    import gymnasium  # noqa: PLC0415 - optional dependency
+
+    def single(env_id):
+        def make_single(**kwargs):
+            from . import make
+            return make(env_id, device=kwargs.pop("device", device), **kwargs)
+        return make_single
+
+    def vector(env_id):
+        def make_vector(num_envs=1, **kwargs):
+            from . import make_vec
+            kwargs.pop("vectorization_mode", None)
+            return make_vec(env_id, num_envs, device=kwargs.pop("device", device), **kwargs)
+        return make_vector
+
+    done = []
+    for env_id in registry:
+        gymnasium.register(id=prefix + env_id, entry_point=single(env_id), vector_entry_point=vector(env_id),
+                           max_episode_steps=None, disable_env_checker=True, order_enforce=False)
+        done.append(prefix + env_id)
+    return done

@@ -98,3 +98,18 @@ def test_spaces():
     assert b.shape == (10, 10, 3) and b.dtype == np.uint8
     m = MultiDiscrete([5, 5])
     assert m.nvec.tolist() == [5, 5]
+
+
+def test_register_with_gymnasium_hands_over_every_id(monkeypatch):
+    """gymnasium is not in the image: a stand-in module records what the helper registers."""
+    import sys
+    import types
+    import gym_multigrid_b200 as mg
+    calls = []
+    fake = types.ModuleType("gymnasium")
+    fake.register = lambda **kw: calls.append(kw)
+    monkeypatch.setitem(sys.modules, "gymnasium", fake)
+    ids = mg.register_with_gymnasium(prefix="b200/")
+    assert ids == ["b200/" + k for k in mg.registry] and len(calls) == len(mg.registry) == 9
+    for kw in calls:
+        assert callable(kw["entry_point"]) and callable(kw["vector_entry_point"]) and kw["max_episode_steps"] is None
