@@ -71,3 +71,11 @@ def make_generic_vec(num_envs: int, width: int, **kwargs):
     """Batched base-class `MultiGridEnv.step` with DefaultWorld (multigrid.py:397-483; layout injected, see generic_env.py)."""
     from .generic_env import GenericVecEnv
     return GenericVecEnv(num_envs, width, **kwargs)
+
+
+def __getattr__(name):
+    """Reference-style single-env classes (same names as gym_multigrid.envs): imported lazily, they need torch + CUDA."""
+    if name in ("MazeSingleAgentEnv", "CtFMvNEnv", "Ctf1v1Env", "MazeActions", "CtfActions"):
+        from . import single_env
+        return getattr(single_env, name)
+    raise AttributeError(f"module 'gym_multigrid_b200' has no attribute {name!r}")

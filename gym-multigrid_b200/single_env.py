@@ -1,0 +1,127 @@
+"""Reference-style single-env adaptors for the map families: the reference's class names, constructor kwargs and
+return types (`MazeSingleAgentEnv` maze.py:26-377, `CtFMvNEnv` ctf.py:657-1433, `Ctf1v1Env` ctf.py:50-654) over ONE env
+of the batched CUDA classes - so that code written against the reference (its tests, `scripts/main_mvn_ctf_rl.py`) runs
+unchanged apart from the import.  Everything is computed by the same kernels as the vector envs; rendering is out of scope
+(`render()` is a no-op, `render_mode` is accepted and ignored)."""
+from __future__ import annotations
+
+import enum
+
+import numpy as np
+import torch
+
+from .map_env import Ctf1v1VecEnv, CtfVecEnv, MazeVecEnv
+from .spaces import Discrete, MultiDiscrete
+
+
+class MazeActions(enum.IntEnum):   # core/agent.py:54-67 (CtfActions has the same members)
+    stay = 0
+    left = 1
+    down = 2
+    right = 3
+    up = 4
+
+
+CtfActions = MazeActions
+
+
+class _SingleMapEnv:
+    actions_set = MazeActions
+
+    def _wrap(self, vec, observation_option):
+        self.vec, self.observation_option = vec, observation_option
+        self.max_steps, self.width, self.height = vec.max_steps, vec.width, vec.height
+        self.observation_space = vec.single_observation_space
+        self._seed = None
+
+    @property
+    def step_count(self):
+        return int(self.vec.step_count[0])
+
+    @property
+    def agent_positions(self):
+        return self.vec.agent_pos[0].cpu().numpy()
+
+    def _info(self):
+        return {k: float(v[0]) for k, v in self.vec.get_info().items()}
+
+    def render(self):
+        return None
+
+    def close(self):
+        self.vec.close()
+
+
+class MazeSingleAgentEnv(_SingleMapEnv):
+    """maze.py:31-40 kwargs; `reset(seed=None) -> (obs, info)`, `step(action) -> (obs float64 (W,H), reward float, bool, bool, info)`."""
+
+    def __init__(self, map_path, max_steps=100, flag_reward=1.0, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01,
+                 observation_option="map", render_mode="rgb_array", device="cuda:0", seed=0):
+        if observation_option != "map":
+            raise NotImplementedError('the adaptor returns observation_option="map" (maze.py:245-260)')
+        self._wrap(MazeVecEnv(1, map_path, max_steps=max_steps, flag_reward=flag_reward, obstacle_penalty_ratio=obstacle_penalty_ratio,
+                              step_penalty_ratio=step_penalty_ratio, device=device, seed=seed, autoreset=False, reference_dtypes=True),
+                   observation_option)
+        self.action_space = Discrete(5)
+
+    def reset(self, seed=None):
+        obs, _ = self.vec.reset()
+        return obs[0].cpu().numpy(), self._info()
+
+    def step(self, action):
+        a = torch.as_tensor([int(action)], dtype=torch.int8, device=self.vec.device)
+        obs, rew, term, trunc, _ = self.vec.step(a)
+        if self.vec.status() & 8:
+            raise ValueError(f"Invalid action: {action}")       # maze.py:286
+        return obs[0].cpu().numpy(), float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
+
+
+class CtFMvNEnv(_SingleMapEnv):
+    """ctf.py:662-679 kwargs (red agents follow RwPolicy, drawn on the device); `step(blue_actions)` returns the scalar team
+    reward.  observation_option: "map" (int64 (H,W)), "flattened" (int64 vector) or "positional" (dict of int64 arrays)."""
+    _vec_cls = CtfVecEnv
+
+    def __init__(self, map_path, num_blue_agents=2, num_red_agents=2, enemy_policies=None, battle_range=1, randomness=0.75,
+                 flag_reward=1, battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
+                 observation_option="positional", observation_scaling=1, render_mode="rgb_array", device="cuda:0", seed=0):
+        if observation_option not in ("map", "flattened", "positional"):
+            raise ValueError(f"Invalid observation_option: {observation_option}")
+        kw = dict(battle_range=battle_range, randomness=randomness, flag_reward=flag_reward, battle_reward_ratio=battle_reward_ratio,
+                  obstacle_penalty_ratio=obstacle_penalty_ratio, step_penalty_ratio=step_penalty_ratio, max_steps=max_steps,
+                  device=device, seed=seed, autoreset=False, reference_dtypes=True)
+        if self._vec_cls is CtfVecEnv:
+            kw.update(num_blue_agents=num_blue_agents, num_red_agents=num_red_agents)
+        self._wrap(self._vec_cls(1, map_path, **kw), observation_option)
+        self.num_blue_agents, self.num_red_agents = self.vec.num_blue, self.vec.num_red
+        self.action_space = MultiDiscrete([5] * self.vec.num_blue) if self._vec_cls is CtfVecEnv else Discrete(5)
+
+    def _obs(self, map_obs):
+        if self.observation_option == "map":
+            return map_obs[0].cpu().numpy()
+        if self.observation_option == "flattened":
+            return self.vec.flattened_obs()[0].cpu().numpy()
+        return {k: v[0].cpu().numpy() for k, v in self.vec.positional_obs().items()}
+
+    def reset(self, *, seed=None, options=None):
+        obs, _ = self.vec.reset()
+        return self._obs(obs), self._info()
+
+    def step(self, blue_actions):
+        a = torch.as_tensor(np.round(np.asarray(blue_actions, dtype=np.float64)).astype(np.int8).reshape(1, -1), device=self.vec.device)
+        obs, rew, term, trunc, _ = self.vec.step(a)
+        if self.vec.status() & 8:
+            raise ValueError(f"Invalid action: {blue_actions}")  # ctf.py:1200-1201
+        return self._obs(obs), float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
+
+
+class Ctf1v1Env(CtFMvNEnv):
+    """ctf.py:55-70 kwargs; one blue agent (scalar Discrete(5) action) against one RwPolicy red agent."""
+    _vec_cls = Ctf1v1VecEnv
+
+    def __init__(self, map_path, enemy_policy=None, battle_range=1.0, randomness=0.75, flag_reward=1.0, battle_reward_ratio=0.25,
+                 obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100, observation_option="positional",
+                 observation_scaling=1, render_mode="rgb_array", device="cuda:0", seed=0):
+        super().__init__(map_path, enemy_policies=enemy_policy, battle_range=battle_range, randomness=randomness, flag_reward=flag_reward,
+                         battle_reward_ratio=battle_reward_ratio, obstacle_penalty_ratio=obstacle_penalty_ratio,
+                         step_penalty_ratio=step_penalty_ratio, max_steps=max_steps, observation_option=observation_option,
+                         observation_scaling=observation_scaling, render_mode=render_mode, device=device, seed=seed)

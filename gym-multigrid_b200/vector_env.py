@@ -7,6 +7,7 @@ hand-written sm_100a kernel each through the C ABI and never synchronise with th
 from __future__ import annotations
 
 import ctypes as C
+import enum
 
 import numpy as np
 import torch
@@ -316,6 +317,25 @@ class CollectVecEnv:
             pass
 
 
+class CollectActions(enum.IntEnum):   # core/agent.py:32-36
+    north = 0
+    east = 1
+    south = 2
+    west = 3
+
+
+class _AgentView:
+    """What callers read from `env.agents[i]` (core/agent.py:92-100): index, pos, dir."""
+
+    def __init__(self, env, i):
+        self._env, self.i = env, i
+        self.index, self.dir = env.vec.agents_index[i], 3        # Collect agents never turn (multigrid.py:371-374)
+
+    @property
+    def pos(self):
+        return self._env.vec.agent_pos[0, self.i].cpu().numpy()
+
+
 class CollectEnv:
     """Single-env adaptor with the reference's own signatures (collect_game.py:107-119,183-214):
     `reset(seed=, options=) -> (obs ndarray (W,H,3) uint8, info dict)`,
@@ -331,6 +351,8 @@ class CollectEnv:
         self.action_space, self.observation_space = v.single_action_space, v.single_observation_space
         self.keys, self.max_steps, self.respawn, self.num_balls = v.keys, v.max_steps, v.respawn, v.num_balls
         self.agents_index = v.agents_index
+        self.actions_set = CollectActions
+        self.agents = [_AgentView(self, i) for i in range(v.num_agents)]      # `for a in env.agents` (tests/test_collect.py:16)
 
     @property
     def step_count(self):
