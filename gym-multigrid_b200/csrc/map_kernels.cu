@@ -170,8 +170,9 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
     }
   }
   const uint32_t red_flag = (uint32_t)p.red_flag, blue_flag = (uint32_t)p.blue_flag;
-  for (int i = 0; i < nb; ++i) if (((ag[i * kMapE] ^ red_flag) & 0xFFFFu) == 0) { rew += p.flag_reward; term = true; }   // :1335-1344
-  for (int i = nb; i < n; ++i) if (((ag[i * kMapE] ^ blue_flag) & 0xFFFFu) == 0) { rew -= p.flag_reward; term = true; }  // :1347-1356
+  // h.y = game_stats (ctf.py:1068-1073): bit0 blue_flag_captured, bit1 red_flag_captured, bit 8+i agent i defeated in a battle
+  for (int i = 0; i < nb; ++i) if (((ag[i * kMapE] ^ red_flag) & 0xFFFFu) == 0) { rew += p.flag_reward; term = true; h.y |= 2; }   // :1335-1344
+  for (int i = nb; i < n; ++i) if (((ag[i * kMapE] ^ blue_flag) & 0xFFFFu) == 0) { rew -= p.flag_reward; term = true; h.y |= 1; }  // :1347-1356
   int nbattle = 0;
   bool all_dead = true;
   for (int b = 0; b < nb; ++b) {  // np.where(distances <= battle_range): row-major, blue-major (:1368-1377)
@@ -192,9 +193,9 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
         blue_win = (unsigned long long)r.u32() < thr;
       }
       ++nbattle;
-      if (blue_win) { rew += p.battle_reward; ag[(nb + q) * kMapE] = wr | FL_DEAD; }   // :1409-1418
-      else if (p.variant_1v1) { rew -= p.battle_reward; term = true; }                 // 1v1: losing ends the episode (ctf.py:629-632)
-      else { rew -= p.battle_reward; wb |= FL_DEAD; ag[b * kMapE] = wb; }
+      if (blue_win) { rew += p.battle_reward; ag[(nb + q) * kMapE] = wr | FL_DEAD; h.y |= 1 << (8 + nb + q); }   // :1409-1418
+      else if (p.variant_1v1) { rew -= p.battle_reward; term = true; h.y |= 1 << 8; }  // 1v1: losing ends the episode (ctf.py:629-636)
+      else { rew -= p.battle_reward; wb |= FL_DEAD; ag[b * kMapE] = wb; h.y |= 1 << (8 + b); }
     }
     all_dead &= (wb & FL_DEAD) != 0;
   }
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   // ---- reset(mask) / autoreset: ONE call site (a random CtF episode lasts ~20 steps, so most warps take it every step)
   if (want_reset) {
     reset_one<FAMILY, MODE>(p, e, ag, r);
-    h.x = 0; h.w += 1;  // step_count = 0 (multigrid.py:141); episode counter
+    h.x = 0; h.y = 0; h.w += 1;  // step_count = 0 (multigrid.py:141); game_stats cleared (ctf.py:1068-1073); episode counter
   }
 
   // ---- state write-back (rows of padded envs of the last tile are written too: the planes are padded)

@@ -316,6 +316,14 @@ class CtfVecEnv(_MapVecEnv):
         self.blue_territory = cells(0) + [self.blue_flag]
         self.red_territory = cells(1) + [self.red_flag]
 
+    def game_stats(self):
+        """The reference's `env.game_stats` (ctf.py:1068-1073) for every env, as bool CUDA tensors.  Cleared by reset - with
+        same-step autoreset the finished episode's stats are gone when `step` returns, so read them with `autoreset=False`."""
+        st = self._planes["hdr"][:, 1]
+        bits = (st[:, None] >> (8 + torch.arange(self.n_agents, device=self.device))) & 1
+        return {"blue_agent_defeated": bits[:, :self.num_blue].bool(), "red_agent_defeated": bits[:, self.num_blue:].bool(),
+                "blue_flag_captured": (st & 1).bool(), "red_flag_captured": ((st >> 1) & 1).bool()}
+
     def positional_obs(self):
         """observation_option="positional" (ctf.py:1112-1135) as batched int64 CUDA tensors."""
         N, nb = self.num_envs, self.num_blue

@@ -193,7 +193,9 @@ typedef struct mg_map_config {
 enum { MG_MAP_PLANE_AGENTS = 0, /* u8  [N_pad][row]: agent i (blue first, n = num_blue + num_red) at bytes 4i .. 4i+3 =
                                    x, y (Agent.pos), dir (Agent.dir), flags (bit0 terminated / defeated, bit1 collided,
                                    agent.py:97-100); row = 4 * (n rounded up to a power of two) bytes */
-       MG_MAP_PLANE_HDR = 1,    /* i32 [N_pad][4]  step_count, 0, Philox block counter, episodes */
+       MG_MAP_PLANE_HDR = 1,    /* i32 [N_pad][4]  step_count, CtF game_stats bits (ctf.py:1068-1073: bit0 blue_flag_captured,
+                                   bit1 red_flag_captured, bit 8+i agent i defeated in a battle; cleared by reset), Philox block
+                                   counter, episodes */
        MG_MAP_PLANE_COUNT = 2 };
 
 /* Validation mode for the map families: recorded outputs of the reference's RNG call sites. */

@@ -148,7 +148,7 @@ def gen_ctf():
             e["obs"] = e["obs"].astype(np.uint8)
             e["init_obs"] = e["init_obs"].astype(np.uint8)
         out = rh.pack_episodes(eps, ["actions", "red_actions", "order", "n_battles", "blue_win", "obs", "reward", "terminated",
-                                     "truncated", "pos", "dir", "dead", "info"],
+                                     "truncated", "pos", "dir", "dead", "info", "stats_flags", "stats_defeated"],
                                ["field_map", "init_obs", "init_pos", "init_dir", "blue_place", "red_place", "init_info"])
         out["field_map"] = out["field_map"][0].astype(np.uint8)
         out["meta_num_blue"], out["meta_num_red"] = np.array(nb), np.array(nr)
@@ -167,7 +167,8 @@ def gen_ctf1v1():
         e["obs"] = e["obs"].astype(np.uint8)
         e["init_obs"] = e["init_obs"].astype(np.uint8)
     out = rh.pack_episodes(eps, ["actions", "red_actions", "n_battles", "blue_win", "obs", "reward", "terminated", "truncated",
-                                 "pos", "dir", "dead", "info"], ["field_map", "init_obs", "init_pos", "blue_place", "red_place", "init_info"])
+                                 "pos", "dir", "dead", "info", "stats_flags", "stats_defeated"],
+                           ["field_map", "init_obs", "init_pos", "blue_place", "red_place", "init_info"])
     out["field_map"] = out["field_map"][0].astype(np.uint8)
     path_out = os.path.join(OUT, "ctf1v1.npz")
     np.savez_compressed(path_out, **out)

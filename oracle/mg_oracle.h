@@ -137,6 +137,7 @@ typedef struct {
   uint8_t* flags;      /* [N][n] bit0 = terminated (defeated), bit1 = collided  (ctf only) */
   int32_t* step_count; /* [N] */
   uint32_t* rng_ctr;   /* [N] */
+  int32_t* stats;      /* [N] or NULL: CtF game_stats bits (ctf.py:1068-1073): 0 blue_flag_captured, 1 red_flag_captured, 8+i agent i defeated in a battle */
 } oc_map_state;
 
 typedef struct {

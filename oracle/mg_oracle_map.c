@@ -180,6 +180,7 @@ int oc_ctf_reset(const oc_map_cfg* c, int64_t N, oc_map_state* st, const uint8_t
         st->rng_ctr[e] = r.ctr;
       }
       ctf_reset_env(c, st->pos + e * n * 2, st->dir + e * n, st->flags + e * n, st->step_count + e, bp, rp);
+      if (st->stats) st->stats[e] = 0;
     }
     if (obs) ctf_encode(c, st->pos + e * n * 2, st->flags + e * n, obs + e * S * S);
   }
@@ -227,8 +228,9 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
       for (int i = 0; i < nb; ++i) if (fl[i] & 2) { rew -= c->obstacle_penalty; fl[i] |= 1; }
       for (int i = nb; i < n; ++i) if (fl[i] & 2) fl[i] |= 1;
     }
-    for (int i = 0; i < nb; ++i) if (pos[2 * i] * S + pos[2 * i + 1] == rflag) { rew += c->flag_reward; term = 1; } /* :1335-1344 */
-    for (int i = nb; i < n; ++i) if (pos[2 * i] * S + pos[2 * i + 1] == bflag) { rew -= c->flag_reward; term = 1; } /* :1347-1356 */
+    int32_t gs = st->stats ? st->stats[e] : 0; /* game_stats (ctf.py:1068-1073): bit0 blue_flag_captured, bit1 red_flag_captured, bit 8+i agent i defeated in a battle */
+    for (int i = 0; i < nb; ++i) if (pos[2 * i] * S + pos[2 * i + 1] == rflag) { rew += c->flag_reward; term = 1; gs |= 2; } /* :1335-1344 */
+    for (int i = nb; i < n; ++i) if (pos[2 * i] * S + pos[2 * i + 1] == bflag) { rew -= c->flag_reward; term = 1; gs |= 1; } /* :1347-1356 */
     int nbattle = 0;
     for (int b = 0; b < nb; ++b) /* np.where(distances <= battle_range): row-major, blue-major (:1368-1377) */
       for (int q = 0; q < nr; ++q) {
@@ -246,9 +248,9 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
           blue_win = (double)p_u32(&r) * (1.0 / 4294967296.0) < pb;
         }
         ++nbattle;
-        if (blue_win) { rew += c->battle_reward; fl[nb + q] |= 1; } /* :1409-1418 */
-        else if (c->variant_1v1) { rew -= c->battle_reward; term = 1; } /* 1v1: blue losing ends the episode (ctf.py:629-632) */
-        else { rew -= c->battle_reward; fl[b] |= 1; }
+        if (blue_win) { rew += c->battle_reward; fl[nb + q] |= 1; gs |= 1 << (8 + nb + q); } /* :1409-1418 */
+        else if (c->variant_1v1) { rew -= c->battle_reward; term = 1; gs |= 1 << 8; } /* 1v1: blue losing ends the episode (ctf.py:629-636) */
+        else { rew -= c->battle_reward; fl[b] |= 1; gs |= 1 << (8 + b); }
       }
     if (rng->mode == 0 && rng->battles_used) rng->battles_used[e] = nbattle;
     int all_dead = 1;
@@ -256,7 +258,9 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
     if (all_dead) term = 1;                  /* :1423 */
     rew -= c->step_penalty * nb;             /* :1428; 1v1: reward -= step_penalty (:646), nb == 1 */
     reward[e] = rew; terminated[e] = term; truncated[e] = trunc;
+    if (st->stats) st->stats[e] = gs;
     if (autoreset && (term || trunc)) {
+      if (st->stats) st->stats[e] = 0;
       if (final_obs) ctf_encode(c, pos, fl, final_obs + e * S * S);
       int bp[OC_MAX_CTF_AGENTS], rp[OC_MAX_CTF_AGENTS];
       if (rng->mode == 0) {

@@ -217,7 +217,7 @@ class MapCfg(C.Structure):
 
 class MapState(C.Structure):
     _fields_ = [("pos", C.c_void_p), ("dir", C.c_void_p), ("flags", C.c_void_p), ("step_count", C.c_void_p),
-                ("rng_ctr", C.c_void_p)]
+                ("rng_ctr", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class MapRng(C.Structure):
@@ -260,13 +260,19 @@ class _MapOracle:
         self.flags = np.zeros((self.N, n_agents), np.uint8)
         self.step_count = np.zeros(self.N, np.int32)
         self.rng_ctr = np.zeros(self.N, np.uint32)
+        self.stats = np.zeros(self.N, np.int32)    # CtF game_stats bits (mg_oracle.h)
         self.status = C.c_int32(0)
 
     def _state(self):
         s = MapState()
         s.pos, s.dir, s.flags = _p(self.pos), _p(self.dir), _p(self.flags)
-        s.step_count, s.rng_ctr = _p(self.step_count), _p(self.rng_ctr)
+        s.step_count, s.rng_ctr, s.stats = _p(self.step_count), _p(self.rng_ctr), _p(self.stats)
         return s
+
+    def game_stats(self):
+        """(flags [N, 2] = blue_flag_captured, red_flag_captured; defeated [N, n]) as the reference's game_stats dict holds them."""
+        st = self.stats
+        return np.stack([st & 1, (st >> 1) & 1], 1).astype(np.uint8), ((st[:, None] >> (8 + np.arange(self.n))) & 1).astype(np.uint8)
 
     def info(self):
         """`_get_info()` of every env: float64 [N, 2] (Maze) or [N, 11] (CtF), columns in the reference dict's key order."""

@@ -337,7 +337,7 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
         del log[:]
         n = num_blue + num_red
         rec = dict(actions=[], red_actions=[], order=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[],
-                   truncated=[], pos=[], dir=[], dead=[], info=[])
+                   truncated=[], pos=[], dir=[], dead=[], info=[], stats_flags=[], stats_defeated=[])
         init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
         init_dir = np.array([a.dir for a in env.agents], np.int8)
         while True:
@@ -361,6 +361,9 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
             rec["dir"].append(np.array([a.dir for a in env.agents], np.int8))
             rec["dead"].append(np.array([a.terminated for a in env.agents], np.uint8))
             rec["info"].append(np.array([info[k] for k in CTF_INFO_KEYS], np.float64))
+            gs = env.game_stats   # ctf.py:1068-1073
+            rec["stats_flags"].append(np.array([gs["blue_flag_captured"], gs["red_flag_captured"]], np.uint8))
+            rec["stats_defeated"].append(np.array(list(gs["blue_agent_defeated"]) + list(gs["red_agent_defeated"]), np.uint8))
             if term or trunc:
                 break
     L = len(rec["actions"])
@@ -448,7 +451,7 @@ def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battle
         assert len(place) == 2
         del log[:]
         rec = dict(actions=[], red_actions=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[], truncated=[],
-                   pos=[], dir=[], dead=[], info=[])
+                   pos=[], dir=[], dead=[], info=[], stats_flags=[], stats_defeated=[])
         init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
         while True:
             a = int(action_rng.integers(0, 5))
@@ -469,6 +472,9 @@ def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battle
             rec["dir"].append(np.array([a_.dir for a_ in env.agents], np.int8))
             rec["dead"].append(np.array([0, int(env._is_red_agent_defeated)], np.uint8))
             rec["info"].append(np.array([info[k] for k in CTF_INFO_KEYS], np.float64))
+            gs = env.game_stats   # ctf.py:340-345
+            rec["stats_flags"].append(np.array([gs["blue_flag_captured"], gs["red_flag_captured"]], np.uint8))
+            rec["stats_defeated"].append(np.array(list(gs["blue_agent_defeated"]) + list(gs["red_agent_defeated"]), np.uint8))
             if term or trunc:
                 break
     L = len(rec["actions"])

@@ -85,6 +85,10 @@ def test_ctf_replay_bit_exact(stem, cuda_device):
         assert np.array_equal(_np(env.agent_terminated)[live], _tile(g["dead"][:, t], k)[live].astype(bool))
         assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
         assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1)[live], _tile(g["info"][:, t], k)[live]), f"step {t}: info"
+        gs = env.game_stats()
+        assert np.array_equal(np.stack([_np(gs["blue_flag_captured"]), _np(gs["red_flag_captured"])], 1)[live], _tile(g["stats_flags"][:, t], k)[live].astype(bool))
+        assert np.array_equal(np.concatenate([_np(gs["blue_agent_defeated"]), _np(gs["red_agent_defeated"])], 1)[live],
+                              _tile(g["stats_defeated"][:, t], k)[live].astype(bool)), f"step {t}: game_stats"
     assert env.status() == 0
     env.close()
 
@@ -252,6 +256,10 @@ def test_ctf1v1_replay_and_philox(cuda_device):
         assert np.array_equal(_np(trunc)[live], _tile(g["truncated"][:, t], k)[live])
         assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][:, t], k)[live])
         assert np.array_equal(np.stack([_np(v) for v in env.get_info().values()], 1)[live], _tile(g["info"][:, t], k)[live]), f"step {t}: info"
+        gs = env.game_stats()
+        assert np.array_equal(np.stack([_np(gs["blue_flag_captured"]), _np(gs["red_flag_captured"])], 1)[live], _tile(g["stats_flags"][:, t], k)[live].astype(bool))
+        assert np.array_equal(np.concatenate([_np(gs["blue_agent_defeated"]), _np(gs["red_agent_defeated"])], 1)[live],
+                              _tile(g["stats_defeated"][:, t], k)[live].astype(bool)), f"step {t}: game_stats"
     assert env.status() == 0
     env.close()
     n = 3000

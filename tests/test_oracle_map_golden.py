@@ -52,6 +52,8 @@ def test_ctf_matches_reference(stem):
         assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal(o.dir[live], g["dir"][live, t])
         assert np.array_equal((o.flags & 1)[live], g["dead"][live, t]) and np.array_equal(used[live], g["n_battles"][live, t])
         assert np.array_equal(o.info()[live], g["info"][live, t]), f"step {t}: _get_info (float64, bit-exact)"
+        gf, gd = o.game_stats()
+        assert np.array_equal(gf[live], g["stats_flags"][live, t]) and np.array_equal(gd[live], g["stats_defeated"][live, t]), f"step {t}: game_stats"
     assert o.status.value == 0
 
 
@@ -90,3 +92,5 @@ def test_ctf1v1_matches_reference():
         assert np.array_equal(o.pos[live], g["pos"][live, t]) and np.array_equal((o.flags & 1)[live], g["dead"][live, t])
         assert np.array_equal(used[live], g["n_battles"][live, t])
         assert np.array_equal(o.info()[live], g["info"][live, t])
+        gf, gd = o.game_stats()
+        assert np.array_equal(gf[live], g["stats_flags"][live, t]) and np.array_equal(gd[live], g["stats_defeated"][live, t])
