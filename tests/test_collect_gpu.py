@@ -219,3 +219,48 @@ def test_create_rejects_bad_configs(cuda_device):
         CollectVecEnv(4, size=10, num_balls=16, layout="quadrants_respawn")
     with pytest.raises(ValueError):
         CollectVecEnv(4, device="cpu")
+
+
+# (size, agents_index, balls_index, balls_reward, num_balls, respawn, layout, time_limit, n)
+SWEEP = [
+    (5, [4], [1], [2.5], 3, True, "even_dist", 7, 70),                      # smallest useful grid, one agent, one ball type
+    (7, [3, 5, 8], [0, 2], [1, -1], 6, False, "even_dist", 0, 131),          # three agents, negative reward, terminates
+    (9, [3, 5, 1, 2], [0, 1, 2, 4], [1, 2, 3, 4], 8, True, "even_dist", 20, 65),
+    (12, [3, 5], [0, 1, 2], [1, 1, 1], 12, True, "quadrants_respawn", 30, 257),
+    (16, [3, 5], [0, 1, 2, 3], [1, 1, 1, 1], 16, False, "quadrants", 40, 100),
+    (11, [3, 5, 6], [0, 1, 2], [1, 1, 1], 9, True, "rooms", 25, 90),
+    (20, [0, 9, 3, 5, 6, 7, 1, 2], [4], [0.5], 10, True, "even_dist", 15, 64),  # eight agents (MG_MAX_AGENTS), fractional reward
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP, ids=[f"{c[6]}-{c[0]}x{c[0]}-A{len(c[1])}-nb{len(c[2])}" for c in SWEEP])
+def test_config_sweep_matches_oracle(cfg, cuda_device):
+    """Grid sizes, agent counts, ball-type counts, rewards and layouts the registered ids never use: CUDA == oracle for the
+    step (with autoreset and final observations), partial views, the toroid wrapper and Grid.encode."""
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    size, agents, balls, rewards, num_balls, respawn, layout, tl, n = cfg
+    kw = dict(size=size, agents_index=agents, balls_index=balls, balls_reward=rewards, num_balls=num_balls, respawn=respawn, layout=layout)
+    env = CollectVecEnv(n, max_episode_steps=tl or None, seed=77, env_id_base=5, **kw)
+    env.enable_final_observation()
+    o = oc.CollectOracle(oc.make_collect_cfg(time_limit=tl, **kw), n)
+    r = oc.PhiloxRng(seed=77, env_id_base=5)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(size)
+    A = len(agents)
+    for t in range(60):
+        act = rng.integers(0, 4, size=(n, A)).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=cuda_device))
+        oobs, orew, oterm, otrunc, ofin = o.step(act, r, autoreset=True, want_final_obs=True)
+        assert np.array_equal(_np(obs), oobs) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc), f"step {t}: flags"
+        d = oterm | otrunc
+        assert np.array_equal(_np(info["final_observation"])[d], ofin[d])
+        assert np.array_equal(_np(env.grid), o.grid) and np.array_equal(_np(env.pickups).reshape(n, -1), o.info)
+    dirs = rng.integers(0, 4, size=(n, A)).astype(np.uint8)
+    for V in (3, 5, 7, 6):
+        assert np.array_equal(_np(env.gen_obs(V, False, dirs=dirs)), oc.partial_view3(o.grid, o.agent_pos, size, size, V, False, dirs=dirs))
+    assert np.array_equal(_np(env.toroid_obs()), oc.toroid(o.grid, o.agent_pos, size, len(balls)))
+    assert np.array_equal(_np(env.encode()), oobs) and env.status() == 0
+    env.close()
