@@ -27,7 +27,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic", "mg_map_info", "mg_set_partial_obs",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic", "mg_map_info", "mg_set_partial_obs", "mg_host_layout",
 ]
 
 
@@ -130,6 +130,8 @@ def load():
     lib.mg_create_wildfire.argtypes = [C.POINTER(WildfireConfig), C.c_int, C.POINTER(C.c_void_p)]
     lib.mg_create_generic.restype = C.c_int
     lib.mg_create_generic.argtypes = [C.POINTER(GenericConfig), C.c_int, C.POINTER(C.c_void_p)]
+    lib.mg_host_layout.restype = C.c_int
+    lib.mg_host_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_size_t)] * 4
     lib.mg_set_partial_obs.restype = C.c_int
     lib.mg_set_partial_obs.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.mg_map_info.restype = C.c_int
@@ -145,3 +147,19 @@ def load():
 def last_error(handle=None) -> str:
     msg = load().mg_last_error(handle)
     return msg.decode() if msg else ""
+
+
+def host_result_buffers(lib, handle, obs_shape, obs_dtype, n, rew_cols):
+    """Page-locked host buffers for mg_step_host laid out as mg_host_layout asks (one block -> one D2H copy per step):
+    returns (block, obs, rewards, terminated, truncated) torch tensors sharing the block's memory."""
+    import torch
+    offs = [C.c_size_t() for _ in range(4)]
+    if lib.mg_host_layout(handle, *[C.byref(o) for o in offs]) != 0:
+        raise RuntimeError("mg_host_layout failed")
+    off_r, off_t, off_u, total = (o.value for o in offs)
+    block = torch.zeros(total, dtype=torch.uint8, pin_memory=True)
+    nobs = int(torch.tensor(obs_shape).prod()) * torch.empty((), dtype=obs_dtype).element_size()
+    obs = block[:nobs].view(obs_dtype).view(*obs_shape)
+    rew = block[off_r: off_r + n * rew_cols * 8].view(torch.float64)
+    rew = rew.view(n, rew_cols) if rew_cols > 1 else rew.view(n)
+    return block, obs, rew, block[off_t: off_t + n], block[off_u: off_u + n]

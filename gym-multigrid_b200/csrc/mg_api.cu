@@ -231,8 +231,7 @@ extern "C" int mg_destroy(mg_env* env) {
   cudaFree(env->d_status);
   cudaFree(env->d_wall_template);
   cudaFree(env->d_map_tables);
-  cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_rewards);
-  cudaFree(env->d_term); cudaFree(env->d_trunc); cudaFree(env->d_final);
+  cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);   // rewards / term / trunc live inside the d_obs block
   delete env;
   return 0;
 }
@@ -491,6 +490,9 @@ extern "C" int mg_set_partial_obs(mg_env* env, int view_size, int see_through_wa
     p.view_oob = mg::cell(3, 7, 1); p.view_agent = mg::cell(1, 4, 0);   // as mg_gen_obs: out-of-map filler, Agent(color="blue")
   }
   p.view_V = view_size; p.view_see_through = see_through_walls != 0;
+  // the observation size changed: mg_step_host re-creates its device staging block on the next call
+  cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);
+  env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr; env->d_final = nullptr;
   return 0;
 }
 
@@ -789,6 +791,23 @@ extern "C" int mg_toroid_obs(mg_env* env, const void* state, float* out, void* s
   return 0;
 }
 
+static size_t env_count(const mg_env* env) {
+  return (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs
+                  : env->family == MG_FAMILY_GENERIC ? env->gcfg.num_envs : env->mcfg.num_envs);
+}
+static void host_layout(const mg_env* env, size_t* off_rewards, size_t* off_term, size_t* off_trunc, size_t* total) {
+  const size_t N = env_count(env), R = (size_t)env->rew_cols;
+  *off_rewards = align_up(mg_obs_bytes(env), 256);
+  *off_term = align_up(*off_rewards + N * R * sizeof(double), 256);
+  *off_trunc = align_up(*off_term + N, 256);
+  *total = align_up(*off_trunc + N, 256);
+}
+extern "C" int mg_host_layout(const mg_env* env, size_t* off_rewards, size_t* off_terminated, size_t* off_truncated, size_t* total_bytes) {
+  if (!env || !off_rewards || !off_terminated || !off_truncated || !total_bytes) return -1;
+  host_layout(env, off_rewards, off_terminated, off_truncated, total_bytes);
+  return 0;
+}
+
 extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void* stream) {
   if (!env || !state || !io) return fail(env, "mg_step_host: null argument");
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step_host: actions/rewards/terminated/truncated must be non-null");
@@ -797,12 +816,16 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs : env->family == MG_FAMILY_GENERIC ? env->gcfg.num_envs : env->mcfg.num_envs);
   const size_t A = (size_t)env->act_cols, R = (size_t)env->rew_cols, ob = mg_obs_bytes(env);
+  // device staging: ONE block laid out obs | rewards | terminated | truncated (256-byte aligned parts, see mg_host_layout):
+  // a caller whose host buffers use the same layout gets a single device-to-host copy per step
+  size_t off_r, off_t, off_u, total;
+  host_layout(env, &off_r, &off_t, &off_u, &total);
   if (!env->d_actions) {
     if ((ce = cudaMalloc(&env->d_actions, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_obs, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_rewards, N * R * sizeof(double))) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_term, N)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_trunc, N)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMalloc(&env->d_obs, total)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMemsetAsync(env->d_obs, 0, total, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
+    env->d_rewards = reinterpret_cast<double*>(env->d_obs + off_r);
+    env->d_term = env->d_obs + off_t; env->d_trunc = env->d_obs + off_u;
   }
   if (io->final_obs && !env->d_final) {
     if ((ce = cudaMalloc(&env->d_final, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
@@ -813,10 +836,16 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
   dio.actions = env->d_actions; dio.obs = io->obs ? static_cast<uint8_t*>(static_cast<void*>(env->d_obs)) : nullptr; dio.rewards = env->d_rewards;
   dio.terminated = env->d_term; dio.truncated = env->d_trunc; dio.final_obs = io->final_obs ? env->d_final : nullptr;
   if (step_device(env, state, &dio, st)) return -1;
-  if (io->obs && (ce = cudaMemcpyAsync(io->obs, env->d_obs, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H obs", ce);
-  if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, N * R * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards", ce);
-  if ((ce = cudaMemcpyAsync(io->terminated, env->d_term, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H terminated", ce);
-  if ((ce = cudaMemcpyAsync(io->truncated, env->d_trunc, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H truncated", ce);
+  const uint8_t* hb = static_cast<const uint8_t*>(static_cast<const void*>(io->obs));
+  const bool one_copy = io->obs && reinterpret_cast<const uint8_t*>(io->rewards) == hb + off_r && io->terminated == hb + off_t && io->truncated == hb + off_u;
+  if (one_copy) {
+    if ((ce = cudaMemcpyAsync(io->obs, env->d_obs, total, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H results", ce);
+  } else {
+    if (io->obs && (ce = cudaMemcpyAsync(io->obs, env->d_obs, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H obs", ce);
+    if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, N * R * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards", ce);
+    if ((ce = cudaMemcpyAsync(io->terminated, env->d_term, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H terminated", ce);
+    if ((ce = cudaMemcpyAsync(io->truncated, env->d_trunc, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H truncated", ce);
+  }
   if (io->final_obs && (ce = cudaMemcpyAsync(io->final_obs, env->d_final, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H final_obs", ce);
   if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
   return 0;

@@ -152,10 +152,9 @@ class _MapVecEnv:
     def step_host(self, actions):
         if self._host is None:
             N, S = self.num_envs, self.size
-            pin = dict(pin_memory=True)
-            self._host = dict(act=torch.zeros((N, self.num_blue), dtype=torch.int8, **pin),
-                              obs=torch.zeros(tuple(self._obs.shape), dtype=self._obs.dtype, **pin), rew=torch.zeros(N, dtype=torch.float64, **pin),
-                              term=torch.zeros(N, dtype=torch.uint8, **pin), trunc=torch.zeros(N, dtype=torch.uint8, **pin))
+            blk, obs, rew, term, trunc = _lib.host_result_buffers(self._lib, self._h, tuple(self._obs.shape), self._obs.dtype, N, 1)
+            self._host = dict(act=torch.zeros((N, self.num_blue), dtype=torch.int8, pin_memory=True), obs=obs, rew=rew, term=term,
+                              trunc=trunc, block=blk)
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
         h = self._host
         self._host_np["act"][...] = np.round(np.asarray(actions)).astype(np.int64).reshape(self.num_envs, self.num_blue)

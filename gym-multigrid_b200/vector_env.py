@@ -195,11 +195,9 @@ class CollectVecEnv:
         overwritten by the next call).  Host<->device copies and the wait are inside the call."""
         if self._host is None:
             N, W, H, A = self.num_envs, self.width, self.height, self.num_agents
-            pin = dict(pin_memory=True)
-            self._host = dict(
-                act=torch.zeros((N, A), dtype=torch.int8, **pin), obs=torch.zeros((N, W, H, 3), dtype=torch.uint8, **pin),
-                rew=torch.zeros((N, A), dtype=torch.float64, **pin), term=torch.zeros(N, dtype=torch.uint8, **pin),
-                trunc=torch.zeros(N, dtype=torch.uint8, **pin))
+            blk, obs, rew, term, trunc = _lib.host_result_buffers(self._lib, self._h, (N, W, H, 3), torch.uint8, N, A)
+            self._host = dict(act=torch.zeros((N, A), dtype=torch.int8, pin_memory=True), obs=obs, rew=rew.view(N, A), term=term,
+                              trunc=trunc, block=blk)
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
         h = self._host
         self._host_np["act"][...] = np.asarray(actions).reshape(self.num_envs, self.num_agents)

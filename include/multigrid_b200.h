@@ -143,6 +143,12 @@ int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stre
  * arrays; buffers should be page-locked for full PCIe bandwidth. */
 int mg_step_host(mg_env* env, void* state_dev, const mg_step_io* io_host, void* stream);
 
+/* Layout that lets mg_step_host return everything with ONE device-to-host copy: if the caller's host buffers are parts of one
+ * (page-locked) block with io->rewards = io->obs + *off_rewards, io->terminated = io->obs + *off_terminated, io->truncated =
+ * io->obs + *off_truncated (block size *total_bytes), the results travel in a single cudaMemcpyAsync; any other placement is
+ * served by one copy per array.  Offsets depend on the observation mode (mg_set_partial_obs). */
+int mg_host_layout(const mg_env* env, size_t* off_rewards, size_t* off_terminated, size_t* off_truncated, size_t* total_bytes);
+
 int mg_set_trace(mg_env* env, const mg_trace* trace_dev);
 
 /* device status word: read (synchronises the stream) and clear */
