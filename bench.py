@@ -247,6 +247,19 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
 
+    # for scale: a bare device-to-host copy of one step's result bytes into page-locked memory on this box
+    dsrc = torch.empty(n * (300 + 16 + 2), dtype=torch.uint8, device=dev)
+    hdst = torch.empty(n * (300 + 16 + 2), dtype=torch.uint8, pin_memory=True)
+    for _ in range(3):
+        hdst.copy_(dsrc, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    for _ in range(20):
+        hdst.copy_(dsrc, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    bare_d2h_gbps = 20 * dsrc.numel() / (time.perf_counter() - t1) / 1e9
+    del dsrc, hdst
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -279,7 +292,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": n * (300 + 16 + 2),
                     "steps": e2e_steps, "api": "CollectVecEnv.step(numpy) -> mg_step_host (pinned host buffers)",
                     "d2h_GBps_per_gpu": n * (300 + 16 + 2) / (e2e_ms_max * 1e-3 / e2e_steps) / 1e9,
-                    "note": "bound by the device-to-host copy of the observations (300 B/env over PCIe), not by the kernel"},
+                    "bare_d2h_copy_GBps": bare_d2h_gbps,
+                    "note": "bound by the device-to-host copy of the observations (300 B/env over PCIe), not by the kernel; "
+                            "bare_d2h_copy_GBps = the same bytes copied by torch alone on this box"},
             "gpu_launches": K_eff,
             "clocks": sampler.summary(),
         }
