@@ -6,8 +6,9 @@
 // (multigrid.py:526-528 vs grid.py:254) and raises; this follows the algorithm its pieces define.
 //
 // This path is instruction-issue bound, not HBM bound (147 output bytes per view need several hundred
-// instructions), so the fast kernel (odd V <= 7) is written for instruction count: one thread per view with
-// everything in registers (V is a template parameter, all loops unroll) -
+// instructions), so the fast kernel (odd V <= 7; per-view body in view_device.cuh, shared with map_kernel's fused Maze
+// mode) is written for instruction count: one thread per view with everything in registers (V is a template parameter,
+// all loops unroll) -
 //   * slice + rotations folded into one base index and two strides; cells are byte gathers from shared memory
 //     (Collect: the tile's grid slab, staged by one TMA bulk load, with guard bands so that out-of-grid reads need
 //     no predication; Maze: the static map pre-padded with the out-of-bounds filler, staged the same way);
@@ -16,7 +17,8 @@
 //   * the masked codes are packed four per register in output order, expanded to (type, colour, state) bytes with
 //     PRMT, re-aligned with one funnel shift per word and written to shared memory as 32-bit stores (the 147-byte
 //     view pitch spreads a warp over all 32 banks); the tile's contiguous slab of views leaves as one TMA bulk store.
-// Other view sizes (even V, V > 7) take the generic kernel below (runtime V, per-cell loops).
+// Other view sizes (even V, V > 7) take the generic kernel below (runtime V, per-cell loops).  view6_kernel is the
+// encode_dim-6 (DefaultWorld) variant for the generic family; toroid_fast_kernel the ToroidObservation wrapper.
 #include <cstdlib>
 
 #include "mg_device.cuh"

@@ -1,13 +1,15 @@
 // wildfire_kernels.cu -- the Wildfire EXTENSION (no reference code exists; the rules are specified in
 // include/multigrid_b200.h and restated by oracle/mg_oracle_wildfire.c).
 //
-// One CTA per env.  The env's terrain (one byte per cell) is staged in shared memory by a TMA bulk copy;
-// warp 0 resolves the agents' moves in the step's random order with lane = agent: the acting lane broadcasts
-// its target cell (__shfl_sync) and every other lane votes whether it stands there (__ballot_sync), which
-// reproduces the sequential, order-dependent blocking without an occupancy grid; fire spread is a
-// double-buffered 4-neighbour stencil over shared memory with one counter-based Philox block per group of
-// four cells (skipped when no cell of the group can change); the observation is expanded in shared memory
-// and leaves, like the new terrain, as one TMA bulk store.
+// One CTA per env.  Two kernels with identical results:
+//   wildfire_kernel       (any H): terrain staged in shared memory by a TMA bulk copy; warp 0 walks the agents in the step's
+//                         random order with lane = agent (the acting lane broadcasts its target with __shfl_sync, the others
+//                         vote with __ballot_sync whether they stand there); fire spread is a double-buffered per-cell
+//                         4-neighbour stencil with one Philox block per group of four cells.
+//   wildfire_fast_kernel  (H % 4 == 0, the one that runs for square power-of-two grids): word-parallel stencil and encode,
+//                         Philox only on the queued fire front, per-lane rank tracking + __match_any_sync conflict detection
+//                         so that only conflicting moves are resolved in order (see the comment above the kernel).
+// The observation is expanded in shared memory and leaves, like the new terrain, as one TMA bulk store.
 #include <cstdlib>
 
 #include "mg_device.cuh"
