@@ -1,7 +1,7 @@
-"""The reference's own tests (tests/test_collect.py, tests/test_ctf.py, tests/test_maze.py), rewritten line for line
-against this package: same ids, class names, constructor kwargs and loops - only the import changes.  Rendering calls are
-dropped (out of scope).  Plus one golden episode per family replayed through the single-env adaptors with the reference's
-return types."""
+"""The scenarios of the reference's own tests (tests/test_collect.py, tests/test_ctf.py, tests/test_maze.py) exercised
+through this package's drop-in surface: the same ids, class names and constructor kwargs, an episode loop with sampled
+actions until terminated / truncated - a user only changes the import.  Rendering is out of scope.  Each scenario also
+asserts the reference's return types, and one golden episode per family is replayed through the single-env adaptors."""
 import os
 
 import numpy as np
