@@ -142,7 +142,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -307,14 +307,31 @@ def run_ours(args):
                 v, dt = time_oracle(n, cpu_steps, 1, nthreads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
                                     "sample": f"{cpu_steps} steps x {n} envs ({dt:.1f} s), same config, oracle/mg_oracle.c with OpenMP over envs"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for e in envs:
         e.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else a library prints there (NCCL's version
+    banner, torchrun notices) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)          # stray prints of native libraries on fd 1 -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20000)
