@@ -482,13 +482,15 @@ cudaError_t configure_wildfire_kernel(int cells, int H) {
   if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<64, 1>, (size_t)bytes)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<128, 1>, (size_t)bytes)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<64, 4>, (size_t)bytes)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)wildfire_fast_kernel<256, 4>, (size_t)bytes)) != cudaSuccess) return e;
   return raise_smem_limit((const void*)wildfire_fast_kernel<128, 4>, (size_t)bytes);
 }
 
 cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
   const bool fast = wf_fast(p.H);
   const bool vec = (p.H & 15) == 0;   // rows are whole 16-byte vectors
-  const int threads = fast ? (p.cells / (vec ? 16 : 4) >= 256 ? 128 : 64) : kWfThreads;
+  const int items = p.cells / (vec ? 16 : 4);   // words / vectors one CTA sweeps
+  const int threads = fast ? (vec && items >= 1024 ? 256 : (items >= 256 ? 128 : 64)) : kWfThreads;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.N); cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = wildfire_smem_bytes(p.cells, p.H); cfg.stream = st;
@@ -498,6 +500,7 @@ cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
   static const bool pdl = [] { const char* v = std::getenv("MG_PDL"); return !(v && v[0] == '0'); }();
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   if (!fast) return cudaLaunchKernelEx(&cfg, wildfire_kernel, p);
+  if (vec && threads == 256) return cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<256, 4>, p);
   if (vec) return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128, 4>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64, 4>, p);
   return threads == 128 ? cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<128, 1>, p) : cudaLaunchKernelEx(&cfg, wildfire_fast_kernel<64, 1>, p);
 }

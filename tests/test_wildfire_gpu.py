@@ -14,7 +14,7 @@ def _np(t):
 
 
 @pytest.mark.parametrize("size,A,fires,n", [(16, 5, 3, 300), (64, 16, 4, 96), (32, 32, 6, 128), (8, 1, 1, 257), (4, 2, 2, 65),
-                                            ((8, 10), 6, 3, 130), ((12, 20), 7, 5, 90), ((24, 6), 4, 2, 70)])
+                                            ((8, 10), 6, 3, 130), ((12, 20), 7, 5, 90), ((24, 6), 4, 2, 70), (128, 9, 5, 40)])
 def test_wildfire_matches_oracle(size, A, fires, n, cuda_device):
     """Square grids and W x H grids; H % 4 == 0 takes the word-parallel kernel, other heights the generic one."""
     import gym_multigrid_b200 as mg

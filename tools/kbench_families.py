@@ -147,7 +147,7 @@ def bench_view(args):
 
 
 def bench_wildfire(args):
-    for size, A, n in ((64, 16, 16384), (64, 16, 131072), (32, 32, 65536)):
+    for size, A, n in ((64, 16, 16384), (64, 16, 131072), (64, 32, 131072), (128, 32, 32768), (32, 32, 65536)):
         cells = size * size
         bpe = A + 2 * (cells + 4 * A + 16) + 3 * cells + 8 * A + 2
         B = batches_for(bpe, n, lo=2, hi=8)
