@@ -51,9 +51,38 @@ __device__ __forceinline__ int respawn(const CollectParams& p, uint8_t* g, Rng<M
   return x * p.H + y;  // the cell that received the ball
 }
 
+// One object of a _gen_grid placement sequence: its cell code and the inclusive box it is rejection-sampled in
+// (place_obj, multigrid.py:282-339: [top, min(top + size, dim - 1)]).
+struct Placement { uint8_t code; int tx, ty, hx, hy; };
+__device__ __forceinline__ Placement boxed(const CollectParams& p, uint8_t code, int tx, int ty, int sx, int sy) {
+  Placement q;
+  q.code = code; q.tx = tx; q.ty = ty; q.hx = min(tx + sx, p.W - 1); q.hy = min(ty + sy, p.H - 1);
+  return q;
+}
+
+// Places objects 0 .. count-1 of a sequence, `spec(k)` describing the k-th one, in ONE loop over candidate draws: a lane
+// whose candidate was accepted moves on to its next object instead of idling until the slowest lane of the warp has placed
+// the current one (nested per-object rejection loops cost the sum of per-object maxima over the warp; this costs the
+// maximum of per-lane totals).  The env's draw sequence is the same as with nested loops, so results are unchanged.
+template <int MODE, typename Spec, typename Placed>
+__device__ __forceinline__ void place_sequence(const CollectParams& p, uint8_t* g, Rng<MODE>& r, int count, Spec&& spec, Placed&& placed) {
+  if (count <= 0) return;
+  int k = 0;
+  Placement q = spec(0);
+  while (k < count) {
+    int x, y;
+    r.rand_pair(q.tx, q.hx, q.ty, q.hy, x, y);
+    if (MODE == 0 && (r.err & MG_ERR_TRACE_OVERFLOW)) return;  // trace exhausted: leave the rest unplaced
+    if (GCELL(g, p.H, x, y) != 0) continue;
+    GCELL(g, p.H, x, y) = q.code;
+    placed(k, x, y);
+    if (++k < count) q = spec(k);
+  }
+}
+
 // CollectGameEnv.reset (collect_game.py:107-119) + the layout's _gen_grid.  `g`, `pos` live in smem.
 template <int MODE>
-__device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8_t* pos, Rng<MODE>& r) {
+__device__ __forceinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8_t* pos, Rng<MODE>& r) {
   const int W = p.W, H = p.H, A = p.A, nb = p.nb;
   // Grid(width, height) + border walls (+ the Rooms inner walls): copied from the handle's template
   // (grid.py:66-89; collect_game.py:239-243, 269-273, 309-320, 379-382)
@@ -64,22 +93,18 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
   } else {
     for (int i = 0; i < p.cells; ++i) g[i] = __ldg(p.wall_template + i);
   }
-  int x, y;
-  if (p.layout == MG_LAYOUT_EVEN_DIST) {  // collect_game.py:236-259
-    const int per = p.num_balls / nb;
-    for (int t = 0; t < nb; ++t)
-      for (int b = 0; b < per; ++b) place_obj<MODE>(p, g, r, cell(T_BALL, p.ball_colour[t], 0), 0, 0, W, H, x, y);
-    for (int i = 0; i < A; ++i) {  // place_agent(a): anywhere empty (multigrid.py:364-369)
-      place_obj<MODE>(p, g, r, p.agent_code[i], 0, 0, W, H, x, y);
-      pos[2 * i] = (uint8_t)x; pos[2 * i + 1] = (uint8_t)y;
-    }
+  auto nothing = [](int, int, int) {};
+  if (p.layout == MG_LAYOUT_EVEN_DIST) {  // collect_game.py:236-259: balls anywhere, then place_agent(a) anywhere empty (multigrid.py:364-369)
+    const int per = p.num_balls / nb, balls = per * nb;
+    place_sequence<MODE>(p, g, r, balls + A,
+                         [&](int k) { return boxed(p, k < balls ? cell(T_BALL, p.ball_colour[k / per], 0) : p.agent_code[k - balls], 0, 0, W, H); },
+                         [&](int k, int x, int y) { if (k >= balls) { pos[2 * (k - balls)] = (uint8_t)x; pos[2 * (k - balls) + 1] = (uint8_t)y; } });
   } else if (p.layout == MG_LAYOUT_QUADRANTS) {  // collect_game.py:266-300
     const int per = p.num_balls / nb;
-    for (int t = 0; t < nb; ++t) {
-      const int tx = (t == 1 || t == 2) ? W / 2 - 1 : 0, ty = t == 1 ? H / 2 - 1 : (t == 3 ? H / 2 : 0);
-      for (int b = 0; b < per; ++b)
-        place_obj<MODE>(p, g, r, cell(T_BALL, p.ball_colour[t], 0), tx, ty, W / 2 - 1, H / 2 - 1, x, y);
-    }
+    place_sequence<MODE>(p, g, r, per * nb, [&](int k) {
+      const int t = k / per;
+      return boxed(p, cell(T_BALL, p.ball_colour[t], 0), (t == 1 || t == 2) ? W / 2 - 1 : 0, t == 1 ? H / 2 - 1 : (t == 3 ? H / 2 : 0), W / 2 - 1, H / 2 - 1);
+    }, nothing);
     for (int i = 0; i < A; ++i) {  // place_agent(a, pos): overwrites (put_obj multigrid.py:341-348)
       GCELL(g, H, 1 + i, H - 2) = p.agent_code[i];
       pos[2 * i] = (uint8_t)(1 + i); pos[2 * i + 1] = (uint8_t)(H - 2);
@@ -95,30 +120,22 @@ __device__ __noinline__ void reset_env(const CollectParams& p, uint8_t* g, uint8
     }
     const int ps = W / 2 - 1;
     const int num_ball = (int)nearbyint((double)p.num_balls / nb);  // python round(): half-to-even
-    int index = -1, tx = 0, ty = 0, left = 0;
-    for (int ball = 0; ball < p.num_balls; ++ball, --left) {
-      if (left == 0) {  // ball % num_ball == 0
-        ++index; left = num_ball;
-        tx = (index == 1 || index == 2) ? m + 1 : 0;
-        ty = (index == 1 || index == 3) ? m + 1 : 0;
-        // the extra ball of this colour in partition 3 (:349-355)
-        place_obj<MODE>(p, g, r, cell(T_BALL, p.ball_colour[index], 0), 0, m + 1, ps, ps, x, y);
-      }
-      place_obj<MODE>(p, g, r, cell(T_BALL, p.ball_colour[index], 0), tx, ty, ps, ps, x, y);
-    }
+    // per colour index: one extra ball in partition 3 (:349-355), then that colour's balls in its own partition
+    // (num_ball == 0: the reference's countdown never returns to zero, so colour 0 gets one extra ball and every ball)
+    const int group = num_ball > 0 ? num_ball + 1 : 0x7fffffff;
+    const int groups = num_ball > 0 ? (p.num_balls + num_ball - 1) / num_ball : (p.num_balls > 0 ? 1 : 0);
+    place_sequence<MODE>(p, g, r, p.num_balls + groups, [&](int k) {
+      const int index = k / group, j = k - index * group;
+      const uint8_t code = cell(T_BALL, p.ball_colour[index], 0);
+      if (j == 0) return boxed(p, code, 0, m + 1, ps, ps);
+      return boxed(p, code, (index == 1 || index == 2) ? m + 1 : 0, (index == 1 || index == 3) ? m + 1 : 0, ps, ps);
+    }, nothing);
   } else {  // MG_LAYOUT_QUADRANTS_RESPAWN, collect_game.py:376-399
     const int per = p.num_balls / 3;
-    int index = -1, tx = 0, ty = 0, left = 0;
-    for (int ball = 0; ball < p.num_balls; ++ball) {
-      if (left == 0) {  // ball % per == 0
-        ++index; left = per;
-        tx = index == 0 ? 0 : W / 2 - 1;
-        ty = index == 1 ? H / 2 - 1 : 0;
-      }
-      --left;
-      // Ball(self.world, index, 1): the colour IS the partition index (:391)
-      place_obj<MODE>(p, g, r, cell(T_BALL, index, 0), tx, ty, W / 2 + 1, H / 2 + 1, x, y);
-    }
+    place_sequence<MODE>(p, g, r, p.num_balls, [&](int k) {
+      const int index = per > 0 ? k / per : 0;  // Ball(self.world, index, 1): the colour IS the partition index (:391)
+      return boxed(p, cell(T_BALL, index, 0), index == 0 ? 0 : W / 2 - 1, index == 1 ? H / 2 - 1 : 0, W / 2 + 1, H / 2 + 1);
+    }, nothing);
     for (int i = 0; i < A; ++i) {
       GCELL(g, H, 1 + i, H - 2) = p.agent_code[i];
       pos[2 * i] = (uint8_t)(1 + i); pos[2 * i + 1] = (uint8_t)(H - 2);
