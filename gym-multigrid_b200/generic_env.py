@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .vector_base import VectorEnvSurface
 from .spaces import Box, Discrete, MultiDiscrete
 
 # DefaultWorld.OBJECT_TO_IDX (world.py:37-51)
@@ -22,7 +23,7 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-class GenericVecEnv:
+class GenericVecEnv(VectorEnvSurface):
     """`step(actions[N, A]) -> (obs u8 [N, A, W, H, 6], rewards f64 [N, A], terminated [N], truncated [N], info)`.
     The reference returns a list of A arrays per env (multigrid.py:476-481); axis 1 is that list."""
 

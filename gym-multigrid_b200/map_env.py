@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .vector_base import VectorEnvSurface
 from .spaces import Box, Discrete, MultiDiscrete
 
 
@@ -24,7 +25,7 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-class _MapVecEnv:
+class _MapVecEnv(VectorEnvSurface):
     family = None
     ref_dtype = None
 

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .vector_base import VectorEnvSurface
 from .spaces import Box, Discrete, MultiDiscrete
 
 # CollectGameEnv.keys (collect_game.py:48-55)
@@ -23,7 +24,7 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-class CollectVecEnv:
+class CollectVecEnv(VectorEnvSurface):
     """`num_envs` independent Collect games stepped in lockstep on `device`.
 
     Constructor kwargs are the reference's (collect_game.py:17-72: size, num_balls, agents_index,

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .vector_base import VectorEnvSurface
 from .spaces import Box, Discrete, MultiDiscrete
 
 
@@ -24,7 +25,7 @@ def thresholds(alpha: float, beta: float):
     return ign, min(2**32 - 1, int(math.floor(beta * 2.0**32)))
 
 
-class WildfireVecEnv:
+class WildfireVecEnv(VectorEnvSurface):
     def __init__(self, num_envs, size=64, num_agents=16, agents_index=None, num_fires=4, alpha=0.15, beta=0.05, max_steps=200,
                  device="cuda:0", seed=0, autoreset=True, env_id_base=0, width=None, height=None):
         self._lib = _lib.load()

@@ -113,3 +113,15 @@ def test_register_with_gymnasium_hands_over_every_id(monkeypatch):
     assert ids == ["b200/" + k for k in mg.registry] and len(calls) == len(mg.registry) == 9
     for kw in calls:
         assert callable(kw["entry_point"]) and callable(kw["vector_entry_point"]) and kw["max_episode_steps"] is None
+
+
+def test_vector_env_surface_is_shared_by_every_batched_class():
+    from gym_multigrid_b200.generic_env import GenericVecEnv
+    from gym_multigrid_b200.map_env import CtfVecEnv, MazeVecEnv
+    from gym_multigrid_b200.vector_base import VectorEnvSurface
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    from gym_multigrid_b200.wildfire_env import WildfireVecEnv
+    for cls in (CollectVecEnv, MazeVecEnv, CtfVecEnv, WildfireVecEnv, GenericVecEnv):
+        assert issubclass(cls, VectorEnvSurface)
+        for name in ("reset", "step", "close", "render", "get_attr", "unwrapped", "metadata"):
+            assert hasattr(cls, name), (cls.__name__, name)
