@@ -86,6 +86,7 @@ class _MapVecEnv(VectorEnvSurface):
             self._planes[name] = self.state[off.value: off.value + nbytes.value].view(dt).view(-1, cols)[:N]
         self._agents = self._planes["agents"].view(N, slots, 4)[:, :n]     # (x, y, dir, flags) per agent
         self._io = _lib.StepIO()
+        self._bound = None
         self._host = None
         self.with_info = False      # True: step() / reset() also return the reference's info dict (one more launch)
         self._trace_keepalive = None
@@ -142,13 +143,22 @@ class _MapVecEnv(VectorEnvSurface):
     def step(self, actions):
         if not isinstance(actions, torch.Tensor):
             return self.step_host(actions)
-        a = self._prep_actions(actions)
-        io = self._io
-        io.actions, io.obs, io.rewards = a.data_ptr(), self._obs.data_ptr(), self._rewards.data_ptr()
-        io.terminated, io.truncated = self._term.data_ptr(), self._trunc.data_ptr()
-        io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
-        self._check(self._lib.mg_step(self._h, _ptr(self.state), C.byref(io), self._stream()))
-        return self._obs, self._rewards, self._term.view(torch.bool), self._trunc.view(torch.bool), self._info()
+        a = actions
+        if not (a.dtype is torch.int8 and a.is_cuda and a.is_contiguous() and a.numel() == self.num_envs * self.num_blue and a.device == self.device):
+            a = self._prep_actions(actions)
+        bound = self._bound
+        if bound is None or bound[0] is not self._obs or bound[1] is not self._final_obs:   # (re)bind what does not change per call
+            io = self._io
+            io.obs, io.rewards = self._obs.data_ptr(), self._rewards.data_ptr()
+            io.terminated, io.truncated = self._term.data_ptr(), self._trunc.data_ptr()
+            io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
+            bound = self._bound = (self._obs, self._final_obs, C.byref(io), _ptr(self.state), self._term.view(torch.bool),
+                                   self._trunc.view(torch.bool), getattr(torch._C, "_cuda_getCurrentRawStream", None))
+        self._io.actions = a.data_ptr()
+        stream = bound[6](self.device.index) if bound[6] else torch.cuda.current_stream(self.device).cuda_stream
+        if self._lib.mg_step(self._h, bound[3], bound[2], stream):
+            raise RuntimeError(_lib.last_error(self._h))
+        return self._obs, self._rewards, bound[4], bound[5], (self._info() if (self.with_info or self._final_obs is not None) else {})
 
     def step_host(self, actions):
         if self._host is None:
