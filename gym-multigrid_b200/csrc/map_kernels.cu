@@ -128,7 +128,8 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
     acts |= (NIB)((a < 0 || a > 4) ? 15 : a) << (4 * i);
   }
   for (int k = 0; k < nr; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301)
-    const int a = MODE == 0 ? p.red_actions[e * nr + k] : below(r, 5);
+    // Philox mode with red_actions given: an external enemy policy (the reference's `enemy_policies`, ctf.py:666) - no draw
+    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * nr + k] : below(r, 5);
     if (a < 0 || a > 4) err |= MG_ERR_BAD_ACTION;
     acts |= (NIB)((a < 0 || a > 4) ? 15 : a) << (4 * (nb + k));
   }

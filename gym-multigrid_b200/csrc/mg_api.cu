@@ -65,6 +65,7 @@ struct mg_env {
   mg_generic_config gcfg;
   mg::GenericParams gbase;
   mg_map_trace mtrace;
+  const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
   int act_cols, rew_cols;
@@ -334,6 +335,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
   env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
   std::memset(&env->mtrace, 0, sizeof env->mtrace);
+  env->ext_red_actions = nullptr;
   env->obs_elem = cfg->obs_dtype == MG_OBS_U8 ? 1 : 8;
   env->act_cols = nb; env->rew_cols = 1;
   const int E = mg::map_tile_envs();
@@ -449,6 +451,7 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
   p.agents = s + env->plane_off[MG_MAP_PLANE_AGENTS]; p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
   p.hdr = reinterpret_cast<int4*>(s + env->plane_off[MG_MAP_PLANE_HDR]);
   p.op = op; p.reset_mask = mask;
+  p.red_actions = env->ext_red_actions;
   if (env->has_trace) {
     const mg_map_trace& t = env->mtrace;
     p.rng_mode = 0;
@@ -471,6 +474,13 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
   cudaError_t ce;
   if ((ce = mg::launch_map(p, st)) != cudaSuccess) return cuda_fail(env, "map_kernel", ce);
   env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_red_actions: CtF family only");
+  env->ext_red_actions = red_actions_dev;
   return 0;
 }
 

@@ -87,6 +87,7 @@ class _MapVecEnv(VectorEnvSurface):
         self._agents = self._planes["agents"].view(N, slots, 4)[:, :n]     # (x, y, dir, flags) per agent
         self._io = _lib.StepIO()
         self._bound = None
+        self._red_actions = None
         self._host = None
         self.with_info = False      # True: step() / reset() also return the reference's info dict (one more launch)
         self._trace_keepalive = None
@@ -325,6 +326,19 @@ class CtfVecEnv(_MapVecEnv):
         self.obstacle, self.blue_flag, self.red_flag = cells(6), cells(4)[0], cells(5)[0]
         self.blue_territory = cells(0) + [self.blue_flag]
         self.red_territory = cells(1) + [self.red_flag]
+
+    def set_red_actions(self, red_actions=None):
+        """Drive the red agents from outside (the reference's `enemy_policies`, ctf.py:666): `red_actions` int8 CUDA tensor
+        [N, num_red] that every following `step` reads - overwrite it in place between steps (a learned opponent, self-play, a
+        host-side A* policy).  None = back to the built-in RwPolicy drawn on the device."""
+        if red_actions is None:
+            self._red_actions = None
+            self._check(self._lib.mg_set_red_actions(self._h, None))
+            return None
+        t = torch.as_tensor(red_actions, device=self.device).to(torch.int8).reshape(self.num_envs, self.num_red).contiguous()
+        self._red_actions = t
+        self._check(self._lib.mg_set_red_actions(self._h, _ptr(t)))
+        return t
 
     def game_stats(self):
         """The reference's `env.game_stats` (ctf.py:1068-1073) for every env, as bool CUDA tensors.  Cleared by reset - with

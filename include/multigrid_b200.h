@@ -226,6 +226,12 @@ typedef struct mg_map_trace {
 int mg_create_map(const mg_map_config* cfg, int device, mg_env** out);
 int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
 
+/* CtF handles: actions of the red agents for the following steps, int8 [N][num_red] on the device, read by every mg_step until
+ * changed (the caller overwrites the buffer between steps) - the reference's `enemy_policies` argument (ctf.py:666) for any
+ * policy that is not the built-in RwPolicy: a learned opponent, self-play, a host-side A* policy.  NULL = RwPolicy drawn on the
+ * device (default).  Shuffle order and battle outcomes stay with the env's Philox stream. */
+int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev);
+
 /* Maze handles: observation mode of mg_reset / mg_step / mg_step_host.  view_size 0 (default) = the "map" observation;
  * 3 / 5 / 7 = MultiGridEnv.gen_obs partial views u8 [N][1][V][V][3] computed by the SAME launch that steps the envs
  * (BASELINE config 4; same cells as mg_gen_obs would return after the step).  final_obs is not available in this mode. */

@@ -148,7 +148,7 @@ typedef struct {
   const int32_t* blue_place;  /* [N][num_blue] */
   const int32_t* red_place;   /* [N][num_red] */
   /* ctf step: RwPolicy integers(0,5) (heuristic.py:72), np_random.shuffle (ctf.py:1245), battle choice (:1393-1403) */
-  const int8_t* red_actions;  /* [N][num_red] */
+  const int8_t* red_actions;  /* [N][num_red]; also honoured in Philox mode: actions of an external enemy policy (no RwPolicy draw) */
   const uint8_t* order;       /* [N][n] */
   const uint8_t* blue_win;    /* [N][KB] */
   int32_t KB;

@@ -200,7 +200,7 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
     int act[OC_MAX_CTF_AGENTS], order[OC_MAX_CTF_AGENTS];
     for (int i = 0; i < nb; ++i) act[i] = blue_actions[e * nb + i];
     for (int k = 0; k < nr; ++k) /* RwPolicy.act for EVERY red agent, defeated or not (:1297-1301) */
-      act[nb + k] = rng->mode == 0 ? rng->red_actions[e * nr + k] : p_below(&r, 5);
+      act[nb + k] = (rng->mode == 0 || rng->red_actions) ? rng->red_actions[e * nr + k] : p_below(&r, 5); /* mode 1 + red_actions: an external enemy policy (enemy_policies, ctf.py:666), no draw */
     if (c->variant_1v1) { order[0] = 0; order[1] = 1; } /* Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510) */
     else if (rng->mode == 0) for (int i = 0; i < n; ++i) order[i] = rng->order[e * n + i];
     else { /* np_random.shuffle stand-in: Fisher-Yates */

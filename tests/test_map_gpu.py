@@ -319,3 +319,31 @@ def test_full_size_invariants_ctf_and_maze(cuda_device):
         assert bool(((rew == -0.01) | (rew == 1.0 - 0.01) | term).all())
     assert env.status() == 0
     env.close()
+
+
+def test_ctf_external_enemy_policy(cuda_device):
+    """`enemy_policies` other than RwPolicy: red actions supplied by the caller (here: a scripted 'always move up / left'
+    opponent computed from the observation on the device), shuffle and battles from the Philox stream; CUDA == oracle."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    n, nb, nr = 1500, 2, 2
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=30, seed=9)
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=30)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(oc.map_rng(mode=1, seed=9)))
+    red = env.set_red_actions(torch.zeros((n, nr), dtype=torch.int8, device=cuda_device))
+    gen = torch.Generator(device=cuda_device).manual_seed(4)
+    r = None
+    for t in range(70):
+        red.copy_(torch.where(env.agent_pos[:, nb:, 0] > 4, 2, 1).to(torch.int8))      # policy: head for x <= 4, then walk left
+        act = torch.randint(0, 5, (n, nb), generator=gen, device=cuda_device, dtype=torch.int8)
+        r = oc.map_rng(mode=1, seed=9, red_actions=_np(red))
+        obs, rew, term, trunc, _ = env.step(act)
+        oo, orew, oterm, otrunc = o.step(_np(act), r, autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+    env.set_red_actions(None)
+    obs, rew, *_ = env.step(torch.zeros((n, nb), dtype=torch.int8, device=cuda_device))
+    oo, orew, *_ = o.step(np.zeros((n, nb), np.int8), oc.map_rng(mode=1, seed=9), autoreset=True)
+    assert np.array_equal(_np(obs), oo) and env.status() == 0
+    env.close()
