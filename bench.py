@@ -245,7 +245,41 @@ def run_ours(args):
         obs, rew, term, trunc, _ = envs[i % EB].step(host_act[i % EB])
         checksum += float(rew[0, 0]) + float(obs[0, 1, 8, 0])
     torch.cuda.synchronize(dev)
+    e2e_block_s = time.perf_counter() - t0
+
+    # the same calls split in their two halves (VectorEnv.step_async / step_wait) with EB env batches in flight: every step
+    # still carries its own H2D of actions and D2H of obs / rewards / flags, but the result copy of one batch overlaps the
+    # step of the other, so the PCIe link never idles.  This is the headline e2e; the blocking figure is reported beside it.
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for b in range(EB):
+        envs[b].step_async(host_act[b])
+    for i in range(e2e_steps):
+        b = i % EB
+        obs, rew, term, trunc, _ = envs[b].step_wait()
+        checksum += float(rew[0, 0]) + float(obs[0, 1, 8, 0])
+        if i + EB < e2e_steps:
+            envs[b].step_async(host_act[b])
+    torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+
+    # for scale: host actions in, host rewards / flags out, observations left on the device (where a GPU policy reads them)
+    pin_act = [torch.as_tensor(a).pin_memory() for a in host_act[:EB]]
+    pin_rew = torch.empty((n, 2), dtype=torch.float64, pin_memory=True)
+    pin_flags = torch.empty((2, n), dtype=torch.bool, pin_memory=True)
+    def dev_obs_step(b):
+        o, r, te, tr, _ = envs[b].step(pin_act[b].to(dev, non_blocking=True))
+        pin_rew.copy_(r, non_blocking=True); pin_flags[0].copy_(te, non_blocking=True); pin_flags[1].copy_(tr, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return float(pin_rew[0, 0])
+    for i in range(4):
+        dev_obs_step(i % EB)
+    dsteps = e2e_steps * 4
+    t0 = time.perf_counter()
+    for i in range(dsteps):
+        checksum += dev_obs_step(i % EB)
+    e2e_devobs_s = (time.perf_counter() - t0) / dsteps
 
     # for scale: a bare device-to-host copy of one step's result bytes into page-locked memory on this box
     dsrc = torch.empty(n * (300 + 16 + 2), dtype=torch.uint8, device=dev)
@@ -260,10 +294,10 @@ def run_ours(args):
     bare_d2h_gbps = 20 * dsrc.numel() / (time.perf_counter() - t1) / 1e9
     del dsrc, hdst
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_block_s * 1e3, e2e_devobs_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, e2e_block_ms_max, e2e_devobs_ms_max = (float(x) for x in t)
 
     if rank == 0:
         value = K_eff * n * world / (ms_max * 1e-3)
@@ -290,9 +324,15 @@ def run_ours(args):
                               "achieved": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3, "frac": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3 / peak,
                               "note": "same graph on ONE stream (launches serialised by programmatic dependent launch)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": n * (300 + 16 + 2),
-                    "steps": e2e_steps, "api": "CollectVecEnv.step(numpy) -> mg_step_host (pinned host buffers)",
+                    "steps": e2e_steps,
+                    "api": f"CollectVecEnv.step_async(numpy) / step_wait() -> mg_step_host_async / _wait (pinned host buffers), {EB} env batches in flight",
                     "d2h_GBps_per_gpu": n * (300 + 16 + 2) / (e2e_ms_max * 1e-3 / e2e_steps) / 1e9,
                     "bare_d2h_copy_GBps": bare_d2h_gbps,
+                    "blocking": {"value": e2e_steps * n * world / (e2e_block_ms_max * 1e-3),
+                                 "api": "CollectVecEnv.step(numpy) -> mg_step_host, one call at a time",
+                                 "d2h_GBps_per_gpu": n * (300 + 16 + 2) / (e2e_block_ms_max * 1e-3 / e2e_steps) / 1e9},
+                    "obs_on_device": {"value": n * world / (e2e_devobs_ms_max * 1e-3), "h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": n * (16 + 2),
+                                      "api": "CollectVecEnv.step(cuda tensor): pinned actions H2D, rewards + flags D2H, obs stay in HBM for a GPU policy"},
                     "note": "bound by the device-to-host copy of the observations (300 B/env over PCIe), not by the kernel; "
                             "bare_d2h_copy_GBps = the same bytes copied by torch alone on this box"},
             "gpu_launches": K_eff,

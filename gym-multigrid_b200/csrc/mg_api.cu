@@ -818,7 +818,7 @@ extern "C" int mg_host_layout(const mg_env* env, size_t* off_rewards, size_t* of
   return 0;
 }
 
-extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void* stream) {
+static int step_host_enqueue(mg_env* env, void* state, const mg_step_io* io, void* stream, bool wait) {
   if (!env || !state || !io) return fail(env, "mg_step_host: null argument");
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step_host: actions/rewards/terminated/truncated must be non-null");
   cudaError_t ce;
@@ -857,7 +857,23 @@ extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void
     if ((ce = cudaMemcpyAsync(io->truncated, env->d_trunc, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H truncated", ce);
   }
   if (io->final_obs && (ce = cudaMemcpyAsync(io->final_obs, env->d_final, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H final_obs", ce);
-  if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
+  if (wait && (ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
+  return 0;
+}
+
+extern "C" int mg_step_host(mg_env* env, void* state, const mg_step_io* io, void* stream) {
+  return step_host_enqueue(env, state, io, stream, true);
+}
+
+extern "C" int mg_step_host_async(mg_env* env, void* state, const mg_step_io* io, void* stream) {
+  return step_host_enqueue(env, state, io, stream, false);
+}
+
+extern "C" int mg_step_host_wait(mg_env* env, void* stream) {
+  if (!env) return -1;
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if ((ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
   return 0;
 }
 

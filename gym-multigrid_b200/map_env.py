@@ -161,21 +161,28 @@ class _MapVecEnv(VectorEnvSurface):
             raise RuntimeError(_lib.last_error(self._h))
         return self._obs, self._rewards, bound[4], bound[5], (self._info() if (self.with_info or self._final_obs is not None) else {})
 
-    def step_host(self, actions):
+    def _host_io(self, actions):
         if self._host is None:
-            N, S = self.num_envs, self.size
+            N = self.num_envs
             blk, obs, rew, term, trunc = _lib.host_result_buffers(self._lib, self._h, tuple(self._obs.shape), self._obs.dtype, N, 1)
             self._host = dict(act=torch.zeros((N, self.num_blue), dtype=torch.int8, pin_memory=True), obs=obs, rew=rew, term=term,
                               trunc=trunc, block=blk)
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
-        h = self._host
+            h, io = self._host, _lib.StepIO()
+            io.actions, io.obs, io.rewards = h["act"].data_ptr(), h["obs"].data_ptr(), h["rew"].data_ptr()
+            io.terminated, io.truncated, io.final_obs = h["term"].data_ptr(), h["trunc"].data_ptr(), None
+            self._host_io_struct = io
         self._host_np["act"][...] = np.round(np.asarray(actions)).astype(np.int64).reshape(self.num_envs, self.num_blue)
-        io = _lib.StepIO()
-        io.actions, io.obs, io.rewards = h["act"].data_ptr(), h["obs"].data_ptr(), h["rew"].data_ptr()
-        io.terminated, io.truncated, io.final_obs = h["term"].data_ptr(), h["trunc"].data_ptr(), None
-        self._check(self._lib.mg_step_host(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        return self._host_io_struct
+
+    def _host_result(self):
         n = self._host_np
         return n["obs"], n["rew"], n["term"].view(np.bool_), n["trunc"].view(np.bool_), {}
+
+    def step_host(self, actions):
+        io = self._host_io(actions)
+        self._check(self._lib.mg_step_host(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        return self._host_result()
 
     def get_info(self, out=None):
         """`_get_info()` of every env as a dict of float64 CUDA tensors [N], keys and values as the reference's dict

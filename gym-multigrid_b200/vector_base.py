@@ -27,6 +27,39 @@ class VectorEnvSurface:
     def set_attr(self, name: str, values):
         setattr(self, name, values)
 
+    # ---- host-buffer path split in two (gymnasium VectorEnv.step_async / step_wait); the classes provide _host_io / _host_result
+    _host_stream = None
+    _host_pending = False
+
+    def step_async(self, actions):
+        """Enqueue one step with HOST arrays (H2D actions -> step kernel -> D2H results) on this env's private stream and
+        return at once.  Two env batches driven alternately keep the PCIe link busy: the result copy of one overlaps the host
+        work and the step of the other (the way gymnasium's AsyncVectorEnv / EnvPool's async mode are used)."""
+        import ctypes as C
+
+        import torch
+        if self._host_pending:
+            raise RuntimeError("step_async called again before step_wait")
+        if not hasattr(self, "_host_io"):
+            raise NotImplementedError(f"{type(self).__name__} has no host-buffer step; pass CUDA tensors to step()")
+        io = self._host_io(actions)
+        if self._host_stream is None:
+            self._host_stream = torch.cuda.Stream(device=self.device)
+        self._host_stream.wait_stream(torch.cuda.current_stream(self.device))   # ordered after device-path calls on the caller's stream
+        if self._lib.mg_step_host_async(self._h, C.c_void_p(self.state.data_ptr()), C.byref(io), C.c_void_p(self._host_stream.cuda_stream)):
+            self._check(-1)
+        self._host_pending = True
+
+    def step_wait(self):
+        """Block until the step enqueued by `step_async` has landed in the page-locked host buffers; returns
+        (obs, rewards, terminated, truncated, info) as numpy views of them (overwritten by this env's next host-path step)."""
+        import ctypes as C
+        if not self._host_pending:
+            raise RuntimeError("step_wait without step_async")
+        self._host_pending = False
+        self._check(self._lib.mg_step_host_wait(self._h, C.c_void_p(self._host_stream.cuda_stream)))
+        return self._host_result()
+
     def __enter__(self):
         return self
 

@@ -206,23 +206,31 @@ class CollectVecEnv(VectorEnvSurface):
             raise RuntimeError(_lib.last_error(self._h))
         return self._obs, self._rewards, self._term_b, self._trunc_b, (self._info_static if self._final_obs is None else self._info())
 
-    def step_host(self, actions):
-        """gymnasium-style call with HOST arrays: numpy in, numpy out (views of page-locked buffers,
-        overwritten by the next call).  Host<->device copies and the wait are inside the call."""
+    def _host_io(self, actions):
         if self._host is None:
             N, W, H, A = self.num_envs, self.width, self.height, self.num_agents
             blk, obs, rew, term, trunc = _lib.host_result_buffers(self._lib, self._h, (N, W, H, 3), torch.uint8, N, A)
             self._host = dict(act=torch.zeros((N, A), dtype=torch.int8, pin_memory=True), obs=obs, rew=rew.view(N, A), term=term,
                               trunc=trunc, block=blk)
             self._host_np = {k: v.numpy() for k, v in self._host.items()}
-        h = self._host
+            h, io = self._host, _lib.StepIO()
+            io.actions, io.obs, io.rewards = h["act"].data_ptr(), h["obs"].data_ptr(), h["rew"].data_ptr()
+            io.terminated, io.truncated, io.final_obs = h["term"].data_ptr(), h["trunc"].data_ptr(), None
+            self._host_io_struct = io
         self._host_np["act"][...] = np.asarray(actions).reshape(self.num_envs, self.num_agents)
-        io = _lib.StepIO()
-        io.actions, io.obs, io.rewards = h["act"].data_ptr(), h["obs"].data_ptr(), h["rew"].data_ptr()
-        io.terminated, io.truncated, io.final_obs = h["term"].data_ptr(), h["trunc"].data_ptr(), None
-        self._check(self._lib.mg_step_host(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        return self._host_io_struct
+
+    def _host_result(self):
         n = self._host_np
         return n["obs"], n["rew"], n["term"].view(np.bool_), n["trunc"].view(np.bool_), self._info()
+
+    def step_host(self, actions):
+        """gymnasium-style call with HOST arrays: numpy in, numpy out (views of page-locked buffers,
+        overwritten by the next call).  Host<->device copies and the wait are inside the call.
+        `step_async` / `step_wait` (vector_base.py) are its two halves."""
+        io = self._host_io(actions)
+        self._check(self._lib.mg_step_host(self._h, _ptr(self.state), C.byref(io), self._stream()))
+        return self._host_result()
 
     def encode(self, out=None):
         """Grid.encode() of the current state (grid.py:223-252) -> u8 [N, W, H, 3]."""

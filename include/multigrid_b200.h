@@ -143,6 +143,13 @@ int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stre
  * arrays; buffers should be page-locked for full PCIe bandwidth. */
 int mg_step_host(mg_env* env, void* state_dev, const mg_step_io* io_host, void* stream);
 
+/* The two halves of mg_step_host - gymnasium's VectorEnv.step_async / step_wait (the pattern AsyncVectorEnv is driven with):
+ * _async enqueues H2D actions -> step -> D2H results on `stream` and returns at once; _wait blocks until that stream has
+ * drained.  With two handles on two streams the device-to-host copy of one env batch overlaps the host work and the step
+ * of the other, which keeps the PCIe link busy back to back.  The host buffers must stay untouched until _wait returns. */
+int mg_step_host_async(mg_env* env, void* state_dev, const mg_step_io* io_host, void* stream);
+int mg_step_host_wait(mg_env* env, void* stream);
+
 /* Layout that lets mg_step_host return everything with ONE device-to-host copy: if the caller's host buffers are parts of one
  * (page-locked) block with io->rewards = io->obs + *off_rewards, io->terminated = io->obs + *off_terminated, io->truncated =
  * io->obs + *off_truncated (block size *total_bytes), the results travel in a single cudaMemcpyAsync; any other placement is

@@ -160,6 +160,40 @@ def test_step_host_matches_device_path(cuda_device):
         e.close()
 
 
+def test_step_async_wait_two_batches_in_flight(cuda_device):
+    """step_async / step_wait (mg_step_host_async / _wait): two env batches alternated with both in flight return exactly what
+    the blocking device path returns, also when device-path calls are mixed in between."""
+    g = load_golden("collect_respawn_clustered")
+    n = 3000
+    ref = [_make(g, "collect_respawn_clustered", n, autoreset=True, seed=s) for s in (4, 5)]
+    pip = [_make(g, "collect_respawn_clustered", n, autoreset=True, seed=s) for s in (4, 5)]
+    for e in ref + pip:
+        e.reset()
+    rng = np.random.default_rng(8)
+    acts = [[rng.integers(0, 4, size=(n, 2)).astype(np.int8) for _ in range(2)] for _ in range(40)]
+    with pytest.raises(RuntimeError):
+        pip[0].step_wait()
+    pip[0].step_async(acts[0][0])
+    with pytest.raises(RuntimeError):
+        pip[0].step_async(acts[0][0])
+    pip[1].step_async(acts[0][1])
+    for t in range(40):
+        for b in range(2):
+            want = ref[b].step(torch.as_tensor(acts[t][b], device=cuda_device))
+            got = pip[b].step_wait()
+            for x, y in zip(want[:4], got[:4]):
+                assert np.array_equal(_np(x), y), f"step {t} batch {b}"
+            if t == 20 and b == 0:      # a device-path step between two host-path steps stays ordered
+                a = torch.as_tensor(acts[t][1], device=cuda_device)
+                x = ref[b].step(a)[0].clone(); y = pip[b].step(a)[0]
+                assert torch.equal(x, y)
+            if t + 1 < 40:
+                pip[b].step_async(acts[t + 1][b])
+    for e in ref + pip:
+        assert e.status() == 0
+        e.close()
+
+
 def test_properties_at_full_size(cuda_device):
     """Size-independent invariants at 65 536 envs (BASELINE config 2), Philox mode, autoreset."""
     import gym_multigrid_b200 as mg
