@@ -205,6 +205,121 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
   rew = __dsub_rn(rew, __dmul_rn(p.step_penalty, (double)nb));  // :1428 -- two roundings like the reference, never an FMA
 }
 
+// The same step for the compile-time team sizes with every agent word in a REGISTER: the order-dependent loop picks and
+// updates "agent order[k]" with select chains instead of dynamically indexed shared memory, the body is branch-free
+// (one commit per agent), and occupancy / flag / battle tests run on registers.  Statement for statement the semantics of
+// ctf_step_one above (which stays the general path for run-time team sizes); tested against it through the oracle.
+template <int MODE, int NB, int NR>
+__device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, uint32_t blue_raw, const uint8_t* terr,
+                                              uint32_t* ag, int4& h, Rng<MODE>& r, double& rew, bool& term, bool& trunc,
+                                              int& err) {
+  constexpr int n = NB + NR;
+  const int S = p.S;
+  uint32_t w[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) w[i] = ag[i * kMapE];
+  h.x += 1;  // ctf.py:1295
+  uint32_t acts = 0, order;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int a = (int)(int8_t)(blue_raw >> (8 * i));   // int8 actions, fetched by the caller together with the state rows
+    const bool bad = a < 0 || a > 4;   // reference: ValueError (ctf.py:1200-1201)
+    if (bad) err |= MG_ERR_BAD_ACTION;
+    acts |= (uint32_t)(bad ? 15 : a) << (4 * i);
+  }
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301), or the external enemy policy
+    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * NR + k] : below(r, 5);
+    const bool bad = a < 0 || a > 4;
+    if (bad) err |= MG_ERR_BAD_ACTION;
+    acts |= (uint32_t)(bad ? 15 : a) << (4 * (NB + k));
+  }
+  if (p.variant_1v1) {  // Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510)
+    order = 0x10u;
+  } else if (MODE == 0) {
+    order = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) order |= (uint32_t)(p.order[e * n + i] & 15) << (4 * i);
+  } else {  // np_random.shuffle stand-in: Fisher-Yates
+    order = 0x76543210u;
+#pragma unroll
+    for (int i = n - 1; i > 0; --i) {
+      const int j = below(r, i + 1);
+      const uint32_t x = ((order >> (4 * i)) ^ (order >> (4 * j))) & 15u;
+      order ^= (x << (4 * i)) | (x << (4 * j));
+    }
+  }
+  const bool pen = p.obstacle_penalty != 0;
+#pragma unroll
+  for (int k = 0; k < n; ++k) {  // _move_agents :1240-1251
+    const int i = (int)((order >> (4 * k)) & 15u);
+    uint32_t wi = w[0];
+#pragma unroll
+    for (int j = 1; j < n; ++j) wi = (i == j) ? w[j] : wi;
+    const int a = (int)((acts >> (4 * i)) & 15u);
+    int dx, dy;
+    action_delta(a & 7, dx, dy);
+    const int nx = ag_x(wi) + dx, ny = ag_y(wi) + dy;  // _move_agent :1184-1238
+    const bool live = !(wi & FL_DEAD) && a != 15;      // "Defeated agent doesn't move, sadly."
+    const bool inb = (unsigned)nx < (unsigned)S && (unsigned)ny < (unsigned)S;
+    const uint32_t target = ((uint32_t)nx & 255u) | (((uint32_t)ny & 255u) << 8);
+    bool occupied = false;  // an agent object (alive, defeated, or itself when staying) sits on the cell
+#pragma unroll
+    for (int j = 0; j < n; ++j) occupied |= ((w[j] ^ target) & 0xFFFFu) == 0;
+    const int tc = terr[inb ? ny * S + nx : 0];
+    const bool go = live && inb && !occupied && !(tc == CT_OBSTACLE && !pen);  // Obstacle.can_overlap()
+    const bool hit = live && inb && occupied && pen && !p.variant_1v1;        // :1231-1236 (1v1 has no collided logic, :498-501)
+    const uint32_t moved = (wi & 0xFF000000u) | target | ((uint32_t)dir_of_action(a, (int)((wi >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
+    const uint32_t nw = go ? moved : (hit ? (wi | FL_COLLIDED) : wi);
+#pragma unroll
+    for (int j = 0; j < n; ++j) w[j] = (i == j) ? nw : w[j];
+  }
+  term = false; trunc = h.x >= p.max_steps;  // :1310-1311
+  rew = 0.0;
+  if (pen) {  // :1316-1332 (collided is never cleared)
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+      if (w[i] & FL_COLLIDED) { if (i < NB) rew -= p.obstacle_penalty; w[i] |= FL_DEAD; }
+  }
+  const uint32_t red_flag = (uint32_t)p.red_flag, blue_flag = (uint32_t)p.blue_flag;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) if (((w[i] ^ red_flag) & 0xFFFFu) == 0) { rew += p.flag_reward; term = true; h.y |= 2; }   // :1335-1344
+#pragma unroll
+  for (int i = NB; i < n; ++i) if (((w[i] ^ blue_flag) & 0xFFFFu) == 0) { rew -= p.flag_reward; term = true; h.y |= 1; }  // :1347-1356
+  int nbattle = 0;
+  bool all_dead = true;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {  // np.where(distances <= battle_range): row-major, blue-major (:1368-1377)
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const uint32_t wb = w[b], wr = w[NB + q];
+      const int ddx = ag_x(wb) - ag_x(wr), ddy = ag_y(wb) - ag_y(wr);
+      if (ddx * ddx + ddy * ddy > p.d2_max) continue;  // == !(np.linalg.norm(int vector) <= battle_range), see MapParams::d2_max
+      if ((wb | wr) & FL_DEAD) continue;               // :1380-1383
+      const int cb = terr[ag_y(wb) * S + ag_x(wb)], cr = terr[ag_y(wr) * S + ag_x(wr)];
+      const bool bh = (cb == CT_BLUE_TERR || cb == CT_BLUE_FLAG), rh = (cr == CT_RED_TERR || cr == CT_RED_FLAG);
+      bool blue_win;
+      if (MODE == 0) {
+        blue_win = nbattle < p.KB ? p.blue_win[e * p.KB + nbattle] != 0 : false;
+        if (nbattle >= p.KB) err |= MG_ERR_TRACE_OVERFLOW;
+      } else {  // :1392-1407; (double)u / 2^32 < p  <=>  u < ceil(p * 2^32)
+        const unsigned long long thr = (bh && !rh) ? p.thr_blue_home : ((!bh && rh) ? p.thr_red_home : p.thr_even);
+        blue_win = (unsigned long long)r.u32() < thr;
+      }
+      ++nbattle;
+      if (blue_win) { rew += p.battle_reward; w[NB + q] = wr | FL_DEAD; h.y |= 1 << (8 + NB + q); }   // :1409-1418
+      else if (p.variant_1v1) { rew -= p.battle_reward; term = true; h.y |= 1 << 8; }  // 1v1: losing ends the episode (ctf.py:629-636)
+      else { rew -= p.battle_reward; w[b] = wb | FL_DEAD; h.y |= 1 << (8 + b); }
+    }
+    all_dead &= (w[b] & FL_DEAD) != 0;
+  }
+  if (MODE == 0 && p.battles_used) p.battles_used[e] = nbattle;
+  if (all_dead) term = true;           // :1423
+  rew = __dsub_rn(rew, __dmul_rn(p.step_penalty, (double)NB));  // :1428 -- two roundings like the reference, never an FMA
+#pragma unroll
+  for (int i = 0; i < n; ++i) ag[i * kMapE] = w[i];
+}
+
 // value an agent shows in the "map" observation
 template <int FAMILY>
 __device__ __forceinline__ int agent_code(const MapParams& p, int i, uint32_t w) {
@@ -230,7 +345,7 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
 template <int FAMILY, int MODE, int MINB>
 __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, bar_tile;
   __shared__ uint8_t s_done[kMapE];
   const int tid = threadIdx.x, n = p.n, cells = p.cells;
   const bool view_mode = FAMILY == MG_FAMILY_MAZE && p.view_V != 0;                 // obs = partial views (gen_obs) instead of the map
@@ -242,13 +357,20 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   const int n_here = (int)min((long long)kMapE, p.N - e0);
   const long long e = e0 + tid;
 
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_tile, 1); fence_mbar_init(); }
   pdl_launch_dependents();
   __syncthreads();
   pdl_wait();
+  // staged u8 tiles: the static part of the whole tile's observation slab (the map repeated once per env) arrives as ONE bulk
+  // load of a host-built image while the envs step - no per-thread replication of the period, no barrier in front of the patches
+  const bool tile_img = !view_mode && p.obs_tile && p.obs;
   if (tid == 0) {
     mbar_expect_tx(&bar, (uint32_t)head);
     tma_load_1d(s_period, view_mode ? p.map_padded : p.obs_period, (uint32_t)head, &bar);
+    if (tile_img) {   // own barrier: the step only waits for the period
+      mbar_expect_tx(&bar_tile, (uint32_t)(kMapE * cells));
+      tma_load_1d(s_obs, p.obs_tile, (uint32_t)(kMapE * cells), &bar_tile);
+    }
   }
 
   // ---- the env's agent row (padded to row_bytes = 4 * 2^k) and header; state planes are padded to whole tiles
@@ -269,6 +391,13 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     ag[0] = *reinterpret_cast<const uint32_t*>(row);
   }
   int4 h = p.hdr[e];
+  uint32_t blue_raw = 0;   // 2v2 / 1v1 step: the blue actions travel with the state loads, ahead of the wait for the staged period
+  if (FAMILY == MG_FAMILY_CTF && p.op == 1 && tid < n_here) {
+    if (p.nb == 2 && p.nr == 2)
+      blue_raw = (reinterpret_cast<uintptr_t>(p.actions) & 1) ? ((uint32_t)(uint8_t)p.actions[e * 2] | ((uint32_t)(uint8_t)p.actions[e * 2 + 1] << 8))
+                                                                : *reinterpret_cast<const uint16_t*>(p.actions + e * 2);
+    else if (p.nb == 1 && p.nr == 1) blue_raw = (uint8_t)p.actions[e];
+  }
   bool done = false, want_reset = false;
   int err = 0;
   Rng<MODE> r;
@@ -281,8 +410,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     } else {
       double rew; bool term, trunc;
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
-      else if (p.nb == 2 && p.nr == 2) ctf_step_one<MODE, uint32_t, 2, 2>(p, e, p.actions + e * 2, s_period, ag, h, r, rew, term, trunc, err);
-      else if (p.nb == 1 && p.nr == 1) ctf_step_one<MODE, uint32_t, 1, 1>(p, e, p.actions + e, s_period, ag, h, r, rew, term, trunc, err);
+      else if (p.nb == 2 && p.nr == 2) ctf_step_regs<MODE, 2, 2>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
+      else if (p.nb == 1 && p.nr == 1) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (n <= 8) ctf_step_one<MODE, uint32_t, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       else ctf_step_one<MODE, unsigned long long, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       p.rewards[e] = rew; p.terminated[e] = term; p.truncated[e] = trunc;
@@ -367,16 +496,20 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   // ---- observation: static map for the whole tile, then the agents on top
   const long long slab = (long long)n_here * cells;  // elements in this tile's obs slab
   if (p.obs_staged) {  // u8, small map: assemble the tile in shared memory, one TMA bulk store
-    const int L16 = p.L16, chunks = kMapE * cells / 16;
-    uint4* dst = reinterpret_cast<uint4*>(s_obs);
-    const uint4* src = reinterpret_cast<const uint4*>(s_period);
-    int m = L16 == 1 ? 0 : tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
-    const int step = p.tile_mod_L16;
-    for (int c = tid; c < chunks; c += kMapE) {
-      dst[c] = src[m];
-      m += step; if (m >= L16) m -= L16;
+    if (!tile_img) {   // handle without the image table: replicate the period by hand
+      const int L16 = p.L16, chunks = kMapE * cells / 16;
+      uint4* dst = reinterpret_cast<uint4*>(s_obs);
+      const uint4* src = reinterpret_cast<const uint4*>(s_period);
+      int m = L16 == 1 ? 0 : tid - (int)__umulhi((uint32_t)tid, p.L16_magic) * L16;   // tid mod L16
+      const int step = p.tile_mod_L16;
+      for (int c = tid; c < chunks; c += kMapE) {
+        dst[c] = src[m];
+        m += step; if (m >= L16) m -= L16;
+      }
+      __syncthreads();
+    } else {
+      mbar_wait(&bar_tile, 0);
     }
-    __syncthreads();
     if (tid < n_here)
       for (int i = 0; i < n; ++i) {  // agents in index order: later agents overwrite earlier ones (ctf.py:1157-1161)
         const uint32_t w = ag[i * kMapE];

@@ -19,6 +19,7 @@ struct MapParams {
   const uint8_t* field_map;    // [cells] x*S+y
   const uint8_t* obs_period;   // [L] obs base repeated to a multiple of 16 bytes (CtF: transposed map)
   int L;                       // lcm(cells, 16)
+  const uint8_t* obs_tile;     // staged u8 tiles: [envs per tile][cells] the obs base once per env of a tile (one bulk load), else null
   const uint16_t* background;  // Maze: cells with code background, np.where order; every list entry is packed x | y << 8
   const uint16_t* blue_terr;   // CtF: blue territory cells + blue flag (ctf.py:765-769)
   const uint16_t* red_terr;

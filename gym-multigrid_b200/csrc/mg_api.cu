@@ -362,11 +362,15 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
                o_pad = align_up(o_pk + cells, 256), o_d2 = 0;  /* o_d2 set below */
   const int pad = 14, pitch = S + 2 * pad;   // view_size <= 15: a view reaches at most 14 cells beyond the map
   const size_t padded_bytes = align_up((size_t)pitch * pitch, 16);
-  const size_t o_d2b = align_up(o_pad + padded_bytes, 256), total = align_up(o_d2b + (size_t)3 * cells * sizeof(int32_t), 256) + 256;
+  const size_t o_d2b = align_up(o_pad + padded_bytes, 256), o_tile = align_up(o_d2b + (size_t)3 * cells * sizeof(int32_t), 256);
+  const bool staged = mg::map_obs_staged(cells, cfg->obs_dtype);
+  const size_t tile_bytes = staged ? (size_t)mg::map_tile_envs() * cells : 0;   // image of one tile's static observation slab
+  const size_t total = align_up(o_tile + tile_bytes, 256) + 256;
   (void)o_d2;
   std::string blob(total, '\0');
   std::memcpy(&blob[o_map], cfg->field_map, cells);
   std::memcpy(&blob[o_per], period.data(), L);
+  for (size_t k = 0; k < tile_bytes; ++k) blob[o_tile + k] = period[k % L];   // tile envs * cells is a multiple of L
   if (!bg.empty()) std::memcpy(&blob[o_bg], bg.data(), bg.size());
   if (!bt.empty()) std::memcpy(&blob[o_bt], bt.data(), bt.size());
   if (!rt.empty()) std::memcpy(&blob[o_rt], rt.data(), rt.size());
@@ -427,6 +431,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   p.tma_reps = mg::map_tma_reps((int)L, cells, cfg->obs_dtype);
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.field_map = env->d_map_tables + o_map; p.obs_period = env->d_map_tables + o_per; p.L = (int)L;
+  p.obs_tile = staged ? env->d_map_tables + o_tile : nullptr;
   p.background = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bg);
   p.blue_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_bt);
   p.red_terr = reinterpret_cast<const uint16_t*>(env->d_map_tables + o_rt);
