@@ -249,6 +249,9 @@ class MazeVecEnv(_MapVecEnv):
     """`num_envs` x MazeSingleAgentEnv (maze.py:26-377), constructor kwargs as in maze.py:31-40.
     Observations: the "map" option - `_encode_map()` values [N, W, H] indexed [x][y] (uint8, or float64 with
     `reference_dtypes=True` as the reference returns, maze.py:246); actions MazeActions Discrete(5)."""
+    _render_family = "maze"
+    metadata = {"render_modes": ["rgb_array"], "autoreset_mode": "same_step"}
+    render_mode = "rgb_array"
     family = _lib.FAMILY_MAZE
     ref_dtype = torch.float64
     info_keys = ("d_a_f", "d_a_ob")

@@ -13,9 +13,31 @@ class VectorEnvSurface:
     def unwrapped(self):
         return self
 
-    def render(self):
-        """Rendering is out of scope: observations are the interface."""
-        return None
+    def render(self, env_ids=None, tile_size=32, out=None):
+        """`MultiGridEnv.render()` frames (rgb_array, highlight off; multigrid.py:546-606, Grid.render grid.py:183-221) of the
+        envs listed in `env_ids` (default: all) -> u8 CUDA tensor [n, H * tile_size, W * tile_size, 3]; one blit kernel over a
+        per-code tile atlas (mg_render).  Collect and Maze families; the other classes return None (no renderer)."""
+        import ctypes as C
+
+        import torch
+        if getattr(self, "_render_family", None) is None:
+            return None
+        ids = None
+        n = self.num_envs
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, device=self.device).to(torch.int32).reshape(-1).contiguous()
+            n = ids.numel()
+        ts = int(tile_size)
+        shape = (n, self.height * ts, self.width * ts, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError(f"render: out must be a contiguous uint8 tensor of shape {shape}")
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self._lib.mg_render(self._h, C.c_void_p(self.state.data_ptr()), None if ids is None else C.c_void_p(ids.data_ptr()), n, ts,
+                                 C.c_void_p(out.data_ptr()), stream)
+        self._check(rc)
+        return out
 
     def close_extras(self, **kwargs):
         return None

@@ -36,8 +36,9 @@ class CollectVecEnv(VectorEnvSurface):
     seed either.  Here: production mode = counter-based Philox4x32-10 keyed by (`seed`, global env
     id); validation mode (`set_trace`) = replay of recorded reference RNG outputs, bit-exact.
     """
-
-    metadata = {"render_modes": []}
+    _render_family = "collect"
+    metadata = {"render_modes": ["rgb_array"], "autoreset_mode": "same_step"}
+    render_mode = "rgb_array"
 
     def __init__(self, num_envs, size=10, num_balls=15, agents_index=(3, 5), balls_index=(0, 1, 2),
                  balls_reward=(1, 1, 1), respawn=False, layout="even_dist", fixed_horizon=False,
@@ -401,6 +402,14 @@ class CollectEnv:
         a = torch.as_tensor(np.asarray(actions, dtype=np.int64).clip(-128, 127).astype(np.int8)).reshape(1, -1)
         obs, rew, term, trunc, _ = self.vec.step(a.to(self.vec.device))
         return (obs[0].cpu().numpy(), rew[0].cpu().numpy(), bool(term[0]), bool(trunc[0]), self._info())
+
+    def render(self, close=False, highlight=False, tile_size=32):
+        """MultiGridEnv.render (multigrid.py:546-606): the frame as ndarray (H * tile_size, W * tile_size, 3) uint8."""
+        if close:
+            return None
+        if highlight:
+            raise NotImplementedError("render(highlight=True) is not available (the default is off)")
+        return self.vec.render(tile_size=tile_size)[0].cpu().numpy()
 
     def close(self):
         self.vec.close()

@@ -138,6 +138,13 @@ int mg_gen_obs(mg_env* env, const void* state_dev, const uint8_t* dirs_dev, int 
  * one-hot planes, out f32 [N][A][W][H][num_ball_types + num_agents].  Collect family, square grids. */
 int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stream);
 
+/* MultiGridEnv.render() frames (render_mode "rgb_array", highlight off: multigrid.py:546-606, Grid.render grid.py:183-221,
+ * Grid.render_tile :132-181, utils/rendering.py) of `n` envs: env_ids_dev int32 [n] on the device, or NULL = envs 0..n-1;
+ * out u8 [n][H*tile_size][W*tile_size][3].  The reference's default tile size is 32 (constants.py:5).  Collect and Maze
+ * handles.  The per-code tile images are rasterised once per tile size on the host when first asked for (the reference's
+ * tile cache); the call itself is one kernel that blits them.  An env id outside [0, N) draws env 0 and sets MG_ERR_OOB. */
+int mg_render(mg_env* env, const void* state_dev, const int32_t* env_ids_dev, int n, int tile_size, uint8_t* out_dev, void* stream);
+
 /* Same as mg_step with HOST buffers: copies actions host->device, steps, copies obs / rewards /
  * flags device->host and waits.  This is the call a gymnasium-style user makes with numpy
  * arrays; buffers should be page-locked for full PCIe bandwidth. */

@@ -198,6 +198,23 @@ def gen_toroid():
         print(f"{stem}: {n} states, toroid {r['toroid'].shape} {r['toroid'].dtype}, {os.path.getsize(path)/1024:.0f} KiB")
 
 
+def gen_render():
+    for stem, env_id, n in (("render_clustered", "multigrid-collect-respawn-clustered-v0", 4),
+                            ("render_rooms", "multigrid-collect-rooms-respawn-v0", 3),
+                            ("render_quadrants15", "multigrid-collect-quadrants15-v0", 2)):
+        r = rh.record_render(env_id, 41, n)
+        path = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path, **r)
+        print(f"{stem}: frames {r['frames_32'].shape} + {r['frames_8'].shape}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
+def gen_maze_render():
+    r = rh.record_maze_render(MAZE_MAP, 51, 8)
+    path = os.path.join(OUT, "render_maze13.npz")
+    np.savez_compressed(path, **r)
+    print(f"render_maze13: frames {r['frames_32'].shape} + {r['frames_8'].shape}, dirs {sorted(set(r['dir'].tolist()))}, {os.path.getsize(path)/1024:.0f} KiB")
+
+
 def gen_generic_partial():
     for stem, size, A, n in (("partial6_9x9_a3", 9, 3, 120), ("partial6_12x12_a5", 12, 5, 60)):
         r = rh.record_generic_partial(size, A, 31, n)
@@ -224,7 +241,7 @@ def gen_generic():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -237,6 +254,9 @@ if __name__ == "__main__":
         gen_partial()
     if "toroid" in which:
         gen_toroid()
+    if "render" in which:
+        gen_render()
+        gen_maze_render()
     if "generic" in which:
         gen_generic()
     if "generic_partial" in which:

@@ -253,3 +253,17 @@ void oc_partial_view6(int64_t N, int W, int H, int A, int V, int see_through_wal
 #ifdef __cplusplus
 }
 #endif
+
+/* ============================================================ rgb_array render (Collect family)
+ * Grid.render / Grid.render_tile / utils/rendering.py, highlight off; see mg_oracle_render.c. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+int oc_render_tile(int type, int colour, int state, int tile_size, uint8_t* out /*[ts][ts][3]*/);
+int oc_render_grid(const uint8_t* obs /*[N][W][H][3] Grid.encode()*/, int64_t N, int W, int H, int tile_size,
+                   uint8_t* out /*[N][H*ts][W*ts][3]*/);
+int oc_render_maze(const uint8_t* field_map /*[S][S]*/, int S, int64_t N, const int16_t* pos /*[N][2]*/, const int8_t* dir /*[N]*/,
+                   int tile_size, uint8_t* out /*[N][S*ts][S*ts][3]*/);
+#ifdef __cplusplus
+}
+#endif

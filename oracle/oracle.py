@@ -199,6 +199,27 @@ def encode3(cells: np.ndarray) -> np.ndarray:
     return out
 
 
+def render_grid(obs: np.ndarray, tile_size: int = 32) -> np.ndarray:
+    """Grid.render(tile_size) of Grid.encode() observations u8 [N, W, H, 3] -> frames u8 [N, H*ts, W*ts, 3]."""
+    obs = np.ascontiguousarray(obs, np.uint8)
+    N, W, H, _ = obs.shape
+    out = np.empty((N, H * tile_size, W * tile_size, 3), np.uint8)
+    rc = lib().oc_render_grid(_p(obs), C.c_int64(N), C.c_int(W), C.c_int(H), C.c_int(tile_size), _p(out))
+    assert rc == 0, "oc_render_grid: cell outside the Collect world"
+    return out
+
+
+def render_maze(field_map: np.ndarray, pos: np.ndarray, dirs: np.ndarray, tile_size: int = 32) -> np.ndarray:
+    """MazeSingleAgentEnv.render(tile_size) for agents at pos [N, 2] facing dirs [N] on one map -> u8 [N, S*ts, S*ts, 3]."""
+    fm = np.ascontiguousarray(field_map, np.uint8)
+    pos = np.ascontiguousarray(pos, np.int16); dirs = np.ascontiguousarray(dirs, np.int8)
+    S, N = fm.shape[0], pos.shape[0]
+    out = np.empty((N, S * tile_size, S * tile_size, 3), np.uint8)
+    rc = lib().oc_render_maze(_p(fm), C.c_int(S), C.c_int64(N), _p(pos), _p(dirs), C.c_int(tile_size), _p(out))
+    assert rc == 0, "oc_render_maze: cell outside the Maze world"
+    return out
+
+
 def philox4x32_10(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)

@@ -414,6 +414,77 @@ def record_partial_views(env_id, seed, n_samples, view_sizes=(3, 5, 7)):
     return {k: np.array(v) for k, v in out.items()}
 
 
+# --------------------------------------------------------------------- rgb_array render recording
+def record_render(env_id, seed, n_samples, tile_sizes=(32, 8)):
+    """Reference `MultiGridEnv.render()` frames (multigrid.py:546-606 -> Grid.render grid.py:183-221 -> Grid.render_tile
+    :132-181 -> utils/rendering.py) on states of a Collect env, highlight off (the default).  Agent directions are set by
+    hand so that all four rotations of the agent triangle are covered (Collect itself never turns its agents)."""
+    import_reference()
+    from gym_multigrid.core.grid import Grid
+    env, tl = make_collect(env_id)
+    random.seed(seed); np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env.reset(seed=seed)
+    A = len(env.agents)
+    out = dict(grid_obs=[], tile_size=[], frame=[], pos=[])
+    for s in range(n_samples):
+        for _ in range(int(rng.integers(1, 6))):
+            _, _, term, trunc, _ = env.step([int(a) for a in rng.integers(0, 4, size=A)])
+            if term or trunc or env.step_count >= 45:
+                env.reset(seed=seed + s)
+        for a in env.agents:
+            a.dir = int(rng.integers(0, 4))
+        for ts in tile_sizes:
+            Grid.tile_cache.clear()            # every frame is rendered from scratch: no tile of an earlier size / test leaks in
+            frame = env.render(tile_size=ts)
+            assert frame.dtype == np.uint8 and frame.shape == (env.height * ts, env.width * ts, 3)
+            out["grid_obs"].append(env.grid.encode().copy())
+            out["tile_size"].append(ts)
+            out["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+            out["frame"].append(frame.copy())
+        for a in env.agents:
+            a.dir = 3
+    r = {k: (np.array(v) if k != "frame" else v) for k, v in out.items()}
+    # frames of the two tile sizes have different shapes: one array per size
+    for ts in tile_sizes:
+        idx = [i for i, t in enumerate(out["tile_size"]) if t == ts]
+        r[f"frames_{ts}"] = np.stack([out["frame"][i] for i in idx])
+        r[f"grid_obs_{ts}"] = np.stack([out["grid_obs"][i] for i in idx])
+        r[f"pos_{ts}"] = np.stack([out["pos"][i] for i in idx])
+    del r["frame"], r["grid_obs"], r["tile_size"], r["pos"]
+    return r
+
+
+def record_maze_render(map_path, seed, n_samples, tile_sizes=(32, 8)):
+    """Reference `render()` frames of MazeSingleAgentEnv (maze.py:26-377; white Floor, grey Obstacle, red Flag on white, blue
+    agent triangle on white) along a random walk; the state needed to redraw them: field_map, agent pos, agent dir."""
+    import_reference()
+    from gym_multigrid.core.grid import Grid
+    from gym_multigrid.envs.maze import MazeSingleAgentEnv
+    env = MazeSingleAgentEnv(map_path, max_steps=1000, observation_option="map")
+    np.random.seed(seed)
+    rng = np.random.default_rng(seed)
+    env.reset(seed=seed)
+    out = dict(pos=[], dir=[])
+    frames = {ts: [] for ts in tile_sizes}
+    for s in range(n_samples):
+        for _ in range(int(rng.integers(0 if s == 0 else 1, 7))):   # sample 0 is the reset state (dir 3)
+            _, _, term, trunc, _ = env.step(int(rng.integers(0, 5)))
+            if term or trunc:
+                env.reset(seed=seed + s)
+        out["pos"].append(np.asarray(env.agents[0].pos, dtype=np.int16).copy())
+        out["dir"].append(int(env.agents[0].dir))
+        for ts in tile_sizes:
+            Grid.tile_cache.clear()
+            f = env.render(tile_size=ts)
+            assert f.dtype == np.uint8 and f.shape == (env.height * ts, env.width * ts, 3)
+            frames[ts].append(f.copy())
+    r = dict(field_map=np.asarray(env._field_map).astype(np.uint8), pos=np.stack(out["pos"]), dir=np.array(out["dir"], np.int8))
+    for ts in tile_sizes:
+        r[f"frames_{ts}"] = np.stack(frames[ts])
+    return r
+
+
 # --------------------------------------------------------------------- Toroid wrapper recording
 def record_toroid(env_id, seed, n_samples):
     """Reference ToroidObservation (wrappers/toroid.py:6-68) outputs on states of a Collect env."""

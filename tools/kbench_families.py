@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of every kernel family besides the Collect step (development aid; tools/kbench.py covers Collect).
 
-    python tools/kbench_families.py [--which ctf,maze,view,toroid,wildfire,generic,collect_streams] [--reps 40]
+    python tools/kbench_families.py [--which ctf,maze,view,toroid,wildfire,generic,render,collect_streams] [--reps 40]
 
 Same protocol as bench.py: CUDA graph over B independent env batches whose working set exceeds the 126 MB L2,
 CUDA events on the launching stream, warm-up first.  Each line reports the algorithmic bytes per env-step of that
@@ -198,6 +198,30 @@ def bench_generic(args):
     report("generic_kernel 12x12 A=5 encode_dim 6 obs per agent", n, us, bpe, batches=B)
     for e in envs:
         e.close()
+
+
+def bench_render(args):
+    """render(): frames of the first n envs, tile sizes 32 (the reference default) and 8; bytes = the frame + the cells read."""
+    N = 4096
+    env = mg.make_vec("multigrid-collect-respawn-clustered-v0", N, seed=0)
+    env.reset()
+    for ts, n in ((32, 1024), (32, 64), (8, 4096)):
+        frame = 10 * ts * 10 * ts * 3
+        B = max(2, int(np.ceil(400e6 / (frame * n))))
+        outs = [torch.empty((n, 10 * ts, 10 * ts, 3), dtype=torch.uint8, device="cuda:0") for _ in range(B)]
+        ids = torch.arange(n, device="cuda:0", dtype=torch.int32)
+        us = graph_time([lambda o=o: env.render(env_ids=ids, tile_size=ts, out=o) for o in outs], args.reps)
+        report(f"render_kernel Collect 10x10 tile_size {ts}", n, us, frame + 100, batches=B)
+    env.close()
+    fm = golden("maze_gen64", "field_map")
+    m = mg.make_maze_vec(256, fm)
+    m.reset()
+    for ts, n in ((8, 256),):
+        frame = 64 * ts * 64 * ts * 3
+        outs = [torch.empty((n, 64 * ts, 64 * ts, 3), dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+        us = graph_time([lambda o=o: m.render(tile_size=ts, out=o) for o in outs], args.reps)
+        report(f"render_kernel Maze 64x64 tile_size {ts}", n, us, frame + 4, batches=2)
+    m.close()
 
 
 def bench_collect_streams(args):
