@@ -32,6 +32,14 @@ constexpr int MZ_AGENT = 1, MZ_FLAG = 2, MZ_OBSTACLE = 3;
 constexpr int CT_BLUE_TERR = 0, CT_RED_TERR = 1, CT_BLUE_AGENT = 2, CT_RED_AGENT = 3, CT_BLUE_FLAG = 4, CT_RED_FLAG = 5,
               CT_OBSTACLE = 6;
 constexpr uint32_t FL_DEAD = 1u << 24, FL_COLLIDED = 2u << 24;  // Agent.terminated / Agent.collided (agent.py:97-100)
+// flags bits 2-3: the CtF agent's sticky background colour, 0 as constructed (the team's), 1 light_blue, 2 light_red: set by a move onto
+// a territory / flag cell, left alone elsewhere (ctf.py:1214-1230, agent.py:197-200); only render() reads it
+constexpr uint32_t FL_BG_MASK = 12u << 24, FL_BG_BLUE = 4u << 24, FL_BG_RED = 8u << 24;
+__device__ __forceinline__ uint32_t bg_after_move(uint32_t w, int terrain_code) {
+  if (terrain_code == 0 || terrain_code == 4) return (w & ~FL_BG_MASK) | FL_BG_BLUE;   // CT_BLUE_TERR, CT_BLUE_FLAG
+  if (terrain_code == 1 || terrain_code == 5) return (w & ~FL_BG_MASK) | FL_BG_RED;    // CT_RED_TERR, CT_RED_FLAG
+  return w;
+}
 
 __device__ __forceinline__ uint32_t ag_pack(int x, int y, int dir, int fl) {
   return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)dir << 16) | ((uint32_t)fl << 24);
@@ -159,8 +167,9 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
     bool occupied = false;  // an agent object (alive, defeated, or itself when staying) sits on the cell
     for (int j = 0; j < n; ++j) occupied |= ((ag[j * kMapE] ^ target) & 0xFFFFu) == 0;
     if (occupied) { if (p.obstacle_penalty != 0 && !p.variant_1v1) ag[i * kMapE] = w | FL_COLLIDED; continue; }  // :1231-1236 (1v1 has no collided logic, :498-501)
-    if (terr[ny * S + nx] == CT_OBSTACLE && p.obstacle_penalty == 0) continue;  // Obstacle.can_overlap()
-    ag[i * kMapE] = (w & 0xFF000000u) | target | ((uint32_t)dir_of_action(a, (int)((w >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
+    const int tc = terr[ny * S + nx];
+    if (tc == CT_OBSTACLE && p.obstacle_penalty == 0) continue;  // Obstacle.can_overlap()
+    ag[i * kMapE] = (bg_after_move(w, tc) & 0xFF000000u) | target | ((uint32_t)dir_of_action(a, (int)((w >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
   }
   term = false; trunc = h.x >= p.max_steps;  // :1310-1311
   rew = 0.0;
@@ -269,7 +278,7 @@ __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, u
     const int tc = terr[inb ? ny * S + nx : 0];
     const bool go = live && inb && !occupied && !(tc == CT_OBSTACLE && !pen);  // Obstacle.can_overlap()
     const bool hit = live && inb && occupied && pen && !p.variant_1v1;        // :1231-1236 (1v1 has no collided logic, :498-501)
-    const uint32_t moved = (wi & 0xFF000000u) | target | ((uint32_t)dir_of_action(a, (int)((wi >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
+    const uint32_t moved = (bg_after_move(wi, tc) & 0xFF000000u) | target | ((uint32_t)dir_of_action(a, (int)((wi >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
     const uint32_t nw = go ? moved : (hit ? (wi | FL_COLLIDED) : wi);
 #pragma unroll
     for (int j = 0; j < n; ++j) w[j] = (i == j) ? nw : w[j];

@@ -46,8 +46,9 @@ cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
 cudaError_t launch_view6(const View6Params& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
 void build_render_atlas(int family, int ts, std::vector<uint8_t>& atlas);
-cudaError_t launch_render(const uint8_t* cells, const uint8_t* agents, int agent_stride, int family, long long N, const int32_t* env_ids,
-                          int n, int W, int H, int ts, const uint8_t* atlas, uint8_t* out, int32_t* status, cudaStream_t st);
+cudaError_t launch_render(const uint8_t* cells, const uint8_t* agents, int agent_stride, int family, int n_agents, int num_blue, int variant_1v1,
+                          long long N, const int32_t* env_ids, int n, int W, int H, int ts, const uint8_t* atlas, uint8_t* out, int32_t* status,
+                          cudaStream_t st);
 size_t view_smem_bytes(const ViewParams& p);
 int view_max();
 int view_tile_envs();
@@ -801,8 +802,8 @@ extern "C" int mg_gen_obs(mg_env* env, const void* state, const uint8_t* dirs, i
 
 extern "C" int mg_render(mg_env* env, const void* state, const int32_t* env_ids, int n, int tile_size, uint8_t* out, void* stream) {
   if (!env || !state || !out) return fail(env, "mg_render: null argument");
-  if (env->family != MG_FAMILY_COLLECT && env->family != MG_FAMILY_MAZE)
-    return fail(env, "mg_render: Collect and Maze families only (CtF agents carry a sticky background colour the state does not hold; the generic family draws DefaultWorld objects)");
+  if (env->family != MG_FAMILY_COLLECT && env->family != MG_FAMILY_MAZE && env->family != MG_FAMILY_CTF)
+    return fail(env, "mg_render: Collect, Maze and CtF families only (the generic family draws DefaultWorld objects; Wildfire has no reference renderer)");
   if (n < 0 || tile_size < 1 || tile_size > 64) return fail(env, "mg_render: n >= 0 and 1 <= tile_size <= 64");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
@@ -810,7 +811,7 @@ extern "C" int mg_render(mg_env* env, const void* state, const int32_t* env_ids,
   for (auto& a : env->atlases) if (a.first == tile_size) atlas = a.second;
   if (!atlas) {   // first frame at this tile size: rasterise the tiles on the host (Grid.render_tile's cache, grid.py:147-150) and upload
     std::vector<uint8_t> host;
-    mg::build_render_atlas(env->family == MG_FAMILY_COLLECT ? 0 : 1, tile_size, host);
+    mg::build_render_atlas(env->family == MG_FAMILY_COLLECT ? 0 : (env->family == MG_FAMILY_MAZE ? 1 : 2), tile_size, host);
     uint8_t* d = nullptr;
     if ((ce = cudaMalloc(&d, host.size())) != cudaSuccess) return cuda_fail(env, "cudaMalloc atlas", ce);
     if ((ce = cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return cuda_fail(env, "atlas upload", ce); }
@@ -819,12 +820,12 @@ extern "C" int mg_render(mg_env* env, const void* state, const int32_t* env_ids,
   }
   const uint8_t* s = static_cast<const uint8_t*>(state);
   if (env->family == MG_FAMILY_COLLECT)
-    ce = mg::launch_render(s + env->plane_off[MG_PLANE_GRID], nullptr, 0, 0, env->cfg.num_envs, env_ids, n, env->cfg.width, env->cfg.height,
-                           tile_size, atlas, out, env->d_status, static_cast<cudaStream_t>(stream));
+    ce = mg::launch_render(s + env->plane_off[MG_PLANE_GRID], nullptr, 0, 0, 0, 0, 0, env->cfg.num_envs, env_ids, n, env->cfg.width,
+                           env->cfg.height, tile_size, atlas, out, env->d_status, static_cast<cudaStream_t>(stream));
   else
-    ce = mg::launch_render(env->mbase.field_map, s + env->plane_off[MG_MAP_PLANE_AGENTS], (int)env->plane_row[MG_MAP_PLANE_AGENTS], 1,
-                           env->mcfg.num_envs, env_ids, n, env->mcfg.size, env->mcfg.size, tile_size, atlas, out, env->d_status,
-                           static_cast<cudaStream_t>(stream));
+    ce = mg::launch_render(env->mbase.field_map, s + env->plane_off[MG_MAP_PLANE_AGENTS], (int)env->plane_row[MG_MAP_PLANE_AGENTS],
+                           env->family == MG_FAMILY_MAZE ? 1 : 2, env->mbase.n, env->mbase.nb, env->mbase.variant_1v1, env->mcfg.num_envs,
+                           env_ids, n, env->mcfg.size, env->mcfg.size, tile_size, atlas, out, env->d_status, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return cuda_fail(env, "render_kernel", ce);
   if (n > 0) env->launches += 1;
   return 0;

@@ -32,6 +32,8 @@ struct TileSpec {      // what Grid.render_tile draws under the two grid lines
 const uint8_t kColors[10][3] = {{228, 3, 3}, {255, 140, 0}, {255, 237, 0}, {0, 128, 38}, {0, 77, 255},
                                 {117, 7, 135}, {120, 79, 23}, {100, 100, 100}, {234, 153, 153}, {90, 170, 223}};
 const uint8_t kMazeWhite[3] = {255, 250, 250}, kMazeRed[3] = {228, 3, 3}, kMazeGrey[3] = {100, 100, 100}, kMazeBlue[3] = {0, 77, 255};
+// CTF_COLORS constants.py:21-35
+const uint8_t kCtfLightBlue[3] = {240, 248, 255}, kCtfLightRed[3] = {255, 228, 225}, kCtfBlueGrey[3] = {140, 146, 172}, kCtfRedGrey[3] = {170, 152, 169};
 
 bool hit(const TileSpec& t, double x, double y, double ct, double st) {
   if (t.shape == 1) return x >= 0 && x <= 1 && y >= 0 && y <= 1;                          // point_in_rect(0, 1, 0, 1)
@@ -83,6 +85,7 @@ void raster_tile(const TileSpec& t, int ts, uint8_t* out) {
 //   Collect (CollectWorld): index = the packed grid byte  type | colour << 2 | dir << 6  (empty 0, wall 1, ball 2, agent 3)
 //   Maze (MazeWorld, maze.py:93-101, 183-198): 0 background Floor (white), 2 Flag (red on white), 3 Obstacle (grey),
 //         4 + dir = the agent (blue triangle on white)
+//   CtF (CtfWorld): the map's codes 0 / 1 / 4 / 5 / 6, agents from 8 (team, grey, background colour, dir)
 void build_render_atlas(int family, int ts, std::vector<uint8_t>& atlas) {
   const size_t tile = (size_t)ts * ts * 3;
   atlas.assign(256 * tile, 0);
@@ -100,6 +103,18 @@ void build_render_atlas(int family, int ts, std::vector<uint8_t>& atlas) {
       put(2 | (colour << 2), 2, 0, kColors[colour], nullptr);                                       // Ball.render object.py:320-321
       for (int dir = 0; dir < 4; ++dir) put(3 | (colour << 2) | (dir << 6), 3, dir, kColors[colour], nullptr);  // Agent.render agent.py:105-117
     }
+  } else if (family == 2) {   // MG_FAMILY_CTF (CtfWorld; ctf.py:998-1031, 765-815)
+    put(0, 1, 0, kCtfLightBlue, nullptr);                                                           // Floor "blue_territory"
+    put(1, 1, 0, kCtfLightRed, nullptr);                                                            // Floor "red_territory"
+    put(4, 2, 0, kMazeBlue, kCtfLightBlue);                                                         // Flag blue on light_blue
+    put(5, 2, 0, kMazeRed, kCtfLightRed);                                                           // Flag red on light_red
+    put(6, 1, 0, kMazeGrey, nullptr);                                                               // Obstacle
+    for (int team = 0; team < 2; ++team)        // agents: 8 + ((team * 2 + grey) * 2 + background is light_red) * 4 + dir
+      for (int g = 0; g < 2; ++g)               // grey once terminated (ctf.py:1316-1332, 1409-1418)
+        for (int bg = 0; bg < 2; ++bg)
+          for (int dir = 0; dir < 4; ++dir)
+            put(8 + ((team * 2 + g) * 2 + bg) * 4 + dir, 3, dir, team ? (g ? kCtfRedGrey : kMazeRed) : (g ? kCtfBlueGrey : kMazeBlue),
+                bg ? kCtfLightRed : kCtfLightBlue);
   } else {             // MG_FAMILY_MAZE
     put(0, 1, 0, kMazeWhite, nullptr);                                                              // Floor.render object.py:147-148
     put(2, 2, 0, kMazeRed, kMazeWhite);                                                             // Flag.render object.py:366-372
@@ -110,8 +125,9 @@ void build_render_atlas(int family, int ts, std::vector<uint8_t>& atlas) {
 
 struct RenderParams {
   const uint8_t* cells;     // Collect: grid plane [N_pad][W*H] index x*H+y; Maze: the shared field_map [S*S] index x*S+y
-  const uint8_t* agents;    // Maze: agent words (x, y, dir, flags), one row of `agent_stride` bytes per env
-  int agent_stride, family;
+  const uint8_t* agents;    // Maze / CtF: agent words (x, y, dir, flags), one row of `agent_stride` bytes per env
+  int agent_stride, family; // 0 Collect, 1 Maze, 2 CtF
+  int n_agents, num_blue, variant_1v1;
   long long N;
   const int32_t* env_ids;   // [n] envs to draw, or null = envs 0..n-1
   int n, W, H, ts, JB;      // JB = rows of tiles one CTA draws
@@ -145,7 +161,15 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
     else {
       code = p.cells[i * p.H + j];
       const uint8_t* a = p.agents + e * p.agent_stride;   // the agent object replaces the cell it stands on (agent.py:195-196)
-      if (a[0] == i && a[1] == j) code = 4 + (a[2] & 3);
+      if (p.family == 1) { if (a[0] == i && a[1] == j) code = 4 + (a[2] & 3); }
+      else
+        for (int k = 0; k < p.n_agents; ++k, a += 4)
+          if (a[0] == i && a[1] == j) {
+            const int team = k >= p.num_blue, bgs = (a[3] >> 2) & 3;
+            const int bg_red = bgs ? bgs == 2 : team;            // 0 = as constructed: the team's own light colour
+            const int grey = (a[3] & 1) && !p.variant_1v1;       // the 1v1 env never recolours (ctf.py:551-654)
+            code = 8 + ((team * 2 + grey) * 2 + bg_red) * 4 + (a[2] & 3);
+          }
     }
     s_tile[t] = (uint32_t)code * (uint32_t)tile_bytes;
   }
@@ -212,12 +236,14 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
   }
 }
 
-cudaError_t launch_render(const uint8_t* cells, const uint8_t* agents, int agent_stride, int family, long long N, const int32_t* env_ids,
-                          int n, int W, int H, int ts, const uint8_t* atlas, uint8_t* out, int32_t* status, cudaStream_t st) {
+cudaError_t launch_render(const uint8_t* cells, const uint8_t* agents, int agent_stride, int family, int n_agents, int num_blue, int variant_1v1,
+                          long long N, const int32_t* env_ids, int n, int W, int H, int ts, const uint8_t* atlas, uint8_t* out, int32_t* status,
+                          cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   if (W > kRenderMaxTiles) return cudaErrorInvalidValue;
   RenderParams p;
   p.cells = cells; p.agents = agents; p.agent_stride = agent_stride; p.family = family; p.N = N; p.env_ids = env_ids;
+  p.n_agents = n_agents; p.num_blue = num_blue; p.variant_1v1 = variant_1v1;
   p.n = n; p.W = W; p.H = H; p.ts = ts; p.atlas = atlas; p.out = out; p.status = status;
   const int trow = ts * 3;
   const long long strip = (long long)ts * W * trow;            // bytes of one row of tiles

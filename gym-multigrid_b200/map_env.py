@@ -310,6 +310,9 @@ class CtfVecEnv(_MapVecEnv):
     the device.  Observations: the "map" option - `_encode_map()` (transposed, [N, H, W]; uint8, or int64 with
     `reference_dtypes=True`); `positional_obs()` / `flattened_obs()` assemble the other two options from the
     state planes.  Actions MultiDiscrete([5] * num_blue_agents); reward = scalar team reward (float64)."""
+    _render_family = "ctf"
+    metadata = {"render_modes": ["rgb_array"], "autoreset_mode": "same_step"}
+    render_mode = "rgb_array"
     family = _lib.FAMILY_CTF
     ref_dtype = torch.int64
     info_keys = ("d_ba_ra", "d_ba_bf", "d_ba_rf", "d_ra_bf", "d_ra_rf", "d_bf_rf", "d_ba_bb", "d_ba_rb", "d_ra_bb", "d_ra_rb", "d_ba_ob")

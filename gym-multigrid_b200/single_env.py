@@ -46,8 +46,7 @@ class _SingleMapEnv:
         return {k: float(v[0]) for k, v in self.vec.get_info().items()}
 
     def render(self, close=False, highlight=False, tile_size=32):
-        """MultiGridEnv.render (multigrid.py:546-606) as ndarray (H * tile_size, W * tile_size, 3) uint8 - Maze; the CtF classes
-        return None (their agents carry a sticky background colour that is not part of the batched state)."""
+        """MultiGridEnv.render (multigrid.py:546-606) as ndarray (H * tile_size, W * tile_size, 3) uint8."""
         if close or highlight:
             return None
         frames = self.vec.render(tile_size=tile_size)

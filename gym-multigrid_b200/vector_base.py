@@ -16,7 +16,7 @@ class VectorEnvSurface:
     def render(self, env_ids=None, tile_size=32, out=None):
         """`MultiGridEnv.render()` frames (rgb_array, highlight off; multigrid.py:546-606, Grid.render grid.py:183-221) of the
         envs listed in `env_ids` (default: all) -> u8 CUDA tensor [n, H * tile_size, W * tile_size, 3]; one blit kernel over a
-        per-code tile atlas (mg_render).  Collect and Maze families; the other classes return None (no renderer)."""
+        per-code tile atlas (mg_render).  Collect, Maze and CtF families; the other classes return None (no renderer)."""
         import ctypes as C
 
         import torch

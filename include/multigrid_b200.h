@@ -140,9 +140,9 @@ int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stre
 
 /* MultiGridEnv.render() frames (render_mode "rgb_array", highlight off: multigrid.py:546-606, Grid.render grid.py:183-221,
  * Grid.render_tile :132-181, utils/rendering.py) of `n` envs: env_ids_dev int32 [n] on the device, or NULL = envs 0..n-1;
- * out u8 [n][H*tile_size][W*tile_size][3].  The reference's default tile size is 32 (constants.py:5).  Collect and Maze
- * handles.  The per-code tile images are rasterised once per tile size on the host when first asked for (the reference's
- * tile cache); the call itself is one kernel that blits them.  An env id outside [0, N) draws env 0 and sets MG_ERR_OOB. */
+ * out u8 [n][H*tile_size][W*tile_size][3].  The reference's default tile size is 32 (constants.py:5).  Collect, Maze and
+ * CtF handles (CtF agents: grey once terminated, on the sticky background colour kept in flags bits 2-3 of the agent word).
+ * The per-code tile images are rasterised once per tile size on the host when first asked for (the reference's tile cache); the call itself is one kernel that blits them.  An env id outside [0, N) draws env 0 and sets MG_ERR_OOB. */
 int mg_render(mg_env* env, const void* state_dev, const int32_t* env_ids_dev, int n, int tile_size, uint8_t* out_dev, void* stream);
 
 /* Same as mg_step with HOST buffers: copies actions host->device, steps, copies obs / rewards /
@@ -212,7 +212,8 @@ typedef struct mg_map_config {
 /* planes of the map families' state buffer */
 enum { MG_MAP_PLANE_AGENTS = 0, /* u8  [N_pad][row]: agent i (blue first, n = num_blue + num_red) at bytes 4i .. 4i+3 =
                                    x, y (Agent.pos), dir (Agent.dir), flags (bit0 terminated / defeated, bit1 collided,
-                                   agent.py:97-100); row = 4 * (n rounded up to a power of two) bytes */
+                                   agent.py:97-100; CtF bits 2-3: Agent.bg_color, 0 as constructed, 1 light_blue, 2 light_red,
+                                   ctf.py:1214-1230); row = 4 * (n rounded up to a power of two) bytes */
        MG_MAP_PLANE_HDR = 1,    /* i32 [N_pad][4]  step_count, CtF game_stats bits (ctf.py:1068-1073: bit0 blue_flag_captured,
                                    bit1 red_flag_captured, bit 8+i agent i defeated in a battle; cleared by reset), Philox block
                                    counter, episodes */

@@ -160,6 +160,30 @@ def gen_ctf():
               f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_ctf_render():
+    """CtF episodes with the agents' sticky background colour after every step and rgb_array frames every 7th step (and at the
+    end): the replay inputs of gen_ctf plus what `render()` shows.  Penalty 0.5 episodes add collided (grey) agents."""
+    for stem, nb, nr, pen, episodes in (("render_ctf_2v2", 2, 2, 0.0, 5), ("render_ctf_3v4_penalty", 3, 4, 0.5, 4)):
+        eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, np.random.default_rng(3500 + seed), nb, nr, pen, render_every=7) for seed in range(episodes)]
+        for e in eps:
+            e["obs"] = e["obs"].astype(np.uint8)
+            e["init_obs"] = e["init_obs"].astype(np.uint8)
+        out = rh.pack_episodes(eps, ["actions", "red_actions", "order", "n_battles", "blue_win", "obs", "pos", "dir", "dead", "bg"],
+                               ["field_map", "init_obs", "init_pos", "init_dir", "init_bg", "blue_place", "red_place"])
+        out["field_map"] = out["field_map"][0].astype(np.uint8)
+        out["meta_num_blue"], out["meta_num_red"] = np.array(nb), np.array(nr)
+        out["meta_obstacle_penalty_ratio"] = np.array(pen)
+        out["frame_episode"] = np.concatenate([np.full(len(e["frame_step"]), i, np.int32) for i, e in enumerate(eps)])
+        out["frame_step"] = np.concatenate([e["frame_step"] for e in eps])       # -1 = after reset
+        for ts in (32, 8):
+            out[f"frames_{ts}"] = np.concatenate([e[f"frames_{ts}"] for e in eps])
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, frames={len(out['frame_step'])}, dead agents drawn="
+              f"{int(sum(out['dead'][e, s].sum() for e, s in zip(out['frame_episode'], out['frame_step']) if s >= 0))}, "
+              f"bg != team colour on {int((out['bg'] != out['init_bg'][:, None]).sum())} agent-steps, {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 def gen_ctf1v1():
     eps = [rh.record_ctf_1v1_episode(CTF_MAP, seed, np.random.default_rng(4000 + seed)) for seed in range(40)]
     for e in eps:
@@ -257,6 +281,7 @@ if __name__ == "__main__":
     if "render" in which:
         gen_render()
         gen_maze_render()
+        gen_ctf_render()
     if "generic" in which:
         gen_generic()
     if "generic_partial" in which:

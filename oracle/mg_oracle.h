@@ -264,6 +264,8 @@ int oc_render_grid(const uint8_t* obs /*[N][W][H][3] Grid.encode()*/, int64_t N,
                    uint8_t* out /*[N][H*ts][W*ts][3]*/);
 int oc_render_maze(const uint8_t* field_map /*[S][S]*/, int S, int64_t N, const int16_t* pos /*[N][2]*/, const int8_t* dir /*[N]*/,
                    int tile_size, uint8_t* out /*[N][S*ts][S*ts][3]*/);
+int oc_render_ctf(const uint8_t* field_map /*[S][S]*/, int S, int64_t N, int n, int num_blue, int variant_1v1, const uint8_t* pos /*[N][n][2]*/,
+                  const uint8_t* dir /*[N][n]*/, const uint8_t* flags /*[N][n]*/, int tile_size, uint8_t* out /*[N][S*ts][S*ts][3]*/);
 #ifdef __cplusplus
 }
 #endif

@@ -221,6 +221,10 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
       if (code == CT_OBSTACLE && c->obstacle_penalty == 0) continue; /* Obstacle.can_overlap() <=> penalty != 0 */
       dir[i] = (uint8_t)dir_of(nx - pos[2 * i], ny - pos[2 * i + 1], dir[i]); /* Agent.move agent.py:167-200 */
       pos[2 * i] = (uint8_t)nx; pos[2 * i + 1] = (uint8_t)ny;
+      /* the agent's background colour follows the territory it moved onto and is left alone elsewhere (ctf.py:1214-1230,
+       * agent.py:197-200): flags bits 2-3 = 0 as constructed (the team's colour), 1 light_blue, 2 light_red; only render() reads it */
+      if (code == CT_BLUE_TERR || code == CT_BLUE_FLAG) fl[i] = (uint8_t)((fl[i] & ~12) | 4);
+      else if (code == CT_RED_TERR || code == CT_RED_FLAG) fl[i] = (uint8_t)((fl[i] & ~12) | 8);
     }
     uint8_t term = 0, trunc = st->step_count[e] >= c->max_steps; /* :1310-1311 */
     double rew = 0.0;

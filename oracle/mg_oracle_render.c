@@ -147,3 +147,46 @@ int oc_render_grid(const uint8_t* obs, int64_t N, int W, int H, int ts, uint8_t*
   free(cache); free(have);
   return rc;
 }
+
+/* CtFMvNEnv.render() (Ctf1v1Env: variant_1v1): one map (field_map [S][S] index [x][y], CtfWorld codes 0 blue territory,
+ * 1 red territory, 4 blue flag, 5 red flag, 6 obstacle; ctf.py:998-1031), n agents per env (the first num_blue are blue)
+ * at pos [N][n][2] facing dir [N][n] with flags [N][n]: bit 0 terminated, bits 2-3 background colour (see oc_ctf_step).
+ * Floor light_blue / light_red (object.py:147-148), Obstacle grey, Flag blue on light_blue / red on light_red (:366-372);
+ * Agent triangle (agent.py:105-117) blue / red, blue_grey / red_grey once terminated (ctf.py:1316-1332, 1409-1418; the 1v1
+ * env never recolours), on its sticky background colour; agent tiles are uncached (ctf.py:69).  CTF_COLORS constants.py:21-35. */
+int oc_render_ctf(const uint8_t* field_map, int S, int64_t N, int n, int num_blue, int variant_1v1, const uint8_t* pos,
+                  const uint8_t* dir, const uint8_t* flags, int ts, uint8_t* out) {
+  static const uint8_t light_blue[3] = {240, 248, 255}, light_red[3] = {255, 228, 225}, grey[3] = {100, 100, 100},
+                       blue[3] = {0, 77, 255}, red[3] = {228, 3, 3}, blue_grey[3] = {140, 146, 172}, red_grey[3] = {170, 152, 169};
+  const size_t tile_bytes = (size_t)ts * ts * 3, row_bytes = (size_t)S * ts * 3;
+  uint8_t* tiles = (uint8_t*)calloc((8 + 32) * tile_bytes, 1);   /* static codes 0..6, then agents 8 + ((team * 2 + grey) * 2 + bg_red) * 4 + dir */
+  if (!tiles) return -1;
+  int rc = render_tile(0, 0, light_blue, NULL, ts, tiles) | render_tile(0, 0, light_red, NULL, ts, tiles + tile_bytes) |
+           render_tile(1, 0, blue, light_blue, ts, tiles + 4 * tile_bytes) | render_tile(1, 0, red, light_red, ts, tiles + 5 * tile_bytes) |
+           render_tile(0, 0, grey, NULL, ts, tiles + 6 * tile_bytes);
+  for (int team = 0; team < 2; ++team)
+    for (int g = 0; g < 2; ++g)
+      for (int bg = 0; bg < 2; ++bg)
+        for (int d = 0; d < 4; ++d)
+          rc |= render_tile(2, d, team ? (g ? red_grey : red) : (g ? blue_grey : blue), bg ? light_red : light_blue, ts,
+                            tiles + (size_t)(8 + ((team * 2 + g) * 2 + bg) * 4 + d) * tile_bytes);
+  for (int64_t e = 0; e < N && !rc; ++e)
+    for (int j = 0; j < S; ++j)
+      for (int i = 0; i < S; ++i) {
+        int code = field_map[i * S + j];
+        if (code == 2 || code == 3 || code > 6) { rc = -1; break; }
+        for (int a = 0; a < n; ++a) {
+          const uint8_t* p = pos + (e * n + a) * 2;
+          if (p[0] != i || p[1] != j) continue;
+          const int team = a >= num_blue, fl = flags[e * n + a], bgs = (fl >> 2) & 3;
+          const int bg_red = bgs ? bgs == 2 : team;                 /* 0 = as constructed: the team's own light colour */
+          const int g = (fl & 1) && !variant_1v1;
+          code = 8 + ((team * 2 + g) * 2 + bg_red) * 4 + (dir[e * n + a] & 3);
+        }
+        const uint8_t* tile = tiles + (size_t)code * tile_bytes;
+        for (int y = 0; y < ts; ++y)
+          memcpy(out + ((size_t)e * S * ts + (size_t)j * ts + y) * row_bytes + (size_t)i * ts * 3, tile + (size_t)y * ts * 3, (size_t)ts * 3);
+      }
+  free(tiles);
+  return rc ? -1 : 0;
+}

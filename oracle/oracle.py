@@ -220,6 +220,18 @@ def render_maze(field_map: np.ndarray, pos: np.ndarray, dirs: np.ndarray, tile_s
     return out
 
 
+def render_ctf(field_map, pos, dirs, flags, num_blue, tile_size=32, variant_1v1=False) -> np.ndarray:
+    """CtFMvNEnv.render(tile_size): agents at pos [N, n, 2] facing dirs [N, n] with oracle flags [N, n] -> u8 [N, S*ts, S*ts, 3]."""
+    fm = np.ascontiguousarray(field_map, np.uint8)
+    pos = np.ascontiguousarray(pos, np.uint8); dirs = np.ascontiguousarray(dirs, np.uint8); flags = np.ascontiguousarray(flags, np.uint8)
+    S, (N, n) = fm.shape[0], dirs.shape
+    out = np.empty((N, S * tile_size, S * tile_size, 3), np.uint8)
+    rc = lib().oc_render_ctf(_p(fm), C.c_int(S), C.c_int64(N), C.c_int(n), C.c_int(num_blue), C.c_int(int(variant_1v1)), _p(pos), _p(dirs),
+                             _p(flags), C.c_int(tile_size), _p(out))
+    assert rc == 0, "oc_render_ctf: cell outside the CtF world"
+    return out
+
+
 def philox4x32_10(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)

@@ -320,7 +320,7 @@ def pack_episodes(eps, keys_per_step, keys_static, T=None):
 CTF_INFO_KEYS = ("d_ba_ra", "d_ba_bf", "d_ba_rf", "d_ra_bf", "d_ra_rf", "d_bf_rf", "d_ba_bb", "d_ba_rb", "d_ra_bb", "d_ra_rb", "d_ba_ob")
 
 def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, obstacle_penalty_ratio=0.0,
-                           max_steps=100, observation_option="map", max_battles=16):
+                           max_steps=100, observation_option="map", max_battles=16, render_every=0, tile_sizes=(32, 8)):
     """One episode of the reference CtFMvNEnv (ctf.py:657-1433) on a FRESH instance (agent.terminated is
     never cleared by reset in the reference), with the ordered RNG event log split per step."""
     import_reference()
@@ -340,9 +340,31 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
                    truncated=[], pos=[], dir=[], dead=[], info=[], stats_flags=[], stats_defeated=[])
         init_pos = np.array([np.asarray(a.pos) for a in env.agents], np.int16)
         init_dir = np.array([a.dir for a in env.agents], np.int8)
+        # render recording (render_every > 0): the agents' sticky background colour after every step (1 light_blue, 2 light_red;
+        # agent.py:197-200, ctf.py:1214-1230) and rgb_array frames after the reset and after every `render_every`-th step
+        BG = {"light_blue": 1, "light_red": 2}
+        frames = {ts: [] for ts in tile_sizes}
+        frame_step = []
+
+        def grab(step_index):
+            from gym_multigrid.core.grid import Grid
+            frame_step.append(step_index)
+            for ts in tile_sizes:
+                Grid.tile_cache.clear()
+                frames[ts].append(env.render(tile_size=ts).copy())
+        if render_every:
+            rec["bg"] = []
+            init_bg = np.array([BG[a.bg_color] for a in env.agents], np.uint8)
+            grab(-1)
         while True:
             acts = action_rng.integers(0, 5, size=num_blue)
             obs, rew, term, trunc, info = env.step([int(a) for a in acts])
+            if render_every:
+                rec["bg"].append(np.array([BG[a.bg_color] for a in env.agents], np.uint8))
+                assert all(a.color == (("blue_grey" if i < num_blue else "red_grey") if a.terminated else ("blue" if i < num_blue else "red"))
+                           for i, a in enumerate(env.agents))     # grey <=> terminated (ctf.py:1316-1332, 1409-1418)
+                if (len(rec["bg"]) % render_every) == 0 or term or trunc:
+                    grab(len(rec["bg"]) - 1)
             ints = [ev[1] for ev in log if ev[0] == "integers"]
             shuf = [ev[1] for ev in log if ev[0] == "shuffle"]
             wins = [bool(ev[1]) for ev in log if ev[0] == "choice"]
@@ -374,6 +396,11 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
         out[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
     out["n_battles"] = out["n_battles"].astype(np.int32)
     out["reward"] = out["reward"].astype(np.float64)
+    if render_every:
+        out["init_bg"] = init_bg
+        out["frame_step"] = np.array(frame_step, np.int32)
+        for ts in tile_sizes:
+            out[f"frames_{ts}"] = np.stack(frames[ts])
     return out
 
 

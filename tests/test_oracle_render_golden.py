@@ -41,3 +41,43 @@ def test_tile_known_answers():
     ball[0, 0, 0] = (2, 0, 0)    # ball, red: centre pixel inside the r = 0.31 circle, corner outside
     b = oc.render_grid(ball, 32)[0]
     assert tuple(b[16, 16]) == (228, 3, 3) and tuple(b[31, 31]) == (0, 0, 0)
+
+
+def replay_ctf_render(g, step_fn, state_fn):
+    """Drive `step_fn(actions, trace kwargs)` over the recorded episodes; after the reset and every recorded frame step yield
+    (episode indices, frame rows) so the caller can compare frames.  Shared by the oracle test here and the GPU test."""
+    E, T, nb = g["actions"].shape
+    n = nb + int(g["meta_num_red"])
+    ident = np.arange(n, dtype=np.uint8)[None]
+    fe, fs = g["frame_episode"], g["frame_step"]
+    yield -1, fe[fs == -1], np.where(fs == -1)[0]
+    for t in range(T):
+        live = g["length"] > t
+        step_fn(np.where(live[:, None], g["actions"][:, t], 0),
+                dict(red_actions=g["red_actions"][:, t], order=np.where(live[:, None], g["order"][:, t], ident), blue_win=g["blue_win"][:, t]))
+        pos, dirs, flags = state_fn()
+        assert np.array_equal(pos[live], g["pos"][live, t]) and np.array_equal(dirs[live], g["dir"][live, t])
+        bgs = (flags >> 2) & 3
+        bg = np.where(bgs == 0, g["init_bg"], bgs)          # 0 = as constructed
+        assert np.array_equal(bg[live], g["bg"][live, t]), f"step {t}: sticky background colour (agent.py:197-200)"
+        assert np.array_equal((flags & 1)[live], g["dead"][live, t])
+        rows = np.where(fs == t)[0]
+        if len(rows):
+            yield t, fe[rows], rows
+
+
+@pytest.mark.parametrize("stem", ["render_ctf_2v2", "render_ctf_3v4_penalty"])
+def test_ctf_frames_and_background_state_match_reference(stem):
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    o = oc.CtfOracle(g["field_map"], E, nb, nr, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]))
+    obs = o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
+    assert np.array_equal(obs, g["init_obs"]) and np.array_equal(g["init_bg"], np.repeat([[1] * nb + [2] * nr], E, 0))
+    seen = 0
+    for t, eps, rows in replay_ctf_render(g, lambda a, tr: o.step(a, oc.map_rng(mode=0, **tr)), lambda: (o.pos, o.dir, o.flags)):
+        for ts in (32, 8):
+            got = oc.render_ctf(g["field_map"], o.pos[eps], o.dir[eps], o.flags[eps], nb, ts)
+            assert np.array_equal(got, g[f"frames_{ts}"][rows]), f"frames after step {t}, tile_size {ts}"
+        seen += len(rows)
+    assert seen == len(g["frame_step"]) and o.status.value == 0

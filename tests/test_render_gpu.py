@@ -85,6 +85,55 @@ def test_maze_render_vs_oracle_64x64(cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("stem", ["render_ctf_2v2", "render_ctf_3v4_penalty"])
+def test_ctf_frames_and_background_state_match_reference(stem, cuda_device):
+    """Recorded reference episodes replayed through the CUDA step (trace mode): the sticky background colour of every agent after
+    every step and every recorded frame (grey terminated agents, agents on foreign territory, both tile sizes)."""
+    import gym_multigrid_b200 as mg
+    from test_oracle_render_golden import replay_ctf_render
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    env = mg.make_ctf_vec(E, g["field_map"], num_blue_agents=nb, num_red_agents=nr,
+                          obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]), autoreset=False)
+    env.set_trace(blue_place=g["blue_place"], red_place=g["red_place"])
+    env.reset()
+
+    def step(actions, tr):
+        env.set_trace(**tr)
+        env.step(torch.as_tensor(actions.astype(np.int8), device=cuda_device))
+
+    seen = 0
+    for t, eps, rows in replay_ctf_render(g, step, lambda: (_np(env.agent_pos), _np(env.agent_dir), _np(env.agent_flags))):
+        for ts in (32, 8):
+            got = env.render(env_ids=torch.as_tensor(eps, device=cuda_device), tile_size=ts)
+            assert np.array_equal(_np(got), g[f"frames_{ts}"][rows]), f"frames after step {t}, tile_size {ts}"
+        seen += len(rows)
+    assert seen == len(g["frame_step"]) and env.status() == 0
+    env.close()
+
+
+def test_ctf_render_vs_oracle_philox(cuda_device):
+    """Philox-mode CtF (2v2 with collision penalty, and 1v1 which never recolours) after autoreset steps: frames and flags."""
+    import gym_multigrid_b200 as mg
+    fm = load_golden("ctf_2v2")["field_map"]
+    for nb, nr, v1 in ((2, 2, False), (1, 1, True)):
+        n = 200
+        kw = dict(max_steps=40, seed=13)
+        env = mg.make_ctf1v1_vec(n, fm, **kw) if v1 else mg.make_ctf_vec(n, fm, num_blue_agents=nb, num_red_agents=nr, obstacle_penalty_ratio=0.5, **kw)
+        o = (oc.CtfOracle(fm, n, 1, 1, max_steps=40, variant_1v1=1) if v1 else oc.CtfOracle(fm, n, nb, nr, obstacle_penalty_ratio=0.5, max_steps=40))
+        env.reset(); o.reset(oc.map_rng(mode=1, seed=13))
+        gen = torch.Generator(device=cuda_device).manual_seed(6)
+        for _ in range(25):
+            act = torch.randint(0, 5, (n, nb), generator=gen, device=cuda_device, dtype=torch.int8)
+            env.step(act)
+            o.step(_np(act), oc.map_rng(mode=1, seed=13), autoreset=True)
+        assert np.array_equal(_np(env.agent_flags), o.flags) and np.array_equal(_np(env.agent_pos), o.pos)
+        for ts in (32, 6):
+            assert np.array_equal(_np(env.render(tile_size=ts)), oc.render_ctf(fm, o.pos, o.dir, o.flags, nb, ts, variant_1v1=v1))
+        env.close()
+
+
 def test_single_env_adaptors_render_like_the_reference(cuda_device):
     """`env.render()` of the reference-style classes: ndarray (H * 32, W * 32, 3) uint8 as MultiGridEnv.render returns."""
     import gym_multigrid_b200 as mg
@@ -102,7 +151,7 @@ def test_single_env_adaptors_render_like_the_reference(cuda_device):
     m.close()
     c = CtFMvNEnv(load_golden("ctf_2v2")["field_map"])
     c.reset()
-    assert c.render() is None            # CtF: documented gap (sticky agent background colour)
+    assert c.render().shape == (320, 320, 3)
     c.close()
     wf = mg.make_wildfire_vec(4, size=8, num_agents=2)
     assert wf.render() is None
