@@ -127,10 +127,28 @@ def bench_maze(args):
             e.close()
 
 
+def bench_maze_partial(args):
+    """Config 4 (fused step + V = 7 partial views) over env counts: one wave (131 072) up to many waves (1 M)."""
+    fm = golden("maze_gen64", "field_map")
+    for n in (131072, 524288, 1 << 20):
+        B = 3 if n >= 524288 else 8
+        envs = [mg.make_maze_vec(n, fm, seed=b, env_id_base=b * n) for b in range(B)]
+        acts = [torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+        for e in envs:
+            e.set_partial_obs(7)
+            e.reset()
+        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        report("map_kernel<maze> 64x64 fused step + V=7 partial obs (config 4)", n, us, 147 + 2 * (4 + 16) + 1 + 10, batches=B)
+        for e in envs:
+            e.close()
+        del envs
+        torch.cuda.empty_cache()
+
+
 def bench_view(args):
-    n = 65536
-    for env_id, V in (("multigrid-collect-respawn-clustered-v0", 7), ("multigrid-collect-rooms-respawn-v0", 5)):
-        B = 8
+    for env_id, V, n in (("multigrid-collect-respawn-clustered-v0", 7, 65536), ("multigrid-collect-rooms-respawn-v0", 5, 65536),
+                         ("multigrid-collect-respawn-clustered-v0", 7, 1 << 20)):
+        B = 8 if n <= 65536 else 2
         envs = [mg.make_vec(env_id, n, seed=b, env_id_base=b * n) for b in range(B)]
         for e in envs:
             e.reset()

@@ -29,6 +29,9 @@ def main():
         for V in (3, 5, 7, 4, 9):
             e.gen_obs(V, False); e.gen_obs(V, True, dirs=torch.randint(0, 4, (n, 2), generator=g, device=dev, dtype=torch.uint8))
         e.toroid_obs(); e.encode()
+        for ts in (32, 8, 5):
+            e.render(tile_size=ts); e.render(env_ids=[n - 1, 0, 7], tile_size=ts)
+        e.step_async(np.zeros((n, 2), np.int8)); e.step_wait()
         e.step(np.zeros((n, 2), np.int8))
         assert e.status() == 0
         e.close()
@@ -41,6 +44,10 @@ def main():
         for _ in range(45):
             e.step(torch.randint(0, 5, (n, nb), generator=g, device=dev, dtype=torch.int8))
         e.get_info()
+        e.render(tile_size=8); e.render(env_ids=[3, n - 1], tile_size=3)
+        red = e.set_red_actions(torch.randint(0, 5, (n, nr), generator=g, device=dev, dtype=torch.int8))
+        e.step(torch.randint(0, 5, (n, nb), generator=g, device=dev, dtype=torch.int8))
+        e.set_red_actions(None)
         assert e.status() == 0
         e.close()
     for stem in ("maze_board13", "maze_gen64"):
@@ -52,6 +59,7 @@ def main():
             for _ in range(35):
                 e.step(torch.randint(0, 5, (n,), generator=g, device=dev, dtype=torch.int8))
             e.gen_obs(7); e.gen_obs(6); e.get_info()
+            e.render(env_ids=[0, n - 1], tile_size=8); e.render(env_ids=[5], tile_size=7)
             if not ref:
                 e.set_partial_obs(5)
                 e.reset()
