@@ -177,18 +177,22 @@ def run_ours(args):
     #      independent, so the graph forks them over `--streams` streams: tiles of one launch load while tiles of
     #      another compute / drain (a single stream serialises whole launches, which leaves HBM idle during every
     #      launch's ramp-up and store drain; that figure is reported beside it as `single_stream`).
-    def capture(n_streams):
-        main = torch.cuda.Stream(device=dev)
+    def capture(n_streams, main=None, count=None):
+        """Graph of `count` (default B) launches, batch b on stream b % n_streams."""
+        count = B if count is None else count
+        fresh = main is None
+        main = main or torch.cuda.Stream(device=dev)
         side = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
         with torch.cuda.stream(main):
-            for i in range(Wm):
-                envs[i % B].step(acts[i % B])
+            if fresh:
+                for i in range(Wm):
+                    envs[i % B].step(acts[i % B])
             main.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=main):
                 for s_ in side:
                     s_.wait_stream(main)
-                for b in range(B):
+                for b in range(count):
                     st = main if b % n_streams == 0 else side[b % n_streams - 1]
                     with torch.cuda.stream(st):
                         envs[b].step(acts[b])
@@ -196,7 +200,8 @@ def run_ours(args):
                     main.wait_stream(s_)
         return main, g
 
-    def timed(main, g, reps, sample_clocks):
+    def timed(main, g, reps, sample_clocks, tail=None):
+        """`reps` replays of the B-launch graph (+ one replay of `tail`, the graph of the K % B remaining launches)."""
         with torch.cuda.stream(main):
             for _ in range(max(1, Wm // B)):
                 g.replay()
@@ -211,6 +216,8 @@ def run_ours(args):
             ev0.record(main)
             for _ in range(reps):
                 g.replay()
+            if tail is not None:
+                tail.replay()
             ev1.record(main)
             main.synchronize()
             torch.cuda.synchronize(dev)
@@ -219,14 +226,16 @@ def run_ours(args):
                 smp.join(timeout=2)
         return ev0.elapsed_time(ev1), smp
 
-    reps = max(1, (K + B - 1) // B)
-    K_eff = reps * B
+    reps, rem = divmod(max(1, K), B)     # EXACTLY K timed steps: `reps` full rotations over the B batches + K % B launches
+    K_eff = reps * B + rem
     S = max(1, min(args.streams, B))
     main1, graph1 = capture(1)
-    ms_single, _ = timed(main1, graph1, max(1, reps // 4), False)
-    single_us = ms_single * 1e3 / (max(1, reps // 4) * B)
+    reps1 = max(1, reps // 4)
+    ms_single, _ = timed(main1, graph1, reps1, False)
+    single_us = ms_single * 1e3 / (reps1 * B)
     mainS, graphS = (main1, graph1) if S == 1 else capture(S)
-    ms, sampler = timed(mainS, graphS, reps, True)
+    tailS = capture(S, main=mainS, count=rem)[1] if rem else None
+    ms, sampler = timed(mainS, graphS, reps, True, tail=tailS)
     status = max(e.status() for e in envs)
     assert status == 0, f"device status word {status}"
 
