@@ -192,7 +192,8 @@ def run_ours(args):
             with torch.cuda.graph(g, stream=main):
                 for s_ in side:
                     s_.wait_stream(main)
-                for b in range(count):
+                for i in range(count):
+                    b = i % B                      # launches i and i + B step the same env batch: same stream, in order
                     st = main if b % n_streams == 0 else side[b % n_streams - 1]
                     with torch.cuda.stream(st):
                         envs[b].step(acts[b])
@@ -200,11 +201,15 @@ def run_ours(args):
                     main.wait_stream(s_)
         return main, g
 
-    def timed(main, g, reps, sample_clocks, tail=None):
-        """`reps` replays of the B-launch graph (+ one replay of `tail`, the graph of the K % B remaining launches)."""
+    def timed(main, g, reps, sample_clocks, big=None, tail=None):
+        """Warm up with the B-launch graph `g`, then time `reps` replays of `big` (default `g`) + one replay of `tail`."""
+        big = big or g
         with torch.cuda.stream(main):
-            for _ in range(max(1, Wm // B)):
+            for _ in range(max(200, Wm // B)):     # untimed: the W warm-up steps and ~20 ms more, so a short timed region (small --steps) runs at settled clocks
                 g.replay()
+            for x in (big, tail):
+                if x is not None and x is not g:
+                    x.replay()                     # a graph's first launch uploads it: keep that out of the timed region
             main.synchronize()
             if world > 1:
                 dist.barrier()
@@ -215,7 +220,7 @@ def run_ours(args):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(main)
             for _ in range(reps):
-                g.replay()
+                big.replay()
             if tail is not None:
                 tail.replay()
             ev1.record(main)
@@ -226,16 +231,21 @@ def run_ours(args):
                 smp.join(timeout=2)
         return ev0.elapsed_time(ev1), smp
 
-    reps, rem = divmod(max(1, K), B)     # EXACTLY K timed steps: `reps` full rotations over the B batches + K % B launches
-    K_eff = reps * B + rem
+    # EXACTLY K timed steps.  The timed graphs hold up to CHUNK launches each (launch i steps env batch i % B on stream
+    # (i % B) % S, so launches of one batch stay in order on one stream and the S streams only join at the end of a graph):
+    # K // CHUNK replays of the CHUNK-launch graph + one graph of the K % CHUNK remaining launches.
+    CHUNK = 4096 - 4096 % B
+    K_eff = max(1, K)
+    reps, rem = divmod(K_eff, CHUNK)
     S = max(1, min(args.streams, B))
     main1, graph1 = capture(1)
-    reps1 = max(1, reps // 4)
-    ms_single, _ = timed(main1, graph1, reps1, False)
-    single_us = ms_single * 1e3 / (reps1 * B)
+    n1 = max(B, min(K_eff, 1024))
+    ms_single, _ = timed(main1, graph1, 1, False, big=capture(1, main=main1, count=n1)[1])
+    single_us = ms_single * 1e3 / n1
     mainS, graphS = (main1, graph1) if S == 1 else capture(S)
+    bigS = capture(S, main=mainS, count=CHUNK)[1] if reps else None
     tailS = capture(S, main=mainS, count=rem)[1] if rem else None
-    ms, sampler = timed(mainS, graphS, reps, True, tail=tailS)
+    ms, sampler = timed(mainS, graphS, reps, True, big=bigS, tail=tailS)
     status = max(e.status() for e in envs)
     assert status == 0, f"device status word {status}"
 
@@ -323,12 +333,17 @@ def run_ours(args):
                        "num_envs_per_gpu_per_launch": n, "env_batches_per_gpu": B,
                        "l2": f"inputs larger than L2: timed loop rotates over {B} independent env batches "
                              f"({B * n * (ALGO_BYTES_PER_ENV_STEP + 8) / 1e6:.0f} MB working set > 126 MB L2)",
-                       "launch": f"CUDA graph of one fused step+encode kernel per batch, the {B} independent batches forked over {S} streams",
+                       "launch": f"CUDA graphs of up to {CHUNK} launches of the fused step+encode kernel (one launch = one env batch), "
+                                 f"the {B} independent batches forked over {S} streams",
                        "streams": S},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "collect_step_kernel",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
-                         "avg_launch_us": launch_s * 1e6},
+                         "avg_launch_us": launch_s * 1e6,
+                         "traffic_frac": (ncu_traffic() / launch_s / 1e9 / peak) if (ncu_traffic() and n == 65536) else None,
+                         "note": "achieved = SURVEY 8(d)'s 592 algorithmic B/env-step x envs per launch / average launch time; the packed "
+                                 "layout moves fewer bytes than that count (traffic = DRAM bytes per launch from the committed ncu capture), "
+                                 "so frac can exceed 1 while traffic_frac = traffic / launch time / peak stays below it"},
             "single_stream": {"avg_launch_us": single_us, "value": n / single_us * 1e6,
                               "achieved": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3, "frac": ALGO_BYTES_PER_ENV_STEP * n / single_us / 1e3 / peak,
                               "note": "same graph on ONE stream (launches serialised by programmatic dependent launch)"},
