@@ -35,6 +35,8 @@ int map_tma_reps(int L, int cells, int obs_dtype);
 size_t map_view_smem_bytes(int padded_bytes, int V);
 cudaError_t configure_map_view_mode(size_t smem);
 cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st);
+cudaError_t launch_ctf_flat(const MapParams& p, const long long* tmpl, int L, long long* out, cudaStream_t st);
+int ctf_flat_tile_envs(int L);
 int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
@@ -71,6 +73,8 @@ struct mg_env {
   mg_generic_config gcfg;
   mg::GenericParams gbase;
   mg_map_trace mtrace;
+  std::vector<long long> flat_tmpl;        // CtF: static entries of the "flattened" observation (ctf.py:1084-1104), per-env slots 0
+  long long* d_flat_tmpl;                  // ... uploaded on first use
   std::vector<std::pair<int, uint8_t*>> atlases;    // render: (tile_size, device atlas) built on first use, freed by mg_destroy
   const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
@@ -240,6 +244,7 @@ extern "C" int mg_destroy(mg_env* env) {
   cudaFree(env->d_wall_template);
   cudaFree(env->d_map_tables);
   for (auto& a : env->atlases) cudaFree(a.second);
+  cudaFree(env->d_flat_tmpl);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);   // rewards / term / trunc live inside the d_obs block
   delete env;
   return 0;
@@ -339,6 +344,16 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   env->family = cfg->family;
   env->map_codes_off = 0;
   env->mcfg = *cfg; env->mcfg.field_map = nullptr;
+  if (!maze) {   // blue agent pairs | red agent pairs | blue flag | red flag | blue_territory | red_territory | obstacle | terminated
+    std::vector<long long>& t = env->flat_tmpl;
+    t.assign((size_t)2 * n, 0);
+    auto xy = [&](int c) { t.push_back(c / S); t.push_back(c % S); };
+    xy(blue_flag); xy(red_flag);
+    for (const std::string* v : {&bt, &rt})
+      for (size_t k = 0; k + 1 < v->size(); k += 2) { t.push_back((unsigned char)(*v)[k]); t.push_back((unsigned char)(*v)[k + 1]); }
+    for (int i = 0; i < cells; ++i) if (cfg->field_map[i] == 6) xy(i);
+    t.resize(t.size() + (size_t)n, 0);
+  }
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;
   env->d_final = nullptr; env->d_wall_template = nullptr; env->d_status = nullptr; env->d_map_tables = nullptr;
@@ -528,6 +543,33 @@ extern "C" int mg_map_info(mg_env* env, const void* state, double* out, void* st
   p.agents = const_cast<uint8_t*>(static_cast<const uint8_t*>(state)) + env->plane_off[MG_MAP_PLANE_AGENTS];
   p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
   if ((ce = mg::launch_map_info(p, out, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "map_info_kernel", ce);
+  env->launches += 1;
+  return 0;
+}
+
+// length of the "flattened" observation: 3 n + 4 + 2 (|blue_territory| + |red_territory| + |obstacle|), territories include their flag cell
+extern "C" int mg_ctf_flat_len(const mg_env* env) {
+  if (!env || env->family != MG_FAMILY_CTF) return -1;
+  return (int)env->flat_tmpl.size();
+}
+
+extern "C" int mg_ctf_flat_obs(mg_env* env, const void* state, int64_t* out, void* stream) {
+  if (!env || !state || !out) return fail(env, "mg_ctf_flat_obs: null argument");
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_ctf_flat_obs: CtF family only");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  const int L = (int)env->flat_tmpl.size();
+  if (mg::ctf_flat_tile_envs(L) < 2) return fail(env, "mg_ctf_flat_obs: the map's cell lists are too long for the kernel's shared-memory tile");
+  if (!env->d_flat_tmpl) {
+    if ((ce = cudaMalloc(&env->d_flat_tmpl, (size_t)L * sizeof(long long))) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMemcpy(env->d_flat_tmpl, env->flat_tmpl.data(), (size_t)L * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return cuda_fail(env, "template upload", ce);
+  }
+  mg::MapParams p = env->mbase;
+  p.agents = const_cast<uint8_t*>(static_cast<const uint8_t*>(state)) + env->plane_off[MG_MAP_PLANE_AGENTS];
+  p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
+  if ((ce = mg::launch_ctf_flat(p, env->d_flat_tmpl, L, reinterpret_cast<long long*>(out), static_cast<cudaStream_t>(stream))) != cudaSuccess)
+    return cuda_fail(env, "ctf_flat_kernel", ce);
   env->launches += 1;
   return 0;
 }

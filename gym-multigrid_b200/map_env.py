@@ -361,21 +361,28 @@ class CtfVecEnv(_MapVecEnv):
         return {"blue_agent_defeated": bits[:, :self.num_blue].bool(), "red_agent_defeated": bits[:, self.num_blue:].bool(),
                 "blue_flag_captured": (st & 1).bool(), "red_flag_captured": ((st >> 1) & 1).bool()}
 
-    def positional_obs(self):
-        """observation_option="positional" (ctf.py:1112-1135) as batched int64 CUDA tensors."""
-        N, nb = self.num_envs, self.num_blue
-        pos = self.agent_pos.to(torch.int64)
-        st = lambda x: torch.as_tensor(np.array(x).flatten(), device=self.device).expand(N, -1)  # noqa: E731
-        return {"blue_agent": pos[:, :nb].reshape(N, -1), "red_agent": pos[:, nb:].reshape(N, -1),
-                "blue_flag": st(self.blue_flag), "red_flag": st(self.red_flag), "blue_territory": st(self.blue_territory),
-                "red_territory": st(self.red_territory), "obstacle": st(self.obstacle),
-                "terminated_agents": self.agent_terminated.to(torch.int64)}
+    def flattened_obs(self, out=None):
+        """observation_option="flattened" (ctf.py:1084-1104) of every env: int64 CUDA tensor [N, L], one kernel (mg_ctf_flat_obs)."""
+        L = self._lib.mg_ctf_flat_len(self._h)
+        if out is None:
+            out = torch.empty((self.num_envs, L), dtype=torch.int64, device=self.device)
+        self._check(self._lib.mg_ctf_flat_obs(self._h, _ptr(self.state), _ptr(out), self._stream()))
+        return out
 
-    def flattened_obs(self):
-        """observation_option="flattened" (ctf.py:1084-1104)."""
-        d = self.positional_obs()
-        return torch.cat([d["blue_agent"], d["red_agent"], d["blue_flag"], d["red_flag"], d["blue_territory"], d["red_territory"],
-                          d["obstacle"], d["terminated_agents"]], dim=1)
+    def positional_obs(self):
+        """observation_option="positional" (ctf.py:1112-1135) as batched int64 CUDA tensors: the flattened vector cut at the
+        key boundaries (views of one buffer)."""
+        f = self.flattened_obs()
+        n, nb = self.num_blue + self.num_red, self.num_blue
+        sizes = [("blue_agent", 2 * nb), ("red_agent", 2 * (n - nb)), ("blue_flag", 2), ("red_flag", 2),
+                 ("blue_territory", 2 * len(self.blue_territory)), ("red_territory", 2 * len(self.red_territory)),
+                 ("obstacle", 2 * len(self.obstacle)), ("terminated_agents", n)]
+        out, k = {}, 0
+        for key, w in sizes:
+            out[key] = f[:, k:k + w]
+            k += w
+        assert k == f.shape[1]
+        return out
 
 
 class Ctf1v1VecEnv(CtfVecEnv):

@@ -247,6 +247,14 @@ int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
  * device (default).  Shuffle order and battle outcomes stay with the env's Philox stream. */
 int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev);
 
+/* CtF handles: `_get_obs()` with observation_option="flattened" (ctf.py:1084-1104; what the reference's RL script trains on,
+ * scripts/main_mvn_ctf_rl.py:15-21) for every env: out int64 [N][L] on the device, L = mg_ctf_flat_len() =
+ * 3 n + 4 + 2 (|blue_territory| + |red_territory| + |obstacle|): blue agent (x, y) pairs, red agent pairs, blue flag, red flag,
+ * the three cell lists in the reference's order, int(agent.terminated) per agent.  The "positional" dict (ctf.py:1112-1135) is
+ * the same vector cut at the key boundaries. */
+int mg_ctf_flat_len(const mg_env* env);
+int mg_ctf_flat_obs(mg_env* env, const void* state_dev, int64_t* out_dev, void* stream);
+
 /* Maze handles: observation mode of mg_reset / mg_step / mg_step_host.  view_size 0 (default) = the "map" observation;
  * 3 / 5 / 7 = MultiGridEnv.gen_obs partial views u8 [N][1][V][V][3] computed by the SAME launch that steps the envs
  * (BASELINE config 4; same cells as mg_gen_obs would return after the step).  final_obs is not available in this mode. */

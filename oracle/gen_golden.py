@@ -184,6 +184,28 @@ def gen_ctf_render():
               f"bg != team colour on {int((out['bg'] != out['init_bg'][:, None]).sum())} agent-steps, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_ctf_flat():
+    """observation_option="flattened" (ctf.py:1084-1104) - what the reference's own RL script feeds its policy
+    (scripts/main_mvn_ctf_rl.py:15-21): the replay inputs of gen_ctf with the flattened int64 vectors as `obs`."""
+    for stem, nb, nr, episodes in (("ctf_2v2_flat", 2, 2, 6), ("ctf_3v4_flat", 3, 4, 3)):
+        eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, np.random.default_rng(3700 + seed), nb, nr, 0.0, observation_option="flattened")
+               for seed in range(episodes)]
+        for e in eps:
+            assert e["obs"].dtype == np.int64 and e["obs"].ndim == 2 and e["init_obs"].dtype == np.int64
+            assert e["obs"].max() < 256 and e["obs"].min() >= 0
+            e["obs"] = e["obs"].astype(np.uint8)            # stored compactly; the reference's dtype is int64 (meta_ref_obs_dtype)
+            e["init_obs"] = e["init_obs"].astype(np.uint8)
+        out = rh.pack_episodes(eps, ["actions", "red_actions", "order", "n_battles", "blue_win", "obs", "pos", "dead"],
+                               ["field_map", "init_obs", "init_pos", "blue_place", "red_place"])
+        out["field_map"] = out["field_map"][0].astype(np.uint8)
+        out["meta_num_blue"], out["meta_num_red"] = np.array(nb), np.array(nr)
+        out["meta_obstacle_penalty_ratio"] = np.array(0.0)
+        out["meta_ref_obs_dtype"] = np.array("int64")
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, flattened length {out['obs'].shape[-1]}, {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 def gen_ctf1v1():
     eps = [rh.record_ctf_1v1_episode(CTF_MAP, seed, np.random.default_rng(4000 + seed)) for seed in range(40)]
     for e in eps:
@@ -265,7 +287,7 @@ def gen_generic():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -278,6 +300,8 @@ if __name__ == "__main__":
         gen_partial()
     if "toroid" in which:
         gen_toroid()
+    if "ctf_flat" in which:
+        gen_ctf_flat()
     if "render" in which:
         gen_render()
         gen_maze_render()

@@ -172,6 +172,8 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
 
 /* _get_info of the map families: Maze [N][2] (d_a_f, d_a_ob), CtF [N][11] (ctf.py:1165-1182 key order) */
 int oc_map_info(const oc_map_cfg* c, int is_maze, int64_t N, const oc_map_state* st, double* out);
+/* observation_option="flattened" (ctf.py:1084-1104): int64 [N][L]; out NULL = only return L */
+int oc_ctf_flattened(const oc_map_cfg* c, int64_t N, const oc_map_state* st, int64_t* out);
 
 #define OC_ERR_BAD_ACTION 8 /* action outside the env's action set (reference: ValueError, maze.py:286, ctf.py:1200) */
 

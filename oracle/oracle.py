@@ -373,6 +373,14 @@ class CtfOracle(_MapOracle):
     def step(self, blue_actions, rng, autoreset=False, want_final_obs=False):
         return self._call_step(lib().oc_ctf_step, np.asarray(blue_actions).reshape(self.N, self.nb), rng, autoreset, want_final_obs)
 
+    def flattened(self):
+        """observation_option="flattened" (ctf.py:1084-1104) of the current state: int64 [N, L]."""
+        st = self._state()
+        L = lib().oc_ctf_flattened(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), None)
+        out = np.zeros((self.N, L), np.int64)
+        lib().oc_ctf_flattened(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), _p(out))
+        return out
+
 
 def partial_view3(grid, pos, W, H, V, see_through_walls=False, dirs=None, oob_code=1 | 7 << 2, opaque_rule=0):
     """MultiGridEnv.gen_obs for packed Collect grids [N, W*H] and agent positions [N, A, 2] -> [N, A, V, V, 3]."""

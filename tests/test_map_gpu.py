@@ -347,3 +347,53 @@ def test_ctf_external_enemy_policy(cuda_device):
     oo, orew, *_ = o.step(np.zeros((n, nb), np.int8), oc.map_rng(mode=1, seed=9), autoreset=True)
     assert np.array_equal(_np(obs), oo) and env.status() == 0
     env.close()
+
+
+@pytest.mark.parametrize("stem", ["ctf_2v2_flat", "ctf_3v4_flat"])
+def test_ctf_flattened_obs_matches_reference(stem, cuda_device):
+    """observation_option="flattened" (ctf.py:1084-1104; the option scripts/main_mvn_ctf_rl.py trains on) recorded from the
+    reference, replayed through the CUDA step (trace mode) + mg_ctf_flat_obs, tiled over ragged tiles."""
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    k = 7
+    env = mg.make_ctf_vec(E * k, g["field_map"], num_blue_agents=nb, num_red_agents=nr, autoreset=False)
+    env.set_trace(blue_place=_tile(g["blue_place"], k), red_place=_tile(g["red_place"], k))
+    env.reset()
+    f = env.flattened_obs()
+    assert f.dtype == torch.int64 and np.array_equal(_np(f), _tile(g["init_obs"], k))
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    for t in range(T):
+        lv = g["length"] > t
+        live = _tile(lv, k)
+        env.set_trace(red_actions=_tile(g["red_actions"][:, t], k), order=_tile(np.where(lv[:, None], g["order"][:, t], ident), k),
+                      blue_win=_tile(g["blue_win"][:, t], k))
+        env.step(torch.as_tensor(_tile(np.where(lv[:, None], g["actions"][:, t], 0), k).astype(np.int8), device=cuda_device))
+        assert np.array_equal(_np(env.flattened_obs())[live], _tile(g["obs"][:, t], k)[live]), f"step {t}"
+    d = env.positional_obs()
+    assert list(d) == ["blue_agent", "red_agent", "blue_flag", "red_flag", "blue_territory", "red_territory", "obstacle", "terminated_agents"]
+    assert np.array_equal(_np(d["blue_agent"]).reshape(-1, nb, 2), _np(env.agent_pos)[:, :nb])
+    assert np.array_equal(_np(d["terminated_agents"]).astype(bool), _np(env.agent_terminated))
+    assert env.status() == 0
+    env.close()
+
+
+def test_ctf_flattened_obs_vs_oracle_philox(cuda_device):
+    """Philox mode with autoreset, a ragged env count and an output pointer that is only 8-byte aligned (plain-store path)."""
+    import gym_multigrid_b200 as mg
+    fm = load_golden("ctf_2v2")["field_map"]
+    n = 1003
+    env = mg.make_ctf_vec(n, fm, max_steps=25, seed=31)
+    o = oc.CtfOracle(fm, n, 2, 2, max_steps=25)
+    env.reset(); o.reset(oc.map_rng(mode=1, seed=31))
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    buf = torch.zeros(n * 216 + 1, dtype=torch.int64, device=cuda_device)
+    for t in range(40):
+        act = torch.randint(0, 5, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8)
+        env.step(act); o.step(_np(act), oc.map_rng(mode=1, seed=31), autoreset=True)
+        want = o.flattened()
+        assert np.array_equal(_np(env.flattened_obs()), want), f"step {t}"
+        if t % 10 == 0:
+            assert np.array_equal(_np(env.flattened_obs(out=buf[1:].view(n, 216))), want)
+    env.close()

@@ -94,3 +94,22 @@ def test_ctf1v1_matches_reference():
         assert np.array_equal(o.info()[live], g["info"][live, t])
         gf, gd = o.game_stats()
         assert np.array_equal(gf[live], g["stats_flags"][live, t]) and np.array_equal(gd[live], g["stats_defeated"][live, t])
+
+
+@pytest.mark.parametrize("stem", ["ctf_2v2_flat", "ctf_3v4_flat"])
+def test_ctf_flattened_obs_matches_reference(stem):
+    """observation_option="flattened" (ctf.py:1084-1104), the option the reference's RL script uses: every step of every episode."""
+    g = load_golden(stem)
+    E, T, nb = g["actions"].shape
+    nr = int(g["meta_num_red"])
+    o = oc.CtfOracle(g["field_map"], E, nb, nr)
+    o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
+    f = o.flattened()
+    assert f.dtype == np.int64 and np.array_equal(f, g["init_obs"])
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    for t in range(T):
+        live = g["length"] > t
+        o.step(np.where(live[:, None], g["actions"][:, t], 0),
+               oc.map_rng(mode=0, red_actions=g["red_actions"][:, t], order=np.where(live[:, None], g["order"][:, t], ident), blue_win=g["blue_win"][:, t]))
+        assert np.array_equal(o.flattened()[live], g["obs"][live, t]), f"step {t}"
+    assert o.status.value == 0

@@ -92,6 +92,13 @@ def bench_ctf(args):
         report(f"map_kernel<ctf> {nb}v{nr} 10x10 map obs u8", n, us, bpe, batches=B)
         for e in envs:
             e.close()
+    n = 262144
+    e = mg.make_ctf_vec(n, fm, seed=0)
+    e.reset()
+    outs = [torch.empty((n, 216), dtype=torch.int64, device="cuda:0") for _ in range(2)]
+    us = graph_time([lambda o=o: e.flattened_obs(out=o) for o in outs], args.reps)
+    report("ctf_flat_kernel 2v2 flattened obs int64 [216]", n, us, 216 * 8 + 16, batches=2)
+    e.close()
     n = 65536
     envs = [mg.make_ctf_vec(n, fm, reference_dtypes=True, seed=b, env_id_base=b * n) for b in range(8)]
     acts = [torch.randint(0, 5, (n, 2), device="cuda:0", dtype=torch.int8) for _ in range(8)]

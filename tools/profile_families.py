@@ -47,6 +47,11 @@ def main():
         e = mg.make_wildfire_vec(n, size=64, num_agents=16)
         a = torch.randint(0, 5, (n, 16), device=dev, dtype=torch.int8)
         f = lambda: e.step(a)  # noqa: E731
+    elif fam == "render":
+        n = n or 1024
+        e = mg.make_vec("multigrid-collect-respawn-clustered-v0", n)
+        out = torch.empty((n, 320, 320, 3), dtype=torch.uint8, device=dev)
+        f = lambda: e.render(tile_size=32, out=out)  # noqa: E731
     elif fam == "generic":
         n = n or 65536
         g = {k: golden("generic_12x12_a5", k) for k in ("init_obs", "init_pos")}
