@@ -54,14 +54,21 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
-
-    def run(self):
-        try:
+        self.index, self.stop_flag, self.active, self.sm, self.reasons, self.max_mhz = index, False, False, [], set(), None
+        self.nv = self.h = None
+        try:    # NVML is initialised HERE (caller's thread, before the timed region): the thread only polls
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        nv, h = self.nv, self.h
+        if nv is None:
+            return
+        try:
             names = {
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
                 getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
@@ -71,12 +78,13 @@ class ClockSampler(threading.Thread):
             }
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = get_reasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.002)
+                if self.active:     # samples are kept only while the timed region runs
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = get_reasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.001)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -204,6 +212,9 @@ def run_ours(args):
     def timed(main, g, reps, sample_clocks, big=None, tail=None):
         """Warm up with the B-launch graph `g`, then time `reps` replays of `big` (default `g`) + one replay of `tail`."""
         big = big or g
+        smp = ClockSampler(local_rank) if sample_clocks else None
+        if smp:
+            smp.start()         # polling thread up and NVML initialised before the warm-up; it records only while `active`
         with torch.cuda.stream(main):
             for _ in range(max(200, Wm // B)):     # untimed: the W warm-up steps and ~20 ms more, so a short timed region (small --steps) runs at settled clocks
                 g.replay()
@@ -214,10 +225,9 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize(dev)
-            smp = ClockSampler(local_rank) if sample_clocks else None
-            if smp:
-                smp.start()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if smp:
+                smp.active = True
             ev0.record(main)
             for _ in range(reps):
                 big.replay()
@@ -227,6 +237,7 @@ def run_ours(args):
             main.synchronize()
             torch.cuda.synchronize(dev)
             if smp:
+                smp.active = False
                 smp.stop_flag = True
                 smp.join(timeout=2)
         return ev0.elapsed_time(ev1), smp
