@@ -667,7 +667,8 @@ __global__ void __launch_bounds__(kFlatThreads) ctf_flat_kernel(const __grid_con
     const int r = t / n, i = t - r * n;
     const uint32_t w = *reinterpret_cast<const uint32_t*>(p.agents + (e0 + r) * p.row_bytes + 4 * i);
     s[r * L + 2 * i] = ag_x(w); s[r * L + 2 * i + 1] = ag_y(w);
-    s[r * L + L - n + i] = (w & FL_DEAD) ? 1 : 0;
+    if (!p.variant_1v1) s[r * L + L - n + i] = (w & FL_DEAD) ? 1 : 0;
+    else if (i == 1) s[r * L + L - 1] = (w & FL_DEAD) ? 1 : 0;   // Ctf1v1Env: the tail is int(_is_red_agent_defeated) alone (ctf.py:359-371)
   }
   fence_proxy_async_smem();
   __syncthreads();

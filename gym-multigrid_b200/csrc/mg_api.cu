@@ -352,7 +352,7 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
     for (const std::string* v : {&bt, &rt})
       for (size_t k = 0; k + 1 < v->size(); k += 2) { t.push_back((unsigned char)(*v)[k]); t.push_back((unsigned char)(*v)[k + 1]); }
     for (int i = 0; i < cells; ++i) if (cfg->field_map[i] == 6) xy(i);
-    t.resize(t.size() + (size_t)n, 0);
+    t.resize(t.size() + (size_t)(cfg->variant_1v1 ? 1 : n), 0);   // terminated per agent; Ctf1v1Env: is_red_agent_defeated alone (ctf.py:359-371)
   }
   env->device = device; env->tile = 0; env->has_trace = false; env->launches = 0; env->timeline = nullptr;
   env->d_actions = nullptr; env->d_obs = nullptr; env->d_rewards = nullptr; env->d_term = nullptr; env->d_trunc = nullptr;

@@ -61,6 +61,7 @@ class _MapVecEnv(VectorEnvSurface):
         cfg.max_steps, cfg.autoreset = self.max_steps, int(self.autoreset)
         cfg.obs_dtype = _lib.OBS_REFERENCE if self.reference_dtypes else _lib.OBS_U8
         cfg.variant_1v1 = int(bool(variant_1v1))
+        self._variant_1v1 = bool(variant_1v1)
         cfg.seed = int(seed) & (2**64 - 1)
         h = C.c_void_p()
         if self._lib.mg_create_map(C.byref(cfg), idx, C.byref(h)) != 0:
@@ -88,6 +89,7 @@ class _MapVecEnv(VectorEnvSurface):
         self._io = _lib.StepIO()
         self._bound = None
         self._red_actions = None
+        self._skip_map_obs = False   # CtF "flattened" / "positional" modes: the step does not write the map observation
         self._host = None
         self.with_info = False      # True: step() / reset() also return the reference's info dict (one more launch)
         self._trace_keepalive = None
@@ -128,7 +130,7 @@ class _MapVecEnv(VectorEnvSurface):
 
     def reset(self, *, seed=None, options=None, mask=None):
         m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-        self._check(self._lib.mg_reset(self._h, _ptr(self.state), _ptr(m), _ptr(self._obs), self._stream()))
+        self._check(self._lib.mg_reset(self._h, _ptr(self.state), _ptr(m), None if self._skip_map_obs else _ptr(self._obs), self._stream()))
         return self._obs, (self.get_info() if self.with_info else {})
 
     def _prep_actions(self, actions):
@@ -150,7 +152,7 @@ class _MapVecEnv(VectorEnvSurface):
         bound = self._bound
         if bound is None or bound[0] is not self._obs or bound[1] is not self._final_obs:   # (re)bind what does not change per call
             io = self._io
-            io.obs, io.rewards = self._obs.data_ptr(), self._rewards.data_ptr()
+            io.obs, io.rewards = (None if self._skip_map_obs else self._obs.data_ptr()), self._rewards.data_ptr()
             io.terminated, io.truncated = self._term.data_ptr(), self._trunc.data_ptr()
             io.final_obs = self._final_obs.data_ptr() if self._final_obs is not None else None
             bound = self._bound = (self._obs, self._final_obs, C.byref(io), _ptr(self.state), self._term.view(torch.bool),
@@ -321,8 +323,9 @@ class CtfVecEnv(_MapVecEnv):
                  battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
                  observation_option="map", observation_scaling=1, device="cuda:0", seed=0, autoreset=True, env_id_base=0,
                  reference_dtypes=False, variant_1v1=False):
-        if observation_option != "map":
-            raise NotImplementedError('the device writes observation_option="map"; use positional_obs()/flattened_obs() for the others')
+        if observation_option not in ("map", "flattened", "positional"):
+            raise ValueError(f"Invalid observation_option: {observation_option}")     # ctf.py:1105-1108
+        self.observation_option = observation_option
         fm = load_text_map(map_path)
         fr = flag_reward
         self._create(num_envs, fm, num_blue_agents, num_red_agents, float(fr), float(battle_reward_ratio * fr),
@@ -339,6 +342,31 @@ class CtfVecEnv(_MapVecEnv):
         self.obstacle, self.blue_flag, self.red_flag = cells(6), cells(4)[0], cells(5)[0]
         self.blue_territory = cells(0) + [self.blue_flag]
         self.red_territory = cells(1) + [self.red_flag]
+        if observation_option != "map":   # reset / step return the flattened vector (or its dict of views): step launch + ctf_flat_kernel
+            L = self._lib.mg_ctf_flat_len(self._h)
+            self._flat = torch.zeros((self.num_envs, L), dtype=torch.int64, device=self.device)
+            self._skip_map_obs = True
+            if observation_option == "flattened":                                # ctf.py:940-948
+                self.single_observation_space = Box(0, max(self.size - 1, 1), (L,), np.int64)
+                self.observation_space = Box(0, max(self.size - 1, 1), (self.num_envs, L), np.int64)
+
+    def _option_obs(self):
+        if self.observation_option == "map":
+            return self._obs
+        self.flattened_obs(out=self._flat)
+        return self._flat if self.observation_option == "flattened" else self._positional_views(self._flat)
+
+    def reset(self, *, seed=None, options=None, mask=None):
+        _, info = super().reset(seed=seed, options=options, mask=mask)
+        return self._option_obs(), info
+
+    def step(self, actions):
+        out = super().step(actions)
+        if self.observation_option == "map":
+            return out
+        if isinstance(out[0], np.ndarray):
+            raise NotImplementedError('host-array steps return observation_option="map" only; pass CUDA tensors')
+        return (self._option_obs(),) + tuple(out[1:])
 
     def set_red_actions(self, red_actions=None):
         """Drive the red agents from outside (the reference's `enemy_policies`, ctf.py:666): `red_actions` int8 CUDA tensor
@@ -372,11 +400,14 @@ class CtfVecEnv(_MapVecEnv):
     def positional_obs(self):
         """observation_option="positional" (ctf.py:1112-1135) as batched int64 CUDA tensors: the flattened vector cut at the
         key boundaries (views of one buffer)."""
-        f = self.flattened_obs()
+        return self._positional_views(self.flattened_obs())
+
+    def _positional_views(self, f):
         n, nb = self.num_blue + self.num_red, self.num_blue
         sizes = [("blue_agent", 2 * nb), ("red_agent", 2 * (n - nb)), ("blue_flag", 2), ("red_flag", 2),
                  ("blue_territory", 2 * len(self.blue_territory)), ("red_territory", 2 * len(self.red_territory)),
-                 ("obstacle", 2 * len(self.obstacle)), ("terminated_agents", n)]
+                 ("obstacle", 2 * len(self.obstacle)),
+                 ("is_red_agent_defeated", 1) if self._variant_1v1 else ("terminated_agents", n)]   # ctf.py:378-396 vs :1112-1135
         out, k = {}, 0
         for key, w in sizes:
             out[key] = f[:, k:k + w]

@@ -104,7 +104,10 @@ class CtFMvNEnv(_SingleMapEnv):
             return map_obs[0].cpu().numpy()
         if self.observation_option == "flattened":
             return self.vec.flattened_obs()[0].cpu().numpy()
-        return {k: v[0].cpu().numpy() for k, v in self.vec.positional_obs().items()}
+        d = {k: v[0].cpu().numpy() for k, v in self.vec.positional_obs().items()}
+        if "is_red_agent_defeated" in d:      # Ctf1v1Env returns a plain int there (ctf.py:395)
+            d["is_red_agent_defeated"] = int(d["is_red_agent_defeated"][0])
+        return d
 
     def reset(self, *, seed=None, options=None):
         obs, _ = self.vec.reset()

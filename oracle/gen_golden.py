@@ -204,6 +204,19 @@ def gen_ctf_flat():
         path_out = os.path.join(OUT, stem + ".npz")
         np.savez_compressed(path_out, **out)
         print(f"{stem}: {episodes} episodes, steps={int(out['length'].sum())}, flattened length {out['obs'].shape[-1]}, {os.path.getsize(path_out)/1024:.0f} KiB")
+    # Ctf1v1Env (ctf.py:359-371): same layout, but the tail is the single `is_red_agent_defeated` flag
+    eps = [rh.record_ctf_1v1_episode(CTF_MAP, seed, np.random.default_rng(3800 + seed), observation_option="flattened") for seed in range(8)]
+    for e in eps:
+        assert e["obs"].dtype == np.int64 and e["obs"].max() < 256
+        e["obs"] = e["obs"].astype(np.uint8)
+        e["init_obs"] = e["init_obs"].astype(np.uint8)
+    out = rh.pack_episodes(eps, ["actions", "red_actions", "n_battles", "blue_win", "obs", "pos", "dead"],
+                           ["field_map", "init_obs", "init_pos", "blue_place", "red_place"])
+    out["field_map"] = out["field_map"][0].astype(np.uint8)
+    path_out = os.path.join(OUT, "ctf1v1_flat.npz")
+    np.savez_compressed(path_out, **out)
+    print(f"ctf1v1_flat: {len(eps)} episodes, steps={int(out['length'].sum())}, flattened length {out['obs'].shape[-1]}, "
+          f"red defeated on {int(out['dead'][..., 1].sum())} steps, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
 def gen_ctf1v1():

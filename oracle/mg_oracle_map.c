@@ -319,11 +319,12 @@ int oc_map_info(const oc_map_cfg* c, int is_maze, int64_t N, const oc_map_state*
 /* CtFMvNEnv._get_obs, observation_option="flattened" (ctf.py:1084-1104; the dict of :1112-1135 concatenated in key order):
  * blue agent (x, y) pairs, red agent pairs, blue flag, red flag, blue_territory pairs (np.where order, then the blue flag,
  * ctf.py:765-769), red_territory pairs (+ red flag), obstacle pairs, int(agent.terminated) per agent.  out int64 [N][L];
- * returns L = 3 n + 4 + 2 (|blue_territory| + |red_territory| + |obstacle|). */
+ * returns L = 3 n + 4 + 2 (|blue_territory| + |red_territory| + |obstacle|) (1v1: 2 n + 1 + ...). */
 int oc_ctf_flattened(const oc_map_cfg* c, int64_t N, const oc_map_state* st, int64_t* out) {
   const int S = c->size, n = c->num_blue + c->num_red;
   const int nbt = count_cells(c, CT_BLUE_TERR) + 1, nrt = count_cells(c, CT_RED_TERR) + 1, nob = count_cells(c, CT_OBSTACLE);
-  const int L = 3 * n + 4 + 2 * (nbt + nrt + nob);
+  const int tail = c->variant_1v1 ? 1 : n; /* Ctf1v1Env ends with int(self._is_red_agent_defeated) alone (ctf.py:359-371) */
+  const int L = 2 * n + tail + 4 + 2 * (nbt + nrt + nob);
   if (!out) return L;
   for (int64_t e = 0; e < N; ++e) {
     int64_t* o = out + e * L;
@@ -334,7 +335,7 @@ int oc_ctf_flattened(const oc_map_cfg* c, int64_t N, const oc_map_state* st, int
     for (int i = 0; i < nbt; ++i) { const int cell = terr_cell(c, 1, i); o[k++] = cell / S; o[k++] = cell % S; }
     for (int i = 0; i < nrt; ++i) { const int cell = terr_cell(c, 0, i); o[k++] = cell / S; o[k++] = cell % S; }
     for (int i = 0; i < nob; ++i) { const int cell = nth_cell(c, CT_OBSTACLE, i); o[k++] = cell / S; o[k++] = cell % S; }
-    for (int i = 0; i < n; ++i) o[k++] = st->flags[e * n + i] & 1;
+    for (int i = n - tail; i < n; ++i) o[k++] = st->flags[e * n + i] & 1;
   }
   return L;
 }

@@ -537,13 +537,13 @@ def record_toroid(env_id, seed, n_samples):
     return {k: np.array(v) for k, v in out.items()}
 
 
-def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battles=4):
-    """One episode of the reference Ctf1v1Env (ctf.py:50-654), "map" observations, fresh instance."""
+def record_ctf_1v1_episode(map_path, seed, action_rng, max_steps=100, max_battles=4, observation_option="map"):
+    """One episode of the reference Ctf1v1Env (ctf.py:50-654), "map" (or "flattened") observations, fresh instance."""
     import_reference()
     with tapped_generators(unseeded_entropy=880000 + seed) as log:
         from gym_multigrid.envs.ctf import Ctf1v1Env
         from gym_multigrid.policy.ctf.heuristic import RwPolicy
-        env = Ctf1v1Env(map_path, enemy_policy=RwPolicy(), max_steps=max_steps, observation_option="map")
+        env = Ctf1v1Env(map_path, enemy_policy=RwPolicy(), max_steps=max_steps, observation_option=observation_option)
         obs0, info0 = env.reset(seed=seed)
         place = [ev[1] for ev in log if ev[0] == "integers"]      # ctf.py:317, :322
         assert len(place) == 2

@@ -397,3 +397,38 @@ def test_ctf_flattened_obs_vs_oracle_philox(cuda_device):
         if t % 10 == 0:
             assert np.array_equal(_np(env.flattened_obs(out=buf[1:].view(n, 216))), want)
     env.close()
+
+
+def test_ctf_observation_option_in_step_and_1v1_layout(cuda_device):
+    """`observation_option="flattened" / "positional"` as constructor option: reset / step return that observation (the map
+    observation is not written); Ctf1v1Env's layout ends with is_red_agent_defeated alone.  Reference episodes replayed."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf1v1_flat")
+    E, T, _ = g["actions"].shape
+    env = mg.make_ctf1v1_vec(E, g["field_map"], autoreset=False, observation_option="flattened")
+    assert env.single_observation_space.shape == (g["obs"].shape[-1],)
+    env.set_trace(blue_place=g["blue_place"], red_place=g["red_place"])
+    obs, _ = env.reset()
+    assert obs.dtype == torch.int64 and np.array_equal(_np(obs), g["init_obs"])
+    for t in range(T):
+        live = g["length"] > t
+        env.set_trace(red_actions=g["red_actions"][:, t], blue_win=g["blue_win"][:, t])
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(np.where(live[:, None], g["actions"][:, t], 0).astype(np.int8), device=cuda_device))
+        assert np.array_equal(_np(obs)[live], g["obs"][live, t]), f"step {t}"
+    assert list(env.positional_obs())[-1] == "is_red_agent_defeated" and env.status() == 0
+    env.close()
+    g = load_golden("ctf_2v2_flat")
+    n = 500
+    a = mg.make_ctf_vec(n, g["field_map"], seed=8, observation_option="positional")
+    b = mg.make_ctf_vec(n, g["field_map"], seed=8)
+    da, _ = a.reset(); b.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(1)
+    for t in range(30):
+        act = torch.randint(0, 5, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8)
+        da, ra, ta, ua, _ = a.step(act)
+        ob, rb, tb, ub, _ = b.step(act)
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(ua, ub)
+        assert isinstance(da, dict) and torch.equal(torch.cat(list(da.values()), 1), b.flattened_obs())
+    with pytest.raises(ValueError):
+        mg.make_ctf_vec(4, g["field_map"], observation_option="pixels")
+    a.close(); b.close()

@@ -113,3 +113,17 @@ def test_ctf_flattened_obs_matches_reference(stem):
                oc.map_rng(mode=0, red_actions=g["red_actions"][:, t], order=np.where(live[:, None], g["order"][:, t], ident), blue_win=g["blue_win"][:, t]))
         assert np.array_equal(o.flattened()[live], g["obs"][live, t]), f"step {t}"
     assert o.status.value == 0
+
+
+def test_ctf1v1_flattened_obs_matches_reference():
+    """Ctf1v1Env's flattened vector (ctf.py:359-371): the tail is the single is_red_agent_defeated flag."""
+    g = load_golden("ctf1v1_flat")
+    E, T, _ = g["actions"].shape
+    o = oc.CtfOracle(g["field_map"], E, 1, 1, variant_1v1=True)
+    o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"], red_place=g["red_place"]))
+    assert np.array_equal(o.flattened(), g["init_obs"])
+    for t in range(T):
+        live = g["length"] > t
+        o.step(np.where(live[:, None], g["actions"][:, t], 0), oc.map_rng(mode=0, red_actions=g["red_actions"][:, t], blue_win=g["blue_win"][:, t]))
+        assert np.array_equal(o.flattened()[live], g["obs"][live, t]), f"step {t}"
+    assert o.status.value == 0
