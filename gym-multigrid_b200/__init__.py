@@ -75,7 +75,7 @@ def make_generic_vec(num_envs: int, width: int, **kwargs):
 
 def __getattr__(name):
     """Reference-style single-env classes (same names as gym_multigrid.envs): imported lazily, they need torch + CUDA."""
-    if name in ("MazeSingleAgentEnv", "CtFMvNEnv", "Ctf1v1Env", "MazeActions", "CtfActions"):
+    if name in ("MazeSingleAgentEnv", "CtFMvNEnv", "Ctf1v1Env", "MazeActions", "CtfActions", "RwPolicy"):
         from . import single_env
         return getattr(single_env, name)
     raise AttributeError(f"module 'gym_multigrid_b200' has no attribute {name!r}")

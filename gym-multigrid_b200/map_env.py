@@ -280,6 +280,14 @@ class MazeVecEnv(_MapVecEnv):
         if observation_option == "partial":
             self.set_partial_obs(view_size, see_through_walls)
 
+    def positional_obs(self):
+        """observation_option="positional" (maze.py:224-231): `agent` int64 [N, 2] plus the map's background / flag / obstacle cell
+        lists (np.where order, flattened) broadcast over the envs - the lists are static, so they are expanded views, not copies."""
+        N = self.num_envs
+        st = lambda cells: torch.as_tensor(np.array(cells, np.int64).reshape(-1), device=self.device).expand(N, -1)  # noqa: E731
+        return {"agent": self.agent_pos[:, 0].to(torch.int64), "background": st(self.background), "flag": st(self.flag),
+                "obstacle": st(self.obstacle)}
+
     def set_partial_obs(self, view_size=7, see_through_walls=False):
         """Switch `reset` / `step` observations to MultiGridEnv.gen_obs partial views u8 [N, 1, V, V, 3] (V in 3, 5, 7), computed
         by the same kernel launch that steps the envs; view_size 0 switches back to the "map" observation."""

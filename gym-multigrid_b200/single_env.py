@@ -80,6 +80,20 @@ class MazeSingleAgentEnv(_SingleMapEnv):
         return obs[0].cpu().numpy(), float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
 
 
+class RwPolicy:
+    """policy/ctf/heuristic.py:40-72: uniform random action.  As an `enemy_policies` entry it selects the built-in opponent, whose
+    draws come from the env's Philox stream on the device; `act` exists for callers that drive it by hand."""
+    name = "rw"
+
+    def __init__(self, action_set=None, random_generator=None):
+        self.action_set, self.random_generator = action_set or MazeActions, random_generator
+
+    def act(self, observation=None, curr_pos=None) -> int:
+        if self.random_generator is None:
+            self.random_generator = np.random.default_rng()
+        return int(self.random_generator.integers(0, len(self.action_set)))
+
+
 class CtFMvNEnv(_SingleMapEnv):
     """ctf.py:662-679 kwargs (red agents follow RwPolicy, drawn on the device); `step(blue_actions)` returns the scalar team
     reward.  observation_option: "map" (int64 (H,W)), "flattened" (int64 vector) or "positional" (dict of int64 arrays)."""
@@ -98,6 +112,40 @@ class CtFMvNEnv(_SingleMapEnv):
         self._wrap(self._vec_cls(1, map_path, **kw), observation_option)
         self.num_blue_agents, self.num_red_agents = self.vec.num_blue, self.vec.num_red
         self.action_space = MultiDiscrete([5] * self.vec.num_blue) if self._vec_cls is CtfVecEnv else Discrete(5)
+        self._set_enemy_policies(enemy_policies, seed)
+
+    def _set_enemy_policies(self, enemy_policies, seed):
+        """ctf.py:775-826: one policy for every red agent or a list of `num_red_agents` policies - any object with
+        `act(observation_dict, curr_pos) -> int` (the reference's CtfPolicy interface).  None / RwPolicy entries only = the built-in
+        device opponent.  Otherwise every red action comes from the host: `act` is called with the positional observation dict
+        and the agent's position before each step, exactly where the reference calls it (ctf.py:1297-1301), and the actions reach
+        the kernel through `set_red_actions`; `random_generator`, `field_map` and `action_set` attributes are filled in as the
+        reference's constructor does."""
+        nr = self.vec.num_red
+        pols = list(enemy_policies) if isinstance(enemy_policies, (list, tuple)) else [enemy_policies] * nr
+        if len(pols) != nr:
+            raise AssertionError("len(enemy_policies) must equal num_red_agents")       # ctf.py:779
+        self.np_random = np.random.default_rng(seed)
+        self._policies = None
+        if all(p is None or isinstance(p, RwPolicy) for p in pols):
+            return
+        self._policies = [RwPolicy() if p is None else p for p in pols]
+        for p in self._policies:
+            if hasattr(p, "random_generator"):
+                p.random_generator = self.np_random
+            if getattr(p, "field_map", 0) is None:
+                p.field_map = np.asarray(self.vec.field_map)
+            if hasattr(p, "action_set"):
+                p.action_set = self.actions_set
+        self._red_buf = self.vec.set_red_actions(np.zeros((1, nr), np.int8))
+
+    def _policy_actions(self):
+        if self._policies is None:
+            return
+        d = {k: v[0].cpu().numpy() for k, v in self.vec.positional_obs().items()}
+        pos = self.vec.agent_pos[0, self.vec.num_blue:].cpu().numpy()
+        acts = [int(p.act(d, tuple(int(v) for v in pos[k]))) for k, p in enumerate(self._policies)]
+        self._red_buf.copy_(torch.as_tensor(np.array(acts, np.int8).reshape(1, -1)))
 
     def _obs(self, map_obs):
         if self.observation_option == "map":
@@ -115,6 +163,7 @@ class CtFMvNEnv(_SingleMapEnv):
 
     def step(self, blue_actions):
         a = torch.as_tensor(np.round(np.asarray(blue_actions, dtype=np.float64)).astype(np.int8).reshape(1, -1), device=self.vec.device)
+        self._policy_actions()
         obs, rew, term, trunc, _ = self.vec.step(a)
         if self.vec.status() & 8:
             raise ValueError(f"Invalid action: {blue_actions}")  # ctf.py:1200-1201

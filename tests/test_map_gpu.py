@@ -432,3 +432,19 @@ def test_ctf_observation_option_in_step_and_1v1_layout(cuda_device):
     with pytest.raises(ValueError):
         mg.make_ctf_vec(4, g["field_map"], observation_option="pixels")
     a.close(); b.close()
+
+
+def test_maze_positional_obs(cuda_device):
+    """maze.py:224-231: agent position + the static cell lists in np.where order."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("maze_board13")
+    env = mg.make_maze_vec(33, g["field_map"], seed=2)
+    env.reset()
+    env.step(torch.ones(33, dtype=torch.int8, device=cuda_device))
+    d = env.positional_obs()
+    assert list(d) == ["agent", "background", "flag", "obstacle"] and all(v.dtype == torch.int64 for v in d.values())
+    assert np.array_equal(_np(d["agent"]), _np(env.agent_pos)[:, 0])
+    for key, code in (("background", 0), ("flag", 2), ("obstacle", 3)):
+        want = np.array(list(zip(*np.where(g["field_map"] == code))), np.int64).reshape(-1)
+        assert np.array_equal(_np(d[key]), np.broadcast_to(want, (33, want.size)))
+    env.close()

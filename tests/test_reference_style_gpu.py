@@ -120,3 +120,54 @@ def test_single_env_adaptors_replay_reference_episodes(maps, cuda_device):
         assert (term, trunc) == (bool(g["terminated"][ep, t]), bool(g["truncated"][ep, t]))
         assert list(info.values()) == list(g["info"][ep, t])
     env.close()
+
+
+class _ChasePolicy:
+    """A caller-supplied `enemy_policies` entry with the reference's CtfPolicy interface (policy/ctf/heuristic.py:18-37, 75-177):
+    steps greedily towards the nearest blue agent read from the observation dict; `random_generator` / `field_map` /
+    `action_set` are filled in by the env as ctf.py:785-826 does."""
+    name = "chase"
+
+    def __init__(self, field_map=None):
+        self.field_map, self.random_generator, self.action_set, self.calls = field_map, None, None, 0
+
+    def act(self, observation, curr_pos):
+        assert set(observation) == {"blue_agent", "red_agent", "blue_flag", "red_flag", "blue_territory", "red_territory", "obstacle", "terminated_agents"}
+        self.calls += 1
+        blue = observation["blue_agent"].reshape(-1, 2)
+        t = blue[np.argmin(np.abs(blue - np.array(curr_pos)).sum(1))]
+        d = t - np.array(curr_pos)
+        if d[0] != 0:
+            return int(self.action_set.up if d[0] > 0 else self.action_set.down)      # up = (+1, 0), down = (-1, 0)
+        if d[1] != 0:
+            return int(self.action_set.right if d[1] > 0 else self.action_set.left)   # right = (0, +1), left = (0, -1)
+        return int(self.action_set.stay)
+
+
+def test_enemy_policies_objects(maps, cuda_device):
+    """tests/test_ctf.py:97-125 (`enemy_policies=[FightPolicy(), RwPolicy()]`): host-side policy objects drive the red agents
+    through the adaptor; the first red agent closes in on the blue agents, frames are rendered every step as the test does."""
+    from gym_multigrid_b200 import CtFMvNEnv, RwPolicy
+    chase = _ChasePolicy()
+    env = CtFMvNEnv(num_blue_agents=2, num_red_agents=2, map_path=maps["board.txt"], render_mode="human", observation_option="flattened",
+                    enemy_policies=[chase, RwPolicy()])
+    assert chase.random_generator is env.np_random and chase.field_map is not None and chase.action_set is env.actions_set
+    obs, _ = env.reset()
+    frames = [env.render()]
+    nb = 2
+    dist = lambda: np.abs(env.agent_positions[:nb] - env.agent_positions[nb]).sum(1).min()  # noqa: E731
+    d0 = dist()
+    for _ in range(3):
+        obs, reward, terminated, truncated, info = env.step([0, 0])            # blue stays: the chaser must get closer
+        frames.append(env.render())
+        if terminated or truncated:
+            break
+    assert chase.calls >= 1 and (dist() < d0 or terminated)
+    assert all(f.shape == frames[0].shape and f.dtype == np.uint8 for f in frames)
+    env.close()
+    with pytest.raises(AssertionError):
+        CtFMvNEnv(map_path=maps["board.txt"], enemy_policies=[chase])           # ctf.py:779: one policy per red agent
+    one = CtFMvNEnv(map_path=maps["board.txt"], enemy_policies=_ChasePolicy())  # a single policy is shared by every red agent (ctf.py:776-777)
+    one.reset(); one.step([1, 2])
+    assert one._policies[0] is one._policies[1] and one._policies[0].calls == 2
+    one.close()
