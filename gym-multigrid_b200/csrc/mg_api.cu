@@ -963,6 +963,13 @@ extern "C" int mg_step_host_wait(mg_env* env, void* stream) {
   return 0;
 }
 
+extern "C" int mg_set_seed(mg_env* env, uint64_t seed) {
+  if (!env) return -1;
+  env->base.seed = seed; env->mbase.seed = seed; env->wbase.seed = seed; env->gbase.seed = seed;   // only the handle's family reads its block
+  env->cfg.seed = seed; env->mcfg.seed = seed;
+  return 0;
+}
+
 extern "C" int mg_status(mg_env* env, void* stream, int32_t* status_out) {
   if (!env || !status_out) return -1;
   cudaError_t ce;

@@ -365,6 +365,10 @@ class CtfVecEnv(_MapVecEnv):
         return self._flat if self.observation_option == "flattened" else self._positional_views(self._flat)
 
     def reset(self, *, seed=None, options=None, mask=None):
+        """`seed` (an int) re-keys the env's generator as `super().reset(seed=seed)` does in the reference (ctf.py:1056,
+        multigrid.py:114-119): the same seed gives the same placements and the same episode for the same actions."""
+        if seed is not None:
+            self.reseed(seed)
         _, info = super().reset(seed=seed, options=options, mask=mask)
         return self._option_obs(), info
 

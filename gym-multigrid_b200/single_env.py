@@ -158,7 +158,9 @@ class CtFMvNEnv(_SingleMapEnv):
         return d
 
     def reset(self, *, seed=None, options=None):
-        obs, _ = self.vec.reset()
+        if seed is not None:      # gymnasium.Env.reset(seed=): a fresh np_random (tests/test_ctf.py:37-48); policies keep the generator they were given
+            self.np_random = np.random.default_rng(seed)
+        obs, _ = self.vec.reset(seed=seed)
         return self._obs(obs), self._info()
 
     def step(self, blue_actions):

@@ -49,6 +49,16 @@ class VectorEnvSurface:
     def set_attr(self, name: str, values):
         setattr(self, name, values)
 
+    def reseed(self, seed: int):
+        """Re-key the Philox streams (mg_set_seed) and zero the per-env block counters: everything that follows - resets,
+        respawns, shuffles, battles - is then a function of (`seed`, global env id) alone, as after construction with that seed."""
+        import ctypes as C
+        hdr = getattr(self, "_planes", {}).get("hdr")
+        if hdr is None:
+            raise NotImplementedError(f"{type(self).__name__} keeps its RNG counters elsewhere; construct it with the seed instead")
+        self._check(self._lib.mg_set_seed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)))
+        hdr[:, 2] = 0
+
     # ---- host-buffer path split in two (gymnasium VectorEnv.step_async / step_wait); the classes provide _host_io / _host_result
     _host_stream = None
     _host_pending = False

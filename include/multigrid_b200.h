@@ -145,6 +145,11 @@ int mg_toroid_obs(mg_env* env, const void* state_dev, float* out_dev, void* stre
  * The per-code tile images are rasterised once per tile size on the host when first asked for (the reference's tile cache); the call itself is one kernel that blits them.  An env id outside [0, N) draws env 0 and sets MG_ERR_OOB. */
 int mg_render(mg_env* env, const void* state_dev, const int32_t* env_ids_dev, int n, int tile_size, uint8_t* out_dev, void* stream);
 
+/* Re-key the Philox streams of the following launches (`reset(seed=...)`, multigrid.py:114-119 -> gymnasium's np_random(seed)).
+ * The per-env block counters live in the caller's state buffer (header word 2): zero them as well to make what follows a
+ * function of the seed alone. */
+int mg_set_seed(mg_env* env, uint64_t seed);
+
 /* Same as mg_step with HOST buffers: copies actions host->device, steps, copies obs / rewards /
  * flags device->host and waits.  This is the call a gymnasium-style user makes with numpy
  * arrays; buffers should be page-locked for full PCIe bandwidth. */

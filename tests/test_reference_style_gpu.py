@@ -171,3 +171,28 @@ def test_enemy_policies_objects(maps, cuda_device):
     one.reset(); one.step([1, 2])
     assert one._policies[0] is one._policies[1] and one._policies[0].calls == 2
     one.close()
+
+
+def test_ctf_random_seeding(maps, cuda_device):
+    """tests/test_ctf.py:37-48: `reset(seed=1)` twice gives the same np_random stream - and, here, the same episode."""
+    from gym_multigrid_b200 import Ctf1v1Env, CtFMvNEnv
+    env = Ctf1v1Env(map_path=maps["board.txt"], render_mode="human", observation_option="flattened")
+    env.reset(seed=1)
+    array1 = env.np_random.random(10)
+    env.reset(seed=1)
+    array2 = env.np_random.random(10)
+    np.testing.assert_allclose(array1, array2)
+    env.close()
+    env = CtFMvNEnv(map_path=maps["board.txt"], observation_option="flattened")
+    runs = []
+    for seed in (5, 5, 6):
+        obs, _ = env.reset(seed=seed)
+        traj = [obs]
+        for t in range(12):
+            obs, rew, term, trunc, _ = env.step([t % 5, (t + 2) % 5])
+            traj.append(obs)
+            if term or trunc:
+                break
+        runs.append(np.stack(traj))
+    assert np.array_equal(runs[0], runs[1]) and not (runs[0].shape == runs[2].shape and np.array_equal(runs[0], runs[2]))
+    env.close()
