@@ -36,9 +36,9 @@ constexpr uint32_t FL_DEAD = 1u << 24, FL_COLLIDED = 2u << 24;  // Agent.termina
 // a territory / flag cell, left alone elsewhere (ctf.py:1214-1230, agent.py:197-200); only render() reads it
 constexpr uint32_t FL_BG_MASK = 12u << 24, FL_BG_BLUE = 4u << 24, FL_BG_RED = 8u << 24;
 __device__ __forceinline__ uint32_t bg_after_move(uint32_t w, int terrain_code) {
-  if (terrain_code == 0 || terrain_code == 4) return (w & ~FL_BG_MASK) | FL_BG_BLUE;   // CT_BLUE_TERR, CT_BLUE_FLAG
-  if (terrain_code == 1 || terrain_code == 5) return (w & ~FL_BG_MASK) | FL_BG_RED;    // CT_RED_TERR, CT_RED_FLAG
-  return w;
+  // nibble table over the CtfWorld codes: blue territory 0 / blue flag 4 -> 1, red territory 1 / red flag 5 -> 2, anything else 0 = keep
+  const uint32_t v = (0x0210021u >> (4 * terrain_code)) & 3u;
+  return v ? ((w & ~FL_BG_MASK) | (v << 26)) : w;
 }
 
 __device__ __forceinline__ uint32_t ag_pack(int x, int y, int dir, int fl) {
@@ -351,7 +351,10 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
 // MINB: minimum resident CTAs per SM the register allocation must allow.  8 (64 registers, a few spills) wins when many
 // waves of tiles keep every SM full (>= 256 K envs); 1 (no cap, no spills) has the shorter dependent chain and wins for
 // launches of a wave or two, which are latency-bound.
-template <int FAMILY, int MODE, int MINB>
+// STEPV: which CtF step body the kernel carries - 0 the general one (run-time team sizes), 1 the 2v2 and 2 the 1v1 register
+// bodies.  One body per kernel keeps the instruction stream of the hot path inside the instruction cache (with all of them
+// inlined into one kernel `no_instruction` became the top stall reason).
+template <int FAMILY, int MODE, int MINB, int STEPV = 0>
 __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar, bar_tile;
@@ -402,10 +405,10 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   int4 h = p.hdr[e];
   uint32_t blue_raw = 0;   // 2v2 / 1v1 step: the blue actions travel with the state loads, ahead of the wait for the staged period
   if (FAMILY == MG_FAMILY_CTF && p.op == 1 && tid < n_here) {
-    if (p.nb == 2 && p.nr == 2)
+    if (STEPV == 1)
       blue_raw = (reinterpret_cast<uintptr_t>(p.actions) & 1) ? ((uint32_t)(uint8_t)p.actions[e * 2] | ((uint32_t)(uint8_t)p.actions[e * 2 + 1] << 8))
                                                                 : *reinterpret_cast<const uint16_t*>(p.actions + e * 2);
-    else if (p.nb == 1 && p.nr == 1) blue_raw = (uint8_t)p.actions[e];
+    else if (STEPV == 2) blue_raw = (uint8_t)p.actions[e];
   }
   bool done = false, want_reset = false;
   int err = 0;
@@ -419,8 +422,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     } else {
       double rew; bool term, trunc;
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
-      else if (p.nb == 2 && p.nr == 2) ctf_step_regs<MODE, 2, 2>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
-      else if (p.nb == 1 && p.nr == 1) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
+      else if (STEPV == 1) ctf_step_regs<MODE, 2, 2>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
+      else if (STEPV == 2) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (n <= 8) ctf_step_one<MODE, uint32_t, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       else ctf_step_one<MODE, unsigned long long, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       p.rewards[e] = rew; p.terminated[e] = term; p.truncated[e] = trunc;
@@ -742,7 +745,7 @@ size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
 }
 int map_tile_envs() { return kMapE; }
 
-template <int FAMILY, int MODE, int MINB>
+template <int FAMILY, int MODE, int MINB, int STEPV>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.map_padded_bytes, p.view_V)
                                                                : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
@@ -753,33 +756,44 @@ static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = map_pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB>, p);
+  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB, STEPV>, p);
 }
 
-template <int FAMILY, int MODE>
+template <int FAMILY, int MODE, int STEPV>
 static cudaError_t configure_pair(int smem) {
-  cudaError_t e = raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 1>, (size_t)smem);
+  cudaError_t e = raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 1, STEPV>, (size_t)smem);
   if (e != cudaSuccess) return e;
-  return raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 8>, (size_t)smem);
+  return raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 8, STEPV>, (size_t)smem);
 }
 
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
   const int smem = (int)map_smem_bytes(L, n, cells, obs_dtype);
   cudaError_t e;
-  if ((e = configure_pair<MG_FAMILY_MAZE, 0>(smem)) != cudaSuccess) return e;
-  if ((e = configure_pair<MG_FAMILY_MAZE, 1>(smem)) != cudaSuccess) return e;
-  if ((e = configure_pair<MG_FAMILY_CTF, 0>(smem)) != cudaSuccess) return e;
-  return configure_pair<MG_FAMILY_CTF, 1>(smem);
+  if ((e = configure_pair<MG_FAMILY_MAZE, 0, 0>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_MAZE, 1, 0>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 0, 0>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 0, 1>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 0, 2>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 1, 0>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 1, 1>(smem)) != cudaSuccess) return e;
+  return configure_pair<MG_FAMILY_CTF, 1, 2>(smem);
 }
 
-template <int FAMILY, int MODE>
+template <int FAMILY, int MODE, int STEPV>
 static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
-  return p.N >= 262144 ? launch_one<FAMILY, MODE, 8>(p, st) : launch_one<FAMILY, MODE, 1>(p, st);
+  return p.N >= 262144 ? launch_one<FAMILY, MODE, 8, STEPV>(p, st) : launch_one<FAMILY, MODE, 1, STEPV>(p, st);
+}
+
+template <int MODE>
+static cudaError_t launch_ctf(const MapParams& p, cudaStream_t st) {
+  if (p.nb == 2 && p.nr == 2) return launch_by_size<MG_FAMILY_CTF, MODE, 1>(p, st);
+  if (p.nb == 1 && p.nr == 1) return launch_by_size<MG_FAMILY_CTF, MODE, 2>(p, st);
+  return launch_by_size<MG_FAMILY_CTF, MODE, 0>(p, st);
 }
 
 cudaError_t launch_map(const MapParams& p, cudaStream_t st) {
-  if (p.family == MG_FAMILY_MAZE) return p.rng_mode == 0 ? launch_by_size<MG_FAMILY_MAZE, 0>(p, st) : launch_by_size<MG_FAMILY_MAZE, 1>(p, st);
-  return p.rng_mode == 0 ? launch_by_size<MG_FAMILY_CTF, 0>(p, st) : launch_by_size<MG_FAMILY_CTF, 1>(p, st);
+  if (p.family == MG_FAMILY_MAZE) return p.rng_mode == 0 ? launch_by_size<MG_FAMILY_MAZE, 0, 0>(p, st) : launch_by_size<MG_FAMILY_MAZE, 1, 0>(p, st);
+  return p.rng_mode == 0 ? launch_ctf<0>(p, st) : launch_ctf<1>(p, st);
 }
 
 }  // namespace mg
