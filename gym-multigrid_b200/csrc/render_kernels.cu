@@ -131,6 +131,7 @@ struct RenderParams {
   long long N;
   const int32_t* env_ids;   // [n] envs to draw, or null = envs 0..n-1
   int n, W, H, ts, JB;      // JB = rows of tiles one CTA draws
+  unsigned per_row_magic, cpt_magic, w_magic;   // floor(2^32 / d) + 1 for d = 16-byte chunks per frame row, per tile row, and W: q = umulhi(n, magic) (n * d < 2^32)
   const uint8_t* atlas;     // [256][ts][ts][3]
   uint8_t* out;             // [n][H*ts][W*ts][3]
   int32_t* status;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
       const uint32_t* tile = s_tile + jj * W;
       uint8_t* d = dst0 + (size_t)jj * ts * frame_row;
       for (int c = tid; c < total; c += kRenderThreads) {
-        const int y = c / per_row, r = c - y * per_row, i = r / cpt, k = r - i * cpt;
+        const int y = (int)__umulhi((unsigned)c, p.per_row_magic), r = c - y * per_row, i = (int)__umulhi((unsigned)r, p.cpt_magic), k = r - i * cpt;
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.atlas + tile[i] + y * trow) + k);
         reinterpret_cast<uint4*>(d + (size_t)y * frame_row)[r] = v;
       }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
       uint8_t* sb = s_buf + shift;
       const bool unit_ok = shift % G == 0;
       for (int c = tid; c < total; c += kRenderThreads) {
-        const int yy = c / W, i = c - yy * W, y = y0 + yy, jj = y / ts, ty = y - jj * ts;
+        const int yy = (int)__umulhi((unsigned)c, p.w_magic), i = c - yy * W, y = y0 + yy, jj = y / ts, ty = y - jj * ts;
         const uint8_t* src = p.atlas + s_tile[jj * W + i] + ty * trow;
         uint8_t* d = sb + yy * frame_row + i * trow;
         for (int k = 0; k < upt; ++k, src += G, d += G) {
@@ -252,6 +253,9 @@ cudaError_t launch_render(const uint8_t* cells, const uint8_t* agents, int agent
   if (JB > H) JB = H;
   if (JB * W > kRenderMaxTiles) JB = kRenderMaxTiles / W;
   p.JB = JB;
+  auto magic = [](unsigned d) { return (unsigned)(4294967296ull / d) + 1u; };
+  p.per_row_magic = trow % 16 == 0 ? magic((unsigned)(W * (trow / 16))) : 0u; p.cpt_magic = trow % 16 == 0 ? magic((unsigned)(trow / 16)) : 0u;
+  p.w_magic = magic((unsigned)W);
   const unsigned blocks = (unsigned)n * (unsigned)((H + JB - 1) / JB);
   if (trow % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) render_kernel<0, 1><<<blocks, kRenderThreads, 0, st>>>(p);
   else if (W * trow > kRenderStage) render_kernel<2, 1><<<blocks, kRenderThreads, 0, st>>>(p);
