@@ -1,7 +1,8 @@
 /* c_driver.c -- the C ABI used from plain C: no Python, no torch, only include/multigrid_b200.h and the CUDA runtime for
  * the caller-owned buffers.  Creates `multigrid-collect-respawn-clustered-v0` (registered kwargs, gym_multigrid/__init__.py:122-134),
  * resets, runs `steps` steps with a deterministic action pattern and writes the final observations, the per-step reward
- * sums and the flag counts as raw bytes to `out_path`; tests/test_c_abi_gpu.py recomputes them with the oracle.
+ * sums, the flag counts and rendered frames of three envs as raw bytes to `out_path`; tests/test_c_abi_gpu.py recomputes them
+ * with the oracle.
  *
  *   cc c_driver.c -I include -I $CUDA/include -L pkg -lmultigrid_b200 -L $CUDA/lib64 -lcudart -o c_driver
  *   ./c_driver <num_envs> <steps> <seed> <out_path> */
@@ -62,6 +63,16 @@ int main(int argc, char** argv) {
   uint8_t* h_obs = (uint8_t*)malloc(ob);
   CK(cudaMemcpy(h_obs, obs, ob, cudaMemcpyDeviceToHost));
   fwrite(h_obs, 1, ob, f);
+  /* MultiGridEnv.render() frames of three envs through mg_render (env ids on the device, tile size 32) */
+  const int32_t h_ids[3] = {0, (int32_t)(N / 2), (int32_t)(N - 1)};
+  int32_t* ids; uint8_t* frames;
+  const size_t fb = (size_t)3 * (H * 32) * (W * 32) * 3;
+  CK(cudaMalloc((void**)&ids, sizeof h_ids)); CK(cudaMalloc((void**)&frames, fb));
+  CK(cudaMemcpy(ids, h_ids, sizeof h_ids, cudaMemcpyHostToDevice));
+  if (mg_render(env, state, ids, 3, 32, frames, NULL) != 0) { fprintf(stderr, "mg_render: %s\n", mg_last_error(env)); return 8; }
+  uint8_t* h_frames = (uint8_t*)malloc(fb);
+  CK(cudaMemcpy(h_frames, frames, fb, cudaMemcpyDeviceToHost));
+  fwrite(h_frames, 1, fb, f);
   int32_t status = -1;
   if (mg_status(env, NULL, &status) != 0 || status != 0) { fprintf(stderr, "status word %d\n", status); return 7; }
   fclose(f);

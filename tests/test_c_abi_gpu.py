@@ -23,11 +23,12 @@ def test_plain_c_program_drives_the_library(tmp_path, cuda_device):
     n, steps, seed = 777, 120, 31
     r = subprocess.run([exe, str(n), str(steps), str(seed), out], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
-    assert f"{steps + 1} launches" in r.stdout
+    assert f"{steps + 2} launches" in r.stdout      # reset + steps + render
     raw = np.fromfile(out, dtype=np.uint8)
     per_step = raw[: steps * 24].view(np.int64).reshape(steps, 3)
     sums = raw[: steps * 24].view(np.float64).reshape(steps, 3)[:, 0]
-    final_obs = raw[steps * 24:].reshape(n, 10, 10, 3)
+    final_obs = raw[steps * 24: steps * 24 + n * 300].reshape(n, 10, 10, 3)
+    frames = raw[steps * 24 + n * 300:].reshape(3, 320, 320, 3)
 
     s = mg.spec("multigrid-collect-respawn-clustered-v0")
     o = oc.CollectOracle(oc.make_collect_cfg(layout="quadrants_respawn", time_limit=s.max_episode_steps, **s.kwargs), n)
@@ -39,3 +40,4 @@ def test_plain_c_program_drives_the_library(tmp_path, cuda_device):
         obs, rew, term, trunc = o.step(act, rng, autoreset=True)
         assert rew.sum() == sums[t] and int(term.sum()) == per_step[t, 1] and int(trunc.sum()) == per_step[t, 2], f"step {t}"
     assert np.array_equal(final_obs, obs)
+    assert np.array_equal(frames, oc.render_grid(obs[[0, n // 2, n - 1]], 32))
