@@ -4,7 +4,8 @@ observations for the policy, rgb_array frames of a few envs for a GIF - batched,
 
     python examples/ctf_policy_and_frames.py [--map path/to/board.txt] [--num-envs 4096] [--steps 100] [--out frames.npy]
 
-* `CtfVecEnv(observation_option="flattened")`: `reset` / `step` return the int64 vector of ctf.py:1084-1104 for every env.
+* `CtfVecEnv(observation_option="flattened")`: `reset` / `step` return the vector of ctf.py:1084-1104 for every env (uint8; int64 with
+  `reference_dtypes=True`).
 * `set_red_actions(buffer)`: the red team follows whatever you write into `buffer` before each step (a learned opponent,
   self-play, a scripted policy) instead of the built-in random walk.
 * `render(env_ids=[...])`: `MultiGridEnv.render()` frames of the selected envs, bit-identical to the reference's.
@@ -46,7 +47,7 @@ def main():
         # 1 left = y-1, 3 right = y+1)
         d = blue_flag - env.agent_pos[:, nb:].to(torch.int64)
         red.copy_(torch.where(d[..., 0] != 0, torch.where(d[..., 0] > 0, 4, 2), torch.where(d[..., 1] > 0, 3, torch.where(d[..., 1] < 0, 1, 0))).to(torch.int8))
-        blue = torch.randint(0, 5, (n, nb), device=dev, dtype=torch.int8)          # your policy goes here: obs is [n, 216] int64 on the GPU
+        blue = torch.randint(0, 5, (n, nb), device=dev, dtype=torch.int8)          # your policy goes here: obs is [n, 216] on the GPU
         obs, rew, term, trunc, _ = env.step(blue)
         ret += rew
         frames.append(env.render(env_ids=[0, 1, 2, 3]).cpu())

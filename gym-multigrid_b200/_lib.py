@@ -27,7 +27,7 @@ ERR_TRACE_OVERFLOW, ERR_TRACE_RANGE, ERR_OOB = 1, 2, 4
 EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
-    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic", "mg_map_info", "mg_set_partial_obs", "mg_host_layout", "mg_set_red_actions", "mg_step_host_async", "mg_step_host_wait", "mg_render", "mg_ctf_flat_len", "mg_ctf_flat_obs", "mg_set_seed",
+    "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic", "mg_map_info", "mg_set_partial_obs", "mg_host_layout", "mg_set_red_actions", "mg_step_host_async", "mg_step_host_wait", "mg_render", "mg_ctf_flat_len", "mg_ctf_flat_obs", "mg_ctf_flat_obs_u8", "mg_set_seed",
 ]
 
 
@@ -120,6 +120,7 @@ def load():
     lib.mg_step_host_wait.argtypes = [C.c_void_p, C.c_void_p]
     lib.mg_ctf_flat_len.argtypes = [C.c_void_p]
     lib.mg_ctf_flat_obs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mg_ctf_flat_obs_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mg_set_seed.argtypes = [C.c_void_p, C.c_uint64]
     lib.mg_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.mg_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

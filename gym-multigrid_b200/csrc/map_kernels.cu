@@ -653,15 +653,16 @@ cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st) {
 // (first 2 n entries) and terminated flags (last n) filled in.  A CTA assembles kFlatE env rows in shared memory and writes them
 // with one TMA bulk store: the output is ~1.7 KB per env of which 3 n values differ, so the kernel is a pure HBM write stream.
 constexpr int kFlatThreads = 128;
+template <typename T>   // long long = the reference's dtype; uint8_t = the compact form (every entry is a coordinate < 256 or a flag)
 __global__ void __launch_bounds__(kFlatThreads) ctf_flat_kernel(const __grid_constant__ MapParams p, const long long* __restrict__ tmpl, int L,
-                                                                int E, long long* __restrict__ out, int bulk_ok) {
+                                                                int E, T* __restrict__ out, int bulk_ok) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  long long* s = reinterpret_cast<long long*>(smem_raw);   // [E][L]
+  T* s = reinterpret_cast<T*>(smem_raw);   // [E][L]
   const int tid = threadIdx.x, n = p.n;
   const long long e0 = (long long)blockIdx.x * E;
   const int n_here = (int)min((long long)E, p.N - e0);
   for (int c = tid; c < L; c += kFlatThreads) {
-    const long long v = __ldg(tmpl + c);
+    const T v = (T)__ldg(tmpl + c);
 #pragma unroll 4
     for (int r = 0; r < E; ++r) s[r * L + c] = v;
   }
@@ -669,14 +670,14 @@ __global__ void __launch_bounds__(kFlatThreads) ctf_flat_kernel(const __grid_con
   for (int t = tid; t < n_here * n; t += kFlatThreads) {
     const int r = t / n, i = t - r * n;
     const uint32_t w = *reinterpret_cast<const uint32_t*>(p.agents + (e0 + r) * p.row_bytes + 4 * i);
-    s[r * L + 2 * i] = ag_x(w); s[r * L + 2 * i + 1] = ag_y(w);
+    s[r * L + 2 * i] = (T)ag_x(w); s[r * L + 2 * i + 1] = (T)ag_y(w);
     if (!p.variant_1v1) s[r * L + L - n + i] = (w & FL_DEAD) ? 1 : 0;
     else if (i == 1) s[r * L + L - 1] = (w & FL_DEAD) ? 1 : 0;   // Ctf1v1Env: the tail is int(_is_red_agent_defeated) alone (ctf.py:359-371)
   }
   fence_proxy_async_smem();
   __syncthreads();
-  long long* g = out + e0 * L;
-  const uint32_t bytes = (uint32_t)n_here * (uint32_t)L * 8u;
+  T* g = out + e0 * L;
+  const uint32_t bytes = (uint32_t)n_here * (uint32_t)L * (uint32_t)sizeof(T);
   if (bulk_ok && bytes % 16 == 0) {
     if (tid == 0) { tma_store_1d(g, s, bytes); tma_commit(); tma_wait_read_all(); }
   } else {
@@ -684,21 +685,29 @@ __global__ void __launch_bounds__(kFlatThreads) ctf_flat_kernel(const __grid_con
   }
 }
 
-// envs per CTA: an even count (tile bases stay 16-byte aligned) whose rows fit in ~96 KB of shared memory; 0 = the map's lists are too long
-int ctf_flat_tile_envs(int L) {
-  int E = (int)((96 * 1024) / ((size_t)L * 8)) & ~1;
-  return E > 16 ? 16 : E;
+// envs per CTA: a multiple of 16 / sizeof(T) rows (tile bases stay 16-byte aligned) that fits in ~96 KB of shared memory and moves
+// ~28 KB per bulk store; 0 = the map's lists are too long
+int ctf_flat_tile_envs(int L, int elem) {
+  const int unit = elem == 8 ? 2 : 16;
+  int E = (int)((96 * 1024) / ((size_t)L * elem)) / unit * unit;
+  const int cap = elem == 8 ? 16 : 128;
+  return E > cap ? cap : E;
 }
 
-cudaError_t launch_ctf_flat(const MapParams& p, const long long* tmpl, int L, long long* out, cudaStream_t st) {
-  const int E = ctf_flat_tile_envs(L);
+cudaError_t launch_ctf_flat(const MapParams& p, const long long* tmpl, int L, void* out, int elem, cudaStream_t st) {
+  const int E = ctf_flat_tile_envs(L, elem);
   if (E < 2) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)E * L * 8;
-  cudaError_t e = raise_smem_limit((const void*)ctf_flat_kernel, smem);
-  if (e != cudaSuccess) return e;
+  const size_t smem = (size_t)E * L * elem;
   const unsigned blocks = (unsigned)((p.N + E - 1) / E);
   const int bulk_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  ctf_flat_kernel<<<blocks, kFlatThreads, smem, st>>>(p, tmpl, L, E, out, bulk_ok);
+  cudaError_t e;
+  if (elem == 8) {
+    if ((e = raise_smem_limit((const void*)ctf_flat_kernel<long long>, smem)) != cudaSuccess) return e;
+    ctf_flat_kernel<long long><<<blocks, kFlatThreads, smem, st>>>(p, tmpl, L, E, static_cast<long long*>(out), bulk_ok);
+  } else {
+    if ((e = raise_smem_limit((const void*)ctf_flat_kernel<uint8_t>, smem)) != cudaSuccess) return e;
+    ctf_flat_kernel<uint8_t><<<blocks, kFlatThreads, smem, st>>>(p, tmpl, L, E, static_cast<uint8_t*>(out), bulk_ok);
+  }
   return cudaGetLastError();
 }
 

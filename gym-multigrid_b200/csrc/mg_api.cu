@@ -35,8 +35,8 @@ int map_tma_reps(int L, int cells, int obs_dtype);
 size_t map_view_smem_bytes(int padded_bytes, int V);
 cudaError_t configure_map_view_mode(size_t smem);
 cudaError_t launch_map_info(const MapParams& p, double* out, cudaStream_t st);
-cudaError_t launch_ctf_flat(const MapParams& p, const long long* tmpl, int L, long long* out, cudaStream_t st);
-int ctf_flat_tile_envs(int L);
+cudaError_t launch_ctf_flat(const MapParams& p, const long long* tmpl, int L, void* out, int elem, cudaStream_t st);
+int ctf_flat_tile_envs(int L, int elem);
 int map_tile_envs();
 }  // namespace mg
 #include "map_params.cuh"
@@ -553,13 +553,13 @@ extern "C" int mg_ctf_flat_len(const mg_env* env) {
   return (int)env->flat_tmpl.size();
 }
 
-extern "C" int mg_ctf_flat_obs(mg_env* env, const void* state, int64_t* out, void* stream) {
+static int ctf_flat(mg_env* env, const void* state, void* out, int elem, void* stream) {
   if (!env || !state || !out) return fail(env, "mg_ctf_flat_obs: null argument");
   if (env->family != MG_FAMILY_CTF) return fail(env, "mg_ctf_flat_obs: CtF family only");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   const int L = (int)env->flat_tmpl.size();
-  if (mg::ctf_flat_tile_envs(L) < 2) return fail(env, "mg_ctf_flat_obs: the map's cell lists are too long for the kernel's shared-memory tile");
+  if (mg::ctf_flat_tile_envs(L, elem) < 2) return fail(env, "mg_ctf_flat_obs: the map's cell lists are too long for the kernel's shared-memory tile");
   if (!env->d_flat_tmpl) {
     if ((ce = cudaMalloc(&env->d_flat_tmpl, (size_t)L * sizeof(long long))) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
     if ((ce = cudaMemcpy(env->d_flat_tmpl, env->flat_tmpl.data(), (size_t)L * sizeof(long long), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -568,11 +568,14 @@ extern "C" int mg_ctf_flat_obs(mg_env* env, const void* state, int64_t* out, voi
   mg::MapParams p = env->mbase;
   p.agents = const_cast<uint8_t*>(static_cast<const uint8_t*>(state)) + env->plane_off[MG_MAP_PLANE_AGENTS];
   p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
-  if ((ce = mg::launch_ctf_flat(p, env->d_flat_tmpl, L, reinterpret_cast<long long*>(out), static_cast<cudaStream_t>(stream))) != cudaSuccess)
+  if ((ce = mg::launch_ctf_flat(p, env->d_flat_tmpl, L, out, elem, static_cast<cudaStream_t>(stream))) != cudaSuccess)
     return cuda_fail(env, "ctf_flat_kernel", ce);
   env->launches += 1;
   return 0;
 }
+
+extern "C" int mg_ctf_flat_obs(mg_env* env, const void* state, int64_t* out, void* stream) { return ctf_flat(env, state, out, 8, stream); }
+extern "C" int mg_ctf_flat_obs_u8(mg_env* env, const void* state, uint8_t* out, void* stream) { return ctf_flat(env, state, out, 1, stream); }
 
 // -------------------------------------------------------------------------------- Wildfire
 extern "C" int mg_create_wildfire(const mg_wildfire_config* cfg, int device, mg_env** out) {

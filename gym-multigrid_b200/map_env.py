@@ -352,11 +352,13 @@ class CtfVecEnv(_MapVecEnv):
         self.red_territory = cells(1) + [self.red_flag]
         if observation_option != "map":   # reset / step return the flattened vector (or its dict of views): step launch + ctf_flat_kernel
             L = self._lib.mg_ctf_flat_len(self._h)
-            self._flat = torch.zeros((self.num_envs, L), dtype=torch.int64, device=self.device)
+            fdt = torch.int64 if reference_dtypes else torch.uint8      # as for the map observation: the reference's dtype on request
+            self._flat = torch.zeros((self.num_envs, L), dtype=fdt, device=self.device)
             self._skip_map_obs = True
             if observation_option == "flattened":                                # ctf.py:940-948
-                self.single_observation_space = Box(0, max(self.size - 1, 1), (L,), np.int64)
-                self.observation_space = Box(0, max(self.size - 1, 1), (self.num_envs, L), np.int64)
+                odt = np.int64 if reference_dtypes else np.uint8
+                self.single_observation_space = Box(0, max(self.size - 1, 1), (L,), odt)
+                self.observation_space = Box(0, max(self.size - 1, 1), (self.num_envs, L), odt)
 
     def _option_obs(self):
         if self.observation_option == "map":
@@ -401,12 +403,16 @@ class CtfVecEnv(_MapVecEnv):
         return {"blue_agent_defeated": bits[:, :self.num_blue].bool(), "red_agent_defeated": bits[:, self.num_blue:].bool(),
                 "blue_flag_captured": (st & 1).bool(), "red_flag_captured": ((st >> 1) & 1).bool()}
 
-    def flattened_obs(self, out=None):
-        """observation_option="flattened" (ctf.py:1084-1104) of every env: int64 CUDA tensor [N, L], one kernel (mg_ctf_flat_obs)."""
+    def flattened_obs(self, out=None, dtype=None):
+        """observation_option="flattened" (ctf.py:1084-1104) of every env: CUDA tensor [N, L], one kernel (mg_ctf_flat_obs).
+        dtype int64 (default: the reference's) or uint8 (1/8 of the bytes; every entry is a coordinate < 256 or a flag)."""
         L = self._lib.mg_ctf_flat_len(self._h)
         if out is None:
-            out = torch.empty((self.num_envs, L), dtype=torch.int64, device=self.device)
-        self._check(self._lib.mg_ctf_flat_obs(self._h, _ptr(self.state), _ptr(out), self._stream()))
+            out = torch.empty((self.num_envs, L), dtype=dtype or torch.int64, device=self.device)
+        if out.dtype not in (torch.int64, torch.uint8) or tuple(out.shape) != (self.num_envs, L) or not out.is_contiguous():
+            raise ValueError(f"flattened_obs: out must be a contiguous int64 or uint8 tensor of shape {(self.num_envs, L)}")
+        fn = self._lib.mg_ctf_flat_obs if out.dtype is torch.int64 else self._lib.mg_ctf_flat_obs_u8
+        self._check(fn(self._h, _ptr(self.state), _ptr(out), self._stream()))
         return out
 
     def positional_obs(self):

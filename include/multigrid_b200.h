@@ -259,6 +259,8 @@ int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev);
  * the same vector cut at the key boundaries. */
 int mg_ctf_flat_len(const mg_env* env);
 int mg_ctf_flat_obs(mg_env* env, const void* state_dev, int64_t* out_dev, void* stream);
+/* the same vector as u8 [N][L] (every entry is a coordinate < 256 or a flag): 1/8 of the bytes for consumers on the device */
+int mg_ctf_flat_obs_u8(mg_env* env, const void* state_dev, uint8_t* out_dev, void* stream);
 
 /* Maze handles: observation mode of mg_reset / mg_step / mg_step_host.  view_size 0 (default) = the "map" observation;
  * 3 / 5 / 7 = MultiGridEnv.gen_obs partial views u8 [N][1][V][V][3] computed by the SAME launch that steps the envs

@@ -405,7 +405,7 @@ def test_ctf_observation_option_in_step_and_1v1_layout(cuda_device):
     import gym_multigrid_b200 as mg
     g = load_golden("ctf1v1_flat")
     E, T, _ = g["actions"].shape
-    env = mg.make_ctf1v1_vec(E, g["field_map"], autoreset=False, observation_option="flattened")
+    env = mg.make_ctf1v1_vec(E, g["field_map"], autoreset=False, observation_option="flattened", reference_dtypes=True)
     assert env.single_observation_space.shape == (g["obs"].shape[-1],)
     env.set_trace(blue_place=g["blue_place"], red_place=g["red_place"])
     obs, _ = env.reset()
@@ -428,7 +428,9 @@ def test_ctf_observation_option_in_step_and_1v1_layout(cuda_device):
         da, ra, ta, ua, _ = a.step(act)
         ob, rb, tb, ub, _ = b.step(act)
         assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(ua, ub)
-        assert isinstance(da, dict) and torch.equal(torch.cat(list(da.values()), 1), b.flattened_obs())
+        f8 = torch.cat(list(da.values()), 1)                      # default dtypes: the compact uint8 form
+        assert isinstance(da, dict) and f8.dtype == torch.uint8 and torch.equal(f8.to(torch.int64), b.flattened_obs())
+        assert torch.equal(b.flattened_obs(dtype=torch.uint8), f8)
     with pytest.raises(ValueError):
         mg.make_ctf_vec(4, g["field_map"], observation_option="pixels")
     a.close(); b.close()

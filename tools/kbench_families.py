@@ -98,6 +98,13 @@ def bench_ctf(args):
     outs = [torch.empty((n, 216), dtype=torch.int64, device="cuda:0") for _ in range(2)]
     us = graph_time([lambda o=o: e.flattened_obs(out=o) for o in outs], args.reps)
     report("ctf_flat_kernel 2v2 flattened obs int64 [216]", n, us, 216 * 8 + 16, batches=2)
+    n8 = 1 << 20
+    e8 = mg.make_ctf_vec(n8, fm, seed=0)
+    e8.reset()
+    outs8 = [torch.empty((n8, 216), dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+    us = graph_time([lambda o=o: e8.flattened_obs(out=o) for o in outs8], args.reps)
+    report("ctf_flat_kernel 2v2 flattened obs uint8 [216]", n8, us, 216 + 16, batches=2)
+    e8.close()
     e.close()
     n = 65536
     envs = [mg.make_ctf_vec(n, fm, reference_dtypes=True, seed=b, env_id_base=b * n) for b in range(8)]
