@@ -450,3 +450,31 @@ def test_maze_positional_obs(cuda_device):
         want = np.array(list(zip(*np.where(g["field_map"] == code))), np.int64).reshape(-1)
         assert np.array_equal(_np(d[key]), np.broadcast_to(want, (33, want.size)))
     env.close()
+
+
+def test_map_envs_step_async_wait(cuda_device):
+    """step_async / step_wait on the map families: two CtF batches and two Maze batches in flight == the blocking device path."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    mz = load_golden("maze_board13")
+    n = 900
+    pairs = [([mg.make_ctf_vec(n, g["field_map"], seed=s) for s in (1, 2)], [mg.make_ctf_vec(n, g["field_map"], seed=s) for s in (1, 2)], (n, 2)),
+             ([mg.make_maze_vec(n, mz["field_map"], seed=s) for s in (3, 4)], [mg.make_maze_vec(n, mz["field_map"], seed=s) for s in (3, 4)], (n,))]
+    rng = np.random.default_rng(5)
+    for ref, pip, shape in pairs:
+        for e in ref + pip:
+            e.reset()
+        acts = [[rng.integers(0, 5, size=shape).astype(np.int8) for _ in range(2)] for _ in range(25)]
+        for b in range(2):
+            pip[b].step_async(acts[0][b])
+        for t in range(25):
+            for b in range(2):
+                want = ref[b].step(torch.as_tensor(acts[t][b], device=cuda_device))
+                got = pip[b].step_wait()
+                for x, y in zip(want[:4], got[:4]):
+                    assert np.array_equal(_np(x), y), f"step {t} batch {b}"
+                if t + 1 < 25:
+                    pip[b].step_async(acts[t + 1][b])
+        for e in ref + pip:
+            assert e.status() == 0
+            e.close()
