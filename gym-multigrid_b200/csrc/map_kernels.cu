@@ -788,9 +788,18 @@ cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
   return configure_pair<MG_FAMILY_CTF, 1, 2>(smem);
 }
 
+// env count from which the 64-register allocation (8 CTAs per SM) is used; MG_MAP_MINB8_FROM overrides it for experiments
+static long long minb8_from() {
+  static const long long v = [] { const char* e = std::getenv("MG_MAP_MINB8_FROM"); return e ? std::atoll(e) : 262144ll; }();
+  return v;
+}
+
 template <int FAMILY, int MODE, int STEPV>
 static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
-  return p.N >= 262144 ? launch_one<FAMILY, MODE, 8, STEPV>(p, st) : launch_one<FAMILY, MODE, 1, STEPV>(p, st);
+  // Maze partial-view mode is issue-bound: as soon as the uncapped allocation (5 CTAs per SM) would need a second wave
+  // (148 * 5 * 128 envs) the 8-CTA one wins (131 072 envs: 11.3 -> 10.1 us); the other modes switch at 256 K envs
+  const long long from = (FAMILY == MG_FAMILY_MAZE && p.view_V && !std::getenv("MG_MAP_MINB8_FROM")) ? 148ll * 5 * kMapE + 1 : minb8_from();
+  return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV>(p, st) : launch_one<FAMILY, MODE, 1, STEPV>(p, st);
 }
 
 template <int MODE>
