@@ -66,6 +66,51 @@ def _worker(conn, seed):
         conn.send((obs, rew, term, trunc))
 
 
+def _other_families(seconds):
+    """Single-process step rates of the reference's CtF (2v2, RwPolicy reds, each observation option) and Maze (13x13 test board
+    and a 64x64 map) envs, and the cost of one `render()` call (tile cache warm) - context for BASELINE configs 3 and 4."""
+    import tempfile
+
+    import ref_harness as rh
+    rh.import_reference()
+    from gym_multigrid.envs.ctf import CtFMvNEnv
+    from gym_multigrid.envs.maze import MazeSingleAgentEnv
+    from gym_multigrid.policy.ctf.heuristic import RwPolicy
+    assets = "/root/reference/tests/assets"
+    out = {}
+
+    def rate(env, sample, seconds):
+        env.reset(seed=0)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            _, _, term, trunc, _ = env.step(sample())
+            n += 1
+            if term or trunc:
+                env.reset()
+        return n / (time.perf_counter() - t0)
+
+    rng = np.random.default_rng(0)
+    for opt in ("map", "flattened", "positional"):
+        env = CtFMvNEnv(os.path.join(assets, "board.txt"), num_blue_agents=2, num_red_agents=2, enemy_policies=RwPolicy(), observation_option=opt)
+        out[f"ctf_2v2_{opt}_env_steps_per_s"] = rate(env, lambda: [int(a) for a in rng.integers(0, 5, size=2)], seconds)
+    env.reset(seed=0); env.render()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        env.step([int(a) for a in rng.integers(0, 5, size=2)]); env.render()
+    out["ctf_2v2_step_plus_render_per_s"] = 20 / (time.perf_counter() - t0)
+    np.random.seed(0)
+    env = MazeSingleAgentEnv(os.path.join(assets, "board_maze.txt"), observation_option="map")
+    out["maze_13x13_env_steps_per_s"] = rate(env, lambda: int(rng.integers(0, 5)), seconds)
+    m = (np.random.default_rng(0).random((64, 64)) < 0.2).astype(np.int64) * 3
+    m[5, 7] = 2
+    tmp = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
+    np.savetxt(tmp.name, m.T, fmt="%d")
+    env = MazeSingleAgentEnv(tmp.name, observation_option="map")
+    out["maze_64x64_env_steps_per_s"] = rate(env, lambda: int(rng.integers(0, 5)), seconds)
+    os.unlink(tmp.name)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=3.0)
@@ -95,7 +140,8 @@ def main():
         p.send(None)
     print(json.dumps({"env": ENV_ID, "impl": "unmodified Python reference under oracle/refshim", "cores": args.workers,
                       "single_process_env_steps_per_s": single, "independent_processes_env_steps_per_s": indep,
-                      "lockstep_pipes_env_steps_per_s": lockstep, "seconds_each": args.seconds}))
+                      "lockstep_pipes_env_steps_per_s": lockstep, "seconds_each": args.seconds,
+                      "other_families_single_process": _other_families(args.seconds)}))
 
 
 if __name__ == "__main__":
