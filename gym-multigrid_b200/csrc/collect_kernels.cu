@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
   //      warps [E/32, ..): meanwhile expand the PRE-step grid (only the <= 3A cells a step writes can change;
   //      they are patched below), which takes Grid.encode off the critical path of the tile.
   constexpr bool OVERLAP = (THREADS - E) >= 64;
+  // early observation store: 70 % of a tile's output bytes (the pre-step encoding, produced by warps [E/32, ..) while the env threads
+  // walk their agents) go out during the agent loop instead of after it; full tiles with a 16-byte aligned obs pointer only
+  const bool early = OVERLAP && p.early_obs && p.obs && p.obs_bulk_ok && n_here == E && !p.timeline;
   const int n16 = (int)(grid_bytes / 16);
   bool done = false;
   int err = 0, nchg = 0;
@@ -318,6 +321,15 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
     done = p.autoreset && (term || trunc);
   } else if (OVERLAP && tid >= E && p.obs) {
     expand_tile<THREADS - E>(s.grid, s.obs, n16, tid - E);
+    if (early) {  // the slab leaves NOW, under the agent loop; cells the step changes are patched in place below
+      fence_proxy_async_smem();
+      named_bar_sync(1, THREADS - E);
+      if (tid == E) {
+        tma_store_1d(p.obs + e0 * 3 * cells, s.obs, (uint32_t)E * 3 * cells);
+        tma_commit();
+        tma_wait_all();   // performed, not just read: the patches below go to the same addresses
+      }
+    }
   }
   if (tl && tid == 0) tl[2] = globaltimer_ns();
   if (tid < E) s.done[tid] = done;
@@ -329,10 +341,14 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
     } else if (tid < n_here) {  // patch the cells this env's step wrote
       const uint8_t* g = s.grid + (size_t)tid * cells;
       uint8_t* o = s.obs + (size_t)tid * cells * 3;
+      // early store: the same three bytes also go to the slab already in global memory - unless the tile is about to be
+      // re-encoded and stored again as a whole (autoreset), which must not race with these stores
+      uint8_t* go = (early && !any_done) ? p.obs + (e0 + tid) * 3 * cells : nullptr;
       for (int k = 0; k < nchg; ++k) {
         const int idx = chg[k];
         const uint8_t c = g[idx];
         o[3 * idx] = c & 3; o[3 * idx + 1] = (c >> 2) & 15; o[3 * idx + 2] = c >> 6;
+        if (go) { go[3 * idx] = c & 3; go[3 * idx + 1] = (c >> 2) & 15; go[3 * idx + 2] = c >> 6; }
       }
     }
   }
@@ -379,7 +395,8 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
   __syncthreads();
   if (tl && tid == 0) tl[4] = globaltimer_ns();
   const uint32_t obs_bytes = (uint32_t)n_here * 3 * cells;
-  const uint32_t obs_bulk = (p.obs && p.obs_bulk_ok) ? (obs_bytes & ~15u) : 0u;
+  const bool obs_done = early && !any_done;   // the slab went out early and was patched in place
+  const uint32_t obs_bulk = (p.obs && p.obs_bulk_ok && !obs_done) ? (obs_bytes & ~15u) : 0u;
   if (tid == 0) {
     if (obs_bulk) tma_store_1d(p.obs + e0 * 3 * cells, s.obs, obs_bulk);
     tma_store_1d(p.grid + e0 * cells, s.grid, grid_bytes);
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
     }
     tma_commit();
   }
-  if (p.obs) copy_out_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, obs_bulk, obs_bytes, tid);
+  if (p.obs && !obs_done) copy_out_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, obs_bulk, obs_bytes, tid);
   if (!io_bulk) {
     for (int i = tid; i < n_here * A; i += THREADS) p.rewards[e0 * A + i] = s.rew[i];
     for (int i = tid; i < n_here; i += THREADS) { p.terminated[e0 + i] = s.term[i]; p.truncated[e0 + i] = s.trunc[i]; }

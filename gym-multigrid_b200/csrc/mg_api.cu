@@ -214,6 +214,7 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   }
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.rng_mode = 1;
+  { const char* v = std::getenv("MG_EARLY_OBS"); p.early_obs = !(v && v[0] == '0'); }   // A/B switch for the early observation store
 
   if ((ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess) { delete env; return cuda_fail(nullptr, "cudaMalloc(status)", ce); }
   if ((ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) { cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "cudaMemset(status)", ce); }

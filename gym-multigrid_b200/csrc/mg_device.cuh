@@ -61,6 +61,7 @@ struct CollectParams {
   int obs_bulk_ok;        // obs base pointer is 16-byte aligned
   int io_bulk_ok;         // actions / rewards / terminated / truncated pointers are 16-byte aligned
   unsigned long long* timeline;  // optional [tiles][8] per-CTA phase timestamps (globaltimer ns), profiling only
+  int early_obs;          // 1 = full tiles store the pre-step observation slab while the agents are stepped and patch the <= 3A changed cells in place
 };
 
 // ------------------------------------------------------------------------ Philox4x32-10
@@ -151,6 +152,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       "}\n" ::"r"(smem_u32(bar)), "r"(phase)
       : "memory");
 }
+// barrier over a subset of the CTA's warps (id 1..15; `count` threads, a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // global -> shared bulk copy (TMA, 1-D).  16-byte aligned addresses, size % 16 == 0.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
