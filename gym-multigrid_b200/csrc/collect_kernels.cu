@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
     for (int i = tid; i < n_here * A; i += THREADS) s.act[i] = p.actions[e0 * A + i];
   if (MODE == 0)
     for (int i = tid; i < n_here * A; i += THREADS) s.ord[i] = p.order[e0 * A + i];
-  __syncthreads();
+  if (!io_bulk || MODE == 0) __syncthreads();   // only the hand-copied inputs need it: everything else arrives on the mbarrier
   mbar_wait(&bar, 0);
   if (tl && tid == 0) tl[1] = globaltimer_ns();
 
