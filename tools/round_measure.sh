@@ -13,3 +13,7 @@ bash tools/ncu_families.sh ${tag} ctf maze view_maze view_collect toroid wildfir
 python tools/profile_collect.py > gpurun_out/plain_collect.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:collect_step -s 20 -c 1 -f -o gpurun_out/prof_collect_${tag} python tools/profile_collect.py > gpurun_out/ncu_collect.log 2>&1
 echo "collect: rc=$?"
+# steady-state DRAM bytes per launch of the Collect step (roofline.traffic): application replay, no cache flush, launches 30-37 of a rotation
+timeout 200 ncu --replay-mode application --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+    -k regex:collect_step -s 30 -c 8 python tools/profile_collect.py 2>&1 | grep -v "^==PROF==" > gpurun_out/${tag}_ncu_collect_steady_traffic.txt
+echo "steady traffic: $(grep -c dram__bytes_read gpurun_out/${tag}_ncu_collect_steady_traffic.txt) launches"
