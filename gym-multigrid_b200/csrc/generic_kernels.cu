@@ -12,10 +12,10 @@
 namespace mg {
 
 // One CTA = a tile of 8 envs.  The tile's two cell planes and agent positions are staged in shared memory (coalesced
-// loads); warp 0 steps the envs, one lane per env, in the given agent order; then all threads encode
-// [env][agent][cell] -> 6 bytes into shared memory and the tile's contiguous observation slab leaves as ONE TMA bulk
+// loads); warp 0 steps the envs, one lane per env, in the given agent order; then all 256 threads encode
+// [env][agent][cell] -> 6 bytes into shared memory (two cells per thread: three 32-bit stores per agent) and the tile's contiguous observation slab leaves as ONE TMA bulk
 // store (full-line writes); the cell planes are written back coalesced.
-constexpr int kGenE = 8, kGenThreads = 128;
+constexpr int kGenE = 8, kGenThreads = 256;
 constexpr int G_EMPTY = 1, G_DOOR = 4, G_GOAL = 8, G_AGENT = 10;  // DefaultWorld.OBJECT_TO_IDX (world.py:37-51)
 
 struct GenSmem {
@@ -32,21 +32,45 @@ __host__ __device__ inline size_t gen_smem_bytes(int A, int cells) {
 // all threads: encode_for_agents (grid.py:254-284) of the tile's envs (those with sel[el] != 0 when sel is given) into s.obs
 __device__ __forceinline__ void generic_encode_tile(const GenericParams& p, const GenSmem& s, int n_here, const uint8_t* sel, int tid) {
   const int cells = p.cells, A = p.A;
+  auto enc = [&](int idx, uint32_t& w0, uint32_t& w1, uint32_t& w2, bool& agent) {   // the three 16-bit halves of one cell's 6 bytes
+    const uint32_t c = s.cell[idx], st = s.state[idx];
+    const uint32_t type = c & 15u;
+    w0 = type | ((c >> 4) << 8);
+    w1 = type == G_DOOR ? st : 0u;                     // Door.encode object.py:238-259
+    agent = type == G_AGENT;
+    w2 = agent ? (st & 3u) : 0u;                       // Agent.encode agent.py:127-165 (carrying is always None here)
+  };
+  if ((cells & 1) == 0) {   // two cells per thread: 12 bytes per agent as three 32-bit stores (6-byte records, 4-byte aligned pairs)
+    const int half = cells / 2, total = n_here * half;
+    for (int q = tid; q < total; q += kGenThreads) {
+      const int el = (int)__umulhi((uint32_t)q, p.half_magic);
+      if (sel && !sel[el]) continue;
+      const int i = 2 * (q - el * half), idx = el * cells + i;
+      uint32_t a0, a1, a2, b0, b1, b2;
+      bool aga, agb;
+      enc(idx, a0, a1, a2, aga); enc(idx + 1, b0, b1, b2, agb);
+      uint32_t* o = reinterpret_cast<uint32_t*>(s.obs + ((size_t)el * A * cells + i) * 6);
+      for (int k = 0; k < A; ++k) {
+        const int self = s.pos[(el * A + k) * 2] * p.H + s.pos[(el * A + k) * 2 + 1];                // the is_self plane
+        const uint32_t sa = (aga && i == self) ? 0x100u : 0u, sb = (agb && i + 1 == self) ? 0x100u : 0u;
+        o[0] = a0 | (a1 << 16); o[1] = (a2 | sa) | (b0 << 16); o[2] = b1 | ((b2 | sb) << 16);
+        o += (cells * 6) / 4;
+      }
+    }
+    return;
+  }
   const int total = n_here * cells;
   for (int idx = tid; idx < total; idx += kGenThreads) {   // one thread per (env, cell): decoded once, written for every agent
     const int el = (int)__umulhi((uint32_t)idx, p.cells_magic);
     if (sel && !sel[el]) continue;
     const int i = idx - el * cells;
-    const uint32_t c = s.cell[idx], st = s.state[idx];
-    const uint32_t type = c & 15u;
-    const uint16_t w0 = (uint16_t)(type | ((c >> 4) << 8));
-    const uint16_t w1 = (uint16_t)(type == G_DOOR ? st : 0u);                 // Door.encode object.py:238-259
-    const bool agent = type == G_AGENT;
-    const uint16_t w2 = (uint16_t)(agent ? (st & 3u) : 0u);                   // Agent.encode agent.py:127-165 (carrying is always None here)
+    uint32_t w0, w1, w2;
+    bool agent;
+    enc(idx, w0, w1, w2, agent);
     uint16_t* o = reinterpret_cast<uint16_t*>(s.obs + ((size_t)el * A * cells + i) * 6);
     for (int k = 0; k < A; ++k) {
       const bool self = agent && i == s.pos[(el * A + k) * 2] * p.H + s.pos[(el * A + k) * 2 + 1];   // the is_self plane
-      o[0] = w0; o[1] = w1; o[2] = (uint16_t)(w2 | (self ? 0x100u : 0u));
+      o[0] = (uint16_t)w0; o[1] = (uint16_t)w1; o[2] = (uint16_t)(w2 | (self ? 0x100u : 0u));
       o += cells * 3;
     }
   }

@@ -7,6 +7,7 @@ namespace mg {
 
 struct GenericParams {
   uint32_t cells_magic, per_env_magic;   // floor(2^32 / cells) + 1, floor(2^32 / (A * cells)) + 1 (tile-local indices < 2^16)
+  uint32_t half_magic;                   // floor(2^32 / (cells / 2)) + 1 (even cell counts: the encode handles two cells per thread)
   int W, H, cells, A, max_steps, autoreset, op;   // op: 0 = reset(mask) from the snapshot planes, 1 = step
   long long N;
   unsigned long long env_id_base, seed;

@@ -704,6 +704,7 @@ extern "C" int mg_create_generic(const mg_generic_config* cfg, int device, mg_en
   std::memset(&p, 0, sizeof p);
   p.W = W; p.H = H; p.cells = cells; p.A = A; p.max_steps = cfg->max_steps; p.autoreset = cfg->autoreset != 0;
   p.cells_magic = (uint32_t)(4294967296ull / (unsigned)cells) + 1u; p.per_env_magic = (uint32_t)(4294967296ull / (unsigned)(A * cells)) + 1u;
+  p.half_magic = cells >= 2 ? (uint32_t)(4294967296ull / (unsigned)(cells / 2)) + 1u : 0u;
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed; p.status = env->d_status;
   *out = env;
   return 0;
