@@ -115,6 +115,18 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const __grid_const
   pdl_launch_dependents();
   pdl_wait();
   // ---- stage the tile (reset: from the episode-start snapshot planes of the selected envs)
+  // full step tiles whose plane slabs are 16-byte multiples move as 128-bit words (e0 * cells is then a multiple of 16 too)
+  const bool vec = p.op == 1 && n_here == kGenE && ((kGenE * cells) & 15) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(p.gcell) | reinterpret_cast<uintptr_t>(p.gstate)) & 15) == 0;
+  if (vec) {
+    const int n16 = kGenE * cells / 16;
+    const uint4* gc4 = reinterpret_cast<const uint4*>(p.gcell + e0 * cells);
+    const uint4* gs4 = reinterpret_cast<const uint4*>(p.gstate + e0 * cells);
+    for (int i = tid; i < 2 * n16; i += kGenThreads) {
+      if (i < n16) reinterpret_cast<uint4*>(s.cell)[i] = gc4[i];
+      else reinterpret_cast<uint4*>(s.state)[i - n16] = gs4[i - n16];
+    }
+  } else
   for (int i = tid; i < n_here * cells; i += kGenThreads) {
     const int el = (int)__umulhi((uint32_t)i, p.cells_magic);
     const bool from_init = p.op == 0 && (!p.reset_mask || p.reset_mask[e0 + el]);
@@ -199,6 +211,15 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const __grid_const
   }
   if (tid < n_here) p.hdr[e0 + tid] = h;
   // ---- state write-back (coalesced) and the observation
+  if (vec) {
+    const int n16 = kGenE * cells / 16;
+    uint4* gc4 = reinterpret_cast<uint4*>(p.gcell + e0 * cells);
+    uint4* gs4 = reinterpret_cast<uint4*>(p.gstate + e0 * cells);
+    for (int i = tid; i < 2 * n16; i += kGenThreads) {
+      if (i < n16) gc4[i] = reinterpret_cast<const uint4*>(s.cell)[i];
+      else gs4[i - n16] = reinterpret_cast<const uint4*>(s.state)[i - n16];
+    }
+  } else
   for (int i = tid; i < n_here * cells; i += kGenThreads) { p.gcell[e0 * cells + i] = s.cell[i]; p.gstate[e0 * cells + i] = s.state[i]; }
   for (int i = tid; i < n_here * A * 2; i += kGenThreads) p.pos[e0 * A * 2 + i] = s.pos[i];
   if (p.obs) {
