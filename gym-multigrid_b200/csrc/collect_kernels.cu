@@ -361,7 +361,11 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
         if (!s.done[j]) continue;
         uint8_t* dst = p.final_obs + (e0 + j) * 3 * cells;
         const uint8_t* src = s.obs + (size_t)j * 3 * cells;
-        for (int i = tid; i < 3 * cells; i += THREADS) dst[i] = src[i];
+        if (((3 * cells) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.final_obs) & 3) == 0) {   // 32-bit words when every env's slab is word-aligned
+          for (int i = tid; i < 3 * cells / 4; i += THREADS) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+        } else {
+          for (int i = tid; i < 3 * cells; i += THREADS) dst[i] = src[i];
+        }
       }
       __syncthreads();
     }
