@@ -73,9 +73,22 @@ def make_generic_vec(num_envs: int, width: int, **kwargs):
     return GenericVecEnv(num_envs, width, **kwargs)
 
 
+_POLICIES = ("CtfPolicy", "RwPolicy", "DestinationPolicy", "FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy")
+
+
 def __getattr__(name):
-    """Reference-style single-env classes (same names as gym_multigrid.envs): imported lazily, they need torch + CUDA."""
-    if name in ("MazeSingleAgentEnv", "CtFMvNEnv", "Ctf1v1Env", "MazeActions", "CtfActions", "RwPolicy"):
+    """Reference-style single-env classes (same names as gym_multigrid.envs; imported lazily, they need torch + CUDA) and the
+    host-side pieces user code imports beside them: action enums, world tables, the scripted CtF opponents."""
+    if name in ("MazeSingleAgentEnv", "CtFMvNEnv", "Ctf1v1Env"):
         from . import single_env
         return getattr(single_env, name)
+    if name in ("MazeActions", "CtfActions", "CollectActions"):
+        from . import actions
+        return getattr(actions, name)
+    if name in ("DefaultWorld", "CollectWorld", "CtfWorld", "MazeWorld"):
+        from . import world
+        return getattr(world, name)
+    if name in _POLICIES:
+        from .policy.ctf import heuristic
+        return getattr(heuristic, name)
     raise AttributeError(f"module 'gym_multigrid_b200' has no attribute {name!r}")

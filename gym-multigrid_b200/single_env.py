@@ -1,28 +1,18 @@
 """Reference-style single-env adaptors for the map families: the reference's class names, constructor kwargs and
 return types (`MazeSingleAgentEnv` maze.py:26-377, `CtFMvNEnv` ctf.py:657-1433, `Ctf1v1Env` ctf.py:50-654) over ONE env
 of the batched CUDA classes - so that code written against the reference (its tests, `scripts/main_mvn_ctf_rl.py`) runs
-unchanged apart from the import.  Everything is computed by the same kernels as the vector envs; rendering is out of scope
-(`render()` is a no-op, `render_mode` is accepted and ignored)."""
+unchanged apart from the import.  Everything is computed by the same kernels as the vector envs; `render()` returns the
+rgb_array frame whatever `render_mode` says (there is no `human` window).  Red agents: the built-in RwPolicy on the device,
+or the reference's `enemy_policies` objects (`policy/ctf/heuristic.py` has this package's own) deciding on the host."""
 from __future__ import annotations
-
-import enum
 
 import numpy as np
 import torch
 
+from .actions import CtfActions, MazeActions  # noqa: F401
 from .map_env import Ctf1v1VecEnv, CtfVecEnv, MazeVecEnv
+from .policy.ctf.heuristic import RwPolicy
 from .spaces import Discrete, MultiDiscrete
-
-
-class MazeActions(enum.IntEnum):   # core/agent.py:54-67 (CtfActions has the same members)
-    stay = 0
-    left = 1
-    down = 2
-    right = 3
-    up = 4
-
-
-CtfActions = MazeActions
 
 
 class _SingleMapEnv:
@@ -78,20 +68,6 @@ class MazeSingleAgentEnv(_SingleMapEnv):
         if self.vec.status() & 8:
             raise ValueError(f"Invalid action: {action}")       # maze.py:286
         return obs[0].cpu().numpy(), float(rew[0]), bool(term[0]), bool(trunc[0]), self._info()
-
-
-class RwPolicy:
-    """policy/ctf/heuristic.py:40-72: uniform random action.  As an `enemy_policies` entry it selects the built-in opponent, whose
-    draws come from the env's Philox stream on the device; `act` exists for callers that drive it by hand."""
-    name = "rw"
-
-    def __init__(self, action_set=None, random_generator=None):
-        self.action_set, self.random_generator = action_set or MazeActions, random_generator
-
-    def act(self, observation=None, curr_pos=None) -> int:
-        if self.random_generator is None:
-            self.random_generator = np.random.default_rng()
-        return int(self.random_generator.integers(0, len(self.action_set)))
 
 
 class CtFMvNEnv(_SingleMapEnv):

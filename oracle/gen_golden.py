@@ -298,9 +298,76 @@ def gen_generic():
               f"{os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_policies():
+    """Decisions of the reference's scripted CtF opponents (policy/ctf/heuristic.py) and routes of its A* (policy/ctf/utils.py)
+    on recorded inputs.  Every policy x team is driven for a few hundred decisions with ONE seeded Generator, partly closed
+    loop (the agent makes the move it chose), so the actions pin the targets, the routes' tie-breaking and the order and kind of
+    every random draw; `tail` is a draw made after the last decision (the stream position)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    from replay import POLICY_NAMES, policy_maps, policy_observation
+    rh.import_reference()
+    from gym_multigrid.policy.ctf import heuristic as H
+    from gym_multigrid.policy.ctf.utils import a_star
+    maps = policy_maps()
+    out = {}
+    rng = np.random.default_rng(2024)
+    for name, fm in maps.items():
+        rows, cols = fm.shape
+        n = 260 if name != "walls" else 420
+        starts = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1)
+        ends = np.stack([rng.integers(0, rows, n), rng.integers(0, cols, n)], 1)
+        ends[:6] = starts[:6]                                         # start == end
+        paths = [np.array(a_star(tuple(s), tuple(e), fm), np.int64).reshape(-1, 2) for s, e in zip(starts, ends)]
+        out[f"astar_{name}_start"], out[f"astar_{name}_end"] = starts, ends
+        out[f"astar_{name}_len"] = np.array([len(p) for p in paths])
+        out[f"astar_{name}_cells"] = np.concatenate(paths)
+        print(f"a_star {name}: {n} routes, {sum(len(p) == 0 for p in paths)} without a route, longest {max(len(p) for p in paths)}")
+    moves = {0: (0, 0), 1: (0, -1), 2: (-1, 0), 3: (0, 1), 4: (1, 0)}
+    seed = 9000
+    for mname in ("board", "wide"):
+        fm = maps[mname]
+        rows, cols = fm.shape
+        for pname in POLICY_NAMES:
+            for ego in ("red", "blue"):
+                seed += 1
+                gen = np.random.Generator(np.random.PCG64(seed))
+                kw = dict(field_map=fm, random_generator=gen, ego_agent=ego, randomness=0.75 if ego == "red" else 0.6)
+                pol = getattr(H, pname)(**kw)
+                K, nb, nr = 320, 3, 2
+                cur = np.array([rng.integers(0, rows), rng.integers(0, cols)])
+                rec = dict(curr=[], blue=[], red=[], action=[])
+                blue = np.stack([rng.integers(0, rows, nb), rng.integers(0, cols, nb)], 1)
+                red = np.stack([rng.integers(0, rows, nr), rng.integers(0, cols, nr)], 1)
+                for k in range(K):
+                    if k % 40 == 0:                                   # a jump: fresh positions (on the border half of the time)
+                        border = getattr(pol, "border", [])
+                        cur = np.array(border[rng.integers(0, len(border))]) if len(border) and rng.random() < 0.5 else \
+                            np.array([rng.integers(0, rows), rng.integers(0, cols)])
+                    step = np.array([moves[int(a)] for a in rng.integers(0, 5, nb + nr)])
+                    blue = np.clip(blue + step[:nb], 0, [rows - 1, cols - 1])
+                    red = np.clip(red + step[nb:], 0, [rows - 1, cols - 1])
+                    (red if ego == "red" else blue)[0] = cur          # the controlled agent is the first of its team
+                    a = int(pol.act(policy_observation(fm, blue, red), tuple(cur)))
+                    for key, v in (("curr", cur), ("blue", blue), ("red", red), ("action", a)):
+                        rec[key].append(np.array(v))
+                    cur = np.clip(cur + moves[a], 0, [rows - 1, cols - 1])
+                stem = f"{mname}_{pname}_{ego}"
+                for key, v in rec.items():
+                    out[f"{stem}_{key}"] = np.stack(v).astype(np.int16)
+                out[f"{stem}_seed"] = np.array(seed)
+                out[f"{stem}_tail"] = np.array(gen.integers(0, 2 ** 31))
+                out[f"{stem}_randomness"] = np.array(kw["randomness"])
+                if hasattr(pol, "border"):
+                    out[f"{stem}_border"] = np.array(pol.border, np.int64).reshape(-1, 2)
+                print(f"{stem}: {K} decisions, action histogram {np.bincount(out[f'{stem}_action'], minlength=5).tolist()}")
+    path_out = os.path.join(OUT, "ctf_policies.npz")
+    np.savez_compressed(path_out, **out)
+    print(f"ctf_policies: {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat", "policies"]
     if "collect" in which:
         gen_collect()
     if "maze" in which:
@@ -323,3 +390,5 @@ if __name__ == "__main__":
         gen_generic()
     if "generic_partial" in which:
         gen_generic_partial()
+    if "policies" in which:
+        gen_policies()

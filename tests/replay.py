@@ -54,3 +54,33 @@ def expected(g, t, tile=1):
     if tile > 1:
         out = {k: np.concatenate([v] * tile) for k, v in out.items()}
     return out
+
+
+# --------------------------------------------------------------------------- CtF heuristic policies (tests/test_policies.py)
+POLICY_NAMES = ("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy")
+
+
+def policy_maps():
+    """Field maps the policy fixtures were recorded on: the reference's 10x10 board (from the CtF fixture), a 14x11 map
+    with irregular territories and obstacles, and - for `a_star` alone - a 12x9 map that also holds the value 8, the
+    only one the reference's A* treats as blocking (policy/ctf/utils.py:73)."""
+    board = load_golden("ctf_2v2")["field_map"].astype(np.float64)
+    rng = np.random.default_rng(77)
+    wide = np.where(np.arange(14)[:, None] + rng.integers(-2, 3, size=(14, 11)) < 7, 1.0, 0.0)
+    wide[rng.random(wide.shape) < 0.08] = 6.0
+    wide[1, 2], wide[12, 8] = 5.0, 4.0
+    walls = np.zeros((12, 9))
+    walls[rng.random(walls.shape) < 0.28] = 8.0
+    walls[3:6, 4] = 8.0
+    walls[9:12, 6], walls[9, 6:9] = 8.0, 8.0        # (10..11, 7..8) is sealed off: routes into it do not exist
+    return {"board": board, "wide": wide, "walls": walls}
+
+
+def policy_observation(field_map, blue, red, terminated=None):
+    """The dictionary `CtFMvNEnv._get_dict_obs` hands to `policy.act` (ctf.py:1112-1135) for agents at `blue` / `red`."""
+    cells = lambda v: np.array(list(zip(*np.where(field_map == v)))).flatten()   # noqa: E731
+    blue, red = np.asarray(blue), np.asarray(red)
+    return {"blue_agent": blue.flatten(), "red_agent": red.flatten(),
+            "blue_flag": np.array(list(zip(*np.where(field_map == 4)))[0]), "red_flag": np.array(list(zip(*np.where(field_map == 5)))[0]),
+            "blue_territory": cells(0), "red_territory": cells(1), "obstacle": cells(6),
+            "terminated_agents": np.zeros(len(blue) + len(red), np.int64) if terminated is None else np.asarray(terminated)}

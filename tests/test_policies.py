@@ -1,0 +1,162 @@
+"""Scripted CtF opponents (`gym_multigrid_b200.policy.ctf`) against the unmodified reference classes
+(policy/ctf/heuristic.py, policy/ctf/utils.py): the recorded decisions of `tests/golden/ctf_policies.npz`
+(`oracle/gen_golden.py policies`) and, where /root/reference exists, a live differential run on fresh random inputs.
+Host-side code: no GPU involved (the policies are callers of the CUDA step)."""
+import numpy as np
+import pytest
+
+from replay import POLICY_NAMES, load_golden, policy_maps, policy_observation
+
+from gym_multigrid_b200.policy.ctf import heuristic as H
+from gym_multigrid_b200.policy.ctf.utils import a_star, closest_area_pos, manhattan_distance, position_in_positions
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return load_golden("ctf_policies")
+
+
+@pytest.fixture(scope="module")
+def maps():
+    return policy_maps()
+
+
+@pytest.mark.parametrize("mname", ["board", "wide", "walls"])
+def test_a_star_routes_are_the_reference_routes(golden, maps, mname):
+    """Cell for cell - tie-breaking included; `walls` holds the blocking value 8 and pairs without any route."""
+    g, fm = golden, maps[mname]
+    cells, k = g[f"astar_{mname}_cells"], 0
+    none = 0
+    for s, e, n in zip(g[f"astar_{mname}_start"], g[f"astar_{mname}_end"], g[f"astar_{mname}_len"]):
+        path = a_star(tuple(s), tuple(e), fm)
+        assert np.array_equal(np.array(path, np.int64).reshape(-1, 2), cells[k:k + n]), (mname, s, e)
+        if n:
+            assert path[0] == tuple(s) and path[-1] == tuple(e) and len(path) >= manhattan_distance(s, e) + 1
+        none += n == 0
+        k += n
+    assert k == len(cells) and (none > 0) == (mname == "walls")
+
+
+def test_a_star_ignores_ctf_obstacles(maps):
+    """policy/ctf/utils.py:73 blocks on the value 8 only; CtF obstacles are 6 (core/world.py:66-79) and are walked through."""
+    fm = maps["board"]
+    assert (fm == 6).sum() == 4 and fm[4, 4] == 6 and fm[5, 4] == 6
+    path = a_star((3, 4), (6, 4), fm)
+    assert path == [(3, 4), (4, 4), (5, 4), (6, 4)]
+    assert a_star((2, 2), (2, 2), fm) == [(2, 2)]
+    assert a_star((0, 0), (99, 0), fm) == []                     # a target outside the map: no route
+
+
+def _replay(golden, maps, mname, pname, ego, **extra):
+    stem = f"{mname}_{pname}_{ego}"
+    gen = np.random.Generator(np.random.PCG64(int(golden[f"{stem}_seed"])))
+    pol = getattr(H, pname)(field_map=maps[mname], random_generator=gen, ego_agent=ego, randomness=float(golden[f"{stem}_randomness"]), **extra)
+    got = [int(pol.act(policy_observation(maps[mname], b, r), tuple(c)))
+           for c, b, r in zip(golden[f"{stem}_curr"], golden[f"{stem}_blue"], golden[f"{stem}_red"])]
+    return pol, gen, got
+
+
+@pytest.mark.parametrize("ego", ["red", "blue"])
+@pytest.mark.parametrize("pname", POLICY_NAMES)
+@pytest.mark.parametrize("mname", ["board", "wide"])
+def test_policy_decisions_and_rng_stream(golden, maps, mname, pname, ego):
+    """320 recorded decisions per policy x team x map from ONE seeded generator: equal actions need equal targets, equal routes
+    and the same draws in the same order; `tail` checks where the stream stands afterwards."""
+    stem = f"{mname}_{pname}_{ego}"
+    pol, gen, got = _replay(golden, maps, mname, pname, ego)
+    want = golden[f"{stem}_action"].tolist()
+    assert got == want, next(i for i, (a, b) in enumerate(zip(got, want)) if a != b)
+    assert int(gen.integers(0, 2 ** 31)) == int(golden[f"{stem}_tail"])
+    if f"{stem}_border" in golden:
+        assert np.array_equal(np.array(pol.border, np.int64).reshape(-1, 2), golden[f"{stem}_border"])
+
+
+def test_interface_mirrors_the_reference():
+    """Names, defaults and attributes user code touches (heuristic.py:51-67, 84-106, 189-214, 284-319; ctf.py:785-826)."""
+    from gym_multigrid_b200.actions import CtfActions
+    from gym_multigrid_b200.world import CtfWorld
+    assert [H.RwPolicy().name, H.FightPolicy().name, H.CapturePolicy().name, H.PatrolPolicy().name, H.PatrolFightPolicy().name] == \
+        ["rw", "fight", "capture", "patrol", "patrol_fight"]
+    p = H.FightPolicy()
+    assert p.field_map is None and p.action_set is CtfActions and p.randomness == 0.75 and p.ego_agent == "red"
+    assert isinstance(p.random_generator, np.random.Generator)
+    assert issubclass(H.PatrolFightPolicy, H.PatrolPolicy) and issubclass(H.PatrolPolicy, H.DestinationPolicy)
+    assert issubclass(H.DestinationPolicy, H.CtfPolicy) and issubclass(H.RwPolicy, H.CtfPolicy)
+    assert CtfWorld.OBJECT_TO_IDX["obstacle"] == 6 and [a.name for a in CtfActions] == ["stay", "left", "down", "right", "up"]
+    assert 0 <= int(H.RwPolicy(random_generator=np.random.default_rng(0)).act()) < 5
+    with pytest.raises(NotImplementedError):
+        H.CtfPolicy().act({}, (0, 0))
+    # a patrol policy built without a map has an empty border for good and fails on its first decision (heuristic.py:319, utils/map.py:61)
+    q = H.PatrolPolicy()
+    assert q.border == [] and q.obstacle == []
+    with pytest.raises(ValueError):
+        q.get_target({}, (1, 1))
+    assert closest_area_pos((0, 0), [(3, 0), (0, 3), (1, 1), (1, 1)]) == (1, 1)
+    assert closest_area_pos((0, 0), [(0, 3), (3, 0)]) == (0, 3)                   # first of equals
+    assert position_in_positions((1, 2), [(0, 0), (1, 2)]) and not position_in_positions((2, 1), [(0, 0), (1, 2)])
+
+
+def test_route_cache_follows_the_map(maps):
+    """The env installs `field_map` after construction (ctf.py:796-799); memoised routes belong to one map object."""
+    fm = maps["walls"].copy()
+    pol = H.CapturePolicy(field_map=fm, random_generator=np.random.default_rng(0), randomness=1.0)
+    obs = {"blue_flag": np.array([2, 3])}
+    first = pol._next_cell((3, 0), (2, 3))
+    assert first == (3, 1) == tuple(a_star((3, 0), (2, 3), fm)[1]) and pol._next_cell((3, 0), (2, 3)) is first   # around the 8s
+    assert int(pol.act(obs, (3, 0))) == 3                                        # right = (0, +1)
+    open_map = np.zeros_like(fm)
+    pol.field_map = open_map
+    assert pol._next_cell((3, 0), (2, 3)) == tuple(a_star((3, 0), (2, 3), open_map)[1]) == (2, 0)
+    assert int(pol.act(obs, (3, 0))) == 2                                        # down = (-1, 0)
+
+
+def _reference_heuristic():
+    import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("needs /root/reference (build container only)")
+    rh.import_reference()
+    from gym_multigrid.policy.ctf import heuristic, utils
+    return heuristic, utils
+
+
+def test_live_differential_against_the_reference(maps):
+    """Fresh random maps, team sizes and positions through both implementations with equally seeded generators."""
+    RH, RU = _reference_heuristic()
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        rows, cols = int(rng.integers(6, 15)), int(rng.integers(6, 15))
+        fm = np.where(np.arange(rows)[:, None] + rng.integers(-1, 2, size=(rows, cols)) < rows // 2, 1.0, 0.0)
+        fm[rng.random(fm.shape) < 0.1] = 6.0
+        fm[0, 0], fm[rows - 1, cols - 1] = 5.0, 4.0
+        blocked = fm.copy()
+        blocked[rng.random(fm.shape) < 0.2] = 8.0
+        for _ in range(60):
+            s, e = (int(rng.integers(0, rows)), int(rng.integers(0, cols))), (int(rng.integers(0, rows)), int(rng.integers(0, cols)))
+            assert [tuple(int(v) for v in p) for p in RU.a_star(s, e, blocked)] == a_star(s, e, blocked)
+        for pname in POLICY_NAMES:
+            for ego in ("red", "blue"):
+                ga, gb = (np.random.Generator(np.random.PCG64(100 + trial)) for _ in range(2))
+                kw = dict(field_map=fm, ego_agent=ego, randomness=float(rng.choice([0.75, 0.3, 1.0])))
+                try:
+                    ref = getattr(RH, pname)(random_generator=ga, **kw)
+                except Exception as exc:      # noqa: BLE001 - whatever the reference raises, ours must raise too
+                    with pytest.raises(type(exc)):
+                        getattr(H, pname)(random_generator=gb, **kw)
+                    continue
+                ours = getattr(H, pname)(random_generator=gb, **kw)
+                nb, nr = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+                for k in range(80):
+                    blue = np.stack([rng.integers(0, rows, nb), rng.integers(0, cols, nb)], 1)
+                    red = np.stack([rng.integers(0, rows, nr), rng.integers(0, cols, nr)], 1)
+                    border = getattr(ref, "border", [])
+                    cur = tuple(int(v) for v in border[rng.integers(0, len(border))]) if len(border) and k % 2 else \
+                        (int(rng.integers(0, rows)), int(rng.integers(0, cols)))
+                    obs = policy_observation(fm, blue, red)
+                    try:
+                        want = int(ref.act(obs, cur))
+                    except Exception as exc:  # noqa: BLE001
+                        with pytest.raises(type(exc)):
+                            ours.act(obs, cur)
+                        break
+                    assert int(ours.act(obs, cur)) == want, (trial, pname, ego, k)
+                assert ga.integers(0, 2 ** 31) == gb.integers(0, 2 ** 31)

@@ -196,3 +196,90 @@ def test_ctf_random_seeding(maps, cuda_device):
         runs.append(np.stack(traj))
     assert np.array_equal(runs[0], runs[1]) and not (runs[0].shape == runs[2].shape and np.array_equal(runs[0], runs[2]))
     env.close()
+
+
+_MOVES = {0: (0, 0), 1: (0, -1), 2: (-1, 0), 3: (0, 1), 4: (1, 0)}       # core/agent.py:54-67, ctf.py:1189-1199
+
+
+def _spy(policy):
+    """Record every decision of a policy object without changing it."""
+    policy.decisions = []
+    inner = policy.act
+
+    def act(observation, curr_pos):
+        a = inner(observation, curr_pos)
+        policy.decisions.append((tuple(int(v) for v in curr_pos), int(a)))
+        return a
+    policy.act = act
+    return policy
+
+
+def _policy_episode(env, red_policies):
+    """The loop of tests/test_ctf.py:110-121 (sampled blue actions, a frame per step) with one extra check per step: every red
+    agent either stood still (stay, blocked, defeated) or made exactly the move its policy decided on, from the cell the policy
+    was shown - i.e. the host-side decisions are the ones the CUDA step executed."""
+    nb = env.num_blue_agents
+    obs, _ = env.reset()
+    frames = [env.render()]
+    moved = steps = 0
+    while True:
+        before = env.agent_positions.astype(np.int64)
+        marks = [len(p.decisions) for p in red_policies]
+        obs, reward, terminated, truncated, info = env.step(env.action_space.sample())
+        frames.append(env.render())
+        steps += 1
+        after = env.agent_positions.astype(np.int64)
+        seen = {}
+        for k, p in enumerate(red_policies):
+            shown, a = p.decisions[marks[k] + seen.get(id(p), 0)]         # a shared policy object decides for its agents in order
+            seen[id(p)] = seen.get(id(p), 0) + 1
+            assert shown == tuple(before[nb + k].tolist())
+            delta = tuple((after[nb + k] - before[nb + k]).tolist())
+            assert delta in ((0, 0), _MOVES[a]), (steps, k, a, delta)
+            moved += delta != (0, 0)
+        if terminated or truncated:
+            break
+    assert steps <= env.max_steps and moved > 0 and isinstance(reward, float)
+    assert all(f.shape == frames[0].shape and f.dtype == np.uint8 for f in frames)
+    return steps
+
+
+def test_fight_policy(maps, cuda_device):
+    """tests/test_ctf.py:97-125: `enemy_policies=[FightPolicy(), RwPolicy()]` - the env fills in the map and its generator."""
+    from gym_multigrid_b200 import CtFMvNEnv
+    from gym_multigrid_b200.policy.ctf.heuristic import FightPolicy, RwPolicy
+    fight, rw = _spy(FightPolicy()), _spy(RwPolicy())
+    env = CtFMvNEnv(num_blue_agents=2, num_red_agents=2, map_path=maps["board.txt"], render_mode="human", observation_option="flattened",
+                    enemy_policies=[fight, rw])
+    assert fight.field_map is not None and fight.random_generator is env.np_random and rw.random_generator is env.np_random
+    _policy_episode(env, [fight, rw])
+    env.close()
+
+
+def test_capture_policy(maps, cuda_device):
+    """tests/test_ctf.py:127-155"""
+    from gym_multigrid_b200 import CtFMvNEnv
+    from gym_multigrid_b200.map_env import load_text_map
+    from gym_multigrid_b200.policy.ctf.heuristic import CapturePolicy, RwPolicy
+    field_map = load_text_map(maps["board.txt"])
+    capture, rw = _spy(CapturePolicy(field_map)), _spy(RwPolicy())
+    env = CtFMvNEnv(num_blue_agents=2, num_red_agents=2, map_path=maps["board.txt"], render_mode="human", observation_option="flattened",
+                    enemy_policies=[capture, rw])
+    assert capture.field_map is field_map                                      # a map given by the caller is kept (ctf.py:796-799)
+    _policy_episode(env, [capture, rw])
+    env.close()
+
+
+@pytest.mark.parametrize("cls_name", ["PatrolPolicy", "PatrolFightPolicy"])
+def test_patrol_policies(cls_name, maps, cuda_device):
+    """tests/test_ctf.py:157-215: one policy object shared by both red agents."""
+    from gym_multigrid_b200 import CtFMvNEnv
+    from gym_multigrid_b200.map_env import load_text_map
+    from gym_multigrid_b200.policy.ctf import heuristic
+    policy = _spy(getattr(heuristic, cls_name)(load_text_map(maps["board.txt"])))
+    assert len(policy.border) > 0
+    env = CtFMvNEnv(num_blue_agents=2, num_red_agents=2, map_path=maps["board.txt"], render_mode="human", observation_option="flattened",
+                    enemy_policies=policy)
+    steps = _policy_episode(env, [policy, policy])
+    assert len(policy.decisions) == 2 * steps
+    env.close()
