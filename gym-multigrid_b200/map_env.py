@@ -375,6 +375,8 @@ class CtfVecEnv(_MapVecEnv):
         return self._option_obs(), info
 
     def step(self, actions):
+        if self._enemy_policies is not None:
+            self._decide_red_actions()
         out = super().step(actions)
         if self.observation_option == "map":
             return out
@@ -394,6 +396,52 @@ class CtfVecEnv(_MapVecEnv):
         self._red_actions = t
         self._check(self._lib.mg_set_red_actions(self._h, _ptr(t)))
         return t
+
+    _enemy_policies = None
+
+    def set_enemy_policies(self, enemy_policies=None, random_generator=None):
+        """The reference's `enemy_policies` argument (ctf.py:666, 775-826) for every env of the batch: one policy for all red
+        agents or a list of `num_red_agents` of them - any object with `act(observation_dict, curr_pos) -> int` (the reference's
+        CtfPolicy interface; `policy/ctf/heuristic.py` has Fight / Capture / Patrol / PatrolFight).  `random_generator`,
+        `field_map` and `action_set` attributes are filled in as the reference's constructor does (`random_generator` and
+        `action_set` always, `field_map` when None).  The policies decide on the HOST, as in the reference: before each `step`
+        the positional observation is read back once, `act` is called per env and red agent in index order (env 0 first), and
+        the actions go to the kernel through `set_red_actions` - a per-step device sync, meant for SB3-sized batches.
+        None, or only None / RwPolicy entries = the built-in opponent drawn on the device.  Returns the list in use (or None)."""
+        from .actions import CtfActions
+        from .policy.ctf.heuristic import RwPolicy
+        nr = self.num_red
+        pols = list(enemy_policies) if isinstance(enemy_policies, (list, tuple)) else [enemy_policies] * nr
+        if len(pols) != nr:
+            raise AssertionError("len(enemy_policies) must equal num_red_agents")       # ctf.py:779
+        if all(p is None or type(p) is RwPolicy for p in pols):
+            self._enemy_policies = None
+            self.set_red_actions(None)
+            return None
+        gen = random_generator if random_generator is not None else np.random.default_rng()
+        pols = [RwPolicy() if p is None else p for p in pols]
+        for p in pols:
+            if hasattr(p, "random_generator"):
+                p.random_generator = gen
+            if getattr(p, "field_map", 0) is None:
+                p.field_map = np.asarray(self.field_map)
+            if hasattr(p, "action_set"):
+                p.action_set = CtfActions
+        self._enemy_policies = pols
+        self._red_host = np.zeros((self.num_envs, nr), np.int8)
+        self._red_buf = self.set_red_actions(self._red_host)
+        return pols
+
+    def _decide_red_actions(self):
+        d = {k: v.cpu().numpy() for k, v in self.positional_obs().items()}
+        pos = d["red_agent"].reshape(self.num_envs, self.num_red, 2)
+        for e in range(self.num_envs):
+            obs = {k: v[e] for k, v in d.items()}
+            if "is_red_agent_defeated" in obs:      # Ctf1v1Env hands a plain int there (ctf.py:395)
+                obs["is_red_agent_defeated"] = int(obs["is_red_agent_defeated"][0])
+            for k, p in enumerate(self._enemy_policies):
+                self._red_host[e, k] = int(p.act(obs, (int(pos[e, k, 0]), int(pos[e, k, 1]))))     # ctf.py:1297-1301
+        self._red_buf.copy_(torch.from_numpy(self._red_host))
 
     def game_stats(self):
         """The reference's `env.game_stats` (ctf.py:1068-1073) for every env, as bool CUDA tensors.  Cleared by reset - with

@@ -11,7 +11,7 @@ import torch
 
 from .actions import CtfActions, MazeActions  # noqa: F401
 from .map_env import Ctf1v1VecEnv, CtfVecEnv, MazeVecEnv
-from .policy.ctf.heuristic import RwPolicy
+from .policy.ctf.heuristic import RwPolicy  # noqa: F401  (re-exported beside the env classes, as gym_multigrid.envs users expect)
 from .spaces import Discrete, MultiDiscrete
 
 
@@ -93,35 +93,12 @@ class CtFMvNEnv(_SingleMapEnv):
     def _set_enemy_policies(self, enemy_policies, seed):
         """ctf.py:775-826: one policy for every red agent or a list of `num_red_agents` policies - any object with
         `act(observation_dict, curr_pos) -> int` (the reference's CtfPolicy interface).  None / RwPolicy entries only = the built-in
-        device opponent.  Otherwise every red action comes from the host: `act` is called with the positional observation dict
-        and the agent's position before each step, exactly where the reference calls it (ctf.py:1297-1301), and the actions reach
-        the kernel through `set_red_actions`; `random_generator`, `field_map` and `action_set` attributes are filled in as the
-        reference's constructor does."""
-        nr = self.vec.num_red
-        pols = list(enemy_policies) if isinstance(enemy_policies, (list, tuple)) else [enemy_policies] * nr
-        if len(pols) != nr:
-            raise AssertionError("len(enemy_policies) must equal num_red_agents")       # ctf.py:779
+        device opponent.  Otherwise every red action comes from the host (`CtfVecEnv.set_enemy_policies`): `act` is called with
+        the positional observation dict and the agent's position before each step, exactly where the reference calls it
+        (ctf.py:1297-1301), and the actions reach the kernel through `set_red_actions`; `random_generator`, `field_map` and
+        `action_set` attributes are filled in as the reference's constructor does (the generator is the env's `np_random`)."""
         self.np_random = np.random.default_rng(seed)
-        self._policies = None
-        if all(p is None or isinstance(p, RwPolicy) for p in pols):
-            return
-        self._policies = [RwPolicy() if p is None else p for p in pols]
-        for p in self._policies:
-            if hasattr(p, "random_generator"):
-                p.random_generator = self.np_random
-            if getattr(p, "field_map", 0) is None:
-                p.field_map = np.asarray(self.vec.field_map)
-            if hasattr(p, "action_set"):
-                p.action_set = self.actions_set
-        self._red_buf = self.vec.set_red_actions(np.zeros((1, nr), np.int8))
-
-    def _policy_actions(self):
-        if self._policies is None:
-            return
-        d = {k: v[0].cpu().numpy() for k, v in self.vec.positional_obs().items()}
-        pos = self.vec.agent_pos[0, self.vec.num_blue:].cpu().numpy()
-        acts = [int(p.act(d, tuple(int(v) for v in pos[k]))) for k, p in enumerate(self._policies)]
-        self._red_buf.copy_(torch.as_tensor(np.array(acts, np.int8).reshape(1, -1)))
+        self._policies = self.vec.set_enemy_policies(enemy_policies, random_generator=self.np_random)
 
     def _obs(self, map_obs):
         if self.observation_option == "map":
@@ -141,7 +118,6 @@ class CtFMvNEnv(_SingleMapEnv):
 
     def step(self, blue_actions):
         a = torch.as_tensor(np.round(np.asarray(blue_actions, dtype=np.float64)).astype(np.int8).reshape(1, -1), device=self.vec.device)
-        self._policy_actions()
         obs, rew, term, trunc, _ = self.vec.step(a)
         if self.vec.status() & 8:
             raise ValueError(f"Invalid action: {blue_actions}")  # ctf.py:1200-1201

@@ -349,6 +349,45 @@ def test_ctf_external_enemy_policy(cuda_device):
     env.close()
 
 
+def test_ctf_vec_enemy_policies(cuda_device):
+    """`CtfVecEnv.set_enemy_policies`: the reference's heuristic opponents (policy/ctf/heuristic.py) deciding on the host for a whole
+    batch.  Twin policies with an equally seeded generator, fed the same positional observations in the same order (env-major, red
+    agents in index order), must decide the same actions; the CUDA step with those decisions == the oracle stepped with the twins'."""
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.policy.ctf.heuristic import FightPolicy, PatrolFightPolicy
+    g = load_golden("ctf_2v2")
+    fm = g["field_map"].astype(np.float64)
+    n, nb, nr = 37, 2, 2
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=25, seed=5)
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=25)
+    mine = env.set_enemy_policies([FightPolicy(randomness=0.8), PatrolFightPolicy(fm, randomness=0.8)], random_generator=np.random.default_rng(11))
+    assert mine[0].field_map is not None and mine[0].random_generator is mine[1].random_generator
+    twin_gen = np.random.default_rng(11)
+    twins = [FightPolicy(fm, random_generator=twin_gen, randomness=0.8), PatrolFightPolicy(fm, random_generator=twin_gen, randomness=0.8)]
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(oc.map_rng(mode=1, seed=5)))
+    gen = torch.Generator(device=cuda_device).manual_seed(6)
+    for t in range(60):
+        d = {k: _np(v) for k, v in env.positional_obs().items()}
+        pos = _np(env.agent_pos).astype(np.int64)
+        want = np.array([[int(twins[k].act({key: v[e] for key, v in d.items()}, tuple(pos[e, nb + k].tolist()))) for k in range(nr)]
+                         for e in range(n)], np.int8)
+        act = torch.randint(0, 5, (n, nb), generator=gen, device=cuda_device, dtype=torch.int8)
+        obs, rew, term, trunc, _ = env.step(act)
+        assert np.array_equal(env._red_host, want), f"step {t}"
+        oo, orew, oterm, otrunc = o.step(_np(act), oc.map_rng(mode=1, seed=5, red_actions=want), autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+    assert len(set(env._red_host.reshape(-1).tolist())) > 1
+    assert env.set_enemy_policies(None) is None                      # back to the device opponent
+    obs, rew, *_ = env.step(torch.zeros((n, nb), dtype=torch.int8, device=cuda_device))
+    oo, orew, *_ = o.step(np.zeros((n, nb), np.int8), oc.map_rng(mode=1, seed=5), autoreset=True)
+    assert np.array_equal(_np(obs), oo) and env.status() == 0
+    with pytest.raises(AssertionError):
+        env.set_enemy_policies([FightPolicy()])                      # ctf.py:779: one policy per red agent
+    env.close()
+
+
 @pytest.mark.parametrize("stem", ["ctf_2v2_flat", "ctf_3v4_flat"])
 def test_ctf_flattened_obs_matches_reference(stem, cuda_device):
     """observation_option="flattened" (ctf.py:1084-1104; the option scripts/main_mvn_ctf_rl.py trains on) recorded from the
