@@ -18,7 +18,7 @@ import numpy as np
 from ...actions import CtfActions
 from ...world import CtfWorld
 from ..base import BaseAgentPolicy
-from .utils import NEIGHBOUR_ORDER, a_star, closest_area_pos, position_in_positions
+from .utils import NEIGHBOUR_ORDER, a_star, closest_area_pos
 
 
 class CtfPolicy(BaseAgentPolicy):
@@ -191,8 +191,8 @@ class PatrolFightPolicy(PatrolPolicy):
 
     def get_target(self, observation, curr_pos):
         ego_territory, _, opp_agents, _ = _team_keys(self.ego_agent)
-        opponents = [tuple(p) for p in np.asarray(observation[opp_agents]).reshape(-1, 2)]
+        opp = np.asarray(observation[opp_agents]).reshape(-1, 2)
         home = np.asarray(observation[ego_territory]).reshape(-1, 2)
-        if any(position_in_positions(p, home) for p in opponents):
-            return closest_area_pos(curr_pos, opponents)
+        if (opp[:, None, :] == home[None, :, :]).all(axis=2).any():      # heuristic.py:448-455, all pairs at once
+            return closest_area_pos(curr_pos, [tuple(p) for p in opp])
         return super().get_target(observation, curr_pos)
