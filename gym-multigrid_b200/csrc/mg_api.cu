@@ -43,7 +43,9 @@ int map_tile_envs();
 #include "view_params.cuh"
 #include "wildfire_params.cuh"
 #include "generic_params.cuh"
+#include "policy_params.cuh"
 namespace mg {
+cudaError_t launch_ctf_policy(const PolicyParams& p, cudaStream_t st);
 cudaError_t launch_view(const ViewParams& p, cudaStream_t st);
 cudaError_t launch_view6(const View6Params& p, cudaStream_t st);
 cudaError_t launch_toroid(const uint8_t* grid, const uint8_t* pos, float* out, long long N, int W, int A, int nb, cudaStream_t st);
@@ -76,6 +78,8 @@ struct mg_env {
   std::vector<long long> flat_tmpl;        // CtF: static entries of the "flattened" observation (ctf.py:1084-1104), per-env slots 0
   long long* d_flat_tmpl;                  // ... uploaded on first use
   std::vector<std::pair<int, uint8_t*>> atlases;    // render: (tile_size, device atlas) built on first use, freed by mg_destroy
+  uint8_t* d_policy_tables;        // CtF: tables of the scripted opponents (mg_set_red_policies), or null
+  mg::PolicyParams pbase;
   const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
@@ -246,6 +250,7 @@ extern "C" int mg_destroy(mg_env* env) {
   cudaFree(env->d_map_tables);
   for (auto& a : env->atlases) cudaFree(a.second);
   cudaFree(env->d_flat_tmpl);
+  cudaFree(env->d_policy_tables);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);   // rewards / term / trunc live inside the d_obs block
   delete env;
   return 0;
@@ -510,6 +515,79 @@ extern "C" int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev) {
   if (!env) return -1;
   if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_red_actions: CtF family only");
   env->ext_red_actions = red_actions_dev;
+  return 0;
+}
+
+extern "C" int mg_set_red_policies(mg_env* env, const mg_red_policies* t) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_red_policies: CtF family only");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(env, "cudaDeviceSynchronize", ce);   // a launch may still read the old tables
+  cudaFree(env->d_policy_tables);
+  env->d_policy_tables = nullptr;
+  if (!t) return 0;
+  if (t->struct_size != sizeof(mg_red_policies)) return fail(env, "mg_set_red_policies: mg_red_policies size mismatch (ABI)");
+  const mg::MapParams& m = env->mbase;
+  if (t->num_red != m.nr) return fail(env, "mg_set_red_policies: num_red differs from the handle's num_red_agents");
+  if (!t->first_move || !t->patrol_goal || !t->on_border) return fail(env, "mg_set_red_policies: null table");
+  const size_t cells = (size_t)m.cells;
+  if (cells > 65535) return fail(env, "mg_set_red_policies: map too large for 16-bit cell indices");
+  bool patrols = false;
+  mg::PolicyParams p{};
+  for (int k = 0; k < m.nr; ++k) {
+    if (t->kind[k] < MG_POLICY_RW || t->kind[k] > MG_POLICY_PATROL_FIGHT) return fail(env, "mg_set_red_policies: unknown policy kind");
+    if (!(t->randomness[k] >= 0.0 && t->randomness[k] <= 1.0)) return fail(env, "mg_set_red_policies: randomness must be in [0, 1]");
+    patrols |= t->kind[k] == MG_POLICY_PATROL || t->kind[k] == MG_POLICY_PATROL_FIGHT;
+    p.kind[k] = t->kind[k];
+    const double th = std::ceil(t->randomness[k] * 4294967296.0);   // (double)u / 2^32 < r  <=>  u < ceil(r * 2^32)
+    p.thr[k] = th <= 0.0 ? 0ull : (th >= 4294967296.0 ? 4294967296ull : (unsigned long long)th);
+  }
+  if (t->n_along < 0 || (t->n_along > 0 && !t->along_border)) return fail(env, "mg_set_red_policies: bad along_border");
+  for (size_t i = 0; i < cells * cells; ++i)
+    if (t->first_move[i] > 4) return fail(env, "mg_set_red_policies: first_move holds a value outside CtfActions");
+  for (size_t i = 0; i < cells; ++i) {
+    if (patrols && t->patrol_goal[i] >= cells) return fail(env, "mg_set_red_policies: patrol_goal outside the map (empty border?)");
+    if (patrols && t->on_border[i] && t->n_along == 0) return fail(env, "mg_set_red_policies: a border without patrol candidates (the reference raises there)");
+  }
+  for (int i = 0; i < t->n_along; ++i)
+    if (t->along_border[i] >= cells) return fail(env, "mg_set_red_policies: along_border outside the map");
+  const size_t o_fm = 0, o_goal = align_up(cells * cells, 16), o_border = o_goal + align_up(cells * 2, 16),
+               o_along = o_border + align_up(cells, 16), total = o_along + align_up((size_t)t->n_along * 2 + 2, 16);
+  std::vector<uint8_t> host(total, 0);
+  std::memcpy(host.data() + o_fm, t->first_move, cells * cells);
+  std::memcpy(host.data() + o_goal, t->patrol_goal, cells * 2);
+  std::memcpy(host.data() + o_border, t->on_border, cells);
+  if (t->n_along) std::memcpy(host.data() + o_along, t->along_border, (size_t)t->n_along * 2);
+  if ((ce = cudaMalloc(&env->d_policy_tables, total)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+  if ((ce = cudaMemcpy(env->d_policy_tables, host.data(), total, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(env, "policy table upload", ce);
+  p.S = m.S; p.cells = m.cells; p.nb = m.nb; p.nr = m.nr; p.n_along = t->n_along;
+  p.blue_flag_cell = (m.blue_flag & 255) * m.S + (m.blue_flag >> 8);
+  p.N = m.N; p.seed = m.seed; p.env_id_base = m.env_id_base;
+  p.field_map = m.field_map;
+  p.first_move = env->d_policy_tables + o_fm;
+  p.patrol_goal = reinterpret_cast<const uint16_t*>(env->d_policy_tables + o_goal);
+  p.on_border = env->d_policy_tables + o_border;
+  p.along = reinterpret_cast<const uint16_t*>(env->d_policy_tables + o_along);
+  env->pbase = p;
+  return 0;
+}
+
+extern "C" int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream) {
+  if (!env || !state || !red_actions_dev) return fail(env, "mg_red_policy_actions: null argument");
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_red_policy_actions: CtF family only");
+  if (!env->d_policy_tables) return fail(env, "mg_red_policy_actions: no policies set (mg_set_red_policies)");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  mg::PolicyParams p = env->pbase;
+  const uint8_t* base = static_cast<const uint8_t*>(state);
+  p.agents = base + env->plane_off[MG_MAP_PLANE_AGENTS];
+  p.row_bytes = (int)env->plane_row[MG_MAP_PLANE_AGENTS];
+  p.hdr = reinterpret_cast<const int4*>(base + env->plane_off[MG_MAP_PLANE_HDR]);
+  p.seed = env->mbase.seed;      // mg_set_seed may have re-keyed the handle since the tables were set
+  p.out = red_actions_dev;
+  if ((ce = mg::launch_ctf_policy(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "ctf_policy_kernel", ce);
+  env->launches += 1;
   return 0;
 }
 

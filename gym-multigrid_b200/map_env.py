@@ -375,7 +375,9 @@ class CtfVecEnv(_MapVecEnv):
         return self._option_obs(), info
 
     def step(self, actions):
-        if self._enemy_policies is not None:
+        if self._device_policies:      # one small launch ahead of the step's: red actions from the current state
+            self._check(self._lib.mg_red_policy_actions(self._h, _ptr(self.state), _ptr(self._red_buf), self._stream()))
+        elif self._enemy_policies is not None:
             self._decide_red_actions()
         out = super().step(actions)
         if self.observation_option == "map":
@@ -399,7 +401,9 @@ class CtfVecEnv(_MapVecEnv):
 
     _enemy_policies = None
 
-    def set_enemy_policies(self, enemy_policies=None, random_generator=None):
+    _device_policies = False
+
+    def set_enemy_policies(self, enemy_policies=None, random_generator=None, device=False):
         """The reference's `enemy_policies` argument (ctf.py:666, 775-826) for every env of the batch: one policy for all red
         agents or a list of `num_red_agents` of them - any object with `act(observation_dict, curr_pos) -> int` (the reference's
         CtfPolicy interface; `policy/ctf/heuristic.py` has Fight / Capture / Patrol / PatrolFight).  `random_generator`,
@@ -407,17 +411,39 @@ class CtfVecEnv(_MapVecEnv):
         `action_set` always, `field_map` when None).  The policies decide on the HOST, as in the reference: before each `step`
         the positional observation is read back once, `act` is called per env and red agent in index order (env 0 first), and
         the actions go to the kernel through `set_red_actions` - a per-step device sync, meant for SB3-sized batches.
-        None, or only None / RwPolicy entries = the built-in opponent drawn on the device.  Returns the list in use (or None)."""
+        None, or only None / RwPolicy entries = the built-in opponent drawn on the device.  Returns the list in use (or None).
+
+        `device=True` keeps the whole loop on the GPU for any batch size: the policies of this package (exact types, ego red)
+        are turned into tables - the first move of the reference's A* route per (cell, target), the patrol targets - and a
+        small kernel decides for every env before each step (`mg_set_red_policies` / `mg_red_policy_actions`).  Targets and
+        routes are the reference's; the random draws (follow the route or not, random action, patrol target) come from the
+        env's Philox generator instead of numpy's, as RwPolicy's do."""
         from .actions import CtfActions
         from .policy.ctf.heuristic import RwPolicy
         nr = self.num_red
         pols = list(enemy_policies) if isinstance(enemy_policies, (list, tuple)) else [enemy_policies] * nr
         if len(pols) != nr:
             raise AssertionError("len(enemy_policies) must equal num_red_agents")       # ctf.py:779
+        if self._device_policies:
+            self._check(self._lib.mg_set_red_policies(self._h, None))
+            self._device_policies = False
         if all(p is None or type(p) is RwPolicy for p in pols):
             self._enemy_policies = None
             self.set_red_actions(None)
             return None
+        if device:
+            from .policy.ctf.device import build_tables
+            t = build_tables(pols, self.field_map)
+            rp = _lib.RedPolicies()
+            rp.struct_size, rp.num_red, rp.n_along = C.sizeof(_lib.RedPolicies), nr, len(t["along_border"])
+            for k in range(nr):
+                rp.kind[k], rp.randomness[k] = int(t["kind"][k]), float(t["randomness"][k])
+            keep = [np.ascontiguousarray(t[name]) for name in ("first_move", "patrol_goal", "on_border", "along_border")]
+            rp.first_move, rp.patrol_goal, rp.on_border, rp.along_border = (a.ctypes.data for a in keep)
+            self._check(self._lib.mg_set_red_policies(self._h, C.byref(rp)))      # copies the tables during the call
+            self._enemy_policies, self._device_policies, self._policy_tables = None, True, t
+            self._red_buf = self.set_red_actions(torch.zeros((self.num_envs, nr), dtype=torch.int8, device=self.device))
+            return pols
         gen = random_generator if random_generator is not None else np.random.default_rng()
         pols = [RwPolicy() if p is None else p for p in pols]
         for p in pols:

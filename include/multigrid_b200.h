@@ -252,6 +252,30 @@ int mg_set_map_trace(mg_env* env, const mg_map_trace* trace_dev);
  * device (default).  Shuffle order and battle outcomes stay with the env's Philox stream. */
 int mg_set_red_actions(mg_env* env, const int8_t* red_actions_dev);
 
+/* CtF handles: the reference's scripted opponents (policy/ctf/heuristic.py:40-463) decided ON THE DEVICE for every env.
+ * mg_set_red_policies copies the tables (host pointers, read during the call) to the device; mg_red_policy_actions is one
+ * launch that writes the red team's actions int8 [N][num_red] from the current state - bind the same buffer with
+ * mg_set_red_actions and call it before each mg_step.  Targets are the reference's (closest blue agent, blue flag, border
+ * patrol, fight while a blue agent stands on red ground); the move towards a target is the first step of the reference's
+ * A* route (policy/ctf/utils.py:17-120), which the caller tabulates per (cell, target) by running that A* - cells are
+ * indexed x * size + y; "follow the route with probability randomness, else a uniform action" (heuristic.py:150-175) draws
+ * from the env's Philox generator (blocks disjoint from the step's), the device stand-in for numpy's Generator as for
+ * RwPolicy.  NULL tables = forget them. */
+enum { MG_POLICY_RW = 0, MG_POLICY_FIGHT = 1, MG_POLICY_CAPTURE = 2, MG_POLICY_PATROL = 3, MG_POLICY_PATROL_FIGHT = 4 };
+typedef struct mg_red_policies {
+  uint32_t struct_size;         /* sizeof(mg_red_policies) */
+  int32_t num_red;              /* must equal the handle's num_red_agents */
+  int32_t kind[16];             /* MG_POLICY_* per red agent */
+  double randomness[16];        /* probability of following the route (heuristic.py:89, default 0.75) */
+  const uint8_t* first_move;    /* [cells][cells] start-major: CtfActions value of the first move from `start` towards `target` */
+  const uint16_t* patrol_goal;  /* [cells] closest border cell of every cell (PatrolPolicy off the border, heuristic.py:336) */
+  const uint8_t* on_border;     /* [cells] 1 = the cell is in PatrolPolicy.border */
+  const uint16_t* along_border; /* [n_along] border cells next to a border cell, duplicates kept (heuristic.py:323-333) */
+  int32_t n_along;              /* may be 0 only if no agent patrols */
+} mg_red_policies;
+int mg_set_red_policies(mg_env* env, const mg_red_policies* tables);
+int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream);
+
 /* CtF handles: `_get_obs()` with observation_option="flattened" (ctf.py:1084-1104; what the reference's RL script trains on,
  * scripts/main_mvn_ctf_rl.py:15-21) for every env: out int64 [N][L] on the device, L = mg_ctf_flat_len() =
  * 3 n + 4 + 2 (|blue_territory| + |red_territory| + |obstacle|): blue agent (x, y) pairs, red agent pairs, blue flag, red flag,

@@ -175,6 +175,13 @@ int oc_map_info(const oc_map_cfg* c, int is_maze, int64_t N, const oc_map_state*
 /* observation_option="flattened" (ctf.py:1084-1104): int64 [N][L]; out NULL = only return L */
 int oc_ctf_flattened(const oc_map_cfg* c, int64_t N, const oc_map_state* st, int64_t* out);
 
+/* Scripted CtF opponents decided for every env (the rule of csrc/policy_kernels.cu; targets as policy/ctf/heuristic.py): kind 0 rw,
+ * 1 fight, 2 capture, 3 patrol, 4 patrol_fight; tables indexed by cell = x * size + y; out int8 [N][num_red]. */
+int oc_ctf_policy_actions(const oc_map_cfg* c, int64_t N, const oc_map_state* st, const int32_t* episode, const int32_t* kind,
+                          const double* randomness, const uint8_t* first_move, const uint16_t* patrol_goal,
+                          const uint8_t* on_border, const uint16_t* along, int32_t n_along, uint64_t seed, uint64_t env_id_base,
+                          int8_t* out);
+
 #define OC_ERR_BAD_ACTION 8 /* action outside the env's action set (reference: ValueError, maze.py:286, ctf.py:1200) */
 
 #ifdef __cplusplus

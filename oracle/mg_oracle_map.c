@@ -339,3 +339,58 @@ int oc_ctf_flattened(const oc_map_cfg* c, int64_t N, const oc_map_state* st, int
   }
   return L;
 }
+
+/* ------------------------------------------------------------------------------------ scripted CtF opponents
+ * CPU restatement of csrc/policy_kernels.cu's decision rule (targets: heuristic.py:216-226, 265-272, 321-338, 434-463;
+ * follow-or-random: :150-175; the first move of the A* route comes from the caller's [cell][target] table, which
+ * tests/test_policy_device_gpu.py fills with the reference-pinned host A*).  Philox blocks: counter (env id,
+ * 16 * step_count + block, 2^31 | episode), key = seed; draw order per red agent: patrol target, follow-or-not, random action. */
+typedef struct { uint32_t c[4], k[2], buf[4]; int have; } pol_rng_t;
+static uint32_t pol_u32(pol_rng_t* r) {
+  if (!r->have) { oc_philox4x32_10(r->c, r->k, r->buf); r->c[2]++; r->have = 4; }
+  return r->buf[4 - r->have--];
+}
+static int pol_below(pol_rng_t* r, int n) { return (int)(((uint64_t)pol_u32(r) * (uint32_t)n) >> 32); }
+
+int oc_ctf_policy_actions(const oc_map_cfg* c, int64_t N, const oc_map_state* st, const int32_t* episode, const int32_t* kind,
+                          const double* randomness, const uint8_t* first_move, const uint16_t* patrol_goal,
+                          const uint8_t* on_border, const uint16_t* along, int32_t n_along, uint64_t seed, uint64_t env_id_base,
+                          int8_t* out) {
+  const int S = c->size, cells = S * S, nb = c->num_blue, nr = c->num_red, n = nb + nr;
+  int blue_flag = -1;
+  for (int i = 0; i < cells && blue_flag < 0; ++i) if (c->field_map[i] == CT_BLUE_FLAG) blue_flag = i;
+  for (int64_t e = 0; e < N; ++e) {
+    const uint8_t* pos = st->pos + (size_t)e * n * 2;
+    const uint64_t id = env_id_base + (uint64_t)e;
+    pol_rng_t r = {{(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)st->step_count[e] * 16u, 0x80000000u | (uint32_t)episode[e]},
+                   {(uint32_t)seed, (uint32_t)(seed >> 32)}, {0}, 0};
+    int intruder = 0;
+    for (int i = 0; i < nb; ++i) {
+      const int code = c->field_map[pos[2 * i] * S + pos[2 * i + 1]];
+      intruder |= code == CT_RED_TERR || code == CT_RED_FLAG;
+    }
+    for (int k = 0; k < nr; ++k) {
+      int a;
+      if (kind[k] == 0) a = pol_below(&r, 5);
+      else {
+        const int x = pos[2 * (nb + k)], y = pos[2 * (nb + k) + 1], cell = x * S + y;
+        int target;
+        if (kind[k] == 2) target = blue_flag;
+        else if (kind[k] == 1 || (kind[k] == 4 && intruder)) {
+          long best = 1L << 40;
+          target = cell;
+          for (int i = 0; i < nb; ++i) {
+            const long dx = pos[2 * i] - x, dy = pos[2 * i + 1] - y, d2 = dx * dx + dy * dy;
+            if (d2 < best) { best = d2; target = pos[2 * i] * S + pos[2 * i + 1]; }
+          }
+        } else if (on_border[cell]) target = along[pol_below(&r, n_along)];
+        else target = patrol_goal[cell];
+        const int mv = first_move[(size_t)cell * cells + target];
+        const double u = (double)pol_u32(&r) / 4294967296.0;
+        a = u < randomness[k] ? mv : pol_below(&r, 5);
+      }
+      out[e * nr + k] = (int8_t)a;
+    }
+  }
+  return 0;
+}

@@ -373,6 +373,19 @@ class CtfOracle(_MapOracle):
     def step(self, blue_actions, rng, autoreset=False, want_final_obs=False):
         return self._call_step(lib().oc_ctf_step, np.asarray(blue_actions).reshape(self.N, self.nb), rng, autoreset, want_final_obs)
 
+    def policy_actions(self, tables, seed, episode, env_id_base=0):
+        """Red actions int8 [N, num_red] of the scripted opponents for the current state (oc_ctf_policy_actions); `tables` as
+        `gym_multigrid_b200.policy.ctf.device.build_tables` returns them, `episode` = per-env episode counters."""
+        out = np.zeros((self.N, self.nr), np.int8)
+        st = self._state()
+        keep = [np.ascontiguousarray(episode, np.int32), np.ascontiguousarray(tables["kind"], np.int32),
+                np.ascontiguousarray(tables["randomness"], np.float64), np.ascontiguousarray(tables["first_move"], np.uint8),
+                np.ascontiguousarray(tables["patrol_goal"], np.uint16), np.ascontiguousarray(tables["on_border"], np.uint8),
+                np.ascontiguousarray(tables["along_border"], np.uint16)]
+        lib().oc_ctf_policy_actions(C.byref(self.cfg), C.c_int64(self.N), C.byref(st), *[_p(a) for a in keep],
+                                    C.c_int32(len(tables["along_border"])), C.c_uint64(int(seed)), C.c_uint64(int(env_id_base)), _p(out))
+        return out
+
     def flattened(self):
         """observation_option="flattened" (ctf.py:1084-1104) of the current state: int64 [N, L]."""
         st = self._state()

@@ -160,3 +160,41 @@ def test_live_differential_against_the_reference(maps):
                         break
                     assert int(ours.act(obs, cur)) == want, (trial, pname, ego, k)
                 assert ga.integers(0, 2 ** 31) == gb.integers(0, 2 ** 31)
+
+
+def test_oracle_rule_of_the_device_policies_matches_the_host_policies():
+    """The C restatement of csrc/policy_kernels.cu's decision rule (`oc_ctf_policy_actions`, the checker of
+    tests/test_policy_device_gpu.py) against the host policies above, on CtF states stepped by the oracle: with randomness 1
+    every decision that involves no patrol draw must be the host policy's; with randomness 0 every action is a uniform draw."""
+    import oracle as oc
+    from gym_multigrid_b200.policy.ctf.device import build_tables
+    g = load_golden("ctf_3v4")
+    fm = g["field_map"].astype(np.float64)
+    nb, nr, n = 3, 4, 64
+    names = ("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy")
+    host = [getattr(H, name)(fm, randomness=1.0, random_generator=np.random.default_rng(0)) for name in names]
+    tables = build_tables(host, fm)
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=25)
+    o.reset(oc.map_rng(mode=1, seed=4))
+    rng = np.random.default_rng(1)
+    episode = np.zeros(n, np.int32)
+    compared = drawn = 0
+    for t in range(60):
+        red = o.policy_actions(tables, 4, episode)
+        for e in range(n):
+            obs = policy_observation(fm, o.pos[e, :nb].astype(np.int64), o.pos[e, nb:].astype(np.int64))
+            intruder = any(fm[tuple(b)] in (1, 5) for b in o.pos[e, :nb].astype(np.int64).tolist())
+            for k, p in enumerate(host):
+                cur = tuple(o.pos[e, nb + k].astype(np.int64).tolist())
+                if (k == 2 or (k == 3 and not intruder)) and cur in p._border_cells:
+                    drawn += 1
+                    assert tables["first_move"][cur[0] * 10 + cur[1]].max() <= 4
+                    continue
+                assert int(p.act(obs, cur)) == int(red[e, k]), (t, e, k, cur)
+                compared += 1
+        _, _, term, trunc = o.step(rng.integers(0, 5, (n, nb)).astype(np.int8), oc.map_rng(mode=1, seed=4, red_actions=red), autoreset=True)
+        episode += (term | trunc)
+    assert compared > 10000 and drawn > 50
+    tables0 = build_tables([getattr(H, name)(fm, randomness=0.0) for name in names], fm)
+    acts = np.concatenate([o.policy_actions(tables0, s, episode).reshape(-1) for s in range(40)])
+    assert np.bincount(acts, minlength=5).min() > 0.15 * len(acts)

@@ -1,0 +1,126 @@
+"""Scripted CtF opponents decided on the device (`CtfVecEnv.set_enemy_policies(..., device=True)` -> mg_set_red_policies /
+mg_red_policy_actions, csrc/policy_kernels.cu):
+ * the kernel's actions == the C oracle's restatement of the rule (same Philox blocks), step after step with autoreset, and the
+   CUDA step driven by them == the oracle's step driven by the oracle's;
+ * with randomness 1 (always follow the route) the kernel's actions == the decisions of the host policies - which are pinned
+   to the unmodified reference classes (tests/test_policies.py) - for every env and red agent whose decision involves no draw."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as oc
+from replay import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _policies(names, fm, randomness):
+    from gym_multigrid_b200.policy.ctf import heuristic as H
+    out = []
+    for name, r in zip(names, randomness):
+        out.append(H.RwPolicy() if name == "RwPolicy" else getattr(H, name)(fm, randomness=r))
+    return out
+
+
+@pytest.mark.parametrize("stem,names,randomness", [
+    ("ctf_2v2", ("FightPolicy", "PatrolFightPolicy"), (0.75, 0.6)),
+    ("ctf_2v2", ("CapturePolicy", "PatrolPolicy"), (0.9, 0.5)),
+    ("ctf_2v2", ("RwPolicy", "FightPolicy"), (0.0, 0.0)),
+    ("ctf_3v4", ("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy"), (0.75, 1.0, 0.75, 0.25)),
+])
+def test_device_policies_match_oracle(stem, names, randomness, cuda_device):
+    import gym_multigrid_b200 as mg
+    g = load_golden(stem)
+    fm = g["field_map"].astype(np.float64)
+    nb, nr = int(g["meta_num_blue"]), int(g["meta_num_red"])
+    n, seed = 777, 5
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=20, seed=seed)
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=20)
+    env.set_enemy_policies(_policies(names, fm, randomness), device=True)
+    tables = env._policy_tables
+    assert tables["kind"].tolist() == [dict(RwPolicy=0, FightPolicy=1, CapturePolicy=2, PatrolPolicy=3, PatrolFightPolicy=4)[k] for k in names]
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(oc.map_rng(mode=1, seed=seed)))
+    gen = torch.Generator(device=cuda_device).manual_seed(8)
+    seen = set()
+    for t in range(50):
+        want = o.policy_actions(tables, seed, _np(env.episode_count))
+        act = torch.randint(0, 5, (n, nb), generator=gen, device=cuda_device, dtype=torch.int8)
+        obs, rew, term, trunc, _ = env.step(act)
+        got = _np(env._red_buf)
+        assert np.array_equal(got, want), f"step {t}: {np.argwhere(got != want)[:5].tolist()}"
+        oo, orew, oterm, otrunc = o.step(_np(act), oc.map_rng(mode=1, seed=seed, red_actions=want), autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+        seen.update(got.reshape(-1).tolist())
+    assert seen == {0, 1, 2, 3, 4} and env.status() == 0
+    assert int(_np(env.episode_count).max()) >= 2          # autoresets happened: the episode word of the counter was exercised
+    env.set_enemy_policies(None)                            # back to the built-in RwPolicy
+    obs, *_ = env.step(torch.zeros((n, nb), dtype=torch.int8, device=cuda_device))
+    oo, *_ = o.step(np.zeros((n, nb), np.int8), oc.map_rng(mode=1, seed=seed), autoreset=True)
+    assert np.array_equal(_np(obs), oo)
+    env.close()
+
+
+def test_device_decisions_are_the_host_policies_decisions(cuda_device):
+    """randomness = 1: `choice([True, False], p=[1, 0])` always follows the route, so a decision without a patrol draw is a pure
+    function of the state - the device must return what the (reference-pinned) host policy returns."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_3v4")
+    fm = g["field_map"].astype(np.float64)
+    nb, nr, n = 3, 4, 300
+    names = ("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy")
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=30, seed=2)
+    env.set_enemy_policies(_policies(names, fm, (1.0,) * 4), device=True)
+    host = _policies(names, fm, (1.0,) * 4)
+    for p in host:
+        p.random_generator = np.random.default_rng(0)
+    along = set(env._policy_tables["along_border"].tolist())
+    env.reset()
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    compared = drawn = 0
+    for t in range(40):
+        d = {k: _np(v) for k, v in env.positional_obs().items()}
+        pos = _np(env.agent_pos).astype(np.int64)
+        env.step(torch.randint(0, 5, (n, nb), generator=gen, device=cuda_device, dtype=torch.int8))
+        got = _np(env._red_buf)
+        for e in range(n):
+            obs = {key: v[e] for key, v in d.items()}
+            for k, p in enumerate(host):
+                cur = tuple(pos[e, nb + k].tolist())
+                patrolling = k == 2 or (k == 3 and not any(fm[tuple(b)] in (1, 5) for b in pos[e, :nb].tolist()))
+                if patrolling and cur in p._border_cells:
+                    drawn += 1                      # the target is a draw: numpy's on the host, Philox's on the device
+                    continue
+                assert int(p.act(obs, cur)) == int(got[e, k]), (t, e, k, cur)
+                compared += 1
+    assert compared > 30000 and drawn > 100 and along
+    env.close()
+
+
+def test_device_policies_reject_what_they_cannot_express(cuda_device):
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.policy.ctf import heuristic as H
+    g = load_golden("ctf_2v2")
+    fm = g["field_map"].astype(np.float64)
+    env = mg.make_ctf_vec(4, g["field_map"], num_blue_agents=2, num_red_agents=2)
+
+    class Mine(H.FightPolicy):
+        pass
+    with pytest.raises(TypeError):
+        env.set_enemy_policies([Mine(fm), H.RwPolicy()], device=True)
+    with pytest.raises(ValueError):
+        env.set_enemy_policies([H.PatrolPolicy(), H.RwPolicy()], device=True)          # built without a map: empty border
+    with pytest.raises(ValueError):
+        env.set_enemy_policies([H.FightPolicy(fm, ego_agent="blue"), H.RwPolicy()], device=True)
+    with pytest.raises(ValueError):
+        env.set_enemy_policies([H.FightPolicy(fm.T.copy()), H.RwPolicy()], device=True)
+    assert env.set_enemy_policies([H.FightPolicy(fm), None], device=True) is not None
+    env.reset()
+    env.step(torch.zeros((4, 2), dtype=torch.int8, device=cuda_device))
+    assert env.status() == 0
+    env.close()
