@@ -37,17 +37,19 @@ struct PolicyRng {
 __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= p.N) return;
-  const uint8_t* row = p.agents + e * p.row_bytes;
+  // one 32-bit load per agent: x | y << 8 | dir << 16 | flags << 24 (rows are 4 * 2^k bytes, 4-byte aligned)
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(p.agents + e * p.row_bytes);
   const int4 h = p.hdr[e];
   const unsigned long long id = p.env_id_base + (unsigned long long)e;
   PolicyRng r;
   r.k0 = (uint32_t)p.seed; r.k1 = (uint32_t)(p.seed >> 32); r.id0 = (uint32_t)id; r.id1 = (uint32_t)(id >> 32);
   r.c2 = (uint32_t)h.x * 16u; r.c3 = 0x80000000u | (uint32_t)h.w; r.have = 0;
   const int S = p.S;
-  // closest blue agent and "a blue agent stands on red ground", shared by every red agent of the env
+  // "a blue agent stands on red ground", shared by every red agent of the env
   bool intruder = false;
   for (int i = 0; i < p.nb; ++i) {
-    const int code = __ldg(p.field_map + row[4 * i] * S + row[4 * i + 1]);
+    const uint32_t w = row[i];
+    const int code = __ldg(p.field_map + (w & 255u) * S + ((w >> 8) & 255u));
     intruder |= code == 1 || code == 5;   // observation["red_territory"] = red territory cells + the red flag (ctf.py:765-769)
   }
   for (int k = 0; k < p.nr; ++k) {
@@ -56,7 +58,8 @@ __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
     if (kind == MG_POLICY_RW) {
       a = r.below(5);
     } else {
-      const int x = row[4 * (p.nb + k)], y = row[4 * (p.nb + k) + 1], cell = x * S + y;
+      const uint32_t me = row[p.nb + k];
+      const int x = me & 255u, y = (me >> 8) & 255u, cell = x * S + y;
       int target;
       if (kind == MG_POLICY_CAPTURE) {
         target = p.blue_flag_cell;
@@ -64,8 +67,9 @@ __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
         int best = 0x7fffffff;
         target = cell;
         for (int i = 0; i < p.nb; ++i) {
-          const int dx = row[4 * i] - x, dy = row[4 * i + 1] - y, d2 = dx * dx + dy * dy;
-          if (d2 < best) { best = d2; target = row[4 * i] * S + row[4 * i + 1]; }
+          const uint32_t w = row[i];
+          const int bx = w & 255u, by = (w >> 8) & 255u, dx = bx - x, dy = by - y, d2 = dx * dx + dy * dy;
+          if (d2 < best) { best = d2; target = bx * S + by; }
         }
       } else if (__ldg(p.on_border + cell)) {
         target = __ldg(p.along + r.below(p.n_along));

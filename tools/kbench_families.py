@@ -117,6 +117,30 @@ def bench_ctf(args):
         e.close()
 
 
+def bench_ctf_policy(args):
+    """CtF 2v2 with the scripted opponents decided on the device: the policy launch alone, and policy + step per env-step."""
+    from gym_multigrid_b200.policy.ctf.heuristic import FightPolicy, PatrolFightPolicy
+    fm = golden("ctf_2v2", "field_map")
+    fmf = fm.astype(np.float64)
+    n, nb, nr = 1 << 20, 2, 2
+    bpe_step = 100 + 2 * (4 * (nb + nr) + 16) + nb + 10
+    bpe_pol = 4 * (nb + nr) + 16 + nr                        # agents row + header read, red actions written
+    B = batches_for(bpe_step, n)
+    envs = [mg.make_ctf_vec(n, fm, num_blue_agents=nb, num_red_agents=nr, seed=b, env_id_base=b * n) for b in range(B)]
+    acts = [torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+    for e in envs:
+        e.set_enemy_policies([FightPolicy(fmf), PatrolFightPolicy(fmf)], device=True)
+        e.reset()
+    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    report("ctf_policy_kernel + map_kernel<ctf> 2v2 (fight, patrol_fight reds on device)", n, us, bpe_step + bpe_pol, batches=B)
+    import ctypes as C
+    ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+    us = graph_time([lambda e=e: e._check(e._lib.mg_red_policy_actions(e._h, ptr(e.state), ptr(e._red_buf), e._stream())) for e in envs], args.reps)
+    report("ctf_policy_kernel alone 2v2", n, us, bpe_pol, batches=B)
+    for e in envs:
+        e.close()
+
+
 def bench_maze(args):
     fm = golden("maze_gen64", "field_map")
     for n, ref in ((16384, False), (131072, False), (16384, True)):
