@@ -26,6 +26,14 @@ def main():
         e = mg.make_ctf_vec(n, golden("ctf_2v2", "field_map"))
         a = torch.randint(0, 5, (n, 2), device=dev, dtype=torch.int8)
         f = lambda: e.step(a)  # noqa: E731
+    elif fam == "ctf_policy":      # scripted opponents decided on the device: ctf_policy_kernel ahead of every step
+        from gym_multigrid_b200.policy.ctf.heuristic import FightPolicy, PatrolFightPolicy
+        n = n or (1 << 20)
+        fm = golden("ctf_2v2", "field_map")
+        e = mg.make_ctf_vec(n, fm)
+        e.set_enemy_policies([FightPolicy(fm.astype(np.float64)), PatrolFightPolicy(fm.astype(np.float64))], device=True)
+        a = torch.randint(0, 5, (n, 2), device=dev, dtype=torch.int8)
+        f = lambda: e.step(a)  # noqa: E731
     elif fam == "maze":
         n = n or 131072
         e = mg.make_maze_vec(n, golden("maze_gen64", "field_map"))
