@@ -371,6 +371,7 @@ class CtfVecEnv(_MapVecEnv):
         multigrid.py:114-119): the same seed gives the same placements and the same episode for the same actions."""
         if seed is not None:
             self.reseed(seed)
+            self._planes["hdr"][:, 3] = 0     # episode counters too: the device opponents' draws are keyed by (step, episode)
         _, info = super().reset(seed=seed, options=options, mask=mask)
         return self._option_obs(), info
 
