@@ -198,3 +198,44 @@ def test_oracle_rule_of_the_device_policies_matches_the_host_policies():
     tables0 = build_tables([getattr(H, name)(fm, randomness=0.0) for name in names], fm)
     acts = np.concatenate([o.policy_actions(tables0, s, episode).reshape(-1) for s in range(40)])
     assert np.bincount(acts, minlength=5).min() > 0.15 * len(acts)
+
+
+def test_device_tables(maps):
+    """`policy/ctf/device.build_tables` (what mg_set_red_policies uploads): the first-move table restates `DestinationPolicy.act`'s
+    route step for every (cell, target) pair, the patrol tables restate `PatrolPolicy.get_target`; inputs with no device form
+    are refused."""
+    from gym_multigrid_b200.policy.ctf.device import build_tables, first_move_table
+    fm = maps["board"]
+    pols = [H.FightPolicy(fm, randomness=0.3), H.PatrolFightPolicy(fm), None, H.CapturePolicy(fm, randomness=1.0)]
+    t = build_tables(pols, fm)
+    assert t["kind"].tolist() == [1, 4, 0, 2] and t["randomness"].tolist() == [0.3, 0.75, 0.0, 1.0]
+    fmv = t["first_move"]
+    assert fmv.shape == (100, 100) and fmv.dtype == np.uint8 and np.array_equal(fmv, first_move_table(fm))
+    probe = H.CapturePolicy(fm, randomness=1.0, random_generator=np.random.default_rng(0))
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        s, g = (int(rng.integers(0, 10)), int(rng.integers(0, 10))), (int(rng.integers(0, 10)), int(rng.integers(0, 10)))
+        assert int(probe.act({"blue_flag": np.array(g)}, s)) == fmv[s[0] * 10 + s[1], g[0] * 10 + g[1]]
+    patrol = pols[1]
+    assert sorted(set(np.flatnonzero(t["on_border"]).tolist())) == sorted({x * 10 + y for x, y in patrol._border_cells})
+    assert t["along_border"].tolist() == [int(x) * 10 + int(y) for x, y in patrol._along_border]
+    for c in range(100):
+        x, y = closest_area_pos(divmod(c, 10), patrol.border)
+        assert t["patrol_goal"][c] == x * 10 + y
+    no_patrol = build_tables([H.FightPolicy(fm), H.RwPolicy()], fm)
+    assert len(no_patrol["along_border"]) == 0 and not no_patrol["on_border"].any()
+
+    class Mine(H.FightPolicy):
+        pass
+    with pytest.raises(TypeError):
+        build_tables([Mine(fm)], fm)
+    with pytest.raises(ValueError):
+        build_tables([H.PatrolPolicy()], fm)                                  # no map at construction: empty border
+    with pytest.raises(ValueError):
+        build_tables([H.FightPolicy(fm, ego_agent="blue")], fm)
+    with pytest.raises(ValueError):
+        build_tables([H.FightPolicy(maps["wide"][:10, :10].copy())], fm)      # another map
+    with pytest.raises(ValueError):
+        build_tables([H.PatrolPolicy(fm), H.PatrolPolicy(fm, ego_agent="red", world=type("W", (), {"OBJECT_TO_IDX": dict(red_territory=0, blue_territory=1, obstacle=6)}))], fm)
+    with pytest.raises(ValueError):
+        build_tables([H.FightPolicy()], np.zeros((21, 21)))                   # > 400 cells
