@@ -37,6 +37,26 @@ def test_config_struct_matches_header_layout():
     assert C.sizeof(_lib.MapConfig) == 120 and C.sizeof(_lib.MapTrace) == 8 * 8
     assert C.sizeof(_lib.WildfireConfig) == 4 + 4 + 16 + 12 + 128 + 4 + 20 + 4 + 8 + 8
     assert C.sizeof(_lib.Trace) == 9 * 8
+    assert C.sizeof(_lib.RedPolicies) == 4 + 4 + 64 + 128 + 4 * 8 + 4 + 4
+
+
+def test_struct_sizes_agree_with_the_c_compiler(tmp_path):
+    """The ctypes mirrors against `sizeof` as gcc sees include/multigrid_b200.h (every struct the ABI checks by struct_size)."""
+    import shutil
+    import subprocess
+    from gym_multigrid_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    names = {"mg_config": _lib.Config, "mg_map_config": _lib.MapConfig, "mg_wildfire_config": _lib.WildfireConfig,
+             "mg_generic_config": _lib.GenericConfig, "mg_red_policies": _lib.RedPolicies, "mg_step_io": _lib.StepIO, "mg_trace": _lib.Trace, "mg_map_trace": _lib.MapTrace}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "multigrid_b200.h"\nint main(void) {\n'
+                   + "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for n, cls in names.items():
+        assert int(out[n]) == C.sizeof(cls), n
 
 
 def test_create_fails_loudly_without_gpu_or_with_bad_abi():
