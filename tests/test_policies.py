@@ -239,3 +239,37 @@ def test_device_tables(maps):
         build_tables([H.PatrolPolicy(fm), H.PatrolPolicy(fm, ego_agent="red", world=type("W", (), {"OBJECT_TO_IDX": dict(red_territory=0, blue_territory=1, obstacle=6)}))], fm)
     with pytest.raises(ValueError):
         build_tables([H.FightPolicy()], np.zeros((21, 21)))                   # > 400 cells
+
+
+@pytest.mark.parametrize("names", [("FightPolicy", "CapturePolicy"), ("PatrolPolicy", "PatrolFightPolicy"), ("FightPolicy", "RwPolicy"),
+                                   ("PatrolFightPolicy", "PatrolFightPolicy")])
+def test_policies_drop_into_the_unmodified_reference_env(names):
+    """The other direction of the drop-in: this package's policy objects handed to the REFERENCE `CtFMvNEnv(enemy_policies=...)`
+    (tests/test_ctf.py:97-215) reproduce, step for step, the episodes the reference's own policies produce - observations, rewards,
+    flags - with the policies' draws interleaved with the env's own (shuffle, battles) as ctf.py:821-826 arranges."""
+    import os
+    RH, _ = _reference_heuristic()
+    import ref_harness as rh
+    from gym_multigrid.envs.ctf import CtFMvNEnv
+    map_path = os.path.join(rh.REFERENCE_ROOT, "tests", "assets", "board.txt")
+    fm = np.loadtxt(map_path).T
+    for seed in (7, 8, 9):
+        runs = []
+        for mod in (RH, H):
+            pols = [mod.RwPolicy() if n == "RwPolicy" else getattr(mod, n)(fm.copy()) for n in names]
+            env = CtFMvNEnv(map_path, num_blue_agents=2, num_red_agents=2, enemy_policies=pols, observation_option="map")
+            shared = np.random.Generator(np.random.PCG64(40 + seed))     # the construction-time np_random is unseeded: pin it
+            env._np_random = shared
+            for agent in env.agents[2:]:
+                assert agent.policy.action_set is env.actions_set
+                agent.policy.random_generator = shared
+            obs, _ = env.reset(seed=seed)
+            arng, traj, rews, flags = np.random.default_rng(seed), [np.asarray(obs)], [], []
+            while True:
+                obs, rew, term, trunc, info = env.step([int(v) for v in arng.integers(0, 5, 2)])
+                traj.append(np.asarray(obs)); rews.append(rew); flags.append((term, trunc))
+                if term or trunc:
+                    break
+            runs.append((np.stack(traj), rews, flags, shared.integers(0, 2 ** 31)))
+        assert runs[0][0].shape == runs[1][0].shape and np.array_equal(runs[0][0], runs[1][0]), (names, seed)
+        assert runs[0][1] == runs[1][1] and runs[0][2] == runs[1][2] and runs[0][3] == runs[1][3] and len(runs[0][1]) >= 10
