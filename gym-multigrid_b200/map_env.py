@@ -12,13 +12,7 @@ import torch
 from . import _lib
 from .vector_base import VectorEnvSurface
 from .spaces import Box, Discrete, MultiDiscrete
-
-
-def load_text_map(map_path) -> np.ndarray:
-    """utils/map.py:22-39: `np.loadtxt(map_path).T`, i.e. field_map[x, y]; arrays are passed through."""
-    if isinstance(map_path, (str, bytes)) or hasattr(map_path, "__fspath__"):
-        return np.loadtxt(map_path).T
-    return np.asarray(map_path)
+from .utils.map import load_text_map
 
 
 def _ptr(t):

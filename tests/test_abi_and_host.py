@@ -145,3 +145,54 @@ def test_vector_env_surface_is_shared_by_every_batched_class():
         assert issubclass(cls, VectorEnvSurface)
         for name in ("reset", "step", "close", "render", "get_attr", "unwrapped", "metadata"):
             assert hasattr(cls, name), (cls.__name__, name)
+
+
+def test_reference_import_paths_resolve():
+    """Code written against the reference changes the package name only: the module paths its tests and script import from
+    (tests/test_ctf.py:7-16, tests/test_maze.py:3, scripts/main_mvn_ctf_rl.py:7) exist under gym_multigrid_b200."""
+    from gym_multigrid_b200.core.agent import CollectActions, CtfActions, MazeActions
+    from gym_multigrid_b200.core.world import CollectWorld, CtfWorld, DefaultWorld, MazeWorld
+    from gym_multigrid_b200.envs.collect_game import CollectEnv, CollectVecEnv
+    from gym_multigrid_b200.envs.ctf import Ctf1v1Env, CtFMvNEnv
+    from gym_multigrid_b200.envs.maze import MazeSingleAgentEnv
+    from gym_multigrid_b200.policy.ctf.heuristic import CapturePolicy, FightPolicy, PatrolFightPolicy, PatrolPolicy, RwPolicy
+    from gym_multigrid_b200.utils.map import load_text_map
+    from gym_multigrid_b200.utils.misc import set_seed
+    from gym_multigrid_b200.wrappers import ToroidObservation
+    import gym_multigrid_b200 as mg
+    assert mg.CtFMvNEnv is CtFMvNEnv and mg.Ctf1v1Env is Ctf1v1Env and mg.MazeSingleAgentEnv is MazeSingleAgentEnv
+    assert mg.FightPolicy is FightPolicy and mg.CtfWorld is CtfWorld and mg.CtfActions is CtfActions is MazeActions
+    assert [a.name for a in CollectActions] == ["north", "east", "south", "west"]                       # core/agent.py:32-36
+    assert CollectWorld.OBJECT_TO_IDX == dict(empty=0, wall=1, ball=2, agent=3) and DefaultWorld.encode_dim == 6
+    assert MazeWorld.IDX_TO_OBJECT[3] == "obstacle" and all(c is not None for c in (CollectEnv, CollectVecEnv, ToroidObservation))
+    assert all(callable(f) for f in (CapturePolicy, PatrolFightPolicy, PatrolPolicy, RwPolicy, load_text_map, set_seed))
+    set_seed(5)
+    a = np.random.rand()
+    set_seed(5)
+    assert a == np.random.rand()
+
+
+def test_map_helpers(tmp_path):
+    """utils/map.py:7-61 - against the reference's functions where /root/reference exists, known answers everywhere."""
+    from gym_multigrid_b200.utils import map as M
+    p = tmp_path / "m.txt"
+    p.write_text("0 1 2\n3 4 5\n")
+    fm = M.load_text_map(str(p))
+    assert fm.shape == (3, 2) and fm[2, 0] == 2 and fm[0, 1] == 3 and M.load_text_map(fm) is fm       # field_map[x, y] = row y, column x
+    assert M.distance_points((0, 0), (3, 4)) == 5.0 and M.distance_points((0, 0), (3, 4), True) == float("inf")
+    assert M.distance_area_point((0, 0), [(5, 5), (1, 1), (2, 0)]) == np.sqrt(2.0)
+    assert M.closest_area_pos((0, 0), [(5, 5), (1, 1), (1, 1)]) == (1, 1) and M.position_in_positions((1, 1), [(0, 1), (1, 1)])
+    import ref_harness as rh
+    if not rh.reference_available():
+        return
+    rh.import_reference()
+    from gym_multigrid.utils import map as R
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        a, b = tuple(rng.integers(0, 70, 2)), tuple(rng.integers(0, 70, 2))
+        area = [tuple(v) for v in rng.integers(0, 70, (int(rng.integers(1, 9)), 2))]
+        assert M.distance_points(a, b) == R.distance_points(a, b)
+        assert M.distance_area_point(a, area) == R.distance_area_point(a, area)
+        assert tuple(M.closest_area_pos(a, area)) == tuple(R.closest_area_pos(a, area))
+        assert M.position_in_positions(a, area) == R.position_in_positions(a, area)
+    assert np.array_equal(M.load_text_map(str(p)), R.load_text_map(str(p)))
