@@ -6,7 +6,7 @@
 * single env, reference style: `CtFMvNEnv(enemy_policies=[FightPolicy(), RwPolicy()])` - the policies decide on the host from the
   positional observation, exactly where the reference calls them; the step, the battles and the observation are CUDA kernels.
 * a batch: `CtfVecEnv.set_enemy_policies(policy)` - the same objects for every env (a device sync per step; for very large
-  batches write red actions on the device instead, see ctf_policy_and_frames.py).
+  batches pass `device=True`: the decisions move into a kernel, see below).
 The policies reproduce the reference's decisions and random draws (tests/test_policies.py), A* tie-breaking included.
 """
 import argparse
@@ -67,6 +67,18 @@ def main():
         episodes += int((term | trunc).sum())
     print(f"{n} envs vs {args.policy} x 2: 100 steps, {episodes} episodes finished, mean return per env {float(ret.mean()):+.2f}")
     vec.close()
+
+    # --- a large batch: the same opponents decided by a kernel (first moves of the reference's A* routes from a host-built table)
+    n = 1 << 16
+    big = mg.make_ctf_vec(n, map_path, num_blue_agents=2, num_red_agents=2, max_steps=100, seed=0)
+    big.set_enemy_policies([POLICIES[args.policy](field_map), POLICIES[args.policy](field_map)], device=True)
+    big.reset()
+    ret = torch.zeros(n, dtype=torch.float64, device=big.device)
+    for _ in range(100):
+        _, rew, _, _, _ = big.step(torch.randint(0, 5, (n, 2), device=big.device, dtype=torch.int8))
+        ret += rew
+    print(f"{n} envs vs {args.policy} x 2 decided on the device: 100 steps, mean return per env {float(ret.mean()):+.2f}")
+    big.close()
 
 
 if __name__ == "__main__":
