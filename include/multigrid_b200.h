@@ -274,6 +274,12 @@ typedef struct mg_red_policies {
   int32_t n_along;              /* may be 0 only if no agent patrols */
 } mg_red_policies;
 int mg_set_red_policies(mg_env* env, const mg_red_policies* tables);
+/* Host-only helper that fills mg_red_policies.first_move: for every (start, target) pair of a rows x cols map - cell index
+ * x * cols + y - the CtfActions value of the first move of the route the reference's A* returns (policy/ctf/utils.py:17-120, its
+ * frontier order and neighbour order restated; blocked[cell] != 0 marks the cells the reference treats as blocking, map value
+ * 8, utils.py:73); `stay` when start == target; a pair without a route gets the move towards the target if adjacent, else
+ * `stay` (the reference raises there, heuristic.py:172).  first_move: [cells][cells] start-major.  No device involved. */
+int mg_astar_first_moves(const uint8_t* blocked, int32_t rows, int32_t cols, uint8_t* first_move);
 int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream);
 
 /* CtF handles: `_get_obs()` with observation_option="flattened" (ctf.py:1084-1104; what the reference's RL script trains on,

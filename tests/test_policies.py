@@ -200,6 +200,24 @@ def test_oracle_rule_of_the_device_policies_matches_the_host_policies():
     assert np.bincount(acts, minlength=5).min() > 0.15 * len(acts)
 
 
+def test_native_first_move_table_matches_the_python_a_star(maps):
+    """`mg_astar_first_moves` (csrc/astar_host.cu, host-only C++) against one `utils.a_star` run per (start, target) pair - the
+    Python A* being the one pinned to the reference's routes above: non-square maps, blocking cells, pairs without a route."""
+    from gym_multigrid_b200.policy.ctf.device import first_move_table, first_move_table_py
+    rng = np.random.default_rng(12)
+    cases = dict(maps)
+    for i in range(5):
+        r, c = int(rng.integers(2, 9)), int(rng.integers(2, 9))
+        m = np.zeros((r, c))
+        m[rng.random((r, c)) < 0.3] = 8.0
+        cases[f"random{i}"] = m
+    for name, fm in cases.items():
+        native, py = first_move_table(fm), first_move_table_py(fm)
+        assert native.shape == py.shape == (fm.size, fm.size) and np.array_equal(native, py), name
+    with pytest.raises(ValueError):
+        first_move_table(np.zeros((300, 300)))
+
+
 def test_device_tables(maps):
     """`policy/ctf/device.build_tables` (what mg_set_red_policies uploads): the first-move table restates `DestinationPolicy.act`'s
     route step for every (cell, target) pair, the patrol tables restate `PatrolPolicy.get_target`; inputs with no device form
@@ -238,7 +256,7 @@ def test_device_tables(maps):
     with pytest.raises(ValueError):
         build_tables([H.PatrolPolicy(fm), H.PatrolPolicy(fm, ego_agent="red", world=type("W", (), {"OBJECT_TO_IDX": dict(red_territory=0, blue_territory=1, obstacle=6)}))], fm)
     with pytest.raises(ValueError):
-        build_tables([H.FightPolicy()], np.zeros((21, 21)))                   # > 400 cells
+        build_tables([H.FightPolicy()], np.zeros((33, 33)))                   # > 1024 cells
 
 
 @pytest.mark.parametrize("names", [("FightPolicy", "CapturePolicy"), ("PatrolPolicy", "PatrolFightPolicy"), ("FightPolicy", "RwPolicy"),
