@@ -162,6 +162,48 @@ def test_live_differential_against_the_reference(maps):
                 assert ga.integers(0, 2 ** 31) == gb.integers(0, 2 ** 31)
 
 
+def _random_ctf_map(size, seed):
+    """A square CtF map: ragged frontier between the territories, scattered obstacles, one flag each."""
+    rng = np.random.default_rng(seed)
+    fm = np.where(np.arange(size)[:, None] + rng.integers(-2, 3, size=(size, size)) < size // 2, 1.0, 0.0)
+    fm[rng.random(fm.shape) < 0.07] = 6.0
+    fm[1, 1], fm[size - 2, size - 2] = 5.0, 4.0
+    return fm
+
+
+@pytest.mark.parametrize("size,nb,nr,seed", [(12, 2, 3, 1), (9, 4, 2, 2), (16, 1, 1, 3), (7, 3, 5, 4)])
+def test_oracle_rule_on_random_maps(size, nb, nr, seed):
+    """Same comparison on generated maps, team sizes from 1v1 to 3v5 and every assignment of the four policies."""
+    import oracle as oc
+    from gym_multigrid_b200.policy.ctf.device import build_tables
+    fm = _random_ctf_map(size, seed)
+    names = [("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy")[(k + seed) % 4] for k in range(nr)]
+    host = [getattr(H, name)(fm, randomness=1.0, random_generator=np.random.default_rng(0)) for name in names]
+    tables = build_tables(host, fm)
+    n = 48
+    o = oc.CtfOracle(fm.astype(np.uint8), n, nb, nr, max_steps=20)
+    o.reset(oc.map_rng(mode=1, seed=seed))
+    rng = np.random.default_rng(seed)
+    episode = np.zeros(n, np.int32)
+    compared = 0
+    for t in range(45):
+        red = o.policy_actions(tables, seed, episode)
+        blue, reds = o.pos[:, :nb].astype(np.int64), o.pos[:, nb:].astype(np.int64)
+        for e in range(n):
+            obs = policy_observation(fm, blue[e], reds[e])
+            intruder = any(fm[tuple(b)] in (1, 5) for b in blue[e].tolist())
+            for k, p in enumerate(host):
+                cur = tuple(reds[e, k].tolist())
+                patrols = names[k] == "PatrolPolicy" or (names[k] == "PatrolFightPolicy" and not intruder)
+                if patrols and cur in p._border_cells:
+                    continue
+                assert int(p.act(obs, cur)) == int(red[e, k]), (t, e, k, names[k], cur)
+                compared += 1
+        _, _, term, trunc = o.step(rng.integers(0, 5, (n, nb)).astype(np.int8), oc.map_rng(mode=1, seed=seed, red_actions=red), autoreset=True)
+        episode += (term | trunc)
+    assert compared > 1000
+
+
 def test_oracle_rule_of_the_device_policies_matches_the_host_policies():
     """The C restatement of csrc/policy_kernels.cu's decision rule (`oc_ctf_policy_actions`, the checker of
     tests/test_policy_device_gpu.py) against the host policies above, on CtF states stepped by the oracle: with randomness 1
