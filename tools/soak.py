@@ -115,14 +115,32 @@ def soak_ctf(rng, stats):
     steps = int(rng.integers(10, 80))
     ext = bool(rng.integers(0, 3) == 0)
     red = env.set_red_actions(torch.zeros((n, nr), dtype=torch.int8, device=DEV)) if ext else None
+    tables = None
+    if not ext and rng.integers(0, 3) == 0:      # the scripted opponents decided on the device (ctf_policy_kernel) vs the oracle's rule
+        from gym_multigrid_b200.policy.ctf import heuristic as H
+        fmf = fm.astype(np.float64)
+        classes = [H.RwPolicy, H.FightPolicy, H.CapturePolicy, H.PatrolPolicy, H.PatrolFightPolicy]
+        picks = [classes[int(rng.integers(0, 5))] for _ in range(nr)]
+        pols = [c() if c is H.RwPolicy else c(fmf, randomness=float(rng.choice([0.75, 0.3, 1.0]))) for c in picks]
+        try:
+            env.set_enemy_policies(pols, device=True)
+        except ValueError:                        # e.g. a map whose territories do not touch: no border to patrol
+            pass
+        if env._device_policies:
+            tables = env._policy_tables
+            cfg["device_policies"] = [c.__name__ for c in picks]
     for t in range(steps):
         act = rng.integers(0, 5, size=(n, nb)).astype(np.int8)
         ra = None
         if ext:
             ra = rng.integers(0, 5, size=(n, nr)).astype(np.int8)
             red.copy_(torch.as_tensor(ra))
+        elif tables is not None:
+            ra = o.policy_actions(tables, seed, _np(env.episode_count), env_id_base=base)
         obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=DEV))
-        oobs, orew, oterm, otrunc = o.step(act, mk(red_actions=ra) if ext else mk(), autoreset=True)
+        if tables is not None:
+            b += same(_np(env._red_buf), ra, f"ctf device policy actions step {t}", cfg)
+        oobs, orew, oterm, otrunc = o.step(act, mk(red_actions=ra) if ra is not None else mk(), autoreset=True)
         b += same(_np(obs), oobs, f"ctf obs step {t}", cfg) + same(_np(rew), orew, "ctf reward", cfg)
         b += same(_np(term), oterm, "ctf terminated", cfg) + same(_np(trunc), otrunc, "ctf truncated", cfg)
     b += same(_np(env.agent_pos), o.pos, "ctf pos", cfg) + same(_np(env.agent_flags), o.flags, "ctf flags", cfg)
