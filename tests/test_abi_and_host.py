@@ -196,3 +196,36 @@ def test_map_helpers(tmp_path):
         assert tuple(M.closest_area_pos(a, area)) == tuple(R.closest_area_pos(a, area))
         assert M.position_in_positions(a, area) == R.position_in_positions(a, area)
     assert np.array_equal(M.load_text_map(str(p)), R.load_text_map(str(p)))
+
+
+def test_constants_module():
+    """core/constants.py:5-74 and the colour maps of the worlds: against the oracle's rasteriser (pinned to frames recorded from the
+    reference: the centre pixel of a ball tile is the ball's colour, a wall tile is grey) and, where it exists, the reference."""
+    import oracle as oc
+    import gym_multigrid_b200 as mg
+    from gym_multigrid_b200.core import constants as K
+    assert list(K.COLOR_TO_IDX) == ["red", "orange", "yellow", "green", "blue", "purple", "brown", "grey", "light_red", "light_blue"]
+    assert mg.CtfWorld.COLOR_TO_IDX["blue_grey"] == 12 and mg.MazeWorld.COLOR_TO_IDX["white"] == 10 and K.TILE_PIXELS == 32
+    assert [v.tolist() for v in K.DIR_TO_VEC] == [[1, 0], [0, 1], [-1, 0], [0, -1]]
+    obs = np.zeros((1, 10, 1, 3), np.uint8)
+    for c in range(10):
+        obs[0, c, 0] = (mg.CollectWorld.OBJECT_TO_IDX["ball"], c, 0)
+    frame = oc.render_grid(obs, 32)[0]
+    for name, c in K.COLOR_TO_IDX.items():
+        assert frame[16, 32 * c + 16].tolist() == K.COLORS[name].tolist(), name
+    obs[0, 0, 0] = (mg.CollectWorld.OBJECT_TO_IDX["wall"], K.COLOR_TO_IDX["grey"], 0)
+    assert oc.render_grid(obs, 32)[0][16, 16].tolist() == K.COLORS["grey"].tolist()
+    import ref_harness as rh
+    if not rh.reference_available():
+        return
+    rh.import_reference()
+    from gym_multigrid.core import constants as R, world as RW
+    for n in ("COLORS", "CTF_COLORS", "MAZE_COLORS"):
+        a, b = getattr(R, n), getattr(K, n)
+        assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a), n
+    assert R.COLOR_TO_IDX == K.COLOR_TO_IDX and R.STATE_TO_IDX == K.STATE_TO_IDX and R.COLOR_NAMES == K.COLOR_NAMES
+    assert all(np.array_equal(x, y) for x, y in zip(R.DIR_TO_VEC, K.DIR_TO_VEC))
+    for n in ("DefaultWorld", "CollectWorld", "CtfWorld", "MazeWorld"):
+        a, b = getattr(RW, n), getattr(mg, n)
+        assert dict(a.OBJECT_TO_IDX) == dict(b.OBJECT_TO_IDX) and dict(a.COLOR_TO_IDX) == dict(b.COLOR_TO_IDX)
+        assert dict(a.IDX_TO_OBJECT) == dict(b.IDX_TO_OBJECT) and dict(a.IDX_TO_COLOR) == dict(b.IDX_TO_COLOR) and a.encode_dim == b.encode_dim
