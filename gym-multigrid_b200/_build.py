@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmultigrid_b200.so")
-SOURCES = ["collect_kernels.cu", "map_kernels.cu", "view_kernels.cu", "wildfire_kernels.cu", "generic_kernels.cu", "render_kernels.cu", "policy_kernels.cu", "astar_host.cu", "mg_api.cu"]
+SOURCES = ["collect_kernels.cu", "map_kernels.cu", "view_kernels.cu", "wildfire_kernels.cu", "generic_kernels.cu", "render_kernels.cu", "policy_kernels.cu", "astar_host.cu", "host_transport.cpp", "mg_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-shared", "-Xcompiler", "-fPIC"]
 

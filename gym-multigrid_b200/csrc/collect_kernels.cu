@@ -44,9 +44,9 @@ __device__ __forceinline__ int respawn(const CollectParams& p, uint8_t* g, Rng<M
   if (p.layout == MG_LAYOUT_QUADRANTS_RESPAWN) {
     const int q = colour < 3 ? colour : 0;
     const int tx = q == 0 ? 0 : p.W / 2 - 1, ty = q == 1 ? p.H / 2 - 1 : 0;
-    place_obj<MODE>(p, g, r, cell(T_BALL, colour, 0), tx, ty, p.W / 2 + 1, p.H / 2 + 1, x, y);
+    place_obj<MODE>(p, g, r, cell(T_BALL, colour, p.mark_respawned), tx, ty, p.W / 2 + 1, p.H / 2 + 1, x, y);
   } else {
-    place_obj<MODE>(p, g, r, cell(T_BALL, colour, 0), 0, 0, p.W, p.H, x, y);
+    place_obj<MODE>(p, g, r, cell(T_BALL, colour, p.mark_respawned), 0, 0, p.W, p.H, x, y);
   }
   return x * p.H + y;  // the cell that received the ball
 }
@@ -157,9 +157,11 @@ struct TileSmem {
   uint8_t* trunc;  // [E]                 out
   uint8_t* done;   // [E]
   uint16_t* chg;   // [E][3A] cells written by the step (index x*H+y), for patching the pre-expanded obs
+  uint8_t* delta;  // [E][delta_record_bytes] compact host-transport records (bytes 1..A double as the per-agent pickup scratch)
 };
 __host__ __device__ inline size_t tile_smem_bytes(int E, int cells, int A) {
-  return (size_t)E * cells * 4 + (size_t)E * 16 + (size_t)E * A * 8 + (size_t)E * A * 4 + (size_t)E * 3 + (size_t)E * A * 6 + 16;
+  return (size_t)E * cells * 4 + (size_t)E * 16 + (size_t)E * A * 8 + (size_t)E * A * 4 + (size_t)E * 3 + (size_t)E * A * 6 + 16 +
+         (size_t)E * delta_record_bytes(cells, A) + 16;
 }
 __device__ __forceinline__ TileSmem carve(uint8_t* base, int E, int cells, int A) {
   TileSmem s;
@@ -174,6 +176,7 @@ __device__ __forceinline__ TileSmem carve(uint8_t* base, int E, int cells, int A
   s.trunc = s.term + E;
   s.done = s.trunc + E;
   s.chg = reinterpret_cast<uint16_t*>(s.done + E + (E & 1));
+  s.delta = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s.chg + (size_t)E * 3 * A) + 15) & ~(uintptr_t)15);
   return s;
 }
 
@@ -207,7 +210,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 template <int MODE>
 __device__ __forceinline__ int step_one_env(const CollectParams& p, long long e, uint8_t* g, uint8_t* pos, uint8_t* ord,
                                             const int8_t* act, double* rew, int4& h, Rng<MODE>& r, bool& term, bool& trunc,
-                                            uint16_t* chg, int& nchg) {
+                                            uint16_t* chg, int& nchg, uint8_t* pick) {
   const int A = p.A;
   int err = 0;
   if (MODE == 1) {  // production order: Fisher-Yates over Philox draws (trace mode replays np.random.permutation)
@@ -217,7 +220,7 @@ __device__ __forceinline__ int step_one_env(const CollectParams& p, long long e,
       const uint8_t t = ord[i]; ord[i] = ord[j]; ord[j] = t;
     }
   }
-  for (int i = 0; i < A; ++i) rew[i] = 0.0;  // :187
+  for (int i = 0; i < A; ++i) { rew[i] = 0.0; pick[i] = 0; }  // :187
   h.x += 1;                                  // step_count += 1 :190
   for (int k = 0; k < A; ++k) {              // for i in order :191
     const int i = ord[k];
@@ -234,7 +237,9 @@ __device__ __forceinline__ int step_one_env(const CollectParams& p, long long e,
       GCELL(g, p.H, nx, ny) = 0;                 // grid.set(*fwd_pos, None) :141
       if (p.respawn) chg[nchg++] = (uint16_t)respawn<MODE>(p, g, r, colour);  // :142-143 -- may land on (nx, ny)
       h.y += 1;                                  // collected_balls += 1 :144
-      rew[i] += p.reward_of_colour[colour];      // _reward(i, rewards, fwd_cell.reward) :145
+      const int resp = (c >> 6) & 1;             // placed by _respawn (only marked when its reward differs, mg_create)
+      rew[i] += resp ? p.reward_respawned[colour] : p.reward_initial[colour];  // _reward(i, rewards, fwd_cell.reward) :145
+      pick[i] = (uint8_t)(1 + (colour | (resp << 4)));
       const int t = p.type_of_colour[colour];
       if (t >= 0) atomicAdd(&p.info[e * (A * p.nb) + p.nb * i + t], 1);  // info[keys[nb*i + ball_idx]] += 1 :147 (fire-and-forget RED)
       enter = true;
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
   const long long e0 = (long long)blockIdx.x * E;
   const int n_here = (int)min((long long)E, p.N - e0);
   const uint32_t grid_bytes = (uint32_t)E * cells;
+  const int R = delta_record_bytes(cells, A);
   // the caller's per-env arrays are not padded: bulk copies only for full tiles with aligned pointers
   const bool io_bulk = p.io_bulk_ok && n_here == E;
   unsigned long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 8 : nullptr;
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
     else r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
     bool term, trunc;
     err = step_one_env<MODE>(p, e, s.grid + (size_t)tid * cells, s.pos + tid * A * 2, s.ord + tid * A, s.act + tid * A,
-                             s.rew + tid * A, h, r, term, trunc, chg, nchg);
+                             s.rew + tid * A, h, r, term, trunc, chg, nchg, s.delta + (size_t)tid * R + 1);
     s.term[tid] = term; s.trunc[tid] = trunc;
     if (MODE == 0 && p.draws_used) p.draws_used[e] = r.k;
     done = p.autoreset && (term || trunc);
@@ -347,9 +353,21 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
       for (int k = 0; k < nchg; ++k) {
         const int idx = chg[k];
         const uint8_t c = g[idx];
-        o[3 * idx] = c & 3; o[3 * idx + 1] = (c >> 2) & 15; o[3 * idx + 2] = c >> 6;
-        if (go) { go[3 * idx] = c & 3; go[3 * idx + 1] = (c >> 2) & 15; go[3 * idx + 2] = c >> 6; }
+        o[3 * idx] = c & 3; o[3 * idx + 1] = (c >> 2) & 15; o[3 * idx + 2] = state_of(c);
+        if (go) { go[3 * idx] = c & 3; go[3 * idx + 1] = (c >> 2) & 15; go[3 * idx + 2] = state_of(c); }
       }
+    }
+  }
+
+  if (p.delta && tid < n_here) {  // compact host transport: the cells this env's step wrote, with their post-step codes
+    const uint8_t* g = s.grid + (size_t)tid * cells;
+    uint8_t* rec = s.delta + (size_t)tid * R;
+    rec[0] = (uint8_t)(nchg | (s.term[tid] << 5) | (s.trunc[tid] << 6) | ((int)done << 7));
+    uint8_t* ent = rec + 1 + A;
+    if (!p.delta_wide) {
+      for (int k = 0; k < nchg; ++k) { const int idx = chg[k]; ent[2 * k] = (uint8_t)idx; ent[2 * k + 1] = g[idx]; }
+    } else {
+      for (int k = 0; k < nchg; ++k) { const int idx = chg[k]; ent[3 * k] = (uint8_t)idx; ent[3 * k + 1] = (uint8_t)(idx >> 8); ent[3 * k + 2] = g[idx]; }
     }
   }
 
@@ -383,9 +401,26 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
       err |= rr.err;
       h.x = 0; h.y = 0; h.w += 1;  // step_count, collected_balls (:108, multigrid.py:141); episode counter
       for (int k = 0; k < A * p.nb; ++k) p.info[e * (A * p.nb) + k] = 0;  // :109-116
+      // compact host transport: claim a slot for this env's fresh row (every chg list has been consumed above)
+      if (p.delta) reinterpret_cast<int*>(s.chg)[tid] = atomicAdd(p.reset_count, 1);
     }
     __syncthreads();
     if (p.obs) expand_tile<THREADS>(s.grid, s.obs, n16, tid);  // re-encode (the reset envs changed everywhere)
+    if (p.delta) {
+      const int* slots = reinterpret_cast<const int*>(s.chg);
+      for (int j = 0; j < n_here; ++j) {
+        if (!s.done[j]) continue;
+        uint8_t* dst_row = p.reset_rows + (size_t)slots[j] * p.reset_stride;
+        if (tid == 0) *reinterpret_cast<int32_t*>(dst_row) = (int32_t)(e0 + j);
+        if ((cells & 3) == 0) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(s.grid + (size_t)j * cells);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(dst_row + 4);
+          for (int i = tid; i < cells / 4; i += THREADS) dst[i] = src[i];
+        } else {
+          for (int i = tid; i < cells; i += THREADS) dst_row[4 + i] = s.grid[(size_t)j * cells + i];
+        }
+      }
+    }
   }
   if (tid < n_here) {
     if (MODE == 1) h.z = (int)r.ctr;
@@ -411,8 +446,10 @@ __global__ void __launch_bounds__(THREADS, min_blocks(E, THREADS)) collect_step_
       tma_store_1d(p.terminated + e0, s.term, (uint32_t)E);
       tma_store_1d(p.truncated + e0, s.trunc, (uint32_t)E);
     }
+    if (p.delta && n_here == E) tma_store_1d(p.delta + e0 * R, s.delta, (uint32_t)E * R);
     tma_commit();
   }
+  if (p.delta && n_here != E) copy_out_tail<THREADS>(p.delta + e0 * R, s.delta, 0u, (uint32_t)n_here * R, tid);
   if (p.obs && !obs_done) copy_out_tail<THREADS>(p.obs + e0 * 3 * cells, s.obs, obs_bulk, obs_bytes, tid);
   if (!io_bulk) {
     for (int i = tid; i < n_here * A; i += THREADS) p.rewards[e0 * A + i] = s.rew[i];

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/multigrid_b200.h"
+#include "host_transport.h"
 #include "mg_device.cuh"
 #include "smem_config.h"
 
@@ -101,6 +102,19 @@ struct mg_env {
   long long launches;
   unsigned long long* timeline;
   std::string err;
+  // compact host transports (mg_set_host_transport; Collect family)
+  int transport;             // MG_TRANSPORT_*
+  int host_threads;
+  uint8_t* d_delta_blk;      // [16-byte header: int32 reset count][N x delta records]
+  uint8_t* d_reset_rows;     // [N][reset_stride]: int32 env index + packed row
+  uint8_t* h_delta_blk;      // page-locked mirrors of the two, plus the packed grid plane for full refreshes
+  uint8_t* h_reset_rows;
+  uint8_t* h_grid;
+  size_t reset_stride;
+  double reward_table[33];
+  const uint8_t* mirror;     // the caller's obs buffer the delta transport patches in place
+  bool mirror_valid;
+  struct { bool active, refresh, plane; mg_step_io io; } pend;
 };
 
 static thread_local std::string g_create_err;
@@ -210,12 +224,27 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   p.fixed_horizon = cfg->fixed_horizon != 0; p.max_steps = cfg->max_steps; p.time_limit = cfg->time_limit;
   p.autoreset = cfg->autoreset != 0;
   for (int i = 0; i < A; ++i) p.agent_code[i] = mg::cell(mg::T_AGENT, cfg->agent_colour[i], 3);  // dir 3, multigrid.py:371-374
-  for (int c = 0; c < 16; ++c) { p.type_of_colour[c] = -1; p.reward_of_colour[c] = 1.0; }  // Ball(world, index, 1) collect_game.py:391
+  // Ball.reward is an attribute of the ball OBJECT with two possible values in the reference:
+  //   placed by _gen_grid: balls_reward[type] (collect_game.py:98-101, :252, :287, :354, :359), QuadrantsRespawn: the literal 1 (:393);
+  //   placed by _respawn:  balls_reward[COLOUR index] (:130, :409).  Where that raises in the reference (colour >= len(balls_reward):
+  //   IndexError) the initial value is kept.  If the two differ for a colour this env can hold, respawned balls carry bit 6.
+  for (int c = 0; c < 16; ++c) { p.type_of_colour[c] = -1; p.reward_initial[c] = 1.0; }
   for (int t = nb - 1; t >= 0; --t) {
     p.ball_colour[t] = (uint8_t)cfg->ball_colour[t];
     p.type_of_colour[cfg->ball_colour[t]] = (int8_t)t;
-    p.reward_of_colour[cfg->ball_colour[t]] = cfg->ball_reward[t];
+    if (cfg->layout != MG_LAYOUT_QUADRANTS_RESPAWN) p.reward_initial[cfg->ball_colour[t]] = cfg->ball_reward[t];
   }
+  for (int c = 0; c < 16; ++c) p.reward_respawned[c] = c < nb ? cfg->ball_reward[c] : p.reward_initial[c];
+  p.mark_respawned = 0;
+  if (cfg->respawn) {
+    if (cfg->layout == MG_LAYOUT_QUADRANTS_RESPAWN) {
+      for (int c = 0; c < 3; ++c) if (p.reward_initial[c] != p.reward_respawned[c]) p.mark_respawned = 1;
+    } else {
+      for (int t = 0; t < nb; ++t) if (p.reward_initial[cfg->ball_colour[t]] != p.reward_respawned[cfg->ball_colour[t]]) p.mark_respawned = 1;
+    }
+  }
+  env->reward_table[0] = 0.0;
+  for (int c = 0; c < 16; ++c) { env->reward_table[1 + c] = p.reward_initial[c]; env->reward_table[17 + c] = p.reward_respawned[c]; }
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.rng_mode = 1;
   { const char* v = std::getenv("MG_EARLY_OBS"); p.early_obs = !(v && v[0] == '0'); }   // A/B switch for the early observation store
@@ -252,6 +281,8 @@ extern "C" int mg_destroy(mg_env* env) {
   cudaFree(env->d_flat_tmpl);
   cudaFree(env->d_policy_tables);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);   // rewards / term / trunc live inside the d_obs block
+  cudaFree(env->d_delta_blk); cudaFree(env->d_reset_rows);
+  cudaFreeHost(env->h_delta_blk); cudaFreeHost(env->h_reset_rows); cudaFreeHost(env->h_grid);
   delete env;
   return 0;
 }
@@ -829,13 +860,14 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   mg::CollectParams p = env->base;
   bind_state(env, p, state);
   bind_trace(env, p);
+  env->mirror_valid = false;   // the delta transport's host mirror no longer matches the state
   p.reset_mask = mask; p.obs = obs; p.obs_bulk_ok = aligned16(obs);
   if ((ce = mg::launch_collect_reset(env->tile, p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "collect_reset_kernel", ce);
   env->launches += 1;
   return 0;
 }
 
-static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
+static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st, bool with_delta = false) {
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
   if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
   if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 1, io, nullptr, nullptr, st);
@@ -850,6 +882,11 @@ static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStrea
   p.obs_bulk_ok = aligned16(io->obs);
   p.io_bulk_ok = aligned16(io->actions) && aligned16(io->rewards) && aligned16(io->terminated) && aligned16(io->truncated);
   p.timeline = env->timeline;
+  if (with_delta) {
+    p.delta = env->d_delta_blk + 16; p.delta_stride = mg::delta_record_bytes(p.cells, p.A); p.delta_wide = p.cells > 256;
+    p.reset_count = reinterpret_cast<int32_t*>(env->d_delta_blk);
+    p.reset_rows = env->d_reset_rows; p.reset_stride = (int)env->reset_stride;
+  }
   cudaError_t ce;
   if ((ce = mg::launch_collect_step(env->tile, p, st)) != cudaSuccess) return cuda_fail(env, "collect_step_kernel", ce);
   env->launches += 1;
@@ -861,6 +898,7 @@ extern "C" int mg_step(mg_env* env, void* state, const mg_step_io* io, void* str
   if (!aligned16(state)) return fail(env, "mg_step: state buffer must be 16-byte aligned");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  env->mirror_valid = false;
   return step_device(env, state, io, static_cast<cudaStream_t>(stream));
 }
 
@@ -987,24 +1025,190 @@ extern "C" int mg_host_layout(const mg_env* env, size_t* off_rewards, size_t* of
   return 0;
 }
 
+// ---- compact host transports (Collect family) ----------------------------------------------------------------------
+static int transport_alloc(mg_env* env) {
+  if (env->d_delta_blk) return 0;
+  const size_t N = (size_t)env->cfg.num_envs, cells = (size_t)env->base.cells;
+  const size_t R = (size_t)mg::delta_record_bytes(env->base.cells, env->base.A);
+  env->reset_stride = align_up(cells, 4) + 4;
+  cudaError_t ce;
+  if ((ce = cudaMalloc(&env->d_delta_blk, 16 + N * R)) != cudaSuccess ||
+      (ce = cudaMalloc(&env->d_reset_rows, N * env->reset_stride)) != cudaSuccess ||
+      (ce = cudaHostAlloc(&env->h_delta_blk, 16 + N * R, cudaHostAllocDefault)) != cudaSuccess ||
+      (ce = cudaHostAlloc(&env->h_reset_rows, N * env->reset_stride, cudaHostAllocDefault)) != cudaSuccess ||
+      (ce = cudaHostAlloc(&env->h_grid, N * cells, cudaHostAllocDefault)) != cudaSuccess) {
+    cudaFree(env->d_delta_blk); cudaFree(env->d_reset_rows);
+    cudaFreeHost(env->h_delta_blk); cudaFreeHost(env->h_reset_rows); cudaFreeHost(env->h_grid);
+    env->d_delta_blk = env->d_reset_rows = env->h_delta_blk = env->h_reset_rows = env->h_grid = nullptr;
+    return cuda_fail(env, "mg_set_host_transport: staging buffers", ce);
+  }
+  return 0;
+}
+
+extern "C" int mg_set_host_transport(mg_env* env, int mode, int host_threads) {
+  if (!env) return -1;
+  if (mode != MG_TRANSPORT_FULL && mode != MG_TRANSPORT_PACKED && mode != MG_TRANSPORT_DELTA) return fail(env, "mg_set_host_transport: unknown mode");
+  if (mode != MG_TRANSPORT_FULL && env->family != MG_FAMILY_COLLECT) return fail(env, "mg_set_host_transport: the compact transports exist for the Collect family only");
+  if (env->pend.active) return fail(env, "mg_set_host_transport: a host step is still in flight (mg_step_host_wait first)");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if (mode != MG_TRANSPORT_FULL && transport_alloc(env)) return -1;
+  env->host_threads = host_threads > 0 ? host_threads : mg::host_default_threads();
+  if (mode != MG_TRANSPORT_FULL) mg::host_pool_ensure(env->host_threads);
+  env->transport = mode;
+  env->mirror = nullptr; env->mirror_valid = false;
+  return 0;
+}
+
+extern "C" int mg_host_invalidate(mg_env* env) {
+  if (!env) return -1;
+  env->mirror_valid = false;
+  return 0;
+}
+
+extern "C" int mg_host_expand_plane(const uint8_t* grid, uint8_t* obs, size_t n_cells, int host_threads) {
+  if (!grid || !obs) return -1;
+  const int t = host_threads > 0 ? host_threads : mg::host_default_threads();
+  mg::host_pool_ensure(t);
+  mg::host_expand_plane(grid, obs, n_cells, t);
+  return 0;
+}
+
+extern "C" int mg_host_apply_delta(const uint8_t* records, size_t n, int cells, int num_agents, const double* reward_table, uint8_t* obs,
+                                   double* rewards, uint8_t* terminated, uint8_t* truncated, uint8_t* final_obs, int host_threads) {
+  if (!records || !reward_table || cells < 1 || num_agents < 1 || num_agents > MG_MAX_AGENTS) return -1;
+  const int t = host_threads > 0 ? host_threads : mg::host_default_threads();
+  mg::host_pool_ensure(t);
+  mg::HostDeltaJob j;
+  j.records = records; j.n = n; j.stride = mg::delta_record_bytes(cells, num_agents); j.wide = cells > 256; j.cells = cells; j.A = num_agents;
+  j.reward_table = reward_table; j.obs = obs; j.skip_patches = 0; j.rewards = rewards; j.terminated = terminated; j.truncated = truncated;
+  j.final_obs = final_obs;
+  mg::host_apply_delta(j, t);
+  return 0;
+}
+
+extern "C" int mg_delta_record_bytes(int cells, int num_agents) { return mg::delta_record_bytes(cells, num_agents); }
+
+// H2D actions -> step -> D2H of the step's compact results into the handle's page-locked staging; decoded by finish_host_step
+static int step_host_compact(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
+  if (!aligned16(state)) return fail(env, "mg_step_host: state buffer must be 16-byte aligned");
+  const size_t N = (size_t)env->cfg.num_envs, A = (size_t)env->act_cols, cells = (size_t)env->base.cells;
+  const size_t R = (size_t)mg::delta_record_bytes(env->base.cells, env->base.A);
+  cudaError_t ce;
+  if (!env->d_actions) {
+    size_t off_r, off_t, off_u, total;
+    host_layout(env, &off_r, &off_t, &off_u, &total);
+    int8_t* da = nullptr; uint8_t* dobs = nullptr;
+    if ((ce = cudaMalloc(&da, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMalloc(&dobs, total)) != cudaSuccess) { cudaFree(da); return cuda_fail(env, "cudaMalloc", ce); }
+    if ((ce = cudaMemsetAsync(dobs, 0, total, st)) != cudaSuccess) { cudaFree(da); cudaFree(dobs); return cuda_fail(env, "cudaMemsetAsync", ce); }
+    env->d_actions = da; env->d_obs = dobs;
+    env->d_rewards = reinterpret_cast<double*>(dobs + off_r); env->d_term = dobs + off_t; env->d_trunc = dobs + off_u;
+  }
+  const bool delta = env->transport == MG_TRANSPORT_DELTA;
+  // the delta transport patches the caller's obs buffer in place: it must be the buffer the previous host step filled
+  const bool refresh = delta && io->obs && (!env->mirror_valid || env->mirror != io->obs);
+  const bool want_plane = io->obs && (!delta || refresh);
+  const bool dev_final = io->final_obs && (!delta || refresh);   // no valid mirror to take the terminal rows from
+  const size_t ob = mg_obs_bytes(env);
+  if (dev_final && !env->d_final) {
+    if ((ce = cudaMalloc(&env->d_final, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMemsetAsync(env->d_final, 0, ob, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
+  }
+  if ((ce = cudaMemcpyAsync(env->d_actions, io->actions, N * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(env, "H2D actions", ce);
+  if (delta && (ce = cudaMemsetAsync(env->d_delta_blk, 0, 16, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
+  mg_step_io dio;
+  dio.actions = env->d_actions; dio.rewards = env->d_rewards; dio.terminated = env->d_term; dio.truncated = env->d_trunc;
+  dio.obs = dev_final ? static_cast<uint8_t*>(env->d_obs) : nullptr;   // the expanded observation stays off the wire
+  dio.final_obs = dev_final ? env->d_final : nullptr;
+  if (step_device(env, state, &dio, st, delta)) return -1;
+  if (delta) {
+    if ((ce = cudaMemcpyAsync(env->h_delta_blk, env->d_delta_blk, 16 + N * R, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H delta records", ce);
+  } else {
+    size_t off_r, off_t, off_u, total;
+    host_layout(env, &off_r, &off_t, &off_u, &total);
+    const uint8_t* hr = reinterpret_cast<const uint8_t*>(io->rewards);
+    if (io->terminated == hr + (off_t - off_r) && io->truncated == hr + (off_u - off_r)) {   // one block on the host as well: one copy
+      if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, total - off_r, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards / flags", ce);
+    } else {
+      if ((ce = cudaMemcpyAsync(io->rewards, env->d_rewards, N * (size_t)env->rew_cols * sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H rewards", ce);
+      if ((ce = cudaMemcpyAsync(io->terminated, env->d_term, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H terminated", ce);
+      if ((ce = cudaMemcpyAsync(io->truncated, env->d_trunc, N, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H truncated", ce);
+    }
+  }
+  if (want_plane) {
+    const uint8_t* grid = static_cast<const uint8_t*>(state) + env->plane_off[MG_PLANE_GRID];
+    if ((ce = cudaMemcpyAsync(env->h_grid, grid, N * cells, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H grid plane", ce);
+  }
+  if (dev_final && (ce = cudaMemcpyAsync(io->final_obs, env->d_final, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H final_obs", ce);
+  env->pend.active = true; env->pend.refresh = refresh; env->pend.plane = want_plane; env->pend.io = *io;
+  return 0;
+}
+
+// after the stream has drained: decode the staged results into the caller's buffers
+static int finish_host_step(mg_env* env, cudaStream_t st) {
+  if (!env->pend.active) return 0;
+  env->pend.active = false;
+  const mg_step_io& io = env->pend.io;
+  const size_t N = (size_t)env->cfg.num_envs, cells = (size_t)env->base.cells;
+  const int T = env->host_threads;
+  if (env->transport == MG_TRANSPORT_PACKED) {
+    if (io.obs) mg::host_expand_plane(env->h_grid, io.obs, N * cells, T);
+    return 0;
+  }
+  mg::HostDeltaJob j;
+  j.records = env->h_delta_blk + 16; j.n = N; j.stride = mg::delta_record_bytes(env->base.cells, env->base.A);
+  j.wide = env->base.cells > 256; j.cells = env->base.cells; j.A = env->base.A; j.reward_table = env->reward_table;
+  j.obs = io.obs; j.skip_patches = env->pend.refresh; j.rewards = io.rewards; j.terminated = io.terminated; j.truncated = io.truncated;
+  j.final_obs = env->pend.refresh ? nullptr : io.final_obs;
+  mg::host_apply_delta(j, T);
+  if (!io.obs) { env->mirror_valid = false; return 0; }   // nothing was patched: a mirror kept by the caller is now stale
+  if (env->pend.refresh) {
+    mg::host_expand_plane(env->h_grid, io.obs, N * cells, T);
+  } else {
+    int32_t count;
+    std::memcpy(&count, env->h_delta_blk, 4);
+    if (count < 0 || (size_t)count > N) return fail(env, "mg_step_host: corrupt reset count");
+    if (count > 0) {   // rows of the envs that autoreset this step: a second, count-sized copy
+      cudaError_t ce;
+      if ((ce = cudaMemcpyAsync(env->h_reset_rows, env->d_reset_rows, (size_t)count * env->reset_stride, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        return cuda_fail(env, "D2H reset rows", ce);
+      if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
+      mg::host_apply_rows(env->h_reset_rows, env->reset_stride, (size_t)count, env->base.cells, io.obs, T);
+    }
+  }
+  env->mirror = io.obs; env->mirror_valid = true;
+  return 0;
+}
+
 static int step_host_enqueue(mg_env* env, void* state, const mg_step_io* io, void* stream, bool wait) {
   if (!env || !state || !io) return fail(env, "mg_step_host: null argument");
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step_host: actions/rewards/terminated/truncated must be non-null");
+  if (io->final_obs && !io->obs) return fail(env, "mg_step_host: final_obs needs obs");
+  if (env->pend.active) return fail(env, "mg_step_host: the previous host step has not been waited for (mg_step_host_wait)");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t N = (size_t)(env->family == MG_FAMILY_COLLECT ? env->cfg.num_envs : env->family == MG_FAMILY_WILDFIRE ? env->wcfg.num_envs : env->family == MG_FAMILY_GENERIC ? env->gcfg.num_envs : env->mcfg.num_envs);
+  if (env->transport != MG_TRANSPORT_FULL) {
+    if (step_host_compact(env, state, io, st)) return -1;
+    if (!wait) return 0;
+    if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaStreamSynchronize", ce); }
+    return finish_host_step(env, st);
+  }
+  const size_t N = env_count(env);
   const size_t A = (size_t)env->act_cols, R = (size_t)env->rew_cols, ob = mg_obs_bytes(env);
   // device staging: ONE block laid out obs | rewards | terminated | truncated (256-byte aligned parts, see mg_host_layout):
   // a caller whose host buffers use the same layout gets a single device-to-host copy per step
   size_t off_r, off_t, off_u, total;
   host_layout(env, &off_r, &off_t, &off_u, &total);
-  if (!env->d_actions) {
-    if ((ce = cudaMalloc(&env->d_actions, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMalloc(&env->d_obs, total)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
-    if ((ce = cudaMemsetAsync(env->d_obs, 0, total, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
-    env->d_rewards = reinterpret_cast<double*>(env->d_obs + off_r);
-    env->d_term = env->d_obs + off_t; env->d_trunc = env->d_obs + off_u;
+  if (!env->d_actions) {   // committed to the handle only when both allocations succeeded
+    int8_t* da = nullptr; uint8_t* dobs = nullptr;
+    if ((ce = cudaMalloc(&da, N * A)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
+    if ((ce = cudaMalloc(&dobs, total)) != cudaSuccess) { cudaFree(da); return cuda_fail(env, "cudaMalloc", ce); }
+    if ((ce = cudaMemsetAsync(dobs, 0, total, st)) != cudaSuccess) { cudaFree(da); cudaFree(dobs); return cuda_fail(env, "cudaMemsetAsync", ce); }
+    env->d_actions = da; env->d_obs = dobs;
+    env->d_rewards = reinterpret_cast<double*>(dobs + off_r);
+    env->d_term = dobs + off_t; env->d_trunc = dobs + off_u;
   }
   if (io->final_obs && !env->d_final) {
     if ((ce = cudaMalloc(&env->d_final, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
@@ -1014,6 +1218,7 @@ static int step_host_enqueue(mg_env* env, void* state, const mg_step_io* io, voi
   mg_step_io dio;
   dio.actions = env->d_actions; dio.obs = io->obs ? static_cast<uint8_t*>(static_cast<void*>(env->d_obs)) : nullptr; dio.rewards = env->d_rewards;
   dio.terminated = env->d_term; dio.truncated = env->d_trunc; dio.final_obs = io->final_obs ? env->d_final : nullptr;
+  env->mirror_valid = false;
   if (step_device(env, state, &dio, st)) return -1;
   const uint8_t* hb = static_cast<const uint8_t*>(static_cast<const void*>(io->obs));
   const bool one_copy = io->obs && reinterpret_cast<const uint8_t*>(io->rewards) == hb + off_r && io->terminated == hb + off_t && io->truncated == hb + off_u;
@@ -1042,8 +1247,8 @@ extern "C" int mg_step_host_wait(mg_env* env, void* stream) {
   if (!env) return -1;
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
-  if ((ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
-  return 0;
+  if ((ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream))) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaStreamSynchronize", ce); }
+  return finish_host_step(env, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mg_set_seed(mg_env* env, uint64_t seed) {

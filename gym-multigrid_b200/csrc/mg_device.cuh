@@ -29,7 +29,9 @@ struct CollectParams {
   uint8_t agent_code[MG_MAX_AGENTS];   // cell(T_AGENT, agents_index[i], dir = 3)
   uint8_t ball_colour[MG_MAX_BALL_TYPES];
   int8_t type_of_colour[16];
-  double reward_of_colour[16];
+  double reward_initial[16];      // fwd_cell.reward of a ball placed by _gen_grid, by colour (QuadrantsRespawn: the literal 1, collect_game.py:393)
+  double reward_respawned[16];    // ... of a ball placed by _respawn: balls_reward[colour] (collect_game.py:130, :409)
+  int mark_respawned;             // 1 = the two tables differ somewhere: respawned balls carry bit 6 of their cell (never shown: a ball's STATE is 0)
   long long N;            // envs on this device
   unsigned long long env_id_base, seed;
   // state planes (caller-owned buffer)
@@ -62,7 +64,22 @@ struct CollectParams {
   int io_bulk_ok;         // actions / rewards / terminated / truncated pointers are 16-byte aligned
   unsigned long long* timeline;  // optional [tiles][8] per-CTA phase timestamps (globaltimer ns), profiling only
   int early_obs;          // 1 = full tiles store the pre-step observation slab while the agents are stepped and patch the <= 3A changed cells in place
+  // compact host transport (mg_set_host_transport, MG_TRANSPORT_DELTA): one record per env with the cells the step wrote, plus the
+  // packed rows of the envs that autoreset, compacted behind a device counter.  Record (delta_stride bytes, see delta_record_bytes):
+  //   byte 0      n_changes (bits 0-4) | terminated << 5 | truncated << 6 | autoreset << 7
+  //   bytes 1..A  per agent: 0 = no pickup, else 1 + (ball colour | respawned << 4)   (the reward is a table lookup on the host)
+  //   then 3A entries (cell index u8 when W*H <= 256 else u16 little endian, packed cell code u8), n_changes of them valid
+  uint8_t* delta;
+  int delta_stride, delta_wide;
+  int32_t* reset_count;   // zeroed by the host before the launch
+  uint8_t* reset_rows;    // [N][reset_stride]: int32 env index (on this device) followed by the env's fresh packed row
+  int reset_stride;       // 4 + W*H rounded up to a multiple of 4
 };
+
+__host__ __device__ inline int delta_record_bytes(int cells, int A) {
+  const int entry = cells <= 256 ? 2 : 3;
+  return (1 + A + 3 * A * entry + 3) & ~3;
+}
 
 // ------------------------------------------------------------------------ Philox4x32-10
 // Salmon et al. SC'11.  Production-mode generator (the reference's python `random` and legacy
@@ -183,9 +200,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // 16 packed cells (one uint4) -> 48 obs bytes (three uint4), byte order (type, colour, state).
 // four cells given as separate type / colour / state byte planes -> 12 interleaved obs bytes
 __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2);
+// STATE is the agent's dir (type 3); a Collect ball (type 2) may carry the internal "respawned" mark in bit 6, which is not
+// part of the observation: WorldObj.encode gives (type, colour, 0) for it (object.py:58-74).
 __device__ __forceinline__ void expand4(uint32_t w, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
-  interleave3(w & 0x03030303u, (w >> 2) & 0x0F0F0F0Fu, (w >> 6) & 0x03030303u, o0, o1, o2);
+  const uint32_t ball = (w >> 1) & ~w & 0x01010101u;
+  interleave3(w & 0x03030303u, (w >> 2) & 0x0F0F0F0Fu, (w >> 6) & 0x03030303u & ~(ball * 3u), o0, o1, o2);
 }
+__device__ __forceinline__ uint8_t state_of(uint8_t c) { return (c & 3) == T_BALL ? 0 : (uint8_t)(c >> 6); }
 __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
   // out bytes: t0 c0 s0 t1 | c1 s1 t2 c2 | s2 t3 c3 s3
   const uint32_t tc = __byte_perm(t, c, 0x5140);   // t0 c0 t1 c1  (bytes: [t0, c0, t1, c1])

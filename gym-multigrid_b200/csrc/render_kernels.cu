@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(kRenderThreads) render_kernel(const __grid_con
   for (int t = tid; t < jn * W; t += kRenderThreads) {
     const int jj = t / W, i = t - jj * W, j = j0 + jj;
     int code;
-    if (p.family == 0) code = p.cells[e * (long long)(W * p.H) + i * p.H + j];
+    if (p.family == 0) {
+      code = p.cells[e * (long long)(W * p.H) + i * p.H + j];
+      if ((code & 3) == 2) code &= 0x3F;   // a ball's bit 6 is the step's internal "respawned" mark, not part of its appearance
+    }
     else {
       code = p.cells[i * p.H + j];
       const uint8_t* a = p.agents + e * p.agent_stride;   // the agent object replaces the cell it stands on (agent.py:195-196)

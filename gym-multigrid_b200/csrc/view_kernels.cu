@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kViewThreads) view_kernel(const __grid_constan
     for (int a = 0; a < V; ++a)
       for (int b = 0; b < V; ++b) {  // encode_for_agents: cells outside the mask stay (0, 0, 0)
         const uint8_t c = ((msk[b] >> a) & 1u) ? code[a * V + b] : 0;
-        o[(a * V + b) * 3] = c & 3; o[(a * V + b) * 3 + 1] = (c >> 2) & 15; o[(a * V + b) * 3 + 2] = c >> 6;
+        o[(a * V + b) * 3] = c & 3; o[(a * V + b) * 3 + 1] = (c >> 2) & 15; o[(a * V + b) * 3 + 2] = state_of(c);
       }
   }
   fence_proxy_async_smem();

@@ -43,7 +43,7 @@ class CollectVecEnv(VectorEnvSurface):
     def __init__(self, num_envs, size=10, num_balls=15, agents_index=(3, 5), balls_index=(0, 1, 2),
                  balls_reward=(1, 1, 1), respawn=False, layout="even_dist", fixed_horizon=False,
                  max_steps=100, max_episode_steps=None, device="cuda:0", seed=0, autoreset=True,
-                 env_id_base=0, width=None, height=None):
+                 env_id_base=0, width=None, height=None, host_transport="delta", host_threads=None):
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -126,6 +126,25 @@ class CollectVecEnv(VectorEnvSurface):
         self._io = _lib.StepIO()
         self.closed = False
         self._bind_io()
+        self.set_host_transport(host_transport, host_threads)
+
+    def set_host_transport(self, mode="delta", host_threads=None):
+        """What `step(numpy)` / `step_async` move over PCIe for the observation (mg_set_host_transport): "full" = the expanded
+        (W, H, 3) array (300 B per 10x10 env), "packed" = the 1-byte-per-cell grid plane expanded on the host, "delta" (default) =
+        a 16-byte record of the cells the step changed, patched into the page-locked observation buffer this env returns (plus
+        the packed rows of the envs that autoreset).  The results are identical; only the bytes on the wire differ.
+        `host_threads`: host threads of the decoder (default: this process's cores / LOCAL_WORLD_SIZE)."""
+        import os
+        if host_threads is None:
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except AttributeError:
+                cores = os.cpu_count() or 1
+            host_threads = max(1, min(32, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        if getattr(self, "_host_pending", False):
+            raise RuntimeError("set_host_transport while a step_async is in flight")
+        self._check(self._lib.mg_set_host_transport(self._h, _lib.TRANSPORTS[mode], int(host_threads)))
+        self.host_transport, self.host_threads = mode, int(host_threads)
 
     def _bind_io(self):
         """Everything `step` needs that does not change from call to call: the output pointers of the io block, the bool views
@@ -310,12 +329,14 @@ class CollectVecEnv(VectorEnvSurface):
         self._planes["hdr"][:, 0] = step_count
         self._planes["hdr"][:, 1] = 0
         self._planes["info"].zero_()
+        self._lib.mg_host_invalidate(self._h)
 
     def get_state(self):
         return self.state.clone()
 
     def set_state(self, state):
         self.state.copy_(state)
+        self._lib.mg_host_invalidate(self._h)      # the delta transport's host mirror no longer matches
 
     def status(self) -> int:
         """Read-and-clear the device error word (MG_ERR_* bits); synchronises the stream."""

@@ -62,7 +62,9 @@ typedef struct mg_config {
 
 /* Planes inside the caller-owned state buffer (struct of arrays, one row per env; rows are padded
  * to a whole number of kernel tiles, N_pad >= N; every plane starts 256-byte aligned). */
-enum { MG_PLANE_GRID = 0,      /* u8  [N_pad][W*H]  packed cell = type | colour<<2 | state<<6, index x*H+y */
+enum { MG_PLANE_GRID = 0,      /* u8  [N_pad][W*H]  packed cell = type | colour<<2 | state<<6, index x*H+y; state = agent dir.  A ball
+                                  placed by _respawn carries bit 6 when the config gives it a reward different from a ball
+                                  placed by _gen_grid (collect_game.py:130/:409 vs :101/:393); its observed STATE stays 0 */
        MG_PLANE_AGENT_POS = 1, /* u8  [N_pad][A][2] (x, y)                              Agent.pos */
        MG_PLANE_HDR = 2,       /* i32 [N_pad][4]    step_count, collected_balls, Philox block counter, episodes */
        MG_PLANE_INFO = 3,      /* i32 [N_pad][A*nb] env.info counters, index nb*agent + ball_type */
@@ -167,6 +169,30 @@ int mg_step_host_wait(mg_env* env, void* stream);
  * io->obs + *off_truncated (block size *total_bytes), the results travel in a single cudaMemcpyAsync; any other placement is
  * served by one copy per array.  Offsets depend on the observation mode (mg_set_partial_obs). */
 int mg_host_layout(const mg_env* env, size_t* off_rewards, size_t* off_terminated, size_t* off_truncated, size_t* total_bytes);
+
+/* What mg_step_host[_async] moves over PCIe for the observation (Collect handles; the step always runs on the device):
+ *   MG_TRANSPORT_FULL    the expanded observation, 3 bytes per cell (default);
+ *   MG_TRANSPORT_PACKED  the packed grid plane, 1 byte per cell (type | colour << 2 | state << 6), expanded to the caller's
+ *                        (W, H, 3) uint8 array on `host_threads` host threads inside mg_step_host / mg_step_host_wait;
+ *   MG_TRANSPORT_DELTA   one record per env with the <= 3 * num_agents cells the step wrote, the pickups (rewards are a table
+ *                        lookup on the host) and the flags - mg_delta_record_bytes() bytes, 16 for 2 agents on a 10x10 grid -
+ *                        plus the packed rows of the envs that autoreset in this step.  io->obs is then a PERSISTENT mirror that
+ *                        the library patches in place: pass the same host buffer on every call and do not write to it.  A new
+ *                        buffer, or a mirror invalidated by mg_reset / mg_step / mg_host_invalidate (call it after writing the
+ *                        state buffer directly), is refreshed in full from the packed plane on the next host step.
+ * Same results as MG_TRANSPORT_FULL, byte for byte.  host_threads <= 0: the cores of the process's affinity mask (at most 32). */
+enum { MG_TRANSPORT_FULL = 0, MG_TRANSPORT_PACKED = 1, MG_TRANSPORT_DELTA = 2 };
+int mg_set_host_transport(mg_env* env, int mode, int host_threads);
+int mg_host_invalidate(mg_env* env);
+/* The host-side decoders on their own (no device involved): packed cells -> Grid.encode() triples (grid.py:223-252), and
+ * the delta records of n envs applied to an observation mirror.  reward_table: double [33], entry 0 = 0.0, entry
+ * 1 + (colour | respawned << 4) = the reward of such a ball.  Record layout: byte 0 = n_changes | terminated << 5 |
+ * truncated << 6 | autoreset << 7; bytes 1..A = per agent 0 or 1 + (colour | respawned << 4) of the ball it picked up; then
+ * 3A entries (cell index x*H+y as u8 if W*H <= 256 else u16 little endian, packed cell code u8); padded to a multiple of 4. */
+int mg_host_expand_plane(const uint8_t* grid_host, uint8_t* obs_host, size_t n_cells, int host_threads);
+int mg_delta_record_bytes(int cells, int num_agents);
+int mg_host_apply_delta(const uint8_t* records, size_t n, int cells, int num_agents, const double* reward_table, uint8_t* obs,
+                        double* rewards, uint8_t* terminated, uint8_t* truncated, uint8_t* final_obs, int host_threads);
 
 int mg_set_trace(mg_env* env, const mg_trace* trace_dev);
 

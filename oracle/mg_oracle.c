@@ -88,7 +88,7 @@ void oc_encode3(const uint8_t* cells, int64_t n, uint8_t* obs) {
     uint8_t c = cells[i];
     obs[3 * i + 0] = c & 3;
     obs[3 * i + 1] = (c >> 2) & 15;
-    obs[3 * i + 2] = c >> 6;
+    obs[3 * i + 2] = (c & 3) == OC_T_BALL ? 0 : c >> 6; /* a ball's bit 6 is the "placed by _respawn" mark below, not its STATE */
   }
 }
 
@@ -217,16 +217,44 @@ static int reset_env(const oc_collect_cfg* c, uint8_t* g, uint8_t* pos, int32_t*
   return 0;
 }
 
+static int type_of_colour(const oc_collect_cfg* c, int colour);
+
+/* Ball.reward (object.py:308-321) is an attribute of the ball OBJECT, and the reference gives it two different values:
+ *   balls placed by _gen_grid:  balls_reward[type] (collect_game.py:98-101, :252, :287, :354, :359); QuadrantsRespawn: the literal 1 (:393)
+ *   balls placed by _respawn:   balls_reward[colour index] (:130, :409 -- indexed by COLOUR, not by type)
+ * One byte per cell keeps (type, colour); where the two values differ for some colour the env can hold, a respawned ball also
+ * carries bit 6 of its cell (never shown: oc_encode3).  Where the reference raises (colour >= len(balls_reward): IndexError)
+ * the initial value is kept. */
+static double reward_initial(const oc_collect_cfg* c, int colour) {
+  if (c->layout == OC_LAYOUT_QUADRANTS_RESPAWN) return 1.0;
+  int t = type_of_colour(c, colour);
+  return t >= 0 ? c->ball_reward[t] : 1.0;
+}
+static double reward_respawned(const oc_collect_cfg* c, int colour) {
+  return colour < c->num_ball_types ? c->ball_reward[colour] : reward_initial(c, colour);
+}
+int oc_collect_marks_respawned(const oc_collect_cfg* c) {
+  if (!c->respawn) return 0;
+  if (c->layout == OC_LAYOUT_QUADRANTS_RESPAWN) {
+    for (int k = 0; k < 3; ++k) if (reward_initial(c, k) != reward_respawned(c, k)) return 1;
+    return 0;
+  }
+  for (int t = 0; t < c->num_ball_types; ++t)
+    if (reward_initial(c, c->ball_colour[t]) != reward_respawned(c, c->ball_colour[t])) return 1;
+  return 0;
+}
+
 /* CollectGameEnv._respawn (:129-130) / CollectGameQuadrantsRespawn._respawn (:401-409) */
 static void respawn(const oc_collect_cfg* c, uint8_t* g, rng_t* r, int colour) {
   const int W = c->width, H = c->height;
+  const int mark = oc_collect_marks_respawned(c);
   int x, y;
   if (c->layout == OC_LAYOUT_QUADRANTS_RESPAWN) {
     int px[3] = {0, W / 2 - 1, W / 2 - 1}, py[3] = {0, H / 2 - 1, 0};
     int p = colour < 3 ? colour : 0; /* reference: IndexError for colour >= 3 */
-    place_obj(c, g, r, OC_CELL(OC_T_BALL, colour, 0), px[p], py[p], W / 2 + 1, H / 2 + 1, &x, &y);
+    place_obj(c, g, r, OC_CELL(OC_T_BALL, colour, mark), px[p], py[p], W / 2 + 1, H / 2 + 1, &x, &y);
   } else {
-    place_obj(c, g, r, OC_CELL(OC_T_BALL, colour, 0), 0, 0, W, H, &x, &y);
+    place_obj(c, g, r, OC_CELL(OC_T_BALL, colour, mark), 0, 0, W, H, &x, &y);
   }
 }
 
@@ -258,9 +286,7 @@ static void step_env(const oc_collect_cfg* c, uint8_t* g, uint8_t* pos, int32_t*
       if (c->respawn) respawn(c, g, r, colour);     /* :142-143, may land on (nx, ny) */
       *collected += 1;                              /* :144 */
       int t = type_of_colour(c, colour);
-      /* fwd_cell.reward (:145): balls_reward[type] for placed and respawned balls; the initial balls of
-       * QuadrantsRespawn carry a literal 1 (:391), identical for the registered balls_reward=[1,1,1]. */
-      rew[i] += t >= 0 ? c->ball_reward[t] : 1.0;
+      rew[i] += (cell >> 6) & 1 ? reward_respawned(c, colour) : reward_initial(c, colour); /* fwd_cell.reward :145 */
       if (t >= 0) info[nb * i + t] += 1;            /* :147 */
       enter = 1;
     } else if (cell == 0) { /* :178-181 */
@@ -401,7 +427,7 @@ void oc_partial_view3(const uint8_t* grid, const uint8_t* pos, const uint8_t* di
       for (int a = 0; a < V; ++a)
         for (int b = 0; b < V; ++b) { /* encode_for_agents grid.py:254-284: unseen cells stay (0,0,0) */
           const uint8_t c = mask[a][b] ? cell[a][b] : 0;
-          o[(a * V + b) * 3 + 0] = c & 3; o[(a * V + b) * 3 + 1] = (c >> 2) & 15; o[(a * V + b) * 3 + 2] = c >> 6;
+          o[(a * V + b) * 3 + 0] = c & 3; o[(a * V + b) * 3 + 1] = (c >> 2) & 15; o[(a * V + b) * 3 + 2] = (c & 3) == OC_T_BALL ? 0 : c >> 6;  /* type 2 = Collect ball (bit 6: respawn mark) or Maze flag, STATE 0 either way */
         }
     }
 }

@@ -87,6 +87,10 @@ void oc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
 /* Grid.encode for encode_dim 3 (grid.py:223-252): n_cells packed cells -> 3*n_cells bytes. */
 void oc_encode3(const uint8_t* cells, int64_t n_cells, uint8_t* obs);
 
+/* 1 = this config makes a respawned ball's reward differ from an initial ball's for some colour, so balls placed by
+ * _respawn carry bit 6 of their cell in the state (see mg_oracle.c: reward_initial / reward_respawned). */
+int oc_collect_marks_respawned(const oc_collect_cfg* cfg);
+
 /* reset: CollectGameEnv.reset + _gen_grid (collect_game.py:107-119 + layout).  mask may be NULL
  * (= all).  obs may be NULL. */
 int oc_collect_reset(const oc_collect_cfg* cfg, int64_t N, oc_collect_state* st, const uint8_t* mask,

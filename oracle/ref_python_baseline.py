@@ -1,7 +1,9 @@
 """Throughput of the UNMODIFIED Python reference on host cores, reproducible in the build container.
 
-TEST / MEASUREMENT INFRASTRUCTURE ONLY: needs /root/reference (absent on the GPU box), imports the reference under
-oracle/refshim exactly as the golden recorder does.  Nothing in the product, the tests or bench.py imports this file.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY: needs the reference package - /root/reference (build container) or the copy that
+oracle/install_reference.py pip-installs into baseline/_ref (travels to the GPU box; set MG_REFERENCE_ROOT to it) - and imports
+it under oracle/refshim exactly as the golden recorder does.  Nothing in the product or the tests imports this file; bench.py's
+CPU-baseline legs call `measure()` to quote the Python reference beside the C port (`cpu_baseline.python_reference`).
 
     python oracle/ref_python_baseline.py [--seconds 3] [--workers N]
 
@@ -76,7 +78,9 @@ def _other_families(seconds):
     from gym_multigrid.envs.ctf import CtFMvNEnv
     from gym_multigrid.envs.maze import MazeSingleAgentEnv
     from gym_multigrid.policy.ctf.heuristic import RwPolicy
-    assets = "/root/reference/tests/assets"
+    assets = os.path.join(rh.REFERENCE_ROOT, "tests", "assets")
+    if not os.path.isdir(assets):
+        assets = os.path.join(rh.REFERENCE_ROOT, "assets")     # the copy installed by oracle/install_reference.py
     out = {}
 
     def rate(env, sample, seconds):
@@ -111,37 +115,51 @@ def _other_families(seconds):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--seconds", type=float, default=3.0)
-    ap.add_argument("--workers", type=int, default=os.cpu_count() or 1)
-    args = ap.parse_args()
-    single = _loop(args.seconds, 0)
+def measure(seconds=3.0, workers=None, families=True):
+    """The numbers as a dict (see the module docstring); `workers` defaults to the cores of this process's affinity mask."""
+    if workers is None:
+        try:
+            workers = len(os.sched_getaffinity(0))
+        except AttributeError:
+            workers = os.cpu_count() or 1
+    single = _loop(seconds, 0)
     ctx = mp.get_context("fork")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_indep, args=(args.seconds, 100 + i, q)) for i in range(args.workers)]
+    procs = [ctx.Process(target=_indep, args=(seconds, 100 + i, q)) for i in range(workers)]
     [p.start() for p in procs]
     indep = sum(q.get() for _ in procs)
     [p.join() for p in procs]
-    pipes = [ctx.Pipe() for _ in range(args.workers)]
-    workers = [ctx.Process(target=_worker, args=(c, 200 + i), daemon=True) for i, (_, c) in enumerate(pipes)]
-    [w.start() for w in workers]
+    pipes = [ctx.Pipe() for _ in range(workers)]
+    ws = [ctx.Process(target=_worker, args=(c, 200 + i), daemon=True) for i, (_, c) in enumerate(pipes)]
+    [w.start() for w in ws]
     rng = np.random.default_rng(1)
     steps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < args.seconds:
-        acts = rng.integers(0, 4, size=(args.workers, 2))
+    while time.perf_counter() - t0 < seconds:
+        acts = rng.integers(0, 4, size=(workers, 2))
         for (p, _), a in zip(pipes, acts):
             p.send([int(a[0]), int(a[1])])
         for p, _ in pipes:
             p.recv()
-        steps += args.workers
+        steps += workers
     lockstep = steps / (time.perf_counter() - t0)
     for p, _ in pipes:
         p.send(None)
-    print(json.dumps({"env": ENV_ID, "impl": "unmodified Python reference under oracle/refshim", "cores": args.workers,
-                      "single_process_env_steps_per_s": single, "independent_processes_env_steps_per_s": indep,
-                      "lockstep_pipes_env_steps_per_s": lockstep, "seconds_each": args.seconds,
-                      "other_families_single_process": _other_families(args.seconds)}))
+    [w.join(timeout=5) for w in ws]
+    out = {"env": ENV_ID, "impl": "unmodified Python reference under oracle/refshim", "cores": workers,
+           "single_process_env_steps_per_s": single, "independent_processes_env_steps_per_s": indep,
+           "lockstep_pipes_env_steps_per_s": lockstep, "seconds_each": seconds}
+    if families:
+        out["other_families_single_process"] = _other_families(seconds)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--workers", type=int, default=None)
+    ap.add_argument("--no-families", action="store_true")
+    args = ap.parse_args()
+    print(json.dumps(measure(args.seconds, args.workers, not args.no_families)))
 
 
 if __name__ == "__main__":

@@ -143,30 +143,87 @@ def test_encode_matches_oracle_all_codes(cuda_device):
     env.close()
 
 
-def test_step_host_matches_device_path(cuda_device):
+@pytest.mark.parametrize("transport", ["full", "packed", "delta"])
+def test_step_host_matches_device_path(transport, cuda_device):
+    """numpy in -> numpy out through mg_step_host equals the device path, whatever crosses PCIe for the observation:
+    the expanded array, the packed plane, or per-env delta records patched into the host mirror (autoresets included)."""
     g = load_golden("collect_respawn_clustered")
-    envs = [_make(g, "collect_respawn_clustered", 2051, autoreset=True, seed=9) for _ in range(2)]
+    envs = [_make(g, "collect_respawn_clustered", 2051, autoreset=True, seed=9, host_transport=transport) for _ in range(2)]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(3)
-    for t in range(60):
+    for t in range(110):     # two lockstep TimeLimit autoresets inside
         act = rng.integers(0, 4, size=(2051, 2)).astype(np.int8)
         a = envs[0].step(torch.as_tensor(act, device=cuda_device))
         b = envs[1].step(act)   # numpy in -> numpy out through mg_step_host
         assert isinstance(b[0], np.ndarray)
         for x, y in zip(a[:4], b[:4]):
-            assert np.array_equal(_np(x), y)
+            assert np.array_equal(_np(x), y), f"step {t}"
+        if t == 30:     # a device-path step in between invalidates the delta transport's mirror: the next host step refreshes it
+            for e in envs:
+                e.step(torch.as_tensor(act, device=cuda_device))
+        if t == 60:     # ... and so does writing the state
+            st = envs[0].get_state()
+            envs[1].set_state(st)
     for e in envs:
+        assert e.status() == 0
         e.close()
 
 
-def test_step_async_wait_two_batches_in_flight(cuda_device):
+# (kwargs, n): staggered terminations (no respawn: episodes end when the last ball is collected), a wide-record grid
+# (W*H > 256 -> 16-bit cell indices), three agents, rooms ghosts
+DELTA_CASES = [
+    (dict(size=8, agents_index=[1, 2], balls_index=[0, 1], balls_reward=[1, 2], num_balls=[4], respawn=False, layout="even_dist", max_steps=30), 1500),
+    (dict(size=17, agents_index=[3, 5], balls_index=[0, 1, 2], balls_reward=[1, 1, 1], num_balls=[15], respawn=True, layout="quadrants_respawn", max_steps=40), 700),
+    (dict(size=10, agents_index=[3, 5, 1], balls_index=[0, 1, 2], balls_reward=[1, 1, 1], num_balls=[15], respawn=True, layout="even_dist", max_steps=25), 999),
+    (dict(size=11, agents_index=[3, 5], balls_index=[0, 1, 2], balls_reward=[1, 1, 1], num_balls=[15], respawn=False, layout="rooms", max_steps=35), 1111),
+]
+
+
+@pytest.mark.parametrize("kw,n", DELTA_CASES)
+@pytest.mark.parametrize("transport", ["packed", "delta"])
+def test_compact_transports_with_final_observation(kw, n, transport, cuda_device):
+    """Compact transports vs the device path incl. `final_observation` (the terminal rows come from the host mirror in delta
+    mode), on envs that finish at different steps, with greedy-ish actions so that episodes really terminate."""
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    dev = CollectVecEnv(n, seed=21, autoreset=True, **kw)
+    host = CollectVecEnv(n, seed=21, autoreset=True, host_transport=transport, **kw)
+    dev.enable_final_observation()
+    dev.reset(); host.reset()
+    A = len(kw["agents_index"])
+    W = kw["size"]
+    hb = None
+    rng = np.random.default_rng(5)
+    import ctypes as C
+    from gym_multigrid_b200 import _lib
+    fin = torch.zeros((n, W, W, 3), dtype=torch.uint8).pin_memory()
+    finished = 0
+    for t in range(90):
+        act = rng.integers(0, 4, size=(n, A)).astype(np.int8)
+        want = dev.step(torch.as_tensor(act, device=cuda_device))
+        io = host._host_io(act)
+        io.final_obs = fin.data_ptr()
+        host._check(host._lib.mg_step_host(host._h, C.c_void_p(host.state.data_ptr()), C.byref(io), host._stream()))
+        got = host._host_result()
+        for x, y in zip(want[:4], got[:4]):
+            assert np.array_equal(_np(x), y), f"step {t}"
+        done = _np(want[2] | want[3])
+        finished += int(done.sum())
+        if done.any():
+            assert np.array_equal(_np(want[4]["final_observation"])[done], fin.numpy()[done]), f"final_observation, step {t}"
+    assert finished > n, "the case must exercise autoresets"
+    assert dev.status() == 0 and host.status() == 0
+    dev.close(); host.close()
+
+
+@pytest.mark.parametrize("transport", ["full", "delta"])
+def test_step_async_wait_two_batches_in_flight(transport, cuda_device):
     """step_async / step_wait (mg_step_host_async / _wait): two env batches alternated with both in flight return exactly what
     the blocking device path returns, also when device-path calls are mixed in between."""
     g = load_golden("collect_respawn_clustered")
     n = 3000
     ref = [_make(g, "collect_respawn_clustered", n, autoreset=True, seed=s) for s in (4, 5)]
-    pip = [_make(g, "collect_respawn_clustered", n, autoreset=True, seed=s) for s in (4, 5)]
+    pip = [_make(g, "collect_respawn_clustered", n, autoreset=True, seed=s, host_transport=transport) for s in (4, 5)]
     for e in ref + pip:
         e.reset()
     rng = np.random.default_rng(8)

@@ -20,7 +20,9 @@ def test_encode3_table():
     obs = oc.encode3(cells)
     assert np.array_equal(obs[:, 0], cells & 3)
     assert np.array_equal(obs[:, 1], (cells >> 2) & 15)
-    assert np.array_equal(obs[:, 2], cells >> 6)
+    # STATE is the agent's dir; a ball (type 2) always encodes STATE 0 (object.py:58-74) - its bit 6 is the internal
+    # "placed by _respawn" mark (include/multigrid_b200.h, MG_PLANE_GRID)
+    assert np.array_equal(obs[:, 2], np.where((cells & 3) == 2, 0, cells >> 6))
     # the codes the Collect world produces
     assert obs[0].tolist() == [0, 0, 0] and obs[1 | 7 << 2].tolist() == [1, 7, 0]
     assert obs[3 | 5 << 2 | 3 << 6].tolist() == [3, 5, 3] and obs[2 | 2 << 2].tolist() == [2, 2, 0]
