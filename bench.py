@@ -335,6 +335,7 @@ def run_ours(args):
         sr = [torch.randint(0, 4, (RING, ns, 2), generator=gen, device=dev, dtype=torch.int8) for _ in range(B)]
         for e in se:
             e.reset()
+        torch.cuda.synchronize(dev)     # the resets ran on the default stream; the streams below are non-blocking
         sm_main = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(sm_main):
             for i in range(B):
@@ -542,6 +543,7 @@ def bench_families(args, dev, rank, world, timed_region_factory):
         Bf = len(envs)
         for e in envs:
             e.reset()
+        torch.cuda.synchronize(dev)     # the resets ran on the default stream; `main` is a non-blocking stream
         main = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(main):
             for i in range(max(warm, 3) * Bf):
@@ -568,7 +570,7 @@ def bench_families(args, dev, rank, world, timed_region_factory):
                 main.synchronize()
                 sampler.sample()
             samples.append(e0.elapsed_time(e1) * 1e3 / (reps * count))
-        st = max(e.status() for e in envs)
+        st = max((e.status() if hasattr(e, "status") else 0) for e in envs)
         assert st == 0, f"{name}: device status word {st}"
         out[name] = {"workload": note, "num_envs_per_gpu": n, "env_batches": Bf, "steps_timed": reps * count, "us_per_step": statistics.median(samples),
                      "algorithmic_bytes_per_env_step": bytes_per_env, "actions": f"fresh per step (ring of {ring})"}

@@ -22,6 +22,9 @@ namespace mg {
 cudaError_t launch_collect_step(int v, const CollectParams& p, cudaStream_t st);
 cudaError_t launch_collect_reset(int v, const CollectParams& p, cudaStream_t st);
 cudaError_t launch_encode3(int v, const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st);
+cudaError_t launch_collect_rollout(const CollectParams& p, int num_sms, cudaStream_t st);
+cudaError_t configure_rollout_kernels(int cells, int A);
+size_t rollout_smem_bytes(int cells, int A, int tile);
 int num_tile_variants();
 int tile_envs(int v);
 cudaError_t configure_kernels(int v, int cells, int A);
@@ -103,6 +106,9 @@ struct mg_env {
   unsigned long long* timeline;
   std::string err;
   // compact host transports (mg_set_host_transport; Collect family)
+  int num_sms; size_t smem_optin;
+  int step_impl;             // 0 = tile kernel (collect_step_kernel), 1 = warp-tile kernel (collect_rollout_kernel, T = 1)
+  bool rollout_ready;
   int transport;             // MG_TRANSPORT_*
   int host_threads;
   uint8_t* d_delta_blk;      // [16-byte header: int32 reset count][N x delta records]
@@ -180,11 +186,13 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
-  int tile = 0;
+  // default tile: 32 envs x 96 threads (variant 9) - the fastest under fresh per-step actions, where most warps take the pickup /
+  // respawn branch every step (profiles/r02_kbench_collect_variants.jsonl); MG_TILE selects another variant for experiments
+  int tile = 9;
   if (const char* tv = std::getenv("MG_TILE")) tile = std::atoi(tv);
   if (tile < 0 || tile >= mg::num_tile_variants()) return fail(nullptr, "mg_create: MG_TILE out of range");
   // large grids: fall back to the smallest tile that fits the 227 KB of shared memory
-  while (mg::tile_smem(tile, W * H, A) > (size_t)prop.sharedMemPerBlockOptin && tile != 6) tile = (tile == 0 ? 5 : 6);
+  while (mg::tile_smem(tile, W * H, A) > (size_t)prop.sharedMemPerBlockOptin && tile != 6) tile = 6;
   if (mg::tile_smem(tile, W * H, A) > (size_t)prop.sharedMemPerBlockOptin)
     return fail(nullptr, "mg_create: grid too large for the shared-memory tile (16 envs x 4*W*H bytes must fit 227 KB)");
 
@@ -193,6 +201,10 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create: out of host memory");
   env->family = MG_FAMILY_COLLECT;
+  env->num_sms = prop.multiProcessorCount; env->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  // mg_step's kernel: the warp-tile kernel (collect_rollout_kernels.cu, T = 1) unless MG_STEP_IMPL=tile asks for the CTA-tile kernel
+  // (collect_kernels.cu), which also serves grids too large for a warp's shared-memory slice
+  { const char* v = std::getenv("MG_STEP_IMPL"); env->step_impl = (v && v[0] == 't') ? 0 : 1; }
   env->map_codes_off = 0;
   env->d_map_tables = nullptr;
   env->obs_elem = 1; env->act_cols = cfg->num_agents; env->rew_cols = cfg->num_agents;
@@ -247,7 +259,10 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   for (int c = 0; c < 16; ++c) { env->reward_table[1 + c] = p.reward_initial[c]; env->reward_table[17 + c] = p.reward_respawned[c]; }
   p.N = cfg->num_envs; p.env_id_base = (unsigned long long)cfg->env_id_base; p.seed = cfg->seed;
   p.rng_mode = 1;
-  { const char* v = std::getenv("MG_EARLY_OBS"); p.early_obs = !(v && v[0] == '0'); }   // A/B switch for the early observation store
+  // early observation store: OFF by default.  It pays only while agents stand still (round 1's frozen-action benchmark): with fresh
+  // actions every env patches ~4 cells x 3 bytes of the slab in global memory, and those 8 x 10^5 partial-sector writes per launch cost
+  // as much L2 bandwidth as storing the slab again (13.9 vs 10.8 us per 65 536-env launch on one stream).  MG_EARLY_OBS=1 enables it.
+  { const char* v = std::getenv("MG_EARLY_OBS"); p.early_obs = (v && v[0] == '1'); }
 
   if ((ce = cudaMalloc(&env->d_status, sizeof(int32_t))) != cudaSuccess) { delete env; return cuda_fail(nullptr, "cudaMalloc(status)", ce); }
   if ((ce = cudaMemset(env->d_status, 0, sizeof(int32_t))) != cudaSuccess) { cudaFree(env->d_status); delete env; return cuda_fail(nullptr, "cudaMemset(status)", ce); }
@@ -867,6 +882,15 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
   return 0;
 }
 
+// the warp-tile kernel needs 2 warps' worth of shared memory per CTA: opt in once per handle; != 0 if the grid is too large for it
+static int rollout_prepare(mg_env* env) {
+  if (env->rollout_ready) return 0;
+  if (mg::rollout_smem_bytes(env->base.cells, env->base.A, 32) > env->smem_optin) return -1;
+  if (mg::configure_rollout_kernels(env->base.cells, env->base.A) != cudaSuccess) return -1;
+  env->rollout_ready = true;
+  return 0;
+}
+
 static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st, bool with_delta = false) {
   if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
   if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
@@ -888,7 +912,41 @@ static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStrea
     p.reset_rows = env->d_reset_rows; p.reset_stride = (int)env->reset_stride;
   }
   cudaError_t ce;
-  if ((ce = mg::launch_collect_step(env->tile, p, st)) != cudaSuccess) return cuda_fail(env, "collect_step_kernel", ce);
+  if (env->step_impl == 1 && rollout_prepare(env) == 0) {
+    p.T = 1;
+    if ((ce = mg::launch_collect_rollout(p, env->num_sms, st)) != cudaSuccess) return cuda_fail(env, "collect_rollout_kernel", ce);
+  } else {
+    if ((ce = mg::launch_collect_step(env->tile, p, st)) != cudaSuccess) return cuda_fail(env, "collect_step_kernel", ce);
+  }
+  env->launches += 1;
+  return 0;
+}
+
+extern "C" int mg_rollout(mg_env* env, void* state, const mg_rollout_io* io, void* stream) {
+  if (!env || !state || !io) return fail(env, "mg_rollout: null argument");
+  if (env->family != MG_FAMILY_COLLECT) return fail(env, "mg_rollout: Collect family only");
+  if (!aligned16(state)) return fail(env, "mg_rollout: state buffer must be 16-byte aligned");
+  if (io->steps < 1) return fail(env, "mg_rollout: steps must be >= 1");
+  if (!io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_rollout: rewards/terminated/truncated must be non-null");
+  if (io->final_obs && !io->obs) return fail(env, "mg_rollout: final_obs needs obs");
+  if (env->has_trace && io->steps != 1) return fail(env, "mg_rollout: trace replay (mg_set_trace) carries one step of recorded draws: steps must be 1");
+  if (env->has_trace && !io->actions) return fail(env, "mg_rollout: trace replay needs actions");
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
+  if (rollout_prepare(env)) return fail(env, "mg_rollout: the grid is too large for the warp-tile kernel's shared memory (32 envs x 4*W*H bytes per warp)");
+  env->mirror_valid = false;
+  mg::CollectParams p = env->base;
+  bind_state(env, p, state);
+  bind_trace(env, p);
+  if (p.rng_mode == 0 && !p.order) return fail(env, "mg_rollout: trace mode needs the recorded agent order");
+  p.T = io->steps;
+  p.actions = io->actions; p.actions_out = io->actions_out; p.obs = io->obs; p.rewards = io->rewards;
+  p.terminated = io->terminated; p.truncated = io->truncated; p.final_obs = io->final_obs;
+  const bool strides_ok = io->steps == 1 || (p.N % 16 == 0);   // step-major arrays: every step's slab must start 16-byte aligned for TMA
+  p.obs_bulk_ok = aligned16(io->obs) && strides_ok;
+  p.io_bulk_ok = (!io->actions || aligned16(io->actions)) && aligned16(io->rewards) && aligned16(io->terminated) && aligned16(io->truncated) && strides_ok;
+  p.timeline = env->timeline;
+  if ((ce = mg::launch_collect_rollout(p, env->num_sms, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "collect_rollout_kernel", ce);
   env->launches += 1;
   return 0;
 }

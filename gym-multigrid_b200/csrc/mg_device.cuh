@@ -64,6 +64,10 @@ struct CollectParams {
   int io_bulk_ok;         // actions / rewards / terminated / truncated pointers are 16-byte aligned
   unsigned long long* timeline;  // optional [tiles][8] per-CTA phase timestamps (globaltimer ns), profiling only
   int early_obs;          // 1 = full tiles store the pre-step observation slab while the agents are stepped and patch the <= 3A changed cells in place
+  // rollout (collect_rollout_kernels.cu): T steps per launch; actions / obs / rewards / flags are [T][N][...] arrays
+  int T;
+  int roll_tile;          // envs per warp (4 / 8 / 16 / 32), chosen per launch from the batch size
+  int8_t* actions_out;    // uniform on-device policy (actions == NULL): the actions taken, [T][N][A], or NULL
   // compact host transport (mg_set_host_transport, MG_TRANSPORT_DELTA): one record per env with the cells the step wrote, plus the
   // packed rows of the envs that autoreset, compacted behind a device counter.  Record (delta_stride bytes, see delta_record_bytes):
   //   byte 0      n_changes (bits 0-4) | terminated << 5 | truncated << 6 | autoreset << 7
@@ -202,9 +206,16 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2);
 // STATE is the agent's dir (type 3); a Collect ball (type 2) may carry the internal "respawned" mark in bit 6, which is not
 // part of the observation: WorldObj.encode gives (type, colour, 0) for it (object.py:58-74).
+// MARK = false: the caller knows no ball of this handle carries the mark (CollectParams::mark_respawned == 0, the case of every
+// registered config), which saves the four masking operations per word.
+template <bool MARK = true>
 __device__ __forceinline__ void expand4(uint32_t w, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
-  const uint32_t ball = (w >> 1) & ~w & 0x01010101u;
-  interleave3(w & 0x03030303u, (w >> 2) & 0x0F0F0F0Fu, (w >> 6) & 0x03030303u & ~(ball * 3u), o0, o1, o2);
+  uint32_t s = (w >> 6) & 0x03030303u;
+  if (MARK) {
+    const uint32_t ball = (w >> 1) & ~w & 0x01010101u;
+    s &= ~(ball * 3u);
+  }
+  interleave3(w & 0x03030303u, (w >> 2) & 0x0F0F0F0Fu, s, o0, o1, o2);
 }
 __device__ __forceinline__ uint8_t state_of(uint8_t c) { return (c & 3) == T_BALL ? 0 : (uint8_t)(c >> 6); }
 __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
@@ -217,12 +228,13 @@ __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, 
   o2 = __byte_perm(st, c, 0x3710);                 // s2 t3 c3 s3
 }
 
+template <bool MARK = true>
 __device__ __forceinline__ void expand16(const uint4 in, uint4& a, uint4& b, uint4& c) {
   uint32_t o[12];
-  expand4(in.x, o[0], o[1], o[2]);
-  expand4(in.y, o[3], o[4], o[5]);
-  expand4(in.z, o[6], o[7], o[8]);
-  expand4(in.w, o[9], o[10], o[11]);
+  expand4<MARK>(in.x, o[0], o[1], o[2]);
+  expand4<MARK>(in.y, o[3], o[4], o[5]);
+  expand4<MARK>(in.z, o[6], o[7], o[8]);
+  expand4<MARK>(in.w, o[9], o[10], o[11]);
   a = make_uint4(o[0], o[1], o[2], o[3]);
   b = make_uint4(o[4], o[5], o[6], o[7]);
   c = make_uint4(o[8], o[9], o[10], o[11]);

@@ -226,6 +226,54 @@ class CollectVecEnv(VectorEnvSurface):
             raise RuntimeError(_lib.last_error(self._h))
         return self._obs, self._rewards, self._term_b, self._trunc_b, (self._info_static if self._final_obs is None else self._info())
 
+    def rollout(self, actions=None, steps=None, obs=True, final_observation=False, out=None):
+        """T env steps in ONE kernel launch with the env state held in shared memory (mg_rollout): the loop
+        `for t in range(T): env.step(actions[t])` of the reference (collect_game.py:183-214), bit-identical to T `step` calls
+        incl. same-step autoresets.  `actions`: int8 CUDA tensor [T, N, A]; or None with `steps=T` for the uniform random policy
+        drawn on the device (the actions taken come back as info["actions"]).  `obs=False` skips the observations (planners
+        that score action sequences by reward).  Returns (obs u8 [T,N,W,H,3] | None, rewards f64 [T,N,A], terminated bool [T,N],
+        truncated bool [T,N], info); the tensors are reused by the next rollout of the same length unless `out` (a dict with
+        the keys obs / rewards / terminated / truncated [/ final_obs / actions]) supplies them."""
+        N, A, W, H = self.num_envs, self.num_agents, self.width, self.height
+        if actions is not None:
+            a = actions
+            if not (isinstance(a, torch.Tensor) and a.dtype is torch.int8 and a.is_cuda and a.is_contiguous() and a.device == self.device):
+                a = torch.as_tensor(a).to(self.device, non_blocking=True).to(torch.int8).contiguous()
+            a = a.reshape(-1, N, A)
+            T = a.shape[0]
+        else:
+            if steps is None:
+                raise ValueError("rollout: pass actions [T, N, A] or steps=T (uniform random policy on the device)")
+            a, T = None, int(steps)
+        key = (T, bool(obs), bool(final_observation), a is None)
+        b = out if out is not None else getattr(self, "_roll_bufs", {}).get(key)
+        if b is None:
+            with torch.cuda.device(self.device):
+                b = dict(rewards=torch.empty((T, N, A), dtype=torch.float64, device=self.device),
+                         terminated=torch.empty((T, N), dtype=torch.uint8, device=self.device),
+                         truncated=torch.empty((T, N), dtype=torch.uint8, device=self.device))
+                if obs:
+                    b["obs"] = torch.empty((T, N, W, H, 3), dtype=torch.uint8, device=self.device)
+                if final_observation:
+                    b["final_obs"] = torch.zeros((T, N, W, H, 3), dtype=torch.uint8, device=self.device)
+                if a is None:
+                    b["actions"] = torch.empty((T, N, A), dtype=torch.int8, device=self.device)
+            self._roll_bufs = {key: b}      # one cached set: the last shape used
+        io = _lib.RolloutIO()
+        io.steps, io.actions = T, (a.data_ptr() if a is not None else None)
+        io.obs = b["obs"].data_ptr() if obs else None
+        io.rewards, io.terminated, io.truncated = b["rewards"].data_ptr(), b["terminated"].data_ptr(), b["truncated"].data_ptr()
+        io.final_obs = b["final_obs"].data_ptr() if final_observation else None
+        io.actions_out = b["actions"].data_ptr() if (a is None and "actions" in b) else None
+        self._check(self._lib.mg_rollout(self._h, self._state_ptr, C.byref(io), self._stream()))
+        info = {"pickups": self.pickups}
+        if a is None:
+            info["actions"] = b.get("actions")
+        if final_observation:
+            info["final_observation"] = b["final_obs"]
+            info["_final_observation"] = (b["terminated"] | b["truncated"]).view(torch.bool)
+        return (b.get("obs") if obs else None), b["rewards"], b["terminated"].view(torch.bool), b["truncated"].view(torch.bool), info
+
     def _host_io(self, actions):
         if self._host is None:
             N, W, H, A = self.num_envs, self.width, self.height, self.num_agents

@@ -122,6 +122,23 @@ int mg_reset(mg_env* env, void* state_dev, const uint8_t* mask_dev, uint8_t* obs
 /* CollectGameEnv.step + Grid.encode, fused, all envs in lockstep (collect_game.py:183-214). */
 int mg_step(mg_env* env, void* state_dev, const mg_step_io* io_dev, void* stream);
 
+/* T steps in ONE launch (Collect handles): the loop `for t in range(T): env.step(actions[t])` (collect_game.py:183-214 called T times)
+ * with the env state held in shared memory across the steps - state traffic and launch latency are paid once per call, which is
+ * what small batches need (4 096 envs: one launch per step is latency-bound).  Bit-identical to T calls of mg_step with the same
+ * actions, autoresets included.  All device pointers; arrays are step-major. */
+typedef struct mg_rollout_io {
+  int32_t steps;           /* T >= 1 */
+  const int8_t* actions;   /* [T][N][A], or NULL = uniform random policy drawn on the device: one Philox4x32-10 block per env and step,
+                              counter (env id lo, env id hi, step_count, 2^30 | episode), key = seed; agent i takes bits 2i..2i+1 of word 0 */
+  uint8_t* obs;            /* [T][N][W][H][3] or NULL (rewards-only rollouts, e.g. planners scoring action sequences) */
+  double* rewards;         /* [T][N][A] */
+  uint8_t* terminated;     /* [T][N] */
+  uint8_t* truncated;      /* [T][N] */
+  uint8_t* final_obs;      /* [T][N][W][H][3] or NULL */
+  int8_t* actions_out;     /* [T][N][A] or NULL: with the on-device policy, the actions that were taken */
+} mg_rollout_io;
+int mg_rollout(mg_env* env, void* state_dev, const mg_rollout_io* io_dev, void* stream);
+
 /* Grid.encode alone: state grid plane -> obs (grid.py:223-252). */
 int mg_encode(mg_env* env, const void* state_dev, uint8_t* obs_dev, void* stream);
 
