@@ -356,6 +356,52 @@ def run_ours(args):
             e.close()
         del se, sr
 
+    # ---- launch-amortised rollouts (mg_rollout): T steps per launch with the env state held in shared memory, ONE stream.
+    #      The loop `for t in range(T): env.step(actions[t])`; per env-step it moves actions 2 + obs 300 + rewards 16 + flags 2 =
+    #      320 B, and 2 x 136 B of state per env once per LAUNCH - so against SURVEY's 592 B per env-step its fraction can exceed 1.
+    rollout = None
+    if not args.skip_rollout:
+        rollout = {"T": args.rollout_steps, "bytes_moved_per_env_step": 320 + 272 / args.rollout_steps,
+                   "note": "one launch = T steps of one env batch, state resident in shared memory; `policy` = uniform random actions drawn "
+                           "on the device (Philox), `actions` = a given [T, N, A] tensor; one stream, CUDA events, median of 3"}
+        Tr = args.rollout_steps
+        for nn in (n, 4096):
+            per_launch = nn * (Tr * 320 + 272)
+            Br = max(1, min(4, int(300e6 // per_launch) + 1))
+            re_ = [mg.make_vec(ENV_ID, nn, device=dev, seed=args.seed + 2, autoreset=True, env_id_base=((2 * world + rank) * B + b) * n) for b in range(Br)]
+            outs = []
+            for e in re_:
+                e.reset()
+                outs.append(dict(rewards=torch.empty((Tr, nn, 2), dtype=torch.float64, device=dev), terminated=torch.empty((Tr, nn), dtype=torch.uint8, device=dev),
+                                 truncated=torch.empty((Tr, nn), dtype=torch.uint8, device=dev), obs=torch.empty((Tr, nn, 10, 10, 3), dtype=torch.uint8, device=dev),
+                                 actions=torch.empty((Tr, nn, 2), dtype=torch.int8, device=dev)))
+            racts = [torch.randint(0, 4, (Tr, nn, 2), generator=gen, device=dev, dtype=torch.int8) for _ in range(Br)]
+            torch.cuda.synchronize(dev)
+            for mode in ("policy", "actions"):
+                rm = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(rm):
+                    def call(b):
+                        if mode == "policy":
+                            re_[b].rollout(steps=Tr, out=outs[b])
+                        else:
+                            re_[b].rollout(racts[b], out=outs[b])
+                    for b in range(Br):
+                        call(b)
+                    rm.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=rm):
+                        for b in range(Br):
+                            call(b)
+                    g.replay()
+                    rm.synchronize()
+                us = statistics.median(timed_region(rm, [g]) for _ in range(3)) * 1e3 / (Br * Tr)
+                rollout[f"{nn}_{mode}"] = {"num_envs": nn, "batches": Br, "us_per_step": us}
+            assert max(e.status() for e in re_) == 0
+            for e in re_:
+                e.close()
+            del re_, outs, racts
+            torch.cuda.empty_cache()
+
     # ---- end to end through the public API with HOST buffers (numpy in, numpy out)
     e2e_steps = args.e2e_steps
     EB = min(B, 2)   # two env batches in flight
@@ -436,12 +482,15 @@ def run_ours(args):
     families = {} if args.skip_families else bench_families(args, dev, rank, world, timed_region_factory=(barrier, sampler))
 
     fam_keys = sorted(families)
-    vec = [ms, single_us, e2e["delta"]["s"] * 1e3, e2e["packed"]["s"] * 1e3, e2e["full"]["s"] * 1e3, block_s * 1e3, e2e_devobs_s * 1e3,
+    roll_keys = sorted(k for k in (rollout or {}) if isinstance(rollout[k], dict))
+    vec = [rollout[k]["us_per_step"] for k in roll_keys] + [ms, single_us, e2e["delta"]["s"] * 1e3, e2e["packed"]["s"] * 1e3, e2e["full"]["s"] * 1e3, block_s * 1e3, e2e_devobs_s * 1e3,
            (small or {}).get("avg_launch_us", 0.0)] + [families[k]["us_per_step"] for k in fam_keys]
     t = torch.tensor(vec, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = [float(x) for x in t]
+    for k in roll_keys:
+        rollout[k]["us_per_step"] = vals.pop(0)
     ms_max, single_us_max, e2e_ms, e2e_packed_ms, e2e_full_ms, e2e_block_ms, e2e_devobs_ms, small_us = vals[:8]
     for k, v in zip(fam_keys, vals[8:]):
         families[k]["us_per_step"] = v
@@ -461,6 +510,11 @@ def run_ours(args):
             ach = f["algorithmic_bytes_per_env_step"] * f["num_envs_per_gpu"] / (f["us_per_step"] * 1e-6) / 1e9
             f["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "algorithmic_bytes": f["algorithmic_bytes_per_env_step"] * f["num_envs_per_gpu"]}
+        for k in roll_keys:
+            rr = rollout[k]
+            rr["value"] = rr["num_envs"] * world / (rr["us_per_step"] * 1e-6)
+            rr["frac_592B"] = ALGO_BYTES_PER_ENV_STEP * rr["num_envs"] / rr["us_per_step"] / 1e3 / peak
+            rr["frac_moved"] = rollout["bytes_moved_per_env_step"] * rr["num_envs"] / rr["us_per_step"] / 1e3 / peak
         if small:
             small.update(avg_launch_us=small_us, value=small["num_envs"] * world / small_us * 1e6,
                          frac=ALGO_BYTES_PER_ENV_STEP * small["num_envs"] / small_us / 1e3 / peak)
@@ -487,6 +541,7 @@ def run_ours(args):
                               "frac": ALGO_BYTES_PER_ENV_STEP * n / single_us_max / 1e3 / peak, "launches": n1,
                               "note": "same launch sequence on ONE stream (launches serialised, programmatic dependent launch)"},
             "small_batch": small,
+            "rollout": rollout,
             "e2e": {"value": e2e_steps * n * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 2, "d2h_bytes_per_step": d2h_delta,
                     "steps": e2e_steps, "repeats": args.e2e_repeats, "transport": "delta",
                     "api": f"CollectVecEnv.step_async(numpy) / step_wait() -> mg_step_host_async / _wait, {EB} env batches in flight, fresh actions per step; "
@@ -637,6 +692,8 @@ def main():
     ap.add_argument("--wildfire-envs", type=int, default=131072)
     ap.add_argument("--skip-families", action="store_true")
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--skip-rollout", action="store_true")
+    ap.add_argument("--rollout-steps", type=int, default=64)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--budget-s", type=float, default=60.0, help="wall budget of the --impl reference arm")

@@ -240,10 +240,12 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   //   placed by _gen_grid: balls_reward[type] (collect_game.py:98-101, :252, :287, :354, :359), QuadrantsRespawn: the literal 1 (:393);
   //   placed by _respawn:  balls_reward[COLOUR index] (:130, :409).  Where that raises in the reference (colour >= len(balls_reward):
   //   IndexError) the initial value is kept.  If the two differ for a colour this env can hold, respawned balls carry bit 6.
-  for (int c = 0; c < 16; ++c) { p.type_of_colour[c] = -1; p.reward_initial[c] = 1.0; }
+  // The info counter of a pickup is indexed by the ball's COLOUR index, not its type: info[keys[num_ball_types * i + ball_idx]] with
+  // ball_idx = COLOR_TO_IDX[fwd_cell.color] (collect_game.py:139,147).  type_of_colour holds that column, -1 where the reference
+  // would run past agent i's num_ball_types columns (it raises or bumps a neighbour's counter there; no counter is touched here).
+  for (int c = 0; c < 16; ++c) { p.type_of_colour[c] = (int8_t)(c < nb ? c : -1); p.reward_initial[c] = 1.0; }
   for (int t = nb - 1; t >= 0; --t) {
     p.ball_colour[t] = (uint8_t)cfg->ball_colour[t];
-    p.type_of_colour[cfg->ball_colour[t]] = (int8_t)t;
     if (cfg->layout != MG_LAYOUT_QUADRANTS_RESPAWN) p.reward_initial[cfg->ball_colour[t]] = cfg->ball_reward[t];
   }
   for (int c = 0; c < 16; ++c) p.reward_respawned[c] = c < nb ? cfg->ball_reward[c] : p.reward_initial[c];
@@ -352,6 +354,8 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   if (nb < 1 || nr < 0 || n > MG_MAX_MAP_AGENTS || (!maze && nr < 1)) return fail(nullptr, "mg_create_map: agent counts out of range (1..16 agents in total)");
   if (cfg->max_steps < 1) return fail(nullptr, "mg_create_map: max_steps must be >= 1");
   if (cfg->variant_1v1 && (maze || nb != 1 || nr != 1)) return fail(nullptr, "mg_create_map: variant_1v1 needs the CtF family with one blue and one red agent");
+  if (cfg->variant_1v1 && cfg->obstacle_penalty != 0.0)
+    return fail(nullptr, "mg_create_map: Ctf1v1Env is only defined for obstacle_penalty == 0 (the reference's own step raises otherwise, ctf.py:639)");
   // cell lists in np.where order (row-major over field_map[x][y])
   std::string bg, bt, rt;  // uint16 lists packed in strings
   // entries are packed cells x | y << 8 (cell index i = x * S + y), so the kernels never divide by S
@@ -461,20 +465,35 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   env->map_padded_off = o_pad; env->map_padded_bytes = padded_bytes; env->map_pad = pad;
   {  // _get_info tables: min squared distance from every cell to the cell lists of maze.py:262-269 / ctf.py:1165-1182
     int32_t* d2 = reinterpret_cast<int32_t*>(&blob[o_d2b]);
+    std::vector<int32_t> col((size_t)cells);
     for (int t = 0; t < 3; ++t) {
       // Maze: flag list, obstacle list; CtF: blue territory + blue flag, red territory + red flag (ctf.py:765-773), obstacle list
       const int ca = maze ? (t == 0 ? 2 : (t == 1 ? 3 : -1)) : (t == 0 ? 0 : (t == 1 ? 1 : 6));
       const int cb = maze ? ca : (t == 0 ? 4 : (t == 1 ? 5 : 6));
-      for (int i = 0; i < cells; ++i) {
-        int best = -1;
-        for (int j = 0; j < cells; ++j) {
-          const int c = cfg->field_map[j];
-          if (c != ca && c != cb) continue;
-          const int dx = i / S - j / S, dy = i % S - j % S, v = dx * dx + dy * dy;
-          if (best < 0 || v < best) best = v;
+      // exact squared Euclidean distance to the nearest listed cell in two separable passes, O(S^3) instead of O(S^4):
+      // col[x][y] = min over x' of (x - x')^2 with (x', y) listed; d2[x][y] = min over y' of col[x][y'] + (y - y')^2
+      for (int y = 0; y < S; ++y)
+        for (int x = 0; x < S; ++x) {
+          int best = -1;
+          for (int xx = 0; xx < S; ++xx) {
+            const int c = cfg->field_map[xx * S + y];
+            if (c != ca && c != cb) continue;
+            const int v = (x - xx) * (x - xx);
+            if (best < 0 || v < best) best = v;
+          }
+          col[(size_t)x * S + y] = best;
         }
-        d2[t * cells + i] = best;
-      }
+      for (int x = 0; x < S; ++x)
+        for (int y = 0; y < S; ++y) {
+          int best = -1;
+          for (int yy = 0; yy < S; ++yy) {
+            const int g = col[(size_t)x * S + yy];
+            if (g < 0) continue;
+            const int v = g + (y - yy) * (y - yy);
+            if (best < 0 || v < best) best = v;
+          }
+          d2[t * cells + x * S + y] = best;
+        }
     }
   }
   if ((ce = cudaMalloc(&env->d_map_tables, total)) != cudaSuccess ||

@@ -364,12 +364,21 @@ class CtfVecEnv(_MapVecEnv):
         """`seed` (an int) re-keys the env's generator as `super().reset(seed=seed)` does in the reference (ctf.py:1056,
         multigrid.py:114-119): the same seed gives the same placements and the same episode for the same actions."""
         if seed is not None:
+            if mask is not None:
+                raise ValueError("reset(seed=..., mask=...): re-keying the generator restarts the RNG streams of EVERY env of the batch; "
+                                 "reseed with a full reset, or reset the masked envs without a seed")
             self.reseed(seed)
             self._planes["hdr"][:, 3] = 0     # episode counters too: the device opponents' draws are keyed by (step, episode)
         _, info = super().reset(seed=seed, options=options, mask=mask)
         return self._option_obs(), info
 
+    def _check_host_option(self):
+        if self.observation_option != "map":     # before anything touches the state
+            raise NotImplementedError('host-array steps return observation_option="map" only; pass CUDA tensors')
+
     def step(self, actions):
+        if not isinstance(actions, torch.Tensor):
+            self._check_host_option()
         if self._device_policies:      # one small launch ahead of the step's: red actions from the current state
             self._check(self._lib.mg_red_policy_actions(self._h, _ptr(self.state), _ptr(self._red_buf), self._stream()))
         elif self._enemy_policies is not None:
@@ -377,9 +386,23 @@ class CtfVecEnv(_MapVecEnv):
         out = super().step(actions)
         if self.observation_option == "map":
             return out
-        if isinstance(out[0], np.ndarray):
-            raise NotImplementedError('host-array steps return observation_option="map" only; pass CUDA tensors')
         return (self._option_obs(),) + tuple(out[1:])
+
+    def step_async(self, actions):
+        """`step` with host arrays, first half: the red team decides exactly as in `step` - the device opponents' kernel is
+        enqueued on the host-path stream ahead of the step, host policies decide now - then H2D actions -> step -> D2H results."""
+        self._check_host_option()
+        if self._host_pending:
+            raise RuntimeError("step_async called again before step_wait")
+        if self._host_stream is None:
+            self._host_stream = torch.cuda.Stream(device=self.device)
+        if self._device_policies:
+            self._host_stream.wait_stream(torch.cuda.current_stream(self.device))
+            self._check(self._lib.mg_red_policy_actions(self._h, _ptr(self.state), _ptr(self._red_buf), C.c_void_p(self._host_stream.cuda_stream)))
+        elif self._enemy_policies is not None:
+            self._host_stream.synchronize()      # the previous host-path step must have landed before the state is read back
+            self._decide_red_actions()
+        super().step_async(actions)
 
     def set_red_actions(self, red_actions=None):
         """Drive the red agents from outside (the reference's `enemy_policies`, ctf.py:666): `red_actions` int8 CUDA tensor

@@ -36,6 +36,14 @@ COLLECT_PLAN = {
     "multigrid-collect-respawn-v0": ("collect_respawn", 12, 0.25),
     "multigrid-collect-quadrants15-v0": ("collect_quadrants15", 6, 0.5),
 }
+# Registered ids with constructor arguments the registry never uses, chosen to tell apart what coincides under balls_index =
+# [0, 1, 2] / balls_reward = [1, 1, 1]: a ball's reward is an attribute of the ball OBJECT - balls_reward[type] (or the literal 1 of
+# QuadrantsRespawn, collect_game.py:393) for balls placed by _gen_grid, balls_reward[COLOUR index] for balls placed by _respawn
+# (:130, :409) - and the info counter is indexed by the colour index (:147).   stem -> (id, overrides, episodes, greedy fraction)
+COLLECT_VARIANTS = {
+    "collect_respawn_clustered_rewards": ("multigrid-collect-respawn-clustered-v0", dict(balls_reward=[2.0, 3.0, 5.0]), 24, 0.75),
+    "collect_respawn_permuted": ("multigrid-collect-respawn-v0", dict(balls_index=[2, 0, 1], balls_reward=[1.0, 2.0, 4.0]), 24, 0.75),
+}
 
 
 class GreedyActions:
@@ -69,10 +77,12 @@ class GreedyActions:
         return acts
 
 
-def gen_collect():
+def gen_collect(only_variants=False):
     rh.import_reference()
-    for env_id, (stem, episodes, greedy_frac) in COLLECT_PLAN.items():
-        env, time_limit = rh.make_collect(env_id)
+    plan = [] if only_variants else [(env_id, {}, stem, episodes, gf) for env_id, (stem, episodes, gf) in COLLECT_PLAN.items()]
+    plan += [(env_id, ov, stem, episodes, gf) for stem, (env_id, ov, episodes, gf) in COLLECT_VARIANTS.items()]
+    for env_id, overrides, stem, episodes, greedy_frac in plan:
+        env, time_limit = rh.make_collect(env_id, **overrides)
         eps = []
         for seed in range(episodes):
             greedy = seed < int(round(greedy_frac * episodes))
@@ -82,7 +92,8 @@ def gen_collect():
         K = max(2, max(int(e["n_draws"].max()) for e in eps))
         packed = rh.pack_collect_episodes(eps, T, K)
         from gymnasium.envs.registration import registry
-        kw = registry[env_id]["kwargs"]
+        kw = dict(registry[env_id]["kwargs"])
+        kw.update(overrides)
         packed["meta_env_id"] = np.array(env_id)
         packed["meta_time_limit"] = np.array(time_limit or 0)
         packed["meta_size"] = np.array(kw["size"])
@@ -370,6 +381,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat", "policies"]
     if "collect" in which:
         gen_collect()
+    elif "collect_variants" in which:      # only the COLLECT_VARIANTS fixtures (added in round 2; the others are unchanged)
+        gen_collect(only_variants=True)
     if "maze" in which:
         gen_maze()
     if "ctf" in which:

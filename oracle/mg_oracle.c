@@ -285,9 +285,8 @@ static void step_env(const oc_collect_cfg* c, uint8_t* g, uint8_t* pos, int32_t*
       CELL(g, H, nx, ny) = 0;                       /* grid.set(*fwd_pos, None) :141 */
       if (c->respawn) respawn(c, g, r, colour);     /* :142-143, may land on (nx, ny) */
       *collected += 1;                              /* :144 */
-      int t = type_of_colour(c, colour);
       rew[i] += (cell >> 6) & 1 ? reward_respawned(c, colour) : reward_initial(c, colour); /* fwd_cell.reward :145 */
-      if (t >= 0) info[nb * i + t] += 1;            /* :147 */
+      if (colour < nb) info[nb * i + colour] += 1;  /* :147 info[keys[num_ball_types * i + ball_idx]], ball_idx = the COLOUR index (:139) */
       enter = 1;
     } else if (cell == 0) { /* :178-181 */
       enter = 1;

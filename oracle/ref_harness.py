@@ -132,8 +132,8 @@ COLLECT_IDS = [
 ]
 
 
-def make_collect(env_id: str):
-    """Construct a reference Collect env for a registered id; returns (env, time_limit)."""
+def make_collect(env_id: str, **overrides):
+    """Construct a reference Collect env for a registered id (`overrides` replace registered kwargs); returns (env, time_limit)."""
     import_reference()
     import importlib
     from gymnasium.envs.registration import registry
@@ -142,6 +142,7 @@ def make_collect(env_id: str):
     mod, cls_name = spec["entry_point"].split(":")
     cls = getattr(importlib.import_module(mod), cls_name)
     kw = dict(spec["kwargs"])
+    kw.update(overrides)
     if cls_name == "CollectGameQuadrantsRespawn":
         from gym_multigrid.envs.collect_game import CollectGameQuadrants
         env = object.__new__(cls)

@@ -17,6 +17,10 @@ COLLECT_FIXTURES = {
     "collect_rooms_respawn": ("rooms", True),
     "collect_respawn": ("even_dist", False),
     "collect_quadrants15": ("quadrants", False),
+    # constructor arguments outside the registry (oracle/gen_golden.py COLLECT_VARIANTS): rewards / counters that differ between
+    # balls placed by _gen_grid and by _respawn, and between type index and colour index
+    "collect_respawn_clustered_rewards": ("quadrants_respawn", False),
+    "collect_respawn_permuted": ("even_dist", False),
 }
 
 

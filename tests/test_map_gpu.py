@@ -232,6 +232,13 @@ def test_map_create_rejects_bad_configs(cuda_device):
         mg.make_ctf_vec(4, np.zeros((6, 6)))            # no flags
     with pytest.raises(ValueError):
         mg.make_ctf_vec(4, load_golden("ctf_2v2")["field_map"], num_blue_agents=12, num_red_agents=12)
+    # Ctf1v1Env with a collision penalty: the reference raises (ctf.py:639); the C ABI refuses it too, not only the Python class
+    with pytest.raises(ValueError, match="obstacle_penalty"):
+        mg.make_ctf_vec(4, load_golden("ctf_2v2")["field_map"], num_blue_agents=1, num_red_agents=1, variant_1v1=True, obstacle_penalty_ratio=0.5)
+    e = mg.make_ctf_vec(4, load_golden("ctf_2v2")["field_map"])
+    with pytest.raises(ValueError, match="mask"):
+        e.reset(seed=3, mask=np.array([1, 0, 0, 1]))
+    e.close()
 
 
 def test_ctf1v1_replay_and_philox(cuda_device):

@@ -124,3 +124,43 @@ def test_device_policies_reject_what_they_cannot_express(cuda_device):
     env.step(torch.zeros((4, 2), dtype=torch.int8, device=cuda_device))
     assert env.status() == 0
     env.close()
+
+
+def test_step_async_runs_the_opponents_like_step(cuda_device):
+    """step_async / step_wait on a CtF batch with opponents (device-decided, and host policies): the red team must decide before
+    every step exactly as in `step` - same observations, rewards and flags as the blocking device path; non-"map" observation
+    options are refused before the state is touched."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    fm = g["field_map"].astype(np.float64)
+    n = 600
+    for device_side in (True, False):
+        m = n if device_side else 12
+        ref = mg.make_ctf_vec(m, g["field_map"], seed=4, max_steps=25)
+        pip = mg.make_ctf_vec(m, g["field_map"], seed=4, max_steps=25)
+        for e in (ref, pip):
+            e.set_enemy_policies(_policies(("FightPolicy", "PatrolFightPolicy"), fm, (0.75, 0.6)), device=device_side,
+                                 random_generator=np.random.default_rng(3))
+            e.reset()
+        rng = np.random.default_rng(1)
+        moved = 0
+        for t in range(40):
+            act = rng.integers(0, 5, size=(m, 2)).astype(np.int8)
+            want = ref.step(torch.as_tensor(act, device=cuda_device))
+            pip.step_async(act)
+            got = pip.step_wait()
+            for x, y in zip(want[:4], got[:4]):
+                assert np.array_equal(_np(x), y), f"device={device_side} step {t}"
+            assert np.array_equal(_np(ref._red_buf), _np(pip._red_buf))
+            moved += int((_np(pip._red_buf) != 0).sum())
+        assert moved > 0, "the opponents never acted"
+        ref.close(); pip.close()
+    flat = mg.make_ctf_vec(8, g["field_map"], observation_option="flattened")
+    flat.reset()
+    before = flat.state.clone()
+    with pytest.raises(NotImplementedError):
+        flat.step_async(np.zeros((8, 2), np.int8))
+    with pytest.raises(NotImplementedError):
+        flat.step(np.zeros((8, 2), np.int8))
+    assert torch.equal(flat.state, before), "a refused host step must not advance the state"
+    flat.close()

@@ -67,6 +67,27 @@ def soak_collect(rng, stats):
         b += same(_np(term), oterm, "collect terminated", cfg) + same(_np(trunc), otrunc, "collect truncated", cfg)
         d = oterm | otrunc
         b += same(_np(info["final_observation"])[d], ofin[d], "collect final obs", cfg)
+    # ... continued as ONE launch (mg_rollout, state held in shared memory over T steps; drawn T includes 1)
+    T = int(rng.integers(1, 2 * tl))
+    racts = rng.integers(-1, 5, size=(T, n, A)).astype(np.int8)
+    robs, rrew, rterm, rtrunc, rinfo = env.rollout(torch.as_tensor(racts, device=DEV), final_observation=True)
+    robs, rrew, rterm, rtrunc, rfin = _np(robs), _np(rrew), _np(rterm), _np(rtrunc), _np(rinfo["final_observation"])
+    for t in range(T):
+        oobs, orew, oterm, otrunc, ofin = o.step(racts[t], r, autoreset=True, want_final_obs=True)
+        b += same(robs[t], oobs, f"rollout obs step {t} of {T}", cfg) + same(rrew[t], orew, "rollout rewards", cfg)
+        b += same(rterm[t], oterm, "rollout terminated", cfg) + same(rtrunc[t], otrunc, "rollout truncated", cfg)
+        d = oterm | otrunc
+        b += same(rfin[t][d], ofin[d], "rollout final obs", cfg)
+    # ... and through host buffers with one of the result transports (expanded obs / packed plane / per-env delta records)
+    tr = str(rng.choice(["full", "packed", "delta"]))
+    env.set_host_transport(tr, int(rng.integers(1, 5)))
+    for t in range(int(rng.integers(2, tl + 4))):
+        act = rng.integers(-1, 5, size=(n, A)).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(act)
+        oobs, orew, oterm, otrunc = o.step(act, r, autoreset=True)
+        b += same(obs, oobs, f"host step {t} obs ({tr})", cfg) + same(rew, orew, f"host rewards ({tr})", cfg)
+        b += same(term, oterm, f"host terminated ({tr})", cfg) + same(trunc, otrunc, f"host truncated ({tr})", cfg)
+    steps += T
     b += same(_np(env.grid), o.grid, "collect grid", cfg) + same(_np(env.pickups).reshape(n, -1), o.info, "collect counters", cfg)
     dirs = rng.integers(0, 4, size=(n, A)).astype(np.uint8)
     V, st = int(rng.choice([3, 4, 5, 6, 7, 9])), bool(rng.integers(0, 2))
