@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   __shared__ uint8_t s_done[kMapE];
   const int tid = threadIdx.x, n = p.n, cells = p.cells;
   const bool view_mode = FAMILY == MG_FAMILY_MAZE && p.view_V != 0;                 // obs = partial views (gen_obs) instead of the map
-  const int head = view_mode ? p.map_padded_bytes : p.L;
+  const bool view_table = view_mode && p.view_table != nullptr;                     // memoised views: no map needed in shared memory
+  const int head = view_table ? 0 : (view_mode ? p.map_padded_bytes : p.L);
   uint8_t* s_period = smem_raw;                                                     // [L], or the padded packed map in view mode
   uint32_t* s_ag = reinterpret_cast<uint32_t*>(smem_raw + head);                    // [n][kMapE] agent words, transposed
   uint8_t* s_obs = smem_raw + head + (size_t)n * kMapE * 4;                         // [kMapE][cells] (staged tiles) / the tile's views
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   // staged u8 tiles: the static part of the whole tile's observation slab (the map repeated once per env) arrives as ONE bulk
   // load of a host-built image while the envs step - no per-thread replication of the period, no barrier in front of the patches
   const bool tile_img = !view_mode && p.obs_tile && p.obs;
-  if (tid == 0) {
+  if (tid == 0 && head) {
     mbar_expect_tx(&bar, (uint32_t)head);
     tma_load_1d(s_period, view_mode ? p.map_padded : p.obs_period, (uint32_t)head, &bar);
     if (tile_img) {   // own barrier: the step only waits for the period
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
       want_reset = done = p.autoreset && (term || trunc);  // same-step autoreset
     }
   }
-  mbar_wait(&bar, 0);
+  if (head) mbar_wait(&bar, 0);
 
   // ---- terminal observations of the finished envs are drawn before their reset (only when the caller asked for them)
   if (p.final_obs) {
@@ -485,7 +486,12 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
       const int x = ag_x(w), y = ag_y(w), dir = (int)((w >> 16) & 3u);
       const uint32_t agent_cell = (uint32_t)p.view_agent | ((uint32_t)dir << 6);
       int x0, y0, sa, sb;
-      if (V == 7) {
+      if (view_table) {
+        const uint4* row = p.view_table + (size_t)((((x * p.S + y) << 2) | dir)) * p.view_row16;
+        if (V == 7) view_copy_store<7>(row, s_obs, tid);
+        else if (V == 5) view_copy_store<5>(row, s_obs, tid);
+        else view_copy_store<3>(row, s_obs, tid);
+      } else if (V == 7) {
         view_geometry<7>(x, y, dir, p.pitch, x0, y0, sa, sb);
         view_compute_store<false, 7>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
       } else if (V == 5) {
@@ -735,6 +741,7 @@ int map_tma_reps(int L, int cells, int obs_dtype) {
   if (r > tile / (16 * Lb)) r = tile / (16 * Lb);
   return r < 1 ? 1 : (int)r;
 }
+// padded_bytes = 0 with the memoised view table (the map is then not staged)
 size_t map_view_smem_bytes(int padded_bytes, int V) { return (size_t)padded_bytes + (size_t)4 * kMapE + (size_t)kMapE * V * V * 3 + 16; }
 cudaError_t configure_map_view_mode(size_t smem) {
   cudaError_t e;
@@ -756,7 +763,7 @@ int map_tile_envs() { return kMapE; }
 
 template <int FAMILY, int MODE, int MINB, int STEPV>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
-  const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.map_padded_bytes, p.view_V)
+  const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.view_table ? 0 : p.map_padded_bytes, p.view_V)
                                                                : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((p.N + kMapE - 1) / kMapE)); cfg.blockDim = dim3(kMapE);

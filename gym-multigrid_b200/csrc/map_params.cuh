@@ -33,6 +33,9 @@ struct MapParams {
   int view_V, view_see_through;            // 0 = off; 3 / 5 / 7
   const uint8_t* map_padded; int pad, pitch, map_padded_bytes;   // packed static map surrounded by the out-of-map filler
   uint8_t view_oob, view_agent;
+  // memoised views: on a static map a Maze view is a pure function of (x, y, dir), so mg_set_partial_obs runs the view kernel once
+  // over all S*S*4 agent states and the step copies its env's row: [((x*S + y) << 2) | dir][view_row16] uint4, 3*V*V bytes used
+  const uint4* view_table; int view_row16;
   int obs_staged;                          // 1 = the tile's u8 obs slab is assembled in shared memory (small maps)
   // state planes
   uint8_t* agents;   // [N_pad][row_bytes]: agent i at bytes 4i..4i+3 = x, y, dir, flags (bit0 terminated, bit1 collided)

@@ -83,6 +83,7 @@ struct mg_env {
   long long* d_flat_tmpl;                  // ... uploaded on first use
   std::vector<std::pair<int, uint8_t*>> atlases;    // render: (tile_size, device atlas) built on first use, freed by mg_destroy
   uint8_t* d_policy_tables;        // CtF: tables of the scripted opponents (mg_set_red_policies), or null
+  uint4* d_view_table;             // Maze partial-observation mode: the memoised views of all S*S*4 agent states, or null
   mg::PolicyParams pbase;
   const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
@@ -297,6 +298,7 @@ extern "C" int mg_destroy(mg_env* env) {
   for (auto& a : env->atlases) cudaFree(a.second);
   cudaFree(env->d_flat_tmpl);
   cudaFree(env->d_policy_tables);
+  cudaFree(env->d_view_table);
   cudaFree(env->d_actions); cudaFree(env->d_obs); cudaFree(env->d_final);   // rewards / term / trunc live inside the d_obs block
   cudaFree(env->d_delta_blk); cudaFree(env->d_reset_rows);
   cudaFreeHost(env->h_delta_blk); cudaFreeHost(env->h_reset_rows); cudaFreeHost(env->h_grid);
@@ -663,13 +665,62 @@ extern "C" int mg_set_partial_obs(mg_env* env, int view_size, int see_through_wa
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   mg::MapParams& p = env->mbase;
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(env, "cudaDeviceSynchronize", ce);   // a launch may still read the old table
+  cudaFree(env->d_view_table);
+  env->d_view_table = nullptr; p.view_table = nullptr; p.view_row16 = 0;
   if (view_size) {
-    const size_t smem = mg::map_view_smem_bytes((int)env->map_padded_bytes, view_size);
-    if (smem > 227 * 1024) return fail(env, "mg_set_partial_obs: padded map does not fit in shared memory");
-    if ((ce = mg::configure_map_view_mode(smem)) != cudaSuccess) return cuda_fail(env, "cudaFuncSetAttribute", ce);
     p.map_padded = env->d_map_tables + env->map_padded_off; p.pad = env->map_pad; p.pitch = p.S + 2 * env->map_pad;
     p.map_padded_bytes = (int)env->map_padded_bytes;
     p.view_oob = mg::cell(3, 7, 1); p.view_agent = mg::cell(1, 4, 0);   // as mg_gen_obs: out-of-map filler, Agent(color="blue")
+    // Memoised views: the map never changes and the agent is the only moving object, so a view is a pure function of (x, y, dir).  The
+    // view kernel - slice, rotations, process_vis, encode - runs ONCE over all S*S*4 agent states; a step then copies its env's 3*V*V
+    // bytes out of the table.  Measured (1 M envs, 64x64, V = 7): 57.0 us against 55.6 us for computing every view in the step - the
+    // uncoalesced 16-byte row gathers cost the load/store unit what the view arithmetic costs the ALUs - so the table is used only
+    // when asked for (MG_VIEW_TABLE=1) or when the padded map is too large to be staged in shared memory (maps beyond ~190x190).
+    const char* tv = std::getenv("MG_VIEW_TABLE");
+    const bool map_fits = mg::map_view_smem_bytes((int)env->map_padded_bytes, view_size) <= 227 * 1024;
+    if ((tv && tv[0] == '1') || (!map_fits && !(tv && tv[0] == '0'))) {
+      const int S = p.S, VV3 = 3 * view_size * view_size, row16 = (VV3 + 15) / 16;
+      const size_t M = (size_t)S * S * 4;
+      std::vector<uint8_t> states(M * 4 + 1024, 0);
+      for (int x = 0; x < S; ++x)
+        for (int y = 0; y < S; ++y)
+          for (int d = 0; d < 4; ++d) {
+            uint8_t* q = &states[((((size_t)x * S + y) << 2) | d) * 4];
+            q[0] = (uint8_t)x; q[1] = (uint8_t)y; q[2] = (uint8_t)d;
+          }
+      uint8_t *d_states = nullptr, *d_tmp = nullptr;
+      uint4* table = nullptr;
+      mg::ViewParams q;
+      std::memset(&q, 0, sizeof q);
+      q.V = view_size; q.see_through = see_through_walls != 0; q.family = MG_FAMILY_MAZE;
+      q.W = q.H = S; q.cells = S * S; q.A = 1; q.N = (long long)M;
+      q.map_codes = env->d_map_tables + env->map_codes_off;
+      q.map_padded = p.map_padded; q.pad = p.pad; q.pitch = p.pitch; q.map_padded_bytes = p.map_padded_bytes;
+      q.oob_code = p.view_oob; q.agent_code = p.view_agent;
+      if (mg::view_smem_bytes(q) > 227 * 1024) q.map_padded = nullptr;   // large padded maps: the generic view kernel reads the map through L1
+      if ((ce = cudaMalloc(&d_states, states.size())) != cudaSuccess || (ce = cudaMalloc(&d_tmp, M * VV3 + 16)) != cudaSuccess ||
+          (ce = cudaMalloc(&table, M * row16 * 16)) != cudaSuccess ||
+          (ce = cudaMemcpy(d_states, states.data(), states.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+          (ce = cudaMemset(table, 0, M * row16 * 16)) != cudaSuccess) {
+        cudaFree(d_states); cudaFree(d_tmp); cudaFree(table);
+        return cuda_fail(env, "mg_set_partial_obs: view table", ce);
+      }
+      q.pos = d_states; q.pos_stride = 4; q.dirs = d_states + 2; q.dir_stride = 4;
+      q.out = d_tmp; q.out_bulk_ok = 1;
+      if ((ce = mg::launch_view(q, nullptr)) != cudaSuccess ||
+          (ce = cudaMemcpy2D(table, (size_t)row16 * 16, d_tmp, (size_t)VV3, (size_t)VV3, M, cudaMemcpyDeviceToDevice)) != cudaSuccess ||
+          (ce = cudaDeviceSynchronize()) != cudaSuccess) {
+        cudaFree(d_states); cudaFree(d_tmp); cudaFree(table);
+        return cuda_fail(env, "mg_set_partial_obs: view table", ce);
+      }
+      cudaFree(d_states); cudaFree(d_tmp);
+      env->d_view_table = table; p.view_table = table; p.view_row16 = row16;
+      env->launches += 1;
+    }
+    const size_t smem = mg::map_view_smem_bytes(p.view_table ? 0 : (int)env->map_padded_bytes, view_size);
+    if (smem > 227 * 1024) return fail(env, "mg_set_partial_obs: padded map does not fit in shared memory");
+    if ((ce = mg::configure_map_view_mode(smem)) != cudaSuccess) return cuda_fail(env, "cudaFuncSetAttribute", ce);
   }
   p.view_V = view_size; p.view_see_through = see_through_walls != 0;
   // the observation size changed: mg_step_host re-creates its device staging block on the next call

@@ -113,4 +113,27 @@ __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, i
   }
 }
 
+// A memoised view (MapParams::view_table): copy the 3*V*V bytes of `row` (16-byte aligned, zero padded) to s_out + v * 3*V*V - the same
+// head / aligned words / tail placement as view_compute_store, since consecutive views of a tile are 3*V*V (odd) bytes apart.
+template <int V>
+__device__ __forceinline__ void view_copy_store(const uint4* row, uint8_t* s_out, int v) {
+  constexpr int VV = V * V, NFULL = (3 * VV - 3) / 4, NQ = (NFULL + 1 + 3) / 4;
+  uint32_t w[4 * NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const uint4 q = __ldg(row + k);
+    w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+  }
+  uint8_t* dst = s_out + (size_t)v * (3 * VV);
+  const int h = (int)((4u - ((uint32_t)v * (3u * VV) & 3u)) & 3u);
+  uint32_t* q = reinterpret_cast<uint32_t*>(dst + h);
+#pragma unroll
+  for (int j = 0; j < NFULL; ++j) q[j] = __funnelshift_r(w[j], w[j + 1], 8 * h);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const bool head = i < h;
+    dst[head ? i : 4 * NFULL + i] = (uint8_t)((head ? w[0] : w[NFULL]) >> (8 * i));
+  }
+}
+
 }  // namespace mg

@@ -150,10 +150,31 @@ def gen_maze():
     os.unlink(tmp.name)
 
 
-def gen_ctf():
+class MovingActions:
+    """Blue actions that never `stay`: with a collision penalty staying is a self-collision that ends the agent (ctf.py:1231-1236),
+    so uniformly random episodes are over before two agents ever meet.  Moving blue agents live long enough to battle."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+
+    def integers(self, lo, hi, size=None):
+        return self.rng.integers(max(lo, 1), hi, size=size)
+
+
+def gen_ctf(only_penalty_battles=False):
     plans = [("ctf_2v2", 2, 2, 0.0, 32), ("ctf_3v4", 3, 4, 0.0, 12), ("ctf_2v2_penalty", 2, 2, 0.5, 12), ("ctf_1v1", 1, 1, 0.0, 8)]
+    if only_penalty_battles:
+        plans = []
+    # round 2: collision penalty AND battles in the same episodes (ctf.py:1316-1332 next to :1359-1420): 3v4, blue never stays,
+    # keeping only the episodes of 400 in which at least one battle was fought
+    plans.append(("ctf_3v4_penalty_battles", 3, 4, 0.5, 400))
     for stem, nb, nr, pen, episodes in plans:
-        eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, np.random.default_rng(3000 + seed), nb, nr, pen) for seed in range(episodes)]
+        if stem == "ctf_3v4_penalty_battles":
+            eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, MovingActions(3300 + seed), nb, nr, pen) for seed in range(episodes)]
+            eps = [e for e in eps if int(np.sum(e["n_battles"])) > 0]
+            episodes = len(eps)
+        else:
+            eps = [rh.record_ctf_mvn_episode(CTF_MAP, seed, np.random.default_rng(3000 + seed), nb, nr, pen) for seed in range(episodes)]
         for e in eps:
             assert e["obs"].dtype == np.int64     # the reference's dtype (ctf.py:1138)
             e["obs"] = e["obs"].astype(np.uint8)
@@ -387,6 +408,8 @@ if __name__ == "__main__":
         gen_maze()
     if "ctf" in which:
         gen_ctf()
+    elif "ctf_penalty_battles" in which:
+        gen_ctf(only_penalty_battles=True)
     if "ctf1v1" in which:
         gen_ctf1v1()
     if "partial" in which:

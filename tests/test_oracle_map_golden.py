@@ -7,7 +7,7 @@ import oracle as oc
 from replay import load_golden
 
 MAZE = ["maze_board13", "maze_board13_penalty", "maze_gen64", "maze_gen64_penalty"]
-CTF = ["ctf_2v2", "ctf_3v4", "ctf_2v2_penalty", "ctf_1v1"]
+CTF = ["ctf_2v2", "ctf_3v4", "ctf_2v2_penalty", "ctf_1v1", "ctf_3v4_penalty_battles"]   # the last: collision penalty AND battles in the same episodes
 
 
 @pytest.mark.parametrize("stem", MAZE)

@@ -77,11 +77,14 @@ def test_maze_views_match_composed_oracle(stem, cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("table", ["1", "0"])
 @pytest.mark.parametrize("V,st", [(7, False), (5, True), (3, False)])
-def test_maze_fused_step_and_partial_view(V, st, cuda_device):
-    """observation_option="partial": the step kernel itself writes the gen_obs views (mg_set_partial_obs); they must equal
-    mg_gen_obs on the post-step state and the composed oracle, including across same-step autoresets and a ragged tile."""
+def test_maze_fused_step_and_partial_view(V, st, table, cuda_device, monkeypatch):
+    """observation_option="partial": the step kernel itself writes the gen_obs views (mg_set_partial_obs) - computed per step (default), or copied from
+    the memoised table of all S*S*4 agent states (MG_VIEW_TABLE=1, what maps too large for shared memory use); they must equal mg_gen_obs on
+    the post-step state and the composed oracle, including across same-step autoresets and a ragged tile."""
     import gym_multigrid_b200 as mg
+    monkeypatch.setenv("MG_VIEW_TABLE", table)
     g = load_golden("maze_gen64")
     fm = g["field_map"]
     S, n = fm.shape[0], 1000

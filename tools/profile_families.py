@@ -39,6 +39,12 @@ def main():
         e = mg.make_maze_vec(n, golden("maze_gen64", "field_map"))
         a = torch.randint(0, 5, (n,), device=dev, dtype=torch.int8)
         f = lambda: e.step(a)  # noqa: E731
+    elif fam == "maze_partial":     # BASELINE config 4: fused step + V = 7 partial views
+        n = n or (1 << 20)
+        e = mg.make_maze_vec(n, golden("maze_gen64", "field_map"))
+        e.set_partial_obs(7)
+        a = torch.randint(0, 5, (n,), device=dev, dtype=torch.int8)
+        f = lambda: e.step(a)  # noqa: E731
     elif fam == "view_maze":
         n = n or 131072
         e = mg.make_maze_vec(n, golden("maze_gen64", "field_map"))
@@ -53,8 +59,9 @@ def main():
     elif fam == "wildfire":
         n = n or 16384
         e = mg.make_wildfire_vec(n, size=64, num_agents=16)
-        a = torch.randint(0, 5, (n, 16), device=dev, dtype=torch.int8)
-        f = lambda: e.step(a)  # noqa: E731
+        acts = [torch.randint(0, 5, (n, 16), device=dev, dtype=torch.int8) for _ in range(12)]
+        it = iter(range(10 ** 9))
+        f = lambda: e.step(acts[next(it) % 12])  # noqa: E731
     elif fam == "render":
         n = n or 1024
         e = mg.make_vec("multigrid-collect-respawn-clustered-v0", n)
@@ -71,7 +78,8 @@ def main():
     else:
         raise SystemExit(f"unknown family {fam}")
     e.reset()
-    for _ in range(12):
+    torch.cuda.synchronize()
+    for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 12):
         f()
     torch.cuda.synchronize()
     e.close()
