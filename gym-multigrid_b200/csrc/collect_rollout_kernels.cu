@@ -79,6 +79,13 @@ __device__ __forceinline__ void expand_warp(const uint8_t* s_grid, uint8_t* s_ob
   }
 }
 
+// mark = CollectParams::mark_respawned (uniform): only then can a ball carry bit 6 and the encoding needs the four extra masking
+// operations per word; no registered config does.  Two copies of this small loop instead of two copies of the whole tile body.
+__device__ __forceinline__ void expand_tile_warp(const uint8_t* s_grid, uint8_t* s_obs, int n16, int lane, int mark) {
+  if (mark) expand_warp<true>(s_grid, s_obs, n16, lane);
+  else expand_warp<false>(s_grid, s_obs, n16, lane);
+}
+
 // `bytes` from shared to global memory by the warp (32-bit words when both sides allow it)
 __device__ __forceinline__ void warp_copy(uint8_t* gdst, const uint8_t* src, uint32_t bytes, int lane) {
   if (((reinterpret_cast<uintptr_t>(gdst) | reinterpret_cast<uintptr_t>(src) | bytes) & 3u) == 0) {
@@ -117,7 +124,7 @@ struct TileClock {
 // One tile (32 envs, lane = env) for T steps.  AT = 2: the two-agent fast path - positions, actions, rewards and flags live in
 // registers, the next step's actions are prefetched into a register, rewards / flags leave as plain coalesced stores and only the
 // observation slab goes through shared memory and TMA.  AT = 0: any agent count, everything staged in shared memory.
-template <int MODE, int AT, bool MARK>
+template <int MODE, int AT>
 __device__ __forceinline__ void rollout_tile(const CollectParams& p, const WarpSmem& s, long long tile, int lane, uint32_t& ph_state,
                                              uint32_t& ph_act0, uint32_t& ph_act1) {
   const int A = AT ? AT : p.A, cells = p.cells, T = p.T;
@@ -247,7 +254,7 @@ __device__ __forceinline__ void rollout_tile(const CollectParams& p, const WarpS
     clk.lap(2);
     if (p.obs) {
       if (!obs_valid) {
-        expand_warp<MARK>(s.grid, s.obs, n16, lane);
+        expand_tile_warp(s.grid, s.obs, n16, lane, p.mark_respawned);
       } else if (AT == 2 && live) {   // (lanes beyond the tile own no row: their pointers lie outside the warp's slice)
         // <= 6 cells; all index loads, then all cell loads, then the stores: the loads overlap instead of forming one dependent chain per cell
         int idx[6]; uint8_t cc[6];
@@ -259,13 +266,13 @@ __device__ __forceinline__ void rollout_tile(const CollectParams& p, const WarpS
         for (int k = 0; k < 6; ++k)
           if (k < nchg) {
             uint8_t* o = o_row + 3 * idx[k];
-            o[0] = cc[k] & 3; o[1] = (cc[k] >> 2) & 15; o[2] = MARK ? state_of(cc[k]) : (uint8_t)(cc[k] >> 6);
+            o[0] = cc[k] & 3; o[1] = (cc[k] >> 2) & 15; o[2] = state_of(cc[k]);
           }
       } else if (AT != 2) {
         for (int k = 0; k < nchg; ++k) {
           const int idx = chg[k];
           const uint8_t c = g[idx];
-          o_row[3 * idx] = c & 3; o_row[3 * idx + 1] = (c >> 2) & 15; o_row[3 * idx + 2] = MARK ? state_of(c) : (uint8_t)(c >> 6);
+          o_row[3 * idx] = c & 3; o_row[3 * idx + 1] = (c >> 2) & 15; o_row[3 * idx + 2] = state_of(c);
         }
       }
       obs_valid = true;
@@ -312,7 +319,7 @@ __device__ __forceinline__ void rollout_tile(const CollectParams& p, const WarpS
       int slot = 0;
       if (p.delta && done) slot = atomicAdd(p.reset_count, 1);
       __syncwarp();
-      if (p.obs) expand_warp<MARK>(s.grid, s.obs, n16, lane);  // re-encode (the reset envs changed everywhere)
+      if (p.obs) expand_tile_warp(s.grid, s.obs, n16, lane, p.mark_respawned);  // re-encode (the reset envs changed everywhere)
       if (p.delta) {
         for (unsigned m = done_mask; m; m &= m - 1) {
           const int j = __ffs(m) - 1;
@@ -394,12 +401,8 @@ __global__ void __launch_bounds__(kRollThreads, 7) collect_rollout_kernel(const 
   pdl_wait();
   uint32_t ph_state = 0, ph_act0 = 0, ph_act1 = 0;
   for (long long tile = gw; tile < ntiles; tile += nw) {
-    if (p.A == 2) {
-      if (p.mark_respawned) rollout_tile<MODE, 2, true>(p, s, tile, lane, ph_state, ph_act0, ph_act1);
-      else rollout_tile<MODE, 2, false>(p, s, tile, lane, ph_state, ph_act0, ph_act1);
-    } else {
-      rollout_tile<MODE, 0, true>(p, s, tile, lane, ph_state, ph_act0, ph_act1);
-    }
+    if (p.A == 2) rollout_tile<MODE, 2>(p, s, tile, lane, ph_state, ph_act0, ph_act1);
+    else rollout_tile<MODE, 0>(p, s, tile, lane, ph_state, ph_act0, ph_act1);
   }
   if (lane == 0) tma_wait_read_all();  // shared memory must outlive the bulk reads
 }
