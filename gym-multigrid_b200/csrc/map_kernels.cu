@@ -57,6 +57,9 @@ __device__ __forceinline__ int dir_of_action(int a, int old) { return a == 0 ? o
 
 template <int MODE>
 __device__ __forceinline__ int below(Rng<MODE>& r, int n) { return (int)__umulhi(r.u32(), (uint32_t)n); }
+// the step's small draws (n <= 16): 16 bits each, multiply-shift
+template <int MODE>
+__device__ __forceinline__ int below16(Rng<MODE>& r, int n) { return (int)((r.u16() * (uint32_t)n) >> 16); }
 
 // `ag` = this env's column of the transposed agent words: agent i at ag[i * kMapE].  Cell lists hold packed x | y << 8.
 template <int FAMILY, int MODE>
@@ -137,7 +140,7 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
   }
   for (int k = 0; k < nr; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301)
     // Philox mode with red_actions given: an external enemy policy (the reference's `enemy_policies`, ctf.py:666) - no draw
-    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * nr + k] : below(r, 5);
+    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * nr + k] : below16(r, 5);
     if (a < 0 || a > 4) err |= MG_ERR_BAD_ACTION;
     acts |= (NIB)((a < 0 || a > 4) ? 15 : a) << (4 * (nb + k));
   }
@@ -148,7 +151,7 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
   } else {  // np_random.shuffle stand-in: Fisher-Yates
     order = (NIB)0xFEDCBA9876543210ull;
     for (int i = n - 1; i > 0; --i) {
-      const int j = below(r, i + 1);
+      const int j = below16(r, i + 1);
       const NIB x = ((order >> (4 * i)) ^ (order >> (4 * j))) & (NIB)15;
       order ^= (x << (4 * i)) | (x << (4 * j));
     }
@@ -238,7 +241,7 @@ __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, u
   }
 #pragma unroll
   for (int k = 0; k < NR; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301), or the external enemy policy
-    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * NR + k] : below(r, 5);
+    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * NR + k] : below16(r, 5);
     const bool bad = a < 0 || a > 4;
     if (bad) err |= MG_ERR_BAD_ACTION;
     acts |= (uint32_t)(bad ? 15 : a) << (4 * (NB + k));
@@ -253,7 +256,7 @@ __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, u
     order = 0x76543210u;
 #pragma unroll
     for (int i = n - 1; i > 0; --i) {
-      const int j = below(r, i + 1);
+      const int j = below16(r, i + 1);
       const uint32_t x = ((order >> (4 * i)) ^ (order >> (4 * j))) & 15u;
       order ^= (x << (4 * i)) | (x << (4 * j));
     }

@@ -106,12 +106,21 @@ template <int MODE>
 struct Rng {
   const uint8_t* draws; int n, k;                       // trace
   uint32_t k0, k1, id0, id1, ctr, b0, b1, b2, b3; int have;  // philox
+  uint32_t h16; int nh16;                                  // ... half-word buffer of u16()
   int err;
 
-  __device__ __forceinline__ void open_trace(const uint8_t* d, int n_) { draws = d; n = n_; k = 0; err = 0; have = 0; }
+  __device__ __forceinline__ void open_trace(const uint8_t* d, int n_) { draws = d; n = n_; k = 0; err = 0; have = 0; nh16 = 0; }
   __device__ __forceinline__ void open_philox(unsigned long long seed, unsigned long long env_id, uint32_t ctr_) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); id0 = (uint32_t)env_id; id1 = (uint32_t)(env_id >> 32);
-    ctr = ctr_; have = 0; err = 0; k = 0; n = 0; draws = nullptr;
+    ctr = ctr_; have = 0; nh16 = 0; err = 0; k = 0; n = 0; draws = nullptr;
+  }
+  // 16 random bits: small draws (an action out of 5, a Fisher-Yates index) take half a Philox word each, so the ~5 draws of a 2v2
+  // CtF step fit one Philox block instead of two (the block is ~100 of the step's ~1000 instructions)
+  __device__ __forceinline__ uint32_t u16() {
+    if (nh16 == 0) { h16 = u32(); nh16 = 2; }
+    const uint32_t v = h16 & 0xFFFFu;
+    h16 >>= 16; --nh16;
+    return v;
   }
   __device__ __forceinline__ uint32_t u32() {
     if (have == 0) {

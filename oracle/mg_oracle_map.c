@@ -9,7 +9,7 @@
 enum { MZ_BACKGROUND = 0, MZ_AGENT = 1, MZ_FLAG = 2, MZ_OBSTACLE = 3 };
 enum { CT_BLUE_TERR = 0, CT_RED_TERR = 1, CT_BLUE_AGENT = 2, CT_RED_AGENT = 3, CT_BLUE_FLAG = 4, CT_RED_FLAG = 5, CT_OBSTACLE = 6 };
 
-typedef struct { uint64_t seed, env_id; uint32_t ctr, buf[4]; int have; } prng_t;
+typedef struct { uint64_t seed, env_id; uint32_t ctr, buf[4]; int have; uint32_t h16; int nh16; } prng_t;
 static uint32_t p_u32(prng_t* r) {
   if (!r->have) {
     uint32_t c[4] = {(uint32_t)r->env_id, (uint32_t)(r->env_id >> 32), r->ctr, 0u};
@@ -20,6 +20,13 @@ static uint32_t p_u32(prng_t* r) {
   return r->buf[4 - r->have--];
 }
 static int p_below(prng_t* r, int n) { return (int)(((uint64_t)p_u32(r) * (uint32_t)n) >> 32); }
+/* the step's small draws (an action out of 5, a Fisher-Yates index) take 16 bits each: low half of a Philox word first */
+static int p_below16(prng_t* r, int n) {
+  if (!r->nh16) { r->h16 = p_u32(r); r->nh16 = 2; }
+  uint32_t v = r->h16 & 0xFFFFu;
+  r->h16 >>= 16; r->nh16--;
+  return (int)((v * (uint32_t)n) >> 16);
+}
 
 /* CtfActions / MazeActions deltas (agent.py:54-67; ctf.py:1189-1199; maze.py:276-285) */
 static const int ADX[5] = {0, 0, -1, 0, 1}, ADY[5] = {0, -1, 0, 1, 0};
@@ -200,12 +207,12 @@ int oc_ctf_step(const oc_map_cfg* c, int64_t N, oc_map_state* st, const int8_t* 
     int act[OC_MAX_CTF_AGENTS], order[OC_MAX_CTF_AGENTS];
     for (int i = 0; i < nb; ++i) act[i] = blue_actions[e * nb + i];
     for (int k = 0; k < nr; ++k) /* RwPolicy.act for EVERY red agent, defeated or not (:1297-1301) */
-      act[nb + k] = (rng->mode == 0 || rng->red_actions) ? rng->red_actions[e * nr + k] : p_below(&r, 5); /* mode 1 + red_actions: an external enemy policy (enemy_policies, ctf.py:666), no draw */
+      act[nb + k] = (rng->mode == 0 || rng->red_actions) ? rng->red_actions[e * nr + k] : p_below16(&r, 5); /* mode 1 + red_actions: an external enemy policy (enemy_policies, ctf.py:666), no draw */
     if (c->variant_1v1) { order[0] = 0; order[1] = 1; } /* Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510) */
     else if (rng->mode == 0) for (int i = 0; i < n; ++i) order[i] = rng->order[e * n + i];
     else { /* np_random.shuffle stand-in: Fisher-Yates */
       for (int i = 0; i < n; ++i) order[i] = i;
-      for (int i = n - 1; i > 0; --i) { int j = p_below(&r, i + 1), t = order[i]; order[i] = order[j]; order[j] = t; }
+      for (int i = n - 1; i > 0; --i) { int j = p_below16(&r, i + 1), t = order[i]; order[i] = order[j]; order[j] = t; }
     }
     for (int k = 0; k < n; ++k) { /* _move_agents :1240-1251 */
       const int i = order[k];
