@@ -26,6 +26,12 @@ def main():
         e = mg.make_ctf_vec(n, golden("ctf_2v2", "field_map"))
         a = torch.randint(0, 5, (n, 2), device=dev, dtype=torch.int8)
         f = lambda: e.step(a)  # noqa: E731
+    elif fam == "ctf8":             # 8v8: the general step body (run-time team sizes)
+        n = n or (1 << 18)
+        e = mg.make_ctf_vec(n, golden("ctf_2v2", "field_map"), num_blue_agents=8, num_red_agents=8)
+        acts = [torch.randint(0, 5, (n, 8), device=dev, dtype=torch.int8) for _ in range(8)]
+        it = iter(range(10 ** 9))
+        f = lambda: e.step(acts[next(it) % 8])  # noqa: E731
     elif fam == "ctf_policy":      # scripted opponents decided on the device: ctf_policy_kernel ahead of every step
         from gym_multigrid_b200.policy.ctf.heuristic import FightPolicy, PatrolFightPolicy
         n = n or (1 << 20)
