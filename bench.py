@@ -528,7 +528,7 @@ def run_ours(args):
             "launch": f"CUDA graphs of up to {CHUNK} launches of the fused step+encode kernel (one launch = one env batch of {n} envs), "
                       f"the {B} independent batches forked over {S} streams; value = median of {R} timed regions of exactly {K} launches",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "collect_step_kernel",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "collect_rollout_kernel (warp-tile kernel, T = 1: mg_step)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "avg_launch_us": launch_s * 1e6,
                          "traffic_frac": (ncu_traffic() / launch_s / 1e9 / peak) if (ncu_traffic() and n == 65536) else None,

@@ -38,6 +38,7 @@ def golden(stem, key):
 def graph_time(fns, reps, streams=1):
     """us per call of the callables in `fns`, captured once into a CUDA graph (forked over `streams` streams)."""
     dev = torch.device("cuda:0")
+    torch.cuda.synchronize(dev)      # resets / setup ran on the default stream; the streams below are non-blocking
     main = torch.cuda.Stream(device=dev)
     side = [torch.cuda.Stream(device=dev) for _ in range(streams - 1)]
     with torch.cuda.stream(main):
@@ -66,6 +67,18 @@ def graph_time(fns, reps, streams=1):
     return e0.elapsed_time(e1) * 1e3 / (reps * len(fns))
 
 
+RING = 8
+
+
+def ring_steps(envs, draw):
+    """Callables for one CUDA graph: launch g steps env batch g % B with ring slot (g // B) % RING of `draw(b)`-shaped fresh
+    actions - every step of every batch gets its own independently drawn action tensor (a constant tensor parks the agents
+    against a wall after a few steps, which hides most of the dynamics: pickups, battles, moving fire fighters)."""
+    rings = [[draw(b) for _ in range(RING)] for b in range(len(envs))]
+    B = len(envs)
+    return [lambda e=envs[g % B], a=rings[g % B][(g // B) % RING]: e.step(a) for g in range(B * RING)]
+
+
 def report(name, n, us, bytes_per_env, **extra):
     gbs = n * bytes_per_env / us / 1e3
     print(json.dumps({"kernel": name, "num_envs": n, "us_per_launch": round(us, 3), "algorithmic_bytes_per_env": bytes_per_env,
@@ -85,10 +98,10 @@ def bench_ctf(args):
         bpe = 100 + 2 * (4 * (nb + nr) + 16) + nb + 10          # obs u8 + state r/w + actions + reward/flags
         B = batches_for(bpe, n)
         envs = [mg.make_ctf_vec(n, fm, num_blue_agents=nb, num_red_agents=nr, seed=b, env_id_base=b * n) for b in range(B)]
-        acts = [torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8) for _ in range(B)]
         for e in envs:
             e.reset()
-        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        torch.cuda.synchronize()
+        us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
         report(f"map_kernel<ctf> {nb}v{nr} 10x10 map obs u8", n, us, bpe, batches=B)
         for e in envs:
             e.close()
@@ -108,10 +121,10 @@ def bench_ctf(args):
     e.close()
     n = 65536
     envs = [mg.make_ctf_vec(n, fm, reference_dtypes=True, seed=b, env_id_base=b * n) for b in range(8)]
-    acts = [torch.randint(0, 5, (n, 2), device="cuda:0", dtype=torch.int8) for _ in range(8)]
     for e in envs:
         e.reset()
-    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    torch.cuda.synchronize()
+    us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 5, (n, 2), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
     report("map_kernel<ctf> 2v2 10x10 map obs int64 (reference dtype)", n, us, 800 + 2 * 32 + 12, batches=8)
     for e in envs:
         e.close()
@@ -127,11 +140,11 @@ def bench_ctf_policy(args):
     bpe_pol = 4 * (nb + nr) + 16 + nr                        # agents row + header read, red actions written
     B = batches_for(bpe_step, n)
     envs = [mg.make_ctf_vec(n, fm, num_blue_agents=nb, num_red_agents=nr, seed=b, env_id_base=b * n) for b in range(B)]
-    acts = [torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8) for _ in range(B)]
     for e in envs:
         e.set_enemy_policies([FightPolicy(fmf), PatrolFightPolicy(fmf)], device=True)
         e.reset()
-    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    torch.cuda.synchronize()
+    us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
     report("ctf_policy_kernel + map_kernel<ctf> 2v2 (fight, patrol_fight reds on device)", n, us, bpe_step + bpe_pol, batches=B)
     import ctypes as C
     ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
@@ -148,10 +161,11 @@ def bench_maze(args):
         bpe = 4096 * elem + 2 * (4 + 16) + 1 + 10
         B = batches_for(bpe, n)
         envs = [mg.make_maze_vec(n, fm, seed=b, env_id_base=b * n, reference_dtypes=ref) for b in range(B)]
-        acts = [torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8) for _ in range(B)]
+        draw = lambda b: torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8)  # noqa: E731
         for e in envs:
             e.reset()
-        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        torch.cuda.synchronize()
+        us = graph_time(ring_steps(envs, draw), max(2, args.reps // RING))
         report(f"map_kernel<maze> 64x64 full-map obs {'float64 (reference dtype)' if ref else 'u8'}", n, us, bpe, batches=B)
         if not ref:
             outs = [torch.empty((n, 1, 7, 7, 3), dtype=torch.uint8, device="cuda:0") for _ in range(B)]
@@ -159,7 +173,7 @@ def bench_maze(args):
             report("view_kernel maze 64x64 V=7 partial obs", n, us, 147 + 4, batches=B)
             for e in envs:
                 e.set_partial_obs(7)
-            us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+            us = graph_time(ring_steps(envs, draw), max(2, args.reps // RING))
             report("map_kernel<maze> 64x64 fused step + V=7 partial obs (config 4)", n, us, 147 + 2 * (4 + 16) + 1 + 10, batches=B)
         for e in envs:
             e.close()
@@ -171,11 +185,11 @@ def bench_maze_partial(args):
     for n in (131072, 524288, 1 << 20):
         B = 3 if n >= 524288 else 8
         envs = [mg.make_maze_vec(n, fm, seed=b, env_id_base=b * n) for b in range(B)]
-        acts = [torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8) for _ in range(B)]
         for e in envs:
             e.set_partial_obs(7)
             e.reset()
-        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+        torch.cuda.synchronize()
+        us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 5, (n,), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
         report("map_kernel<maze> 64x64 fused step + V=7 partial obs (config 4)", n, us, 147 + 2 * (4 + 16) + 1 + 10, batches=B)
         for e in envs:
             e.close()
@@ -208,13 +222,14 @@ def bench_wildfire(args):
         bpe = A + 2 * (cells + 4 * A + 16) + 3 * cells + 8 * A + 2
         B = batches_for(bpe, n, lo=2, hi=8)
         envs = [mg.make_wildfire_vec(n, size=size, num_agents=A, seed=b, env_id_base=b * n) for b in range(B)]
-        acts = [torch.randint(0, 5, (n, A), device="cuda:0", dtype=torch.int8) for _ in range(B)]
         for e in envs:
             e.reset()
-        for _ in range(10):          # let the fires develop: the stencil skips quiet groups
-            for e, a in zip(envs, acts):
-                e.step(a)
-        us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], max(4, args.reps // 4))
+        torch.cuda.synchronize()
+        steps = ring_steps(envs, lambda b: torch.randint(0, 5, (n, A), device="cuda:0", dtype=torch.int8))
+        for _ in range(4):           # let the fires develop: the stencil skips quiet groups
+            for f in steps:
+                f()
+        us = graph_time(steps, max(2, args.reps // (4 * RING)))
         report(f"wildfire_kernel {size}x{size} A={A}", n, us, bpe, batches=B)
         for e in envs:
             e.close()
@@ -249,8 +264,8 @@ def bench_generic(args):
         e.set_layout(g["init_obs"][idx, 0], g["init_pos"][idx])
         e.reset()
         envs.append(e)
-    acts = [torch.randint(0, 4, (n, A), device="cuda:0", dtype=torch.int8) for _ in range(B)]
-    us = graph_time([lambda e=e, a=a: e.step(a) for e, a in zip(envs, acts)], args.reps)
+    torch.cuda.synchronize()
+    us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 4, (n, A), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
     report("generic_kernel 12x12 A=5 encode_dim 6 obs per agent", n, us, bpe, batches=B)
     for e in envs:
         e.close()
@@ -296,7 +311,7 @@ def bench_collect_streams(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="ctf,maze,view,wildfire,generic,collect_streams")
+    ap.add_argument("--which", default="ctf,maze,view,wildfire,generic")
     ap.add_argument("--reps", type=int, default=40)
     args = ap.parse_args()
     for w in args.which.split(","):
