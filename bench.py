@@ -404,7 +404,10 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (numpy in, numpy out)
     e2e_steps = args.e2e_steps
-    EB = min(B, 2)   # two env batches in flight
+    # env batches in flight: two on one or two GPUs (the decode of one overlaps the step of the other); ONE from four GPUs up - eight
+    # ranks share the host's memory system, where every step sweeps its batch's 19.6 MB observation mirror: a second batch in flight per
+    # rank doubles the working set (8 x 39 MB) and measured slower (4.2e8 against 6.3e8 env-steps/s on 8 GPUs, tools/dev/e2e_multi.py)
+    EB = min(B, 2 if world <= 2 else 1)
     host_rings = [rings[b].cpu().numpy() for b in range(EB)]
     cells = envs[0].width * envs[0].height
 

@@ -21,7 +21,7 @@
 namespace mg {
 
 // ------------------------------------------------------------------------------------------------ thread pool
-// Persistent workers; a job is a function of (worker index, worker count).  Workers spin briefly for the next job (steps
+// Persistent workers; a job is a function of (worker index, worker count).  Workers spin ~1 ms for the next job (steps
 // arrive back to back in an RL loop) and then sleep on a condition variable, so an idle env costs no CPU.
 class HostPool {
  public:

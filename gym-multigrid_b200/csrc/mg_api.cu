@@ -1180,7 +1180,8 @@ extern "C" int mg_set_host_transport(mg_env* env, int mode, int host_threads) {
   if (env->pend.active) return fail(env, "mg_set_host_transport: a host step is still in flight (mg_step_host_wait first)");
   cudaError_t ce;
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
-  if (mode != MG_TRANSPORT_FULL && transport_alloc(env)) return -1;
+  // (the staging buffers - 220 bytes per env, half of it page-locked - are allocated by the first host step, not here: most handles
+  //  are only ever stepped with device tensors)
   env->host_threads = host_threads > 0 ? host_threads : mg::host_default_threads();
   if (mode != MG_TRANSPORT_FULL) mg::host_pool_ensure(env->host_threads);
   env->transport = mode;
@@ -1220,6 +1221,7 @@ extern "C" int mg_delta_record_bytes(int cells, int num_agents) { return mg::del
 // H2D actions -> step -> D2H of the step's compact results into the handle's page-locked staging; decoded by finish_host_step
 static int step_host_compact(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
   if (!aligned16(state)) return fail(env, "mg_step_host: state buffer must be 16-byte aligned");
+  if (transport_alloc(env)) return -1;
   const size_t N = (size_t)env->cfg.num_envs, A = (size_t)env->act_cols, cells = (size_t)env->base.cells;
   const size_t R = (size_t)mg::delta_record_bytes(env->base.cells, env->base.A);
   cudaError_t ce;
