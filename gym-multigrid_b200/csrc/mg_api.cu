@@ -83,6 +83,7 @@ struct mg_env {
   long long* d_flat_tmpl;                  // ... uploaded on first use
   std::vector<std::pair<int, uint8_t*>> atlases;    // render: (tile_size, device atlas) built on first use, freed by mg_destroy
   uint8_t* d_policy_tables;        // CtF: tables of the scripted opponents (mg_set_red_policies), or null
+  const uint16_t* pol_tr_patrol; const uint8_t* pol_tr_follow; const int8_t* pol_tr_action;   // mg_set_policy_trace (validation), or null
   uint4* d_view_table;             // Maze partial-observation mode: the memoised views of all S*S*4 agent states, or null
   mg::PolicyParams pbase;
   const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
@@ -640,6 +641,15 @@ extern "C" int mg_set_red_policies(mg_env* env, const mg_red_policies* t) {
   return 0;
 }
 
+extern "C" int mg_set_policy_trace(mg_env* env, const uint16_t* patrol_target_dev, const uint8_t* follow_dev, const int8_t* action_dev) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_policy_trace: CtF family only");
+  if ((follow_dev == nullptr) != (action_dev == nullptr) || (follow_dev == nullptr) != (patrol_target_dev == nullptr))
+    return fail(env, "mg_set_policy_trace: pass all three arrays, or three NULLs to return to Philox draws");
+  env->pol_tr_patrol = patrol_target_dev; env->pol_tr_follow = follow_dev; env->pol_tr_action = action_dev;
+  return 0;
+}
+
 extern "C" int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream) {
   if (!env || !state || !red_actions_dev) return fail(env, "mg_red_policy_actions: null argument");
   if (env->family != MG_FAMILY_CTF) return fail(env, "mg_red_policy_actions: CtF family only");
@@ -653,6 +663,7 @@ extern "C" int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red
   p.hdr = reinterpret_cast<const int4*>(base + env->plane_off[MG_MAP_PLANE_HDR]);
   p.seed = env->mbase.seed;      // mg_set_seed may have re-keyed the handle since the tables were set
   p.out = red_actions_dev;
+  p.tr_patrol = env->pol_tr_patrol; p.tr_follow = env->pol_tr_follow; p.tr_action = env->pol_tr_action;
   if ((ce = mg::launch_ctf_policy(p, static_cast<cudaStream_t>(stream))) != cudaSuccess) return cuda_fail(env, "ctf_policy_kernel", ce);
   env->launches += 1;
   return 0;

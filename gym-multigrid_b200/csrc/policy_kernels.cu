@@ -52,11 +52,13 @@ __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
     const int code = __ldg(p.field_map + (w & 255u) * S + ((w >> 8) & 255u));
     intruder |= code == 1 || code == 5;   // observation["red_territory"] = red territory cells + the red flag (ctf.py:765-769)
   }
+  const bool trace = p.tr_follow != nullptr;
   for (int k = 0; k < p.nr; ++k) {
     const int kind = p.kind[k];
+    const long long ek = e * p.nr + k;
     int a;
     if (kind == MG_POLICY_RW) {
-      a = r.below(5);
+      a = trace ? p.tr_action[ek] : r.below(5);
     } else {
       const uint32_t me = row[p.nb + k];
       const int x = me & 255u, y = (me >> 8) & 255u, cell = x * S + y;
@@ -72,15 +74,19 @@ __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
           if (d2 < best) { best = d2; target = bx * S + by; }
         }
       } else if (__ldg(p.on_border + cell)) {
-        target = __ldg(p.along + r.below(p.n_along));
+        target = trace ? (int)p.tr_patrol[ek] : (int)__ldg(p.along + r.below(p.n_along));
       } else {
         target = __ldg(p.patrol_goal + cell);
       }
       const int mv = __ldg(p.first_move + (size_t)cell * p.cells + target);
-      const bool follow = (unsigned long long)r.u32() < p.thr[k];
-      a = follow ? mv : r.below(5);
+      if (trace) {
+        a = p.tr_follow[ek] ? mv : p.tr_action[ek];
+      } else {
+        const bool follow = (unsigned long long)r.u32() < p.thr[k];
+        a = follow ? mv : r.below(5);
+      }
     }
-    p.out[e * p.nr + k] = (int8_t)a;
+    p.out[ek] = (int8_t)a;
   }
 }
 

@@ -19,6 +19,10 @@ struct PolicyParams {
   int kind[16];                 // per red agent: MG_POLICY_*
   unsigned long long thr[16];   // follow the route iff u32 < thr = ceil(randomness * 2^32)
   int8_t* out;                  // [N][nr]
+  // validation mode (mg_set_policy_trace): the reference generator's recorded outputs per (env, red agent) instead of Philox draws
+  const uint16_t* tr_patrol;    // [N][nr] cell drawn by PatrolPolicy on the border (np_random.choice, heuristic.py:334); unused entries ignored
+  const uint8_t* tr_follow;     // [N][nr] 1 = follow the route (np_random.choice([True, False], p=...), heuristic.py:150-151)
+  const int8_t* tr_action;      // [N][nr] the uniform action (np_random.integers, :72 / :175) where one was drawn
 };
 
 }  // namespace mg

@@ -476,6 +476,22 @@ class CtfVecEnv(_MapVecEnv):
         self._red_buf = self.set_red_actions(self._red_host)
         return pols
 
+    def set_policy_trace(self, patrol_target=None, follow=None, action=None):
+        """Validation mode of the device-decided opponents (mg_set_policy_trace): recorded outputs of the reference's generator
+        per (env, red agent) - the border cell PatrolPolicy drew (cell index x * size + y), follow-the-route booleans, uniform
+        actions - replace the Philox draws of `mg_red_policy_actions`.  No arguments = back to Philox."""
+        if patrol_target is None and follow is None and action is None:
+            self._check(self._lib.mg_set_policy_trace(self._h, None, None, None))
+            self._policy_trace = None
+            return None
+        shape = (self.num_envs, self.num_red)
+        t = (torch.as_tensor(np.ascontiguousarray(patrol_target, dtype=np.uint16).view(np.int16), device=self.device).reshape(shape).contiguous(),   # same 16 bits
+             torch.as_tensor(np.asarray(follow), device=self.device).to(torch.uint8).reshape(shape).contiguous(),
+             torch.as_tensor(np.asarray(action), device=self.device).to(torch.int8).reshape(shape).contiguous())
+        self._check(self._lib.mg_set_policy_trace(self._h, *(_ptr(x) for x in t)))
+        self._policy_trace = t
+        return t
+
     def _decide_red_actions(self):
         d = {k: v.cpu().numpy() for k, v in self.positional_obs().items()}
         pos = d["red_agent"].reshape(self.num_envs, self.num_red, 2)

@@ -324,6 +324,12 @@ int mg_set_red_policies(mg_env* env, const mg_red_policies* tables);
  * `stay` (the reference raises there, heuristic.py:172).  first_move: [cells][cells] start-major.  No device involved. */
 int mg_astar_first_moves(const uint8_t* blocked, int32_t rows, int32_t cols, uint8_t* first_move);
 int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream);
+/* Validation mode of mg_red_policy_actions: replay the outputs the reference's generator produced instead of drawing from Philox -
+ * per (env, red agent), all [N][num_red] on the device: the cell PatrolPolicy drew on the border (np_random.choice over the border
+ * cells with a border neighbour, heuristic.py:323-334; cell index x * size + y), whether the route is followed
+ * (np_random.choice([True, False], p=[randomness, 1 - randomness]), :150-151) and the uniform action (np_random.integers(0, 5), :72,
+ * :175).  Entries a decision does not draw are ignored.  Three NULLs = back to Philox. */
+int mg_set_policy_trace(mg_env* env, const uint16_t* patrol_target_dev, const uint8_t* follow_dev, const int8_t* action_dev);
 
 /* CtF handles: `_get_obs()` with observation_option="flattened" (ctf.py:1084-1104; what the reference's RL script trains on,
  * scripts/main_mvn_ctf_rl.py:15-21) for every env: out int64 [N][L] on the device, L = mg_ctf_flat_len() =

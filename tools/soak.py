@@ -88,6 +88,7 @@ def soak_collect(rng, stats):
         b += same(obs, oobs, f"host step {t} obs ({tr})", cfg) + same(rew, orew, f"host rewards ({tr})", cfg)
         b += same(term, oterm, f"host terminated ({tr})", cfg) + same(trunc, otrunc, f"host truncated ({tr})", cfg)
     steps += T
+    stats["collect_rollout_steps"] += n * T; stats[f"collect_host_{tr}_configs"] += 1
     b += same(_np(env.grid), o.grid, "collect grid", cfg) + same(_np(env.pickups).reshape(n, -1), o.info, "collect counters", cfg)
     dirs = rng.integers(0, 4, size=(n, A)).astype(np.uint8)
     V, st = int(rng.choice([3, 4, 5, 6, 7, 9])), bool(rng.integers(0, 2))
@@ -150,6 +151,7 @@ def soak_ctf(rng, stats):
         if env._device_policies:
             tables = env._policy_tables
             cfg["device_policies"] = [c.__name__ for c in picks]
+            stats["ctf_device_policy_configs"] += 1
     for t in range(steps):
         act = rng.integers(0, 5, size=(n, nb)).astype(np.int8)
         ra = None
@@ -212,8 +214,11 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    stats = {k: 0 for k in ("collect_configs", "collect_env_steps", "collect_rejected", "ctf_configs", "ctf_env_steps", "maze_configs",
-                            "maze_env_steps", "bytes_compared")}
+    import collections
+    stats = collections.defaultdict(int)
+    for k in ("collect_configs", "collect_env_steps", "collect_rejected", "ctf_configs", "ctf_env_steps", "maze_configs", "maze_env_steps",
+              "bytes_compared", "ctf_device_policy_configs", "collect_rollout_steps"):
+        stats[k] = 0
     t0 = time.time()
     fams = [soak_collect, soak_ctf, soak_maze]
     i = 0
@@ -222,7 +227,7 @@ def main():
         i += 1
     stats.update(seconds=round(time.time() - t0, 1), seed=args.seed, mismatches=0,
                  gpu=torch.cuda.get_device_name(0), what="CUDA (C ABI) vs CPU oracle, bit-exact, random configurations")
-    print(json.dumps(stats))
+    print(json.dumps(dict(stats)))
 
 
 if __name__ == "__main__":
