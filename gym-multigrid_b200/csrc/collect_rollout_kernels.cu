@@ -41,29 +41,39 @@ struct WarpSmem {
 
 __host__ __device__ inline size_t up16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-__host__ __device__ inline size_t warp_smem_bytes(int cells, int A, int tile) {
+// Two-agent handles use the register path: the staging arrays of the generic path (rewards, actions, flags, order) are not carved,
+// and the delta-record buffer only when the launch writes records (host transport).  That is what lets 8 two-warp CTAs - 16 tiles -
+// share an SM at 32 envs per warp on a 10x10 grid (13.5 KB per warp) instead of 7.
+__host__ __device__ inline size_t warp_smem_bytes(int cells, int A, int tile, bool with_delta) {
   const size_t E = tile;
-  return up16(E * cells) + 3 * E * cells + E * 16 + up16(E * A * 2) + 2 * up16(E * A) + 2 * E * A * 8 + 4 * E + up16(E * A) +
-         up16(E * 3 * A * 2) + up16(E * delta_record_bytes(cells, A)) + 32;
+  const bool lean = A == 2;
+  size_t b = up16(E * cells) + 3 * E * cells + E * 16 + up16(E * A * 2) + up16(E * 3 * A * 2) + 32;
+  if (!lean) b += 2 * up16(E * A) + 2 * E * A * 8 + 4 * E + up16(E * A);
+  if (!lean || with_delta) b += up16(E * delta_record_bytes(cells, A));
+  return b;
 }
 
-__device__ __forceinline__ WarpSmem carve_warp(uint8_t* b, int cells, int A, int tile) {
+__device__ __forceinline__ WarpSmem carve_warp(uint8_t* b, int cells, int A, int tile, bool with_delta) {
   const size_t E = tile;
+  const bool lean = A == 2;
   WarpSmem s;
   s.grid = b; b += up16(E * cells);
   s.obs = b; b += 3 * E * cells;
   s.hdr = reinterpret_cast<int4*>(b); b += E * 16;
-  s.rew[0] = reinterpret_cast<double*>(b); b += E * A * 8;
-  s.rew[1] = reinterpret_cast<double*>(b); b += E * A * 8;
   s.pos = b; b += up16(E * A * 2);
-  s.act[0] = reinterpret_cast<int8_t*>(b); b += up16(E * A);
-  s.act[1] = reinterpret_cast<int8_t*>(b); b += up16(E * A);
-  s.term[0] = b; b += E; s.term[1] = b; b += E;
-  s.trunc[0] = b; b += E; s.trunc[1] = b; b += E;
-  s.ord = b; b += up16(E * A);
   s.chg = reinterpret_cast<uint16_t*>(b); b += up16(E * 3 * A * 2);
-  s.delta = b; b += up16(E * delta_record_bytes(cells, A));
-  s.bar = reinterpret_cast<uint64_t*>(b);
+  s.bar = reinterpret_cast<uint64_t*>(b); b += 32;
+  s.rew[0] = s.rew[1] = nullptr; s.act[0] = s.act[1] = nullptr; s.term[0] = s.term[1] = s.trunc[0] = s.trunc[1] = nullptr; s.ord = nullptr;
+  if (!lean) {
+    s.rew[0] = reinterpret_cast<double*>(b); b += E * A * 8;
+    s.rew[1] = reinterpret_cast<double*>(b); b += E * A * 8;
+    s.act[0] = reinterpret_cast<int8_t*>(b); b += up16(E * A);
+    s.act[1] = reinterpret_cast<int8_t*>(b); b += up16(E * A);
+    s.term[0] = b; b += E; s.term[1] = b; b += E;
+    s.trunc[0] = b; b += E; s.trunc[1] = b; b += E;
+    s.ord = b; b += up16(E * A);
+  }
+  s.delta = (!lean || with_delta) ? b : nullptr;
   return s;
 }
 
@@ -96,7 +106,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* gdst, const uint8_t* src, uin
 }
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kRollThreads = 64;   // two independent warps per CTA; 7 CTAs / SM = 14 warps (register- and, at 32 envs per warp, shared-memory-bound)
+constexpr int kRollThreads = 64;   // two independent warps per CTA; 8 CTAs / SM = 16 warps: exactly the register file at 128 registers per thread
 
 // profiling (mg_debug_set_timeline): cycles a warp spent per phase, summed over the T steps of a tile.  Compiled in only with
 // -DMG_ROLLOUT_CLOCK (tools/dev/rollout_timeline.py rebuilds the library with it): even a disabled clock costs 4 % of the instructions.
@@ -388,10 +398,11 @@ __device__ __forceinline__ void rollout_tile(const CollectParams& p, const WarpS
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kRollThreads, 7) collect_rollout_kernel(const __grid_constant__ CollectParams p) {
+__global__ void __launch_bounds__(kRollThreads, 8) collect_rollout_kernel(const __grid_constant__ CollectParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const WarpSmem s = carve_warp(smem_raw + (size_t)wib * warp_smem_bytes(p.cells, p.A, p.roll_tile), p.cells, p.A, p.roll_tile);
+  const bool with_delta = p.delta != nullptr;
+  const WarpSmem s = carve_warp(smem_raw + (size_t)wib * warp_smem_bytes(p.cells, p.A, p.roll_tile, with_delta), p.cells, p.A, p.roll_tile, with_delta);
   const long long ntiles = (p.N + p.roll_tile - 1) / p.roll_tile;
   const long long gw = (long long)blockIdx.x * wpc + wib, nw = (long long)gridDim.x * wpc;
 
@@ -410,10 +421,10 @@ __global__ void __launch_bounds__(kRollThreads, 7) collect_rollout_kernel(const 
 // ------------------------------------------------------------------------------ launcher
 constexpr int kRollWarps = kRollThreads / 32;
 
-size_t rollout_smem_bytes(int cells, int A, int tile) { return (size_t)kRollWarps * warp_smem_bytes(cells, A, tile); }
+size_t rollout_smem_bytes(int cells, int A, int tile, bool with_delta) { return (size_t)kRollWarps * warp_smem_bytes(cells, A, tile, with_delta); }
 
 cudaError_t configure_rollout_kernels(int cells, int A) {
-  const size_t smem = rollout_smem_bytes(cells, A, kRollTileMax);
+  const size_t smem = rollout_smem_bytes(cells, A, kRollTileMax, true);
   cudaError_t r;
   if ((r = raise_smem_limit((const void*)collect_rollout_kernel<0>, smem)) != cudaSuccess) return r;
   return raise_smem_limit((const void*)collect_rollout_kernel<1>, smem);
@@ -440,14 +451,15 @@ cudaError_t launch_collect_rollout(const CollectParams& p_in, int num_sms, cudaS
   int per_sm = 0;
   cudaError_t ce;
   // occupancy at the largest tile: 7 CTAs / SM for a 10x10 grid (the smaller tiles use less shared memory, registers then bound it)
-  const size_t smem_max = rollout_smem_bytes(p.cells, p.A, kRollTileMax);
+  const bool with_delta = p.delta != nullptr;
+  const size_t smem_max = rollout_smem_bytes(p.cells, p.A, kRollTileMax, with_delta);
   if (p.rng_mode == 0) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collect_rollout_kernel<0>, kRollThreads, smem_max);
   else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, collect_rollout_kernel<1>, kRollThreads, smem_max);
   if (ce != cudaSuccess) return ce;
   if (per_sm < 1) per_sm = 1;
   const long long resident = (long long)num_sms * per_sm;
   p.roll_tile = pick_roll_tile(p, resident * kRollWarps);
-  const size_t smem = rollout_smem_bytes(p.cells, p.A, p.roll_tile);
+  const size_t smem = rollout_smem_bytes(p.cells, p.A, p.roll_tile, with_delta);
   const long long ntiles = (p.N + p.roll_tile - 1) / p.roll_tile;
   long long blocks = (ntiles + kRollWarps - 1) / kRollWarps;
   if (blocks > resident) blocks = resident;      // persistent: every warp walks its tiles with stride = warps in the grid

@@ -24,7 +24,7 @@ cudaError_t launch_collect_reset(int v, const CollectParams& p, cudaStream_t st)
 cudaError_t launch_encode3(int v, const uint8_t* grid, uint8_t* obs, long long N, int cells, int obs_bulk_ok, cudaStream_t st);
 cudaError_t launch_collect_rollout(const CollectParams& p, int num_sms, cudaStream_t st);
 cudaError_t configure_rollout_kernels(int cells, int A);
-size_t rollout_smem_bytes(int cells, int A, int tile);
+size_t rollout_smem_bytes(int cells, int A, int tile, bool with_delta);
 int num_tile_variants();
 int tile_envs(int v);
 cudaError_t configure_kernels(int v, int cells, int A);
@@ -966,7 +966,7 @@ extern "C" int mg_reset(mg_env* env, void* state, const uint8_t* mask, uint8_t* 
 // the warp-tile kernel needs 2 warps' worth of shared memory per CTA: opt in once per handle; != 0 if the grid is too large for it
 static int rollout_prepare(mg_env* env) {
   if (env->rollout_ready) return 0;
-  if (mg::rollout_smem_bytes(env->base.cells, env->base.A, 32) > env->smem_optin) return -1;
+  if (mg::rollout_smem_bytes(env->base.cells, env->base.A, 32, true) > env->smem_optin) return -1;
   if (mg::configure_rollout_kernels(env->base.cells, env->base.A) != cudaSuccess) return -1;
   env->rollout_ready = true;
   return 0;
