@@ -228,8 +228,9 @@ int64_t mg_launch_count(const mg_env* env);
 /* ===================================================================================== Maze and CtF
  * Static text-map families: MazeSingleAgentEnv (envs/maze.py:26-377) and CtFMvNEnv (envs/ctf.py:657-1433).
  * The map (utils/map.py:22-39, field_map = np.loadtxt(path).T, indexed [x][y]) is shared by all envs and
- * lives in handle-owned device tables; per-env state is only the agents.  Square maps only (the
- * reference mixes width and height: maze.py:68-70 vs :184-186, ctf.py:745-747). */
+ * lives in handle-owned device tables; per-env state is only the agents.  Square maps only: the
+ * reference mixes width and height (maze.py:68-70 vs :184-186, ctf.py:745-747) and raises an AssertionError
+ * from Grid.set on any non-square map, so there is no non-square behaviour to reproduce. */
 #define MG_MAX_MAP_AGENTS 16
 
 enum { MG_OBS_U8 = 0,        /* "map" codes as uint8 (compact default) */

@@ -229,3 +229,42 @@ def test_constants_module():
         a, b = getattr(RW, n), getattr(mg, n)
         assert dict(a.OBJECT_TO_IDX) == dict(b.OBJECT_TO_IDX) and dict(a.COLOR_TO_IDX) == dict(b.COLOR_TO_IDX)
         assert dict(a.IDX_TO_OBJECT) == dict(b.IDX_TO_OBJECT) and dict(a.IDX_TO_COLOR) == dict(b.IDX_TO_COLOR) and a.encode_dim == b.encode_dim
+
+
+def test_reference_raises_on_non_square_maps_too():
+    """`mg_create_map` refuses non-square maps.  So does the reference, by accident: it reads `height, width = field_map.shape`
+    (maze.py:68-70, ctf.py:745-747) and then addresses the grid as (x < width, y < height) with x running over shape[0]
+    (maze.py:184-186 -> Grid.set, grid.py:61-64), so any map with shape[0] != shape[1] trips the bounds assert while the grid
+    is built - in both orientations, for Maze and CtF.  Checked live where /root/reference exists."""
+    import tempfile
+
+    import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("needs /root/reference (build container only)")
+    rh.import_reference()
+    from gym_multigrid.envs.ctf import CtFMvNEnv
+    from gym_multigrid.envs.maze import MazeSingleAgentEnv
+    from gym_multigrid.policy.ctf.heuristic import RwPolicy
+
+    def build(m, cls, **kw):
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as tmp:
+            np.savetxt(tmp.name, m, fmt="%d")
+        try:
+            env = cls(tmp.name, **kw)
+            env.reset(seed=0)
+        finally:
+            os.unlink(tmp.name)
+
+    for shape in ((6, 9), (9, 6)):
+        m = np.zeros(shape, int)
+        m[1, 2], m[3, 3] = 2, 3
+        with pytest.raises(AssertionError):
+            build(m, MazeSingleAgentEnv)
+        c = np.zeros(shape, int)
+        c[:, shape[1] // 2:] = 1
+        c[1, 1], c[2, shape[1] - 2], c[3, 2] = 4, 5, 6
+        with pytest.raises(AssertionError):
+            build(c, CtFMvNEnv, num_blue_agents=2, num_red_agents=2, enemy_policies=RwPolicy())
+    sq = np.zeros((7, 7), int)
+    sq[1, 2], sq[3, 3] = 2, 3
+    build(sq, MazeSingleAgentEnv)        # the square control builds and resets
