@@ -650,7 +650,8 @@ def bench_families(args, dev, rank, world, timed_region_factory):
     for e in mz:
         e.set_partial_obs(7)
     run("maze64_partial7", mz, 5, (n,), 160, 147 + 2 * (4 + 16) + 1 + 10, n,
-        "BASELINE config 4: MazeSingleAgentEnv on a generated 64x64 map, fused step + V=7 partial-view observation (one launch), autoreset")
+        "BASELINE config 4: MazeSingleAgentEnv on a generated 64x64 map, fused step + V=7 partial-view observation (one launch), autoreset; "
+        "Maze + partial view is a composition the reference does not ship: cells outside the map show the filler (3, 7, 1), an extension (unpinned for that one code)")
     nw, A, size = args.wildfire_envs, 16, 64
     cells = size * size
     run("wildfire64_a16", [mg.make_wildfire_vec(nw, size=size, num_agents=A, seed=args.seed, env_id_base=base + (4 + b) * n, device=dev) for b in range(2)],

@@ -195,3 +195,27 @@ def test_cta_tile_kernel_host_transports(transport, cuda_device, monkeypatch):
             assert np.array_equal(_np(x), y), f"step {t}"
     assert host.status() == 0
     dev.close(); host.close()
+
+
+def test_grids_too_large_for_a_warp_slice_fall_back_to_the_cta_tile_kernel(cuda_device):
+    """40x40 grids: 32 envs x 4 x 1600 bytes per warp do not fit two warps' shared-memory slices, so `mg_step` launches the
+    CTA-tile kernel (16-env tiles) instead - same results as the oracle - and `mg_rollout` says so instead of launching."""
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    kw = dict(size=40, agents_index=[3, 5], balls_index=[0, 1, 2], balls_reward=[1, 1, 1], num_balls=[30], respawn=True, layout="even_dist", max_steps=20)
+    n = 300
+    env = CollectVecEnv(n, seed=4, **kw)
+    o = oc.CollectOracle(oc.make_collect_cfg(size=40, agents_index=[3, 5], balls_index=[0, 1, 2], balls_reward=[1, 1, 1], num_balls=30, respawn=True,
+                                             layout="even_dist", max_steps=20, time_limit=0), n)
+    r = oc.PhiloxRng(seed=4)
+    assert np.array_equal(_np(env.reset()[0]), o.reset(r))
+    rng = np.random.default_rng(2)
+    for t in range(45):
+        act = rng.integers(0, 4, size=(n, 2)).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        oobs, orew, oterm, otrunc = o.step(act, r, autoreset=True)
+        assert np.array_equal(_np(obs), oobs) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+    with pytest.raises(RuntimeError, match="too large"):
+        env.rollout(steps=4)
+    assert env.status() == 0
+    env.close()
