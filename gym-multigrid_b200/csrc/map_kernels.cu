@@ -494,15 +494,27 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
         if (V == 7) view_copy_store<7>(row, s_obs, tid);
         else if (V == 5) view_copy_store<5>(row, s_obs, tid);
         else view_copy_store<3>(row, s_obs, tid);
-      } else if (V == 7) {
-        view_geometry<7>(x, y, dir, p.pitch, x0, y0, sa, sb);
-        view_compute_store<false, 7>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
-      } else if (V == 5) {
-        view_geometry<5>(x, y, dir, p.pitch, x0, y0, sa, sb);
-        view_compute_store<false, 5>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
       } else {
-        view_geometry<3>(x, y, dir, p.pitch, x0, y0, sa, sb);
-        view_compute_store<false, 3>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, 0, 0, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+        // the view cells inside the map, over a and over b (everything else shows the filler and blocks sight)
+        auto masks = [&](int VV_, uint32_t& mA, uint32_t& mB) {
+          const bool a_is_x = dir & 1;
+          mA = a_is_x ? range_mask(x0, dir == 3 ? 1 : -1, p.S, VV_) : range_mask(y0, dir == 0 ? 1 : -1, p.S, VV_);
+          mB = a_is_x ? range_mask(y0, dir == 3 ? 1 : -1, p.S, VV_) : range_mask(x0, dir == 2 ? 1 : -1, p.S, VV_);
+        };
+        uint32_t mA, mB;
+        if (V == 7) {
+          view_geometry<7>(x, y, dir, p.pitch, x0, y0, sa, sb);
+          masks(7, mA, mB);
+          view_compute_store<false, 7>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, mA, mB, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+        } else if (V == 5) {
+          view_geometry<5>(x, y, dir, p.pitch, x0, y0, sa, sb);
+          masks(5, mA, mB);
+          view_compute_store<false, 5>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, mA, mB, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+        } else {
+          view_geometry<3>(x, y, dir, p.pitch, x0, y0, sa, sb);
+          masks(3, mA, mB);
+          view_compute_store<false, 3>(s_period + (x0 + p.pad) * p.pitch + (y0 + p.pad), sa, sb, mA, mB, p.view_oob, agent_cell, p.view_see_through != 0, s_obs, tid);
+        }
       }
     }
     fence_proxy_async_smem();

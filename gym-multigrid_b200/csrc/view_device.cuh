@@ -29,6 +29,7 @@ __device__ __forceinline__ void view_geometry(int x, int y, int dir, int pitch, 
 // provides guard bands / a padded map), visibility sweep, encode, and store the 3*V*V bytes at s_out + v * 3*V*V.
 //   COLLECT: cells outside the range masks mA (over a) / mB (over b) become `oob_code`; walls block sight.
 //   Maze (COLLECT = false): the source is pre-padded; view cell (V/2, V-1) shows `agent_cell`; only `oob_code` blocks sight.
+//   Both: mA / mB = the view cells (over a / over b) that lie inside the grid / map.
 template <bool COLLECT, int V>
 __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, int sb, uint32_t mA, uint32_t mB, uint32_t oob_code,
                                                    uint32_t agent_cell, bool see_through, uint8_t* s_out, int v) {
@@ -50,11 +51,13 @@ __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, i
         o |= (uint32_t)((c & 3u) == (uint32_t)T_WALL) << a;     // see_behind() is False only for Wall (object.py:174-179)
       } else {
         if (a == HS && b == V - 1) c = agent_cell;  // the agent stands at view cell (V/2, V-1)
-        o |= (uint32_t)(c == oob_code) << a;         // Maze: only the out-of-map filler blocks sight
       }
       pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
     }
-    opq[b] = o; msk[b] = 0;
+    // Maze: only the out-of-map filler blocks sight, and which view cells lie outside the map is geometry - the complement of the
+    // range masks - not something to find by comparing 49 cell values with the filler code
+    opq[b] = COLLECT ? o : (~rowv & FULL);
+    msk[b] = 0;
   }
   if (see_through) {
 #pragma unroll
@@ -95,7 +98,7 @@ __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, i
 #pragma unroll
   for (int k = 0; k < NPK; ++k) {
     uint32_t o0, o1, o2;
-    expand4(pk[k], o0, o1, o2);
+    expand4<COLLECT>(pk[k], o0, o1, o2);   // only Collect grids can hold a marked ball (bit 6 of a type-2 cell); Maze type 2 is the flag, state 0
     w[3 * k] = o0;
     if (3 * k + 1 < NW + 2) w[3 * k + 1] = o1;
     if (3 * k + 2 < NW + 2) w[3 * k + 2] = o2;

@@ -71,16 +71,12 @@ __global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_co
     const int dir = p.dirs ? (p.dirs[gv * p.dir_stride] & 3) : 3;
     int x0, y0, sa, sb;
     view_geometry<V>(x, y, dir, pitch, x0, y0, sa, sb);
-    uint32_t mA = (1u << V) - 1u, mB = mA;
+    const bool a_is_x = dir & 1;  // dirs 1, 3: a walks along x, b along y
+    const uint32_t mA = a_is_x ? range_mask(x0, dir == 3 ? 1 : -1, p.W, V) : range_mask(y0, dir == 0 ? 1 : -1, p.H, V);
+    const uint32_t mB = a_is_x ? range_mask(y0, dir == 3 ? 1 : -1, p.H, V) : range_mask(x0, dir == 2 ? 1 : -1, p.W, V);
     const uint8_t* src;
-    if (FAMILY == MG_FAMILY_COLLECT) {
-      src = s_src + guard + (v / A) * p.cells + x0 * pitch + y0;
-      const bool a_is_x = dir & 1;  // dirs 1, 3: a walks along x, b along y
-      mA = a_is_x ? range_mask(x0, dir == 3 ? 1 : -1, p.W, V) : range_mask(y0, dir == 0 ? 1 : -1, p.H, V);
-      mB = a_is_x ? range_mask(y0, dir == 3 ? 1 : -1, p.H, V) : range_mask(x0, dir == 2 ? 1 : -1, p.W, V);
-    } else {
-      src = s_src + (x0 + p.pad) * pitch + (y0 + p.pad);
-    }
+    if (FAMILY == MG_FAMILY_COLLECT) src = s_src + guard + (v / A) * p.cells + x0 * pitch + y0;
+    else src = s_src + (x0 + p.pad) * pitch + (y0 + p.pad);
     view_compute_store<FAMILY == MG_FAMILY_COLLECT, V>(src, sa, sb, mA, mB, p.oob_code, (uint32_t)p.agent_code | ((uint32_t)dir << 6),
                                                        p.see_through != 0, s_out, v);
   }
