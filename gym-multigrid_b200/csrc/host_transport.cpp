@@ -187,21 +187,23 @@ void host_apply_delta(const HostDeltaJob& j, int threads) {
       if (j.terminated) j.terminated[e] = (b0 >> 5) & 1;
       if (j.truncated) j.truncated[e] = (b0 >> 6) & 1;
       if (j.rewards)
-        for (int i = 0; i < A; ++i) j.rewards[e * A + i] = j.reward_table[rec[1 + i]];
+        for (int i = 0; i < A; ++i) j.rewards[e * A + i] = j.reward_table[rec[1 + i] <= 32 ? rec[1 + i] : 0];
       if (!j.obs || j.skip_patches) continue;
       uint8_t* o = j.obs + e * row;
       const uint8_t* ent = rec + 1 + A;
+      const size_t ncell = (size_t)j.cells;   // indices are checked: a corrupt record must not write outside its env's row
+      const int nmax = n <= 3 * A ? n : 3 * A;
       if (!j.wide) {
-        for (int q = 0; q < n; ++q) put3(o + 3 * (size_t)ent[2 * q], ent[2 * q + 1]);
+        for (int q = 0; q < nmax; ++q) { const size_t idx = ent[2 * q]; if (idx < ncell) put3(o + 3 * idx, ent[2 * q + 1]); }
       } else {
-        for (int q = 0; q < n; ++q) put3(o + 3 * ((size_t)ent[3 * q] | ((size_t)ent[3 * q + 1] << 8)), ent[3 * q + 2]);
+        for (int q = 0; q < nmax; ++q) { const size_t idx = (size_t)ent[3 * q] | ((size_t)ent[3 * q + 1] << 8); if (idx < ncell) put3(o + 3 * idx, ent[3 * q + 2]); }
       }
       if ((b0 & 0x80) && j.final_obs) std::memcpy(j.final_obs + e * row, o, row);   // terminal observation, before the fresh row lands
     }
   });
 }
 
-void host_apply_rows(const uint8_t* rows, size_t stride, size_t count, int cells, uint8_t* obs, int threads) {
+void host_apply_rows(const uint8_t* rows, size_t stride, size_t count, int cells, uint8_t* obs, size_t num_envs, int threads) {
   HostPool::get().run(threads, [&](int k, int parts) {
     size_t lo, hi;
     split(count, k, parts, 16, lo, hi);
@@ -209,6 +211,7 @@ void host_apply_rows(const uint8_t* rows, size_t stride, size_t count, int cells
       const uint8_t* r = rows + s * stride;
       int32_t e;
       std::memcpy(&e, r, 4);
+      if (e < 0 || (size_t)e >= num_envs) continue;
       expand_cells(r + 4, obs + (size_t)e * 3 * cells, (size_t)cells);
     }
   });

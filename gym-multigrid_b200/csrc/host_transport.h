@@ -26,6 +26,6 @@ struct HostDeltaJob {
 void host_apply_delta(const HostDeltaJob& job, int threads);
 
 // fresh rows of the envs that autoreset: each entry = int32 env index followed by `cells` packed cells (stride bytes apart)
-void host_apply_rows(const uint8_t* rows, size_t stride, size_t count, int cells, uint8_t* obs, int threads);
+void host_apply_rows(const uint8_t* rows, size_t stride, size_t count, int cells, uint8_t* obs, size_t num_envs, int threads);
 
 }  // namespace mg

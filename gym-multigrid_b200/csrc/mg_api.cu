@@ -1315,7 +1315,7 @@ static int finish_host_step(mg_env* env, cudaStream_t st) {
       if ((ce = cudaMemcpyAsync(env->h_reset_rows, env->d_reset_rows, (size_t)count * env->reset_stride, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
         return cuda_fail(env, "D2H reset rows", ce);
       if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(env, "cudaStreamSynchronize", ce);
-      mg::host_apply_rows(env->h_reset_rows, env->reset_stride, (size_t)count, env->base.cells, io.obs, T);
+      mg::host_apply_rows(env->h_reset_rows, env->reset_stride, (size_t)count, env->base.cells, io.obs, N, T);
     }
   }
   env->mirror = io.obs; env->mirror_valid = true;
