@@ -404,10 +404,11 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (numpy in, numpy out)
     e2e_steps = args.e2e_steps
-    # env batches in flight: two on one or two GPUs (the decode of one overlaps the step of the other); ONE from four GPUs up - eight
-    # ranks share the host's memory system, where every step sweeps its batch's 19.6 MB observation mirror: a second batch in flight per
-    # rank doubles the working set (8 x 39 MB) and measured slower (4.2e8 against 6.3e8 env-steps/s on 8 GPUs, tools/dev/e2e_multi.py)
-    EB = min(B, 2 if world <= 2 else 1)
+    # env batches in flight: three on one or two GPUs (16 host cores per GPU: the decode of one batch runs on the library's host pool while
+    # the caller enqueues the others); ONE from four GPUs up - there a rank has 4 cores, the eight ranks' observation mirrors (8 x 19.6 MB)
+    # no longer fit the host's caches, and a second batch in flight per rank only doubles that working set (measured on 8 GPUs:
+    # 8.4e8 env-steps/s with one batch in flight against 5.2-6.2e8 with two, tools/dev/e2e_multi8.sh)
+    EB = min(B, args.e2e_batches if args.e2e_batches > 0 else (3 if world <= 2 else 1))
     host_rings = [rings[b].cpu().numpy() for b in range(EB)]
     cells = envs[0].width * envs[0].height
 
@@ -550,7 +551,9 @@ def run_ours(args):
                     "api": f"CollectVecEnv.step_async(numpy) / step_wait() -> mg_step_host_async / _wait, {EB} env batches in flight, fresh actions per step; "
                            "the observation crosses PCIe as 16-byte per-env records of the cells the step changed (+ the packed rows of the "
                            "envs that autoreset: every 50th step here, averaged into d2h_bytes_per_step) and is patched into the page-locked "
-                           f"(N, W, H, 3) uint8 array the call returns by {host_threads() // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) or 1} host threads",
+                           f"(N, W, H, 3) uint8 array the call returns by {host_threads() // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))) or 1} host threads "
+                           "(the library's pool: the decode of a batch starts when its copy has landed and overlaps the caller's enqueue of the "
+                           "other batches; the steady-state step goes out as one CUDA-graph launch)",
                     "d2h_GBps_per_gpu": d2h_delta / (e2e_ms * 1e-3 / e2e_steps) / 1e9,
                     "bare_d2h_copy_GBps": bare_d2h_gbps,
                     "packed": {"value": e2e_steps * n * world / (e2e_packed_ms * 1e-3), "d2h_bytes_per_step": e2e["packed"]["d2h"],
@@ -688,7 +691,8 @@ def main():
     ap.add_argument("--action-ring", type=int, default=64, help="independently drawn action tensors per env batch, one per step in turn")
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of exactly --steps launches; the median is reported")
     ap.add_argument("--streams", type=int, default=4, help="streams the independent env batches are forked over inside the graph")
-    ap.add_argument("--e2e-steps", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=384)
+    ap.add_argument("--e2e-batches", type=int, default=0, help="env batches in flight in the e2e loop (0 = 3 on one or two GPUs, 1 from four up)")
     ap.add_argument("--e2e-repeats", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--python-seconds", type=float, default=3.0, help="seconds per leg of the Python-reference baseline (when a copy is on the box)")

@@ -4,12 +4,17 @@
 // entry point that produces results does so by launching a kernel on the handle's device.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -122,7 +127,21 @@ struct mg_env {
   double reward_table[33];
   const uint8_t* mirror;     // the caller's obs buffer the delta transport patches in place
   bool mirror_valid;
-  struct { bool active, refresh, plane; mg_step_io io; } pend;
+  struct {
+    bool active, refresh, plane; mg_step_io io;
+    // asynchronous decode (mg_step_host_async with a compact transport): the completer thread waits for `ev`, then the host pool
+    // decodes while the caller is free to enqueue other env batches; mg_step_host_wait helps and waits for `done`
+    bool async; cudaStream_t st;
+    std::atomic<int> done;        // raised after the last decode task (or on an error)
+    std::atomic<int> pre;         // prerequisites of the reset-row task still open: the delta pass, the row copy
+    int cuda_err; const char* err_what; bool corrupt;
+    mg::HostTask t1, t2;
+    mg::HostDeltaJob job;
+  } pend;
+  cudaEvent_t host_ev;           // recorded behind the step's last device-to-host copy
+  // the steady-state delta step (H2D actions, header clear, kernel, D2H records) as ONE graph launch; re-captured when anything the
+  // launches depend on differs from the capture (state / action pointers, the kernel's whole parameter block, the kernel variant)
+  struct { cudaGraphExec_t exec; void* state; const void* h_actions; int step_impl, tile; mg::CollectParams p; int failures; } hgraph;
 };
 
 static thread_local std::string g_create_err;
@@ -290,9 +309,14 @@ extern "C" int mg_create(const mg_config* cfg, int device, mg_env** out) {
   return 0;
 }
 
+static void drain_host_step(mg_env* env);
+
 extern "C" int mg_destroy(mg_env* env) {
   if (!env) return 0;
   cudaSetDevice(env->device);
+  drain_host_step(env);
+  if (env->host_ev) cudaEventDestroy(env->host_ev);
+  if (env->hgraph.exec) cudaGraphExecDestroy(env->hgraph.exec);
   cudaFree(env->d_status);
   cudaFree(env->d_wall_template);
   cudaFree(env->d_map_tables);
@@ -972,13 +996,9 @@ static int rollout_prepare(mg_env* env) {
   return 0;
 }
 
-static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st, bool with_delta = false) {
-  if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
-  if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
-  if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 1, io, nullptr, nullptr, st);
-  if (env->family == MG_FAMILY_GENERIC) return generic_launch(env, state, 1, io, nullptr, nullptr, st);
-  if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 1, io, nullptr, nullptr, st);
-  mg::CollectParams p = env->base;
+// the Collect step's kernel parameter block for one call (everything the launch depends on besides env->step_impl / env->tile)
+static int collect_step_params(mg_env* env, void* state, const mg_step_io* io, bool with_delta, mg::CollectParams& p) {
+  p = env->base;
   bind_state(env, p, state);
   bind_trace(env, p);
   if (p.rng_mode == 0 && !p.order) return fail(env, "mg_step: trace mode needs the recorded agent order");
@@ -992,6 +1012,17 @@ static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStrea
     p.reset_count = reinterpret_cast<int32_t*>(env->d_delta_blk);
     p.reset_rows = env->d_reset_rows; p.reset_stride = (int)env->reset_stride;
   }
+  return 0;
+}
+
+static int step_device(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st, bool with_delta = false) {
+  if (!io->actions || !io->rewards || !io->terminated || !io->truncated) return fail(env, "mg_step: actions/rewards/terminated/truncated must be non-null");
+  if (io->final_obs && !io->obs) return fail(env, "mg_step: final_obs needs obs");
+  if (env->family == MG_FAMILY_WILDFIRE) return wildfire_launch(env, state, 1, io, nullptr, nullptr, st);
+  if (env->family == MG_FAMILY_GENERIC) return generic_launch(env, state, 1, io, nullptr, nullptr, st);
+  if (env->family != MG_FAMILY_COLLECT) return map_launch(env, state, 1, io, nullptr, nullptr, st);
+  mg::CollectParams p;
+  if (collect_step_params(env, state, io, with_delta, p)) return -1;
   cudaError_t ce;
   if (env->step_impl == 1 && rollout_prepare(env) == 0) {
     p.T = 1;
@@ -1229,6 +1260,10 @@ extern "C" int mg_host_apply_delta(const uint8_t* records, size_t n, int cells, 
 
 extern "C" int mg_delta_record_bytes(int cells, int num_agents) { return mg::delta_record_bytes(cells, num_agents); }
 
+static bool host_graph_enabled() {
+  static const bool on = [] { const char* v = std::getenv("MG_HOST_GRAPH"); return !(v && v[0] == '0'); }();
+  return on;
+}
 // H2D actions -> step -> D2H of the step's compact results into the handle's page-locked staging; decoded by finish_host_step
 static int step_host_compact(mg_env* env, void* state, const mg_step_io* io, cudaStream_t st) {
   if (!aligned16(state)) return fail(env, "mg_step_host: state buffer must be 16-byte aligned");
@@ -1256,15 +1291,71 @@ static int step_host_compact(mg_env* env, void* state, const mg_step_io* io, cud
     if ((ce = cudaMalloc(&env->d_final, ob)) != cudaSuccess) return cuda_fail(env, "cudaMalloc", ce);
     if ((ce = cudaMemsetAsync(env->d_final, 0, ob, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
   }
-  if ((ce = cudaMemcpyAsync(env->d_actions, io->actions, N * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(env, "H2D actions", ce);
-  if (delta && (ce = cudaMemsetAsync(env->d_delta_blk, 0, 16, st)) != cudaSuccess) return cuda_fail(env, "cudaMemsetAsync", ce);
   mg_step_io dio;
   dio.actions = env->d_actions; dio.rewards = env->d_rewards; dio.terminated = env->d_term; dio.truncated = env->d_trunc;
   dio.obs = dev_final ? static_cast<uint8_t*>(env->d_obs) : nullptr;   // the expanded observation stays off the wire
   dio.final_obs = dev_final ? env->d_final : nullptr;
-  if (step_device(env, state, &dio, st, delta)) return -1;
+  // steady state of the delta transport: the four stream operations never change from step to step - one graph launch
+  bool capturing = false;
+  if (delta && !want_plane && !dev_final && host_graph_enabled() && env->hgraph.failures < 3) {
+    mg::CollectParams p;
+    if (collect_step_params(env, state, &dio, true, p)) return -1;
+    auto& g = env->hgraph;
+    if (g.exec && g.state == state && g.h_actions == io->actions && g.step_impl == env->step_impl && g.tile == env->tile &&
+        std::memcmp(&g.p, &p, sizeof p) == 0) {
+      if ((ce = cudaGraphLaunch(g.exec, st)) != cudaSuccess) return cuda_fail(env, "cudaGraphLaunch", ce);
+      env->launches += 1;
+      env->pend.active = true; env->pend.refresh = false; env->pend.plane = false; env->pend.io = *io;
+      return 0;
+    }
+    cudaPointerAttributes pa;   // pageable actions cannot be captured (and are not asynchronous either)
+    const bool pinned = cudaPointerGetAttributes(&pa, io->actions) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (pinned && env->step_impl == 1 && rollout_prepare(env) == 0) {
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        capturing = true;
+        g.state = state; g.h_actions = io->actions; g.step_impl = env->step_impl; g.tile = env->tile; g.p = p;
+      } else {
+        (void)cudaGetLastError();
+        g.failures += 1;
+      }
+    }
+  }
+  auto end_capture = [&](bool ok) -> int {   // closes the capture; on success instantiates and launches the graph
+    if (!capturing) return 0;
+    capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+    if (ok && e2 == cudaSuccess && graph) {
+      e2 = cudaGraphInstantiate(&env->hgraph.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e2 == cudaSuccess && (e2 = cudaGraphLaunch(env->hgraph.exec, st)) == cudaSuccess) return 0;
+      if (env->hgraph.exec) { cudaGraphExecDestroy(env->hgraph.exec); env->hgraph.exec = nullptr; }
+    } else if (graph) {
+      cudaGraphDestroy(graph);
+    }
+    (void)cudaGetLastError();
+    env->hgraph.exec = nullptr;
+    env->hgraph.failures += 1;
+    if (std::getenv("MG_DEBUG")) std::fprintf(stderr, "multigrid_b200: host-step graph capture failed (%s), plain launches instead\n", cudaGetErrorString(e2));
+    return -1;
+  };
+  for (int attempt = 0; attempt < 2; ++attempt) {   // a failed capture is followed by one plain pass
+    const bool was_capturing = capturing;
+    bool ok = true;
+    if ((ce = cudaMemcpyAsync(env->d_actions, io->actions, N * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) ok = false;
+    if (ok && delta && (ce = cudaMemsetAsync(env->d_delta_blk, 0, 16, st)) != cudaSuccess) ok = false;
+    if (!ok && !was_capturing) return cuda_fail(env, "H2D actions / header clear", ce);
+    if (ok && step_device(env, state, &dio, st, delta)) { if (!was_capturing) return -1; ok = false; }
+    if (ok && delta && (ce = cudaMemcpyAsync(env->h_delta_blk, env->d_delta_blk, 16 + N * R, cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+      if (!was_capturing) return cuda_fail(env, "D2H delta records", ce);
+      ok = false;
+    }
+    if (!was_capturing) break;
+    if (end_capture(ok) == 0) break;   // captured, instantiated and launched
+  }
   if (delta) {
-    if ((ce = cudaMemcpyAsync(env->h_delta_blk, env->d_delta_blk, 16 + N * R, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H delta records", ce);
   } else {
     size_t off_r, off_t, off_u, total;
     host_layout(env, &off_r, &off_t, &off_u, &total);
@@ -1284,6 +1375,130 @@ static int step_host_compact(mg_env* env, void* state, const mg_step_io* io, cud
   if (dev_final && (ce = cudaMemcpyAsync(io->final_obs, env->d_final, ob, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(env, "D2H final_obs", ce);
   env->pend.active = true; env->pend.refresh = refresh; env->pend.plane = want_plane; env->pend.io = *io;
   return 0;
+}
+
+// ---- asynchronous decode ---------------------------------------------------------------------------------------------
+// A step enqueued by mg_step_host_async is watched by the host pool's idle threads (cudaEventQuery on its event); the thread that
+// sees it land turns the decode into pool tasks, which the workers run while the caller's thread enqueues its other env batches:
+// the host half of step k overlaps the device half of step k + 1 AND the caller's own work.  Rows of envs that autoreset are
+// fetched by the watching thread (a count-sized copy) while the delta pass runs; the row task starts when both are done.
+static bool host_async_enabled() {
+  static const bool on = [] { const char* v = std::getenv("MG_HOST_ASYNC"); return !(v && v[0] == '0'); }();
+  return on;
+}
+
+static void pend_finish(mg_env* env) { env->pend.done.store(1, std::memory_order_release); }
+static void pend_rows_ready(mg_env* env) {   // called twice per step with reset rows: after the delta pass and after the row copy
+  if (env->pend.pre.fetch_sub(1, std::memory_order_acq_rel) == 1) mg::host_submit(&env->pend.t2);
+}
+
+// on the thread that saw the step's event complete: build and submit the decode tasks
+static void start_async_decode(mg_env* env) {
+  auto& pd = env->pend;
+  const mg_step_io& io = pd.io;
+  const size_t N = (size_t)env->cfg.num_envs, cells = (size_t)env->base.cells;
+  const int T = env->host_threads;
+  if (env->transport == MG_TRANSPORT_PACKED) {
+    if (!io.obs) { pend_finish(env); return; }
+    mg::host_expand_task(&pd.t1, env->h_grid, io.obs, N * cells, T);
+    pd.t1.then = [env] { pend_finish(env); };
+    mg::host_submit(&pd.t1);
+    return;
+  }
+  mg::HostDeltaJob& j = pd.job;
+  j.records = env->h_delta_blk + 16; j.n = N; j.stride = mg::delta_record_bytes(env->base.cells, env->base.A);
+  j.wide = env->base.cells > 256; j.cells = env->base.cells; j.A = env->base.A; j.reward_table = env->reward_table;
+  j.obs = io.obs; j.skip_patches = pd.refresh; j.rewards = io.rewards; j.terminated = io.terminated; j.truncated = io.truncated;
+  j.final_obs = pd.refresh ? nullptr : io.final_obs;
+  mg::host_delta_task(&pd.t1, &j, T);
+  if (!io.obs) {
+    pd.t1.then = [env] { pend_finish(env); };
+    mg::host_submit(&pd.t1);
+    return;
+  }
+  if (pd.refresh) {   // the whole mirror again from the packed plane, after rewards / flags
+    mg::host_expand_task(&pd.t2, env->h_grid, io.obs, N * cells, T);
+    pd.t2.then = [env] { pend_finish(env); };
+    pd.t1.then = [env] { mg::host_submit(&env->pend.t2); };
+    mg::host_submit(&pd.t1);
+    return;
+  }
+  int32_t count;
+  std::memcpy(&count, env->h_delta_blk, 4);
+  if (count < 0 || (size_t)count > N) { pd.corrupt = true; pend_finish(env); return; }
+  if (count == 0) {
+    pd.t1.then = [env] { pend_finish(env); };
+    mg::host_submit(&pd.t1);
+    return;
+  }
+  mg::host_rows_task(&pd.t2, env->h_reset_rows, env->reset_stride, (size_t)count, env->base.cells, io.obs, N, T);
+  pd.t2.then = [env] { pend_finish(env); };
+  pd.pre.store(2, std::memory_order_release);
+  pd.t1.then = [env] { pend_rows_ready(env); };
+  mg::host_submit(&pd.t1);
+  cudaError_t ce = cudaSetDevice(env->device);   // a pool thread: its current device is whatever it touched last
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(env->h_reset_rows, env->d_reset_rows, (size_t)count * env->reset_stride, cudaMemcpyDeviceToHost, pd.st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(pd.st);
+  if (ce != cudaSuccess) { pd.cuda_err = (int)ce; pd.err_what = "D2H reset rows"; }   // the rows are still applied (stale): the wait reports the error
+  pend_rows_ready(env);
+}
+
+// steps in flight, watched by the pool's idle threads (host_set_poller): probe = cudaEventQuery over them
+static std::mutex g_inflight_mu;
+static std::vector<mg_env*> g_inflight;
+static void* probe_inflight() {
+  std::lock_guard<std::mutex> lk(g_inflight_mu);
+  for (size_t i = 0; i < g_inflight.size(); ++i) {
+    mg_env* env = g_inflight[i];
+    const cudaError_t ce = cudaEventQuery(env->host_ev);
+    if (ce == cudaErrorNotReady) continue;
+    if (ce != cudaSuccess) { env->pend.cuda_err = (int)ce; env->pend.err_what = "cudaEventQuery"; }
+    g_inflight.erase(g_inflight.begin() + (long)i);
+    return env;
+  }
+  return nullptr;
+}
+static void start_inflight(void* v) {
+  mg_env* env = static_cast<mg_env*>(v);
+  mg::host_poll_add(-1);
+  if (env->pend.cuda_err) { pend_finish(env); return; }
+  start_async_decode(env);
+}
+
+// behind step_host_compact on the async path: mark the step and put it on the watch list
+static int launch_async_decode(mg_env* env, cudaStream_t st) {
+  cudaError_t ce;
+  if (!env->host_ev) {
+    if ((ce = cudaEventCreateWithFlags(&env->host_ev, cudaEventDisableTiming)) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaEventCreate", ce); }
+    mg::host_set_poller(probe_inflight, start_inflight);
+  }
+  if ((ce = cudaEventRecord(env->host_ev, st)) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaEventRecord", ce); }
+  env->pend.async = true; env->pend.st = st; env->pend.cuda_err = 0; env->pend.err_what = nullptr; env->pend.corrupt = false;
+  env->pend.done.store(0, std::memory_order_release);
+  {
+    std::lock_guard<std::mutex> lk(g_inflight_mu);
+    g_inflight.push_back(env);
+  }
+  mg::host_poll_add(1);
+  return 0;
+}
+
+// mg_step_host_wait on the async path: work on queued decode chunks until this step's are done
+static int wait_async_decode(mg_env* env) {
+  mg::host_help_until(env->pend.done);
+  auto& pd = env->pend;
+  pd.active = false; pd.async = false;
+  if (pd.cuda_err) { env->mirror_valid = false; return cuda_fail(env, pd.err_what ? pd.err_what : "host step", (cudaError_t)pd.cuda_err); }
+  if (pd.corrupt) { env->mirror_valid = false; return fail(env, "mg_step_host: corrupt reset count"); }
+  if (env->transport == MG_TRANSPORT_DELTA) {
+    if (!pd.io.obs) env->mirror_valid = false;   // nothing was patched: a mirror kept by the caller is now stale
+    else { env->mirror = pd.io.obs; env->mirror_valid = true; }
+  }
+  return 0;
+}
+
+static void drain_host_step(mg_env* env) {
+  if (env->pend.active && env->pend.async) wait_async_decode(env);
 }
 
 // after the stream has drained: decode the staged results into the caller's buffers
@@ -1332,7 +1547,7 @@ static int step_host_enqueue(mg_env* env, void* state, const mg_step_io* io, voi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (env->transport != MG_TRANSPORT_FULL) {
     if (step_host_compact(env, state, io, st)) return -1;
-    if (!wait) return 0;
+    if (!wait) return host_async_enabled() ? launch_async_decode(env, st) : 0;
     if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaStreamSynchronize", ce); }
     return finish_host_step(env, st);
   }
@@ -1387,6 +1602,7 @@ extern "C" int mg_step_host_async(mg_env* env, void* state, const mg_step_io* io
 extern "C" int mg_step_host_wait(mg_env* env, void* stream) {
   if (!env) return -1;
   cudaError_t ce;
+  if (env->pend.active && env->pend.async) return wait_async_decode(env);
   if ((ce = cudaSetDevice(env->device)) != cudaSuccess) return cuda_fail(env, "cudaSetDevice", ce);
   if ((ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream))) != cudaSuccess) { env->pend.active = false; return cuda_fail(env, "cudaStreamSynchronize", ce); }
   return finish_host_step(env, static_cast<cudaStream_t>(stream));

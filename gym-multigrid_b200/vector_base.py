@@ -77,7 +77,9 @@ class VectorEnvSurface:
         io = self._host_io(actions)
         if self._host_stream is None:
             self._host_stream = torch.cuda.Stream(device=self.device)
-        self._host_stream.wait_stream(torch.cuda.current_stream(self.device))   # ordered after device-path calls on the caller's stream
+        cur = torch.cuda.current_stream(self.device)
+        if not cur.query():   # ordered after device-path calls on the caller's stream (nothing to order after when that stream is idle)
+            self._host_stream.wait_stream(cur)
         if self._lib.mg_step_host_async(self._h, C.c_void_p(self.state.data_ptr()), C.byref(io), C.c_void_p(self._host_stream.cuda_stream)):
             self._check(-1)
         self._host_pending = True

@@ -290,7 +290,9 @@ class CollectVecEnv(VectorEnvSurface):
 
     def _host_result(self):
         n = self._host_np
-        return n["obs"], n["rew"], n["term"].view(np.bool_), n["trunc"].view(np.bool_), self._info()
+        if "term_b" not in n:
+            n["term_b"], n["trunc_b"] = n["term"].view(np.bool_), n["trunc"].view(np.bool_)
+        return n["obs"], n["rew"], n["term_b"], n["trunc_b"], (self._info_static if self._final_obs is None else self._info())
 
     def step_host(self, actions):
         """gymnasium-style call with HOST arrays: numpy in, numpy out (views of page-locked buffers,

@@ -216,6 +216,50 @@ def test_compact_transports_with_final_observation(kw, n, transport, cuda_device
     dev.close(); host.close()
 
 
+@pytest.mark.parametrize("kw,n", DELTA_CASES[:2])
+@pytest.mark.parametrize("transport", ["packed", "delta"])
+def test_async_decode_three_batches_with_autoreset_rows(kw, n, transport, cuda_device):
+    """mg_step_host_async / _wait with the decode running on the host pool while the caller enqueues the other batches (three in
+    flight): staggered terminations, so most steps carry reset rows (the count-sized second copy joins the delta pass) and terminal
+    observations taken from the mirror; the steady-state steps go out as one captured graph launch.  == the device path."""
+    import ctypes as C
+    from gym_multigrid_b200.vector_env import CollectVecEnv
+    B = 3
+    devs = [CollectVecEnv(n, seed=30 + b, autoreset=True, **kw) for b in range(B)]
+    hosts = [CollectVecEnv(n, seed=30 + b, autoreset=True, host_transport=transport, **kw) for b in range(B)]
+    W, A = kw["size"], len(kw["agents_index"])
+    fins = [torch.zeros((n, W, W, 3), dtype=torch.uint8).pin_memory() for _ in range(B)]
+    for d, h in zip(devs, hosts):
+        d.enable_final_observation(); d.reset(); h.reset()
+    rng = np.random.default_rng(6)
+    T = 70
+    acts = rng.integers(0, 4, size=(T, B, n, A)).astype(np.int8)
+
+    def enqueue(b, t):
+        io = hosts[b]._host_io(acts[t, b])
+        io.final_obs = fins[b].data_ptr()
+        hosts[b].step_async(acts[t, b])
+    for b in range(B):
+        enqueue(b, 0)
+    finished = 0
+    for t in range(T):
+        for b in range(B):
+            want = devs[b].step(torch.as_tensor(acts[t, b], device=cuda_device))
+            got = hosts[b].step_wait()
+            for x, y in zip(want[:4], got[:4]):
+                assert np.array_equal(_np(x), y), f"step {t} batch {b}"
+            done = _np(want[2] | want[3])
+            finished += int(done.sum())
+            if done.any():
+                assert np.array_equal(_np(want[4]["final_observation"])[done], fins[b].numpy()[done]), f"final_observation, step {t} batch {b}"
+            if t + 1 < T:
+                enqueue(b, t + 1)
+    assert finished >= B * n, "the case must exercise autoresets"
+    for e in devs + hosts:
+        assert e.status() == 0
+        e.close()
+
+
 @pytest.mark.parametrize("transport", ["full", "delta"])
 def test_step_async_wait_two_batches_in_flight(transport, cuda_device):
     """step_async / step_wait (mg_step_host_async / _wait): two env batches alternated with both in flight return exactly what
