@@ -357,14 +357,18 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
 // STEPV: which CtF step body the kernel carries - 0 the general one (run-time team sizes), 1 the 2v2 and 2 the 1v1 register
 // bodies.  One body per kernel keeps the instruction stream of the hot path inside the instruction cache (with all of them
 // inlined into one kernel `no_instruction` became the top stall reason).
-template <int FAMILY, int MODE, int MINB, int STEPV = 0>
+// LEAN: the kernel of ONE hot configuration with everything else compiled out (the general kernel is ~6 500 SASS instructions of
+// which a step of the common case executes ~1 000: `no_instruction` stalls).  1 = step (op 1) of a CtF handle with the staged u8
+// tile image, obs given, no final_obs; 2 = step of a Maze handle in partial-view mode computed from the padded map (no memoised
+// table), obs given, no final_obs.  The launcher checks those conditions; 0 = the general kernel.
+template <int FAMILY, int MODE, int MINB, int STEPV = 0, int LEAN = 0>
 __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar, bar_tile;
   __shared__ uint8_t s_done[kMapE];
-  const int tid = threadIdx.x, n = p.n, cells = p.cells;
-  const bool view_mode = FAMILY == MG_FAMILY_MAZE && p.view_V != 0;                 // obs = partial views (gen_obs) instead of the map
-  const bool view_table = view_mode && p.view_table != nullptr;                     // memoised views: no map needed in shared memory
+  const int tid = threadIdx.x, n = (LEAN == 1 && STEPV == 1) ? 4 : (LEAN == 2 ? 1 : p.n), cells = p.cells;
+  const bool view_mode = LEAN == 2 || (LEAN == 0 && FAMILY == MG_FAMILY_MAZE && p.view_V != 0);   // obs = partial views (gen_obs) instead of the map
+  const bool view_table = LEAN == 0 && view_mode && p.view_table != nullptr;        // memoised views: no map needed in shared memory
   const int head = view_table ? 0 : (view_mode ? p.map_padded_bytes : p.L);
   uint8_t* s_period = smem_raw;                                                     // [L], or the padded packed map in view mode
   uint32_t* s_ag = reinterpret_cast<uint32_t*>(smem_raw + head);                    // [n][kMapE] agent words, transposed
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   pdl_wait();
   // staged u8 tiles: the static part of the whole tile's observation slab (the map repeated once per env) arrives as ONE bulk
   // load of a host-built image while the envs step - no per-thread replication of the period, no barrier in front of the patches
-  const bool tile_img = !view_mode && p.obs_tile && p.obs;
+  const bool tile_img = LEAN == 1 || (LEAN == 0 && !view_mode && p.obs_tile && p.obs);
   if (tid == 0 && head) {
     mbar_expect_tx(&bar, (uint32_t)head);
     tma_load_1d(s_period, view_mode ? p.map_padded : p.obs_period, (uint32_t)head, &bar);
@@ -392,7 +396,12 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   // ---- the env's agent row (padded to row_bytes = 4 * 2^k) and header; state planes are padded to whole tiles
   uint32_t* ag = s_ag + tid;
   const uint8_t* row = p.agents + e * p.row_bytes;
-  if (p.row_bytes >= 16) {
+  if (LEAN == 1 && STEPV == 1) {   // 2v2: the row is one 16-byte word
+    const uint4 v = *reinterpret_cast<const uint4*>(row);
+    ag[0] = v.x; ag[kMapE] = v.y; ag[2 * kMapE] = v.z; ag[3 * kMapE] = v.w;
+  } else if (LEAN == 2) {
+    ag[0] = *reinterpret_cast<const uint32_t*>(row);
+  } else if (p.row_bytes >= 16) {
     for (int c = 0; c < p.row_bytes / 16; ++c) {
       const uint4 v = *reinterpret_cast<const uint4*>(row + 16 * c);
       if (4 * c + 0 < n) ag[(4 * c + 0) * kMapE] = v.x;
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   }
   int4 h = p.hdr[e];
   uint32_t blue_raw = 0;   // 2v2 / 1v1 step: the blue actions travel with the state loads, ahead of the wait for the staged period
-  if (FAMILY == MG_FAMILY_CTF && p.op == 1 && tid < n_here) {
+  if (FAMILY == MG_FAMILY_CTF && (LEAN || p.op == 1) && tid < n_here) {
     if (STEPV == 1)
       blue_raw = (reinterpret_cast<uintptr_t>(p.actions) & 1) ? ((uint32_t)(uint8_t)p.actions[e * 2] | ((uint32_t)(uint8_t)p.actions[e * 2 + 1] << 8))
                                                                 : *reinterpret_cast<const uint16_t*>(p.actions + e * 2);
@@ -418,10 +427,10 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   int err = 0;
   Rng<MODE> r;
   r.open_trace(nullptr, 0);
-  if (FAMILY == MG_FAMILY_CTF && p.op == 1) mbar_wait(&bar, 0);  // the CtF step reads terrain codes from the staged period
+  if (FAMILY == MG_FAMILY_CTF && (LEAN || p.op == 1)) mbar_wait(&bar, 0);  // the CtF step reads terrain codes from the staged period
   if (tid < n_here) {
     if (MODE == 1) r.open_philox(p.seed, p.env_id_base + (unsigned long long)e, (uint32_t)h.z);
-    if (p.op == 0) {
+    if (LEAN == 0 && p.op == 0) {
       want_reset = !p.reset_mask || p.reset_mask[e];
     } else {
       double rew; bool term, trunc;
@@ -434,10 +443,10 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
       want_reset = done = p.autoreset && (term || trunc);  // same-step autoreset
     }
   }
-  if (head) mbar_wait(&bar, 0);
+  if (LEAN != 1 && head) mbar_wait(&bar, 0);   // (LEAN 1 has waited above)
 
   // ---- terminal observations of the finished envs are drawn before their reset (only when the caller asked for them)
-  if (p.final_obs) {
+  if (LEAN == 0 && p.final_obs) {
     s_done[tid] = done;
     if (__syncthreads_or(done)) {
       for (int j = 0; j < n_here; ++j) {
@@ -464,7 +473,11 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   if (err) atomicOr(p.status, err);
   {
     uint8_t* wrow = p.agents + e * p.row_bytes;
-    if (p.row_bytes >= 16) {
+    if (LEAN == 1 && STEPV == 1) {
+      *reinterpret_cast<uint4*>(wrow) = make_uint4(ag[0], ag[kMapE], ag[2 * kMapE], ag[3 * kMapE]);
+    } else if (LEAN == 2) {
+      *reinterpret_cast<uint32_t*>(wrow) = ag[0];
+    } else if (p.row_bytes >= 16) {
       for (int c = 0; c < p.row_bytes / 16; ++c) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (4 * c + 0 < n) v.x = ag[(4 * c + 0) * kMapE];
@@ -480,7 +493,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     }
   }
 
-  if (!p.obs) return;
+  if (LEAN == 0 && !p.obs) return;
   // ---- Maze partial-observation mode: this env's egocentric view (fused MazeSingleAgentEnv.step + MultiGridEnv.gen_obs)
   if (view_mode) {
     const int V = p.view_V, VV3 = V * V * 3;
@@ -528,8 +541,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   }
   // ---- observation: static map for the whole tile, then the agents on top
   const long long slab = (long long)n_here * cells;  // elements in this tile's obs slab
-  if (p.obs_staged) {  // u8, small map: assemble the tile in shared memory, one TMA bulk store
-    if (!tile_img) {   // handle without the image table: replicate the period by hand
+  if (LEAN == 1 || p.obs_staged) {  // u8, small map: assemble the tile in shared memory, one TMA bulk store
+    if (LEAN == 0 && !tile_img) {   // handle without the image table: replicate the period by hand
       const int L16 = p.L16, chunks = kMapE * cells / 16;
       uint4* dst = reinterpret_cast<uint4*>(s_obs);
       const uint4* src = reinterpret_cast<const uint4*>(s_period);
@@ -557,6 +570,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     if (tid == 0) tma_wait_read_all();
     return;
   }
+  if (LEAN != 0) return;   // (not reached: the lean kernels have returned above)
   if (p.obs_tma) {
     // large tiles: the static map leaves straight from the staged period, one TMA bulk store per period (full-line
     // writes, no per-thread store instructions); the stores are spread over the CTA's threads, each waits for its own
@@ -763,6 +777,8 @@ cudaError_t configure_map_view_mode(size_t smem) {
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 0, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 0, 8>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 1, 0, 2>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 8, 0, 2>, (size_t)smem)) != cudaSuccess) return e;
   return raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 8>, (size_t)smem);
 }
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
@@ -776,7 +792,7 @@ size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
 }
 int map_tile_envs() { return kMapE; }
 
-template <int FAMILY, int MODE, int MINB, int STEPV>
+template <int FAMILY, int MODE, int MINB, int STEPV, int LEAN = 0>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.view_table ? 0 : p.map_padded_bytes, p.view_V)
                                                                : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
@@ -787,7 +803,12 @@ static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = map_pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB, STEPV>, p);
+  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB, STEPV, LEAN>, p);
+}
+
+static bool map_lean_enabled() {
+  static const bool on = [] { const char* v = std::getenv("MG_MAP_LEAN"); return !(v && v[0] == '0'); }();
+  return on;
 }
 
 template <int FAMILY, int MODE, int STEPV>
@@ -807,6 +828,8 @@ cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
   if ((e = configure_pair<MG_FAMILY_CTF, 0, 2>(smem)) != cudaSuccess) return e;
   if ((e = configure_pair<MG_FAMILY_CTF, 1, 0>(smem)) != cudaSuccess) return e;
   if ((e = configure_pair<MG_FAMILY_CTF, 1, 1>(smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   return configure_pair<MG_FAMILY_CTF, 1, 2>(smem);
 }
 
@@ -821,6 +844,12 @@ static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
   // Maze partial-view mode is issue-bound: as soon as the uncapped allocation (5 CTAs per SM) would need a second wave
   // (148 * 5 * 128 envs) the 8-CTA one wins (131 072 envs: 11.3 -> 10.1 us); the other modes switch at 256 K envs
   const long long from = (FAMILY == MG_FAMILY_MAZE && p.view_V && !std::getenv("MG_MAP_MINB8_FROM")) ? 148ll * 5 * kMapE + 1 : minb8_from();
+  if constexpr (MODE == 1 && ((FAMILY == MG_FAMILY_CTF && STEPV == 1) || FAMILY == MG_FAMILY_MAZE)) {   // the hot configurations have kernels of their own
+    constexpr int LEAN = FAMILY == MG_FAMILY_CTF ? 1 : 2;
+    const bool fits = FAMILY == MG_FAMILY_CTF ? (p.obs_staged && p.obs_tile && p.row_bytes == 16) : (p.view_V && !p.view_table && p.row_bytes == 4);
+    if (map_lean_enabled() && p.op == 1 && p.obs && !p.final_obs && fits)
+      return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN>(p, st);
+  }
   return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV>(p, st) : launch_one<FAMILY, MODE, 1, STEPV>(p, st);
 }
 

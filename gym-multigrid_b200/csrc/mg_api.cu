@@ -1640,3 +1640,11 @@ extern "C" int mg_tile_envs(const mg_env* env) {
 }
 
 extern "C" int64_t mg_launch_count(const mg_env* env) { return env ? env->launches : 0; }
+
+extern "C" int mg_stream_idle(void* stream) {
+  const cudaError_t ce = cudaStreamQuery(static_cast<cudaStream_t>(stream));
+  if (ce == cudaSuccess) return 1;
+  if (ce == cudaErrorNotReady) return 0;
+  (void)cudaGetLastError();
+  return -1;
+}

@@ -225,6 +225,11 @@ int mg_tile_envs(const mg_env* env);
 /* number of kernel launches issued through this handle since creation */
 int64_t mg_launch_count(const mg_env* env);
 
+/* 1 = every operation enqueued on `stream` so far has completed, 0 = work is pending, -1 = error (cudaStreamQuery).  For callers
+ * of mg_step_host_async that keep a private stream per env batch: the private stream only has to wait for the caller's compute
+ * stream when that one is busy. */
+int mg_stream_idle(void* stream);
+
 /* ===================================================================================== Maze and CtF
  * Static text-map families: MazeSingleAgentEnv (envs/maze.py:26-377) and CtFMvNEnv (envs/ctf.py:657-1433).
  * The map (utils/map.py:22-39, field_map = np.loadtxt(path).T, indexed [x][y]) is shared by all envs and
