@@ -141,14 +141,15 @@ def time_oracle(num_envs, steps, warmup, nthreads, ring=64, seed=0):
     acts = np.random.default_rng(seed).integers(0, 4, size=(ring, num_envs, 2)).astype(np.int8)
     for i in range(warmup):
         o.step(acts[i % ring], r, autoreset=True, reuse_buffers=True)
-    picked = 0.0
     t0 = time.perf_counter()
     for i in range(steps):
-        out = o.step(acts[(warmup + i) % ring], r, autoreset=True, reuse_buffers=True)
-        if i < 8:
-            picked += float(out[1].sum())
+        o.step(acts[(warmup + i) % ring], r, autoreset=True, reuse_buffers=True)
     dt = time.perf_counter() - t0
-    return num_envs * steps / dt, dt, picked / (min(steps, 8) * num_envs)
+    # pickups per env-step under these actions (untimed), over two whole 50-step episodes like the GPU arm's count
+    picked, PS = 0.0, 100
+    for i in range(PS):
+        picked += float(o.step(acts[(warmup + steps + i) % ring], r, autoreset=True, reuse_buffers=True)[1].sum())
+    return num_envs * steps / dt, dt, picked / (PS * num_envs)
 
 
 def python_reference(seconds=3.0):
