@@ -217,6 +217,144 @@ __device__ __forceinline__ void ctf_step_one(const MapParams& p, long long e, co
   rew = __dsub_rn(rew, __dmul_rn(p.step_penalty, (double)nb));  // :1428 -- two roundings like the reference, never an FMA
 }
 
+// The general step (run-time team sizes) for maps of <= 256 cells - STEPV 3.  Same statements as ctf_step_one, two changes in HOW:
+//   * "does an agent stand on the target cell" is one bit of a per-env occupancy bitmap (`occ`: kOccWords words per env,
+//     transposed like the agent words; built from the agent rows, updated by every move) instead of a scan over all agents -
+//     the scan was a quarter of an 8v8 step's instructions (16 moves x 16 compares);
+//   * positions do not change during the battle phase, so the in-range test of a blue agent against all reds runs first,
+//     branch-free and two reds per instruction (positions byte-packed in `occ`'s second half: __vabsdiffu4 + two dp4a give
+//     both squared distances), and only the pairs in range - visited in the reference's row-major order - take the path
+//     with the dead-flag test, the terrain look-ups and the draw.
+constexpr int kOccWords = 8, kOccBytes = 2 * kOccWords * kMapE * 4;   // bitmap words + packed red pairs (<= 8 words) per env
+template <int MODE, typename NIB>
+__device__ __forceinline__ void ctf_step_occ(const MapParams& p, long long e, const int8_t* blue_act, const uint8_t* terr,
+                                             uint32_t* ag, uint32_t* occ, int4& h, Rng<MODE>& r, double& rew, bool& term, bool& trunc,
+                                             int& err) {
+  const int S = p.S, nb = p.nb, nr = p.nr, n = nb + nr;
+  uint32_t* pr = occ + kOccWords * kMapE;
+  h.x += 1;  // ctf.py:1295
+  NIB acts = 0, order = 0;
+  for (int i = 0; i < nb; ++i) {
+    const int a = blue_act[i];
+    const bool bad = a < 0 || a > 4;   // reference: ValueError (ctf.py:1200-1201)
+    if (bad) err |= MG_ERR_BAD_ACTION;
+    acts |= (NIB)(bad ? 15 : a) << (4 * i);
+  }
+  for (int k = 0; k < nr; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301), or the external enemy policy
+    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * nr + k] : below16(r, 5);
+    const bool bad = a < 0 || a > 4;
+    if (bad) err |= MG_ERR_BAD_ACTION;
+    acts |= (NIB)(bad ? 15 : a) << (4 * (nb + k));
+  }
+  if (p.variant_1v1) {  // Ctf1v1Env._move_agents: blue, then red (ctf.py:503-510)
+    order = (NIB)0x10;
+  } else if (MODE == 0) {
+    for (int i = 0; i < n; ++i) order |= (NIB)(p.order[e * n + i] & 15) << (4 * i);
+  } else {  // np_random.shuffle stand-in: Fisher-Yates
+    order = (NIB)0xFEDCBA9876543210ull;
+    for (int i = n - 1; i > 0; --i) {
+      const int j = below16(r, i + 1);
+      const NIB x = ((order >> (4 * i)) ^ (order >> (4 * j))) & (NIB)15;
+      order ^= (x << (4 * i)) | (x << (4 * j));
+    }
+  }
+  // occupancy bitmap over the cells in observation order (y * S + x): every agent object, alive or defeated
+#pragma unroll
+  for (int k = 0; k < kOccWords; ++k) occ[k * kMapE] = 0u;
+  for (int j = 0; j < n; ++j) {
+    const uint32_t w = ag[j * kMapE];
+    const int c = ag_y(w) * S + ag_x(w);
+    occ[(c >> 5) * kMapE] |= 1u << (c & 31);
+  }
+  const bool pen = p.obstacle_penalty != 0;
+  for (int k = 0; k < n; ++k) {  // _move_agents :1240-1251
+    const int i = (int)((order >> (4 * k)) & (NIB)15);
+    const uint32_t w = ag[i * kMapE];
+    const int a = (int)((acts >> (4 * i)) & (NIB)15);
+    int dx, dy;
+    action_delta(a & 7, dx, dy);
+    const int nx = ag_x(w) + dx, ny = ag_y(w) + dy;  // _move_agent :1184-1238
+    const bool live = !(w & FL_DEAD) && a != 15;     // "Defeated agent doesn't move, sadly."
+    const bool inb = (unsigned)nx < (unsigned)S && (unsigned)ny < (unsigned)S;
+    const int c = inb ? ny * S + nx : 0;
+    const uint32_t bit = 1u << (c & 31);
+    uint32_t* ow = occ + (c >> 5) * kMapE;
+    const bool occupied = (*ow & bit) != 0;   // an agent object (alive, defeated, or itself when staying) sits on the cell
+    const int tc = terr[c];
+    if (live && inb) {
+      if (occupied) {
+        if (pen && !p.variant_1v1) ag[i * kMapE] = w | FL_COLLIDED;   // :1231-1236 (1v1 has no collided logic, :498-501)
+      } else if (!(tc == CT_OBSTACLE && !pen)) {                      // Obstacle.can_overlap()
+        const int c0 = ag_y(w) * S + ag_x(w);
+        occ[(c0 >> 5) * kMapE] &= ~(1u << (c0 & 31));
+        *ow |= bit;
+        ag[i * kMapE] = (bg_after_move(w, tc) & 0xFF000000u) | (uint32_t)nx | ((uint32_t)ny << 8) |
+                        ((uint32_t)dir_of_action(a, (int)((w >> 16) & 255u)) << 16);  // Agent.move agent.py:167-200
+      }
+    }
+  }
+  term = false; trunc = h.x >= p.max_steps;  // :1310-1311
+  rew = 0.0;
+  if (pen) {  // :1316-1332 (collided is never cleared)
+    for (int i = 0; i < n; ++i) {
+      const uint32_t w = ag[i * kMapE];
+      if (w & FL_COLLIDED) { if (i < nb) rew -= p.obstacle_penalty; ag[i * kMapE] = w | FL_DEAD; }
+    }
+  }
+  const uint32_t red_flag = (uint32_t)p.red_flag, blue_flag = (uint32_t)p.blue_flag;
+  // h.y = game_stats (ctf.py:1068-1073): bit0 blue_flag_captured, bit1 red_flag_captured, bit 8+i agent i defeated in a battle
+  for (int i = 0; i < nb; ++i) if (((ag[i * kMapE] ^ red_flag) & 0xFFFFu) == 0) { rew += p.flag_reward; term = true; h.y |= 2; }   // :1335-1344
+  // red positions two per word for the range tests; the flag test of the reds rides along (:1347-1356)
+  const int nr2 = (nr + 1) >> 1;
+  for (int j = 0; j < nr2; ++j) {
+    const uint32_t a0 = ag[(nb + 2 * j) * kMapE] & 0xFFFFu;
+    const uint32_t a1 = 2 * j + 1 < nr ? (ag[(nb + 2 * j + 1) * kMapE] & 0xFFFFu) : a0;
+    if (a0 == blue_flag || (2 * j + 1 < nr && a1 == blue_flag)) { term = true; h.y |= 1; }
+    if (a0 == blue_flag) rew -= p.flag_reward;
+    if (2 * j + 1 < nr && a1 == blue_flag) rew -= p.flag_reward;
+    pr[j * kMapE] = a0 | (a1 << 16);
+  }
+  const uint32_t row_valid = (1u << nr) - 1u;
+  int nbattle = 0;
+  bool all_dead = true;
+  for (int b = 0; b < nb; ++b) {  // np.where(distances <= battle_range): row-major, blue-major (:1368-1377)
+    uint32_t wb = ag[b * kMapE];
+    const uint32_t bb = (wb & 0xFFFFu) * 0x10001u;
+    uint32_t row = 0;   // bit q: red q within battle range of blue b
+    for (int j = 0; j < nr2; ++j) {
+      const uint32_t d = __vabsdiffu4(bb, pr[j * kMapE]);   // |dx0| |dy0| |dx1| |dy1|
+      const int d2a = (int)__dp4a(d, d & 0x0000FFFFu, 0u), d2b = (int)__dp4a(d, d & 0xFFFF0000u, 0u);
+      // == (np.linalg.norm(int vector) <= battle_range), see MapParams::d2_max
+      row |= ((d2a <= p.d2_max ? 1u : 0u) | (d2b <= p.d2_max ? 2u : 0u)) << (2 * j);
+    }
+    row &= row_valid;
+    while (row) {
+      const int q = __ffs((int)row) - 1;
+      row &= row - 1;
+      const uint32_t wr = ag[(nb + q) * kMapE];
+      if ((wb | wr) & FL_DEAD) continue;               // :1380-1383
+      const int cb = terr[ag_y(wb) * S + ag_x(wb)], cr = terr[ag_y(wr) * S + ag_x(wr)];
+      const bool bh = (cb == CT_BLUE_TERR || cb == CT_BLUE_FLAG), rh = (cr == CT_RED_TERR || cr == CT_RED_FLAG);
+      bool blue_win;
+      if (MODE == 0) {
+        blue_win = nbattle < p.KB ? p.blue_win[e * p.KB + nbattle] != 0 : false;
+        if (nbattle >= p.KB) err |= MG_ERR_TRACE_OVERFLOW;
+      } else {  // :1392-1407; (double)u / 2^32 < p  <=>  u < ceil(p * 2^32)
+        const unsigned long long thr = (bh && !rh) ? p.thr_blue_home : ((!bh && rh) ? p.thr_red_home : p.thr_even);
+        blue_win = (unsigned long long)r.u32() < thr;
+      }
+      ++nbattle;
+      if (blue_win) { rew += p.battle_reward; ag[(nb + q) * kMapE] = wr | FL_DEAD; h.y |= 1 << (8 + nb + q); }   // :1409-1418
+      else if (p.variant_1v1) { rew -= p.battle_reward; term = true; h.y |= 1 << 8; }  // 1v1: losing ends the episode (ctf.py:629-636)
+      else { rew -= p.battle_reward; wb |= FL_DEAD; ag[b * kMapE] = wb; h.y |= 1 << (8 + b); }
+    }
+    all_dead &= (wb & FL_DEAD) != 0;
+  }
+  if (MODE == 0 && p.battles_used) p.battles_used[e] = nbattle;
+  if (all_dead) term = true;           // :1423
+  rew = __dsub_rn(rew, __dmul_rn(p.step_penalty, (double)nb));  // :1428 -- two roundings like the reference, never an FMA
+}
+
 // The same step for the compile-time team sizes with every agent word in a REGISTER: the order-dependent loop picks and
 // updates "agent order[k]" with select chains instead of dynamically indexed shared memory, the body is branch-free
 // (one commit per agent), and occupancy / flag / battle tests run on registers.  Statement for statement the semantics of
@@ -355,11 +493,11 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
 // waves of tiles keep every SM full (>= 256 K envs); 1 (no cap, no spills) has the shorter dependent chain and wins for
 // launches of a wave or two, which are latency-bound.
 // STEPV: which CtF step body the kernel carries - 0 the general one (run-time team sizes), 1 the 2v2 and 2 the 1v1 register
-// bodies.  One body per kernel keeps the instruction stream of the hot path inside the instruction cache (with all of them
+// bodies, 3 the general one with the occupancy bitmap (maps of <= 256 cells).  One body per kernel keeps the instruction stream of the hot path inside the instruction cache (with all of them
 // inlined into one kernel `no_instruction` became the top stall reason).
 // LEAN: the kernel of ONE hot configuration with everything else compiled out (the general kernel is ~6 500 SASS instructions of
 // which a step of the common case executes ~1 000: `no_instruction` stalls).  1 = step (op 1) of a CtF handle with the staged u8
-// tile image, obs given, no final_obs; 2 = step of a Maze handle in partial-view mode computed from the padded map (no memoised
+// tile image, obs given, no final_obs (the 2v2 register body, or the general body with the occupancy bitmap); 2 = step of a Maze handle in partial-view mode computed from the padded map (no memoised
 // table), obs given, no final_obs.  The launcher checks those conditions; 0 = the general kernel.
 template <int FAMILY, int MODE, int MINB, int STEPV = 0, int LEAN = 0>
 __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
@@ -372,7 +510,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   const int head = view_table ? 0 : (view_mode ? p.map_padded_bytes : p.L);
   uint8_t* s_period = smem_raw;                                                     // [L], or the padded packed map in view mode
   uint32_t* s_ag = reinterpret_cast<uint32_t*>(smem_raw + head);                    // [n][kMapE] agent words, transposed
-  uint8_t* s_obs = smem_raw + head + (size_t)n * kMapE * 4;                         // [kMapE][cells] (staged tiles) / the tile's views
+  uint32_t* s_occ = reinterpret_cast<uint32_t*>(smem_raw + head + (size_t)n * kMapE * 4);   // STEPV 3: occupancy bitmap + packed red pairs
+  uint8_t* s_obs = smem_raw + head + (size_t)n * kMapE * 4 + (STEPV == 3 ? kOccBytes : 0);  // [kMapE][cells] (staged tiles) / the tile's views
   const long long e0 = (long long)blockIdx.x * kMapE;
   const int n_here = (int)min((long long)kMapE, p.N - e0);
   const long long e = e0 + tid;
@@ -437,6 +576,8 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
       else if (STEPV == 1) ctf_step_regs<MODE, 2, 2>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (STEPV == 2) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
+      else if (STEPV == 3 && n <= 8) ctf_step_occ<MODE, uint32_t>(p, e, p.actions + e * p.nb, s_period, ag, s_occ + tid, h, r, rew, term, trunc, err);
+      else if (STEPV == 3) ctf_step_occ<MODE, unsigned long long>(p, e, p.actions + e * p.nb, s_period, ag, s_occ + tid, h, r, rew, term, trunc, err);
       else if (n <= 8) ctf_step_one<MODE, uint32_t, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       else ctf_step_one<MODE, unsigned long long, 0, 0>(p, e, p.actions + e * p.nb, s_period, ag, h, r, rew, term, trunc, err);
       p.rewards[e] = rew; p.terminated[e] = term; p.truncated[e] = trunc;
@@ -781,12 +922,17 @@ cudaError_t configure_map_view_mode(size_t smem) {
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 8, 0, 2>, (size_t)smem)) != cudaSuccess) return e;
   return raise_smem_limit((const void*)map_kernel<MG_FAMILY_MAZE, 1, 8>, (size_t)smem);
 }
-size_t map_smem_bytes(int L, int n, int cells, int obs_dtype) {
-  size_t extra = 0;
-  if (map_obs_staged(cells, obs_dtype)) extra = (size_t)kMapE * cells;
+// the general CtF body of small maps keeps an occupancy bitmap per env (STEPV 3)
+bool map_ctf_occ(int family, int nb, int nr, int cells) {
+  static const bool off = [] { const char* v = std::getenv("MG_CTF_NO_OCC"); return v && v[0] == '1'; }();
+  return !off && family == MG_FAMILY_CTF && cells <= 32 * kOccWords && !(nb == 2 && nr == 2) && !(nb == 1 && nr == 1);
+}
+size_t map_smem_bytes(int L, int n, int cells, int obs_dtype, bool occ) {
+  size_t extra = occ ? (size_t)kOccBytes : 0;
+  if (map_obs_staged(cells, obs_dtype)) extra += (size_t)kMapE * cells;
   else if (map_obs_tma(L, cells, obs_dtype)) {
     const int reps = map_tma_reps(L, cells, obs_dtype);
-    if (obs_dtype != MG_OBS_U8 || reps > 1) extra = (size_t)L * (obs_dtype == MG_OBS_U8 ? 1 : 8) * reps;
+    if (obs_dtype != MG_OBS_U8 || reps > 1) extra += (size_t)L * (obs_dtype == MG_OBS_U8 ? 1 : 8) * reps;
   }
   return (size_t)L + (size_t)4 * kMapE * n + extra + 16;
 }
@@ -795,7 +941,7 @@ int map_tile_envs() { return kMapE; }
 template <int FAMILY, int MODE, int MINB, int STEPV, int LEAN = 0>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.view_table ? 0 : p.map_padded_bytes, p.view_V)
-                                                               : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype);
+                                                               : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype, STEPV == 3);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)((p.N + kMapE - 1) / kMapE)); cfg.blockDim = dim3(kMapE);
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -818,9 +964,11 @@ static cudaError_t configure_pair(int smem) {
   return raise_smem_limit((const void*)map_kernel<FAMILY, MODE, 8, STEPV>, (size_t)smem);
 }
 
-cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
-  const int smem = (int)map_smem_bytes(L, n, cells, obs_dtype);
+cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype, bool occ) {
+  const int smem = (int)map_smem_bytes(L, n, cells, obs_dtype, occ);
   cudaError_t e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 0, 3>(smem)) != cudaSuccess) return e;
+  if ((e = configure_pair<MG_FAMILY_CTF, 1, 3>(smem)) != cudaSuccess) return e;
   if ((e = configure_pair<MG_FAMILY_MAZE, 0, 0>(smem)) != cudaSuccess) return e;
   if ((e = configure_pair<MG_FAMILY_MAZE, 1, 0>(smem)) != cudaSuccess) return e;
   if ((e = configure_pair<MG_FAMILY_CTF, 0, 0>(smem)) != cudaSuccess) return e;
@@ -830,6 +978,8 @@ cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype) {
   if ((e = configure_pair<MG_FAMILY_CTF, 1, 1>(smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 3, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 3, 1>, (size_t)smem)) != cudaSuccess) return e;
   return configure_pair<MG_FAMILY_CTF, 1, 2>(smem);
 }
 
@@ -844,9 +994,9 @@ static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
   // Maze partial-view mode is issue-bound: as soon as the uncapped allocation (5 CTAs per SM) would need a second wave
   // (148 * 5 * 128 envs) the 8-CTA one wins (131 072 envs: 11.3 -> 10.1 us); the other modes switch at 256 K envs
   const long long from = (FAMILY == MG_FAMILY_MAZE && p.view_V && !std::getenv("MG_MAP_MINB8_FROM")) ? 148ll * 5 * kMapE + 1 : minb8_from();
-  if constexpr (MODE == 1 && ((FAMILY == MG_FAMILY_CTF && STEPV == 1) || FAMILY == MG_FAMILY_MAZE)) {   // the hot configurations have kernels of their own
+  if constexpr (MODE == 1 && ((FAMILY == MG_FAMILY_CTF && (STEPV == 1 || STEPV == 3)) || FAMILY == MG_FAMILY_MAZE)) {   // the hot configurations have kernels of their own
     constexpr int LEAN = FAMILY == MG_FAMILY_CTF ? 1 : 2;
-    const bool fits = FAMILY == MG_FAMILY_CTF ? (p.obs_staged && p.obs_tile && p.row_bytes == 16) : (p.view_V && !p.view_table && p.row_bytes == 4);
+    const bool fits = FAMILY == MG_FAMILY_CTF ? (p.obs_staged && p.obs_tile && (STEPV == 3 || p.row_bytes == 16)) : (p.view_V && !p.view_table && p.row_bytes == 4);
     if (map_lean_enabled() && p.op == 1 && p.obs && !p.final_obs && fits)
       return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN>(p, st);
   }
@@ -857,6 +1007,7 @@ template <int MODE>
 static cudaError_t launch_ctf(const MapParams& p, cudaStream_t st) {
   if (p.nb == 2 && p.nr == 2) return launch_by_size<MG_FAMILY_CTF, MODE, 1>(p, st);
   if (p.nb == 1 && p.nr == 1) return launch_by_size<MG_FAMILY_CTF, MODE, 2>(p, st);
+  if (map_ctf_occ(p.family, p.nb, p.nr, p.cells)) return launch_by_size<MG_FAMILY_CTF, MODE, 3>(p, st);
   return launch_by_size<MG_FAMILY_CTF, MODE, 0>(p, st);
 }
 

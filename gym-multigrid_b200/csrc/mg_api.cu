@@ -36,8 +36,9 @@ cudaError_t configure_kernels(int v, int cells, int A);
 size_t tile_smem(int v, int cells, int A);
 struct MapParams;
 cudaError_t launch_map(const MapParams& p, cudaStream_t st);
-cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype);
-size_t map_smem_bytes(int L, int n, int cells, int obs_dtype);
+cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype, bool occ);
+size_t map_smem_bytes(int L, int n, int cells, int obs_dtype, bool occ);
+bool map_ctf_occ(int family, int nb, int nr, int cells);
 bool map_obs_staged(int cells, int obs_dtype);
 bool map_obs_tma(int L, int cells, int obs_dtype);
 int map_tma_reps(int L, int cells, int obs_dtype);
@@ -418,9 +419,10 @@ extern "C" int mg_create_map(const mg_map_config* cfg, int device, mg_env** out)
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, "cudaGetDeviceProperties", ce);
   if (prop.major != 10) return fail(nullptr, "mg_create_map: kernels are built for sm_100a only");
-  if (mg::map_smem_bytes((int)L, n, cells, cfg->obs_dtype) > (size_t)prop.sharedMemPerBlockOptin)
+  const bool occ = mg::map_ctf_occ(cfg->family, nb, nr, cells);
+  if (mg::map_smem_bytes((int)L, n, cells, cfg->obs_dtype, occ) > (size_t)prop.sharedMemPerBlockOptin)
     return fail(nullptr, "mg_create_map: map too large: lcm(size*size, 16) bytes must fit in shared memory");
-  if ((ce = mg::configure_map_kernels((int)L, n, cells, cfg->obs_dtype)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
+  if ((ce = mg::configure_map_kernels((int)L, n, cells, cfg->obs_dtype, occ)) != cudaSuccess) return cuda_fail(nullptr, "cudaFuncSetAttribute", ce);
 
   mg_env* env = new (std::nothrow) mg_env();
   if (!env) return fail(nullptr, "mg_create_map: out of host memory");

@@ -117,7 +117,8 @@ def test_maze_philox_matches_oracle(stem, n, pen, cuda_device):
     env.close()
 
 
-@pytest.mark.parametrize("nb,nr,n,pen", [(2, 2, 2000, 0.0), (3, 4, 515, 0.0), (2, 2, 300, 0.5), (8, 8, 200, 0.0)])
+@pytest.mark.parametrize("nb,nr,n,pen", [(2, 2, 2000, 0.0), (3, 4, 515, 0.0), (2, 2, 300, 0.5), (8, 8, 200, 0.0),
+                                         (8, 8, 260, 0.5), (1, 3, 300, 0.25), (7, 9, 150, 0.0), (5, 2, 129, 0.5)])
 def test_ctf_philox_matches_oracle(nb, nr, n, pen, cuda_device):
     import gym_multigrid_b200 as mg
     g = load_golden("ctf_2v2")
