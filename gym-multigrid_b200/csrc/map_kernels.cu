@@ -22,6 +22,7 @@
 #include "smem_config.h"
 #include "map_params.cuh"
 #include "view_device.cuh"
+#include "policy_device.cuh"
 
 namespace mg {
 
@@ -355,11 +356,66 @@ __device__ __forceinline__ void ctf_step_occ(const MapParams& p, long long e, co
   rew = __dsub_rn(rew, __dmul_rn(p.step_penalty, (double)nb));  // :1428 -- two roundings like the reference, never an FMA
 }
 
+// The scripted opponents of policy_kernels.cu decided inside the step kernel (mg_set_red_policy_fusion), on the agent words the
+// step has just loaded: statement for statement ctf_policy_kernel (Philox draws; the validation trace keeps the separate kernel),
+// for compile-time team sizes.  `w` = the PRE-step agent words, `h` the pre-step header.  Returns the red actions one byte each
+// and writes them where mg_red_policy_actions would.
+template <int NB, int NR>
+__device__ __forceinline__ uint32_t policy_red_actions(const MapParams& p, long long e, const uint32_t* w, const int4& h) {
+  PolicyRng r;
+  r.open(p.seed, p.env_id_base + (unsigned long long)e, h.x, h.w);
+  const int S = p.S;
+  bool intruder = false;   // "a blue agent stands on red ground", shared by every red agent of the env
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int code = __ldg(p.field_map + (w[i] & 255u) * S + ((w[i] >> 8) & 255u));
+    intruder |= code == CT_RED_TERR || code == CT_RED_FLAG;   // observation["red_territory"] = red territory cells + the red flag (ctf.py:765-769)
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const int kind = p.pol_kind[k];
+    int a;
+    if (kind == MG_POLICY_RW) {
+      a = r.below(5);
+    } else {
+      const uint32_t me = w[NB + k];
+      const int x = me & 255u, y = (me >> 8) & 255u, cell = x * S + y;
+      int target;
+      if (kind == MG_POLICY_CAPTURE) {
+        target = (p.blue_flag & 255) * S + (p.blue_flag >> 8);
+      } else if (kind == MG_POLICY_FIGHT || (kind == MG_POLICY_PATROL_FIGHT && intruder)) {
+        int best = 0x7fffffff;
+        target = cell;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {   // the closest blue agent, first of equals, defeated ones included (heuristic.py:216-226)
+          const int bx = w[i] & 255u, by = (w[i] >> 8) & 255u, dx = bx - x, dy = by - y, d2 = dx * dx + dy * dy;
+          if (d2 < best) { best = d2; target = bx * S + by; }
+        }
+      } else if (__ldg(p.pol_border + cell)) {
+        target = (int)__ldg(p.pol_along + r.below(p.pol_n_along));
+      } else {
+        target = __ldg(p.pol_goal + cell);
+      }
+      const int mv = __ldg(p.pol_first_move + (size_t)cell * p.cells + target);
+      const bool follow = (unsigned long long)r.u32() < p.pol_thr[k];
+      a = mv;
+      if (!follow) a = r.below(5);
+    }
+    out |= (uint32_t)a << (8 * k);
+  }
+  if (NR == 2) { p.pol_out[e * 2] = (int8_t)(out & 255u); p.pol_out[e * 2 + 1] = (int8_t)(out >> 8); }
+  else
+#pragma unroll
+    for (int k = 0; k < NR; ++k) p.pol_out[e * NR + k] = (int8_t)((out >> (8 * k)) & 255u);
+  return out;
+}
+
 // The same step for the compile-time team sizes with every agent word in a REGISTER: the order-dependent loop picks and
 // updates "agent order[k]" with select chains instead of dynamically indexed shared memory, the body is branch-free
 // (one commit per agent), and occupancy / flag / battle tests run on registers.  Statement for statement the semantics of
 // ctf_step_one above (which stays the general path for run-time team sizes); tested against it through the oracle.
-template <int MODE, int NB, int NR>
+template <int MODE, int NB, int NR, int POL = 0>
 __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, uint32_t blue_raw, const uint8_t* terr,
                                               uint32_t* ag, int4& h, Rng<MODE>& r, double& rew, bool& term, bool& trunc,
                                               int& err) {
@@ -368,6 +424,8 @@ __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, u
   uint32_t w[n];
 #pragma unroll
   for (int i = 0; i < n; ++i) w[i] = ag[i * kMapE];
+  uint32_t red_raw = 0;   // POL: the scripted opponents decide on the pre-step state (the reference calls them first, ctf.py:1297-1301)
+  if (POL) red_raw = policy_red_actions<NB, NR>(p, e, w, h);
   h.x += 1;  // ctf.py:1295
   uint32_t acts = 0, order;
 #pragma unroll
@@ -379,7 +437,7 @@ __device__ __forceinline__ void ctf_step_regs(const MapParams& p, long long e, u
   }
 #pragma unroll
   for (int k = 0; k < NR; ++k) {  // RwPolicy.act for EVERY red agent, defeated or not (:1297-1301), or the external enemy policy
-    const int a = (MODE == 0 || p.red_actions) ? p.red_actions[e * NR + k] : below16(r, 5);
+    const int a = POL ? (int)((red_raw >> (8 * k)) & 255u) : ((MODE == 0 || p.red_actions) ? p.red_actions[e * NR + k] : below16(r, 5));
     const bool bad = a < 0 || a > 4;
     if (bad) err |= MG_ERR_BAD_ACTION;
     acts |= (uint32_t)(bad ? 15 : a) << (4 * (NB + k));
@@ -499,7 +557,8 @@ __device__ __forceinline__ void put_obs(const MapParams& p, void* base, long lon
 // which a step of the common case executes ~1 000: `no_instruction` stalls).  1 = step (op 1) of a CtF handle with the staged u8
 // tile image, obs given, no final_obs (the 2v2 register body, or the general body with the occupancy bitmap); 2 = step of a Maze handle in partial-view mode computed from the padded map (no memoised
 // table), obs given, no final_obs.  The launcher checks those conditions; 0 = the general kernel.
-template <int FAMILY, int MODE, int MINB, int STEPV = 0, int LEAN = 0>
+// POL: (2v2 lean kernel only) the scripted opponents' decisions are part of the step (policy_red_actions above).
+template <int FAMILY, int MODE, int MINB, int STEPV = 0, int LEAN = 0, int POL = 0>
 __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant__ MapParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar, bar_tile;
@@ -574,7 +633,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
     } else {
       double rew; bool term, trunc;
       if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
-      else if (STEPV == 1) ctf_step_regs<MODE, 2, 2>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
+      else if (STEPV == 1) ctf_step_regs<MODE, 2, 2, POL>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (STEPV == 2) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (STEPV == 3 && n <= 8) ctf_step_occ<MODE, uint32_t>(p, e, p.actions + e * p.nb, s_period, ag, s_occ + tid, h, r, rew, term, trunc, err);
       else if (STEPV == 3) ctf_step_occ<MODE, unsigned long long>(p, e, p.actions + e * p.nb, s_period, ag, s_occ + tid, h, r, rew, term, trunc, err);
@@ -938,7 +997,7 @@ size_t map_smem_bytes(int L, int n, int cells, int obs_dtype, bool occ) {
 }
 int map_tile_envs() { return kMapE; }
 
-template <int FAMILY, int MODE, int MINB, int STEPV, int LEAN = 0>
+template <int FAMILY, int MODE, int MINB, int STEPV, int LEAN = 0, int POL = 0>
 static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   const size_t smem = (p.family == MG_FAMILY_MAZE && p.view_V) ? map_view_smem_bytes(p.view_table ? 0 : p.map_padded_bytes, p.view_V)
                                                                : map_smem_bytes(p.L, p.n, p.cells, p.obs_dtype, STEPV == 3);
@@ -949,7 +1008,7 @@ static cudaError_t launch_one(const MapParams& p, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = map_pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB, STEPV, LEAN>, p);
+  return cudaLaunchKernelEx(&cfg, map_kernel<FAMILY, MODE, MINB, STEPV, LEAN, POL>, p);
 }
 
 static bool map_lean_enabled() {
@@ -978,6 +1037,8 @@ cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype, bool o
   if ((e = configure_pair<MG_FAMILY_CTF, 1, 1>(smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 3, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 3, 1>, (size_t)smem)) != cudaSuccess) return e;
   return configure_pair<MG_FAMILY_CTF, 1, 2>(smem);
@@ -997,9 +1058,14 @@ static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
   if constexpr (MODE == 1 && ((FAMILY == MG_FAMILY_CTF && (STEPV == 1 || STEPV == 3)) || FAMILY == MG_FAMILY_MAZE)) {   // the hot configurations have kernels of their own
     constexpr int LEAN = FAMILY == MG_FAMILY_CTF ? 1 : 2;
     const bool fits = FAMILY == MG_FAMILY_CTF ? (p.obs_staged && p.obs_tile && (STEPV == 3 || p.row_bytes == 16)) : (p.view_V && !p.view_table && p.row_bytes == 4);
-    if (map_lean_enabled() && p.op == 1 && p.obs && !p.final_obs && fits)
+    if (map_lean_enabled() && p.op == 1 && p.obs && !p.final_obs && fits) {
+      if constexpr (FAMILY == MG_FAMILY_CTF && STEPV == 1) {
+        if (p.pol_on) return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN, 1>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN, 1>(p, st);
+      }
       return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN>(p, st);
+    }
   }
+  if (p.pol_on) return cudaErrorInvalidValue;   // map_can_fuse_policy said no: the caller launches ctf_policy_kernel itself
   return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV>(p, st) : launch_one<FAMILY, MODE, 1, STEPV>(p, st);
 }
 
@@ -1009,6 +1075,13 @@ static cudaError_t launch_ctf(const MapParams& p, cudaStream_t st) {
   if (p.nb == 1 && p.nr == 1) return launch_by_size<MG_FAMILY_CTF, MODE, 2>(p, st);
   if (map_ctf_occ(p.family, p.nb, p.nr, p.cells)) return launch_by_size<MG_FAMILY_CTF, MODE, 3>(p, st);
   return launch_by_size<MG_FAMILY_CTF, MODE, 0>(p, st);
+}
+
+// mg_set_red_policy_fusion: can this launch carry the opponents' decisions (the 2v2 lean step kernel), or does the caller run
+// ctf_policy_kernel ahead of it?
+bool map_can_fuse_policy(const MapParams& p) {
+  return map_lean_enabled() && p.family == MG_FAMILY_CTF && p.rng_mode == 1 && p.nb == 2 && p.nr == 2 && !p.variant_1v1 && p.op == 1 &&
+         p.obs && !p.final_obs && p.obs_staged && p.obs_tile && p.row_bytes == 16;
 }
 
 cudaError_t launch_map(const MapParams& p, cudaStream_t st) {

@@ -50,6 +50,12 @@ struct MapParams {
   const int8_t* red_actions; const uint8_t* order; const uint8_t* blue_win; int KB; int32_t* battles_used;
   int32_t* status;
   int op;  // 0 = reset(mask), 1 = step
+  // scripted opponents decided inside the step kernel (mg_set_red_policy_fusion; the 2v2 lean kernel): the tables of
+  // policy_params.cuh, the kind / follow threshold of the two red agents, and where the decided actions are written
+  int pol_on, pol_n_along;
+  const uint8_t* pol_first_move; const uint16_t* pol_goal; const uint8_t* pol_border; const uint16_t* pol_along;
+  int pol_kind[2]; unsigned long long pol_thr[2];
+  int8_t* pol_out;
 };
 
 }  // namespace mg

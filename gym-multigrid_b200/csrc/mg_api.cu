@@ -39,6 +39,7 @@ cudaError_t launch_map(const MapParams& p, cudaStream_t st);
 cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype, bool occ);
 size_t map_smem_bytes(int L, int n, int cells, int obs_dtype, bool occ);
 bool map_ctf_occ(int family, int nb, int nr, int cells);
+bool map_can_fuse_policy(const MapParams& p);
 bool map_obs_staged(int cells, int obs_dtype);
 bool map_obs_tma(int L, int cells, int obs_dtype);
 int map_tma_reps(int L, int cells, int obs_dtype);
@@ -93,6 +94,7 @@ struct mg_env {
   uint4* d_view_table;             // Maze partial-observation mode: the memoised views of all S*S*4 agent states, or null
   mg::PolicyParams pbase;
   const int8_t* ext_red_actions;   // CtF: actions of an external enemy policy for the next steps (Philox mode), or null = RwPolicy
+  int8_t* fused_red_out;           // CtF: mg_set_red_policy_fusion - every step decides the scripted opponents' actions itself, or null
   uint8_t* d_map_tables;  // field_map | obs_period | background / territory lists
   size_t obs_elem;        // bytes per obs element
   int act_cols, rew_cols;
@@ -600,6 +602,23 @@ static int map_launch(mg_env* env, void* state, int op, const mg_step_io* io, co
   if (p.obs && !aligned16(p.obs)) return fail(env, "obs buffer must be 16-byte aligned");
   if (p.view_V && p.final_obs) return fail(env, "final_obs is not available in partial-observation mode");
   cudaError_t ce;
+  if (op == 1 && env->fused_red_out && !env->has_trace) {   // the scripted opponents decide as part of this step (mg_set_red_policy_fusion)
+    if (!env->d_policy_tables) return fail(env, "mg_step: red-policy fusion is on but no policies are set (mg_set_red_policies)");
+    p.red_actions = env->fused_red_out;
+    const mg::PolicyParams& q = env->pbase;
+    if (!env->pol_tr_follow && mg::map_can_fuse_policy(p)) {   // one launch: the 2v2 lean kernel with the policy prologue
+      p.pol_on = 1; p.pol_n_along = q.n_along;
+      p.pol_first_move = q.first_move; p.pol_goal = q.patrol_goal; p.pol_border = q.on_border; p.pol_along = q.along;
+      for (int k = 0; k < 2; ++k) { p.pol_kind[k] = q.kind[k]; p.pol_thr[k] = q.thr[k]; }
+      p.pol_out = env->fused_red_out;
+    } else {                                                   // any other configuration: the policy kernel first, same stream
+      mg::PolicyParams pp = q;
+      pp.agents = p.agents; pp.row_bytes = p.row_bytes; pp.hdr = p.hdr; pp.seed = p.seed; pp.out = env->fused_red_out;
+      pp.tr_patrol = env->pol_tr_patrol; pp.tr_follow = env->pol_tr_follow; pp.tr_action = env->pol_tr_action;
+      if ((ce = mg::launch_ctf_policy(pp, st)) != cudaSuccess) return cuda_fail(env, "ctf_policy_kernel", ce);
+      env->launches += 1;
+    }
+  }
   if ((ce = mg::launch_map(p, st)) != cudaSuccess) return cuda_fail(env, "map_kernel", ce);
   env->launches += 1;
   return 0;
@@ -620,6 +639,7 @@ extern "C" int mg_set_red_policies(mg_env* env, const mg_red_policies* t) {
   if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(env, "cudaDeviceSynchronize", ce);   // a launch may still read the old tables
   cudaFree(env->d_policy_tables);
   env->d_policy_tables = nullptr;
+  env->fused_red_out = nullptr;   // fusion is re-armed per table set
   if (!t) return 0;
   if (t->struct_size != sizeof(mg_red_policies)) return fail(env, "mg_set_red_policies: mg_red_policies size mismatch (ABI)");
   const mg::MapParams& m = env->mbase;
@@ -664,6 +684,14 @@ extern "C" int mg_set_red_policies(mg_env* env, const mg_red_policies* t) {
   p.on_border = env->d_policy_tables + o_border;
   p.along = reinterpret_cast<const uint16_t*>(env->d_policy_tables + o_along);
   env->pbase = p;
+  return 0;
+}
+
+extern "C" int mg_set_red_policy_fusion(mg_env* env, int8_t* red_actions_dev) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_red_policy_fusion: CtF family only");
+  if (red_actions_dev && !env->d_policy_tables) return fail(env, "mg_set_red_policy_fusion: no policies set (mg_set_red_policies)");
+  env->fused_red_out = red_actions_dev;
   return 0;
 }
 

@@ -15,24 +15,12 @@
 //     (4th counter word 0).  Draw order per red agent as in the reference: patrol target, follow-or-not, random action.
 #include "mg_device.cuh"
 #include "policy_params.cuh"
+#include "policy_device.cuh"
 #include "../../include/multigrid_b200.h"
 
 namespace mg {
 
 namespace {
-
-struct PolicyRng {
-  uint32_t k0, k1, id0, id1, c2, c3, buf[4];
-  int have;
-  __device__ __forceinline__ uint32_t u32() {
-    if (have == 0) {
-      philox4x32_10(id0, id1, c2, c3, k0, k1, buf);
-      ++c2; have = 4;
-    }
-    return buf[4 - have--];
-  }
-  __device__ __forceinline__ int below(int n) { return (int)__umulhi(u32(), (uint32_t)n); }
-};
 
 __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,8 +30,7 @@ __global__ void __launch_bounds__(128) ctf_policy_kernel(const PolicyParams p) {
   const int4 h = p.hdr[e];
   const unsigned long long id = p.env_id_base + (unsigned long long)e;
   PolicyRng r;
-  r.k0 = (uint32_t)p.seed; r.k1 = (uint32_t)(p.seed >> 32); r.id0 = (uint32_t)id; r.id1 = (uint32_t)(id >> 32);
-  r.c2 = (uint32_t)h.x * 16u; r.c3 = 0x80000000u | (uint32_t)h.w; r.have = 0;
+  r.open(p.seed, id, h.x, h.w);
   const int S = p.S;
   // "a blue agent stands on red ground", shared by every red agent of the env
   bool intruder = false;

@@ -379,7 +379,7 @@ class CtfVecEnv(_MapVecEnv):
     def step(self, actions):
         if not isinstance(actions, torch.Tensor):
             self._check_host_option()
-        if self._device_policies:      # one small launch ahead of the step's: red actions from the current state
+        if self._device_policies and not self._fused_policies:      # one small launch ahead of the step's: red actions from the current state
             self._check(self._lib.mg_red_policy_actions(self._h, _ptr(self.state), _ptr(self._red_buf), self._stream()))
         elif self._enemy_policies is not None:
             self._decide_red_actions()
@@ -396,7 +396,7 @@ class CtfVecEnv(_MapVecEnv):
             raise RuntimeError("step_async called again before step_wait")
         if self._host_stream is None:
             self._host_stream = torch.cuda.Stream(device=self.device)
-        if self._device_policies:
+        if self._device_policies and not self._fused_policies:
             self._host_stream.wait_stream(torch.cuda.current_stream(self.device))
             self._check(self._lib.mg_red_policy_actions(self._h, _ptr(self.state), _ptr(self._red_buf), C.c_void_p(self._host_stream.cuda_stream)))
         elif self._enemy_policies is not None:
@@ -421,7 +421,9 @@ class CtfVecEnv(_MapVecEnv):
 
     _device_policies = False
 
-    def set_enemy_policies(self, enemy_policies=None, random_generator=None, device=False):
+    _fused_policies = False
+
+    def set_enemy_policies(self, enemy_policies=None, random_generator=None, device=False, fused=True):
         """The reference's `enemy_policies` argument (ctf.py:666, 775-826) for every env of the batch: one policy for all red
         agents or a list of `num_red_agents` of them - any object with `act(observation_dict, curr_pos) -> int` (the reference's
         CtfPolicy interface; `policy/ctf/heuristic.py` has Fight / Capture / Patrol / PatrolFight).  `random_generator`,
@@ -435,7 +437,9 @@ class CtfVecEnv(_MapVecEnv):
         are turned into tables - the first move of the reference's A* route per (cell, target), the patrol targets - and a
         small kernel decides for every env before each step (`mg_set_red_policies` / `mg_red_policy_actions`).  Targets and
         routes are the reference's; the random draws (follow the route or not, random action, patrol target) come from the
-        env's Philox generator instead of numpy's, as RwPolicy's do."""
+        env's Philox generator instead of numpy's, as RwPolicy's do.  `fused=True` (default) makes the decision part of the step
+        itself (`mg_set_red_policy_fusion`: one launch for 2v2 with the u8 map observation, the policy kernel ahead of the step
+        kernel otherwise); `fused=False` keeps the explicit `mg_red_policy_actions` call before every step.  Same results."""
         from .actions import CtfActions
         from .policy.ctf.heuristic import RwPolicy
         nr = self.num_red
@@ -443,8 +447,8 @@ class CtfVecEnv(_MapVecEnv):
         if len(pols) != nr:
             raise AssertionError("len(enemy_policies) must equal num_red_agents")       # ctf.py:779
         if self._device_policies:
-            self._check(self._lib.mg_set_red_policies(self._h, None))
-            self._device_policies = False
+            self._check(self._lib.mg_set_red_policies(self._h, None))     # (switches the fusion off too)
+            self._device_policies = self._fused_policies = False
         if all(p is None or type(p) is RwPolicy for p in pols):
             self._enemy_policies = None
             self.set_red_actions(None)
@@ -461,6 +465,9 @@ class CtfVecEnv(_MapVecEnv):
             self._check(self._lib.mg_set_red_policies(self._h, C.byref(rp)))      # copies the tables during the call
             self._enemy_policies, self._device_policies, self._policy_tables = None, True, t
             self._red_buf = self.set_red_actions(torch.zeros((self.num_envs, nr), dtype=torch.int8, device=self.device))
+            if fused:
+                self._check(self._lib.mg_set_red_policy_fusion(self._h, _ptr(self._red_buf)))
+                self._fused_policies = True
             return pols
         gen = random_generator if random_generator is not None else np.random.default_rng()
         pols = [RwPolicy() if p is None else p for p in pols]

@@ -330,6 +330,14 @@ int mg_set_red_policies(mg_env* env, const mg_red_policies* tables);
  * `stay` (the reference raises there, heuristic.py:172).  first_move: [cells][cells] start-major.  No device involved. */
 int mg_astar_first_moves(const uint8_t* blocked, int32_t rows, int32_t cols, uint8_t* first_move);
 int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_dev, void* stream);
+/* Fold that launch into the step: from now on every mg_step / mg_step_host* of the handle first decides the red team's actions
+ * from the state it is given - exactly what mg_red_policy_actions(env, state, red_actions_dev, stream) on the step's stream would
+ * write, and red_actions_dev [N][num_red] int8 receives them as before - and then steps with them, as the reference's step calls
+ * its enemy policies before moving anybody (ctf.py:1297-1301).  One launch where the configuration has a fused kernel (2v2,
+ * Philox draws, staged u8 map observation, no final_obs: the policy prologue runs on the agent words the step has loaded anyway);
+ * any other configuration, and the validation trace, run ctf_policy_kernel ahead of the step kernel on the same stream.
+ * NULL = off.  mg_set_red_policies switches it off (new tables, new call). */
+int mg_set_red_policy_fusion(mg_env* env, int8_t* red_actions_dev);
 /* Validation mode of mg_red_policy_actions: replay the outputs the reference's generator produced instead of drawing from Philox -
  * per (env, red agent), all [N][num_red] on the device: the cell PatrolPolicy drew on the border (np_random.choice over the border
  * cells with a border neighbour, heuristic.py:323-334; cell index x * size + y), whether the route is followed

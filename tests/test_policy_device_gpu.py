@@ -32,7 +32,8 @@ def _policies(names, fm, randomness):
     ("ctf_2v2", ("RwPolicy", "FightPolicy"), (0.0, 0.0)),
     ("ctf_3v4", ("FightPolicy", "CapturePolicy", "PatrolPolicy", "PatrolFightPolicy"), (0.75, 1.0, 0.75, 0.25)),
 ])
-def test_device_policies_match_oracle(stem, names, randomness, cuda_device):
+@pytest.mark.parametrize("fused", [True, False])   # decided inside the step kernel (mg_set_red_policy_fusion) / by an explicit call before it
+def test_device_policies_match_oracle(stem, names, randomness, fused, cuda_device):
     import gym_multigrid_b200 as mg
     g = load_golden(stem)
     fm = g["field_map"].astype(np.float64)
@@ -40,7 +41,8 @@ def test_device_policies_match_oracle(stem, names, randomness, cuda_device):
     n, seed = 777, 5
     env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=20, seed=seed)
     o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=20)
-    env.set_enemy_policies(_policies(names, fm, randomness), device=True)
+    env.set_enemy_policies(_policies(names, fm, randomness), device=True, fused=fused)
+    assert env._fused_policies == fused
     tables = env._policy_tables
     assert tables["kind"].tolist() == [dict(RwPolicy=0, FightPolicy=1, CapturePolicy=2, PatrolPolicy=3, PatrolFightPolicy=4)[k] for k in names]
     obs, _ = env.reset()
@@ -64,6 +66,29 @@ def test_device_policies_match_oracle(stem, names, randomness, cuda_device):
     oo, *_ = o.step(np.zeros((n, nb), np.int8), oc.map_rng(mode=1, seed=seed), autoreset=True)
     assert np.array_equal(_np(obs), oo)
     env.close()
+
+
+def test_fused_policy_step_equals_two_launches_at_full_size(cuda_device):
+    """The 64-register variant of the fused kernel (batches of >= 262 144 envs) against policy kernel + step kernel."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    fm = g["field_map"].astype(np.float64)
+    n = 262144 + 77
+    envs = []
+    for fused in (True, False):
+        e = mg.make_ctf_vec(n, g["field_map"], max_steps=12, seed=3)
+        e.set_enemy_policies(_policies(("PatrolFightPolicy", "FightPolicy"), fm, (0.7, 0.85)), device=True, fused=fused)
+        envs.append(e)
+    o0, o1 = envs[0].reset()[0], envs[1].reset()[0]
+    assert torch.equal(o0, o1)
+    gen = torch.Generator(device=cuda_device).manual_seed(2)
+    for t in range(16):
+        act = torch.randint(0, 5, (n, 2), generator=gen, device=cuda_device, dtype=torch.int8)
+        a, b = envs[0].step(act), envs[1].step(act)
+        assert torch.equal(envs[0]._red_buf, envs[1]._red_buf), f"step {t}"
+        for x, y in zip(a[:4], b[:4]):
+            assert torch.equal(x, y), f"step {t}"
+    assert torch.equal(envs[0].state, envs[1].state) and envs[0].status() == 0
 
 
 def test_device_decisions_are_the_host_policies_decisions(cuda_device):

@@ -145,7 +145,7 @@ def bench_ctf_policy(args):
         e.reset()
     torch.cuda.synchronize()
     us = graph_time(ring_steps(envs, lambda b: torch.randint(0, 5, (n, nb), device="cuda:0", dtype=torch.int8)), max(2, args.reps // RING))
-    report("ctf_policy_kernel + map_kernel<ctf> 2v2 (fight, patrol_fight reds on device)", n, us, bpe_step + bpe_pol, batches=B)
+    report("map_kernel<ctf> 2v2 with the fused policy prologue (fight, patrol_fight reds decided on the device)", n, us, bpe_step + bpe_pol, batches=B)
     import ctypes as C
     ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
     us = graph_time([lambda e=e: e._check(e._lib.mg_red_policy_actions(e._h, ptr(e.state), ptr(e._red_buf), e._stream())) for e in envs], args.reps)
