@@ -62,13 +62,20 @@ __global__ void __launch_bounds__(kViewThreads) view_fast_kernel(const __grid_co
       tma_load_1d(s_src, p.map_padded, (uint32_t)p.map_padded_bytes, &bar);
     }
   }
+  // the first view's position and direction travel while the source tile loads (a tile is normally one view per thread)
+  int x_n = 0, y_n = 0, dir_n = 3;
+  auto fetch = [&](int v) {
+    const long long gv = e0 * A + v;
+    x_n = p.pos[gv * p.pos_stride]; y_n = p.pos[gv * p.pos_stride + 1];
+    dir_n = p.dirs ? (p.dirs[gv * p.dir_stride] & 3) : 3;
+  };
+  if (tid < views) fetch(tid);
   mbar_wait(&bar, 0);
 
   const int pitch = FAMILY == MG_FAMILY_COLLECT ? p.H : p.pitch;
   for (int v = tid; v < views; v += kViewThreads) {
-    const long long gv = e0 * A + v;
-    const int x = p.pos[gv * p.pos_stride], y = p.pos[gv * p.pos_stride + 1];
-    const int dir = p.dirs ? (p.dirs[gv * p.dir_stride] & 3) : 3;
+    const int x = x_n, y = y_n, dir = dir_n;
+    if (v + kViewThreads < views) fetch(v + kViewThreads);
     int x0, y0, sa, sb;
     view_geometry<V>(x, y, dir, pitch, x0, y0, sa, sb);
     const bool a_is_x = dir & 1;  // dirs 1, 3: a walks along x, b along y

@@ -145,13 +145,15 @@ def soak_ctf(rng, stats):
         picks = [classes[int(rng.integers(0, 5))] for _ in range(nr)]
         pols = [c() if c is H.RwPolicy else c(fmf, randomness=float(rng.choice([0.75, 0.3, 1.0]))) for c in picks]
         try:
-            env.set_enemy_policies(pols, device=True)
+            env.set_enemy_policies(pols, device=True, fused=bool(rng.integers(0, 4) != 0))   # inside the step kernel / explicit launch before it
         except ValueError:                        # e.g. a map whose territories do not touch: no border to patrol
             pass
         if env._device_policies:
             tables = env._policy_tables
             cfg["device_policies"] = [c.__name__ for c in picks]
+            cfg["fused_policies"] = env._fused_policies
             stats["ctf_device_policy_configs"] += 1
+            stats["ctf_fused_policy_configs"] = stats.get("ctf_fused_policy_configs", 0) + int(env._fused_policies)
     for t in range(steps):
         act = rng.integers(0, 5, size=(n, nb)).astype(np.int8)
         ra = None
