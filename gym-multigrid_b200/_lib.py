@@ -28,7 +28,7 @@ EXPORTS = [
     "mg_abi_version", "mg_create", "mg_destroy", "mg_last_error", "mg_state_bytes", "mg_obs_bytes",
     "mg_state_plane", "mg_reset", "mg_step", "mg_encode", "mg_step_host", "mg_set_trace", "mg_status",
     "mg_launch_count", "mg_debug_set_timeline", "mg_tile_envs", "mg_create_map", "mg_set_map_trace", "mg_gen_obs", "mg_toroid_obs", "mg_create_wildfire", "mg_create_generic", "mg_map_info", "mg_set_partial_obs", "mg_host_layout", "mg_set_red_actions", "mg_step_host_async", "mg_step_host_wait", "mg_render", "mg_ctf_flat_len", "mg_ctf_flat_obs", "mg_ctf_flat_obs_u8", "mg_set_seed",
-    "mg_set_red_policies", "mg_red_policy_actions", "mg_set_red_policy_fusion", "mg_astar_first_moves",
+    "mg_set_red_policies", "mg_red_policy_actions", "mg_set_red_policy_fusion", "mg_set_carry_agent_flags", "mg_astar_first_moves",
     "mg_set_policy_trace", "mg_rollout", "mg_set_host_transport", "mg_host_invalidate", "mg_host_expand_plane", "mg_delta_record_bytes", "mg_host_apply_delta", "mg_stream_idle",
 ]
 TRANSPORTS = {"full": 0, "packed": 1, "delta": 2}
@@ -155,6 +155,8 @@ def load():
     lib.mg_set_red_actions.argtypes = [C.c_void_p, C.c_void_p]
     lib.mg_set_red_policies.restype = C.c_int
     lib.mg_set_red_policies.argtypes = [C.c_void_p, C.POINTER(RedPolicies)]
+    lib.mg_set_carry_agent_flags.restype = C.c_int
+    lib.mg_set_carry_agent_flags.argtypes = [C.c_void_p, C.c_int]
     lib.mg_set_red_policy_fusion.restype = C.c_int
     lib.mg_set_red_policy_fusion.argtypes = [C.c_void_p, C.c_void_p]
     lib.mg_red_policy_actions.restype = C.c_int

@@ -68,7 +68,9 @@ __device__ __forceinline__ void reset_one(const MapParams& p, long long e, uint3
   if (FAMILY == MG_FAMILY_MAZE) {  // maze.py:202-205: agent on a random background cell, dir 3
     const int idx = MODE == 0 ? p.start_index[e] : below(r, p.n_background);
     ag[0] = (uint32_t)p.background[idx] | (3u << 16);
-  } else {  // ctf.py:1033-1048; flags 0: a fresh env instance (the reference never clears terminated/collided on reset)
+  } else {  // ctf.py:1033-1048; flags 0: a fresh env instance - or, with carry_flags, the SAME instance going on: the reference never
+            // clears terminated / collided / bg_color on reset (agent.py:97-100 are their only assignments outside step)
+    const uint32_t keep = p.carry_flags ? 0xFF000000u : 0u;
     for (int team = 0; team < 2; ++team) {
       const int k = team ? p.nr : p.nb, len = team ? p.len_red : p.len_blue, base = team ? p.nb : 0;
       const uint16_t* terr = team ? p.red_terr : p.blue_terr;
@@ -94,7 +96,7 @@ __device__ __forceinline__ void reset_one(const MapParams& p, long long e, uint3
             if (!dup) break;
           }
         }
-        ag[(base + i) * kMapE] = (uint32_t)terr[v] | (3u << 16);
+        ag[(base + i) * kMapE] = (uint32_t)terr[v] | (3u << 16) | (ag[(base + i) * kMapE] & keep);
       }
     }
   }

@@ -52,6 +52,7 @@ struct MapParams {
   int op;  // 0 = reset(mask), 1 = step
   // scripted opponents decided inside the step kernel (mg_set_red_policy_fusion; the 2v2 lean kernel): the tables of
   // policy_params.cuh, the kind / follow threshold of the two red agents, and where the decided actions are written
+  int carry_flags;   // CtF: reset keeps the agents' flag byte (mg_set_carry_agent_flags: one env instance through several episodes)
   int pol_on, pol_n_along;
   const uint8_t* pol_first_move; const uint16_t* pol_goal; const uint8_t* pol_border; const uint16_t* pol_along;
   int pol_kind[2]; unsigned long long pol_thr[2];

@@ -687,6 +687,13 @@ extern "C" int mg_set_red_policies(mg_env* env, const mg_red_policies* t) {
   return 0;
 }
 
+extern "C" int mg_set_carry_agent_flags(mg_env* env, int on) {
+  if (!env) return -1;
+  if (env->family != MG_FAMILY_CTF || env->mbase.variant_1v1) return fail(env, "mg_set_carry_agent_flags: CtFMvN handles only");
+  env->mbase.carry_flags = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int mg_set_red_policy_fusion(mg_env* env, int8_t* red_actions_dev) {
   if (!env) return -1;
   if (env->family != MG_FAMILY_CTF) return fail(env, "mg_set_red_policy_fusion: CtF family only");

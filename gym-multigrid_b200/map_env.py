@@ -324,7 +324,7 @@ class CtfVecEnv(_MapVecEnv):
     def __init__(self, num_envs, map_path, num_blue_agents=2, num_red_agents=2, battle_range=1, randomness=0.75, flag_reward=1,
                  battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
                  observation_option="map", observation_scaling=1, device="cuda:0", seed=0, autoreset=True, env_id_base=0,
-                 reference_dtypes=False, variant_1v1=False):
+                 reference_dtypes=False, variant_1v1=False, carry_agent_flags=False):
         if observation_option not in ("map", "flattened", "positional"):
             raise ValueError(f"Invalid observation_option: {observation_option}")     # ctf.py:1105-1108
         self.observation_option = observation_option
@@ -334,6 +334,8 @@ class CtfVecEnv(_MapVecEnv):
                      float(obstacle_penalty_ratio * fr), float(step_penalty_ratio * fr), float(battle_range), float(randomness),
                      max_steps, device, seed, autoreset, env_id_base, reference_dtypes, variant_1v1)
         self.num_blue_agents, self.num_red_agents = self.num_blue, self.num_red
+        if carry_agent_flags:
+            self.set_carry_agent_flags(True)
         self.single_action_space = MultiDiscrete([5] * self.num_blue)
         self.action_space = MultiDiscrete(np.full((self.num_envs, self.num_blue), 5))
         odt = np.int64 if reference_dtypes else np.uint8
@@ -403,6 +405,14 @@ class CtfVecEnv(_MapVecEnv):
             self._host_stream.synchronize()      # the previous host-path step must have landed before the state is read back
             self._decide_red_actions()
         super().step_async(actions)
+
+    def set_carry_agent_flags(self, on=True):
+        """One reference env INSTANCE per slot, stepped through several episodes: the reference's `reset()` never clears
+        `Agent.terminated` / `collided` / `bg_color` (core/agent.py:97-100 are their only assignments outside `step`),
+        so an agent defeated in one episode starts the next one defeated.  Off (default): every reset - explicit, masked, or the
+        same-step autoreset - starts a fresh instance, which is how the reference's own tests and training script use the env."""
+        self._check(self._lib.mg_set_carry_agent_flags(self._h, int(bool(on))))
+        self.carry_agent_flags = bool(on)
 
     def set_red_actions(self, red_actions=None):
         """Drive the red agents from outside (the reference's `enemy_policies`, ctf.py:666): `red_actions` int8 CUDA tensor

@@ -77,14 +77,17 @@ class CtFMvNEnv(_SingleMapEnv):
 
     def __init__(self, map_path, num_blue_agents=2, num_red_agents=2, enemy_policies=None, battle_range=1, randomness=0.75,
                  flag_reward=1, battle_reward_ratio=0.25, obstacle_penalty_ratio=0, step_penalty_ratio=0.01, max_steps=100,
-                 observation_option="positional", observation_scaling=1, render_mode="rgb_array", device="cuda:0", seed=0):
+                 observation_option="positional", observation_scaling=1, render_mode="rgb_array", device="cuda:0", seed=0,
+                 carry_agent_flags=False):
         if observation_option not in ("map", "flattened", "positional"):
             raise ValueError(f"Invalid observation_option: {observation_option}")
         kw = dict(battle_range=battle_range, randomness=randomness, flag_reward=flag_reward, battle_reward_ratio=battle_reward_ratio,
                   obstacle_penalty_ratio=obstacle_penalty_ratio, step_penalty_ratio=step_penalty_ratio, max_steps=max_steps,
                   device=device, seed=seed, autoreset=False, reference_dtypes=True)
         if self._vec_cls is CtfVecEnv:
-            kw.update(num_blue_agents=num_blue_agents, num_red_agents=num_red_agents)
+            # carry_agent_flags=True: this object behaves like ONE reference instance across reset() calls - defeated agents stay
+            # defeated, as the reference's reset never clears Agent.terminated / collided; default: a fresh one per episode
+            kw.update(num_blue_agents=num_blue_agents, num_red_agents=num_red_agents, carry_agent_flags=carry_agent_flags)
         self._wrap(self._vec_cls(1, map_path, **kw), observation_option)
         self.num_blue_agents, self.num_red_agents = self.vec.num_blue, self.vec.num_red
         self.action_space = MultiDiscrete([5] * self.vec.num_blue) if self._vec_cls is CtfVecEnv else Discrete(5)

@@ -338,6 +338,13 @@ int mg_red_policy_actions(mg_env* env, const void* state, int8_t* red_actions_de
  * any other configuration, and the validation trace, run ctf_policy_kernel ahead of the step kernel on the same stream.
  * NULL = off.  mg_set_red_policies switches it off (new tables, new call). */
 int mg_set_red_policy_fusion(mg_env* env, int8_t* red_actions_dev);
+/* CtFMvN handles: on != 0 makes every following reset (mg_reset, masked or not, and the same-step autoreset) keep each agent's
+ * flag byte - terminated, collided, background colour - instead of clearing it: ONE reference env instance stepped through several
+ * episodes.  The reference assigns Agent.terminated / collided only in Agent.__init__ and in step (core/agent.py:97-100;
+ * ctf.py:1231-1236, 1316-1332, 1409-1418) and no reset() touches them (multigrid.py:114-153, ctf.py:1050-1075), so an agent
+ * defeated in one episode starts the next one defeated (pinned by tests/golden/ctf_*_carry.npz, recorded from one
+ * reference instance per session).  Default off = every reset starts a fresh instance, which is what the reference's own tests do. */
+int mg_set_carry_agent_flags(mg_env* env, int on);
 /* Validation mode of mg_red_policy_actions: replay the outputs the reference's generator produced instead of drawing from Philox -
  * per (env, red agent), all [N][num_red] on the device: the cell PatrolPolicy drew on the border (np_random.choice over the border
  * cells with a border neighbour, heuristic.py:323-334; cell index x * size + y), whether the route is followed

@@ -192,6 +192,34 @@ def gen_ctf(only_penalty_battles=False):
               f"terminated={int(out['terminated'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
 
 
+def gen_ctf_carry():
+    """Consecutive episodes of ONE env instance: the reference's reset() keeps Agent.terminated / collided, so agents
+    defeated in an earlier episode start the next one defeated.  Sessions x episodes, episode index = session * K + k; short
+    max_steps keeps the file small and makes several resets per session."""
+    for stem, nb, nr, pen, sessions, K, max_steps in (("ctf_2v2_carry", 2, 2, 0.0, 10, 6, 30), ("ctf_3v4_penalty_carry", 3, 4, 0.5, 6, 5, 30)):
+        eps = []
+        for sidx in range(sessions):
+            acts = MovingActions(3900 + sidx) if pen else np.random.default_rng(3900 + sidx)
+            eps += rh.record_ctf_mvn_session(CTF_MAP, sidx, acts, K, nb, nr, pen, max_steps=max_steps)
+        for e in eps:
+            assert e["obs"].dtype == np.int64     # the reference's dtype (ctf.py:1138)
+            e["obs"] = e["obs"].astype(np.uint8)
+            e["init_obs"] = e["init_obs"].astype(np.uint8)
+        out = rh.pack_episodes(eps, ["actions", "red_actions", "order", "n_battles", "blue_win", "obs", "reward", "terminated",
+                                     "truncated", "pos", "dir", "dead", "collided", "info", "stats_flags", "stats_defeated"],
+                               ["field_map", "init_obs", "init_pos", "init_dir", "init_dead", "init_collided", "blue_place", "red_place",
+                                "init_info"])
+        out["field_map"] = out["field_map"][0].astype(np.uint8)
+        out["meta_num_blue"], out["meta_num_red"] = np.array(nb), np.array(nr)
+        out["meta_obstacle_penalty_ratio"] = np.array(pen)
+        out["meta_sessions"], out["meta_episodes_per_session"], out["meta_max_steps"] = np.array(sessions), np.array(K), np.array(max_steps)
+        path_out = os.path.join(OUT, stem + ".npz")
+        np.savez_compressed(path_out, **out)
+        print(f"{stem}: {sessions} sessions x {K} episodes, steps={int(out['length'].sum())}, battles={int(out['n_battles'].sum())}, "
+              f"episodes starting with a defeated agent={int(out['init_dead'].any(1).sum())}, with a collided one="
+              f"{int(out['init_collided'].any(1).sum())}, {os.path.getsize(path_out)/1024:.0f} KiB")
+
+
 def gen_ctf_render():
     """CtF episodes with the agents' sticky background colour after every step and rgb_array frames every 7th step (and at the
     end): the replay inputs of gen_ctf plus what `render()` shows.  Penalty 0.5 episodes add collided (grey) agents."""
@@ -399,7 +427,7 @@ def gen_policies():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat", "policies"]
+    which = sys.argv[1:] or ["collect", "maze", "ctf", "ctf_carry", "ctf1v1", "partial", "toroid", "generic", "generic_partial", "render", "ctf_flat", "policies"]
     if "collect" in which:
         gen_collect()
     elif "collect_variants" in which:      # only the COLLECT_VARIANTS fixtures (added in round 2; the others are unchanged)
@@ -410,6 +438,8 @@ if __name__ == "__main__":
         gen_ctf()
     elif "ctf_penalty_battles" in which:
         gen_ctf(only_penalty_battles=True)
+    if "ctf_carry" in which:               # round 2, closing pass: episodes of one env instance (flags surviving reset)
+        gen_ctf_carry()
     if "ctf1v1" in which:
         gen_ctf1v1()
     if "partial" in which:

@@ -133,6 +133,9 @@ typedef struct {
   int32_t num_blue, num_red;
   double battle_range, randomness, battle_reward;
   int32_t variant_1v1;         /* 1 = Ctf1v1Env (ctf.py:50-654): fixed order blue->red, losing a battle ends the episode */
+  int32_t carry_agent_flags;   /* 1 = one env INSTANCE stepped through several episodes: reset keeps Agent.terminated / collided /
+                                  bg_color as the reference's does (agent.py:97-100 are the only assignments outside step);
+                                  0 = every reset starts a fresh instance */
 } oc_map_cfg;
 
 typedef struct {

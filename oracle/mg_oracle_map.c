@@ -164,7 +164,8 @@ static void ctf_reset_env(const oc_map_cfg* c, uint8_t* pos, uint8_t* dir, uint8
     const int cell = i < nb ? terr_cell(c, 1, bplace[i]) : terr_cell(c, 0, rplace[i - nb]); /* ctf.py:1033-1048 */
     pos[2 * i] = (uint8_t)(cell / c->size); pos[2 * i + 1] = (uint8_t)(cell % c->size);
     dir[i] = 3;
-    flags[i] = 0; /* a FRESH env instance: the reference never clears terminated/collided in reset */
+    if (!c->carry_agent_flags) flags[i] = 0; /* a FRESH env instance; with carry_agent_flags the same instance goes on: the
+                                                reference never clears terminated / collided / bg_color in reset */
   }
   *step = 0;
 }

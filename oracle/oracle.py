@@ -245,7 +245,8 @@ class MapCfg(C.Structure):
     _fields_ = [("size", C.c_int32), ("field_map", C.c_void_p), ("flag_reward", C.c_double),
                 ("obstacle_penalty", C.c_double), ("step_penalty", C.c_double), ("max_steps", C.c_int32),
                 ("num_blue", C.c_int32), ("num_red", C.c_int32), ("battle_range", C.c_double),
-                ("randomness", C.c_double), ("battle_reward", C.c_double), ("variant_1v1", C.c_int32)]
+                ("randomness", C.c_double), ("battle_reward", C.c_double), ("variant_1v1", C.c_int32),
+                ("carry_agent_flags", C.c_int32)]
 
 
 class MapState(C.Structure):
@@ -359,12 +360,14 @@ class CtfOracle(_MapOracle):
     """CtFMvNEnv (ctf.py:657-1433) batched on the CPU; obs = `_encode_map()` (transposed) as uint8 [N, H, W]."""
 
     def __init__(self, field_map, num_envs, num_blue=2, num_red=2, battle_range=1.0, randomness=0.75, flag_reward=1.0,
-                 battle_reward_ratio=0.25, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100, variant_1v1=False):
+                 battle_reward_ratio=0.25, obstacle_penalty_ratio=0.0, step_penalty_ratio=0.01, max_steps=100, variant_1v1=False,
+                 carry_agent_flags=False):
         fr = float(flag_reward)
         super().__init__(field_map, num_envs, num_blue + num_red, flag_reward=fr, battle_reward=float(battle_reward_ratio) * fr,
                          obstacle_penalty=float(obstacle_penalty_ratio) * fr, step_penalty=float(step_penalty_ratio) * fr,
                          max_steps=max_steps, num_blue=num_blue, num_red=num_red, battle_range=float(battle_range),
-                         randomness=float(randomness), variant_1v1=int(bool(variant_1v1)))   # ctf.py:724-727
+                         randomness=float(randomness), variant_1v1=int(bool(variant_1v1)),    # ctf.py:724-727
+                         carry_agent_flags=int(bool(carry_agent_flags)))
         self.nb, self.nr = num_blue, num_red
 
     def reset(self, rng, mask=None):

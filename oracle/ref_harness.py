@@ -405,6 +405,70 @@ def record_ctf_mvn_episode(map_path, seed, action_rng, num_blue=2, num_red=2, ob
     return out
 
 
+def record_ctf_mvn_session(map_path, seed, action_rng, episodes, num_blue=2, num_red=2, obstacle_penalty_ratio=0.0, max_steps=100,
+                           max_battles=16):
+    """`episodes` consecutive episodes of ONE reference CtFMvNEnv instance (reset(seed) once, then plain reset() calls): the
+    reference's reset never clears Agent.terminated / collided / bg_color (agent.py:97-100; multigrid.py:114-153, ctf.py:1050-1075;
+    SURVEY 3.3), so from the second episode on agents defeated earlier START defeated.  Returns one dict per episode in
+    record_ctf_mvn_episode's format plus `init_dead` / `init_collided` (the flags the episode started with)."""
+    import_reference()
+    out = []
+    with tapped_generators(unseeded_entropy=880000 + seed) as log:
+        from gym_multigrid.envs.ctf import CtFMvNEnv
+        from gym_multigrid.policy.ctf.heuristic import RwPolicy
+        env = CtFMvNEnv(map_path, num_blue_agents=num_blue, num_red_agents=num_red, enemy_policies=RwPolicy(),
+                        obstacle_penalty_ratio=obstacle_penalty_ratio, max_steps=max_steps, observation_option="map")
+        for ep in range(episodes):
+            del log[:]
+            obs0, info0 = env.reset(seed=seed) if ep == 0 else env.reset()
+            place = [np.asarray(ev[1]).copy() for ev in log if ev[0] == "choice"]
+            assert len(place) == 2
+            del log[:]
+            rec = dict(actions=[], red_actions=[], order=[], n_battles=[], blue_win=[], obs=[], reward=[], terminated=[],
+                       truncated=[], pos=[], dir=[], dead=[], collided=[], info=[], stats_flags=[], stats_defeated=[])
+            d = dict(field_map=np.asarray(env._field_map).copy(), init_obs=np.asarray(obs0).copy(),
+                     init_pos=np.array([np.asarray(a.pos) for a in env.agents], np.int16),
+                     init_dir=np.array([a.dir for a in env.agents], np.int8),
+                     init_dead=np.array([a.terminated for a in env.agents], np.uint8),
+                     init_collided=np.array([a.collided for a in env.agents], np.uint8),
+                     blue_place=place[0].astype(np.int32), red_place=place[1].astype(np.int32),
+                     init_info=np.array([info0[k] for k in CTF_INFO_KEYS], np.float64))
+            while True:
+                acts = action_rng.integers(0, 5, size=num_blue)
+                obs, rew, term, trunc, info = env.step([int(a) for a in acts])
+                ints = [ev[1] for ev in log if ev[0] == "integers"]
+                shuf = [ev[1] for ev in log if ev[0] == "shuffle"]
+                wins = [bool(ev[1]) for ev in log if ev[0] == "choice"]
+                assert len(ints) == num_red and len(shuf) == 1 and len(wins) <= max_battles
+                del log[:]
+                rec["actions"].append(acts.astype(np.int8))
+                rec["red_actions"].append(np.array(ints, np.int8))
+                rec["order"].append(np.array(shuf[0], np.uint8))
+                rec["n_battles"].append(len(wins))
+                rec["blue_win"].append(np.array(wins + [False] * (max_battles - len(wins)), np.uint8))
+                rec["obs"].append(np.asarray(obs).copy())
+                rec["reward"].append(float(rew))
+                rec["terminated"].append(bool(term))
+                rec["truncated"].append(bool(trunc))
+                rec["pos"].append(np.array([np.asarray(a.pos) for a in env.agents], np.int16))
+                rec["dir"].append(np.array([a.dir for a in env.agents], np.int8))
+                rec["dead"].append(np.array([a.terminated for a in env.agents], np.uint8))
+                rec["collided"].append(np.array([a.collided for a in env.agents], np.uint8))
+                rec["info"].append(np.array([info[k] for k in CTF_INFO_KEYS], np.float64))
+                gs = env.game_stats   # ctf.py:1068-1073
+                rec["stats_flags"].append(np.array([gs["blue_flag_captured"], gs["red_flag_captured"]], np.uint8))
+                rec["stats_defeated"].append(np.array(list(gs["blue_agent_defeated"]) + list(gs["red_agent_defeated"]), np.uint8))
+                if term or trunc:
+                    break
+            d["length"] = len(rec["actions"])
+            for k, v in rec.items():
+                d[k] = np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v)
+            d["n_battles"] = d["n_battles"].astype(np.int32)
+            d["reward"] = d["reward"].astype(np.float64)
+            out.append(d)
+    return out
+
+
 # ------------------------------------------------------------------- partial-view recording
 def record_partial_views(env_id, seed, n_samples, view_sizes=(3, 5, 7)):
     """Reference partial observations (MultiGridEnv.gen_obs_grid multigrid.py:485-515 + Grid.encode_for_agents

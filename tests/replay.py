@@ -88,3 +88,29 @@ def policy_observation(field_map, blue, red, terminated=None):
             "blue_flag": np.array(list(zip(*np.where(field_map == 4)))[0]), "red_flag": np.array(list(zip(*np.where(field_map == 5)))[0]),
             "blue_territory": cells(0), "red_territory": cells(1), "obstacle": cells(6),
             "terminated_agents": np.zeros(len(blue) + len(red), np.int64) if terminated is None else np.asarray(terminated)}
+
+
+def ctf_session_schedule(g):
+    """Golden files of CONSECUTIVE episodes of one env instance (oracle/gen_golden.py gen_ctf_carry; episode index =
+    session * K + k): every session walks through its K episodes at its own pace.  Yields
+      ("reset", mask[S], ep[S])           - sessions in `mask` start episode ep[s] now (a masked reset with that episode's placements)
+      ("step", live[S], ep[S], t[S])      - step t[s] of episode ep[s] for the sessions in `live` (the others have finished all
+                                            their episodes: feed them anything valid and do not compare)."""
+    S, K = int(g["meta_sessions"]), int(g["meta_episodes_per_session"])
+    length = g["length"].reshape(S, K)
+    cur_ep, cur_t, need = np.zeros(S, np.int64), np.zeros(S, np.int64), np.ones(S, bool)
+    base = np.arange(S) * K
+    while True:
+        live = cur_ep < K
+        if not live.any():
+            return
+        ep = base + np.minimum(cur_ep, K - 1)
+        if (need & live).any():
+            yield ("reset", need & live, ep)
+            need[:] = False
+        yield ("step", live.copy(), ep, cur_t.copy())
+        cur_t[live] += 1
+        done = live & (cur_t >= length[np.arange(S), np.minimum(cur_ep, K - 1)])
+        cur_ep[done] += 1
+        cur_t[done] = 0
+        need |= done

@@ -93,6 +93,72 @@ def test_ctf_replay_bit_exact(stem, cuda_device):
     env.close()
 
 
+@pytest.mark.parametrize("stem", ["ctf_2v2_carry", "ctf_3v4_penalty_carry"])
+def test_ctf_flags_survive_reset_like_the_reference(stem, cuda_device):
+    """Consecutive episodes of ONE reference env instance per slot (`carry_agent_flags`): masked resets keep the agents'
+    terminated / collided flags, every session walks through its episodes at its own pace, k copies of every session."""
+    import gym_multigrid_b200 as mg
+    from replay import ctf_session_schedule
+    g = load_golden(stem)
+    nb, nr = int(g["meta_num_blue"]), int(g["meta_num_red"])
+    S, k = int(g["meta_sessions"]), 5
+    env = mg.make_ctf_vec(S * k, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=int(g["meta_max_steps"]),
+                          obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]), autoreset=False, carry_agent_flags=True)
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    steps = 0
+    for ev in ctf_session_schedule(g):
+        if ev[0] == "reset":
+            _, mask, ep = ev
+            m = _tile(mask, k)
+            env.set_trace(blue_place=_tile(g["blue_place"][ep], k), red_place=_tile(g["red_place"][ep], k))
+            obs, _ = env.reset(mask=torch.as_tensor(m, device=cuda_device))
+            assert np.array_equal(_np(obs)[m], _tile(g["init_obs"][ep], k)[m]) and np.array_equal(_np(env.agent_pos)[m], _tile(g["init_pos"][ep], k)[m])
+            assert np.array_equal(_np(env.agent_terminated)[m], _tile(g["init_dead"][ep], k)[m].astype(bool)), "terminated flags the episode starts with"
+            assert np.array_equal(((_np(env.agent_flags) >> 1) & 1)[m], _tile(g["init_collided"][ep], k)[m])
+            continue
+        _, lv, ep, t = ev
+        live = _tile(lv, k)
+        tr = env.set_trace(red_actions=_tile(np.where(lv[:, None], g["red_actions"][ep, t], 0).astype(np.int8), k),
+                           order=_tile(np.where(lv[:, None], g["order"][ep, t], ident).astype(np.uint8), k), blue_win=_tile(g["blue_win"][ep, t], k))
+        act = _tile(np.where(lv[:, None], g["actions"][ep, t], 0), k).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        assert np.array_equal(_np(obs)[live], _tile(g["obs"][ep, t], k)[live]), "obs"
+        assert np.array_equal(_np(rew)[live], _tile(g["reward"][ep, t], k)[live]), "reward (float64 bit-exact)"
+        assert np.array_equal(_np(term)[live], _tile(g["terminated"][ep, t], k)[live]) and np.array_equal(_np(trunc)[live], _tile(g["truncated"][ep, t], k)[live])
+        assert np.array_equal(_np(env.agent_pos)[live], _tile(g["pos"][ep, t], k)[live]) and np.array_equal(_np(env.agent_dir)[live], _tile(g["dir"][ep, t], k)[live])
+        assert np.array_equal(_np(env.agent_terminated)[live], _tile(g["dead"][ep, t], k)[live].astype(bool))
+        assert np.array_equal(((_np(env.agent_flags) >> 1) & 1)[live], _tile(g["collided"][ep, t], k)[live])
+        assert np.array_equal(_np(tr["battles_used"])[live], _tile(g["n_battles"][ep, t], k)[live])
+        steps += int(lv.sum())
+    assert steps == int(g["length"].sum()) and env.status() == 0
+    env.close()
+
+
+@pytest.mark.parametrize("carry", [False, True])
+def test_ctf_autoreset_with_carried_flags_matches_oracle(carry, cuda_device):
+    """Philox mode with same-step autoreset, short episodes: the flags of defeated agents survive (or not) the autoreset exactly as in the oracle."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    n, nb, nr = 4099, 3, 2
+    env = mg.make_ctf_vec(n, g["field_map"], num_blue_agents=nb, num_red_agents=nr, max_steps=9, seed=21, carry_agent_flags=carry, obstacle_penalty_ratio=0.25)
+    o = oc.CtfOracle(g["field_map"], n, nb, nr, max_steps=9, carry_agent_flags=carry, obstacle_penalty_ratio=0.25)
+    r = oc.map_rng(mode=1, seed=21)
+    obs, _ = env.reset()
+    assert np.array_equal(_np(obs), o.reset(r))
+    rng = np.random.default_rng(4)
+    started_dead = 0
+    for t in range(60):
+        act = rng.integers(1, 5, size=(n, nb)).astype(np.int8)
+        obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+        oo, orew, oterm, otrunc = o.step(act, r, autoreset=True)
+        assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        assert np.array_equal(_np(term), oterm) and np.array_equal(_np(trunc), otrunc)
+        assert np.array_equal(_np(env.agent_flags) & 3, o.flags & 3), f"step {t}: flags"
+        started_dead += int(((o.flags & 1).any(1) & (o.step_count == 0)).sum())
+    assert (started_dead > 0) == carry and env.status() == 0
+    env.close()
+
+
 @pytest.mark.parametrize("stem,n,pen", [("maze_board13", 1000, 0.0), ("maze_board13", 333, 0.5), ("maze_gen64", 300, 0.5)])
 def test_maze_philox_matches_oracle(stem, n, pen, cuda_device):
     import gym_multigrid_b200 as mg

@@ -57,6 +57,48 @@ def test_ctf_matches_reference(stem):
     assert o.status.value == 0
 
 
+@pytest.mark.parametrize("stem", ["ctf_2v2_carry", "ctf_3v4_penalty_carry"])
+def test_ctf_flags_survive_reset_like_the_reference(stem):
+    """Several episodes of ONE reference env instance: Agent.terminated / collided are never cleared by reset(), so an
+    agent defeated in episode k starts episode k + 1 defeated.  `carry_agent_flags` reproduces that; every session steps at its own pace."""
+    from replay import ctf_session_schedule
+    g = load_golden(stem)
+    nb, nr = int(g["meta_num_blue"]), int(g["meta_num_red"])
+    S = int(g["meta_sessions"])
+    assert g["init_dead"].any(1).sum() > S, "the fixture must hold episodes that START with a defeated agent"
+    o = oc.CtfOracle(g["field_map"], S, nb, nr, obstacle_penalty_ratio=float(g["meta_obstacle_penalty_ratio"]),
+                     max_steps=int(g["meta_max_steps"]), carry_agent_flags=True)
+    ident = np.arange(nb + nr, dtype=np.uint8)[None]
+    steps = 0
+    for ev in ctf_session_schedule(g):
+        if ev[0] == "reset":
+            _, mask, ep = ev
+            obs = o.reset(oc.map_rng(mode=0, blue_place=g["blue_place"][ep], red_place=g["red_place"][ep]), mask=mask)
+            assert np.array_equal(obs[mask], g["init_obs"][ep][mask]) and np.array_equal(o.pos[mask], g["init_pos"][ep][mask])
+            assert np.array_equal((o.flags & 1)[mask], g["init_dead"][ep][mask]), "terminated flags the episode starts with"
+            assert np.array_equal(((o.flags >> 1) & 1)[mask], g["init_collided"][ep][mask])
+            assert np.array_equal(o.info()[mask], g["init_info"][ep][mask])
+            continue
+        _, live, ep, t = ev
+        used = np.zeros(S, np.int32)
+        r = oc.map_rng(mode=0, red_actions=np.where(live[:, None], g["red_actions"][ep, t], 0).astype(np.int8),
+                       order=np.where(live[:, None], g["order"][ep, t], ident).astype(np.uint8), blue_win=g["blue_win"][ep, t], battles_used=used)
+        obs, rew, term, trunc = o.step(np.where(live[:, None], g["actions"][ep, t], 0), r)
+        assert np.array_equal(obs[live], g["obs"][ep, t][live]), "obs"
+        assert np.array_equal(rew[live], g["reward"][ep, t][live]), "reward (float64, bit-exact)"
+        assert np.array_equal(term[live], g["terminated"][ep, t][live]) and np.array_equal(trunc[live], g["truncated"][ep, t][live])
+        assert np.array_equal(o.pos[live], g["pos"][ep, t][live]) and np.array_equal(o.dir[live], g["dir"][ep, t][live])
+        assert np.array_equal((o.flags & 1)[live], g["dead"][ep, t][live]) and np.array_equal(((o.flags >> 1) & 1)[live], g["collided"][ep, t][live])
+        assert np.array_equal(used[live], g["n_battles"][ep, t][live])
+        assert np.array_equal(o.info()[live], g["info"][ep, t][live])
+        gf, gd = o.game_stats()
+        assert np.array_equal(gf[live], g["stats_flags"][ep, t][live]) and np.array_equal(gd[live], g["stats_defeated"][ep, t][live])
+        steps += int(live.sum())
+    assert steps == int(g["length"].sum()) and o.status.value == 0
+    # and without the flag the second episode of some session already differs: the fixture is not satisfiable by fresh instances
+    assert g["init_dead"].reshape(S, -1)[:, 1:].any()
+
+
 def test_map_philox_mode_shard_invariant():
     g = load_golden("ctf_3v4")
     acts = np.random.default_rng(0).integers(0, 5, size=(40, 48, 3)).astype(np.int8)
