@@ -596,6 +596,18 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   // ---- the env's agent row (padded to row_bytes = 4 * 2^k) and header; state planes are padded to whole tiles
   uint32_t* ag = s_ag + tid;
   const uint8_t* row = p.agents + e * p.row_bytes;
+  // every global load that does not depend on another is issued here, ahead of the first shared-memory store of a loaded value:
+  // issue is in order, so a store waiting for its row would hold the header / action loads back by one memory latency
+  int maze_act = 0;
+  if (FAMILY == MG_FAMILY_MAZE && (LEAN == 2 || p.op == 1) && tid < n_here) maze_act = p.actions[e];
+  int4 h = p.hdr[e];
+  uint32_t blue_raw = 0;   // 2v2 / 1v1 step: the blue actions travel with the state loads, ahead of the wait for the staged period
+  if (FAMILY == MG_FAMILY_CTF && (LEAN || p.op == 1) && tid < n_here) {
+    if (STEPV == 1)
+      blue_raw = (reinterpret_cast<uintptr_t>(p.actions) & 1) ? ((uint32_t)(uint8_t)p.actions[e * 2] | ((uint32_t)(uint8_t)p.actions[e * 2 + 1] << 8))
+                                                                : *reinterpret_cast<const uint16_t*>(p.actions + e * 2);
+    else if (STEPV == 2) blue_raw = (uint8_t)p.actions[e];
+  }
   if (LEAN == 1 && STEPV == 1) {   // 2v2: the row is one 16-byte word
     const uint4 v = *reinterpret_cast<const uint4*>(row);
     ag[0] = v.x; ag[kMapE] = v.y; ag[2 * kMapE] = v.z; ag[3 * kMapE] = v.w;
@@ -615,14 +627,6 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
   } else {
     ag[0] = *reinterpret_cast<const uint32_t*>(row);
   }
-  int4 h = p.hdr[e];
-  uint32_t blue_raw = 0;   // 2v2 / 1v1 step: the blue actions travel with the state loads, ahead of the wait for the staged period
-  if (FAMILY == MG_FAMILY_CTF && (LEAN || p.op == 1) && tid < n_here) {
-    if (STEPV == 1)
-      blue_raw = (reinterpret_cast<uintptr_t>(p.actions) & 1) ? ((uint32_t)(uint8_t)p.actions[e * 2] | ((uint32_t)(uint8_t)p.actions[e * 2 + 1] << 8))
-                                                                : *reinterpret_cast<const uint16_t*>(p.actions + e * 2);
-    else if (STEPV == 2) blue_raw = (uint8_t)p.actions[e];
-  }
   bool done = false, want_reset = false;
   int err = 0;
   Rng<MODE> r;
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(kMapE, MINB) map_kernel(const __grid_constant_
       want_reset = !p.reset_mask || p.reset_mask[e];
     } else {
       double rew; bool term, trunc;
-      if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, p.actions[e], w, h, rew, term, trunc, err); ag[0] = w; }
+      if (FAMILY == MG_FAMILY_MAZE) { uint32_t w = ag[0]; maze_step_one(p, maze_act, w, h, rew, term, trunc, err); ag[0] = w; }
       else if (STEPV == 1) ctf_step_regs<MODE, 2, 2, POL>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (STEPV == 2) ctf_step_regs<MODE, 1, 1>(p, e, blue_raw, s_period, ag, h, r, rew, term, trunc, err);
       else if (STEPV == 3 && n <= 8) ctf_step_occ<MODE, uint32_t>(p, e, p.actions + e * p.nb, s_period, ag, s_occ + tid, h, r, rew, term, trunc, err);
