@@ -409,7 +409,10 @@ def run_ours(args):
     # the caller enqueues the others); ONE from four GPUs up - there a rank has 4 cores, the eight ranks' observation mirrors (8 x 19.6 MB)
     # no longer fit the host's caches, and a second batch in flight per rank only doubles that working set (measured on 8 GPUs:
     # 8.4e8 env-steps/s with one batch in flight against 5.2-6.2e8 with two, tools/dev/e2e_multi8.sh)
-    EB = min(B, args.e2e_batches if args.e2e_batches > 0 else (3 if world <= 2 else 1))
+    # measured on this pool's boxes (16 / 24 / 32 / 32 vCPUs for 1 / 2 / 4 / 8 GPUs): the ranks share the host's cores and memory system,
+    # so the best number of batches in flight per rank falls as ranks are added (N=1: 0.68 / 0.90 / 0.87e9 with 2 / 3 / 4; N=2: 0.64 / 1.05 /
+    # 0.92e9 with 1 / 2 / 3; N=4: 1.01 / 0.84 / 0.62e9 with 1 / 2 / 3)
+    EB = min(B, args.e2e_batches if args.e2e_batches > 0 else (3 if world <= 1 else (2 if world == 2 else 1)))
     host_rings = [rings[b].cpu().numpy() for b in range(EB)]
     cells = envs[0].width * envs[0].height
 
@@ -693,7 +696,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of exactly --steps launches; the median is reported")
     ap.add_argument("--streams", type=int, default=4, help="streams the independent env batches are forked over inside the graph")
     ap.add_argument("--e2e-steps", type=int, default=384)
-    ap.add_argument("--e2e-batches", type=int, default=0, help="env batches in flight in the e2e loop (0 = 3 on one or two GPUs, 1 from four up)")
+    ap.add_argument("--e2e-batches", type=int, default=0, help="env batches in flight in the e2e loop (0 = 3 on one GPU, 2 on two, 1 from four up)")
     ap.add_argument("--e2e-repeats", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--python-seconds", type=float, default=3.0, help="seconds per leg of the Python-reference baseline (when a copy is on the box)")
