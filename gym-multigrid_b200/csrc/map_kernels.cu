@@ -1043,6 +1043,8 @@ cudaError_t configure_map_kernels(int L, int n, int cells, int obs_dtype, bool o
   if ((e = configure_pair<MG_FAMILY_CTF, 1, 1>(smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 10, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
+  if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 12, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 8, 1, 1, 1>, (size_t)smem)) != cudaSuccess) return e;
   if ((e = raise_smem_limit((const void*)map_kernel<MG_FAMILY_CTF, 1, 1, 3, 1>, (size_t)smem)) != cudaSuccess) return e;
@@ -1067,6 +1069,11 @@ static cudaError_t launch_by_size(const MapParams& p, cudaStream_t st) {
     if (map_lean_enabled() && p.op == 1 && p.obs && !p.final_obs && fits) {
       if constexpr (FAMILY == MG_FAMILY_CTF && STEPV == 1) {
         if (p.pol_on) return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN, 1>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN, 1>(p, st);
+      }
+      if constexpr (FAMILY == MG_FAMILY_CTF && STEPV == 1) {   // experiment switch: more resident CTAs at fewer registers
+        static const int minb = [] { const char* v = std::getenv("MG_MAP_MINB"); return v ? std::atoi(v) : 0; }();
+        if (minb == 10 && p.N >= from) return launch_one<FAMILY, MODE, 10, STEPV, LEAN>(p, st);
+        if (minb == 12 && p.N >= from) return launch_one<FAMILY, MODE, 12, STEPV, LEAN>(p, st);
       }
       return p.N >= from ? launch_one<FAMILY, MODE, 8, STEPV, LEAN>(p, st) : launch_one<FAMILY, MODE, 1, STEPV, LEAN>(p, st);
     }
