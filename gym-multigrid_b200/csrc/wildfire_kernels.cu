@@ -218,8 +218,56 @@ __global__ void __launch_bounds__(kWfThreads) wildfire_kernel(const __grid_const
 // step memory-bound instead of RNG-bound.  The agent order is drawn by warp 0 in parallel (lane d computes the Philox
 // block of draw d; the Fisher-Yates swaps are register shuffles), so the serial section per env is the ordered move loop
 // only.  Same Philox counters and word assignment as the generic kernel and the oracle: results are bit-identical.
+// all threads: tnew + agents -> the observation tile (type byte = state; colour green / red / grey), word-parallel
 template <int T, int VEC>
-__global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant__ WildfireParams p) {
+__device__ __forceinline__ void wf_encode_tile(const WildfireParams& p, const uint32_t* n32, uint8_t* s_obs, const int* s_ax, const int* s_ay,
+                                               const int* s_adir, int nwords, int tid) {
+  const int A = p.A, H = p.H;
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(s_obs);
+  for (int q = tid; q < nwords / VEC; q += T) {
+    uint32_t w[VEC], o[3 * VEC];
+    if (VEC == 4) {
+      const uint4 a = reinterpret_cast<const uint4*>(n32)[q];
+      w[0] = a.x; w[VEC > 1 ? 1 : 0] = a.y; w[VEC > 2 ? 2 : 0] = a.z; w[VEC > 3 ? 3 : 0] = a.w;
+    } else {
+      w[0] = n32[q];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const uint32_t burnt = (w[i] >> 1) & 0x01010101u, healthy = ~(w[i] | (w[i] >> 1)) & 0x01010101u;
+      interleave3(w[i], healthy * 3u + burnt * 7u, 0u, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    }
+    if (VEC == 4) {
+      uint4* d = reinterpret_cast<uint4*>(o32) + 3 * q;
+      d[0] = make_uint4(o[0], o[1], o[2], o[3 % (3 * VEC)]);
+      d[1] = make_uint4(o[4 % (3 * VEC)], o[5 % (3 * VEC)], o[6 % (3 * VEC)], o[7 % (3 * VEC)]);
+      d[2] = make_uint4(o[8 % (3 * VEC)], o[9 % (3 * VEC)], o[10 % (3 * VEC)], o[11 % (3 * VEC)]);
+    } else {
+      o32[3 * q] = o[0]; o32[3 * q + 1] = o[1]; o32[3 * q + 2] = o[2];
+    }
+  }
+  __syncthreads();
+  if (tid < A) {
+    uint8_t* o = s_obs + 3 * (s_ax[tid] * H + s_ay[tid]);
+    o[0] = 3; o[1] = p.agent_colour[tid]; o[2] = (uint8_t)s_adir[tid];
+  }
+}
+
+// the same, out of line: the terminal observation of an env that resets (rare) must not cost the hot path registers
+template <int T, int VEC>
+__device__ __noinline__ void wf_encode_tile_cold(const WildfireParams& p, const uint32_t* n32, uint8_t* s_obs, const int* s_ax, const int* s_ay,
+                                                 const int* s_adir, int nwords, int tid) {
+  wf_encode_tile<T, VEC>(p, n32, s_obs, s_ax, s_ay, s_adir, nwords, tid);
+}
+
+// Shared memory (4 bytes per cell): guard | told [cells] | guard | queue [2 * cells] | tnew [cells].  The observation tile
+// (3 bytes per cell) is assembled over told + guard + queue once pass 2 has consumed them: 66 KB instead of 82 KB for a 128x128
+// env, i.e. 3 CTAs per SM instead of 2 (956 -> 760 us per step of 32 768 envs).  Not capped at 40 registers for 12 CTAs of a 64x64
+// env per SM: measured, 798 against 793 us at 10 CTAs - the step is issue-bound there, not latency-bound - and 32x32 loses 4 %.
+// The bound below asks for 1 280 threads per SM = 10 CTAs of 128: 47 registers without spills (uncapped, the second inlined copy of
+// the encoder takes the allocation to 53-56 registers and 64x64 to 9 CTAs per SM: 827 us).
+template <int T, int VEC>
+__global__ void __launch_bounds__(T, 1280 / T) wildfire_fast_kernel(const __grid_constant__ WildfireParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int s_ax[MG_MAX_WILDFIRE_AGENTS], s_ay[MG_MAX_WILDFIRE_AGENTS], s_adir[MG_MAX_WILDFIRE_AGENTS];
@@ -228,8 +276,9 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
   const int rw = H >> 2, nwords = cells >> 2, guard = (H + 15) & ~15;
   const long long e = blockIdx.x;
   uint8_t* s_told = smem_raw + guard;                                      // guard | [cells] | guard
-  uint8_t* s_tnew = smem_raw + 2 * (size_t)guard + cells;                  // [cells]
-  uint8_t* s_obs = s_tnew + cells;                                         // [3 * cells]
+  uint8_t* s_queue = smem_raw + 2 * (size_t)guard + cells;                 // [2 * cells] fire-front queue of passes 1 / 2
+  uint8_t* s_tnew = s_queue + 2 * (size_t)cells;                           // [cells]
+  uint8_t* s_obs = s_told;                                                 // [3 * cells] over told | guard | queue, after pass 2
   uint32_t* t32 = reinterpret_cast<uint32_t*>(s_told);
   uint32_t* n32 = reinterpret_cast<uint32_t*>(s_tnew);
   uint8_t* g_terrain = p.terrain + e * cells;
@@ -329,7 +378,7 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
     //      pass 1: neighbour counts for every word; quiet words are copied, words on the fire front are queued
     //      (word index + packed state / neighbour-count bytes) in the not-yet-used obs area
     const uint32_t tick = (uint32_t)h.y;
-    uint2* s_list = reinterpret_cast<uint2*>(s_obs);
+    uint2* s_list = reinterpret_cast<uint2*>(s_queue);
     const int rv = rw / VEC;   // vectors per row (VEC == 4 only when H % 16 == 0)
     for (int q = tid; q < nwords / VEC; q += T) {
       const int j0 = q * VEC;
@@ -391,8 +440,8 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
     const bool term = !__syncthreads_or(any_burning), trunc = h.x >= p.max_steps;
     if (tid == 0) { p.terminated[e] = term; p.truncated[e] = trunc; }
     need_reset = p.autoreset && (term || trunc);
-    if (need_reset && p.final_obs) {
-      wf_encode(p, s_tnew, s_told, s_obs, s_ax, s_ay, s_adir, tid, T);
+    if (need_reset && p.final_obs) {   // (the queue is consumed: every thread has passed the barrier above)
+      wf_encode_tile_cold<T, VEC>(p, n32, s_obs, s_ax, s_ay, s_adir, nwords, tid);
       __syncthreads();
       uint4* dst = reinterpret_cast<uint4*>(p.final_obs + e * 3 * cells);
       for (int i = tid; i < 3 * cells / 16; i += T) dst[i] = reinterpret_cast<const uint4*>(s_obs)[i];
@@ -424,36 +473,7 @@ __global__ void __launch_bounds__(T) wildfire_fast_kernel(const __grid_constant_
   __syncthreads();
 
   // ---- 5. observation (type byte = state; colour green / red / grey) + write-back
-  if (p.obs) {
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(s_obs);
-    for (int q = tid; q < nwords / VEC; q += T) {
-      uint32_t w[VEC], o[3 * VEC];
-      if (VEC == 4) {
-        const uint4 a = reinterpret_cast<const uint4*>(n32)[q];
-        w[0] = a.x; w[VEC > 1 ? 1 : 0] = a.y; w[VEC > 2 ? 2 : 0] = a.z; w[VEC > 3 ? 3 : 0] = a.w;
-      } else {
-        w[0] = n32[q];
-      }
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const uint32_t burnt = (w[i] >> 1) & 0x01010101u, healthy = ~(w[i] | (w[i] >> 1)) & 0x01010101u;
-        interleave3(w[i], healthy * 3u + burnt * 7u, 0u, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
-      }
-      if (VEC == 4) {
-        uint4* d = reinterpret_cast<uint4*>(o32) + 3 * q;
-        d[0] = make_uint4(o[0], o[1], o[2], o[3 % (3 * VEC)]);
-        d[1] = make_uint4(o[4 % (3 * VEC)], o[5 % (3 * VEC)], o[6 % (3 * VEC)], o[7 % (3 * VEC)]);
-        d[2] = make_uint4(o[8 % (3 * VEC)], o[9 % (3 * VEC)], o[10 % (3 * VEC)], o[11 % (3 * VEC)]);
-      } else {
-        o32[3 * q] = o[0]; o32[3 * q + 1] = o[1]; o32[3 * q + 2] = o[2];
-      }
-    }
-    __syncthreads();
-    if (tid < A) {
-      uint8_t* o = s_obs + 3 * (s_ax[tid] * H + s_ay[tid]);
-      o[0] = 3; o[1] = p.agent_colour[tid]; o[2] = (uint8_t)s_adir[tid];
-    }
-  }
+  if (p.obs) wf_encode_tile<T, VEC>(p, n32, s_obs, s_ax, s_ay, s_adir, nwords, tid);
   fence_proxy_async_smem();
   __syncthreads();
   if (tid == 0) {
@@ -471,7 +491,7 @@ static bool wf_fast(int H) {
   static const bool off = [] { const char* v = std::getenv("MG_WF_GENERIC"); return v && v[0] == '1'; }();
   return !off && (H & 3) == 0;
 }
-static size_t wf_fast_smem(int cells, int H) { return (size_t)cells * 5 + 2 * (size_t)((H + 15) & ~15) + 16; }
+static size_t wf_fast_smem(int cells, int H) { return (size_t)cells * 4 + 2 * (size_t)((H + 15) & ~15) + 16; }
 
 size_t wildfire_smem_bytes(int cells, int H) { return wf_fast(H) ? wf_fast_smem(cells, H) : (size_t)cells * 5 + 64; }
 
