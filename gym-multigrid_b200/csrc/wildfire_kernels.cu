@@ -510,7 +510,9 @@ cudaError_t launch_wildfire(const WildfireParams& p, cudaStream_t st) {
   const bool fast = wf_fast(p.H);
   const bool vec = (p.H & 15) == 0;   // rows are whole 16-byte vectors
   const int items = p.cells / (vec ? 16 : 4);   // words / vectors one CTA sweeps
-  const int threads = fast ? (vec && items >= 1024 ? 256 : (items >= 256 ? 128 : 64)) : kWfThreads;
+  int threads = fast ? (vec && items >= 1024 ? 256 : (items >= 256 ? 128 : 64)) : kWfThreads;
+  static const int forced = [] { const char* v = std::getenv("MG_WF_THREADS"); return v ? std::atoi(v) : 0; }();   // experiment switch
+  if (fast && (forced == 64 || forced == 128 || (forced == 256 && vec))) threads = forced;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p.N); cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = wildfire_smem_bytes(p.cells, p.H); cfg.stream = st;
