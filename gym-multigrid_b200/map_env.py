@@ -418,6 +418,14 @@ class CtfVecEnv(_MapVecEnv):
         """Drive the red agents from outside (the reference's `enemy_policies`, ctf.py:666): `red_actions` int8 CUDA tensor
         [N, num_red] that every following `step` reads - overwrite it in place between steps (a learned opponent, self-play, a
         host-side A* policy).  None = back to the built-in RwPolicy drawn on the device."""
+        if self._device_policies or self._enemy_policies is not None:     # the caller takes the red team over: scripted opponents off
+            if self._device_policies:
+                self._check(self._lib.mg_set_red_policies(self._h, None))     # (switches the fusion off too)
+            self._device_policies = self._fused_policies = False
+            self._enemy_policies = None
+        return self._bind_red_actions(red_actions)
+
+    def _bind_red_actions(self, red_actions):
         if red_actions is None:
             self._red_actions = None
             self._check(self._lib.mg_set_red_actions(self._h, None))
@@ -461,7 +469,7 @@ class CtfVecEnv(_MapVecEnv):
             self._device_policies = self._fused_policies = False
         if all(p is None or type(p) is RwPolicy for p in pols):
             self._enemy_policies = None
-            self.set_red_actions(None)
+            self._bind_red_actions(None)
             return None
         if device:
             from .policy.ctf.device import build_tables
@@ -474,7 +482,7 @@ class CtfVecEnv(_MapVecEnv):
             rp.first_move, rp.patrol_goal, rp.on_border, rp.along_border = (a.ctypes.data for a in keep)
             self._check(self._lib.mg_set_red_policies(self._h, C.byref(rp)))      # copies the tables during the call
             self._enemy_policies, self._device_policies, self._policy_tables = None, True, t
-            self._red_buf = self.set_red_actions(torch.zeros((self.num_envs, nr), dtype=torch.int8, device=self.device))
+            self._red_buf = self._bind_red_actions(torch.zeros((self.num_envs, nr), dtype=torch.int8, device=self.device))
             if fused:
                 self._check(self._lib.mg_set_red_policy_fusion(self._h, _ptr(self._red_buf)))
                 self._fused_policies = True
@@ -490,7 +498,7 @@ class CtfVecEnv(_MapVecEnv):
                 p.action_set = CtfActions
         self._enemy_policies = pols
         self._red_host = np.zeros((self.num_envs, nr), np.int8)
-        self._red_buf = self.set_red_actions(self._red_host)
+        self._red_buf = self._bind_red_actions(self._red_host)
         return pols
 
     def set_policy_trace(self, patrol_target=None, follow=None, action=None):

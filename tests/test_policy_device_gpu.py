@@ -91,6 +91,29 @@ def test_fused_policy_step_equals_two_launches_at_full_size(cuda_device):
     assert torch.equal(envs[0].state, envs[1].state) and envs[0].status() == 0
 
 
+def test_set_red_actions_takes_the_red_team_over_from_device_policies(cuda_device):
+    """`set_red_actions(buffer)` after `set_enemy_policies(device=True)`: the caller's buffer drives the red team (fused or not)."""
+    import gym_multigrid_b200 as mg
+    g = load_golden("ctf_2v2")
+    fm = g["field_map"].astype(np.float64)
+    n, seed = 513, 12
+    for fused in (True, False):
+        env = mg.make_ctf_vec(n, g["field_map"], max_steps=15, seed=seed)
+        o = oc.CtfOracle(g["field_map"], n, 2, 2, max_steps=15)
+        env.set_enemy_policies(_policies(("FightPolicy", "CapturePolicy"), fm, (1.0, 1.0)), device=True, fused=fused)
+        red = env.set_red_actions(torch.zeros((n, 2), dtype=torch.int8, device=cuda_device))
+        assert not env._device_policies and not env._fused_policies
+        assert np.array_equal(_np(env.reset()[0]), o.reset(oc.map_rng(mode=1, seed=seed)))
+        rng = np.random.default_rng(3)
+        for t in range(20):
+            act, ra = rng.integers(0, 5, size=(n, 2)).astype(np.int8), rng.integers(0, 5, size=(n, 2)).astype(np.int8)
+            red.copy_(torch.as_tensor(ra))
+            obs, rew, term, trunc, _ = env.step(torch.as_tensor(act, device=cuda_device))
+            oo, orew, oterm, otrunc = o.step(act, oc.map_rng(mode=1, seed=seed, red_actions=ra), autoreset=True)
+            assert np.array_equal(_np(obs), oo) and np.array_equal(_np(rew), orew), f"step {t}"
+        env.close()
+
+
 def test_device_decisions_are_the_host_policies_decisions(cuda_device):
     """randomness = 1: `choice([True, False], p=[1, 0])` always follows the route, so a decision without a patrol draw is a pure
     function of the state - the device must return what the (reference-pinned) host policy returns."""
