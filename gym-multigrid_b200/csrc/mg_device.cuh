@@ -237,6 +237,20 @@ __device__ __forceinline__ void interleave3(uint32_t t, uint32_t c, uint32_t s, 
   o2 = __byte_perm(st, c, 0x3710);                 // s2 t3 c3 s3
 }
 
+// the same with an all-zero state plane, three PRMTs instead of six: a selector nibble with bit 3 set replicates the SIGN of the
+// byte it names, and every type / colour byte is < 128, so such a nibble yields 0x00 (PTX prmt, default mode; the __byte_perm
+// intrinsic masks that bit away, hence the asm)
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void interleave3_zero_state(uint32_t t, uint32_t c, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+  o0 = prmt_raw(t, c, 0x1840u);   // t0 c0 0  t1
+  o1 = prmt_raw(t, c, 0x6285u);   // c1 0  t2 c2
+  o2 = prmt_raw(t, c, 0x8738u);   // 0  t3 c3 0
+}
+
 template <bool MARK = true>
 __device__ __forceinline__ void expand16(const uint4 in, uint4& a, uint4& b, uint4& c) {
   uint32_t o[12];

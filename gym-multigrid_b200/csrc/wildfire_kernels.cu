@@ -235,7 +235,7 @@ __device__ __forceinline__ void wf_encode_tile(const WildfireParams& p, const ui
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const uint32_t burnt = (w[i] >> 1) & 0x01010101u, healthy = ~(w[i] | (w[i] >> 1)) & 0x01010101u;
-      interleave3(w[i], healthy * 3u + burnt * 7u, 0u, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      interleave3_zero_state(w[i], healthy * 3u + burnt * 7u, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
     }
     if (VEC == 4) {
       uint4* d = reinterpret_cast<uint4*>(o32) + 3 * q;
@@ -346,9 +346,16 @@ __global__ void __launch_bounds__(T, 1280 / T) wildfire_fast_kernel(const __grid
       // (every lane executes every warp collective: no short-circuit in front of a *_sync call)
       const unsigned same_tgt = __match_any_sync(0xffffffffu, tgt);             // same target, or the target of a stayer
       bool conflict = __popc(same_tgt) > 1;
-      for (int d = 0; d < A; ++d) {
-        const uint32_t cd = __shfl_sync(0xffffffffu, cur, d);                   // someone stands there now
-        conflict |= (cd == tgt) & (d != lane);
+      {  // "someone stands on my target now": one bit per cell in the (not yet used) queue area instead of A shuffles - every lane
+         // clears the words it will touch, the agents mark their cells, and a mover's own cell is never its target
+        uint32_t* bm = reinterpret_cast<uint32_t*>(s_queue);
+        const int cc = lane < A ? x * H + y : 0, ct = wants ? nx * H + ny : cc;
+        bm[cc >> 5] = 0u; bm[ct >> 5] = 0u;
+        __syncwarp();
+        if (lane < A) atomicOr(&bm[cc >> 5], 1u << (cc & 31));
+        __syncwarp();
+        conflict |= ((bm[ct >> 5] >> (ct & 31)) & 1u) != 0;
+        __syncwarp();
       }
       conflict &= wants;
       uint32_t fin = (wants && !conflict) ? tgt : cur;   // position after this agent's own turn
