@@ -43,19 +43,18 @@ __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, i
   for (int b = 0; b < V; ++b) {
     const uint32_t rowv = ((mB >> b) & 1u) ? mA : 0u;
     uint32_t o = 0;
+    if (COLLECT) {
 #pragma unroll
-    for (int a = 0; a < V; ++a) {
-      uint32_t c = src[a * sa + b * sb];
-      if (COLLECT) {
+      for (int a = 0; a < V; ++a) {
+        uint32_t c = src[a * sa + b * sb];
         c = ((rowv >> a) & 1u) ? c : oob_code;
         o |= (uint32_t)((c & 3u) == (uint32_t)T_WALL) << a;     // see_behind() is False only for Wall (object.py:174-179)
-      } else {
-        if (a == HS && b == V - 1) c = agent_cell;  // the agent stands at view cell (V/2, V-1)
+        pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
       }
-      pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
     }
     // Maze: only the out-of-map filler blocks sight, and which view cells lie outside the map is geometry - the complement of the
-    // range masks - not something to find by comparing 49 cell values with the filler code
+    // range masks - not something to find by comparing 49 cell values with the filler code; the cells are gathered AFTER the
+    // visibility sweep below, and only the visible ones
     opq[b] = COLLECT ? o : (~rowv & FULL);
     msk[b] = 0;
   }
@@ -89,11 +88,23 @@ __device__ __forceinline__ void view_compute_store(const uint8_t* src, int sa, i
     }
   }
   // encode_for_agents: cells outside the mask stay (0, 0, 0)
+  if (COLLECT) {
 #pragma unroll
-  for (int a = 0; a < V; ++a)
+    for (int a = 0; a < V; ++a)
+#pragma unroll
+      for (int b = 0; b < V; ++b)
+        if (!((msk[b] >> a) & 1u)) pk[(a * V + b) / 4] &= ~(0xFFu << (8 * ((a * V + b) % 4)));
+  } else {   // Maze: the mask is known before a single cell has been read - load the visible cells, leave the others zero
 #pragma unroll
     for (int b = 0; b < V; ++b)
-      if (!((msk[b] >> a) & 1u)) pk[(a * V + b) / 4] &= ~(0xFFu << (8 * ((a * V + b) % 4)));
+#pragma unroll
+      for (int a = 0; a < V; ++a) {
+        uint32_t c = 0;
+        if ((msk[b] >> a) & 1u) c = src[a * sa + b * sb];
+        if (a == HS && b == V - 1) c = agent_cell;  // the agent stands at view cell (V/2, V-1), always visible (the sweep starts there)
+        pk[(a * V + b) / 4] |= c << (8 * ((a * V + b) % 4));
+      }
+  }
   uint32_t w[NW + 2];
 #pragma unroll
   for (int k = 0; k < NPK; ++k) {
