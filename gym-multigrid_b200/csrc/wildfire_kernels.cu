@@ -300,6 +300,26 @@ __global__ void __launch_bounds__(T, 1280 / T) wildfire_fast_kernel(const __grid
   const bool do_reset = p.op == 0 && (!p.reset_mask || p.reset_mask[e]);
   bool need_reset = do_reset;
   uint32_t order_blocks = 0;                // Philox blocks the agent order consumed
+  // Warp 0's share of the step that needs no terrain runs UNDER the terrain load: the agents' actions (a global load) and the
+  // step's agent order (a Philox block and A - 1 dependent shuffles) - the other warps wait for warp 0's agent phase at a barrier,
+  // so every cycle taken off it is taken off the whole CTA (A/B in one run: 64x64 772.4 against 774.3 us, 128x128 657 against 667).
+  int act_pre = 0, rank_pre = lane;
+  if (p.op == 1 && warp == 0) {
+    act_pre = lane < A ? p.actions[e * A + lane] : 0;
+    if (!p.order && A > 1) {
+      // rank = this agent's position in the step's order.  Fisher-Yates: draw d (for i = A-1-d) is word d % 4 of Philox
+      // block ctr0 + d / 4; instead of permuting an array serially every lane tracks ITS OWN element through the swaps
+      // (p == i -> j, p == j -> i): the draws are broadcast by independent shuffles, no lane waits for another.
+      uint32_t u[4];
+      philox4x32_10(id0, id1, ctr0 + (uint32_t)(lane >> 2), 0u, k0, k1, u);
+      const uint32_t word = (lane & 2) ? ((lane & 1) ? u[3] : u[2]) : ((lane & 1) ? u[1] : u[0]);
+      const int jl = (int)__umulhi(word, (uint32_t)(A - lane));   // below(i + 1), i = A - 1 - lane
+      for (int d = 0; d < A - 1; ++d) {
+        const int i = A - 1 - d, j = __shfl_sync(0xffffffffu, jl, d);
+        rank_pre = rank_pre == i ? j : (rank_pre == j ? i : rank_pre);
+      }
+    }
+  }
   mbar_wait(&bar, 0);
   __syncthreads();
 
@@ -308,10 +328,7 @@ __global__ void __launch_bounds__(T, 1280 / T) wildfire_fast_kernel(const __grid
     // ---- 1/2. ordered agent moves: warp 0, lane = agent
     order_blocks = (!p.order && A > 1) ? (uint32_t)(A - 1 + 3) / 4u : 0u;
     if (warp == 0) {
-      // rank = this agent's position in the step's order.  Fisher-Yates: draw d (for i = A-1-d) is word d % 4 of Philox
-      // block ctr0 + d / 4; instead of permuting an array serially every lane tracks ITS OWN element through the swaps
-      // (p == i -> j, p == j -> i): the draws are broadcast by independent shuffles, no lane waits for another.
-      int rank = lane;
+      int rank = rank_pre;   // (computed above, under the terrain load; a replayed order is read here)
       if (p.order) {
         int* s_rank = s_adir;                // scratch: s_adir is read into `dir` first
         const int d0 = lane < A ? s_adir[lane] : 0;
@@ -322,19 +339,10 @@ __global__ void __launch_bounds__(T, 1280 / T) wildfire_fast_kernel(const __grid
         __syncwarp();
         if (lane < A) s_adir[lane] = d0;
         __syncwarp();
-      } else if (A > 1) {
-        uint32_t u[4];
-        philox4x32_10(id0, id1, ctr0 + (uint32_t)(lane >> 2), 0u, k0, k1, u);
-        const uint32_t word = (lane & 2) ? ((lane & 1) ? u[3] : u[2]) : ((lane & 1) ? u[1] : u[0]);
-        const int jl = (int)__umulhi(word, (uint32_t)(A - lane));   // below(i + 1), i = A - 1 - lane
-        for (int d = 0; d < A - 1; ++d) {
-          const int i = A - 1 - d, j = __shfl_sync(0xffffffffu, jl, d);
-          rank = rank == i ? j : (rank == j ? i : rank);
-        }
       }
       // an agent acts once per step, so its target cell is known up front; positions travel packed as x | y << 8.
       // `tgt` = the cell the agent will stand on if nothing blocks it (its own cell when it stays).
-      const int a = lane < A ? p.actions[e * A + lane] : 0;
+      const int a = act_pre;
       int x = lane < A ? s_ax[lane] : 0, y = lane < A ? s_ay[lane] : 0, dir = lane < A ? s_adir[lane] : 0;
       const int dx = (a == 4) - (a == 2), dy = (a == 3) - (a == 1);
       const int nx = x + dx, ny = y + dy;
