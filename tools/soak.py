@@ -210,6 +210,37 @@ def soak_maze(rng, stats):
     stats["maze_configs"] += 1; stats["maze_env_steps"] += n * steps; stats["bytes_compared"] += b
 
 
+def soak_wildfire(rng, stats):
+    """The Wildfire extension against the in-repo oracle of its specification (no reference code exists: parity unpinned)."""
+    W = int(rng.choice([4, 8, 12, 16, 20, 24, 32, 40, 64, 96]))
+    H = W if rng.integers(0, 3) else int(rng.choice([4, 6, 8, 10, 12, 16, 20, 32]))
+    if (W * H) % 16:
+        return
+    A = int(rng.integers(1, min(32, W * H // 2) + 1))
+    fires = int(rng.integers(1, min(8, W * H - A) + 1))
+    n, seed, base, ms = int(rng.integers(1, 200)), int(rng.integers(0, 1 << 30)), int(rng.integers(0, 1000)), int(rng.integers(5, 50))
+    kw = dict(num_agents=A, num_fires=fires, alpha=float(rng.choice([0.05, 0.2, 0.5])), beta=float(rng.choice([0.02, 0.08, 0.3])),
+              max_steps=ms, seed=seed, env_id_base=base)
+    kw.update(dict(size=W) if W == H else dict(width=W, height=H))
+    cfg = dict(family="wildfire", W=W, H=H, A=A, fires=fires, n=n, **{k: kw[k] for k in ("alpha", "beta", "max_steps", "seed")})
+    env = mg.make_wildfire_vec(n, **kw)
+    env.enable_final_observation()
+    o = oc.WildfireOracle(n, **kw)
+    b = same(_np(env.reset()[0]), o.reset(), "wildfire reset", cfg)
+    steps = int(rng.integers(10, 70))
+    for t in range(steps):
+        act = rng.integers(0, 5, size=(n, A)).astype(np.int8)
+        obs, rew, term, trunc, info = env.step(torch.as_tensor(act, device=DEV))
+        oo, orew, oterm, otrunc, ofin = o.step(act, autoreset=True, want_final_obs=True)
+        b += same(_np(obs), oo, f"wildfire obs step {t}", cfg) + same(_np(rew), orew, "wildfire rewards", cfg)
+        b += same(_np(term), oterm, "wildfire terminated", cfg) + same(_np(trunc), otrunc, "wildfire truncated", cfg)
+        d = oterm | otrunc
+        b += same(_np(info["final_observation"])[d], ofin[d], "wildfire final observation", cfg)
+    b += same(_np(env.terrain), o.terrain, "wildfire terrain", cfg) + same(_np(env.agents), o.agents, "wildfire agents", cfg)
+    env.close()
+    stats["wildfire_configs"] += 1; stats["wildfire_env_steps"] += n * steps; stats["bytes_compared"] += b
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120.0)
@@ -222,10 +253,10 @@ def main():
               "bytes_compared", "ctf_device_policy_configs", "collect_rollout_steps"):
         stats[k] = 0
     t0 = time.time()
-    fams = [soak_collect, soak_ctf, soak_maze]
+    fams = [soak_collect, soak_ctf, soak_maze, soak_wildfire]
     i = 0
     while time.time() - t0 < args.seconds:
-        fams[i % 3](rng, stats)
+        fams[i % len(fams)](rng, stats)
         i += 1
     stats.update(seconds=round(time.time() - t0, 1), seed=args.seed, mismatches=0,
                  gpu=torch.cuda.get_device_name(0), what="CUDA (C ABI) vs CPU oracle, bit-exact, random configurations")
