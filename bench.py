@@ -281,12 +281,19 @@ def run_ours(args):
             start, count = start + c, count - c
         return out
 
+    # Every timed region starts behind an UNTIMED fill of a 160 MB scratch buffer on the same stream (the do_bench pattern): it writes
+    # more than the 126 MB L2 holds, so no region starts with a warm cache, and the host enqueues the region's graphs while the fill
+    # runs, so the device-side interval ev0 -> ev1 holds the K launches and not the host's graph-launch latency (with the driver's
+    # --steps 20 a region is ~140 us: that latency was ~5 % of it; with the default K it is noise).
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
+
     def timed_region(main, graphs):
         barrier()
         with torch.cuda.stream(main):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             sampler.sample()
             sampler.active = True
+            flush.zero_()
             ev0.record(main)
             for g in graphs:
                 g.replay()
@@ -534,7 +541,9 @@ def run_ours(args):
             "config": workload_config(args),
             "repeats": R, "repeat_ms": all_ms, "pickups_per_env_step": pickups,
             "launch": f"CUDA graphs of up to {CHUNK} launches of the fused step+encode kernel (one launch = one env batch of {n} envs), "
-                      f"the {B} independent batches forked over {S} streams; value = median of {R} timed regions of exactly {K} launches",
+                      f"the {B} independent batches forked over {S} streams; value = median of {R} timed regions of exactly {K} launches, each timed "
+                      "with CUDA events on the launching stream right behind an untimed 160 MB fill (L2 flushed; the host's graph-launch "
+                      "latency stays outside the device-timed interval)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "collect_rollout_kernel (warp-tile kernel, T = 1: mg_step)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
